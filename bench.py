@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Benchmark of the gate-application hot path (BASELINE.json metric: gate-apps/s and achieved HBM
+GB/s on the n-qubit random circuit).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--qubits n] [--depth d] [--impl reference]
+
+A step = one pass of the whole random circuit (H/RZ/CNOT/CPHASE, generator of SURVEY.md 8d, seed
+1234) over a |0...0> state that is already resident in HBM: reset, queue every gate, fuse, launch,
+sync.  `value` is device-timed (CUDA events on the library's stream, max over ranks); `e2e` is the
+same metric through the public API (QVMConnection.run_and_measure: host Program in, host bit lists
+out, all host<->device traffic inside the timed region).
+
+Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+for _p in (REPO, os.path.join(REPO, "reference-qvm_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+SEED = 1234
+METRIC = "gate-apps/s"
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.device_index = device_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device_index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons = [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    out["sm_max_mhz"] = float(f[2])
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+def circuit(n, depth):
+    from oracle.qvm_oracle import random_circuit_spec      # generator only (no arithmetic)
+    return random_circuit_spec(n, depth, SEED)
+
+
+def build_program(spec):
+    from pyquil.quil import Program
+    from pyquil.quilbase import Gate
+    prog = Program()
+    for name, params, qubits in spec:
+        prog.inst(Gate(name, params, qubits))
+    return prog
+
+
+def cpu_reference_sample(n, depth, repeats=1):
+    """Time the oracle's restatement of the reference's own algorithm (sparse lifted operators,
+    swap chains: oracle.qvm_oracle.ref_*) on a bounded sample of the workload.  Single thread --
+    scipy.sparse products are serial, as in the reference."""
+    from oracle import qvm_oracle as orc
+    from referenceqvm import gates as G
+    spec = circuit(n, depth)
+    ops = []
+    for name, params, qubits in spec:
+        m = G.gate_matrix[name]
+        ops.append(("gate", np.asarray(m(*params) if params else m), qubits))
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        orc.ref_run_wavefunction(ops, n)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return len(ops) / best, best, len(ops)
+
+
+def run_reference_arm(args, rank):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is pure
+    Python + un-vendored pyquil and /root/reference does not exist on the GPU box)."""
+    if rank != 0:
+        return
+    n, depth = args.ref_qubits, args.ref_depth
+    for _ in range(args.warmup):
+        cpu_reference_sample(n, depth)
+    times = []
+    gates = 0
+    for _ in range(args.steps):
+        _, dt, gates = cpu_reference_sample(n, depth)
+        times.append(dt)
+    total = sum(times)
+    value = gates * len(times) / total
+    sample = "n=%d depth=%d random circuit (seed %d, %d gates): same generator as the GPU arm" % (n, depth, SEED, gates)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "reference_sample": sample},
+        "cpu_baseline": {"value": value, "unit": METRIC, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_name(args):
+    return "%d-qubit random circuit depth %d (H/RZ/CNOT/CPHASE, seed %d), complex128 state %.1f GiB" % (
+        args.qubits, args.depth, SEED, 16.0 * 2 ** args.qubits / 2 ** 30)
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--qubits", type=int, default=int(os.environ.get("QVM_BENCH_QUBITS", "33")))
+    ap.add_argument("--depth", type=int, default=int(os.environ.get("QVM_BENCH_DEPTH", "40")))
+    ap.add_argument("--shots", type=int, default=1000000)
+    ap.add_argument("--ref-qubits", type=int, default=12)
+    ap.add_argument("--ref-depth", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun (one rank per GPU)" % args.gpus)
+    if world > 1:
+        raise SystemExit("sharded bench not wired yet")
+
+    import torch
+    from referenceqvm import _engine, _native
+    from referenceqvm.api import QVMConnection
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    os.environ["QVM_B200_DEVICE"] = str(local_rank)
+
+    n, depth = args.qubits, args.depth
+    spec = circuit(n, depth)
+    prog = build_program(spec)
+    n_gates = len(spec)
+
+    qvm = QVMConnection()
+    qvm.device = local_rank
+    qvm.load_program(prog)
+    eng = qvm._fresh_engine()
+    from referenceqvm.unitary_generator import resolve_gate
+    ops = [_engine.compile_gate(*resolve_gate(qvm.gate_set, {}, ins)) for ins in prog]
+    stream = torch.cuda.ExternalStream(eng.state.stream_ptr(), device=local_rank)
+
+    def step():
+        eng.reset()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for op in ops:
+            eng.queue(op)
+        eng.flush()
+        e1.record(stream)
+        return e0, e1
+
+    for _ in range(args.warmup):
+        step()
+    eng.sync()
+    torch.cuda.synchronize()
+
+    eng.state.stats_reset()
+    groups_before = eng.groups_launched
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_begin = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_begin.record(stream)
+    pairs = [step() for _ in range(args.steps)]
+    t_end.record(stream)
+    eng.sync()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    total_ms = t_begin.elapsed_time(t_end)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in pairs)
+    stats = eng.state.stats()
+    groups = eng.groups_launched - groups_before
+    ms_per_step = total_ms / args.steps
+    value = n_gates * args.steps / (total_ms * 1e-3)
+
+    peak, peak_src = measured_peaks()
+    bytes_per_launch = 32.0 * 2 ** n
+    avg_launch_ms = kernel_ms / max(groups, 1)
+    achieved = bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_launch_ms,
+                "launches_per_step": groups / float(args.steps),
+                "effective_gbs": n_gates * args.steps * bytes_per_launch / (total_ms * 1e-3) / 1e9}
+
+    # ---- e2e: the call a user makes -----------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        qubits = list(range(n))
+        eng.state.stats_reset()
+        qvm.run_and_measure(prog, qubits, trials=args.shots)          # warm (allocations, caches)
+        torch.cuda.synchronize()
+        eng2 = qvm._engine
+        eng2.state.stats_reset()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            res = qvm.run_and_measure(prog, qubits, trials=args.shots)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert len(res) == args.shots and len(res[0]) == n
+        s2 = eng2.state.stats()
+        e2e = {"value": n_gates * e2e_steps / dt, "unit": METRIC,
+               "h2d_bytes_per_step": s2["h2d_bytes"] / e2e_steps, "d2h_bytes_per_step": s2["d2h_bytes"] / e2e_steps,
+               "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
+               "call": "QVMConnection().run_and_measure(program, qubits=all, trials=%d)" % args.shots}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, dt, g = cpu_reference_sample(args.ref_qubits, args.ref_depth)
+        cpu = {"value": v, "unit": METRIC, "cores": 1, "kind": "port",
+               "sample": "n=%d depth=%d random circuit (seed %d, %d gates, %.1f s): oracle restatement of the "
+                         "reference's sparse lifted-operator algorithm; host has %d cores, the algorithm uses 1"
+                         % (args.ref_qubits, args.ref_depth, SEED, g, dt, os.cpu_count())}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "qubits": n, "depth": depth, "gates_per_step": n_gates,
+                   "l2_policy": "state (%.1f GiB) is far larger than the 126 MB L2" % (16.0 * 2 ** n / 2 ** 30),
+                   "tile_bits": eng.tile_bits, "low_bits": eng.low_bits},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": stats["kernel_launches"], "clocks": clocks,
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,155 @@
+/*
+ * qvm_b200.h -- C ABI of libqvm_b200.so, the B200 (sm_100a) gate-application engine that sits
+ * behind referenceqvm.api.QVMConnection.
+ *
+ * The reference (rigetti/reference-qvm) is pure Python and has no FFI; each entry point below
+ * names the reference code whose work it takes over (paths relative to the reference root).
+ * Plain pointers and sizes only -- no torch / numpy types cross this boundary.  The Python host
+ * (reference-qvm_b200/referenceqvm/_native.py) binds it with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - A handle owns one shard of a state vector: 2^n_local complex128 amplitudes resident in HBM,
+ *     interleaved (re, im).  Amplitude index is little-endian: bit q of the index is qubit q
+ *     (reference docs/source/walkthrough.rst:8-44).
+ *   - "Physical position" p < n_local is bit p of the local index; n_local <= p < n_local+n_global
+ *     is bit (p - n_local) of the shard index (multi-GPU: the top qubits select the GPU).
+ *     Diagonal factors and controls may sit on any position; dense targets must be local.
+ *   - k-qubit matrices are row-major 2^k x 2^k, interleaved (re, im); gate-local index bit
+ *     (k-1-j) belongs to qubits[j] -- the first argument is the most significant bit, exactly the
+ *     reference's apply_gate convention (referenceqvm/unitary_generator.py:266-323, pinned by
+ *     referenceqvm/tests/test_unitary_generator.py:57-65).
+ *   - Every function returns 0 (QVM_OK) or a negative code; qvm_last_error() gives the message
+ *     (thread-local).  CUDA failures are sticky on the handle.  There is no CPU fallback.
+ *   - One handle = one stream of work; calls on one handle must not overlap.  Host buffers are
+ *     caller-owned and fully consumed/filled when the call returns.
+ */
+#ifndef QVM_B200_H
+#define QVM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qvm_state qvm_t;
+
+#define QVM_OK               0
+#define QVM_ERR_INVALID     -1   /* bad argument (maps to ValueError / TypeError on the host)  */
+#define QVM_ERR_CUDA        -2   /* CUDA runtime failure (sticky)                               */
+#define QVM_ERR_NOMEM       -3   /* device or host allocation failed                            */
+#define QVM_ERR_UNSUPPORTED -4   /* valid request outside what the kernels implement            */
+
+#define QVM_OP_NOP   0           /* identity (classified away)                                  */
+#define QVM_OP_DENSE 1           /* dense 2^k x 2^k block on k local targets, optional controls */
+#define QVM_OP_DIAG  2           /* 2^k diagonal entries (k may be 0: a scalar), controls       */
+
+#define QVM_MAX_TARGETS   6      /* dense / diagonal target qubits per op                        */
+#define QVM_MAX_TILE_BITS 13     /* 2^13 amplitudes = 128 KiB of the 227 KiB shared memory / SM   */
+
+/* One classified gate.  Produced by qvm_classify(), consumed by qvm_apply_group(). */
+typedef struct qvm_op {
+    int32_t  kind;                        /* QVM_OP_*                                            */
+    int32_t  k;                           /* number of targets                                   */
+    int32_t  targets[QVM_MAX_TARGETS];    /* physical positions, targets[0] = MSB of the block   */
+    uint64_t ctrl_mask;                   /* physical positions that must be 1 for the op to act */
+    uint32_t mat_offset;                  /* offset into the matrix pool, in complex entries     */
+    uint32_t mat_entries;                 /* 4^k (dense) or 2^k (diag) complex entries           */
+} qvm_op_t;
+
+typedef struct qvm_stats {
+    uint64_t kernel_launches;             /* launches of this library's kernels                  */
+    uint64_t gate_ops;                    /* classified ops executed (NOPs excluded)             */
+    uint64_t hbm_passes;                  /* full read+write sweeps of the shard                 */
+    uint64_t hbm_bytes;                   /* algorithmic bytes moved by those kernels            */
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+} qvm_stats_t;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+const char* qvm_version(void);
+const char* qvm_last_error(void);
+int qvm_device_count(int* count);
+
+/* Allocate a shard of 2^n_local amplitudes on `device` (replaces the numpy allocation at
+ * referenceqvm/qvm_wavefunction.py:354 and the csc_matrix at qvm_density.py:390-391). */
+int qvm_create(int n_local, int device, qvm_t** out);
+/* Same, but adopt caller-owned device memory (e.g. a torch CUDA tensor) of 16 * 2^n_local bytes. */
+int qvm_create_external(int n_local, int device, void* device_ptr, qvm_t** out);
+int qvm_destroy(qvm_t* q);
+/* Multi-GPU: this handle is shard `shard_index` of 2^n_global (positions >= n_local). */
+int qvm_set_shard(qvm_t* q, int n_global, uint64_t shard_index);
+/* Run on a caller-owned cudaStream_t (0 restores the handle's own stream). */
+int qvm_set_stream(qvm_t* q, void* cuda_stream);
+int qvm_set_tile_bits(qvm_t* q, int tile_bits, int low_bits);   /* tuning: defaults 12 / 5      */
+int qvm_n_local(const qvm_t* q);
+void* qvm_device_ptr(qvm_t* q);         /* raw amplitudes, for NCCL/P2P plumbing on the host     */
+void* qvm_stream(qvm_t* q);
+int qvm_sync(qvm_t* q);
+int qvm_stats(const qvm_t* q, qvm_stats_t* out);
+int qvm_stats_reset(qvm_t* q);
+
+/* ---- state I/O (wavefunction() / density() readback: qvm_wavefunction.py:361-367) ------------ */
+int qvm_reset_zero(qvm_t* q, int set_amp0);     /* all zeros; amp[0] = 1 if set_amp0 (:354-355)   */
+int qvm_set_state(qvm_t* q, uint64_t offset, uint64_t count, const double* re_im);
+int qvm_get_state(qvm_t* q, uint64_t offset, uint64_t count, double* re_im);
+/* Strided gather of `count` amplitudes: element j is amp[offset + j*stride] (diag of rho). */
+int qvm_get_strided(qvm_t* q, uint64_t offset, uint64_t stride, uint64_t count, double* re_im);
+int qvm_copy_state(qvm_t* dst, qvm_t* src);
+int qvm_norm2(qvm_t* q, double* out);           /* sum |amp|^2 over the shard                    */
+
+/* ---- gate application ------------------------------------------------------------------------- */
+/* Classify a k-qubit matrix on `qubits` into one canonical op: exact-zero off-diagonals make it
+ * DIAG, identity blocks make controls (CNOT -> control + X, CPHASE -> two controls + scalar).
+ * Writes the reduced matrix/diagonal to `mat_out` (capacity 4^k complex) and its size to
+ * op->mat_entries; op->mat_offset is left 0.  Takes over the name -> operator step of
+ * tensor_gates / apply_gate (unitary_generator.py:326-363, :266-323).  Validation mirrors
+ * apply_gate: non power-of-two / non-square / k<1 -> QVM_ERR_INVALID. */
+int qvm_classify(int k, const int32_t* qubits, const double* matrix, qvm_op_t* op, double* mat_out);
+
+/* psi <- lifted(G) psi for one gate: the kernel-side replacement of
+ * `unitary = tensor_gates(...); self.wf = unitary.dot(self.wf)` (qvm_wavefunction.py:158-162).
+ * Qubit indices are physical positions; out of range / duplicates -> QVM_ERR_INVALID
+ * (reference: ValueError at unitary_generator.py:200-203). */
+int qvm_apply(qvm_t* q, int k, const int32_t* qubits, const double* matrix);
+
+/* Apply `n_ops` classified ops, in order, in ONE pass over HBM: each CTA stages the 2^n_tile
+ * amplitudes addressed by `tile_bits` (sorted physical positions, must contain every dense target
+ * of every op) in shared memory, runs all ops on them and writes them back.  `mats` is the
+ * matrix pool the ops' mat_offset index (complex entries, interleaved re/im). */
+int qvm_apply_group(qvm_t* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops,
+                    const double* mats, uint64_t mats_entries);
+
+/* rho[i,j] *= f^popcount((i xor j) & mask) on a 2n-qubit vectorised rho (n = n_total/2): the fused
+ * form of `dephasing` Kraus pairs on every qubit in `mask` (qvm_density.py:298-313, :350-361). */
+int qvm_dephase_all(qvm_t* q, int n_rho_qubits, uint64_t qubit_mask, double factor);
+
+/* ---- MEASURE (qvm_wavefunction.py:96-129, :147-156; qvm_density.py:120-143, :150-156) --------- */
+/* One cooperative kernel: p0 = sum_{bit=0} |amp|^2 (warp-shuffle + block reduce), outcome 0 iff
+ * r < p0, zero the other half and scale by 1/sqrt(p_outcome).  Single-shard handles only. */
+int qvm_measure(qvm_t* q, int qubit, double r, int* outcome, double* p0);
+/* The two halves of the above for sharded states (host all-reduces p0 in between). */
+int qvm_prob_zero(qvm_t* q, int qubit, double* p0_partial);
+int qvm_collapse(qvm_t* q, int qubit, int outcome, double scale);
+/* Density flavour on a vectorised rho of n_rho_qubits: p0 = tr(P0 rho) over the local rows. */
+int qvm_density_prob_zero(qvm_t* q, int n_rho_qubits, int qubit, double* p0_partial);
+
+/* ---- sampling (qvm_density.py:442-452; statistical meaning of qvm_wavefunction.py:266-321) ----- */
+/* Build the two-level CDF of |amp|^2 (mode 0) or of diag(rho) (mode 1, n_rho_qubits = n). */
+int qvm_probs_prepare(qvm_t* q, int mode, int n_rho_qubits, double* total);
+/* Inverse-CDF draws: index = first i with cdf[i] > uniforms[s] * total (numpy's searchsorted
+ * 'right' on the normalised cdf).  Indices are local to the shard. */
+int qvm_sample(qvm_t* q, uint64_t n_shots, const double* uniforms, uint64_t* out_index);
+
+/* ---- shard exchange plumbing (global<->local qubit remap) --------------------------------------- */
+/* Gather / scatter elements [elem_offset, elem_offset+count) of the half-shard whose local bit
+ * `local_bit` equals `bit_value`, to / from a contiguous device buffer. */
+int qvm_pack_half(qvm_t* q, int local_bit, int bit_value, uint64_t elem_offset, uint64_t count,
+                  void* device_dst);
+int qvm_unpack_half(qvm_t* q, int local_bit, int bit_value, uint64_t elem_offset, uint64_t count,
+                    const void* device_src);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QVM_B200_H */

@@ -1,0 +1,864 @@
+// C-ABI entry points of libqvm_b200.so (see include/qvm_b200.h for the contract and the reference
+// code each call replaces).  Host logic here is deliberately thin: validation, gate classification,
+// tile-local op encoding and kernel launches.  No CPU fallback exists: without a CUDA device
+// qvm_create fails.
+#include "qvm_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/qvm_b200.h"
+
+using namespace qvm;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+constexpr size_t kRingBytes = 8u << 20;     // op-descriptor ring (pinned host + device mirror)
+constexpr int kReduceThreads = 256;
+
+}  // namespace
+
+struct qvm_state {
+    int device = 0;
+    int n_local = 0;
+    int n_global = 0;
+    uint64_t shard_index = 0;
+    uint64_t n_elems = 0;
+    double2* amps = nullptr;
+    bool owns_amps = true;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    int tile_bits = 12;
+    int low_bits = 5;
+    int sticky = 0;
+    // op ring
+    unsigned char* ring_host = nullptr;
+    unsigned char* ring_dev = nullptr;
+    size_t ring_pos = 0;
+    // small scratch: reduction partials + results
+    double* partials = nullptr;     // device, kPartialsCap doubles
+    double* result_dev = nullptr;   // device, 8 doubles
+    double* result_host = nullptr;  // pinned, 8 doubles
+    double* pow_dev = nullptr;      // device, 65 doubles (dephasing powers)
+    // sampling workspace
+    double* cdf = nullptr;
+    uint64_t cdf_blocks = 0;
+    uint64_t cdf_cap = 0;
+    int sample_mode = -1;
+    int sample_n_rho = 0;
+    uint64_t sample_n_probs = 0;
+    double* total_dev = nullptr;
+    // staging for host<->device traffic
+    unsigned char* stage = nullptr;   // pinned
+    size_t stage_bytes = 0;
+    int measure_grid = 0;
+    qvm_stats_t stats{};
+};
+
+namespace {
+
+constexpr int kPartialsCap = 4096;
+
+#define QVM_CUDA(q, expr)                                                                              \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            if (q) (q)->sticky = QVM_ERR_CUDA;                                                         \
+            return fail(QVM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                        __LINE__);                                                                     \
+        }                                                                                              \
+    } while (0)
+
+#define QVM_CHECK_HANDLE(q)                                                        \
+    do {                                                                           \
+        if (!(q)) return fail(QVM_ERR_INVALID, "null handle");                     \
+        if ((q)->sticky) return (q)->sticky; /* message of the original failure is kept */ \
+        cudaError_t _e = cudaSetDevice((q)->device);                               \
+        if (_e != cudaSuccess) return fail(QVM_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(_e)); \
+    } while (0)
+
+int grid_for(const qvm_state* q, uint64_t work_items, int threads, int per_sm = 8) {
+    uint64_t blocks = (work_items + threads - 1) / threads;
+    uint64_t cap = (uint64_t)q->sm_count * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+int total_positions(const qvm_state* q) { return q->n_local + q->n_global; }
+
+// ---- gate classification -----------------------------------------------------------------------
+struct cplx {
+    double re, im;
+};
+inline bool is_zero(cplx a) { return a.re == 0.0 && a.im == 0.0; }
+inline bool is_one(cplx a) { return a.re == 1.0 && a.im == 0.0; }
+
+int classify(int k, const int32_t* qubits, const double* matrix, qvm_op_t* op, double* mat_out) {
+    if (k < 1) return fail(QVM_ERR_INVALID, "gate must act on at least one qubit");
+    if (k > 10) return fail(QVM_ERR_UNSUPPORTED, "gates on more than 10 qubits are not supported");
+    const int dim = 1 << k;
+    std::vector<cplx> m((size_t)dim * dim);
+    for (size_t i = 0; i < m.size(); ++i) m[i] = cplx{matrix[2 * i], matrix[2 * i + 1]};
+    std::vector<int> tq(qubits, qubits + k);      // remaining targets, MSB first
+    uint64_t ctrl = 0;
+
+    bool diag = true;
+    for (int r = 0; r < dim && diag; ++r)
+        for (int c = 0; c < dim; ++c)
+            if (r != c && !is_zero(m[(size_t)r * dim + c])) {
+                diag = false;
+                break;
+            }
+
+    if (diag) {
+        std::vector<cplx> d(dim);
+        for (int r = 0; r < dim; ++r) d[r] = m[(size_t)r * dim + r];
+        // a qubit whose 0-half is all ones is a control
+        bool again = true;
+        while (again && !tq.empty()) {
+            again = false;
+            const int kk = (int)tq.size();
+            for (int j = 0; j < kk; ++j) {
+                const int bit = kk - 1 - j;
+                bool ctrl_like = true;
+                for (int r = 0; r < (1 << kk); ++r)
+                    if (!((r >> bit) & 1) && !is_one(d[r])) {
+                        ctrl_like = false;
+                        break;
+                    }
+                if (!ctrl_like) continue;
+                std::vector<cplx> nd(1 << (kk - 1));
+                for (int r = 0; r < (1 << (kk - 1)); ++r) nd[r] = d[insert_zero32((uint32_t)r, (uint32_t)bit) | (1u << bit)];
+                d.swap(nd);
+                ctrl |= 1ull << tq[j];
+                tq.erase(tq.begin() + j);
+                again = true;
+                break;
+            }
+        }
+        if (tq.empty() && is_one(d[0])) {
+            op->kind = QVM_OP_NOP;
+            op->k = 0;
+            op->ctrl_mask = 0;
+            op->mat_entries = 0;
+            op->mat_offset = 0;
+            for (int j = 0; j < QVM_MAX_TARGETS; ++j) op->targets[j] = -1;
+            return QVM_OK;
+        }
+        if ((int)tq.size() > QVM_MAX_TARGETS)
+            return fail(QVM_ERR_UNSUPPORTED, "diagonal gate on %d qubits exceeds %d", (int)tq.size(), QVM_MAX_TARGETS);
+        op->kind = QVM_OP_DIAG;
+        op->k = (int)tq.size();
+        for (int j = 0; j < QVM_MAX_TARGETS; ++j) op->targets[j] = j < op->k ? tq[j] : -1;
+        op->ctrl_mask = ctrl;
+        op->mat_entries = (uint32_t)d.size();
+        op->mat_offset = 0;
+        for (size_t i = 0; i < d.size(); ++i) {
+            mat_out[2 * i] = d[i].re;
+            mat_out[2 * i + 1] = d[i].im;
+        }
+        return QVM_OK;
+    }
+
+    // dense: peel off controls (identity on the 0-half, no coupling between halves)
+    bool again = true;
+    while (again && tq.size() > 1) {
+        again = false;
+        const int kk = (int)tq.size();
+        const int dd = 1 << kk;
+        for (int j = 0; j < kk; ++j) {
+            const int bit = kk - 1 - j;
+            bool ctrl_like = true;
+            for (int r = 0; r < dd && ctrl_like; ++r)
+                for (int c = 0; c < dd; ++c) {
+                    const int rb = (r >> bit) & 1, cb = (c >> bit) & 1;
+                    if (rb && cb) continue;
+                    const cplx v = m[(size_t)r * dd + c];
+                    if (r == c ? !is_one(v) : !is_zero(v)) {
+                        ctrl_like = false;
+                        break;
+                    }
+                }
+            if (!ctrl_like) continue;
+            const int nd = dd >> 1;
+            std::vector<cplx> nm((size_t)nd * nd);
+            for (int r = 0; r < nd; ++r)
+                for (int c = 0; c < nd; ++c) {
+                    const uint32_t rr = insert_zero32((uint32_t)r, (uint32_t)bit) | (1u << bit);
+                    const uint32_t cc = insert_zero32((uint32_t)c, (uint32_t)bit) | (1u << bit);
+                    nm[(size_t)r * nd + c] = m[(size_t)rr * dd + cc];
+                }
+            m.swap(nm);
+            ctrl |= 1ull << tq[j];
+            tq.erase(tq.begin() + j);
+            again = true;
+            break;
+        }
+    }
+    if ((int)tq.size() > QVM_MAX_TARGETS)
+        return fail(QVM_ERR_UNSUPPORTED, "dense gate on %d qubits exceeds the supported %d", (int)tq.size(),
+                    QVM_MAX_TARGETS);
+    op->kind = QVM_OP_DENSE;
+    op->k = (int)tq.size();
+    for (int j = 0; j < QVM_MAX_TARGETS; ++j) op->targets[j] = j < op->k ? tq[j] : -1;
+    op->ctrl_mask = ctrl;
+    op->mat_entries = (uint32_t)m.size();
+    op->mat_offset = 0;
+    for (size_t i = 0; i < m.size(); ++i) {
+        mat_out[2 * i] = m[i].re;
+        mat_out[2 * i + 1] = m[i].im;
+    }
+    return QVM_OK;
+}
+
+int validate_qubits(const qvm_state* q, int k, const int32_t* qubits) {
+    const int npos = total_positions(q);
+    uint64_t seen = 0;
+    for (int j = 0; j < k; ++j) {
+        if (qubits[j] < 0 || qubits[j] >= npos)
+            return fail(QVM_ERR_INVALID, "qubit index %d out of range [0, %d)", qubits[j], npos);
+        if ((seen >> qubits[j]) & 1ull) return fail(QVM_ERR_INVALID, "duplicate qubit index %d", qubits[j]);
+        seen |= 1ull << qubits[j];
+    }
+    return QVM_OK;
+}
+
+// ---- op ring -----------------------------------------------------------------------------------
+int ring_alloc(qvm_state* q, size_t bytes, size_t* off) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes > kRingBytes) return fail(QVM_ERR_UNSUPPORTED, "op group of %zu bytes exceeds the descriptor ring", bytes);
+    if (q->ring_pos + bytes > kRingBytes) {
+        QVM_CUDA(q, cudaStreamSynchronize(q->stream));      // wrap: everything queued has consumed the ring
+        q->ring_pos = 0;
+    }
+    *off = q->ring_pos;
+    q->ring_pos += bytes;
+    return QVM_OK;
+}
+
+// Encode ops in tile-local coordinates and launch one tile kernel.
+int launch_group(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops, const double* mats,
+                 uint64_t mats_entries) {
+    if (n_tile < 0 || n_tile > q->n_local || n_tile > QVM_MAX_TILE_BITS)
+        return fail(QVM_ERR_INVALID, "tile of %d bits is outside [0, min(n_local=%d, %d)]", n_tile, q->n_local,
+                    QVM_MAX_TILE_BITS);
+    TileParams P{};
+    P.n_local = q->n_local;
+    P.k = n_tile;
+    P.shard_bits = q->shard_index << q->n_local;
+    int8_t local_of[64];
+    memset(local_of, -1, sizeof(local_of));
+    for (int j = 0; j < n_tile; ++j) {
+        const int p = tile_bits[j];
+        if (p < 0 || p >= q->n_local) return fail(QVM_ERR_INVALID, "tile bit %d is not a local position", p);
+        if (j && p <= tile_bits[j - 1]) return fail(QVM_ERR_INVALID, "tile bits must be strictly ascending");
+        P.tile_pos[j] = (uint8_t)p;
+        P.tile_mask |= 1ull << p;
+        local_of[p] = (int8_t)j;
+    }
+    int low = 0;
+    while (low < n_tile && tile_bits[low] == low) ++low;
+    // keep the offset table small: at most 2^8 entries come from the high part
+    if (n_tile - low > 10) return fail(QVM_ERR_INVALID, "tile needs at least %d contiguous low bits", n_tile - 10);
+    P.low = low;
+
+    std::vector<DevOp> dev;
+    dev.reserve(n_ops);
+    const int npos = total_positions(q);
+    uint64_t executed = 0;
+    for (int i = 0; i < n_ops; ++i) {
+        const qvm_op_t& op = ops[i];
+        if (op.kind == QVM_OP_NOP) continue;
+        if (op.kind != QVM_OP_DENSE && op.kind != QVM_OP_DIAG) return fail(QVM_ERR_INVALID, "op %d: bad kind %d", i, op.kind);
+        if (op.k < 0 || op.k > QVM_MAX_TARGETS) return fail(QVM_ERR_INVALID, "op %d: bad target count %d", i, op.k);
+        const uint64_t want = op.kind == QVM_OP_DENSE ? (1ull << (2 * op.k)) : (1ull << op.k);
+        if (op.mat_entries != want || (uint64_t)op.mat_offset + want > mats_entries)
+            return fail(QVM_ERR_INVALID, "op %d: matrix pool reference out of range", i);
+        if (npos < 64 && (op.ctrl_mask >> npos)) return fail(QVM_ERR_INVALID, "op %d: control outside the register", i);
+        DevOp d{};
+        d.kind = op.kind == QVM_OP_DENSE ? DK_DENSE : DK_DIAG;
+        d.k = (uint8_t)op.k;
+        d.mat_off = op.mat_offset;
+        uint64_t used = op.ctrl_mask;
+        for (int p = 0; p < q->n_local; ++p)
+            if (((op.ctrl_mask >> p) & 1ull) && local_of[p] >= 0) d.ctrl_tile |= 1u << local_of[p];
+        d.ctrl_outer = op.ctrl_mask & ~P.tile_mask;
+        uint32_t fixmask = d.ctrl_tile;
+        for (int j = 0; j < op.k; ++j) {
+            const int p = op.targets[j];
+            if (p < 0 || p >= npos) return fail(QVM_ERR_INVALID, "op %d: target %d out of range", i, p);
+            if ((used >> p) & 1ull) return fail(QVM_ERR_INVALID, "op %d: qubit %d used twice", i, p);
+            used |= 1ull << p;
+            if (op.kind == QVM_OP_DENSE) {
+                if (p >= q->n_local || local_of[p] < 0)
+                    return fail(QVM_ERR_INVALID, "op %d: dense target %d is not a tile bit", i, p);
+                d.tgt[j] = (uint8_t)local_of[p];
+                fixmask |= 1u << local_of[p];
+            } else {
+                d.tgt[j] = (p < q->n_local && local_of[p] >= 0) ? (uint8_t)local_of[p] : (uint8_t)(0x80 | p);
+            }
+        }
+        if (op.kind == QVM_OP_DENSE) {
+            if (op.k < 1) return fail(QVM_ERR_INVALID, "op %d: dense op without targets", i);
+            int nf = 0;
+            for (int b = 0; b < n_tile; ++b)
+                if ((fixmask >> b) & 1u) d.fix[nf++] = (uint8_t)b;
+            d.nfix = (uint8_t)nf;
+        }
+        dev.push_back(d);
+        ++executed;
+    }
+    if (dev.empty()) return QVM_OK;
+
+    const size_t ops_bytes = dev.size() * sizeof(DevOp);
+    const size_t mats_bytes = (size_t)mats_entries * sizeof(double2);
+    const size_t ops_pad = (ops_bytes + 255) & ~(size_t)255;
+    size_t off = 0;
+    int rc = ring_alloc(q, ops_pad + mats_bytes, &off);
+    if (rc) return rc;
+    memcpy(q->ring_host + off, dev.data(), ops_bytes);
+    memcpy(q->ring_host + off + ops_pad, mats, mats_bytes);
+    QVM_CUDA(q, cudaMemcpyAsync(q->ring_dev + off, q->ring_host + off, ops_pad + mats_bytes, cudaMemcpyHostToDevice,
+                                q->stream));
+    P.n_ops = (int)dev.size();
+    P.ops = reinterpret_cast<const DevOp*>(q->ring_dev + off);
+    P.mats = reinterpret_cast<const double2*>(q->ring_dev + off + ops_pad);
+
+    const size_t smem = tile_smem_bytes(P.k, P.low, P.n_ops);
+    if (smem > 227 * 1024) return fail(QVM_ERR_UNSUPPORTED, "group needs %zu bytes of shared memory (> 227 KiB)", smem);
+    const uint64_t n_tiles = q->n_elems >> n_tile;
+    if (n_tiles > 0x7fffffffull) return fail(QVM_ERR_UNSUPPORTED, "too many tiles for one launch");
+    tile_kernel<<<(unsigned)n_tiles, kTileThreads, smem, q->stream>>>(q->amps, P);
+    QVM_CUDA(q, cudaGetLastError());
+    q->stats.kernel_launches += 1;
+    q->stats.gate_ops += executed;
+    q->stats.hbm_passes += 1;
+    q->stats.hbm_bytes += 32ull * q->n_elems;
+    q->stats.h2d_bytes += ops_pad + mats_bytes;
+    return QVM_OK;
+}
+
+int reduce_partials(qvm_state* q, int n_partials, double* out_host) {
+    final_sum_kernel<<<1, kReduceThreads, 0, q->stream>>>(q->partials, n_partials, q->result_dev);
+    QVM_CUDA(q, cudaGetLastError());
+    QVM_CUDA(q, cudaMemcpyAsync(q->result_host, q->result_dev, sizeof(double), cudaMemcpyDeviceToHost, q->stream));
+    QVM_CUDA(q, cudaStreamSynchronize(q->stream));
+    *out_host = q->result_host[0];
+    q->stats.kernel_launches += 1;
+    q->stats.d2h_bytes += sizeof(double);
+    return QVM_OK;
+}
+
+int ensure_stage(qvm_state* q, size_t bytes) {
+    if (q->stage_bytes >= bytes) return QVM_OK;
+    if (q->stage) cudaFreeHost(q->stage);
+    q->stage = nullptr;
+    q->stage_bytes = 0;
+    QVM_CUDA(q, cudaMallocHost(&q->stage, bytes));
+    q->stage_bytes = bytes;
+    return QVM_OK;
+}
+
+constexpr size_t kStageChunk = 64u << 20;   // 64 MiB pinned bounce buffer for pageable host arrays
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* qvm_version(void) { return "qvm_b200 0.1 (sm_100a)"; }
+const char* qvm_last_error(void) { return g_err; }
+
+int qvm_device_count(int* count) {
+    if (!count) return fail(QVM_ERR_INVALID, "null pointer");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(QVM_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return QVM_OK;
+}
+
+static int create_impl(int n_local, int device, void* external, qvm_t** out) {
+    if (!out) return fail(QVM_ERR_INVALID, "null output pointer");
+    *out = nullptr;
+    if (n_local < 0 || n_local > 40) return fail(QVM_ERR_INVALID, "n_local=%d outside [0, 40]", n_local);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(QVM_ERR_CUDA, "no CUDA device available (%s); libqvm_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(QVM_ERR_INVALID, "device %d not in [0, %d)", device, count);
+    qvm_state* q = new (std::nothrow) qvm_state();
+    if (!q) return fail(QVM_ERR_NOMEM, "host allocation failed");
+    q->device = device;
+    q->n_local = n_local;
+    q->n_elems = 1ull << n_local;
+#define QVM_CREATE_CUDA(expr)                                                                          \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            int code = (_e == cudaErrorMemoryAllocation) ? QVM_ERR_NOMEM : QVM_ERR_CUDA;               \
+            fail(code, "%s failed: %s", #expr, cudaGetErrorString(_e));                                \
+            cudaGetLastError();                                                                        \
+            qvm_destroy(q);                                                                            \
+            return code;                                                                               \
+        }                                                                                              \
+    } while (0)
+    QVM_CREATE_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    QVM_CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
+    q->sm_count = prop.multiProcessorCount;
+    QVM_CREATE_CUDA(cudaStreamCreateWithFlags(&q->own_stream, cudaStreamNonBlocking));
+    q->stream = q->own_stream;
+    if (external) {
+        q->amps = static_cast<double2*>(external);
+        q->owns_amps = false;
+    } else {
+        QVM_CREATE_CUDA(cudaMalloc(&q->amps, q->n_elems * sizeof(double2)));
+    }
+    QVM_CREATE_CUDA(cudaMallocHost(&q->ring_host, kRingBytes));
+    QVM_CREATE_CUDA(cudaMalloc(&q->ring_dev, kRingBytes));
+    QVM_CREATE_CUDA(cudaMalloc(&q->partials, kPartialsCap * sizeof(double)));
+    QVM_CREATE_CUDA(cudaMalloc(&q->result_dev, 8 * sizeof(double)));
+    QVM_CREATE_CUDA(cudaMallocHost(&q->result_host, 8 * sizeof(double)));
+    QVM_CREATE_CUDA(cudaMalloc(&q->pow_dev, 65 * sizeof(double)));
+    QVM_CREATE_CUDA(cudaMalloc(&q->total_dev, sizeof(double)));
+    QVM_CREATE_CUDA(cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int per_sm = 0;
+    QVM_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, measure_kernel, kReduceThreads, 0));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    q->measure_grid = std::min(per_sm * q->sm_count, kPartialsCap);
+#undef QVM_CREATE_CUDA
+    *out = q;
+    return QVM_OK;
+}
+
+int qvm_create(int n_local, int device, qvm_t** out) { return create_impl(n_local, device, nullptr, out); }
+
+int qvm_create_external(int n_local, int device, void* device_ptr, qvm_t** out) {
+    if (!device_ptr) return fail(QVM_ERR_INVALID, "null device pointer");
+    return create_impl(n_local, device, device_ptr, out);
+}
+
+int qvm_destroy(qvm_t* q) {
+    if (!q) return QVM_OK;
+    cudaSetDevice(q->device);
+    if (q->stream) cudaStreamSynchronize(q->stream);
+    if (q->amps && q->owns_amps) cudaFree(q->amps);
+    if (q->ring_host) cudaFreeHost(q->ring_host);
+    if (q->ring_dev) cudaFree(q->ring_dev);
+    if (q->partials) cudaFree(q->partials);
+    if (q->result_dev) cudaFree(q->result_dev);
+    if (q->result_host) cudaFreeHost(q->result_host);
+    if (q->pow_dev) cudaFree(q->pow_dev);
+    if (q->total_dev) cudaFree(q->total_dev);
+    if (q->cdf) cudaFree(q->cdf);
+    if (q->stage) cudaFreeHost(q->stage);
+    if (q->own_stream) cudaStreamDestroy(q->own_stream);
+    delete q;
+    return QVM_OK;
+}
+
+int qvm_set_shard(qvm_t* q, int n_global, uint64_t shard_index) {
+    QVM_CHECK_HANDLE(q);
+    if (n_global < 0 || q->n_local + n_global > 62) return fail(QVM_ERR_INVALID, "bad n_global=%d", n_global);
+    if (n_global < 64 && (shard_index >> n_global)) return fail(QVM_ERR_INVALID, "shard index out of range");
+    q->n_global = n_global;
+    q->shard_index = shard_index;
+    return QVM_OK;
+}
+
+int qvm_set_stream(qvm_t* q, void* cuda_stream) {
+    QVM_CHECK_HANDLE(q);
+    QVM_CUDA(q, cudaStreamSynchronize(q->stream));
+    q->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : q->own_stream;
+    return QVM_OK;
+}
+
+int qvm_set_tile_bits(qvm_t* q, int tile_bits, int low_bits) {
+    QVM_CHECK_HANDLE(q);
+    if (tile_bits < 1 || tile_bits > QVM_MAX_TILE_BITS || low_bits < 0 || low_bits > tile_bits)
+        return fail(QVM_ERR_INVALID, "bad tile configuration (%d, %d)", tile_bits, low_bits);
+    q->tile_bits = tile_bits;
+    q->low_bits = low_bits;
+    return QVM_OK;
+}
+
+int qvm_n_local(const qvm_t* q) { return q ? q->n_local : -1; }
+void* qvm_device_ptr(qvm_t* q) { return q ? q->amps : nullptr; }
+void* qvm_stream(qvm_t* q) { return q ? q->stream : nullptr; }
+
+int qvm_sync(qvm_t* q) {
+    QVM_CHECK_HANDLE(q);
+    QVM_CUDA(q, cudaStreamSynchronize(q->stream));
+    return QVM_OK;
+}
+
+int qvm_stats(const qvm_t* q, qvm_stats_t* out) {
+    if (!q || !out) return fail(QVM_ERR_INVALID, "null pointer");
+    *out = q->stats;
+    return QVM_OK;
+}
+
+int qvm_stats_reset(qvm_t* q) {
+    if (!q) return fail(QVM_ERR_INVALID, "null handle");
+    q->stats = qvm_stats_t{};
+    return QVM_OK;
+}
+
+// ---- state I/O ------------------------------------------------------------------------------------
+int qvm_reset_zero(qvm_t* q, int set_amp0) {
+    QVM_CHECK_HANDLE(q);
+    fill_zero_kernel<<<grid_for(q, q->n_elems, 256), 256, 0, q->stream>>>(q->amps, q->n_elems, set_amp0);
+    QVM_CUDA(q, cudaGetLastError());
+    q->stats.kernel_launches += 1;
+    q->stats.hbm_bytes += 16ull * q->n_elems;
+    q->sample_mode = -1;
+    return QVM_OK;
+}
+
+static int copy_chunked(qvm_t* q, double2* dev, double* host, uint64_t count, bool to_device) {
+    int rc = ensure_stage(q, std::min<size_t>(kStageChunk, std::max<size_t>(count * 16, 16)));
+    if (rc) return rc;
+    uint64_t done = 0;
+    while (done < count) {
+        const uint64_t n = std::min<uint64_t>(count - done, q->stage_bytes / 16);
+        if (to_device) {
+            memcpy(q->stage, host + 2 * done, n * 16);
+            QVM_CUDA(q, cudaMemcpyAsync(dev + done, q->stage, n * 16, cudaMemcpyHostToDevice, q->stream));
+        } else {
+            QVM_CUDA(q, cudaMemcpyAsync(q->stage, dev + done, n * 16, cudaMemcpyDeviceToHost, q->stream));
+        }
+        QVM_CUDA(q, cudaStreamSynchronize(q->stream));
+        if (!to_device) memcpy(host + 2 * done, q->stage, n * 16);
+        done += n;
+    }
+    return QVM_OK;
+}
+
+int qvm_set_state(qvm_t* q, uint64_t offset, uint64_t count, const double* re_im) {
+    QVM_CHECK_HANDLE(q);
+    if (!re_im && count) return fail(QVM_ERR_INVALID, "null host buffer");
+    if (offset > q->n_elems || count > q->n_elems - offset) return fail(QVM_ERR_INVALID, "range outside the shard");
+    q->sample_mode = -1;
+    q->stats.h2d_bytes += count * 16;
+    return copy_chunked(q, q->amps + offset, const_cast<double*>(re_im), count, true);
+}
+
+int qvm_get_state(qvm_t* q, uint64_t offset, uint64_t count, double* re_im) {
+    QVM_CHECK_HANDLE(q);
+    if (!re_im && count) return fail(QVM_ERR_INVALID, "null host buffer");
+    if (offset > q->n_elems || count > q->n_elems - offset) return fail(QVM_ERR_INVALID, "range outside the shard");
+    q->stats.d2h_bytes += count * 16;
+    return copy_chunked(q, q->amps + offset, re_im, count, false);
+}
+
+int qvm_get_strided(qvm_t* q, uint64_t offset, uint64_t stride, uint64_t count, double* re_im) {
+    QVM_CHECK_HANDLE(q);
+    if (!count) return QVM_OK;
+    if (!re_im) return fail(QVM_ERR_INVALID, "null host buffer");
+    if (offset >= q->n_elems || (count - 1) > (q->n_elems - 1 - offset) / (stride ? stride : 1))
+        return fail(QVM_ERR_INVALID, "strided range outside the shard");
+    double2* tmp = nullptr;
+    QVM_CUDA(q, cudaMallocAsync(&tmp, count * 16, q->stream));
+    gather_strided_kernel<<<grid_for(q, count, 256), 256, 0, q->stream>>>(q->amps, offset, stride, count, tmp);
+    QVM_CUDA(q, cudaGetLastError());
+    q->stats.kernel_launches += 1;
+    int rc = copy_chunked(q, tmp, re_im, count, false);
+    cudaFreeAsync(tmp, q->stream);
+    q->stats.d2h_bytes += count * 16;
+    return rc;
+}
+
+int qvm_copy_state(qvm_t* dst, qvm_t* src) {
+    QVM_CHECK_HANDLE(dst);
+    if (!src) return fail(QVM_ERR_INVALID, "null source");
+    if (dst->n_local != src->n_local || dst->device != src->device)
+        return fail(QVM_ERR_INVALID, "copy needs equal shapes on one device");
+    QVM_CUDA(src, cudaStreamSynchronize(src->stream));
+    QVM_CUDA(dst, cudaMemcpyAsync(dst->amps, src->amps, dst->n_elems * 16, cudaMemcpyDeviceToDevice, dst->stream));
+    dst->sample_mode = -1;
+    dst->stats.hbm_bytes += 32ull * dst->n_elems;
+    return QVM_OK;
+}
+
+int qvm_norm2(qvm_t* q, double* out) {
+    QVM_CHECK_HANDLE(q);
+    if (!out) return fail(QVM_ERR_INVALID, "null pointer");
+    const int grid = std::min(grid_for(q, q->n_elems, kReduceThreads), kPartialsCap);
+    prob_partial_kernel<<<grid, kReduceThreads, 0, q->stream>>>(q->amps, q->n_elems, q->n_local, -1, 0, 0, 0, q->partials);
+    QVM_CUDA(q, cudaGetLastError());
+    q->stats.kernel_launches += 1;
+    q->stats.hbm_bytes += 16ull * q->n_elems;
+    return reduce_partials(q, grid, out);
+}
+
+// ---- gates ----------------------------------------------------------------------------------------
+int qvm_classify(int k, const int32_t* qubits, const double* matrix, qvm_op_t* op, double* mat_out) {
+    if (!qubits || !matrix || !op || !mat_out) return fail(QVM_ERR_INVALID, "null pointer");
+    return classify(k, qubits, matrix, op, mat_out);
+}
+
+int qvm_apply(qvm_t* q, int k, const int32_t* qubits, const double* matrix) {
+    QVM_CHECK_HANDLE(q);
+    if (!qubits || !matrix) return fail(QVM_ERR_INVALID, "null pointer");
+    if (k < 1 || k > 10) return fail(QVM_ERR_INVALID, "gate size k=%d outside [1, 10]", k);
+    int rc = validate_qubits(q, k, qubits);
+    if (rc) return rc;
+    qvm_op_t op{};
+    std::vector<double> mat((size_t)2 << (2 * k));
+    rc = classify(k, qubits, matrix, &op, mat.data());
+    if (rc) return rc;
+    if (op.kind == QVM_OP_NOP) return QVM_OK;
+    // tile = dense targets + lowest positions, up to the configured tile size
+    const int want = std::min(q->n_local, q->tile_bits);
+    uint64_t mask = 0;
+    int cnt = 0;
+    if (op.kind == QVM_OP_DENSE)
+        for (int j = 0; j < op.k; ++j) {
+            if (op.targets[j] >= q->n_local)
+                return fail(QVM_ERR_INVALID, "dense target %d is a global position; remap it to a local one first",
+                            op.targets[j]);
+            mask |= 1ull << op.targets[j];
+            ++cnt;
+        }
+    for (int p = 0; p < q->n_local && cnt < want; ++p)
+        if (!((mask >> p) & 1ull)) {
+            mask |= 1ull << p;
+            ++cnt;
+        }
+    int32_t tile[QVM_MAX_TILE_BITS + QVM_MAX_TARGETS];
+    int nt = 0;
+    for (int p = 0; p < q->n_local; ++p)
+        if ((mask >> p) & 1ull) tile[nt++] = p;
+    q->sample_mode = -1;
+    return launch_group(q, nt, tile, 1, &op, mat.data(), op.mat_entries);
+}
+
+int qvm_apply_group(qvm_t* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops, const double* mats,
+                    uint64_t mats_entries) {
+    QVM_CHECK_HANDLE(q);
+    if (n_ops < 0 || (n_ops && !ops) || (n_tile && !tile_bits)) return fail(QVM_ERR_INVALID, "null pointer");
+    if (mats_entries && !mats) return fail(QVM_ERR_INVALID, "null matrix pool");
+    q->sample_mode = -1;
+    return launch_group(q, n_tile, tile_bits, n_ops, ops, mats, mats_entries);
+}
+
+int qvm_dephase_all(qvm_t* q, int n_rho, uint64_t qubit_mask, double factor) {
+    QVM_CHECK_HANDLE(q);
+    if (2 * n_rho != total_positions(q) || n_rho > 31) return fail(QVM_ERR_INVALID, "state is not a %d-qubit rho", n_rho);
+    double table[65];
+    table[0] = 1.0;
+    for (int i = 1; i <= 64; ++i) table[i] = table[i - 1] * factor;
+    size_t off = 0;
+    int rc = ring_alloc(q, sizeof(table), &off);
+    if (rc) return rc;
+    memcpy(q->ring_host + off, table, sizeof(table));
+    QVM_CUDA(q, cudaMemcpyAsync(q->ring_dev + off, q->ring_host + off, sizeof(table), cudaMemcpyHostToDevice, q->stream));
+    dephase_kernel<<<grid_for(q, q->n_elems, 256, 16), 256, 0, q->stream>>>(
+        q->amps, q->n_elems, n_rho, qubit_mask, q->shard_index << q->n_local,
+        reinterpret_cast<const double*>(q->ring_dev + off));
+    QVM_CUDA(q, cudaGetLastError());
+    q->sample_mode = -1;
+    q->stats.kernel_launches += 1;
+    q->stats.hbm_passes += 1;
+    q->stats.hbm_bytes += 32ull * q->n_elems;
+    return QVM_OK;
+}
+
+// ---- MEASURE ----------------------------------------------------------------------------------------
+int qvm_measure(qvm_t* q, int qubit, double r, int* outcome, double* p0) {
+    QVM_CHECK_HANDLE(q);
+    if (!outcome || !p0) return fail(QVM_ERR_INVALID, "null pointer");
+    if (q->n_global) return fail(QVM_ERR_INVALID, "qvm_measure is single-shard; use qvm_prob_zero + qvm_collapse");
+    if (qubit < 0 || qubit >= q->n_local) return fail(QVM_ERR_INVALID, "qubit %d out of range", qubit);
+    void* args[] = {&q->amps, &q->n_elems, &q->n_local, &qubit, &r, &q->partials, &q->result_dev};
+    QVM_CUDA(q, cudaLaunchCooperativeKernel((void*)measure_kernel, dim3(q->measure_grid), dim3(kReduceThreads), args, 0,
+                                            q->stream));
+    QVM_CUDA(q, cudaMemcpyAsync(q->result_host, q->result_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, q->stream));
+    QVM_CUDA(q, cudaStreamSynchronize(q->stream));
+    *outcome = (int)q->result_host[0];
+    *p0 = q->result_host[1];
+    q->sample_mode = -1;
+    q->stats.kernel_launches += 1;
+    q->stats.hbm_bytes += 16ull * q->n_elems + 24ull * q->n_elems;
+    q->stats.d2h_bytes += 16;
+    return QVM_OK;
+}
+
+int qvm_prob_zero(qvm_t* q, int qubit, double* p0_partial) {
+    QVM_CHECK_HANDLE(q);
+    if (!p0_partial) return fail(QVM_ERR_INVALID, "null pointer");
+    if (qubit < 0 || qubit >= total_positions(q)) return fail(QVM_ERR_INVALID, "qubit %d out of range", qubit);
+    if (qubit >= q->n_local && ((q->shard_index >> (qubit - q->n_local)) & 1ull)) {
+        *p0_partial = 0.0;          // this shard holds only the |1> half of a global qubit
+        return QVM_OK;
+    }
+    const int grid = std::min(grid_for(q, q->n_elems, kReduceThreads), kPartialsCap);
+    prob_partial_kernel<<<grid, kReduceThreads, 0, q->stream>>>(q->amps, q->n_elems, q->n_local, qubit, 0, 0, 0,
+                                                                q->partials);
+    QVM_CUDA(q, cudaGetLastError());
+    q->stats.kernel_launches += 1;
+    q->stats.hbm_bytes += 16ull * q->n_elems;
+    return reduce_partials(q, grid, p0_partial);
+}
+
+int qvm_density_prob_zero(qvm_t* q, int n_rho, int qubit, double* p0_partial) {
+    QVM_CHECK_HANDLE(q);
+    if (!p0_partial) return fail(QVM_ERR_INVALID, "null pointer");
+    if (2 * n_rho != total_positions(q) || q->n_local < n_rho)
+        return fail(QVM_ERR_INVALID, "state is not a %d-qubit rho sharded by rows", n_rho);
+    if (qubit < -1 || qubit >= n_rho) return fail(QVM_ERR_INVALID, "qubit %d out of range", qubit);
+    const uint64_t rows = q->n_elems >> n_rho;
+    const int grid = std::min(grid_for(q, rows, kReduceThreads), kPartialsCap);
+    prob_partial_kernel<<<grid, kReduceThreads, 0, q->stream>>>(q->amps, q->n_elems, q->n_local, qubit, 1, n_rho,
+                                                                q->shard_index << q->n_local, q->partials);
+    QVM_CUDA(q, cudaGetLastError());
+    q->stats.kernel_launches += 1;
+    return reduce_partials(q, grid, p0_partial);
+}
+
+int qvm_collapse(qvm_t* q, int qubit, int outcome, double scale) {
+    QVM_CHECK_HANDLE(q);
+    if (qubit < 0 || qubit >= total_positions(q)) return fail(QVM_ERR_INVALID, "qubit %d out of range", qubit);
+    if (outcome != 0 && outcome != 1) return fail(QVM_ERR_INVALID, "outcome must be 0 or 1");
+    double s = scale;
+    if (qubit >= q->n_local) {
+        const int mine = (int)((q->shard_index >> (qubit - q->n_local)) & 1ull);
+        if (mine != outcome) s = -1.0;      // zero the shard
+    }
+    collapse_kernel<<<grid_for(q, q->n_elems, 256, 16), 256, 0, q->stream>>>(q->amps, q->n_elems, q->n_local, qubit,
+                                                                             outcome, s);
+    QVM_CUDA(q, cudaGetLastError());
+    q->sample_mode = -1;
+    q->stats.kernel_launches += 1;
+    q->stats.hbm_bytes += 24ull * q->n_elems;
+    return QVM_OK;
+}
+
+// ---- sampling ---------------------------------------------------------------------------------------
+int qvm_probs_prepare(qvm_t* q, int mode, int n_rho, double* total) {
+    QVM_CHECK_HANDLE(q);
+    if (mode != 0 && mode != 1) return fail(QVM_ERR_INVALID, "mode must be 0 (|psi|^2) or 1 (diag rho)");
+    uint64_t n_probs = q->n_elems;
+    uint64_t row_base = 0;
+    if (mode == 1) {
+        if (2 * n_rho != total_positions(q) || q->n_local < n_rho)
+            return fail(QVM_ERR_INVALID, "state is not a %d-qubit rho sharded by rows", n_rho);
+        n_probs = q->n_elems >> n_rho;
+        row_base = (q->shard_index << q->n_local) >> n_rho;
+    }
+    const uint64_t n_blocks = (n_probs + (1ull << kSampleBlockBits) - 1) >> kSampleBlockBits;
+    if (n_blocks > q->cdf_cap) {
+        if (q->cdf) cudaFree(q->cdf);
+        q->cdf = nullptr;
+        q->cdf_cap = 0;
+        QVM_CUDA(q, cudaMalloc(&q->cdf, n_blocks * sizeof(double)));
+        q->cdf_cap = n_blocks;
+    }
+    const int threads = 256;
+    const int grid = grid_for(q, n_blocks * 32, threads, 16);
+    sample_block_sums_kernel<<<grid, threads, 0, q->stream>>>(q->amps, n_probs, mode, n_rho, row_base, q->cdf, n_blocks);
+    QVM_CUDA(q, cudaGetLastError());
+    scan_inclusive_kernel<<<1, 1024, 0, q->stream>>>(q->cdf, n_blocks, q->total_dev);
+    QVM_CUDA(q, cudaGetLastError());
+    QVM_CUDA(q, cudaMemcpyAsync(q->result_host, q->total_dev, sizeof(double), cudaMemcpyDeviceToHost, q->stream));
+    QVM_CUDA(q, cudaStreamSynchronize(q->stream));
+    if (total) *total = q->result_host[0];
+    q->cdf_blocks = n_blocks;
+    q->sample_mode = mode;
+    q->sample_n_rho = n_rho;
+    q->sample_n_probs = n_probs;
+    q->stats.kernel_launches += 2;
+    q->stats.hbm_bytes += 16ull * (mode == 0 ? q->n_elems : n_probs);
+    q->stats.d2h_bytes += 8;
+    return QVM_OK;
+}
+
+int qvm_sample(qvm_t* q, uint64_t n_shots, const double* uniforms, uint64_t* out_index) {
+    QVM_CHECK_HANDLE(q);
+    if (q->sample_mode < 0) return fail(QVM_ERR_INVALID, "call qvm_probs_prepare first (state changed since)");
+    if (!n_shots) return QVM_OK;
+    if (!uniforms || !out_index) return fail(QVM_ERR_INVALID, "null pointer");
+    const uint64_t row_base = q->sample_mode == 1 ? ((q->shard_index << q->n_local) >> q->sample_n_rho) : 0;
+    double* u_dev = nullptr;
+    unsigned long long* idx_dev = nullptr;
+    const uint64_t chunk = 1ull << 22;
+    QVM_CUDA(q, cudaMallocAsync(&u_dev, std::min(n_shots, chunk) * 8, q->stream));
+    QVM_CUDA(q, cudaMallocAsync(&idx_dev, std::min(n_shots, chunk) * 8, q->stream));
+    int rc = ensure_stage(q, std::min<uint64_t>(n_shots, chunk) * 8);
+    if (rc) return rc;
+    for (uint64_t done = 0; done < n_shots; done += chunk) {
+        const uint64_t n = std::min(chunk, n_shots - done);
+        memcpy(q->stage, uniforms + done, n * 8);
+        QVM_CUDA(q, cudaMemcpyAsync(u_dev, q->stage, n * 8, cudaMemcpyHostToDevice, q->stream));
+        const int threads = 128;
+        const int grid = grid_for(q, n * 32, threads, 16);
+        sample_kernel<<<grid, threads, 0, q->stream>>>(q->amps, q->sample_n_probs, q->sample_mode, q->sample_n_rho,
+                                                       row_base, q->cdf, q->cdf_blocks, q->total_dev, u_dev, n, idx_dev);
+        QVM_CUDA(q, cudaGetLastError());
+        QVM_CUDA(q, cudaMemcpyAsync(q->stage, idx_dev, n * 8, cudaMemcpyDeviceToHost, q->stream));
+        QVM_CUDA(q, cudaStreamSynchronize(q->stream));
+        memcpy(out_index + done, q->stage, n * 8);
+        q->stats.kernel_launches += 1;
+        q->stats.h2d_bytes += n * 8;
+        q->stats.d2h_bytes += n * 8;
+    }
+    cudaFreeAsync(u_dev, q->stream);
+    cudaFreeAsync(idx_dev, q->stream);
+    return QVM_OK;
+}
+
+// ---- shard exchange plumbing ---------------------------------------------------------------------------
+int qvm_pack_half(qvm_t* q, int local_bit, int bit_value, uint64_t elem_offset, uint64_t count, void* device_dst) {
+    QVM_CHECK_HANDLE(q);
+    if (local_bit < 0 || local_bit >= q->n_local || (bit_value | 1) != 1) return fail(QVM_ERR_INVALID, "bad bit");
+    if (!device_dst && count) return fail(QVM_ERR_INVALID, "null buffer");
+    const uint64_t half = q->n_elems >> 1;
+    if (elem_offset > half || count > half - elem_offset) return fail(QVM_ERR_INVALID, "range outside the half-shard");
+    if (!count) return QVM_OK;
+    pack_half_kernel<<<grid_for(q, count, 256, 16), 256, 0, q->stream>>>(q->amps, local_bit, bit_value, elem_offset, count,
+                                                                         static_cast<double2*>(device_dst));
+    QVM_CUDA(q, cudaGetLastError());
+    q->stats.kernel_launches += 1;
+    q->stats.hbm_bytes += 32ull * count;
+    return QVM_OK;
+}
+
+int qvm_unpack_half(qvm_t* q, int local_bit, int bit_value, uint64_t elem_offset, uint64_t count,
+                    const void* device_src) {
+    QVM_CHECK_HANDLE(q);
+    if (local_bit < 0 || local_bit >= q->n_local || (bit_value | 1) != 1) return fail(QVM_ERR_INVALID, "bad bit");
+    if (!device_src && count) return fail(QVM_ERR_INVALID, "null buffer");
+    const uint64_t half = q->n_elems >> 1;
+    if (elem_offset > half || count > half - elem_offset) return fail(QVM_ERR_INVALID, "range outside the half-shard");
+    if (!count) return QVM_OK;
+    unpack_half_kernel<<<grid_for(q, count, 256, 16), 256, 0, q->stream>>>(q->amps, local_bit, bit_value, elem_offset,
+                                                                           count, static_cast<const double2*>(device_src));
+    QVM_CUDA(q, cudaGetLastError());
+    q->sample_mode = -1;
+    q->stats.kernel_launches += 1;
+    q->stats.hbm_bytes += 32ull * count;
+    return QVM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,584 @@
+// Device kernels of libqvm_b200 (sm_100a).  All arithmetic is complex128 held as double2.
+//
+// The workhorse is tile_kernel: one CTA stages the 2^k amplitudes addressed by an arbitrary set of
+// k index bits ("tile bits", always containing the lowest `low` bits so global accesses are
+// 16*2^low-byte contiguous runs) in shared memory, applies a whole run of gates to them and writes
+// them back -- ONE read + ONE write of HBM for the run.  It implements the closed form of the
+// reference's lifted operator (unitary_generator.py:266-323):
+//     psi'[x] = sum_c G[r(x), c] * psi[x with bits a_j := c_(k-1-j)],   r(x)_(k-1-j) = x_(a_j).
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cg = cooperative_groups;
+
+namespace qvm {
+
+constexpr int kTileThreads = 256;
+constexpr int kMaxFix = 13;
+
+enum : uint8_t { DK_DENSE = 1, DK_DIAG = 2 };
+
+// Per-op descriptor in tile-local coordinates (built on the host by build_dev_ops()).
+struct __align__(16) DevOp {
+    uint8_t kind;
+    uint8_t k;                 // number of targets
+    uint8_t nfix;              // dense: number of fixed tile positions (targets + tile controls)
+    uint8_t pad0;
+    uint8_t tgt[6];            // dense: tile-local target positions, MSB first
+                               // diag : bit7 set -> physical position (outer / global), else tile-local
+    uint8_t fix[kMaxFix];      // dense: fixed tile positions, ascending
+    uint8_t pad1;
+    uint32_t ctrl_tile;        // tile-local control mask
+    uint32_t mat_off;          // offset into mats[], in double2
+    uint64_t ctrl_outer;       // physical control mask outside the tile (incl. global positions)
+};
+static_assert(sizeof(DevOp) == 48, "DevOp layout");
+
+struct TileParams {
+    int n_local;
+    int k;                     // tile bits
+    int low;                   // tile_pos[0..low) == 0..low-1
+    int n_ops;
+    uint64_t tile_mask;        // physical mask of the tile bits
+    uint64_t shard_bits;       // shard_index << n_local
+    uint8_t tile_pos[16];      // physical position of tile bit j (ascending)
+    const DevOp* ops;
+    const double2* mats;
+};
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cfma(double2 m, double2 a, double2 acc) {
+    acc.x = fma(m.x, a.x, acc.x);
+    acc.x = fma(-m.y, a.y, acc.x);
+    acc.y = fma(m.x, a.y, acc.y);
+    acc.y = fma(m.y, a.x, acc.y);
+    return acc;
+}
+
+__host__ __device__ __forceinline__ uint32_t insert_zero32(uint32_t x, uint32_t pos) {
+    uint32_t lo = x & ((1u << pos) - 1u);
+    return ((x >> pos) << (pos + 1)) | lo;
+}
+__host__ __device__ __forceinline__ uint64_t insert_zero64(uint64_t x, uint32_t pos) {
+    uint64_t lo = x & ((1ull << pos) - 1ull);
+    return ((x >> pos) << (pos + 1)) | lo;
+}
+
+__device__ __forceinline__ uint32_t expand_fixed(uint32_t p, const uint8_t* fix, int nfix) {
+    for (int j = 0; j < nfix; ++j) p = insert_zero32(p, fix[j]);
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gate application on a tile resident in shared memory.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_dense1(double2* tile, const DevOp& op, const double2* mats, int k_tile,
+                                            int tid, int nthreads) {
+    const double2* m = mats + op.mat_off;
+    const double2 m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
+    const uint32_t tbit = 1u << op.tgt[0];
+    const uint32_t cnt = 1u << (k_tile - op.nfix);
+    for (uint32_t p = tid; p < cnt; p += nthreads) {
+        const uint32_t i0 = expand_fixed(p, op.fix, op.nfix) | op.ctrl_tile;
+        const uint32_t i1 = i0 | tbit;
+        const double2 a0 = tile[i0], a1 = tile[i1];
+        double2 b0 = cmul(m00, a0), b1 = cmul(m10, a0);
+        b0 = cfma(m01, a1, b0);
+        b1 = cfma(m11, a1, b1);
+        tile[i0] = b0;
+        tile[i1] = b1;
+    }
+}
+
+__device__ __forceinline__ void tile_dense2(double2* tile, const DevOp& op, const double2* mats, int k_tile,
+                                            int tid, int nthreads) {
+    const double2* m = mats + op.mat_off;
+    const uint32_t bhi = 1u << op.tgt[0], blo = 1u << op.tgt[1];
+    const uint32_t cnt = 1u << (k_tile - op.nfix);
+    for (uint32_t p = tid; p < cnt; p += nthreads) {
+        const uint32_t i0 = expand_fixed(p, op.fix, op.nfix) | op.ctrl_tile;
+        const uint32_t idx[4] = {i0, i0 | blo, i0 | bhi, i0 | bhi | blo};
+        double2 a[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) a[c] = tile[idx[c]];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            double2 acc = cmul(m[r * 4 + 0], a[0]);
+#pragma unroll
+            for (int c = 1; c < 4; ++c) acc = cfma(m[r * 4 + c], a[c], acc);
+            tile[idx[r]] = acc;
+        }
+    }
+}
+
+// 3 <= k <= 6: a group of min(32, 2^k) lanes owns one 2^k-amplitude block; lane r computes row r
+// (and row r+32 when k == 6).  Inputs are read (broadcast) from shared memory, the matrix from
+// global memory through L1.  Slow path: DefGates wider than two qubits only.
+__device__ __forceinline__ void tile_densek(double2* tile, const DevOp& op, const double2* mats, int k_tile,
+                                            int tid, int nthreads) {
+    const int k = op.k;
+    const int dim = 1 << k;
+    const int lanes = dim < 32 ? dim : 32;
+    const int per_warp = 32 / lanes;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    const int sub = lane / lanes, r0 = lane % lanes;
+    const double2* m = mats + op.mat_off;
+    const uint32_t cnt = 1u << (k_tile - op.nfix);
+    uint32_t scat0 = 0, scat1 = 0;       // tile offsets of rows r0 and r0+32
+    for (int j = 0; j < k; ++j) {
+        if ((r0 >> (k - 1 - j)) & 1) scat0 |= 1u << op.tgt[j];
+        if (((r0 + 32) >> (k - 1 - j)) & 1) scat1 |= 1u << op.tgt[j];
+    }
+    const uint32_t stride = (uint32_t)(nwarps * per_warp);
+    const uint32_t rounds = (cnt + stride - 1) / stride;
+    for (uint32_t it = 0; it < rounds; ++it) {
+        const uint32_t g = it * stride + warp * per_warp + sub;
+        const bool active = g < cnt;
+        const uint32_t ib = active ? (expand_fixed(g, op.fix, op.nfix) | op.ctrl_tile) : 0u;
+        double2 acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
+        if (active) {
+            for (int c = 0; c < dim; ++c) {
+                uint32_t sc = 0;
+                for (int j = 0; j < k; ++j)
+                    if ((c >> (k - 1 - j)) & 1) sc |= 1u << op.tgt[j];
+                const double2 a = tile[ib | sc];
+                acc0 = cfma(__ldg(&m[r0 * dim + c]), a, acc0);
+                if (dim == 64) acc1 = cfma(__ldg(&m[(r0 + 32) * dim + c]), a, acc1);
+            }
+        }
+        __syncwarp();
+        if (active) {
+            tile[ib | scat0] = acc0;
+            if (dim == 64) tile[ib | scat1] = acc1;
+        }
+        __syncwarp();
+    }
+}
+
+// A run of consecutive DIAG ops [o, e): one read-modify-write of each amplitude for the whole run.
+__device__ __forceinline__ void tile_diag_run(double2* tile, const DevOp* ops, int o, int e, const uint8_t* op_active,
+                                              const uint8_t* op_outer_idx, const double2* mats, int k_tile, int tid,
+                                              int nthreads) {
+    const uint32_t tile_n = 1u << k_tile;
+    for (uint32_t i = tid; i < tile_n; i += nthreads) {
+        double2 v = tile[i];
+        bool changed = false;
+        for (int j = o; j < e; ++j) {
+            if (!op_active[j]) continue;
+            const DevOp& op = ops[j];
+            if ((i & op.ctrl_tile) != op.ctrl_tile) continue;
+            uint32_t idx = op_outer_idx[j];
+            for (int t = 0; t < op.k; ++t) {
+                const uint8_t loc = op.tgt[t];
+                if (!(loc & 0x80)) idx |= ((i >> loc) & 1u) << (op.k - 1 - t);
+            }
+            v = cmul(__ldg(&mats[op.mat_off + idx]), v);
+            changed = true;
+        }
+        if (changed) tile[i] = v;
+    }
+}
+
+// Applies ops[0..n_ops) to the tile.  Caller guarantees the tile is loaded and synchronised; on
+// return all writes are synchronised.
+__device__ __forceinline__ void tile_apply_ops(double2* tile, const DevOp* ops, int n_ops, const uint8_t* op_active,
+                                               const uint8_t* op_outer_idx, const double2* mats, int k_tile, int tid,
+                                               int nthreads) {
+    int o = 0;
+    while (o < n_ops) {
+        const DevOp& op = ops[o];
+        if (op.kind == DK_DIAG) {
+            int e = o + 1;
+            while (e < n_ops && ops[e].kind == DK_DIAG) ++e;
+            tile_diag_run(tile, ops, o, e, op_active, op_outer_idx, mats, k_tile, tid, nthreads);
+            o = e;
+            __syncthreads();
+            continue;
+        }
+        if (op_active[o]) {                     // CTA-uniform
+            if (op.k == 1) tile_dense1(tile, op, mats, k_tile, tid, nthreads);
+            else if (op.k == 2) tile_dense2(tile, op, mats, k_tile, tid, nthreads);
+            else tile_densek(tile, op, mats, k_tile, tid, nthreads);
+            __syncthreads();
+        }
+        ++o;
+    }
+}
+
+// Shared-memory carve-up: [tile: 2^k double2][ops: n_ops DevOp][active: n_ops u8][outer_idx: n_ops u8][hi_off]
+__host__ __device__ inline size_t tile_smem_bytes(int k, int low, int n_ops) {
+    size_t b = (size_t)16 << k;
+    b += (size_t)n_ops * sizeof(DevOp);
+    b += (((size_t)n_ops * 2 + 15) / 16) * 16;
+    b += (size_t)8 << (k - low);
+    return b;
+}
+
+__global__ void __launch_bounds__(kTileThreads) tile_kernel(double2* __restrict__ state, const TileParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* tile = reinterpret_cast<double2*>(smem_raw);
+    DevOp* ops = reinterpret_cast<DevOp*>(smem_raw + ((size_t)16 << P.k));
+    uint8_t* op_active = reinterpret_cast<uint8_t*>(ops + P.n_ops);
+    uint8_t* op_outer_idx = op_active + P.n_ops;
+    uint64_t* hi_off = reinterpret_cast<uint64_t*>(smem_raw + ((size_t)16 << P.k) + (size_t)P.n_ops * sizeof(DevOp) +
+                                                   (((size_t)P.n_ops * 2 + 15) / 16) * 16);
+    const int tid = threadIdx.x;
+    const int k = P.k, low = P.low;
+
+    // outer bits of this tile: deposit blockIdx into the non-tile positions
+    uint64_t base = 0;
+    {
+        uint64_t t = blockIdx.x;
+        for (int p = 0; p < P.n_local; ++p)
+            if (!((P.tile_mask >> p) & 1ull)) {
+                base |= (t & 1ull) << p;
+                t >>= 1;
+            }
+    }
+    const uint64_t full = base | P.shard_bits;
+
+    const uint32_t n_hi = 1u << (k - low);
+    for (uint32_t j = tid; j < n_hi; j += kTileThreads) {
+        uint64_t off = 0;
+        for (int b = 0; b < k - low; ++b)
+            if ((j >> b) & 1u) off |= 1ull << P.tile_pos[low + b];
+        hi_off[j] = off;
+    }
+    // stage op descriptors + CTA-uniform per-op facts
+    {
+        const uint32_t words = (uint32_t)(P.n_ops * (sizeof(DevOp) / 16));
+        const uint4* src = reinterpret_cast<const uint4*>(P.ops);
+        uint4* dst = reinterpret_cast<uint4*>(ops);
+        for (uint32_t w = tid; w < words; w += kTileThreads) dst[w] = __ldg(&src[w]);
+    }
+    for (int j = tid; j < P.n_ops; j += kTileThreads) {
+        const DevOp* g = &P.ops[j];
+        const uint64_t co = g->ctrl_outer;
+        op_active[j] = ((full & co) == co) ? 1 : 0;
+        uint32_t oi = 0;
+        if (g->kind == DK_DIAG)
+            for (int t = 0; t < g->k; ++t) {
+                const uint8_t loc = g->tgt[t];
+                if (loc & 0x80) oi |= (uint32_t)((full >> (loc & 0x7f)) & 1ull) << (g->k - 1 - t);
+            }
+        op_outer_idx[j] = (uint8_t)oi;
+    }
+    __syncthreads();
+
+    const uint32_t tile_n = 1u << k;
+    const uint32_t low_mask = (1u << low) - 1u;
+    double2* gbase = state + base;
+    for (uint32_t i = tid; i < tile_n; i += kTileThreads) tile[i] = gbase[(i & low_mask) + hi_off[i >> low]];
+    __syncthreads();
+
+    tile_apply_ops(tile, ops, P.n_ops, op_active, op_outer_idx, P.mats, k, tid, kTileThreads);
+
+    for (uint32_t i = tid; i < tile_n; i += kTileThreads) gbase[(i & low_mask) + hi_off[i >> low]] = tile[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused all-qubit dephasing on a vectorised rho: rho[i,j] *= f^popcount((i^j) & mask).
+// ---------------------------------------------------------------------------------------------
+__global__ void dephase_kernel(double2* __restrict__ state, uint64_t n_elems, int n_rho, uint64_t qubit_mask,
+                               uint64_t shard_bits, const double* __restrict__ pow_table) {
+    const uint64_t row_mask = (1ull << n_rho) - 1ull;
+    for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < n_elems;
+         x += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t g = x | shard_bits;
+        const uint64_t col = g & row_mask, row = (g >> n_rho) & row_mask;
+        const int pc = __popcll((row ^ col) & qubit_mask);
+        if (pc) {
+            const double f = pow_table[pc];
+            double2 v = state[x];
+            v.x *= f;
+            v.y *= f;
+            state[x] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reductions, MEASURE, collapse
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block sum (fixed tree); result valid in every thread.
+__device__ __forceinline__ double block_sum(double v, double* scratch /* >= 33 doubles */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double t = lane < nw ? scratch[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) scratch[32] = t;
+    }
+    __syncthreads();
+    const double r = scratch[32];
+    __syncthreads();
+    return r;
+}
+
+// mode 0: sum over amplitudes whose bit `qubit` is 0 of |amp|^2 (qubit < 0: all amplitudes)
+// mode 1: vectorised rho with n_rho qubits: sum over local rows i with bit `qubit` == 0 of Re rho[i,i]
+__device__ __forceinline__ double partial_prob(const double2* __restrict__ state, uint64_t n_elems, int n_local,
+                                               int qubit, int mode, int n_rho, uint64_t shard_bits, uint64_t gtid,
+                                               uint64_t gthreads) {
+    double acc = 0.0;
+    if (mode == 0) {
+        if (qubit < 0 || qubit >= n_local) {
+            // whole shard (caller handles a global qubit by looking at its shard bit)
+            for (uint64_t x = gtid; x < n_elems; x += gthreads) {
+                const double2 a = state[x];
+                acc += a.x * a.x + a.y * a.y;
+            }
+        } else if (qubit < 3) {
+            for (uint64_t x = gtid; x < n_elems; x += gthreads) {
+                const double2 a = state[x];
+                if (!((x >> qubit) & 1ull)) acc += a.x * a.x + a.y * a.y;
+            }
+        } else {
+            const uint64_t half = n_elems >> 1;
+            for (uint64_t h = gtid; h < half; h += gthreads) {
+                const double2 a = state[insert_zero64(h, qubit)];
+                acc += a.x * a.x + a.y * a.y;
+            }
+        }
+    } else {
+        // local rows: the local index is (row_local << n_rho | col) when n_local >= n_rho
+        const uint64_t n_rows_local = n_elems >> n_rho;
+        const uint64_t row_base = shard_bits >> n_rho;      // global row offset of this shard
+        for (uint64_t r = gtid; r < n_rows_local; r += gthreads) {
+            const uint64_t row = row_base | r;
+            if (qubit >= 0 && ((row >> qubit) & 1ull)) continue;
+            acc += state[(r << n_rho) | row].x;
+        }
+    }
+    return acc;
+}
+
+__global__ void prob_partial_kernel(const double2* __restrict__ state, uint64_t n_elems, int n_local, int qubit,
+                                    int mode, int n_rho, uint64_t shard_bits, double* __restrict__ partials) {
+    __shared__ double scratch[33];
+    const uint64_t gtid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t gthreads = (uint64_t)gridDim.x * blockDim.x;
+    double acc = partial_prob(state, n_elems, n_local, qubit, mode, n_rho, shard_bits, gtid, gthreads);
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+__global__ void final_sum_kernel(const double* __restrict__ partials, int n, double* __restrict__ out) {
+    __shared__ double scratch[33];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partials[i];
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) out[0] = acc;
+}
+
+__device__ __forceinline__ void collapse_range(double2* __restrict__ state, uint64_t n_elems, int qubit, int outcome,
+                                               double scale, uint64_t gtid, uint64_t gthreads) {
+    const double2 zero = make_double2(0.0, 0.0);
+    for (uint64_t x = gtid; x < n_elems; x += gthreads) {
+        if ((int)((x >> qubit) & 1ull) == outcome) {
+            double2 a = state[x];
+            a.x *= scale;
+            a.y *= scale;
+            state[x] = a;
+        } else {
+            state[x] = zero;
+        }
+    }
+}
+
+// scale < 0 means "zero the whole shard" (global qubit measured to the other value).
+__global__ void collapse_kernel(double2* __restrict__ state, uint64_t n_elems, int n_local, int qubit, int outcome,
+                                double scale) {
+    const uint64_t gtid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t gthreads = (uint64_t)gridDim.x * blockDim.x;
+    if (qubit >= n_local || qubit < 0) {
+        for (uint64_t x = gtid; x < n_elems; x += gthreads) {
+            double2 a = state[x];
+            if (scale < 0.0) a = make_double2(0.0, 0.0);
+            else { a.x *= scale; a.y *= scale; }
+            state[x] = a;
+        }
+        return;
+    }
+    collapse_range(state, n_elems, qubit, outcome, scale, gtid, gthreads);
+}
+
+// MEASURE as ONE cooperative kernel: reduce -> grid.sync -> decide -> collapse + renormalise.
+// result[0] = outcome, result[1] = p0 (as doubles).
+__global__ void measure_kernel(double2* __restrict__ state, uint64_t n_elems, int n_local, int qubit, double r,
+                               double* __restrict__ partials, double* __restrict__ result) {
+    __shared__ double scratch[33];
+    cg::grid_group grid = cg::this_grid();
+    const uint64_t gtid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t gthreads = (uint64_t)gridDim.x * blockDim.x;
+    double acc = partial_prob(state, n_elems, n_local, qubit, 0, 0, 0, gtid, gthreads);
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+    grid.sync();
+    double tot = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) tot += partials[i];
+    const double p0 = block_sum(tot, scratch);       // same order in every block -> identical value
+    const int outcome = (r < p0) ? 0 : 1;
+    const double scale = 1.0 / sqrt(outcome ? (1.0 - p0) : p0);
+    collapse_range(state, n_elems, qubit, outcome, scale, gtid, gthreads);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        result[0] = (double)outcome;
+        result[1] = p0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sampling: two-level CDF + per-shot binary search
+// ---------------------------------------------------------------------------------------------
+constexpr int kSampleBlockBits = 11;      // 2048 probabilities per CDF block
+
+__device__ __forceinline__ double prob_at(const double2* __restrict__ state, uint64_t i, int mode, int n_rho,
+                                          uint64_t row_base) {
+    if (mode == 0) {
+        const double2 a = state[i];
+        return a.x * a.x + a.y * a.y;
+    }
+    return state[(i << n_rho) | (row_base | i)].x;
+}
+
+// block_sums[b] = sum of the probabilities in block b.  One warp per block.
+__global__ void sample_block_sums_kernel(const double2* __restrict__ state, uint64_t n_probs, int mode, int n_rho,
+                                         uint64_t row_base, double* __restrict__ block_sums, uint64_t n_blocks) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t b = warp; b < n_blocks; b += nwarps) {
+        const uint64_t lo = b << kSampleBlockBits;
+        uint64_t hi = lo + (1ull << kSampleBlockBits);
+        if (hi > n_probs) hi = n_probs;
+        double acc = 0.0;
+        for (uint64_t i = lo + lane; i < hi; i += 32) acc += prob_at(state, i, mode, n_rho, row_base);
+        acc = warp_sum(acc);
+        if (lane == 0) block_sums[b] = acc;
+    }
+}
+
+// In-place inclusive scan of v[0..n) by ONE block (deterministic); out_total[0] = v[n-1] after scan.
+__global__ void scan_inclusive_kernel(double* __restrict__ v, uint64_t n, double* __restrict__ out_total) {
+    __shared__ double chunk_tot[1024];
+    const int t = threadIdx.x, nt = blockDim.x;
+    const uint64_t per = (n + nt - 1) / nt;
+    const uint64_t lo = (uint64_t)t * per;
+    uint64_t hi = lo + per;
+    if (hi > n) hi = n;
+    double acc = 0.0;
+    for (uint64_t i = lo; i < hi; ++i) acc += v[i];
+    chunk_tot[t] = acc;
+    __syncthreads();
+    if (t == 0) {
+        double run = 0.0;
+        for (int i = 0; i < nt; ++i) {
+            const double c = chunk_tot[i];
+            chunk_tot[i] = run;
+            run += c;
+        }
+        out_total[0] = run;
+    }
+    __syncthreads();
+    double run = chunk_tot[t];
+    for (uint64_t i = lo; i < hi; ++i) {
+        run += v[i];
+        v[i] = run;
+    }
+}
+
+// One warp per shot.  target = u * total; block = first b with cdf[b] > target; then walk the block.
+__global__ void sample_kernel(const double2* __restrict__ state, uint64_t n_probs, int mode, int n_rho,
+                              uint64_t row_base, const double* __restrict__ block_cdf, uint64_t n_blocks,
+                              const double* __restrict__ total_ptr, const double* __restrict__ uniforms,
+                              uint64_t n_shots, unsigned long long* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const double total = total_ptr[0];
+    for (uint64_t s = warp; s < n_shots; s += nwarps) {
+        const double target = uniforms[s] * total;
+        uint64_t lo = 0, hi = n_blocks;             // first b in [0, n_blocks) with cdf[b] > target
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (block_cdf[mid] > target) hi = mid; else lo = mid + 1;
+        }
+        uint64_t b = lo < n_blocks ? lo : n_blocks - 1;
+        double run = b ? block_cdf[b - 1] : 0.0;
+        const uint64_t first = b << kSampleBlockBits;
+        uint64_t last = first + (1ull << kSampleBlockBits);
+        if (last > n_probs) last = n_probs;
+        uint64_t found = last - 1;
+        bool done = false;
+        uint64_t last_nonzero = first;
+        for (uint64_t i0 = first; i0 < last && !done; i0 += 32) {
+            const uint64_t i = i0 + lane;
+            const double p = i < last ? prob_at(state, i, mode, n_rho, row_base) : 0.0;
+            double incl = p;                         // warp inclusive scan
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
+            }
+            const double c = run + incl;
+            const unsigned hit = __ballot_sync(0xffffffffu, (i < last) && (c > target));
+            const unsigned nz = __ballot_sync(0xffffffffu, (i < last) && (p > 0.0));
+            if (nz) last_nonzero = i0 + (31 - __clz(nz));
+            if (hit) {
+                found = i0 + (__ffs(hit) - 1);
+                done = true;
+            }
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (!done) found = last_nonzero;             // rounding at the very top of the block
+        if (lane == 0) out[s] = found;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small utilities
+// ---------------------------------------------------------------------------------------------
+__global__ void fill_zero_kernel(double2* __restrict__ state, uint64_t n_elems, int set_amp0) {
+    const double2 zero = make_double2(0.0, 0.0);
+    for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < n_elems;
+         x += (uint64_t)gridDim.x * blockDim.x)
+        state[x] = (x == 0 && set_amp0) ? make_double2(1.0, 0.0) : zero;
+}
+
+__global__ void gather_strided_kernel(const double2* __restrict__ state, uint64_t offset, uint64_t stride,
+                                      uint64_t count, double2* __restrict__ dst) {
+    for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < count;
+         j += (uint64_t)gridDim.x * blockDim.x)
+        dst[j] = state[offset + j * stride];
+}
+
+// half-shard pack / unpack (global<->local qubit exchange): element j of the half whose bit
+// `local_bit` == bit_value lives at insert(j, local_bit, bit_value).
+__global__ void pack_half_kernel(const double2* __restrict__ state, int local_bit, int bit_value, uint64_t off,
+                                 uint64_t count, double2* __restrict__ dst) {
+    const uint64_t vbit = (uint64_t)bit_value << local_bit;
+    for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < count;
+         j += (uint64_t)gridDim.x * blockDim.x)
+        dst[j] = state[insert_zero64(off + j, local_bit) | vbit];
+}
+__global__ void unpack_half_kernel(double2* __restrict__ state, int local_bit, int bit_value, uint64_t off,
+                                   uint64_t count, const double2* __restrict__ src) {
+    const uint64_t vbit = (uint64_t)bit_value << local_bit;
+    for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < count;
+         j += (uint64_t)gridDim.x * blockDim.x)
+        state[insert_zero64(off + j, local_bit) | vbit] = src[j];
+}
+
+}  // namespace qvm

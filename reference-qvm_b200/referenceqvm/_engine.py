@@ -1,0 +1,191 @@
+"""Execution engine shared by the wavefunction / density / unitary QVMs.
+
+Owns the HBM-resident state (a ``DeviceState``), a queue of classified-but-not-yet-applied gates and
+the logical->physical qubit layout.  Gates are queued as the state machine walks the program and
+flushed -- through the fusion planner, one tile-kernel launch per group -- whenever something needs
+the amplitudes (MEASURE, readback, sampling, a classical branch is never such a reason).
+"""
+import os
+
+import numpy as np
+
+from referenceqvm import _native as nat
+from referenceqvm import _planner
+
+_TILE_BITS = int(os.environ.get("QVM_B200_TILE_BITS", "12"))
+_LOW_BITS = int(os.environ.get("QVM_B200_LOW_BITS", "5"))
+
+_classify_cache = {}
+
+
+def compile_gate(matrix, qubits):
+    """(matrix, qubits) -> ClassifiedOp, memoised on the matrix bytes and the qubit tuple."""
+    m = np.ascontiguousarray(matrix, dtype=np.complex128)
+    key = (m.shape[0], m.tobytes(), tuple(qubits))
+    op = _classify_cache.get(key)
+    if op is None:
+        op = nat.classify(m, qubits)
+        if len(_classify_cache) > 65536:
+            _classify_cache.clear()
+        _classify_cache[key] = op
+    return op
+
+
+def validate_qubits(qubits, n_positions):
+    """Index checks of the reference's permutation_arbitrary (unitary_generator.py:200-203);
+    duplicates are rejected too (the reference's duplicate check :205-208 is dead code and a
+    duplicate there ends in an unrelated exception)."""
+    seen = set()
+    for q in qubits:
+        if not (0 <= q < n_positions):
+            raise ValueError("Permutation SWAP index not valid")
+        if q in seen:
+            raise ValueError("Duplicate qubit %d found" % q)
+        seen.add(q)
+
+
+class Engine(object):
+    """Single-GPU engine: every position is local."""
+
+    def __init__(self, n_positions, device=0, tile_bits=None, low_bits=None, _state=None):
+        self.n = int(n_positions)
+        self.device = device
+        self.tile_bits = _TILE_BITS if tile_bits is None else tile_bits
+        self.low_bits = _LOW_BITS if low_bits is None else low_bits
+        self.state = nat.DeviceState(self.n, device) if _state is None else _state
+        self.pending = []
+        self.gates_queued = 0
+        self.groups_launched = 0
+
+    @classmethod
+    def from_state(cls, device_state, tile_bits=None, low_bits=None):
+        """Engine around an existing DeviceState (takes ownership)."""
+        return cls(device_state.n_local, device_state.device, tile_bits, low_bits, _state=device_state)
+
+    # -- lifetime ----------------------------------------------------------------------------
+    def close(self):
+        self.pending = []
+        if self.state is not None:
+            self.state.close()
+            self.state = None
+
+    def adopt(self, device_state):
+        """Replace the state buffer (same shape) -- used by the density QVM's ``_density`` setter."""
+        assert device_state.n_local == self.n
+        self.pending = []
+        self.state.close()
+        self.state = device_state
+
+    # -- state -------------------------------------------------------------------------------
+    def reset(self):
+        self.pending = []
+        self.state.reset_zero(True)
+
+    def set_amplitudes(self, amplitudes):
+        self.pending = []
+        a = np.asarray(amplitudes).reshape(-1)
+        if a.size != (1 << self.n):
+            raise ValueError("state of %d amplitudes does not match %d positions" % (a.size, self.n))
+        self.state.set_state(a)
+
+    def amplitudes(self, offset=0, count=None):
+        self.flush()
+        return self.state.get_state(offset, count)
+
+    def strided(self, offset, stride, count):
+        self.flush()
+        return self.state.get_strided(offset, stride, count)
+
+    def norm2(self):
+        self.flush()
+        return self.state.norm2()
+
+    def clone_state(self):
+        self.flush()
+        return self.state.clone()
+
+    # -- gates -------------------------------------------------------------------------------
+    def queue_matrix(self, matrix, qubits):
+        """Queue a k-qubit matrix on logical qubits (first = most significant, reference order)."""
+        qubits = [int(q) for q in qubits]
+        validate_qubits(qubits, self.n)
+        self.queue(compile_gate(matrix, qubits))
+
+    def queue(self, op):
+        self.gates_queued += 1
+        if op.kind != nat.OP_NOP:
+            self.pending.append(op)
+
+    def flush(self):
+        if not self.pending:
+            return
+        ops, self.pending = self.pending, []
+        for group in _planner.plan(ops, self.n, self.tile_bits, self.low_bits):
+            self.state.apply_group(group.tile, group.ops)
+            self.groups_launched += 1
+
+    # -- measurement -------------------------------------------------------------------------
+    def measure(self, qubit, r):
+        """MEASURE with a host-drawn uniform r: outcome 0 iff r < p0; collapse + renormalise."""
+        self.flush()
+        return self.state.measure(int(qubit), float(r))
+
+    def prob_zero(self, qubit):
+        self.flush()
+        return self.state.prob_zero(int(qubit))
+
+    def density_prob_zero(self, n_rho, qubit):
+        self.flush()
+        return self.state.density_prob_zero(n_rho, int(qubit))
+
+    def sample(self, uniforms, mode=0, n_rho=0):
+        """Inverse-CDF draws of basis-state indices from |psi|^2 (mode 0) or diag(rho) (mode 1)."""
+        self.flush()
+        total = self.state.probs_prepare(mode, n_rho)
+        return self.state.sample(uniforms), total
+
+    def sync(self):
+        self.flush()
+        self.state.sync()
+
+    def stats(self):
+        s = self.state.stats()
+        s["gates_queued"] = self.gates_queued
+        s["groups_launched"] = self.groups_launched
+        return s
+
+
+class DeviceAmplitudes(object):
+    """Lazy, sliceable view of amplitudes that stay in HBM (used when 2^n * 16 B is too large to
+    hand back as one ndarray; reference returns ``self.wf`` itself, qvm_wavefunction.py:367)."""
+
+    def __init__(self, engine):
+        self._engine = engine
+        self.shape = (1 << engine.n,)
+        self.dtype = np.dtype(np.complex128)
+        self.ndim = 1
+        self.size = self.shape[0]
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, key):
+        n = self.shape[0]
+        if isinstance(key, slice):
+            start, stop, step = key.indices(n)
+            if step == 1:
+                return self._engine.amplitudes(start, max(stop - start, 0))
+            if step > 1:
+                cnt = max((stop - start + step - 1) // step, 0)
+                return self._engine.strided(start, step, cnt)
+            raise IndexError("negative steps are not supported")
+        idx = int(key)
+        if idx < 0:
+            idx += n
+        if not (0 <= idx < n):
+            raise IndexError(idx)
+        return self._engine.amplitudes(idx, 1)[0]
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._engine.amplitudes()
+        return a if dtype is None else a.astype(dtype)

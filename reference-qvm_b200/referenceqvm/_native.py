@@ -1,0 +1,362 @@
+"""ctypes binding of libqvm_b200.so -- the only door from the Python host to the CUDA kernels.
+
+Signatures follow ``include/qvm_b200.h`` one to one.  There is deliberately no fallback: if the
+shared object is missing or no CUDA device is present, the first call raises ``NativeError``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqvm_b200.so")
+
+QVM_OK, QVM_ERR_INVALID, QVM_ERR_CUDA, QVM_ERR_NOMEM, QVM_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
+OP_NOP, OP_DENSE, OP_DIAG = 0, 1, 2
+MAX_TARGETS = 6
+MAX_TILE_BITS = 13
+
+
+class NativeError(RuntimeError):
+    """The CUDA library reported a failure (or is not loadable)."""
+
+    def __init__(self, code, message):
+        super(NativeError, self).__init__("libqvm_b200 [%d]: %s" % (code, message))
+        self.code = code
+
+
+class Op(C.Structure):
+    """``qvm_op_t``"""
+    _fields_ = [("kind", C.c_int32), ("k", C.c_int32), ("targets", C.c_int32 * MAX_TARGETS),
+                ("ctrl_mask", C.c_uint64), ("mat_offset", C.c_uint32), ("mat_entries", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    """``qvm_stats_t``"""
+    _fields_ = [(name, C.c_uint64) for name in
+                ("kernel_launches", "gate_ops", "hbm_passes", "hbm_bytes", "h2d_bytes", "d2h_bytes")]
+
+    def as_dict(self):
+        return {name: int(getattr(self, name)) for name, _ in self._fields_}
+
+
+_P = C.c_void_p
+_SIGNATURES = {
+    "qvm_version": (C.c_char_p, []),
+    "qvm_last_error": (C.c_char_p, []),
+    "qvm_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "qvm_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(_P)]),
+    "qvm_create_external": (C.c_int, [C.c_int, C.c_int, _P, C.POINTER(_P)]),
+    "qvm_destroy": (C.c_int, [_P]),
+    "qvm_set_shard": (C.c_int, [_P, C.c_int, C.c_uint64]),
+    "qvm_set_stream": (C.c_int, [_P, _P]),
+    "qvm_set_tile_bits": (C.c_int, [_P, C.c_int, C.c_int]),
+    "qvm_n_local": (C.c_int, [_P]),
+    "qvm_device_ptr": (_P, [_P]),
+    "qvm_stream": (_P, [_P]),
+    "qvm_sync": (C.c_int, [_P]),
+    "qvm_stats": (C.c_int, [_P, C.POINTER(Stats)]),
+    "qvm_stats_reset": (C.c_int, [_P]),
+    "qvm_reset_zero": (C.c_int, [_P, C.c_int]),
+    "qvm_set_state": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P]),
+    "qvm_get_state": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P]),
+    "qvm_get_strided": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
+    "qvm_copy_state": (C.c_int, [_P, _P]),
+    "qvm_norm2": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "qvm_classify": (C.c_int, [C.c_int, _P, _P, C.POINTER(Op), _P]),
+    "qvm_apply": (C.c_int, [_P, C.c_int, _P, _P]),
+    "qvm_apply_group": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, C.c_uint64]),
+    "qvm_dephase_all": (C.c_int, [_P, C.c_int, C.c_uint64, C.c_double]),
+    "qvm_measure": (C.c_int, [_P, C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
+    "qvm_prob_zero": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
+    "qvm_density_prob_zero": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "qvm_collapse": (C.c_int, [_P, C.c_int, C.c_int, C.c_double]),
+    "qvm_probs_prepare": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "qvm_sample": (C.c_int, [_P, C.c_uint64, _P, _P]),
+    "qvm_pack_half": (C.c_int, [_P, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _P]),
+    "qvm_unpack_half": (C.c_int, [_P, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _P]),
+}
+EXPORTED = tuple(sorted(_SIGNATURES))
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library with argtypes/restypes set."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(QVM_ERR_CUDA, "%s is missing: build it with `python reference-qvm_b200/build.py` "
+                                            "(there is no CPU fallback)" % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def last_error():
+    return lib().qvm_last_error().decode("utf-8", "replace")
+
+
+def check(code):
+    if code != QVM_OK:
+        raise NativeError(code, last_error())
+
+
+def device_count():
+    n = C.c_int(0)
+    code = lib().qvm_device_count(C.byref(n))
+    return n.value if code == QVM_OK else 0
+
+
+def _c128(a):
+    return np.ascontiguousarray(a, dtype=np.complex128)
+
+
+class ClassifiedOp(object):
+    """One classified gate: the ``qvm_op_t`` plus its reduced matrix / diagonal."""
+    __slots__ = ("kind", "targets", "ctrl_mask", "mat")
+
+    def __init__(self, kind, targets, ctrl_mask, mat):
+        self.kind = kind
+        self.targets = targets          # tuple of positions, MSB first
+        self.ctrl_mask = ctrl_mask
+        self.mat = mat                  # 1-D complex128 (4^k or 2^k entries)
+
+    def remapped(self, mapping):
+        """Same op with every position p replaced by mapping[p]."""
+        mask, m, p = 0, self.ctrl_mask, 0
+        while m:
+            if m & 1:
+                mask |= 1 << mapping[p]
+            m >>= 1
+            p += 1
+        return ClassifiedOp(self.kind, tuple(mapping[t] for t in self.targets), mask, self.mat)
+
+    @property
+    def ctrl_positions(self):
+        out, m, p = [], self.ctrl_mask, 0
+        while m:
+            if m & 1:
+                out.append(p)
+            m >>= 1
+            p += 1
+        return out
+
+    def __repr__(self):
+        return "ClassifiedOp(%s, targets=%r, ctrl=%r)" % ({0: "NOP", 1: "DENSE", 2: "DIAG"}[self.kind],
+                                                         self.targets, self.ctrl_positions)
+
+
+def classify(matrix, qubits):
+    """``qvm_classify``: matrix (2^k x 2^k) on ``qubits`` (first = MSB) -> ClassifiedOp.
+
+    Shape errors follow the reference's apply_gate (unitary_generator.py:284-300): TypeError."""
+    m = np.asarray(matrix)
+    if m.ndim != 2 or m.shape[0] != m.shape[1]:
+        raise TypeError("Gate array must be two-dimensional and square matrix.")
+    dim = m.shape[0]
+    if dim == 0 or dim & (dim - 1):
+        raise TypeError("Invalid gate size. Must be power of 2! Received {} size".format(m.shape))
+    k = dim.bit_length() - 1
+    if k != len(qubits):
+        raise TypeError("Invalid gate size: %d-qubit matrix applied to %d qubits" % (k, len(qubits)))
+    if k < 1:
+        raise TypeError("Invalid gate size. k-qubit gates supported, for k in [1, num_qubits]")
+    m = _c128(m)
+    q = np.ascontiguousarray(qubits, dtype=np.int32)
+    op = Op()
+    out = np.empty(dim * dim, dtype=np.complex128)
+    code = lib().qvm_classify(k, q.ctypes.data, m.ctypes.data, C.byref(op), out.ctypes.data)
+    if code == QVM_ERR_UNSUPPORTED:
+        raise NotImplementedError(last_error())
+    check(code)
+    return ClassifiedOp(op.kind, tuple(op.targets[j] for j in range(op.k)), int(op.ctrl_mask),
+                        out[:op.mat_entries].copy())
+
+
+class DeviceState(object):
+    """Owner of one ``qvm_t``: a shard of 2^n_local complex128 amplitudes in HBM."""
+
+    def __init__(self, n_local, device=0, external_ptr=None):
+        self._h = _P()
+        self.n_local = int(n_local)
+        self.device = int(device)
+        if external_ptr is None:
+            code = lib().qvm_create(self.n_local, self.device, C.byref(self._h))
+        else:
+            code = lib().qvm_create_external(self.n_local, self.device, _P(external_ptr), C.byref(self._h))
+        if code == QVM_ERR_NOMEM:
+            raise MemoryError(last_error())
+        check(code)
+        self.n_global = 0
+        self.shard_index = 0
+
+    # -- lifetime --------------------------------------------------------------------------
+    def close(self):
+        if self._h:
+            lib().qvm_destroy(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # interpreter shutdown
+            pass
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise NativeError(QVM_ERR_INVALID, "state was closed")
+        return self._h
+
+    def __len__(self):
+        return 1 << self.n_local
+
+    def set_shard(self, n_global, shard_index):
+        check(lib().qvm_set_shard(self.handle, n_global, shard_index))
+        self.n_global, self.shard_index = int(n_global), int(shard_index)
+
+    def set_stream(self, cuda_stream_ptr):
+        check(lib().qvm_set_stream(self.handle, _P(cuda_stream_ptr)))
+
+    def set_tile_bits(self, tile_bits, low_bits):
+        check(lib().qvm_set_tile_bits(self.handle, tile_bits, low_bits))
+
+    def device_ptr(self):
+        return int(lib().qvm_device_ptr(self.handle) or 0)
+
+    def stream_ptr(self):
+        return int(lib().qvm_stream(self.handle) or 0)
+
+    def sync(self):
+        check(lib().qvm_sync(self.handle))
+
+    def stats(self):
+        s = Stats()
+        check(lib().qvm_stats(self.handle, C.byref(s)))
+        return s.as_dict()
+
+    def stats_reset(self):
+        check(lib().qvm_stats_reset(self.handle))
+
+    # -- state I/O -------------------------------------------------------------------------
+    def reset_zero(self, set_amp0=True):
+        check(lib().qvm_reset_zero(self.handle, 1 if set_amp0 else 0))
+
+    def set_state(self, amplitudes, offset=0):
+        a = _c128(np.asarray(amplitudes).reshape(-1))
+        check(lib().qvm_set_state(self.handle, offset, a.size, a.ctypes.data))
+
+    def get_state(self, offset=0, count=None, out=None):
+        count = (len(self) - offset) if count is None else int(count)
+        if out is None:
+            out = np.empty(count, dtype=np.complex128)
+        assert out.dtype == np.complex128 and out.flags.c_contiguous and out.size >= count
+        check(lib().qvm_get_state(self.handle, offset, count, out.ctypes.data))
+        return out
+
+    def get_strided(self, offset, stride, count):
+        out = np.empty(int(count), dtype=np.complex128)
+        check(lib().qvm_get_strided(self.handle, offset, stride, count, out.ctypes.data))
+        return out
+
+    def copy_from(self, other):
+        check(lib().qvm_copy_state(self.handle, other.handle))
+
+    def clone(self):
+        dup = DeviceState(self.n_local, self.device)
+        if self.n_global:
+            dup.set_shard(self.n_global, self.shard_index)
+        dup.copy_from(self)
+        return dup
+
+    def norm2(self):
+        v = C.c_double(0.0)
+        check(lib().qvm_norm2(self.handle, C.byref(v)))
+        return v.value
+
+    # -- gates -----------------------------------------------------------------------------
+    def apply(self, matrix, qubits):
+        """One gate through ``qvm_apply`` (library picks the tile)."""
+        m = _c128(matrix)
+        q = np.ascontiguousarray(qubits, dtype=np.int32)
+        code = lib().qvm_apply(self.handle, q.size, q.ctypes.data, m.ctypes.data)
+        if code == QVM_ERR_INVALID:
+            raise ValueError(last_error())
+        if code == QVM_ERR_UNSUPPORTED:
+            raise NotImplementedError(last_error())
+        check(code)
+
+    def apply_group(self, tile_bits, ops):
+        """A run of ClassifiedOps in one HBM pass (``qvm_apply_group``)."""
+        ops = [o for o in ops if o.kind != OP_NOP]
+        if not ops:
+            return
+        arr = (Op * len(ops))()
+        total = sum(o.mat.size for o in ops)
+        pool = np.empty(max(total, 1), dtype=np.complex128)
+        off = 0
+        for i, o in enumerate(ops):
+            a = arr[i]
+            a.kind, a.k, a.ctrl_mask = o.kind, len(o.targets), o.ctrl_mask
+            for j in range(MAX_TARGETS):
+                a.targets[j] = o.targets[j] if j < len(o.targets) else -1
+            a.mat_offset, a.mat_entries = off, o.mat.size
+            pool[off:off + o.mat.size] = o.mat
+            off += o.mat.size
+        tb = np.ascontiguousarray(sorted(tile_bits), dtype=np.int32)
+        code = lib().qvm_apply_group(self.handle, tb.size, tb.ctypes.data, len(ops), C.cast(arr, _P),
+                                     pool.ctypes.data, total)
+        if code == QVM_ERR_INVALID:
+            raise ValueError(last_error())
+        if code == QVM_ERR_UNSUPPORTED:
+            raise NotImplementedError(last_error())
+        check(code)
+
+    def dephase_all(self, n_rho, qubit_mask, factor):
+        check(lib().qvm_dephase_all(self.handle, n_rho, qubit_mask, factor))
+
+    # -- measurement / sampling ------------------------------------------------------------
+    def measure(self, qubit, r):
+        """Single-kernel MEASURE: returns (outcome, p0)."""
+        outcome, p0 = C.c_int(0), C.c_double(0.0)
+        code = lib().qvm_measure(self.handle, qubit, r, C.byref(outcome), C.byref(p0))
+        if code == QVM_ERR_INVALID:
+            raise ValueError(last_error())
+        check(code)
+        return outcome.value, p0.value
+
+    def prob_zero(self, qubit):
+        v = C.c_double(0.0)
+        check(lib().qvm_prob_zero(self.handle, qubit, C.byref(v)))
+        return v.value
+
+    def density_prob_zero(self, n_rho, qubit):
+        v = C.c_double(0.0)
+        check(lib().qvm_density_prob_zero(self.handle, n_rho, qubit, C.byref(v)))
+        return v.value
+
+    def collapse(self, qubit, outcome, scale):
+        check(lib().qvm_collapse(self.handle, qubit, outcome, scale))
+
+    def probs_prepare(self, mode=0, n_rho=0):
+        v = C.c_double(0.0)
+        check(lib().qvm_probs_prepare(self.handle, mode, n_rho, C.byref(v)))
+        return v.value
+
+    def sample(self, uniforms):
+        u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        out = np.empty(u.size, dtype=np.uint64)
+        check(lib().qvm_sample(self.handle, u.size, u.ctypes.data, out.ctypes.data))
+        return out
+
+    # -- exchange plumbing -------------------------------------------------------------------
+    def pack_half(self, local_bit, bit_value, elem_offset, count, device_dst_ptr):
+        check(lib().qvm_pack_half(self.handle, local_bit, bit_value, elem_offset, count, _P(device_dst_ptr)))
+
+    def unpack_half(self, local_bit, bit_value, elem_offset, count, device_src_ptr):
+        check(lib().qvm_unpack_half(self.handle, local_bit, bit_value, elem_offset, count, _P(device_src_ptr)))

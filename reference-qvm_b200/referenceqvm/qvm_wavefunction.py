@@ -1,0 +1,229 @@
+"""Wavefunction QVM whose state lives in HBM.
+
+Public surface and semantics follow reference ``referenceqvm/qvm_wavefunction.py``:
+``wavefunction`` (:323-367), ``run`` (:266-285), ``run_and_measure`` (:287-321), ``measurement``
+(:96-129), ``transition`` with ``pre``/``post`` hooks (:238-264).  What changed is where the work
+happens:
+
+* Gate branch (:158-162): instead of ``unitary = tensor_gates(...); self.wf = unitary.dot(self.wf)``
+  the gate is classified and queued; queued gates are fused into one-HBM-pass groups and run by
+  the sm_100a tile kernel when the amplitudes are next needed.
+* Measurement branch (:147-156): one cooperative kernel (reduce, decide, collapse, renormalise).
+  The uniform is drawn on the host from ``np.random.random()`` exactly once per MEASURE, in program
+  order, so seeded programs reproduce the reference's classical memory draw for draw.
+* ``run`` / ``run_and_measure``: the reference re-simulates the whole program per trial.  When
+  that is provably equivalent to sampling one final state (no MEASURE in the program, or a purely
+  terminal block of MEASUREs and no control flow) the program is simulated once and the trials
+  are drawn by the prefix-sum + binary-search kernel; otherwise the per-trial loop is kept.
+"""
+import os
+
+import numpy as np
+
+from pyquil.quil import Program  # noqa: F401  (kept for parity with the reference's namespace)
+from pyquil.quilbase import (Gate, Halt, Jump, JumpConditional, JumpTarget, Measurement)
+from pyquil.wavefunction import Wavefunction
+
+from referenceqvm import _engine
+from referenceqvm.gates import utility_gates  # noqa: F401
+from referenceqvm.qam import QAM
+from referenceqvm.unitary_generator import lifted_gate, resolve_gate, tensor_gates, value_get  # noqa: F401
+
+# Above this many qubits ``wavefunction()`` hands back a lazy, sliceable view of the device
+# amplitudes instead of one host ndarray (2^31 amplitudes = 32 GiB of host memory).
+LAZY_QUBITS = int(os.environ.get("QVM_B200_LAZY_QUBITS", "30"))
+
+
+class QVM_Wavefunction(QAM):
+    """Supports run(), run_and_measure() and wavefunction()."""
+
+    def __init__(self, num_qubits=None, program=None, program_counter=None,
+                 classical_memory=None, gate_set=None, defgate_set=None):
+        super(QVM_Wavefunction, self).__init__(num_qubits=num_qubits, program=program,
+                                               program_counter=program_counter,
+                                               classical_memory=classical_memory,
+                                               gate_set=gate_set, defgate_set=defgate_set)
+        self.all_inst = True
+        self._engine = None
+        self.device = int(os.environ.get("QVM_B200_DEVICE", "0"))
+        #: set False to force the reference's per-trial re-simulation in run()/run_and_measure()
+        self.sampling_fast_path = True
+
+    # -- device state --------------------------------------------------------------------------
+    def _fresh_engine(self):
+        """|0...0> on the device, re-using the allocation when the register size is unchanged."""
+        if self._engine is not None and self._engine.n != self.num_qubits:
+            self._engine.close()
+            self._engine = None
+        if self._engine is None:
+            self._engine = self._make_engine(self.num_qubits)
+        self._engine.reset()
+        return self._engine
+
+    def _make_engine(self, n):
+        return _engine.Engine(n, device=self.device)
+
+    @property
+    def wf(self):
+        """Host copy of the amplitudes (the reference keeps ``self.wf`` as an ndarray)."""
+        if self._engine is None:
+            return None
+        return self._engine.amplitudes()
+
+    @wf.setter
+    def wf(self, amplitudes):
+        if amplitudes is None:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = None
+            return
+        amplitudes = np.asarray(amplitudes).reshape(-1)
+        n = int(amplitudes.size).bit_length() - 1
+        if self._engine is None or self._engine.n != n:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = self._make_engine(n)
+        self._engine.set_amplitudes(amplitudes)
+
+    # -- transitions -----------------------------------------------------------------------------
+    def measurement(self, qubit_index, psi=None):
+        """Measure ``qubit_index`` of the device state: returns (outcome, p0).
+
+        The reference returns (outcome, collapse operator) and lets the caller multiply
+        (qvm_wavefunction.py:96-129); here the kernel collapses in place.  ``psi`` is accepted for
+        signature compatibility: a host vector is uploaded first."""
+        if psi is not None:
+            self.wf = psi
+        return self._engine.measure(qubit_index, np.random.random())
+
+    def _transition(self, instruction):
+        if isinstance(instruction, Measurement):
+            outcome, _ = self.measurement(value_get(instruction.qubit))
+            self.classical_memory[value_get(instruction.classical_reg)] = outcome
+            self.program_counter += 1
+        elif isinstance(instruction, Gate):
+            matrix, qubits = resolve_gate(self.gate_set, self.defgate_set, instruction)
+            self._engine.queue_matrix(matrix, qubits)
+            self.program_counter += 1
+        elif not self._classical_transition(instruction):
+            raise self._unsupported(instruction)
+
+    def transition(self, instruction):
+        """One full transition including the (empty) pre/post noise hooks; True when halted."""
+        self.pre()
+        self._transition(instruction)
+        self.post()
+        return self.program_counter == len(self.program)
+
+    def pre(self):
+        pass
+
+    def post(self):
+        pass
+
+    # -- public API --------------------------------------------------------------------------------
+    def _address_mask(self, classical_addresses):
+        if classical_addresses is None:
+            return None
+        assert len(set(classical_addresses)) == len(classical_addresses)
+        if np.min(classical_addresses) < 0 or np.max(classical_addresses) >= len(self.classical_memory):
+            raise RuntimeError("Improper classical memory access outside allocated classical memory range.")
+        return np.array(classical_addresses)
+
+    def _simulate(self, pyquil_program, classical_addresses):
+        self.load_program(pyquil_program)
+        mask = self._address_mask(classical_addresses)
+        self._fresh_engine()
+        self.kernel()
+        return mask
+
+    def wavefunction(self, pyquil_program, classical_addresses=None):
+        """Simulate a program; returns (Wavefunction, [classical bits at ``classical_addresses``])."""
+        mask = self._simulate(pyquil_program, classical_addresses)
+        memory = self.classical_memory if mask is None else self.classical_memory[mask]
+        results = [int(x) for x in memory]
+        if self.num_qubits > LAZY_QUBITS:
+            self._engine.flush()
+            return Wavefunction(_engine.DeviceAmplitudes(self._engine)), results
+        return Wavefunction(self._engine.amplitudes()), results
+
+    def _terminal_measure_block(self, program):
+        """Index where a purely terminal run of MEASUREs starts, or None when sampling the final
+        state would not be equivalent to re-running the program per trial."""
+        instrs = list(program)
+        if any(isinstance(i, (Jump, JumpConditional, JumpTarget, Halt)) for i in instrs):
+            return None
+        first = next((k for k, i in enumerate(instrs) if isinstance(i, Measurement)), None)
+        if first is None:
+            return len(instrs)
+        if not all(isinstance(i, Measurement) for i in instrs[first:]):
+            return None
+        return first
+
+    def run(self, pyquil_program, classical_addresses=None, trials=1):
+        """Run a program ``trials`` times; list of the classical bits at ``classical_addresses``."""
+        if not isinstance(pyquil_program, Program):
+            raise TypeError("I can only generate from pyQuil programs")
+        split = self._terminal_measure_block(pyquil_program) if self.sampling_fast_path else None
+        if split is not None and split == len(pyquil_program) and trials > 1:
+            # no MEASURE at all: every trial is the same deterministic run
+            _, classical_vals = self.wavefunction(pyquil_program, classical_addresses=classical_addresses)
+            return [list(classical_vals) for _ in range(trials)]
+        if split is None or trials <= 1:
+            results = []
+            for _ in range(trials):
+                _, classical_vals = self.wavefunction(pyquil_program, classical_addresses=classical_addresses)
+                results.append(classical_vals)
+            return results
+
+        # simulate the measurement-free prefix once, then sample the terminal MEASURE block
+        self.load_program(pyquil_program)
+        mask = self._address_mask(classical_addresses)
+        self._fresh_engine()
+        while self.program_counter < split:
+            self.transition(self.current_instruction())
+        indices, _ = self._engine.sample(np.random.random_sample(trials))
+        memory = np.repeat(self.classical_memory[None, :], trials, axis=0)
+        for instr in list(pyquil_program)[split:]:
+            q, c = value_get(instr.qubit), value_get(instr.classical_reg)
+            memory[:, c] = (indices >> np.uint64(q)) & np.uint64(1)
+        self.program_counter = len(self.program)
+        self.classical_memory = memory[-1].copy()
+        picked = memory if mask is None else memory[:, mask]
+        return picked.astype(np.int64).tolist()
+
+    def run_and_measure(self, pyquil_program, qubits=None, trials=1):
+        """Simulate, then measure ``qubits`` (in the given order) ``trials`` times.
+
+        Qubits beyond the program's register read 0 (reference :316-317)."""
+        if qubits is None:
+            qubits = []
+        elif type(qubits) is not list:
+            raise TypeError("Must pass in qubit indices as list")
+        if not isinstance(pyquil_program, Program):
+            raise TypeError("I can only generate from pyQuil programs")
+
+        deterministic = not any(isinstance(i, Measurement) for i in pyquil_program)
+        if self.sampling_fast_path and deterministic and trials > 1 and len(qubits) > 0:
+            self._simulate(pyquil_program, None)
+            indices, _ = self._engine.sample(np.random.random_sample(trials))
+            cols = []
+            for q in qubits:
+                if q < self.num_qubits:
+                    cols.append(((indices >> np.uint64(q)) & np.uint64(1)).astype(np.int64))
+                else:
+                    cols.append(np.zeros(trials, dtype=np.int64))
+            return np.stack(cols, axis=1).tolist()
+
+        results = []
+        for _ in range(trials):
+            self._simulate(pyquil_program, None)
+            trial_results = []
+            for qubit_index in qubits:
+                if qubit_index < self.num_qubits:
+                    measured_val, _ = self._engine.measure(qubit_index, np.random.random())
+                else:
+                    measured_val = 0
+                trial_results.append(measured_val)
+            results.append(trial_results)
+        return results

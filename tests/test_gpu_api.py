@@ -1,0 +1,481 @@
+"""GPU parity, API level: QVMConnection(...).wavefunction / run / run_and_measure / density /
+unitary against (a) fixtures produced by the unmodified reference (tests/golden/) and (b) the
+reference's own test-suite, re-expressed here test for test (file:line cited per test)."""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+from pyquil.gates import (CNOT, CZ, FALSE, H, HALT, I, NOP, PHASE, RX, RY, RZ, TRUE, WAIT, X, Y, Z)
+from pyquil.quil import Program
+
+from _programs import load_golden, oracle_ops, program_from_json, spec_program
+from oracle import qvm_oracle as orc
+from referenceqvm import gates as G
+from referenceqvm.api import QVMConnection
+from referenceqvm.qvm_density import INFINITY, NoiseModel
+from referenceqvm.unitary_generator import apply_gate, lifted_gate, tensor_gates
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+# ---- golden fixtures (reference outputs) -------------------------------------------------------
+def test_golden_wavefunctions(qvm):
+    meta, arr = load_golden("wavefunctions")
+    for case in meta:
+        wf, _ = qvm.wavefunction(program_from_json(case["program"]))
+        assert qvm.num_qubits == case["n"]
+        err = np.max(np.abs(np.asarray(wf.amplitudes) - arr[case["name"]]))
+        assert err < TOL, (case["name"], err)
+
+
+def test_golden_seeded_measurement(qvm):
+    """Identical classical memory, collapsed state and RNG stream position for seeded programs."""
+    meta, arr = load_golden("measure")
+    done = 0
+    for case in meta:
+        key = case["key"]
+        if key + ":wf" not in arr.files:
+            continue
+        np.random.seed(case["seed"])
+        wf, mem = qvm.wavefunction(program_from_json(case["program"]))
+        nxt = np.random.random()
+        assert mem[:16] == arr[key + ":mem"].tolist(), key
+        assert nxt == arr[key + ":next"][0], key
+        assert np.max(np.abs(wf.amplitudes - arr[key + ":wf"])) < TOL, key
+        done += 1
+    assert done >= 25
+
+
+def test_golden_run_streams_with_per_trial_path(qvm):
+    meta, arr = load_golden("measure")
+    progs = {c["name"]: c for c in meta}
+    qvm.sampling_fast_path = False
+    try:
+        np.random.seed(42)
+        res = qvm.run(program_from_json(progs["biased"]["program"]), [2, 3, 4], trials=50)
+        assert np.array_equal(np.asarray(res), arr["run_biased@42"])
+        case = progs["ram_random4"]
+        np.random.seed(43)
+        res = qvm.run_and_measure(program_from_json(case["program"]), case["qubits"], trials=case["trials"])
+        assert np.array_equal(np.asarray(res), arr["ram_random4@43"])
+    finally:
+        qvm.sampling_fast_path = True
+
+
+def test_golden_density():
+    meta, arr = load_golden("density")
+    done = 0
+    for case in meta:
+        if "program" not in case:
+            continue
+        noise = None
+        if case["noise"] is not None:
+            noise = NoiseModel(**{k: (INFINITY if v == "inf" else v) for k, v in case["noise"].items()})
+        qvm = QVMConnection(type_trans="density", noise_model=noise)
+        if "seed" in case:
+            np.random.seed(case["seed"])
+        rho = qvm.density(program_from_json(case["program"]))
+        err = np.max(np.abs(np.asarray(rho.todense()) - arr[case["name"]]))
+        assert err < TOL, (case["name"], err)
+        if case["name"] + ":mem" in arr.files:
+            assert qvm.classical_memory[:8].astype(int).tolist() == arr[case["name"] + ":mem"].tolist()
+        done += 1
+    assert done >= 17
+
+
+def test_golden_apply_kraus():
+    meta, arr = load_golden("density")
+    rho0 = arr["kraus_rho0"]
+    for case in meta:
+        if "channel" not in case:
+            continue
+        qvm = QVMConnection(type_trans="density")
+        qvm._density = sps.csc_matrix(rho0)
+        qvm.num_qubits = case["n"]
+        out = qvm.apply_kraus(G.noise_gates[case["channel"]](case["p"]), case["qubit"])
+        assert np.max(np.abs(np.asarray(out.todense()) - arr[case["name"]])) < TOL, case["name"]
+        assert np.array_equal(np.asarray(qvm._density.todense()), rho0)       # input left untouched
+
+
+def test_golden_sampling_streams():
+    meta, arr = load_golden("sampling")
+    for case in meta:
+        qvm = QVMConnection(type_trans="density")
+        np.random.seed(case["seed"])
+        prog = program_from_json(case["program"])
+        if case["name"] == "density_run":
+            res = qvm.run(prog, case["addresses"], trials=case["trials"])
+            assert np.array_equal(np.asarray(res).astype(np.int8), arr["density_run:draws"])
+            assert all(r.dtype == bool for r in res)
+            continue
+        res = np.asarray(qvm.run_and_measure(prog, trials=case["trials"]), dtype=np.int8)
+        want = arr[case["name"] + ":draws"]
+        assert res.shape == want.shape
+        assert np.sum(np.any(res != want, axis=1)) <= 1, case["name"]      # cdf-boundary ties only
+
+
+def test_golden_unitary(qvm_unitary):
+    meta, arr = load_golden("unitary")
+    for case in meta:
+        u = qvm_unitary.unitary(program_from_json(case["program"]))
+        assert u.shape == arr[case["name"]].shape
+        assert np.max(np.abs(u - arr[case["name"]])) < TOL, case["name"]
+
+
+def test_golden_operators():
+    meta, arr = load_golden("operators")
+    for case in meta:
+        if "lift" in case:
+            assert np.array_equal(lifted_gate(case["lift"], G.SWAP, case["n"]).toarray(), arr[case["key"]])
+        elif "vec" in case:
+            got = apply_gate(arr["G%d" % case["k"]], case["args"], case["n"]).dot(arr[case["vec"]])
+            assert np.max(np.abs(got - arr[case["key"]])) < 1e-12 * np.max(np.abs(arr[case["key"]]))
+        else:
+            got = apply_gate(arr["G%d" % case["k"]], case["args"], case["n"]).toarray()
+            assert np.max(np.abs(got - arr[case["key"]])) < TOL, case["key"]
+
+
+# ---- reference tests/test_unitary_generator.py ----------------------------------------------------
+def test_lifted_swap():                      # :14-53
+    assert np.allclose(lifted_gate(0, G.SWAP, 2).toarray(), G.SWAP)
+    assert np.allclose(lifted_gate(0, G.SWAP, 3).toarray(), np.kron(np.eye(2), G.SWAP))
+    assert np.allclose(lifted_gate(0, G.SWAP, 4).toarray(), np.kron(np.eye(4), G.SWAP))
+    assert np.allclose(lifted_gate(1, G.SWAP, 3).toarray(), np.kron(G.SWAP, np.eye(2)))
+    assert np.allclose(lifted_gate(1, G.SWAP, 4).toarray(), np.kron(np.eye(2), np.kron(G.SWAP, np.eye(2))))
+    assert np.allclose(lifted_gate(2, G.SWAP, 4).toarray(), np.kron(G.SWAP, np.eye(4)))
+    assert np.allclose(lifted_gate(8, G.SWAP, 10).toarray(), np.kron(G.SWAP, np.eye(2 ** 8)))
+
+
+def test_two_qubit_gates():                  # :56-136 argument-order convention
+    P0, P1 = G.P0, G.P1
+    assert np.allclose(apply_gate(G.CNOT, [1, 0], 2).toarray(), np.kron(P0, np.eye(2)) + np.kron(P1, G.X))
+    assert np.allclose(apply_gate(G.CNOT, [0, 1], 2).toarray(), np.kron(np.eye(2), P0) + np.kron(G.X, P1))
+    assert np.allclose(apply_gate(G.CNOT, [2, 1], 3).toarray(), np.kron(G.CNOT, np.eye(2)))
+    v = np.kron(np.eye(2), G.SWAP)
+    far = v.dot(np.kron(G.CNOT, np.eye(2))).dot(v)            # CNOT(2, 0) via swap conjugation
+    assert np.allclose(apply_gate(G.CNOT, [2, 0], 3).toarray(), far)
+    assert np.allclose(apply_gate(G.ISWAP, [0, 1], 3).toarray(), np.kron(np.eye(2), G.ISWAP))
+    assert np.allclose(apply_gate(G.SWAP, [0, 2], 3).toarray(), apply_gate(G.SWAP, [2, 0], 3).toarray())
+
+
+def test_single_qubit_lifting_and_tensor_gates():     # :139-213
+    for n in (4, 5):
+        for q in range(n):
+            want = np.kron(np.eye(2 ** (n - 1 - q)), np.kron(G.H, np.eye(2 ** q)))
+            assert np.allclose(apply_gate(G.H, [q], n).toarray(), want)
+    t = tensor_gates(G.gate_matrix, {}, H(1), 3)
+    assert np.allclose(t.toarray(), np.kron(np.eye(2), np.kron(G.H, np.eye(2))))
+    t = tensor_gates(G.gate_matrix, {}, RX(0.2, 3), 4)
+    assert np.allclose(t.toarray(), np.kron(G.RX(0.2), np.eye(8)))
+    t = tensor_gates(G.gate_matrix, {}, CNOT(0, 1), 2)
+    assert np.allclose(t.toarray(), np.kron(np.eye(2), G.P0) + np.kron(G.X, G.P1))
+
+
+# ---- reference tests/test_wavefunction.py, test_system.py, test_arbitrary_state_prep.py ------------
+def test_belltest(qvm):                      # test_wavefunction.py:27-36
+    bellout, _ = qvm.wavefunction(Program().inst([H(0), CNOT(0, 1)]))
+    bell = np.zeros(4)
+    bell[0] = bell[-1] = 1.0 / np.sqrt(2)
+    assert np.allclose(bellout.amplitudes, bell)
+
+
+def test_occupation_basis(qvm):              # :38-44
+    state = np.zeros(16)
+    state[3] = 1.0
+    wf, _ = qvm.wavefunction(Program().inst([X(0), X(1), I(2), I(3)]))
+    assert np.allclose(wf.amplitudes, state)
+
+
+def test_exp_circuit_norm(qvm):              # :46-68 (shim-dependent: pyquil.paulis.exponentiate)
+    from pyquil.paulis import PauliTerm, exponentiate
+    op = PauliTerm("X", 1, -0.25) * PauliTerm("Y", 2)
+    op += PauliTerm("Y", 1, 0.25) * PauliTerm("Y", 2)
+    op += PauliTerm("Y", 1, 0.25) * PauliTerm("X", 2)
+    op += PauliTerm("X", 1, 0.25) * PauliTerm("X", 2)
+    op += PauliTerm("I", 0, 1.0)
+    prog = Program()
+    for term in op.terms:
+        prog += exponentiate(term)
+    wf, _ = qvm.wavefunction(prog)
+    a = np.reshape(wf.amplitudes, -1)
+    assert np.allclose(a.dot(np.conj(a).T), 1.0)
+
+
+QAOA2 = [RY(np.pi / 2, 0), RX(np.pi, 0), RY(np.pi / 2, 1), RX(np.pi, 1), CNOT(0, 1), RX(-np.pi / 2, 1),
+         RY(4.71572463191, 1), RX(np.pi / 2, 1), CNOT(0, 1), RX(-2 * 2.74973750579, 0), RX(-2 * 2.74973750579, 1)]
+QAOA2_WF = [0.00167784 + 1.00210180e-05 * 1j, 0.50000000 - 4.99997185e-01 * 1j,
+            0.50000000 - 4.99997185e-01 * 1j, 0.00167784 + 1.00210180e-05 * 1j]
+
+
+def test_qaoa_circuit(qvm):                  # :71-81
+    wf, _ = qvm.wavefunction(Program().inst(QAOA2))
+    assert np.allclose(wf.amplitudes, QAOA2_WF)
+
+
+def test_against_cloud_fixtures(qvm):        # test_system.py:7-23 + data_containers QFT-8
+    p = Program(H(0))
+    assert len(qvm.run(p, classical_addresses=[0], trials=10)) == 10
+    wf, _ = qvm.wavefunction(p)
+    assert np.allclose([0.70710678, 0.70710678], wf.amplitudes)
+    wf, _ = qvm.wavefunction(spec_program(orc.qft_spec(8)))
+    assert np.allclose(wf.amplitudes, np.full(256, 0.0625))
+
+
+# ---- reference tests/test_measurement.py -------------------------------------------------------------
+def test_measurement(qvm):                   # :6-17
+    p = Program().inst(X(0))
+    results = qvm.run_and_measure(p)
+    assert len(results) == 1 and len(results[0]) == 0
+    results = qvm.run_and_measure(p, qubits=[0, 1, 2, 3])
+    assert len(results) == 1 and len(results[0]) == 4
+    assert np.allclose(results, [1, 0, 0, 0])
+    with pytest.raises(TypeError):
+        qvm.run_and_measure(p, qubits=(0, 1))
+
+
+def test_many_sample_measurements(qvm):      # :20-26
+    prog = Program().inst(H(0)).measure(0, [0]).measure(0, [1])
+    for fast in (True, False):
+        qvm.sampling_fast_path = fast
+        samples = 1000 if fast else 200
+        result = qvm.run(prog, [0, 1], trials=samples)
+        assert len(result) == samples and all(x[0] == x[1] for x in result)
+        bias = sum(x[0] for x in result) / float(samples)
+        assert np.isclose(0.5, bias, atol=0.12 if not fast else 0.05, rtol=0.05)
+    qvm.sampling_fast_path = True
+
+
+def test_biased_coin(qvm):                   # :29-34
+    prog = Program().inst(RX(np.pi / 3, 0))
+    results = qvm.run_and_measure(prog, qubits=[0], trials=1000)
+    assert np.isclose(sum(x[0] for x in results) / 1000.0, 0.25, atol=0.05, rtol=0.05)
+
+
+def test_run_and_measure_chi_squared_against_reference_distribution(qvm):
+    spec = orc.random_circuit_spec(5, 6, 77)
+    psi, _ = orc.fast_run_wavefunction(oracle_ops(spec_program(spec)), 5)
+    probs = psi.real ** 2 + psi.imag ** 2
+    shots = 100000
+    np.random.seed(5)
+    res = np.asarray(qvm.run_and_measure(spec_program(spec), qubits=[0, 1, 2, 3, 4, 7], trials=shots))
+    assert res.shape == (shots, 6) and not res[:, 5].any()
+    idx = res[:, :5].dot(1 << np.arange(5))
+    counts = np.bincount(idx, minlength=32)
+    keep = probs > 1e-12
+    chi2 = np.sum((counts[keep] - shots * probs[keep]) ** 2 / (shots * probs[keep]))
+    assert counts[~keep].sum() == 0 and chi2 < 75.0
+
+
+# ---- reference tests/test_controlflow.py, test_qvm_funcs.py ---------------------------------------------
+def test_if_then(qvm):                       # :6-21
+    def build():
+        main = Program().inst(X(0))
+        main.if_then(0, Program().inst(X(0)), Program().inst())
+        return main
+    assert qvm.run_and_measure(Program().inst(TRUE(0)) + build(), [0])[0][0] == 0
+    assert qvm.run_and_measure(Program().inst(FALSE(0)) + build(), [0])[0][0] == 1
+
+
+def test_while(qvm):                         # :24-37
+    loop = Program(TRUE([2])).while_do(2, Program(X(0), H(0)).measure(0, 2))
+    _, cregs = qvm.wavefunction(loop, [2])
+    assert cregs[0] == False  # noqa: E712
+
+
+def test_halt(qvm):                          # :40-50
+    prog = Program(X(0))
+    prog.inst(HALT)
+    prog.inst(X(0))
+    assert qvm.run_and_measure(prog, [0])[0][0] == 1
+    assert qvm.run_and_measure(Program(X(0)).inst(X(0)), [0])[0][0] == 0
+
+
+def test_unsupported_instructions(qvm):      # :53-68
+    for bad in (NOP, WAIT):
+        prog = Program(bad)
+        with pytest.raises(TypeError):
+            qvm.wavefunction(prog)
+        with pytest.raises(TypeError):
+            qvm.run(prog)
+        with pytest.raises(TypeError):
+            qvm.run_and_measure(prog)
+
+
+def test_identify_bits_through_api(qvm):     # test_qvm_funcs.py:5-31
+    p = Program()
+    for i in range(5):
+        p.inst(X(i))
+    for i in range(670):
+        p.inst(TRUE(i))
+    qvm.wavefunction(p)
+    qvm.run(p)
+    qvm.run_and_measure(p)
+    assert qvm.num_qubits == 5 and len(qvm.classical_memory) == 670
+    p = Program()
+    for i in range(670):
+        p.inst(TRUE(i))
+    wf, mem = qvm.wavefunction(p)
+    qvm.run(p)
+    qvm.run_and_measure(p)
+    assert qvm.num_qubits == 0 and len(qvm.classical_memory) == 670
+    assert np.allclose(wf.amplitudes, [1.0]) and sum(mem) == 670
+
+
+def test_classical_address_checks(qvm):      # qvm_wavefunction.py:340-347
+    p = Program(X(0)).measure(0, [3])
+    _, mem = qvm.wavefunction(p, [3, 0])
+    assert mem == [1, 0]
+    with pytest.raises(RuntimeError):
+        qvm.wavefunction(p, [512])
+    with pytest.raises(AssertionError):
+        qvm.wavefunction(p, [1, 1])
+    with pytest.raises(ValueError):
+        qvm.wavefunction(Program().inst(("NOSUCHGATE", 0)))
+
+
+# ---- reference tests/test_density.py -------------------------------------------------------------------
+def random_1q_density():
+    state = np.random.random(2) + 1j * np.random.random()
+    state /= np.sqrt(np.conj(state).T.dot(state))
+    state = state.reshape((-1, 1))
+    return state.dot(np.conj(state).T)
+
+
+def test_qaoa_density():                     # :36-51
+    wf_true = np.reshape(np.array(QAOA2_WF), (4, 1))
+    rho_true = np.dot(wf_true, np.conj(wf_true).T)
+    rho = QVMConnection(type_trans="density").density(Program().inst(QAOA2))
+    assert np.isclose(rho_true, rho.todense()).all()
+
+
+@pytest.mark.parametrize("chan,expect", [
+    ("bit_flip", lambda r, p: (1 - p) * r + p * G.X.dot(r).dot(G.X)),
+    ("phase_flip", lambda r, p: (1 - p) * r + p * G.Z.dot(r).dot(G.Z)),
+    ("bitphase_flip", lambda r, p: (1 - p) * r + p * G.Y.dot(r).dot(G.Y)),
+    ("relaxation", lambda r, p: np.array([[r[0, 0] + r[1, 1] * p, np.sqrt(1 - p) * r[0, 1]],
+                                          [np.sqrt(1 - p) * r[1, 0], (1 - p) * r[1, 1]]])),
+    ("dephasing", lambda r, p: np.array([[r[0, 0], (1 - p) * r[0, 1]], [(1 - p) * r[1, 0], r[1, 1]]])),
+    ("depolarizing", lambda r, p: (1 - p) * r + (p / 3) * (G.X.dot(r).dot(G.X) + G.Y.dot(r).dot(G.Y) +
+                                                          G.Z.dot(r).dot(G.Z))),
+])
+def test_kraus_application(chan, expect):    # :183-257
+    qvm = QVMConnection(type_trans="density")
+    rho = random_1q_density()
+    qvm._density = sps.csc_matrix(rho)
+    qvm.num_qubits = 1
+    p = 0.372
+    out = qvm.apply_kraus(G.noise_gates[chan](p), 0)
+    assert np.allclose(out.todense(), expect(rho, p))
+
+
+def test_kraus_compound_T1T2_application():  # :260-272
+    qvm = QVMConnection(type_trans="density")
+    rho = random_1q_density()
+    qvm._density = sps.csc_matrix(rho)
+    qvm.num_qubits = 1
+    p1, p2 = 0.372, 0.45
+    want = np.array([[rho[0, 0] + rho[1, 1] * p1, (1 - p2) * np.sqrt(1 - p1) * rho[0, 1]],
+                     [(1 - p2) * np.sqrt(1 - p1) * rho[1, 0], (1 - p1) * rho[1, 1]]])
+    qvm._density = qvm.apply_kraus(G.noise_gates["relaxation"](p1), 0)
+    qvm._density = qvm.apply_kraus(G.noise_gates["dephasing"](p2), 0)
+    assert np.allclose(qvm._density.todense(), want)
+
+
+@pytest.mark.parametrize("kw", [dict(T2=INFINITY, ro_fidelity=1.0), dict(T1=INFINITY, ro_fidelity=1.0),
+                                dict(ro_fidelity=1.0)])
+def test_kraus_through_qvm(kw):              # :275-318
+    noise = NoiseModel(**kw)
+    qvm = QVMConnection(type_trans="density", noise_model=noise)
+    rho = random_1q_density()
+    qvm._density = sps.csc_matrix(rho)
+    qvm.num_qubits = 1
+    qvm.load_program(Program().inst(I(0)))
+    qvm.kernel()
+    p1 = 0.0 if noise.T1 == INFINITY else 1 - np.exp(-noise.gate_time_1q / noise.T1)
+    p2 = 0.0 if noise.T2 == INFINITY else 1 - np.exp(-noise.gate_time_1q / noise.T2)
+    want = np.array([[rho[0, 0] + p1 * rho[1, 1], np.sqrt(1 - p1) * (1 - p2) * rho[0, 1]],
+                     [np.sqrt(1 - p1) * (1 - p2) * rho[1, 0], (1 - p1) * rho[1, 1]]])
+    assert np.allclose(want, qvm._density.todense())
+
+
+# ---- reference tests/test_sampling.py ---------------------------------------------------------------------
+def test_density_sampling_statistics():      # :12-54
+    qvm = QVMConnection(type_trans="density")
+    res = qvm.run_and_measure(Program().inst(H(0)), trials=10000)
+    assert np.isclose(sum(x[0] for x in res) / 10000.0, 0.5, atol=0.05, rtol=0.05)
+    res = qvm.run_and_measure(Program().inst(H(0), CNOT(0, 1)), trials=100000)
+    assert all(rr[0] == rr[1] for rr in res)
+    assert np.isclose(sum(x[0] for x in res) / 100000.0, 0.5, atol=0.05, rtol=0.05)
+    res = qvm.run_and_measure(Program().inst(RX(np.pi / 3, 0)), trials=100000)
+    assert np.isclose(sum(x[0] for x in res) / 100000.0, 0.25, atol=0.05, rtol=0.05)
+    prog = Program().inst(H(0)).measure(0, [0]).measure(0, [1])
+    result = qvm.run(prog, [0, 1], trials=300)
+    assert all(x[0] == x[1] for x in result)
+    assert np.isclose(0.5, sum(x[0] for x in result) / 300.0, atol=0.1, rtol=0.05)
+
+
+# ---- reference tests/test_unitary.py ------------------------------------------------------------------------
+def test_unitary_qvm(qvm_unitary):           # :8-52
+    u = qvm_unitary.unitary(Program().inst([H(0), H(1), H(0)]))
+    assert np.allclose(u, np.kron(G.H, np.eye(2)))
+    u = qvm_unitary.unitary(Program().inst([H(0), X(1), Y(2), Z(3)]))
+    assert np.allclose(u, np.kron(G.Z, np.kron(G.Y, np.kron(G.X, G.H))))
+    u = qvm_unitary.unitary(Program().inst([X(2), CNOT(2, 1), CNOT(1, 0)]))
+    want = np.kron(np.eye(2), G.CNOT).dot(np.kron(G.CNOT, np.eye(2))).dot(np.kron(G.X, np.eye(4)))
+    assert np.allclose(u, want)
+    assert np.allclose(qvm_unitary.unitary(Program()), np.eye(1))
+    u = qvm_unitary.unitary(Program().inst(QAOA2))
+    assert np.allclose(u.dot([1, 0, 0, 0]), QAOA2_WF)
+
+
+def test_unitary_errors(qvm_unitary):        # :55-70
+    prog = Program().inst([H(0), H(1)])
+    prog.measure(0, [0])
+    with pytest.raises(TypeError):
+        qvm_unitary.unitary(prog)
+    prog = Program()
+    prog.defgate("hello", np.array([[0, 1], [1, 0]]))
+    prog.inst(("hello2", 0))
+    with pytest.raises(TypeError):
+        qvm_unitary.unitary(prog)
+
+
+# ---- differential, at sizes the reference's algorithm cannot reach: closed-form oracle ---------------------
+@pytest.mark.parametrize("n,depth,seed", [(16, 10, 1234), (20, 6, 1), (22, 4, 2)])
+def test_random_circuit_vs_closed_form_oracle(qvm, n, depth, seed):
+    spec = orc.random_circuit_spec(n, depth, seed)
+    prog = spec_program(spec)
+    wf, _ = qvm.wavefunction(prog)
+    want, _ = orc.fast_run_wavefunction(oracle_ops(prog), n)
+    assert np.max(np.abs(wf.amplitudes - want)) < TOL
+
+
+def test_qft_on_product_state_vs_oracle(qvm):
+    n = 16
+    rs = np.random.RandomState(n)
+    prep = [("RY", [float(rs.uniform(0, np.pi))], [q]) for q in range(n)] + \
+           [("RZ", [float(rs.uniform(0, 2 * np.pi))], [q]) for q in range(n)]
+    prog = spec_program(prep + orc.qft_spec(n))
+    wf, _ = qvm.wavefunction(prog)
+    want, _ = orc.fast_run_wavefunction(oracle_ops(prog), n)
+    assert np.max(np.abs(wf.amplitudes - want)) < TOL
+
+
+def test_density_config2_shape_vs_oracle():
+    """Config 2 at a size the oracle finishes quickly: H layer + random circuit + T2 dephasing."""
+    n = 7
+    spec = [("H", [], [q]) for q in range(n)] + orc.random_circuit_spec(n, 3, 1234)
+    prog = spec_program(spec)
+    nm = NoiseModel(T1=INFINITY, T2=30e-6, gate_time_1q=50e-9, gate_time_2q=150e-9, ro_fidelity=1.0)
+    rho = QVMConnection(type_trans="density", noise_model=nm).density(prog)
+    vec = np.zeros(4 ** n, dtype=complex)
+    vec[0] = 1.0
+    for _, m, q in oracle_ops(prog):
+        vec = orc.fast_density_gate(vec, m, q, n)
+        p = 1.0 - np.exp(-(50e-9 if len(q) == 1 else 150e-9) / 30e-6)
+        for i in range(n):
+            vec = orc.fast_apply_kraus(vec, G.dephasing(p), i, n)
+    got = np.asarray(rho.todense())
+    assert np.max(np.abs(got - orc.vec_to_rho(vec, n))) < TOL
+    assert abs(np.trace(got) - 1.0) < 1e-12

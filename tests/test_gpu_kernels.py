@@ -1,0 +1,302 @@
+"""GPU parity, kernel level: every C-ABI compute entry point against the CPU oracle on the same
+seeded inputs.  Tolerance: 1e-12 max-abs on amplitudes (float64), as BASELINE.json's north_star
+states; integers (outcomes, sampled indices) must be identical."""
+import itertools
+
+import numpy as np
+import pytest
+
+from _model import random_state, random_unitary
+from oracle import qvm_oracle as orc
+from referenceqvm import _engine, _native as nat, _planner
+from referenceqvm import gates as G
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def fresh(n, psi):
+    st = nat.DeviceState(n)
+    st.set_state(psi)
+    return st
+
+
+def check_apply(n, matrix, qubits, seed=0, tile=None):
+    psi = random_state(n, seed)
+    st = fresh(n, psi)
+    if tile is not None:
+        st.set_tile_bits(*tile)
+    st.apply(matrix, qubits)
+    got = st.get_state()
+    st.close()
+    want = orc.fast_apply_gate(psi, matrix, qubits, n)
+    err = np.max(np.abs(got - want))
+    assert err < TOL, (n, qubits, err)
+
+
+def test_state_roundtrip_and_reset():
+    for n in (0, 1, 5, 13, 20):
+        psi = random_state(n, n)
+        st = fresh(n, psi)
+        assert np.array_equal(st.get_state(), psi)
+        if n >= 5:
+            assert np.array_equal(st.get_state(7, 9), psi[7:16])
+            assert np.array_equal(st.get_strided(3, 5, 4), psi[3:3 + 20:5])
+        assert abs(st.norm2() - 1.0) < 1e-12
+        st.reset_zero(True)
+        z = st.get_state()
+        assert z[0] == 1.0 and not z[1:].any()
+        st.close()
+
+
+def test_one_qubit_gate_every_position():
+    rs = np.random.RandomState(1)
+    g = rs.standard_normal((2, 2)) + 1j * rs.standard_normal((2, 2))       # non-unitary on purpose
+    for n in (1, 3, 9, 14):
+        for q in range(n):
+            check_apply(n, g, [q], seed=q)
+    check_apply(16, G.H, [15])
+    check_apply(16, G.H, [0])
+
+
+def test_two_qubit_gate_all_orders():
+    rs = np.random.RandomState(2)
+    g = rs.standard_normal((4, 4)) + 1j * rs.standard_normal((4, 4))
+    n = 14
+    pairs = [(0, 1), (1, 0), (0, 13), (13, 0), (12, 13), (13, 12), (5, 9), (9, 5), (3, 12), (2, 6)]
+    for a, b in pairs:
+        check_apply(n, g, [a, b], seed=a + b)
+    for a, b in itertools.permutations(range(4), 2):
+        check_apply(4, g, [a, b])
+
+
+def test_standard_gate_set_far_and_near():
+    n = 14
+    cases = [("CNOT", [], [0, 13]), ("CNOT", [], [13, 0]), ("CNOT", [], [6, 7]), ("CCNOT", [], [13, 0, 6]),
+             ("CCNOT", [], [1, 2, 12]), ("CSWAP", [], [12, 0, 13]), ("CSWAP", [], [3, 13, 1]),
+             ("SWAP", [], [0, 13]), ("ISWAP", [], [13, 2]), ("PSWAP", [0.4], [5, 11]), ("CZ", [], [13, 0]),
+             ("CPHASE", [1.1], [12, 13]), ("CPHASE00", [1.1], [0, 13]), ("CPHASE01", [1.1], [13, 0]),
+             ("CPHASE10", [1.1], [7, 1]), ("RZ", [0.3], [13]), ("RZ", [0.3], [0]), ("PHASE", [0.3], [12]),
+             ("S", [], [13]), ("T", [], [0]), ("Z", [], [6]), ("X", [], [13]), ("Y", [], [0]), ("H", [], [12]),
+             ("RX", [0.7], [13]), ("RY", [0.7], [1]), ("I", [], [4]), ("BARENCO", [0.3, 0.7, -1.1], [13, 0])]
+    for name, params, qubits in cases:
+        m = G.gate_matrix[name]
+        check_apply(n, m(*params) if params else m, qubits, seed=len(name))
+
+
+def test_dense_k3_to_k6():
+    rs = np.random.RandomState(3)
+    n = 14
+    for k, qubits in [(3, [13, 0, 6]), (3, [2, 1, 0]), (4, [0, 13, 5, 9]), (5, [12, 3, 13, 0, 7]),
+                      (6, [1, 13, 4, 10, 0, 8])]:
+        g = rs.standard_normal((2 ** k,) * 2) + 1j * rs.standard_normal((2 ** k,) * 2)
+        check_apply(n, g, qubits, seed=k)
+    check_apply(3, random_unitary(8, rs), [1, 2, 0])
+    check_apply(6, random_unitary(64, rs), [5, 0, 3, 1, 4, 2])
+
+
+def test_tile_configurations():
+    rs = np.random.RandomState(4)
+    g2 = rs.standard_normal((4, 4)) + 1j * rs.standard_normal((4, 4))
+    for tile in [(4, 0), (6, 3), (8, 4), (10, 5), (12, 5), (13, 5), (13, 4)]:
+        check_apply(15, g2, [14, 9], tile=tile)
+        check_apply(15, G.CNOT, [3, 14], tile=tile)
+        check_apply(15, G.RZ(0.2), [14], tile=tile)
+
+
+def test_errors_map_to_python_exceptions():
+    st = nat.DeviceState(5)
+    with pytest.raises(ValueError):
+        st.apply(G.H, [5])
+    with pytest.raises(ValueError):
+        st.apply(G.CNOT, [2, 2])
+    with pytest.raises(ValueError):
+        st.apply(G.H, [-1])
+    with pytest.raises(ValueError):
+        st.measure(9, 0.5)
+    st.close()
+
+
+def compile_spec(spec):
+    ops = []
+    for name, params, qubits in spec:
+        m = G.gate_matrix[name]
+        ops.append(_engine.compile_gate(m(*params) if params else m, qubits))
+    return ops
+
+
+@pytest.mark.parametrize("n,depth,seed,tile,low", [(14, 8, 1, 12, 5), (16, 6, 2, 12, 5), (15, 8, 3, 10, 4),
+                                                    (13, 10, 4, 8, 3), (18, 4, 5, 13, 5), (17, 6, 6, 12, 3),
+                                                    (20, 4, 1234, 12, 5)])
+def test_fused_groups_random_circuits(n, depth, seed, tile, low):
+    spec = orc.random_circuit_spec(n, depth, seed)
+    psi = random_state(n, seed)
+    want = psi
+    for name, params, qubits in spec:
+        m = G.gate_matrix[name]
+        want = orc.fast_apply_gate(want, m(*params) if params else m, qubits, n)
+    st = fresh(n, psi)
+    groups = _planner.plan(compile_spec(spec), n, tile, low)
+    for g in groups:
+        st.apply_group(g.tile, g.ops)
+    got = st.get_state()
+    stats = st.stats()
+    st.close()
+    assert np.max(np.abs(got - want)) < TOL
+    assert stats["hbm_passes"] == len(groups) and stats["gate_ops"] == len(spec)
+
+
+def test_group_with_outer_controls_and_diagonals_on_non_tile_bits():
+    n = 16
+    rs = np.random.RandomState(7)
+    mats = [(G.H, [3]), (G.CNOT, [15, 3]), (G.RZ(0.4), [14]), (G.CPHASE(0.9), [15, 2]), (G.CCNOT, [14, 13, 0]),
+            (G.CPHASE01(0.3), [13, 1]), (G.T, [15]), (random_unitary(4, rs), [4, 2]), (G.CSWAP, [12, 0, 4]),
+            (G.CZ, [15, 14])]
+    ops = [_engine.compile_gate(m, q) for m, q in mats]
+    psi = random_state(n, 3)
+    st = fresh(n, psi)
+    st.apply_group(list(range(8)), ops)            # one launch; bits 8..15 are outer
+    got = st.get_state()
+    st.close()
+    want = psi
+    for m, q in mats:
+        want = orc.fast_apply_gate(want, m, q, n)
+    assert np.max(np.abs(got - want)) < TOL
+
+
+def test_sharded_positions_diagonals_and_controls():
+    """Global positions (>= n_local) feed controls / diagonal factors from the shard index."""
+    n_local, n_global = 10, 2
+    n = n_local + n_global
+    mats = [(G.H, [4]), (G.CNOT, [11, 4]), (G.RZ(0.7), [10]), (G.CPHASE(0.5), [11, 10]), (G.CZ, [10, 0]),
+            (G.CCNOT, [11, 10, 9]), (G.CPHASE10(0.2), [11, 3]), (G.PHASE(1.3), [11])]
+    ops = [_engine.compile_gate(m, q) for m, q in mats]
+    psi = random_state(n, 9)
+    want = psi
+    for m, q in mats:
+        want = orc.fast_apply_gate(want, m, q, n)
+    for shard in range(4):
+        st = nat.DeviceState(n_local)
+        st.set_shard(n_global, shard)
+        st.set_state(psi[shard << n_local:(shard + 1) << n_local])
+        for g in _planner.plan(ops, n_local, 8, 4):
+            st.apply_group(g.tile, g.ops)
+        got = st.get_state()
+        st.close()
+        assert np.max(np.abs(got - want[shard << n_local:(shard + 1) << n_local])) < TOL, shard
+
+
+def test_measure_kernel():
+    for n, q in [(1, 0), (6, 0), (6, 5), (14, 2), (14, 3), (14, 13), (20, 11)]:
+        psi = random_state(n, n + q)
+        for r in (0.0, 0.3, 0.77, 0.999999):
+            st = fresh(n, psi)
+            outcome, p0 = st.measure(q, r)
+            got = st.get_state()
+            st.close()
+            w_out, w_p0, want = orc.fast_measure(psi, q, n, r)
+            assert outcome == w_out and abs(p0 - w_p0) < 1e-13
+            assert np.max(np.abs(got - want)) < TOL
+    # split form used by sharded states
+    psi = random_state(12, 5)
+    st = fresh(12, psi)
+    p0 = st.prob_zero(7)
+    assert abs(p0 - orc.fast_prob_zero(psi, 7, 12)) < 1e-13
+    st.collapse(7, 1, 1.0 / np.sqrt(1 - p0))
+    assert np.max(np.abs(st.get_state() - orc.fast_collapse(psi, 7, 1, 1 - p0, 12))) < TOL
+    st.close()
+
+
+def test_sampling_matches_inverse_cdf():
+    rs = np.random.RandomState(11)
+    for n in (1, 4, 11, 12, 17):
+        psi = random_state(n, n)
+        if n >= 11:
+            psi[rs.randint(0, 2 ** n, size=2 ** n // 2)] = 0.0      # holes, whole zero blocks
+            psi[: 2 ** (n - 2)] = 0.0
+            psi /= np.linalg.norm(psi)
+        st = fresh(n, psi)
+        total = st.probs_prepare(0)
+        u = rs.random_sample(5000)
+        got = st.sample(u)
+        st.close()
+        probs = psi.real ** 2 + psi.imag ** 2
+        want = orc.inverse_cdf_sample(probs, u)
+        assert abs(total - 1.0) < 1e-12
+        mism = np.nonzero(got != want)[0]
+        # ties at cdf boundaries can move a draw to a neighbour when the summation order differs
+        assert len(mism) <= 2, (n, len(mism))
+        assert np.all(probs[got] > 0)
+
+
+def test_sampling_chi_squared():
+    n = 5
+    psi = random_state(n, 2)
+    st = fresh(n, psi)
+    st.probs_prepare(0)
+    shots = 200000
+    got = st.sample(np.random.RandomState(0).random_sample(shots))
+    st.close()
+    probs = psi.real ** 2 + psi.imag ** 2
+    counts = np.bincount(got.astype(np.int64), minlength=2 ** n)
+    chi2 = np.sum((counts - shots * probs) ** 2 / (shots * probs))
+    assert chi2 < 70.0        # 31 dof: P(chi2 > 70) ~ 7e-5
+
+
+def test_density_diag_sampling_and_prob():
+    n = 5
+    rs = np.random.RandomState(4)
+    a = rs.standard_normal((2 ** n, 2 ** n)) + 1j * rs.standard_normal((2 ** n, 2 ** n))
+    rho = a @ a.conj().T
+    rho /= np.trace(rho).real
+    st = fresh(2 * n, rho.reshape(-1))
+    for q in range(n):
+        want = orc.fast_density_prob_zero(rho.reshape(-1), q, n)
+        assert abs(st.density_prob_zero(n, q) - want) < 1e-13
+    total = st.probs_prepare(1, n)
+    u = rs.random_sample(3000)
+    got = st.sample(u)
+    st.close()
+    want = orc.inverse_cdf_sample(np.real(np.diag(rho)), u)
+    assert abs(total - 1.0) < 1e-12 and np.sum(got != want) <= 1
+
+
+def test_dephase_all_matches_kraus_pairs():
+    n = 4
+    rs = np.random.RandomState(6)
+    rho = rs.standard_normal((16, 16)) + 1j * rs.standard_normal((16, 16))
+    p = 0.2
+    vec = rho.reshape(-1)
+    want = vec
+    for q in range(n):
+        want = orc.fast_apply_kraus(want, G.dephasing(p), q, n)
+    st = fresh(2 * n, vec)
+    st.dephase_all(n, (1 << n) - 1, 1 - p)
+    got = st.get_state()
+    st.close()
+    assert np.max(np.abs(got - want)) < TOL
+
+
+def test_pack_unpack_half_roundtrip():
+    import torch
+    n = 12
+    psi = random_state(n, 1)
+    st = fresh(n, psi)
+    half = 2 ** (n - 1)
+    buf = torch.empty(half * 2, dtype=torch.float64, device="cuda")
+    for bit in (0, 5, 11):
+        for val in (0, 1):
+            st.pack_half(bit, val, 0, half, buf.data_ptr())
+            st.sync()
+            got = buf.cpu().numpy().view(np.complex128)
+            idx = np.arange(2 ** n)
+            assert np.array_equal(got, psi[((idx >> bit) & 1) == val])
+    # swap the two halves of bit 5 through the buffer
+    buf2 = torch.empty_like(buf)
+    st.pack_half(5, 0, 0, half, buf.data_ptr())
+    st.pack_half(5, 1, 0, half, buf2.data_ptr())
+    st.unpack_half(5, 1, 0, half, buf.data_ptr())
+    st.unpack_half(5, 0, 0, half, buf2.data_ptr())
+    got = st.get_state()
+    st.close()
+    assert np.array_equal(got, orc.fast_apply_gate(psi, G.X, [5], n))

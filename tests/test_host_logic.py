@@ -1,0 +1,146 @@
+"""Host-side state machine pieces that need no device (reference tests/test_qvm_funcs.py,
+parts of tests/test_controlflow.py and the API factory)."""
+import numpy as np
+import pytest
+
+from pyquil.gates import CNOT, H, MEASURE, TRUE, FALSE, NOT, AND, OR, MOVE, EXCHANGE, X, HALT
+from pyquil.quil import Program
+from pyquil.quilbase import Jump, JumpTarget, JumpWhen, Label
+
+from referenceqvm.api import QVMConnection
+from referenceqvm.qvm_density import QVM_Density, NoiseModel, INFINITY, kraus_superoperator
+from referenceqvm.qvm_unitary import QVM_Unitary
+from referenceqvm.qvm_wavefunction import QVM_Wavefunction
+from referenceqvm import gates as G
+from referenceqvm import unitary_generator as ug
+
+
+def test_factory_types_and_errors():
+    assert isinstance(QVMConnection(), QVM_Wavefunction)
+    assert isinstance(QVMConnection(type_trans="wavefunction"), QVM_Wavefunction)
+    assert isinstance(QVMConnection(type_trans="unitary"), QVM_Unitary)
+    nm = NoiseModel(T1=INFINITY)
+    d = QVMConnection(type_trans="density", noise_model=nm)
+    assert isinstance(d, QVM_Density) and d.noise_model is nm
+    with pytest.raises(TypeError):
+        QVMConnection(type_trans="tensor-network")
+    with pytest.raises(NotImplementedError):
+        QVMConnection(type_trans="stabilizer")
+
+
+def test_identify_bits_like_reference():
+    qvm = QVMConnection()
+    p = Program()
+    for i in range(5):
+        p.inst(X(i))
+    for i in range(670):
+        p.inst(TRUE(i))
+    qvm.load_program(p)
+    assert qvm.num_qubits == 5 and len(qvm.classical_memory) == 670
+    p = Program()
+    for i in range(670):
+        p.inst(TRUE(i))
+    qvm.load_program(p)
+    assert qvm.num_qubits == 0 and len(qvm.classical_memory) == 670
+    qvm.load_program(Program(X(0)))
+    assert qvm.num_qubits == 1 and len(qvm.classical_memory) == 512
+    assert qvm.classical_memory.dtype == bool and qvm.program_counter == 0
+
+
+def test_load_program_errors():
+    qvm = QVMConnection()
+    with pytest.raises(TypeError):
+        qvm.load_program([H(0)])
+    with pytest.raises(RuntimeError):
+        qvm.load_program(Program(H(51)))
+    qvm.load_program(Program(H(50)))
+    assert qvm.num_qubits == 51
+    qu = QVMConnection(type_trans="unitary")
+    with pytest.raises(TypeError):
+        qu.load_program(Program(H(0)).measure(0, [0]))
+    prog = Program()
+    prog.defgate("hello", np.array([[0, 1], [1, 0]]))
+    prog.inst(("hello2", 0))
+    with pytest.raises(TypeError):
+        qu.load_program(prog)
+
+
+def test_classical_and_control_flow_transitions_without_device():
+    qvm = QVMConnection()
+    lbl = Label("L")
+    prog = Program(TRUE(0), FALSE(1), NOT(1), AND(0, 2), OR(0, 2), MOVE(2, 3), EXCHANGE(3, 4), FALSE(0))
+    prog.inst(JumpWhen(lbl, 0), TRUE(7), JumpTarget(lbl), TRUE(8), HALT, TRUE(9))
+    qvm.load_program(prog)
+    while qvm.program_counter < len(qvm.program):
+        assert qvm._classical_transition(qvm.current_instruction())
+    mem = qvm.classical_memory
+    assert list(mem[:5].astype(int)) == [0, 1, 1, 0, 1]
+    assert mem[7] and mem[8] and not mem[9]
+    with pytest.raises(RuntimeError):
+        qvm.find_label(Label("missing"))
+    qvm.load_program(Program(Jump(Label("nowhere"))))
+    with pytest.raises(RuntimeError):
+        qvm._classical_transition(qvm.current_instruction())
+
+
+def test_operator_descriptor_validation():
+    # reference tests/test_unitary_generator.py:34-41
+    for i, n in [(2, 3), (3, 3), (-1, 3), (3, 4)]:
+        with pytest.raises(ValueError):
+            ug.lifted_gate(i, G.SWAP, n)
+    op = ug.lifted_gate(8, G.SWAP, 10)
+    assert op.qubits == (9, 8) and op.shape == (1024, 1024)
+    assert ug.apply_gate(G.CNOT, [1, 0], 2).qubits == (1, 0)
+    with pytest.raises(ValueError):
+        ug.apply_gate(G.H, [3], 3)
+    with pytest.raises(ValueError):
+        ug.apply_gate(G.CNOT, [1, 1], 3)
+    with pytest.raises(TypeError):
+        ug.apply_gate(np.eye(3), [0], 3)
+    with pytest.raises(TypeError):
+        ug.apply_gate(G.CCNOT, [0, 1, 2], 2)
+    with pytest.raises(ValueError):
+        ug.apply_gate(G.H, [0], 0)
+    from pyquil.quilbase import Gate
+    with pytest.raises(ValueError):
+        ug.tensor_gates(G.gate_matrix, {}, Gate("NOPE", [], [0]), 2)
+    t = ug.tensor_gates(G.gate_matrix, {}, Gate("RX", [0.2], [1]), 3)
+    assert np.allclose(t.matrix, G.RX(0.2)) and t.qubits == (1,)
+
+
+def test_value_get():
+    from pyquil.quilbase import Addr, Qubit
+    assert ug.value_get(Qubit(3)) == 3 and ug.value_get(Addr(9)) == 9 and ug.value_get(Label("a")) == "a"
+    assert ug.value_get(2.5) == 2.5
+    with pytest.raises(TypeError):
+        ug.value_get("q")
+
+
+def test_kraus_superoperator_forms():
+    p = 0.3
+    s = kraus_superoperator(G.dephasing(p))
+    assert np.allclose(s, np.diag([1, 1 - p, 1 - p, 1]))
+    s = kraus_superoperator(G.relaxation(p))
+    rho = np.array([[0.6, 0.2 - 0.1j], [0.2 + 0.1j, 0.4]])
+    out = (s @ rho.reshape(-1)).reshape(2, 2)
+    want = sum(k @ rho @ k.conj().T for k in G.relaxation(p))
+    assert np.allclose(out, want)
+
+
+def test_terminal_measure_analysis():
+    qvm = QVMConnection()
+    f = qvm._terminal_measure_block
+    assert f(Program(H(0), CNOT(0, 1))) == 2
+    assert f(Program(H(0)).measure(0, [0]).measure(0, [1])) == 1
+    assert f(Program(H(0)).measure(0, [0]).inst(X(0))) is None
+    assert f(Program(H(0), HALT).measure(0, [0])) is None
+    assert f(Program(TRUE(0)).while_do(0, Program(X(0)).measure(0, 0))) is None
+
+
+def test_tensor_up_small():
+    from pyquil.paulis import PauliSum, PauliTerm
+    ps = PauliSum([PauliTerm("X", 0, 1.0) * PauliTerm("Y", 1), PauliTerm("Y", 1, 1.0) * PauliTerm("X", 0)])
+    m = ug.tensor_up(ps, 2)
+    assert np.allclose(m, 2 * np.kron(G.Y, G.X))
+    with pytest.raises(TypeError):
+        ug.tensor_up("X0", 2)

@@ -1,0 +1,93 @@
+"""The fusion planner only reorders commuting ops and respects the tile constraints (CPU)."""
+import numpy as np
+import pytest
+
+from _model import apply_op, random_state, random_unitary, run_groups
+from _programs import spec_program
+from oracle import qvm_oracle as orc
+from referenceqvm import _engine, _native as nat, _planner
+from referenceqvm import gates as G
+
+
+def compile_spec(spec, extra=()):
+    ops = []
+    for name, params, qubits in spec:
+        m = G.gate_matrix[name]
+        ops.append(_engine.compile_gate(m(*params) if params else m, qubits))
+    return ops + list(extra)
+
+
+def spec_ops_for_oracle(spec):
+    out = []
+    for name, params, qubits in spec:
+        m = G.gate_matrix[name]
+        out.append(("gate", np.asarray(m(*params) if params else m, dtype=complex), qubits))
+    return out
+
+
+@pytest.mark.parametrize("n,depth,seed,tile,low", [(9, 12, 1, 5, 2), (10, 10, 2, 6, 3), (11, 8, 3, 7, 3),
+                                                    (12, 6, 4, 8, 5), (8, 20, 5, 4, 0), (10, 6, 1234, 12, 5)])
+def test_plan_equals_sequential_execution(n, depth, seed, tile, low):
+    spec = orc.random_circuit_spec(n, depth, seed)
+    ops = compile_spec(spec)
+    groups = _planner.plan(ops, n, tile, low)
+    assert sum(len(g.ops) for g in groups) == len([o for o in ops if o.kind != nat.OP_NOP])
+    for g in groups:
+        assert len(g.tile) == min(tile, n) and list(g.tile) == sorted(set(g.tile))
+        assert all(p in g.tile for p in range(min(low, tile, n)))
+        for op in g.ops:
+            if op.kind == nat.OP_DENSE:
+                assert set(op.targets) <= set(g.tile)
+    psi0 = random_state(n, seed)
+    want, _ = orc.fast_run_wavefunction(spec_ops_for_oracle(spec), n, psi0=psi0)
+    got = run_groups(psi0, groups, n)
+    assert np.max(np.abs(got - want)) < 1e-13
+    if n > tile:
+        assert len(groups) < len(ops) / 2          # fusion actually happens
+
+
+def test_plan_with_wide_and_controlled_gates():
+    rs = np.random.RandomState(0)
+    n = 9
+    mats = [(random_unitary(8, rs), [7, 1, 4]), (G.CCNOT, [8, 0, 5]), (G.CSWAP, [2, 8, 6]),
+            (random_unitary(4, rs), [0, 8]), (G.H, [8]), (G.CZ, [8, 7]), (random_unitary(16, rs), [3, 8, 1, 6]),
+            (G.RZ(0.3), [8]), (G.CNOT, [8, 3]), (G.PSWAP(0.2), [5, 7])]
+    ops = [_engine.compile_gate(m, q) for m, q in mats]
+    groups = _planner.plan(ops, n, 6, 2)
+    psi0 = random_state(n, 1)
+    want = psi0
+    for m, q in mats:
+        want = orc.fast_apply_gate(want, m, q, n)
+    assert np.max(np.abs(run_groups(psi0, groups, n) - want)) < 1e-13
+
+
+def test_gate_wider_than_tile_grows_the_tile():
+    rs = np.random.RandomState(1)
+    ops = [_engine.compile_gate(random_unitary(32, rs), [8, 2, 6, 4, 0])]
+    groups = _planner.plan(ops, 10, 4, 2)
+    assert len(groups) == 1 and len(groups[0].tile) == 5
+
+
+def test_single_tile_register_is_one_group():
+    ops = compile_spec(orc.random_circuit_spec(10, 20, 1234))
+    groups = _planner.plan(ops, 10, 12, 5)
+    assert len(groups) == 1 and groups[0].tile == tuple(range(10)) and len(groups[0].ops) == 200
+
+
+def test_dependencies_keep_non_commuting_order():
+    # H(0) RZ(0) H(0): nothing may be reordered; RZ(1) is free to move
+    ops = [_engine.compile_gate(G.H, [0]), _engine.compile_gate(G.RZ(0.5), [0]),
+           _engine.compile_gate(G.RZ(0.7), [1]), _engine.compile_gate(G.H, [0])]
+    deps = _planner.dependencies(ops)
+    assert deps[1] == {0} and deps[2] == set() and deps[3] == {0, 1}
+
+
+def test_headline_circuit_fuses_well():
+    ops = compile_spec(orc.random_circuit_spec(33, 40, 1234))
+    groups = _planner.plan(ops, 33, 12, 5)
+    assert len(ops) == 1320 and len(groups) <= 45
+
+
+def test_dense_target_outside_register_is_rejected():
+    with pytest.raises(ValueError):
+        _planner.plan([_engine.compile_gate(G.H, [5])], 4, 12, 5)
