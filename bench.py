@@ -257,6 +257,7 @@ def main():
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_launch_ms,
                 "launches_per_step": groups / float(args.steps),
+                "regtile_rounds_per_launch": stats.get("regtile_rounds", 0) / float(max(groups, 1)),
                 "effective_gbs": n_gates * args.steps * bytes_per_launch / (total_ms * 1e-3) / 1e9}
 
     # ---- e2e: the call a user makes -----------------------------------------------------------

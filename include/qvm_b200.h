@@ -64,6 +64,7 @@ typedef struct qvm_stats {
     uint64_t hbm_bytes;                   /* algorithmic bytes moved by those kernels            */
     uint64_t h2d_bytes;
     uint64_t d2h_bytes;
+    uint64_t regtile_rounds;              /* register-tile rounds run by those launches            */
 } qvm_stats_t;
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
@@ -82,6 +83,8 @@ int qvm_set_shard(qvm_t* q, int n_global, uint64_t shard_index);
 /* Run on a caller-owned cudaStream_t (0 restores the handle's own stream). */
 int qvm_set_stream(qvm_t* q, void* cuda_stream);
 int qvm_set_tile_bits(qvm_t* q, int tile_bits, int low_bits);   /* tuning: defaults 12 / 5      */
+/* 1 (default): register-tiled kernel where eligible; 0: shared-memory kernel only (testing).   */
+int qvm_set_kernel_path(qvm_t* q, int use_regtile);
 int qvm_n_local(const qvm_t* q);
 void* qvm_device_ptr(qvm_t* q);         /* raw amplitudes, for NCCL/P2P plumbing on the host     */
 void* qvm_stream(qvm_t* q);

@@ -3,6 +3,7 @@
 // tile-local op encoding and kernel launches.  No CPU fallback exists: without a CUDA device
 // qvm_create fails.
 #include "qvm_kernels.cuh"
+#include "qvm_regtile.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -46,6 +47,7 @@ struct qvm_state {
     int sm_count = 0;
     int tile_bits = 12;
     int low_bits = 5;
+    int use_regtile = 1;
     int sticky = 0;
     // op ring
     unsigned char* ring_host = nullptr;
@@ -253,6 +255,9 @@ int ring_alloc(qvm_state* q, size_t bytes, size_t* off) {
     return QVM_OK;
 }
 
+int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops,
+                         const double* mats, uint64_t mats_entries, bool* handled);
+
 // Encode ops in tile-local coordinates and launch one tile kernel.
 int launch_group(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops, const double* mats,
                  uint64_t mats_entries) {
@@ -278,6 +283,12 @@ int launch_group(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, 
     // keep the offset table small: at most 2^8 entries come from the high part
     if (n_tile - low > 10) return fail(QVM_ERR_INVALID, "tile needs at least %d contiguous low bits", n_tile - 10);
     P.low = low;
+
+    if (q->use_regtile) {
+        bool handled = false;
+        int rc2 = launch_group_regtile(q, n_tile, tile_bits, n_ops, ops, mats, mats_entries, &handled);
+        if (rc2 != QVM_OK || handled) return rc2;
+    }
 
     std::vector<DevOp> dev;
     dev.reserve(n_ops);
@@ -352,6 +363,320 @@ int launch_group(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, 
     q->stats.hbm_passes += 1;
     q->stats.hbm_bytes += 32ull * q->n_elems;
     q->stats.h2d_bytes += ops_pad + mats_bytes;
+    return QVM_OK;
+}
+
+
+// ---- register-tiled path: round planning + encoding ---------------------------------------------
+struct LocalOp {
+    int kind = 0, k = 0;
+    int tgt[QVM_MAX_TARGETS];        // dense: tile-local bit; diag: tile-local bit, or -(1 + physical) when outer
+    uint32_t ctrl_tile = 0;
+    uint64_t ctrl_outer = 0;
+    uint32_t mat_off = 0;
+    uint32_t dense_mask = 0;         // tile-local bits touched densely
+    uint32_t diag_mask = 0;          // tile-local bits touched diagonally (controls, diagonal targets)
+};
+
+struct PlannedRound {
+    int slot_bit[4] = {-1, -1, -1, -1};      // tile-local bit held by register slot s
+    std::vector<int> ops;                    // indices into the LocalOp list, execution order
+    uint32_t regmask() const {
+        uint32_t m = 0;
+        for (int s = 0; s < 4; ++s)
+            if (slot_bit[s] >= 0) m |= 1u << slot_bit[s];
+        return m;
+    }
+    int slot_of(int bit) const {
+        for (int s = 0; s < 4; ++s)
+            if (slot_bit[s] == bit) return s;
+        return -1;
+    }
+};
+
+// Try to give the dense targets of `op` register slots in `rd`; `allowed` = tile bits that may
+// become register bits in this round.  Dense2 targets must share a slot pair {0,1} or {2,3}.
+bool place_dense(PlannedRound& rd, const LocalOp& op, uint32_t allowed) {
+    if (op.k == 1) {
+        const int b = op.tgt[0];
+        if (rd.slot_of(b) >= 0) return true;
+        if (!((allowed >> b) & 1u)) return false;
+        static const int pref[4] = {3, 2, 1, 0};
+        for (int s : pref)
+            if (rd.slot_bit[s] < 0) {
+                rd.slot_bit[s] = b;
+                return true;
+            }
+        return false;
+    }
+    const int a = op.tgt[0], b = op.tgt[1];
+    const int sa = rd.slot_of(a), sb = rd.slot_of(b);
+    if (sa >= 0 && sb >= 0) return (sa >> 1) == (sb >> 1);
+    if (sa >= 0 || sb >= 0) {
+        const int have = sa >= 0 ? sa : sb;
+        const int other_bit = sa >= 0 ? b : a;
+        const int partner = have ^ 1;
+        if (rd.slot_bit[partner] >= 0 || !((allowed >> other_bit) & 1u)) return false;
+        rd.slot_bit[partner] = other_bit;
+        return true;
+    }
+    if (!((allowed >> a) & 1u) || !((allowed >> b) & 1u)) return false;
+    for (int p = 0; p < 2; ++p)
+        if (rd.slot_bit[2 * p] < 0 && rd.slot_bit[2 * p + 1] < 0) {
+            rd.slot_bit[2 * p + 1] = a;      // msb -> odd slot
+            rd.slot_bit[2 * p] = b;
+            return true;
+        }
+    return false;
+}
+
+bool is_x_matrix(const double* m) {
+    static const double x[8] = {0, 0, 1, 0, 1, 0, 0, 0};
+    return memcmp(m, x, sizeof(x)) == 0;
+}
+bool is_h_matrix(const double* m) {      // s * [[1, 1], [1, -1]] with real s
+    const double s = m[0];
+    return s != 0.0 && m[1] == 0.0 && m[2] == s && m[3] == 0.0 && m[4] == s && m[5] == 0.0 && m[6] == -s && m[7] == 0.0;
+}
+
+template <int T, int B>
+int launch_regtile(qvm_state* q, unsigned grid, unsigned threads, size_t smem, const RegTileParams& P) {
+    static bool attr_set[64] = {};
+    if (!attr_set[q->device & 63]) {
+        QVM_CUDA(q, cudaFuncSetAttribute(regtile_kernel<T, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set[q->device & 63] = true;
+    }
+    regtile_kernel<T, B><<<grid, threads, smem, q->stream>>>(q->amps, P);
+    QVM_CUDA(q, cudaGetLastError());
+    return QVM_OK;
+}
+
+int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops,
+                         const double* mats, uint64_t mats_entries, bool* handled) {
+    *handled = false;
+    if (n_tile < 9 || n_tile > 13) return QVM_OK;
+    const int npos = total_positions(q);
+    int8_t local_of[64];
+    memset(local_of, -1, sizeof(local_of));
+    RegTileParams P{};
+    P.n_local = q->n_local;
+    P.k = n_tile;
+    P.shard_bits = q->shard_index << q->n_local;
+    for (int j = 0; j < n_tile; ++j) {
+        P.tile_pos[j] = (uint8_t)tile_bits[j];
+        P.tile_mask |= 1ull << tile_bits[j];
+        local_of[tile_bits[j]] = (int8_t)j;
+    }
+
+    // tile-relative view (validation mirrors the v1 path; anything unusual falls back to it)
+    std::vector<LocalOp> lops;
+    lops.reserve(n_ops);
+    for (int i = 0; i < n_ops; ++i) {
+        const qvm_op_t& op = ops[i];
+        if (op.kind == QVM_OP_NOP) continue;
+        if (op.kind != QVM_OP_DENSE && op.kind != QVM_OP_DIAG) return QVM_OK;
+        if (op.k < 0 || op.k > QVM_MAX_TARGETS) return QVM_OK;
+        if (op.kind == QVM_OP_DENSE && (op.k < 1 || op.k > 2)) return QVM_OK;
+        const uint64_t want = op.kind == QVM_OP_DENSE ? (1ull << (2 * op.k)) : (1ull << op.k);
+        if (op.mat_entries != want || (uint64_t)op.mat_offset + want > mats_entries) return QVM_OK;
+        if (npos < 64 && (op.ctrl_mask >> npos)) return QVM_OK;
+        LocalOp l;
+        l.kind = op.kind;
+        l.k = op.k;
+        l.mat_off = op.mat_offset;
+        uint64_t used = op.ctrl_mask;
+        for (int p = 0; p < q->n_local; ++p)
+            if (((op.ctrl_mask >> p) & 1ull) && local_of[p] >= 0) l.ctrl_tile |= 1u << local_of[p];
+        l.ctrl_outer = op.ctrl_mask & ~P.tile_mask;
+        l.diag_mask = l.ctrl_tile;
+        for (int j = 0; j < op.k; ++j) {
+            const int p = op.targets[j];
+            if (p < 0 || p >= npos || ((used >> p) & 1ull)) return QVM_OK;
+            used |= 1ull << p;
+            const bool in_tile = p < q->n_local && local_of[p] >= 0;
+            if (op.kind == QVM_OP_DENSE) {
+                if (!in_tile) return QVM_OK;
+                l.tgt[j] = local_of[p];
+                l.dense_mask |= 1u << local_of[p];
+            } else if (in_tile) {
+                l.tgt[j] = local_of[p];
+                l.diag_mask |= 1u << local_of[p];
+            } else {
+                l.tgt[j] = -(1 + p);
+            }
+        }
+        lops.push_back(l);
+    }
+    if (lops.empty()) {
+        *handled = true;
+        return QVM_OK;
+    }
+
+    // ---- rounds: greedy, commutation aware ------------------------------------------------------
+    const uint32_t all_bits = (1u << n_tile) - 1u;
+    const uint32_t high_bits = all_bits & ~0x1Fu;          // lanes keep the five lowest tile bits in I/O rounds
+    const int n = (int)lops.size();
+    std::vector<char> done(n, 0);
+    std::vector<PlannedRound> rounds;
+    int remaining = n;
+    while (remaining > 0) {
+        PlannedRound rd;
+        const uint32_t allowed = rounds.empty() ? high_bits : all_bits;
+        uint32_t blocked_dense = 0, blocked_diag = 0;
+        for (int i = 0; i < n; ++i) {
+            if (done[i]) continue;
+            const LocalOp& op = lops[i];
+            const bool clash = (op.dense_mask & (blocked_dense | blocked_diag)) || (op.diag_mask & blocked_dense);
+            bool ok = !clash;
+            if (ok && op.kind == QVM_OP_DENSE) {
+                PlannedRound trial = rd;
+                ok = place_dense(trial, op, allowed);
+                if (ok) memcpy(rd.slot_bit, trial.slot_bit, sizeof(rd.slot_bit));
+            }
+            if (!ok) {
+                blocked_dense |= op.dense_mask;
+                blocked_diag |= op.diag_mask;
+                continue;
+            }
+            rd.ops.push_back(i);
+        }
+        for (int i : rd.ops) done[i] = 1;
+        remaining -= (int)rd.ops.size();
+        if (rd.ops.empty() && !rounds.empty()) return fail(QVM_ERR_CUDA, "round planner made no progress");
+        rounds.push_back(rd);
+    }
+    if (rounds.size() > 1 && (rounds.back().regmask() & 0x1Fu)) rounds.push_back(PlannedRound());   // store round
+    if (rounds.size() > 4096) return QVM_OK;
+
+    // fill unused register slots with the highest free tile bits
+    for (PlannedRound& rd : rounds) {
+        uint32_t used = rd.regmask();
+        for (int s = 0; s < 4; ++s)
+            if (rd.slot_bit[s] < 0)
+                for (int b = n_tile - 1; b >= 0; --b)
+                    if (!((used >> b) & 1u)) {
+                        rd.slot_bit[s] = b;
+                        used |= 1u << b;
+                        break;
+                    }
+    }
+
+    // ---- encode ---------------------------------------------------------------------------------
+    std::vector<double> pool(mats, mats + 2 * mats_entries);
+    std::vector<RoundDesc> rdesc(rounds.size());
+    std::vector<RegOp> rops;
+    rops.reserve(n);
+    for (size_t r = 0; r < rounds.size(); ++r) {
+        const PlannedRound& rd = rounds[r];
+        RoundDesc& d = rdesc[r];
+        memset(&d, 0, sizeof(d));
+        int8_t slot_of[16], thr_of[16];
+        memset(slot_of, -1, sizeof(slot_of));
+        memset(thr_of, -1, sizeof(thr_of));
+        for (int s = 0; s < 4; ++s) {
+            d.reg_bit[s] = (uint8_t)rd.slot_bit[s];
+            slot_of[rd.slot_bit[s]] = (int8_t)s;
+        }
+        int nt = 0;
+        for (int b = 0; b < n_tile; ++b)
+            if (slot_of[b] < 0) {
+                d.thr_bit[nt] = (uint8_t)b;
+                thr_of[b] = (int8_t)nt;
+                ++nt;
+            }
+        d.op_begin = (uint16_t)rops.size();
+        for (int i : rd.ops) {
+            const LocalOp& l = lops[i];
+            RegOp o;
+            memset(&o, 0, sizeof(o));
+            o.ctrl_outer = l.ctrl_outer;
+            o.mat_off = l.mat_off;
+            uint32_t kind = 0, b0 = 0, kk = 0, ctrl_reg = 0, ctrl_thr = 0;
+            uint8_t loc[6] = {0, 0, 0, 0, 0, 0};
+            for (int b = 0; b < n_tile; ++b)
+                if ((l.ctrl_tile >> b) & 1u) {
+                    if (slot_of[b] >= 0) ctrl_reg |= 1u << slot_of[b];
+                    else ctrl_thr |= 1u << thr_of[b];
+                }
+            if (l.kind == QVM_OP_DENSE && l.k == 1) {
+                b0 = (uint32_t)slot_of[l.tgt[0]];
+                const double* m = &pool[2 * (size_t)l.mat_off];
+                if (is_x_matrix(m)) kind = RK_X;
+                else if (!l.ctrl_tile && !l.ctrl_outer && is_h_matrix(m)) kind = RK_H;
+                else kind = RK_DENSE1;
+            } else if (l.kind == QVM_OP_DENSE) {
+                const int sa = slot_of[l.tgt[0]];
+                kind = RK_DENSE2;
+                b0 = (uint32_t)(sa >> 1);
+                if (!(sa & 1)) {
+                    // msb target sits in the even slot: swap the roles of the two index bits
+                    static const int perm[4] = {0, 2, 1, 3};
+                    const size_t off = pool.size() / 2;
+                    pool.resize(pool.size() + 32);
+                    for (int rr = 0; rr < 4; ++rr)
+                        for (int cc = 0; cc < 4; ++cc) {
+                            const size_t src = 2 * ((size_t)l.mat_off + perm[rr] * 4 + perm[cc]);
+                            pool[2 * (off + rr * 4 + cc)] = pool[src];
+                            pool[2 * (off + rr * 4 + cc) + 1] = pool[src + 1];
+                        }
+                    o.mat_off = (uint32_t)off;
+                }
+            } else {
+                kk = (uint32_t)l.k;
+                int nreg = 0;
+                for (int t = 0; t < l.k; ++t) {
+                    const int b = l.tgt[t];
+                    if (b < 0) loc[t] = (uint8_t)(LOC_OUT | (-(b + 1)));
+                    else if (slot_of[b] >= 0) {
+                        loc[t] = (uint8_t)(LOC_REG | slot_of[b]);
+                        b0 = (uint32_t)slot_of[b];
+                        ++nreg;
+                    } else loc[t] = (uint8_t)(LOC_THR | thr_of[b]);
+                }
+                if (nreg >= 2) kind = RK_DIAG_R;
+                else if (nreg == 1) kind = RK_DIAG1;
+                else kind = ctrl_reg ? RK_DIAG_S : RK_DIAG_T;
+            }
+            o.w0 = kind | (b0 << 8) | (kk << 16) | (ctrl_reg << 24);
+            o.w1 = ctrl_thr | ((uint32_t)loc[4] << 16) | ((uint32_t)loc[5] << 24);
+            o.loc03 = (uint32_t)loc[0] | ((uint32_t)loc[1] << 8) | ((uint32_t)loc[2] << 16) | ((uint32_t)loc[3] << 24);
+            rops.push_back(o);
+        }
+        d.op_end = (uint16_t)rops.size();
+    }
+
+    const size_t rounds_bytes = (rdesc.size() * sizeof(RoundDesc) + 255) & ~(size_t)255;
+    const size_t ops_bytes = (rops.size() * sizeof(RegOp) + 255) & ~(size_t)255;
+    const size_t mats_bytes = pool.size() * sizeof(double);
+    size_t off = 0;
+    int rc = ring_alloc(q, rounds_bytes + ops_bytes + mats_bytes, &off);
+    if (rc) return rc;
+    memcpy(q->ring_host + off, rdesc.data(), rdesc.size() * sizeof(RoundDesc));
+    memcpy(q->ring_host + off + rounds_bytes, rops.data(), rops.size() * sizeof(RegOp));
+    memcpy(q->ring_host + off + rounds_bytes + ops_bytes, pool.data(), mats_bytes);
+    QVM_CUDA(q, cudaMemcpyAsync(q->ring_dev + off, q->ring_host + off, rounds_bytes + ops_bytes + mats_bytes,
+                                cudaMemcpyHostToDevice, q->stream));
+    P.n_rounds = (int)rdesc.size();
+    P.n_ops = (int)rops.size();
+    P.rounds = reinterpret_cast<const RoundDesc*>(q->ring_dev + off);
+    P.ops = reinterpret_cast<const RegOp*>(q->ring_dev + off + rounds_bytes);
+    P.mats = reinterpret_cast<const double2*>(q->ring_dev + off + rounds_bytes + ops_bytes);
+
+    const size_t smem = regtile_smem_bytes(P.k, P.n_rounds, P.n_ops);
+    if (smem > 227 * 1024) return QVM_OK;          // let the v1 path (or its error) handle it
+    const uint64_t n_tiles = q->n_elems >> n_tile;
+    if (n_tiles > 0x7fffffffull) return fail(QVM_ERR_UNSUPPORTED, "too many tiles for one launch");
+    const unsigned threads = 1u << (n_tile - 4);
+    if (threads > 256) rc = launch_regtile<512, 1>(q, (unsigned)n_tiles, threads, smem, P);
+    else rc = launch_regtile<256, 2>(q, (unsigned)n_tiles, threads, smem, P);
+    if (rc) return rc;
+    q->stats.kernel_launches += 1;
+    q->stats.gate_ops += (uint64_t)n;
+    q->stats.hbm_passes += 1;
+    q->stats.hbm_bytes += 32ull * q->n_elems;
+    q->stats.h2d_bytes += rounds_bytes + ops_bytes + mats_bytes;
+    q->stats.regtile_rounds += (uint64_t)rdesc.size();
+    *handled = true;
     return QVM_OK;
 }
 
@@ -500,6 +825,12 @@ int qvm_set_tile_bits(qvm_t* q, int tile_bits, int low_bits) {
         return fail(QVM_ERR_INVALID, "bad tile configuration (%d, %d)", tile_bits, low_bits);
     q->tile_bits = tile_bits;
     q->low_bits = low_bits;
+    return QVM_OK;
+}
+
+int qvm_set_kernel_path(qvm_t* q, int use_regtile) {
+    QVM_CHECK_HANDLE(q);
+    q->use_regtile = use_regtile ? 1 : 0;
     return QVM_OK;
 }
 

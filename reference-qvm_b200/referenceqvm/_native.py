@@ -34,7 +34,7 @@ class Op(C.Structure):
 class Stats(C.Structure):
     """``qvm_stats_t``"""
     _fields_ = [(name, C.c_uint64) for name in
-                ("kernel_launches", "gate_ops", "hbm_passes", "hbm_bytes", "h2d_bytes", "d2h_bytes")]
+                ("kernel_launches", "gate_ops", "hbm_passes", "hbm_bytes", "h2d_bytes", "d2h_bytes", "regtile_rounds")]
 
     def as_dict(self):
         return {name: int(getattr(self, name)) for name, _ in self._fields_}
@@ -51,6 +51,7 @@ _SIGNATURES = {
     "qvm_set_shard": (C.c_int, [_P, C.c_int, C.c_uint64]),
     "qvm_set_stream": (C.c_int, [_P, _P]),
     "qvm_set_tile_bits": (C.c_int, [_P, C.c_int, C.c_int]),
+    "qvm_set_kernel_path": (C.c_int, [_P, C.c_int]),
     "qvm_n_local": (C.c_int, [_P]),
     "qvm_device_ptr": (_P, [_P]),
     "qvm_stream": (_P, [_P]),
@@ -225,6 +226,9 @@ class DeviceState(object):
 
     def set_tile_bits(self, tile_bits, low_bits):
         check(lib().qvm_set_tile_bits(self.handle, tile_bits, low_bits))
+
+    def set_kernel_path(self, use_regtile):
+        check(lib().qvm_set_kernel_path(self.handle, 1 if use_regtile else 0))
 
     def device_ptr(self):
         return int(lib().qvm_device_ptr(self.handle) or 0)

@@ -129,6 +129,11 @@ def compile_spec(spec):
                                                     (13, 10, 4, 8, 3), (18, 4, 5, 13, 5), (17, 6, 6, 12, 3),
                                                     (20, 4, 1234, 12, 5)])
 def test_fused_groups_random_circuits(n, depth, seed, tile, low):
+    for path in (1, 0):
+        _fused_groups_random_circuits(n, depth, seed, tile, low, path)
+
+
+def _fused_groups_random_circuits(n, depth, seed, tile, low, path):
     spec = orc.random_circuit_spec(n, depth, seed)
     psi = random_state(n, seed)
     want = psi
@@ -136,6 +141,7 @@ def test_fused_groups_random_circuits(n, depth, seed, tile, low):
         m = G.gate_matrix[name]
         want = orc.fast_apply_gate(want, m(*params) if params else m, qubits, n)
     st = fresh(n, psi)
+    st.set_kernel_path(path)
     groups = _planner.plan(compile_spec(spec), n, tile, low)
     for g in groups:
         st.apply_group(g.tile, g.ops)
@@ -300,3 +306,28 @@ def test_pack_unpack_half_roundtrip():
     got = st.get_state()
     st.close()
     assert np.array_equal(got, orc.fast_apply_gate(psi, G.X, [5], n))
+
+
+def test_regtile_mixed_ops_one_group():
+    """Register-tiled kernel: dense1/X/H/dense2/diag with controls on register, thread and outer bits,
+    targets on the lowest tile bits (forces middle rounds) and reversed dense2 argument orders."""
+    n = 17
+    rs = np.random.RandomState(21)
+    u2a, u2b, u1 = random_unitary(4, rs), random_unitary(4, rs), random_unitary(2, rs)
+    mats = [(G.H, [0]), (G.H, [1]), (G.CNOT, [0, 1]), (G.CNOT, [16, 2]), (G.CNOT, [11, 3]), (u1, [4]),
+            (G.RZ(0.3), [0]), (G.RZ(0.4), [9]), (G.RZ(0.5), [15]), (G.CPHASE(0.6), [0, 9]),
+            (G.CPHASE(0.7), [16, 1]), (G.CPHASE01(0.2), [3, 10]), (u2a, [11, 5]), (u2a, [5, 11]), (u2b, [0, 10]),
+            (G.CCNOT, [0, 16, 6]), (G.CSWAP, [15, 7, 2]), (G.ISWAP, [8, 1]), (G.H, [11]), (G.X, [10]),
+            (G.BARENCO(0.1, 0.2, 0.3), [13, 8]), (G.CZ, [2, 3]), (G.T, [4]), (G.PSWAP(0.9), [6, 7]), (G.H, [7]),
+            (G.Y, [9]), (G.CPHASE10(0.8), [14, 0]), (G.PHASE(1.2), [16])]
+    ops = [_engine.compile_gate(m, q) for m, q in mats]
+    psi = random_state(n, 8)
+    want = psi
+    for m, q in mats:
+        want = orc.fast_apply_gate(want, m, q, n)
+    for tile in (list(range(12)), list(range(13)), [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 13], list(range(12)) + [15]):
+        st = fresh(n, psi)
+        st.apply_group(tile, ops)
+        got = st.get_state()
+        st.close()
+        assert np.max(np.abs(got - want)) < TOL, tile
