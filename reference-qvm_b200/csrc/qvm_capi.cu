@@ -462,9 +462,9 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
     P.n_local = q->n_local;
     P.k = n_tile;
     P.shard_bits = q->shard_index << q->n_local;
+    uint64_t P_tile_mask = 0;
     for (int j = 0; j < n_tile; ++j) {
-        P.tile_pos[j] = (uint8_t)tile_bits[j];
-        P.tile_mask |= 1ull << tile_bits[j];
+        P_tile_mask |= 1ull << tile_bits[j];
         local_of[tile_bits[j]] = (int8_t)j;
     }
 
@@ -487,7 +487,7 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
         uint64_t used = op.ctrl_mask;
         for (int p = 0; p < q->n_local; ++p)
             if (((op.ctrl_mask >> p) & 1ull) && local_of[p] >= 0) l.ctrl_tile |= 1u << local_of[p];
-        l.ctrl_outer = op.ctrl_mask & ~P.tile_mask;
+        l.ctrl_outer = op.ctrl_mask & ~P_tile_mask;
         l.diag_mask = l.ctrl_tile;
         for (int j = 0; j < op.k; ++j) {
             const int p = op.targets[j];
@@ -564,50 +564,59 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
     // ---- encode ---------------------------------------------------------------------------------
     std::vector<double> pool(mats, mats + 2 * mats_entries);
     std::vector<RoundDesc> rdesc(rounds.size());
-    std::vector<RegOp> rops;
-    rops.reserve(n);
+    std::vector<HotOp> hot;
+    std::vector<ColdOp> cold;
+    hot.reserve(n);
+    cold.reserve(n);
     for (size_t r = 0; r < rounds.size(); ++r) {
         const PlannedRound& rd = rounds[r];
         RoundDesc& d = rdesc[r];
         memset(&d, 0, sizeof(d));
+        d.scale = 1.0;
         int8_t slot_of[16], thr_of[16];
         memset(slot_of, -1, sizeof(slot_of));
         memset(thr_of, -1, sizeof(thr_of));
+        int sorted[4];
         for (int s = 0; s < 4; ++s) {
             d.reg_bit[s] = (uint8_t)rd.slot_bit[s];
+            d.reg_phys[s] = (uint8_t)tile_bits[rd.slot_bit[s]];
             slot_of[rd.slot_bit[s]] = (int8_t)s;
+            sorted[s] = rd.slot_bit[s];
         }
+        std::sort(sorted, sorted + 4);
+        for (int s = 0; s < 4; ++s) d.reg_sorted[s] = (uint8_t)sorted[s];
         int nt = 0;
         for (int b = 0; b < n_tile; ++b)
-            if (slot_of[b] < 0) {
-                d.thr_bit[nt] = (uint8_t)b;
-                thr_of[b] = (int8_t)nt;
-                ++nt;
-            }
-        d.op_begin = (uint16_t)rops.size();
+            if (slot_of[b] < 0) thr_of[b] = (int8_t)nt++;
+        d.op_begin = (uint16_t)hot.size();
         for (int i : rd.ops) {
             const LocalOp& l = lops[i];
-            RegOp o;
-            memset(&o, 0, sizeof(o));
-            o.ctrl_outer = l.ctrl_outer;
-            o.mat_off = l.mat_off;
-            uint32_t kind = 0, b0 = 0, kk = 0, ctrl_reg = 0, ctrl_thr = 0;
-            uint8_t loc[6] = {0, 0, 0, 0, 0, 0};
+            HotOp h{0, 0, 0, 0};
+            ColdOp c;
+            memset(&c, 0, sizeof(c));
+            c.ctrl_outer = l.ctrl_outer;
+            uint32_t mat_off = l.mat_off;
+            uint32_t opc = 0, crm = 0, cthr = 0, xb = 0, s0 = 0, s1 = 0, p0 = 31, p1 = 31, shr = 0;
             for (int b = 0; b < n_tile; ++b)
                 if ((l.ctrl_tile >> b) & 1u) {
-                    if (slot_of[b] >= 0) ctrl_reg |= 1u << slot_of[b];
-                    else ctrl_thr |= 1u << thr_of[b];
+                    if (slot_of[b] >= 0) crm |= 1u << slot_of[b];
+                    else cthr |= 1u << thr_of[b];
                 }
             if (l.kind == QVM_OP_DENSE && l.k == 1) {
-                b0 = (uint32_t)slot_of[l.tgt[0]];
+                const uint32_t slot = (uint32_t)slot_of[l.tgt[0]];
                 const double* m = &pool[2 * (size_t)l.mat_off];
-                if (is_x_matrix(m)) kind = RK_X;
-                else if (!l.ctrl_tile && !l.ctrl_outer && is_h_matrix(m)) kind = RK_H;
-                else kind = RK_DENSE1;
+                if (is_x_matrix(m)) {
+                    if (crm == 0) {
+                        opc = OPC_X_RELABEL;
+                        xb = slot;
+                    } else opc = OPC_XS_0 + slot;
+                } else if (!l.ctrl_tile && !l.ctrl_outer && is_h_matrix(m)) {
+                    opc = OPC_H0 + slot;
+                    d.scale *= m[0];
+                } else opc = OPC_D1_0 + slot;
             } else if (l.kind == QVM_OP_DENSE) {
                 const int sa = slot_of[l.tgt[0]];
-                kind = RK_DENSE2;
-                b0 = (uint32_t)(sa >> 1);
+                opc = OPC_D2_0 + (uint32_t)(sa >> 1);
                 if (!(sa & 1)) {
                     // msb target sits in the even slot: swap the roles of the two index bits
                     static const int perm[4] = {0, 2, 1, 3};
@@ -619,48 +628,94 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
                             pool[2 * (off + rr * 4 + cc)] = pool[src];
                             pool[2 * (off + rr * 4 + cc) + 1] = pool[src + 1];
                         }
-                    o.mat_off = (uint32_t)off;
+                    mat_off = (uint32_t)off;
                 }
             } else {
-                kk = (uint32_t)l.k;
-                int nreg = 0;
+                c.k = (uint8_t)l.k;
+                int nreg = 0, nthr = 0;
+                uint32_t reg_slot = 0;
                 for (int t = 0; t < l.k; ++t) {
                     const int b = l.tgt[t];
-                    if (b < 0) loc[t] = (uint8_t)(LOC_OUT | (-(b + 1)));
+                    const uint32_t wshift = (uint32_t)(l.k - 1 - t);
+                    if (b < 0) c.loc[t] = (uint8_t)(LOC_OUT | (-(b + 1)));
                     else if (slot_of[b] >= 0) {
-                        loc[t] = (uint8_t)(LOC_REG | slot_of[b]);
-                        b0 = (uint32_t)slot_of[b];
+                        c.loc[t] = (uint8_t)(LOC_REG | slot_of[b]);
+                        reg_slot = (uint32_t)slot_of[b];
+                        shr = wshift;
                         ++nreg;
-                    } else loc[t] = (uint8_t)(LOC_THR | thr_of[b]);
+                    } else {
+                        c.loc[t] = (uint8_t)(LOC_THR | thr_of[b]);
+                        if (nthr == 0) { p0 = (uint32_t)thr_of[b]; s0 = wshift; }
+                        else if (nthr == 1) { p1 = (uint32_t)thr_of[b]; s1 = wshift; }
+                        ++nthr;
+                    }
                 }
-                if (nreg >= 2) kind = RK_DIAG_R;
-                else if (nreg == 1) kind = RK_DIAG1;
-                else kind = ctrl_reg ? RK_DIAG_S : RK_DIAG_T;
+                if (nreg >= 2 || nthr > 2) opc = OPC_DIAG_G;
+                else if (nreg == 1) opc = OPC_DIAG1_0 + reg_slot;
+                else opc = crm ? OPC_DIAG_S : OPC_DIAG_T;
             }
-            o.w0 = kind | (b0 << 8) | (kk << 16) | (ctrl_reg << 24);
-            o.w1 = ctrl_thr | ((uint32_t)loc[4] << 16) | ((uint32_t)loc[5] << 24);
-            o.loc03 = (uint32_t)loc[0] | ((uint32_t)loc[1] << 8) | ((uint32_t)loc[2] << 16) | ((uint32_t)loc[3] << 24);
-            rops.push_back(o);
+            h.x = opc | (crm << 8) | (xb << 12) | (s0 << 16) | (s1 << 24);
+            h.y = cthr | (p0 << 16) | (p1 << 24);
+            h.z = mat_off;
+            h.w = (shr << 8);
+            hot.push_back(h);
+            cold.push_back(c);
         }
-        d.op_end = (uint16_t)rops.size();
+        d.op_end = (uint16_t)hot.size();
+    }
+
+    // launch parameters that replace per-thread bit loops
+    int low = 0;
+    while (low < n_tile && tile_bits[low] == low) ++low;
+    if (low > 5) low = 5;                       // keeps the offset table at >= 2^(k-5) entries, <= 2^13
+    P.low = low;
+    {
+        int nr = 0;
+        int p = 0;
+        while (p < q->n_local) {
+            if ((P_tile_mask >> p) & 1ull) { ++p; continue; }
+            int e = p;
+            while (e < q->n_local && !((P_tile_mask >> e) & 1ull)) ++e;
+            if (nr >= 16) return QVM_OK;        // pathological tile shape: let the v1 kernel take it
+            P.run_start[nr] = (uint8_t)p;
+            P.run_len[nr] = (uint8_t)(e - p);
+            ++nr;
+            p = e;
+        }
+        P.n_runs = nr;
+    }
+    std::vector<uint64_t> hi_off((size_t)1 << (n_tile - low));
+    for (size_t j = 0; j < hi_off.size(); ++j) {
+        uint64_t off = 0;
+        for (int b = 0; b < n_tile - low; ++b)
+            if ((j >> b) & 1u) off |= 1ull << tile_bits[low + b];
+        hi_off[j] = off;
     }
 
     const size_t rounds_bytes = (rdesc.size() * sizeof(RoundDesc) + 255) & ~(size_t)255;
-    const size_t ops_bytes = (rops.size() * sizeof(RegOp) + 255) & ~(size_t)255;
+    const size_t hot_bytes = (hot.size() * sizeof(HotOp) + 255) & ~(size_t)255;
+    const size_t cold_bytes = (cold.size() * sizeof(ColdOp) + 255) & ~(size_t)255;
+    const size_t hi_bytes = (hi_off.size() * sizeof(uint64_t) + 255) & ~(size_t)255;
     const size_t mats_bytes = pool.size() * sizeof(double);
+    const size_t total_bytes = rounds_bytes + hot_bytes + cold_bytes + hi_bytes + mats_bytes;
     size_t off = 0;
-    int rc = ring_alloc(q, rounds_bytes + ops_bytes + mats_bytes, &off);
+    int rc = ring_alloc(q, total_bytes, &off);
     if (rc) return rc;
-    memcpy(q->ring_host + off, rdesc.data(), rdesc.size() * sizeof(RoundDesc));
-    memcpy(q->ring_host + off + rounds_bytes, rops.data(), rops.size() * sizeof(RegOp));
-    memcpy(q->ring_host + off + rounds_bytes + ops_bytes, pool.data(), mats_bytes);
-    QVM_CUDA(q, cudaMemcpyAsync(q->ring_dev + off, q->ring_host + off, rounds_bytes + ops_bytes + mats_bytes,
-                                cudaMemcpyHostToDevice, q->stream));
+    unsigned char* hp = q->ring_host + off;
+    memcpy(hp, rdesc.data(), rdesc.size() * sizeof(RoundDesc));
+    memcpy(hp + rounds_bytes, hot.data(), hot.size() * sizeof(HotOp));
+    memcpy(hp + rounds_bytes + hot_bytes, cold.data(), cold.size() * sizeof(ColdOp));
+    memcpy(hp + rounds_bytes + hot_bytes + cold_bytes, hi_off.data(), hi_off.size() * sizeof(uint64_t));
+    memcpy(hp + rounds_bytes + hot_bytes + cold_bytes + hi_bytes, pool.data(), mats_bytes);
+    QVM_CUDA(q, cudaMemcpyAsync(q->ring_dev + off, hp, total_bytes, cudaMemcpyHostToDevice, q->stream));
+    unsigned char* dp = q->ring_dev + off;
     P.n_rounds = (int)rdesc.size();
-    P.n_ops = (int)rops.size();
-    P.rounds = reinterpret_cast<const RoundDesc*>(q->ring_dev + off);
-    P.ops = reinterpret_cast<const RegOp*>(q->ring_dev + off + rounds_bytes);
-    P.mats = reinterpret_cast<const double2*>(q->ring_dev + off + rounds_bytes + ops_bytes);
+    P.n_ops = (int)hot.size();
+    P.rounds = reinterpret_cast<const RoundDesc*>(dp);
+    P.hot = reinterpret_cast<const HotOp*>(dp + rounds_bytes);
+    P.cold = reinterpret_cast<const ColdOp*>(dp + rounds_bytes + hot_bytes);
+    P.hi_off = reinterpret_cast<const uint64_t*>(dp + rounds_bytes + hot_bytes + cold_bytes);
+    P.mats = reinterpret_cast<const double2*>(dp + rounds_bytes + hot_bytes + cold_bytes + hi_bytes);
 
     const size_t smem = regtile_smem_bytes(P.k, P.n_rounds, P.n_ops);
     if (smem > 227 * 1024) return QVM_OK;          // let the v1 path (or its error) handle it
@@ -668,13 +723,17 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
     if (n_tiles > 0x7fffffffull) return fail(QVM_ERR_UNSUPPORTED, "too many tiles for one launch");
     const unsigned threads = 1u << (n_tile - 4);
     if (threads > 256) rc = launch_regtile<512, 1>(q, (unsigned)n_tiles, threads, smem, P);
+#ifdef QVM_REGTILE_ONE_CTA
+    else rc = launch_regtile<256, 1>(q, (unsigned)n_tiles, threads, smem, P);
+#else
     else rc = launch_regtile<256, 2>(q, (unsigned)n_tiles, threads, smem, P);
+#endif
     if (rc) return rc;
     q->stats.kernel_launches += 1;
     q->stats.gate_ops += (uint64_t)n;
     q->stats.hbm_passes += 1;
     q->stats.hbm_bytes += 32ull * q->n_elems;
-    q->stats.h2d_bytes += rounds_bytes + ops_bytes + mats_bytes;
+    q->stats.h2d_bytes += total_bytes;
     q->stats.regtile_rounds += (uint64_t)rdesc.size();
     *handled = true;
     return QVM_OK;

@@ -11,64 +11,82 @@
 // bits on the five lowest tile bits so every warp access is a run of contiguous 16-byte elements.
 //
 // HBM traffic per launch: one read + one write of the shard, independent of the number of gates.
+//
+// The op stream is interpreted, so instruction economy per op matters more than anything else
+// (profiles/): one 16-byte "hot" word per op, a dense opcode for a jump table, ops that are
+// inactive for this CTA encoded as an impossible thread mask, everything CTA-uniform precomputed by
+// the prologue.
 #pragma once
 #include "qvm_kernels.cuh"
 
 namespace qvm {
 
-enum : uint8_t {
-    RK_DENSE1 = 1,   // generic 2x2 on register slot b0 (controls anywhere)
-    RK_X = 2,        // swap the pair: free (slot relabelling) unless a control sits on a register slot
-    RK_H = 3,        // uncontrolled (a+b, a-b) * s ; the scale goes into the thread scalar
-    RK_DENSE2 = 4,   // generic 4x4 on slot pair b0: 0 -> (msb=1, lsb=0), 1 -> (msb=3, lsb=2)
-    RK_DIAG_T = 5,   // diagonal with no register-slot involvement: one scalar for the whole thread
-    RK_DIAG_S = 6,   // per-thread scalar applied to the slots selected by register-slot controls
-    RK_DIAG1 = 7,    // exactly one diagonal target on register slot b0 (+ thread / outer targets)
-    RK_DIAG_R = 8,   // generic: two or more diagonal targets on register slots
+// Dense opcode space (host assigns; the switch compiles to a jump table).
+enum : uint32_t {
+    OPC_X_RELABEL = 0,    // X / CNOT with no register-slot control: flips a bit of the slot relabel mask
+    OPC_H0 = 1,           // +slot: uncontrolled Hadamard butterfly (scale folded into the round scalar)
+    OPC_D1_0 = 5,         // +slot: generic 2x2
+    OPC_XS_0 = 9,         // +slot: X with a control on a register slot: real pair swaps
+    OPC_D2_0 = 13,        // +pair: generic 4x4 on slots (1,0) / (3,2)
+    OPC_DIAG_T = 15,      // diagonal, no register-slot involvement: one scalar for the thread
+    OPC_DIAG_S = 16,      // per-thread scalar on the slots selected by register-slot controls
+    OPC_DIAG1_0 = 17,     // +slot: one diagonal target on a register slot
+    OPC_DIAG_G = 21,      // generic diagonal (several register-slot targets or > 2 thread targets)
+    OPC_COUNT = 22,
 };
+
+// x: [7:0] opcode | [11:8] crm (register-slot control mask) | [15:12] b (slot for X_RELABEL)
+//    | [23:16] s0 | [31:24] s1           (index weights, as shifts, of the two thread-bit targets)
+// y: [15:0] cthr (thread-bit control mask; 0xFFFF = op inactive for this CTA)
+//    | [23:16] p0 | [31:24] p1           (thread-bit positions of those targets; 31 = none)
+// z: mat_off (double2 units)
+// w: [7:0] oi (index bits from outer targets, patched per CTA) | [15:8] shr (DIAG1: weight shift of
+//    the register-slot target)
+struct __align__(16) HotOp {
+    uint32_t x, y, z, w;
+};
+
+// Read only by the prologue (one thread per op) and by the generic diagonal path.
+struct __align__(16) ColdOp {
+    uint64_t ctrl_outer;      // physical control mask outside the tile (incl. global positions)
+    uint8_t loc[6];           // diagonal targets MSB first: class | index
+    uint8_t k;
+    uint8_t pad[1];
+    uint64_t pad2[2];
+};
+static_assert(sizeof(ColdOp) == 32, "ColdOp layout");
 
 enum : uint8_t { LOC_REG = 0x00, LOC_THR = 0x40, LOC_OUT = 0x80, LOC_CLASS = 0xC0, LOC_INDEX = 0x3F };
 
-// 32 bytes; the first 16 are everything the hot loop needs (one LDS.128).
-struct __align__(16) RegOp {
-    uint32_t w0;          // kind | b0 << 8 | k << 16 | ctrl_reg << 24
-    uint32_t w1;          // ctrl_thr (16 bits) | loc[4] << 16 | loc[5] << 24
-    uint32_t mat_off;     // double2 offset into mats
-    uint32_t loc03;       // loc[0..3], one byte each: diagonal targets MSB first (class | index)
-    uint64_t ctrl_outer;  // physical mask (non-tile local + global positions)
-    uint64_t pad;
-};
-static_assert(sizeof(RegOp) == 32, "RegOp layout");
-
-__host__ __device__ __forceinline__ uint32_t regop_loc(uint32_t loc03, uint32_t w1, int t) {
-    return t < 4 ? ((loc03 >> (8 * t)) & 0xFFu) : ((w1 >> (16 + 8 * (t - 4))) & 0xFFu);
-}
-
 struct __align__(16) RoundDesc {
-    uint8_t reg_bit[4];   // tile-local bit of register slot s
-    uint8_t thr_bit[9];   // tile-local bit of thread bit b (ascending)
-    uint8_t pad[3];
+    uint8_t reg_bit[4];       // tile-local bit of register slot s
+    uint8_t reg_sorted[4];    // the same four bits, ascending (for the insert-zero thread mapping)
+    uint8_t reg_phys[4];      // physical position of register slot s (global I/O rounds)
     uint16_t op_begin, op_end;
-    uint8_t pad2[12];
+    double scale;             // real scalar applied in this round (product of folded H scales)
+    uint8_t pad[8];
 };
 static_assert(sizeof(RoundDesc) == 32, "RoundDesc layout");
 
 struct RegTileParams {
     int n_local;
     int k;
+    int low;                  // tile_pos[j] == j for j < low
     int n_rounds;
     int n_ops;
-    uint64_t tile_mask;
+    int n_runs;               // runs of consecutive non-tile positions
     uint64_t shard_bits;
-    uint8_t tile_pos[16];
+    uint8_t run_start[16];
+    uint8_t run_len[16];
     const RoundDesc* rounds;
-    const RegOp* ops;
+    const HotOp* hot;
+    const ColdOp* cold;
     const double2* mats;
+    const uint64_t* hi_off;   // [2^(k-low)] global offset contributed by tile-index bits >= low
 };
 
 // Bank-conflict swizzle for the double2 tile: XOR index bits 3..6 into bits 0..2 so that (almost)
-// any three "lowest thread bits" land in distinct 16-byte bank groups.  Linear: sw(a|b) = sw(a)^sw(b)
-// for disjoint a, b.
+// any three "lowest thread bits" land in distinct 16-byte bank groups.  Linear over XOR.
 __device__ __forceinline__ uint32_t swz(uint32_t i) {
     uint32_t x = i;
     x ^= ((i >> 3) & 1u) * 3u;
@@ -78,17 +96,34 @@ __device__ __forceinline__ uint32_t swz(uint32_t i) {
     return x;
 }
 
+__device__ __forceinline__ double flip_sign(double v, uint32_t sign_bit) {
+    return __hiloint2double(__double2hiint(v) ^ (int)sign_bit, __double2loint(v));
+}
+
 // Physical register p holds logical slot (p ^ xm): thread-uniform X / CNOT only flips bits of xm.
-// A register-slot control mask crm is therefore tested on the logical index: ((p ^ xm) & crm) == crm.
+// A register-slot control mask crm is tested on the logical index:
+//   ((p ^ xm) & crm) == crm  <=>  (p & crm) == (crm & ~xm) =: want.
 
 template <int B>
-__device__ __forceinline__ void reg_dense1(double2 (&a)[16], double2 m00, double2 m01, double2 m10, double2 m11,
-                                           const uint32_t crm, const uint32_t xm) {
-    if ((xm >> B) & 1u) {          // logical 0/1 live in physical 1/0: use the index-flipped matrix
-        double2 t = m00; m00 = m11; m11 = t;
-        t = m01; m01 = m10; m10 = t;
+__device__ __forceinline__ void reg_h(double2 (&a)[16], const uint32_t sign_bit) {
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        const int i0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1));
+        const int i1 = i0 | (1 << B);
+        const double2 x0 = a[i0], x1 = a[i1];
+        a[i0] = make_double2(x0.x + x1.x, x0.y + x1.y);
+        // logical (l0 - l1): the physical difference, negated when slots 0/1 are relabelled
+        a[i1] = make_double2(flip_sign(x0.x - x1.x, sign_bit), flip_sign(x0.y - x1.y, sign_bit));
     }
-    const uint32_t want = crm & ~xm;      // (p ^ xm) & crm == crm  <=>  p & crm == crm & ~xm
+}
+
+template <int B>
+__device__ __forceinline__ void reg_dense1(double2 (&a)[16], const double2* __restrict__ mat, const uint32_t crm,
+                                           const uint32_t xm) {
+    const uint32_t flip = ((xm >> B) & 1u) ? 3u : 0u;      // relabelled slots: index-flipped matrix
+    const double2 m00 = __ldg(&mat[0 ^ flip]), m01 = __ldg(&mat[1 ^ flip]), m10 = __ldg(&mat[2 ^ flip]),
+                  m11 = __ldg(&mat[3 ^ flip]);
+    const uint32_t want = crm & ~xm;
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
         const int i0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1));
@@ -105,7 +140,7 @@ __device__ __forceinline__ void reg_dense1(double2 (&a)[16], double2 m00, double
 }
 
 template <int B>
-__device__ __forceinline__ void reg_x(double2 (&a)[16], const uint32_t crm, const uint32_t xm) {
+__device__ __forceinline__ void reg_xswap(double2 (&a)[16], const uint32_t crm, const uint32_t xm) {
     const uint32_t want = crm & ~xm;
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
@@ -116,19 +151,6 @@ __device__ __forceinline__ void reg_x(double2 (&a)[16], const uint32_t crm, cons
             a[i0] = a[i1];
             a[i1] = x0;
         }
-    }
-}
-
-// (l0 + l1, l0 - l1); afterwards logical 0 sits in physical 0 (the caller clears bit B of xm).
-template <int B>
-__device__ __forceinline__ void reg_h(double2 (&a)[16], const double sgn) {
-#pragma unroll
-    for (int p = 0; p < 8; ++p) {
-        const int i0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1));
-        const int i1 = i0 | (1 << B);
-        const double2 x0 = a[i0], x1 = a[i1];
-        a[i0] = make_double2(x0.x + x1.x, x0.y + x1.y);
-        a[i1] = make_double2(sgn * (x0.x - x1.x), sgn * (x0.y - x1.y));
     }
 }
 
@@ -158,11 +180,24 @@ __device__ __forceinline__ void reg_dense2(double2 (&a)[16], const double2* __re
     }
 }
 
+template <int B>
+__device__ __forceinline__ void reg_diag1(double2 (&a)[16], double2 d0, double2 d1, const uint32_t crm,
+                                          const uint32_t xm) {
+    if ((xm >> B) & 1u) {
+        const double2 t = d0;
+        d0 = d1;
+        d1 = t;
+    }
+    const uint32_t want = crm & ~xm;
+#pragma unroll
+    for (int p = 0; p < 16; ++p)
+        if ((p & crm) == want) a[p] = cmul(((p >> B) & 1) ? d1 : d0, a[p]);
+}
+
 __host__ __device__ inline size_t regtile_smem_bytes(int k, int n_rounds, int n_ops) {
     size_t b = n_rounds > 1 ? ((size_t)16 << k) : 0;
-    b += (size_t)n_ops * sizeof(RegOp);
+    b += (size_t)n_ops * sizeof(HotOp);
     b += (size_t)n_rounds * sizeof(RoundDesc);
-    b += (((size_t)n_ops * 2 + 15) / 16) * 16;
     return b;
 }
 
@@ -172,70 +207,71 @@ regtile_kernel(double2* __restrict__ state, const RegTileParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const size_t tile_bytes = P.n_rounds > 1 ? ((size_t)16 << P.k) : 0;
     double2* tile = reinterpret_cast<double2*>(smem_raw);
-    RegOp* ops = reinterpret_cast<RegOp*>(smem_raw + tile_bytes);
-    RoundDesc* rounds = reinterpret_cast<RoundDesc*>(ops + P.n_ops);
-    uint8_t* op_active = reinterpret_cast<uint8_t*>(rounds + P.n_rounds);
-    uint8_t* op_outer_idx = op_active + P.n_ops;
+    HotOp* hot = reinterpret_cast<HotOp*>(smem_raw + tile_bytes);
+    RoundDesc* rounds = reinterpret_cast<RoundDesc*>(hot + P.n_ops);
 
     const uint32_t tid = threadIdx.x;
     const uint32_t nthreads = blockDim.x;
-    const int n_thr_bits = P.k - 4;
 
+    // outer bits of this tile: deposit blockIdx into the runs of non-tile positions
     uint64_t base = 0;
     {
         uint64_t t = blockIdx.x;
-        for (int p = 0; p < P.n_local; ++p)
-            if (!((P.tile_mask >> p) & 1ull)) {
-                base |= (t & 1ull) << p;
-                t >>= 1;
-            }
+        for (int r = 0; r < P.n_runs; ++r) {
+            const uint32_t len = P.run_len[r];
+            base |= (t & ((1ull << len) - 1ull)) << P.run_start[r];
+            t >>= len;
+        }
     }
     const uint64_t full = base | P.shard_bits;
 
-    {   // stage descriptors
-        const uint32_t words = (uint32_t)(P.n_ops * (sizeof(RegOp) / 16));
-        const uint4* src = reinterpret_cast<const uint4*>(P.ops);
-        uint4* dst = reinterpret_cast<uint4*>(ops);
-        for (uint32_t w = tid; w < words; w += nthreads) dst[w] = __ldg(&src[w]);
+    // stage descriptors; one thread per op evaluates what is uniform over the CTA
+    for (uint32_t j = tid; j < (uint32_t)P.n_ops; j += nthreads) {
+        uint4 h = __ldg(reinterpret_cast<const uint4*>(&P.hot[j]));
+        const ColdOp* c = &P.cold[j];
+        const uint64_t co = __ldg(&c->ctrl_outer);
+        if ((full & co) != co) h.y |= 0xFFFFu;           // inactive here: impossible thread mask
+        const uint32_t opc = h.x & 0xFFu;
+        if (opc >= OPC_DIAG_T) {
+            const uint32_t kk = c->k;
+            uint32_t oi = 0;
+            for (uint32_t t = 0; t < kk; ++t) {
+                const uint32_t loc = c->loc[t];
+                if ((loc & LOC_CLASS) == LOC_OUT) oi |= (uint32_t)((full >> (loc & LOC_INDEX)) & 1ull) << (kk - 1 - t);
+            }
+            h.w |= oi;
+        }
+        *reinterpret_cast<uint4*>(&hot[j]) = h;
+    }
+    {
         const uint32_t rwords = (uint32_t)(P.n_rounds * (sizeof(RoundDesc) / 16));
         const uint4* rsrc = reinterpret_cast<const uint4*>(P.rounds);
         uint4* rdst = reinterpret_cast<uint4*>(rounds);
         for (uint32_t w = tid; w < rwords; w += nthreads) rdst[w] = __ldg(&rsrc[w]);
     }
-    for (int j = tid; j < P.n_ops; j += nthreads) {
-        const RegOp* g = &P.ops[j];
-        const uint64_t co = g->ctrl_outer;
-        op_active[j] = ((full & co) == co) ? 1 : 0;
-        const uint32_t w0 = g->w0, w1 = g->w1, loc03 = g->loc03;
-        const uint32_t kind = w0 & 0xFFu, k = (w0 >> 16) & 0xFFu;
-        uint32_t oi = 0;
-        if (kind >= RK_DIAG_T)
-            for (uint32_t t = 0; t < k; ++t) {
-                const uint32_t loc = regop_loc(loc03, w1, (int)t);
-                if ((loc & LOC_CLASS) == LOC_OUT) oi |= (uint32_t)((full >> (loc & LOC_INDEX)) & 1ull) << (k - 1 - t);
-            }
-        op_outer_idx[j] = (uint8_t)oi;
-    }
     __syncthreads();
 
     double2 a[16];
     double2* gbase = state + base;
+    const uint32_t low_mask = (1u << P.low) - 1u;
 
     for (int r = 0; r < P.n_rounds; ++r) {
-        const RoundDesc& rd = rounds[r];
-        // tile-local index contributed by this thread, and by each register slot bit
-        uint32_t T = 0;
-        for (int b = 0; b < n_thr_bits; ++b)
-            if ((tid >> b) & 1u) T |= 1u << rd.thr_bit[b];
-        const uint32_t J0 = 1u << rd.reg_bit[0], J1 = 1u << rd.reg_bit[1], J2 = 1u << rd.reg_bit[2],
-                       J3 = 1u << rd.reg_bit[3];
+        const uint4 rw = *reinterpret_cast<const uint4*>(&rounds[r]);      // reg_bit | reg_sorted | reg_phys | op range
+        const uint2 rw2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(&rounds[r]) + 16);
+        // tile index of this thread: tid with zeros inserted at the (ascending) register-bit positions
+        uint32_t T = tid;
+        T = insert_zero32(T, rw.y & 0xFFu);
+        T = insert_zero32(T, (rw.y >> 8) & 0xFFu);
+        T = insert_zero32(T, (rw.y >> 16) & 0xFFu);
+        T = insert_zero32(T, rw.y >> 24);
+        const uint32_t J0 = 1u << (rw.x & 0xFFu), J1 = 1u << ((rw.x >> 8) & 0xFFu), J2 = 1u << ((rw.x >> 16) & 0xFFu),
+                       J3 = 1u << (rw.x >> 24);
+        const uint32_t op_begin = rw.w & 0xFFFFu, op_end = rw.w >> 16;
 
         if (r == 0) {
-            uint64_t gT = 0;
-            for (int b = 0; b < n_thr_bits; ++b)
-                if ((tid >> b) & 1u) gT |= 1ull << P.tile_pos[rd.thr_bit[b]];
-            const uint64_t g0 = 1ull << P.tile_pos[rd.reg_bit[0]], g1 = 1ull << P.tile_pos[rd.reg_bit[1]],
-                           g2 = 1ull << P.tile_pos[rd.reg_bit[2]], g3 = 1ull << P.tile_pos[rd.reg_bit[3]];
+            const uint64_t gT = (uint64_t)(T & low_mask) | __ldg(&P.hi_off[T >> P.low]);
+            const uint64_t g0 = 1ull << (rw.z & 0xFFu), g1 = 1ull << ((rw.z >> 8) & 0xFFu),
+                           g2 = 1ull << ((rw.z >> 16) & 0xFFu), g3 = 1ull << (rw.z >> 24);
             const double2* src = gbase + gT;
 #pragma unroll
             for (int j = 0; j < 16; ++j)
@@ -247,110 +283,46 @@ regtile_kernel(double2* __restrict__ state, const RegTileParams P) {
                 a[j] = tile[sT ^ ((j & 1) ? s0 : 0) ^ ((j & 2) ? s1 : 0) ^ ((j & 4) ? s2 : 0) ^ ((j & 8) ? s3 : 0)];
         }
 
-        double2 ts = make_double2(1.0, 0.0);     // per-thread scalar accumulated by H scales / DIAG_T
-        bool ts_dirty = false;
+        const double rscale = __hiloint2double((int)rw2.y, (int)rw2.x);
+        double2 ts = make_double2(rscale, 0.0);   // per-thread scalar: folded H scales and DIAG_T factors
+        bool ts_dirty = rscale != 1.0;
         uint32_t xm = 0;                          // physical register p holds logical slot p ^ xm
 
-        for (int o = rd.op_begin; o < rd.op_end; ++o) {
-            const uint4 w = *reinterpret_cast<const uint4*>(&ops[o]);
-            const uint32_t kind = w.x & 0xFFu, b0 = (w.x >> 8) & 0xFFu, k = (w.x >> 16) & 0xFFu, crm = w.x >> 24;
+        for (uint32_t o = op_begin; o < op_end; ++o) {
+            const uint4 w = *reinterpret_cast<const uint4*>(&hot[o]);
             const uint32_t cthr = w.y & 0xFFFFu;
-            const bool ok = op_active[o] && ((tid & cthr) == cthr);
+            if ((tid & cthr) != cthr) continue;           // a control on a thread bit is 0, or op inactive here
+            const uint32_t opc = w.x & 0xFFu;
+            const uint32_t crm = (w.x >> 8) & 0xFu;
             const double2* mat = P.mats + w.z;
-            switch (kind) {
-                case RK_X: {
-                    if (crm == 0) {                      // thread-uniform: relabel, no data movement
-                        if (ok) xm ^= 1u << b0;
-                        break;
-                    }
-                    if (!ok) break;
-                    switch (b0) {
-                        case 0: reg_x<0>(a, crm, xm); break;
-                        case 1: reg_x<1>(a, crm, xm); break;
-                        case 2: reg_x<2>(a, crm, xm); break;
-                        default: reg_x<3>(a, crm, xm); break;
-                    }
-                    break;
-                }
-                case RK_H: {
-                    const double sgn = ((xm >> b0) & 1u) ? -1.0 : 1.0;
-                    switch (b0) {
-                        case 0: reg_h<0>(a, sgn); break;
-                        case 1: reg_h<1>(a, sgn); break;
-                        case 2: reg_h<2>(a, sgn); break;
-                        default: reg_h<3>(a, sgn); break;
-                    }
-                    xm &= ~(1u << b0);
-                    const double sc = __ldg(&mat[0]).x;
-                    ts.x *= sc;
-                    ts.y *= sc;
-                    ts_dirty = true;
-                    break;
-                }
-                case RK_DENSE1: {
-                    if (!ok) break;
-                    const double2 m00 = __ldg(&mat[0]), m01 = __ldg(&mat[1]), m10 = __ldg(&mat[2]), m11 = __ldg(&mat[3]);
-                    switch (b0) {
-                        case 0: reg_dense1<0>(a, m00, m01, m10, m11, crm, xm); break;
-                        case 1: reg_dense1<1>(a, m00, m01, m10, m11, crm, xm); break;
-                        case 2: reg_dense1<2>(a, m00, m01, m10, m11, crm, xm); break;
-                        default: reg_dense1<3>(a, m00, m01, m10, m11, crm, xm); break;
-                    }
-                    break;
-                }
-                case RK_DENSE2: {
-                    if (!ok) break;
-                    if (b0 == 0) reg_dense2<0>(a, mat, crm, xm);
-                    else reg_dense2<1>(a, mat, crm, xm);
-                    break;
-                }
-                case RK_DIAG_T:
-                case RK_DIAG_S:
-                case RK_DIAG1: {
-                    if (!ok) break;
-                    uint32_t idx = op_outer_idx[o];
-                    uint32_t sh1 = 0;                    // index weight of the register-slot target (DIAG1)
-                    for (uint32_t t = 0; t < k; ++t) {
-                        const uint32_t loc = regop_loc(w.w, w.y, (int)t);
-                        const uint32_t bit = 1u << (k - 1 - t);
-                        if ((loc & LOC_CLASS) == LOC_THR) idx |= ((tid >> (loc & LOC_INDEX)) & 1u) ? bit : 0u;
-                        else if ((loc & LOC_CLASS) == LOC_REG) sh1 = bit;
-                    }
-                    if (kind == RK_DIAG_T) {
-                        ts = cmul(__ldg(&mat[idx]), ts);
-                        ts_dirty = true;
-                        break;
-                    }
-                    const uint32_t want = crm & ~xm;
-                    if (kind == RK_DIAG_S) {
-                        const double2 d = __ldg(&mat[idx]);
-#pragma unroll
-                        for (int p = 0; p < 16; ++p)
-                            if ((p & crm) == want) a[p] = cmul(d, a[p]);
-                        break;
-                    }
-                    double2 d0 = __ldg(&mat[idx]), d1 = __ldg(&mat[idx | sh1]);
-                    if ((xm >> b0) & 1u) {
-                        const double2 t = d0; d0 = d1; d1 = t;
-                    }
-                    const uint32_t sm = 1u << b0;
-#pragma unroll
-                    for (int p = 0; p < 16; ++p)
-                        if ((p & crm) == want) {
-                            const bool hi = (p & sm) != 0;
-                            const double2 d = make_double2(hi ? d1.x : d0.x, hi ? d1.y : d0.y);
-                            a[p] = cmul(d, a[p]);
-                        }
-                    break;
-                }
-                case RK_DIAG_R: {
-                    if (!ok) break;
-                    uint32_t idx = op_outer_idx[o];
+            if (opc == OPC_X_RELABEL) { xm ^= 1u << ((w.x >> 12) & 0xFu); continue; }
+            if (opc < OPC_D1_0) {                 // Hadamard butterfly on slot opc - OPC_H0
+                if (opc == OPC_H0 + 0) { reg_h<0>(a, (xm & 1u) << 31); xm &= ~1u; }
+                else if (opc == OPC_H0 + 1) { reg_h<1>(a, (xm & 2u) << 30); xm &= ~2u; }
+                else if (opc == OPC_H0 + 2) { reg_h<2>(a, (xm & 4u) << 29); xm &= ~4u; }
+                else { reg_h<3>(a, (xm & 8u) << 28); xm &= ~8u; }
+                continue;
+            }
+            switch (opc) {
+                case OPC_D1_0 + 0: reg_dense1<0>(a, mat, crm, xm); break;
+                case OPC_D1_0 + 1: reg_dense1<1>(a, mat, crm, xm); break;
+                case OPC_D1_0 + 2: reg_dense1<2>(a, mat, crm, xm); break;
+                case OPC_D1_0 + 3: reg_dense1<3>(a, mat, crm, xm); break;
+                case OPC_XS_0 + 0: reg_xswap<0>(a, crm, xm); break;
+                case OPC_XS_0 + 1: reg_xswap<1>(a, crm, xm); break;
+                case OPC_XS_0 + 2: reg_xswap<2>(a, crm, xm); break;
+                case OPC_XS_0 + 3: reg_xswap<3>(a, crm, xm); break;
+                case OPC_D2_0 + 0: reg_dense2<0>(a, mat, crm, xm); break;
+                case OPC_D2_0 + 1: reg_dense2<1>(a, mat, crm, xm); break;
+                case OPC_DIAG_G: {
+                    const ColdOp* c = &P.cold[o];
+                    const uint32_t kk = c->k;
+                    uint32_t idx = w.w & 0xFFu;
                     uint32_t rm0 = 0, rm1 = 0, rm2 = 0, rm3 = 0, rs0 = 0, rs1 = 0, rs2 = 0, rs3 = 0;
-                    for (uint32_t t = 0; t < k; ++t) {
-                        const uint32_t loc = regop_loc(w.w, w.y, (int)t);
+                    for (uint32_t t = 0; t < kk; ++t) {
+                        const uint32_t loc = c->loc[t];
                         const uint32_t cls = loc & LOC_CLASS;
-                        const uint32_t sh = 1u << (k - 1 - t);
+                        const uint32_t sh = 1u << (kk - 1 - t);
                         if (cls == LOC_THR) idx |= ((tid >> (loc & LOC_INDEX)) & 1u) ? sh : 0u;
                         else if (cls == LOC_REG) {
                             const uint32_t slot = loc & LOC_INDEX;       // each slot appears at most once
@@ -372,7 +344,30 @@ regtile_kernel(double2* __restrict__ state, const RegTileParams P) {
                     }
                     break;
                 }
-                default: break;
+                default: {      // OPC_DIAG_T, OPC_DIAG_S, OPC_DIAG1_0 + slot
+                    // index bits from (at most two) thread-bit targets; position 31 means "none"
+                    const uint32_t idx = (w.w & 0xFFu) | (((tid >> ((w.y >> 16) & 0xFFu)) & 1u) << ((w.x >> 16) & 0xFFu)) |
+                                         (((tid >> (w.y >> 24)) & 1u) << (w.x >> 24));
+                    const double2 d0 = __ldg(&mat[idx]);
+                    if (opc == OPC_DIAG_T) {
+                        ts = cmul(d0, ts);
+                        ts_dirty = true;
+                    } else if (opc == OPC_DIAG_S) {
+                        const uint32_t want = crm & ~xm;
+#pragma unroll
+                        for (int p = 0; p < 16; ++p)
+                            if ((p & crm) == want) a[p] = cmul(d0, a[p]);
+                    } else {
+                        const double2 d1 = __ldg(&mat[idx | (1u << ((w.w >> 8) & 0xFFu))]);
+                        switch (opc - OPC_DIAG1_0) {
+                            case 0: reg_diag1<0>(a, d0, d1, crm, xm); break;
+                            case 1: reg_diag1<1>(a, d0, d1, crm, xm); break;
+                            case 2: reg_diag1<2>(a, d0, d1, crm, xm); break;
+                            default: reg_diag1<3>(a, d0, d1, crm, xm); break;
+                        }
+                    }
+                    break;
+                }
             }
         }
 
@@ -382,17 +377,15 @@ regtile_kernel(double2* __restrict__ state, const RegTileParams P) {
         }
 
         if (r == P.n_rounds - 1) {
-            uint64_t gT = 0;
-            for (int b = 0; b < n_thr_bits; ++b)
-                if ((tid >> b) & 1u) gT |= 1ull << P.tile_pos[rd.thr_bit[b]];
-            const uint64_t g0 = 1ull << P.tile_pos[rd.reg_bit[0]], g1 = 1ull << P.tile_pos[rd.reg_bit[1]],
-                           g2 = 1ull << P.tile_pos[rd.reg_bit[2]], g3 = 1ull << P.tile_pos[rd.reg_bit[3]];
+            const uint64_t g0 = 1ull << (rw.z & 0xFFu), g1 = 1ull << ((rw.z >> 8) & 0xFFu),
+                           g2 = 1ull << ((rw.z >> 16) & 0xFFu), g3 = 1ull << (rw.z >> 24);
             // register p holds logical slot p ^ xm; the slot -> address map is XOR-linear
-            const uint64_t gx = ((xm & 1) ? g0 : 0) | ((xm & 2) ? g1 : 0) | ((xm & 4) ? g2 : 0) | ((xm & 8) ? g3 : 0);
-            double2* dst = gbase + gT;
+            const uint64_t gT = ((uint64_t)(T & low_mask) | __ldg(&P.hi_off[T >> P.low])) ^
+                                (((xm & 1) ? g0 : 0) | ((xm & 2) ? g1 : 0) | ((xm & 4) ? g2 : 0) | ((xm & 8) ? g3 : 0));
+            double2* dst = gbase;
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-                dst[gx ^ (((j & 1) ? g0 : 0) | ((j & 2) ? g1 : 0) | ((j & 4) ? g2 : 0) | ((j & 8) ? g3 : 0))] = a[j];
+                dst[gT ^ (((j & 1) ? g0 : 0) | ((j & 2) ? g1 : 0) | ((j & 4) ? g2 : 0) | ((j & 8) ? g3 : 0))] = a[j];
         } else {
             // same mapping as this round's load: every thread rewrites exactly the slots it read
             const uint32_t s0 = swz(J0), s1 = swz(J1), s2 = swz(J2), s3 = swz(J3);

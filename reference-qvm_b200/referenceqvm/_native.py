@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqvm_b200.so")
+LIB_PATH = os.environ.get("QVM_B200_LIB") or os.path.join(_HERE, "libqvm_b200.so")   # env override: A/B builds
 
 QVM_OK, QVM_ERR_INVALID, QVM_ERR_CUDA, QVM_ERR_NOMEM, QVM_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 OP_NOP, OP_DENSE, OP_DIAG = 0, 1, 2
