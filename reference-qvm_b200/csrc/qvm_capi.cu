@@ -513,41 +513,52 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
     }
 
     // ---- rounds: greedy, commutation aware ------------------------------------------------------
+    // Dense ops choose the rounds (each needs its targets in register slots).  Diagonal ops float:
+    // they commute with everything except dense ops on their own qubits, so each is placed, inside
+    // the window those neighbours leave, in the round where it touches the fewest register bits
+    // (ideally none: then it is one scalar per thread instead of work on all 16 slots).
     const uint32_t all_bits = (1u << n_tile) - 1u;
     const uint32_t high_bits = all_bits & ~0x1Fu;          // lanes keep the five lowest tile bits in I/O rounds
     const int n = (int)lops.size();
-    std::vector<char> done(n, 0);
+    std::vector<int> dense_idx;
+    for (int i = 0; i < n; ++i)
+        if (lops[i].kind == QVM_OP_DENSE) dense_idx.push_back(i);
+    std::vector<int> round_of(n, -1);          // earliest legal round of every op (all-ops greedy)
     std::vector<PlannedRound> rounds;
-    int remaining = n;
-    while (remaining > 0) {
-        PlannedRound rd;
-        const uint32_t allowed = rounds.empty() ? high_bits : all_bits;
-        uint32_t blocked_dense = 0, blocked_diag = 0;
-        for (int i = 0; i < n; ++i) {
-            if (done[i]) continue;
-            const LocalOp& op = lops[i];
-            const bool clash = (op.dense_mask & (blocked_dense | blocked_diag)) || (op.diag_mask & blocked_dense);
-            bool ok = !clash;
-            if (ok && op.kind == QVM_OP_DENSE) {
-                PlannedRound trial = rd;
-                ok = place_dense(trial, op, allowed);
-                if (ok) memcpy(rd.slot_bit, trial.slot_bit, sizeof(rd.slot_bit));
+    {
+        std::vector<char> done(n, 0);
+        int remaining = n;
+        while (remaining > 0) {
+            PlannedRound rd;
+            const uint32_t allowed = rounds.empty() ? high_bits : all_bits;
+            uint32_t blocked_dense = 0, blocked_diag = 0;
+            int placed = 0;
+            for (int i = 0; i < n; ++i) {
+                if (done[i]) continue;
+                const LocalOp& op = lops[i];
+                const bool clash = (op.dense_mask & (blocked_dense | blocked_diag)) || (op.diag_mask & blocked_dense);
+                bool ok = !clash;
+                if (ok && op.kind == QVM_OP_DENSE) {
+                    PlannedRound trial = rd;
+                    ok = place_dense(trial, op, allowed);
+                    if (ok) memcpy(rd.slot_bit, trial.slot_bit, sizeof(rd.slot_bit));
+                }
+                if (!ok) {
+                    blocked_dense |= op.dense_mask;
+                    blocked_diag |= op.diag_mask;
+                    continue;
+                }
+                round_of[i] = (int)rounds.size();
+                done[i] = 1;
+                ++placed;
             }
-            if (!ok) {
-                blocked_dense |= op.dense_mask;
-                blocked_diag |= op.diag_mask;
-                continue;
-            }
-            rd.ops.push_back(i);
+            remaining -= placed;
+            if (placed == 0 && !rounds.empty()) return fail(QVM_ERR_CUDA, "round planner made no progress");
+            rounds.push_back(rd);
         }
-        for (int i : rd.ops) done[i] = 1;
-        remaining -= (int)rd.ops.size();
-        if (rd.ops.empty() && !rounds.empty()) return fail(QVM_ERR_CUDA, "round planner made no progress");
-        rounds.push_back(rd);
     }
     if (rounds.size() > 1 && (rounds.back().regmask() & 0x1Fu)) rounds.push_back(PlannedRound());   // store round
     if (rounds.size() > 4096) return QVM_OK;
-
     // fill unused register slots with the highest free tile bits
     for (PlannedRound& rd : rounds) {
         uint32_t used = rd.regmask();
@@ -559,6 +570,32 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
                         used |= 1u << b;
                         break;
                     }
+    }
+
+    // place the floating diagonal ops
+    {
+        const int n_rounds = (int)rounds.size();
+        std::vector<uint32_t> regmask(n_rounds);
+        for (int r = 0; r < n_rounds; ++r) regmask[r] = rounds[r].regmask();
+        for (int i = 0; i < n; ++i) {
+            if (lops[i].kind == QVM_OP_DENSE) continue;
+            const uint32_t touched = lops[i].diag_mask;
+            const int lo = round_of[i];                 // earliest round that respects every dependency
+            int hi = n_rounds - 1;
+            for (int j : dense_idx)
+                if (j > i && (lops[j].dense_mask & touched)) hi = std::min(hi, round_of[j]);
+            if (hi < lo) hi = lo;      // cannot happen: a later conflicting dense op waits for this op
+            int best = lo, best_cost = 99;
+            for (int r = hi; r >= lo; --r) {       // prefer late rounds on ties: keeps early rounds lean
+                const int cost = __builtin_popcount(touched & regmask[r]);
+                if (cost < best_cost) {
+                    best_cost = cost;
+                    best = r;
+                }
+            }
+            round_of[i] = best;
+        }
+        for (int i = 0; i < n; ++i) rounds[round_of[i]].ops.push_back(i);     // ascending original index
     }
 
     // ---- encode ---------------------------------------------------------------------------------
