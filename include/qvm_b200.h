@@ -85,6 +85,8 @@ int qvm_set_stream(qvm_t* q, void* cuda_stream);
 int qvm_set_tile_bits(qvm_t* q, int tile_bits, int low_bits);   /* tuning: defaults 12 / 5      */
 /* 1 (default): register-tiled kernel where eligible; 0: shared-memory kernel only (testing).   */
 int qvm_set_kernel_path(qvm_t* q, int use_regtile);
+/* Debug: how many ops of each register-tile opcode were encoded so far (32 counters). */
+int qvm_debug_opcode_hist(qvm_t* q, uint64_t* out32);
 int qvm_n_local(const qvm_t* q);
 void* qvm_device_ptr(qvm_t* q);         /* raw amplitudes, for NCCL/P2P plumbing on the host     */
 void* qvm_stream(qvm_t* q);

@@ -71,6 +71,7 @@ struct qvm_state {
     size_t stage_bytes = 0;
     int measure_grid = 0;
     qvm_stats_t stats{};
+    uint64_t opc_hist[32] = {};
 };
 
 namespace {
@@ -603,6 +604,7 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
     std::vector<RoundDesc> rdesc(rounds.size());
     std::vector<HotOp> hot;
     std::vector<ColdOp> cold;
+    double group_scale = 1.0;        // all folded H scales, applied once in the last round
     hot.reserve(n);
     cold.reserve(n);
     for (size_t r = 0; r < rounds.size(); ++r) {
@@ -626,7 +628,28 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
         for (int b = 0; b < n_tile; ++b)
             if (slot_of[b] < 0) thr_of[b] = (int8_t)nt++;
         d.op_begin = (uint16_t)hot.size();
-        for (int i : rd.ops) {
+        // DIAG_T ops (no register-slot involvement in this round) commute with the whole round: emit
+        // them first so the kernel can run them as one batch
+        std::vector<int> order;
+        order.reserve(rd.ops.size());
+        auto is_diag_t = [&](const LocalOp& l) {
+            if (l.kind != QVM_OP_DIAG) return false;
+            int nthr = 0;
+            for (int b = 0; b < n_tile; ++b)
+                if (((l.ctrl_tile >> b) & 1u) && slot_of[b] >= 0) return false;
+            for (int t = 0; t < l.k; ++t) {
+                if (l.tgt[t] < 0) continue;
+                if (slot_of[l.tgt[t]] >= 0) return false;
+                ++nthr;
+            }
+            return nthr <= 2;
+        };
+        for (int i : rd.ops)
+            if (is_diag_t(lops[i])) order.push_back(i);
+        d.dt_end = (uint16_t)(hot.size() + order.size());
+        for (int i : rd.ops)
+            if (!is_diag_t(lops[i])) order.push_back(i);
+        for (int i : order) {
             const LocalOp& l = lops[i];
             HotOp h{0, 0, 0, 0};
             ColdOp c;
@@ -649,7 +672,7 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
                     } else opc = OPC_XS_0 + slot;
                 } else if (!l.ctrl_tile && !l.ctrl_outer && is_h_matrix(m)) {
                     opc = OPC_H0 + slot;
-                    d.scale *= m[0];
+                    group_scale *= m[0];
                 } else opc = OPC_D1_0 + slot;
             } else if (l.kind == QVM_OP_DENSE) {
                 const int sa = slot_of[l.tgt[0]];
@@ -688,18 +711,23 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
                     }
                 }
                 if (nreg >= 2 || nthr > 2) opc = OPC_DIAG_G;
-                else if (nreg == 1) opc = OPC_DIAG1_0 + reg_slot;
-                else opc = crm ? OPC_DIAG_S : OPC_DIAG_T;
+                else if (nreg == 1) opc = (crm ? OPC_DIAG1_0 : OPC_DIAG1NC_0) + reg_slot;
+                else if (!crm) opc = OPC_DIAG_T;
+                else if ((crm & (crm - 1)) == 0) opc = OPC_DIAG_S1_0 + (uint32_t)__builtin_ctz(crm);
+                else opc = OPC_DIAG_S;
             }
             h.x = opc | (crm << 8) | (xb << 12) | (s0 << 16) | (s1 << 24);
             h.y = cthr | (p0 << 16) | (p1 << 24);
             h.z = mat_off;
             h.w = (shr << 8);
+            q->opc_hist[opc & 31] += 1;
             hot.push_back(h);
             cold.push_back(c);
         }
         d.op_end = (uint16_t)hot.size();
     }
+
+    rdesc.back().scale = group_scale;
 
     // launch parameters that replace per-thread bit loops
     int low = 0;
@@ -713,9 +741,9 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
             if ((P_tile_mask >> p) & 1ull) { ++p; continue; }
             int e = p;
             while (e < q->n_local && !((P_tile_mask >> e) & 1ull)) ++e;
-            if (nr >= 16) return QVM_OK;        // pathological tile shape: let the v1 kernel take it
-            P.run_start[nr] = (uint8_t)p;
-            P.run_len[nr] = (uint8_t)(e - p);
+            if (nr >= 8) return QVM_OK;         // pathological tile shape: let the v1 kernel take it
+            P.run_start |= (uint64_t)p << (8 * nr);
+            P.run_len |= (uint64_t)(e - p) << (8 * nr);
             ++nr;
             p = e;
         }
@@ -927,6 +955,12 @@ int qvm_set_tile_bits(qvm_t* q, int tile_bits, int low_bits) {
 int qvm_set_kernel_path(qvm_t* q, int use_regtile) {
     QVM_CHECK_HANDLE(q);
     q->use_regtile = use_regtile ? 1 : 0;
+    return QVM_OK;
+}
+
+int qvm_debug_opcode_hist(qvm_t* q, uint64_t* out32) {
+    if (!q || !out32) return fail(QVM_ERR_INVALID, "null pointer");
+    memcpy(out32, q->opc_hist, sizeof(q->opc_hist));
     return QVM_OK;
 }
 

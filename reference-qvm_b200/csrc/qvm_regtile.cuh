@@ -32,7 +32,9 @@ enum : uint32_t {
     OPC_DIAG_S = 16,      // per-thread scalar on the slots selected by register-slot controls
     OPC_DIAG1_0 = 17,     // +slot: one diagonal target on a register slot
     OPC_DIAG_G = 21,      // generic diagonal (several register-slot targets or > 2 thread targets)
-    OPC_COUNT = 22,
+    OPC_DIAG_S1_0 = 22,   // +slot: DIAG_S whose only register-slot control is that slot (8 multiplies)
+    OPC_DIAG1NC_0 = 26,   // +slot: DIAG1 without register-slot controls (16 multiplies, no predicates)
+    OPC_COUNT = 30,
 };
 
 // x: [7:0] opcode | [11:8] crm (register-slot control mask) | [15:12] b (slot for X_RELABEL)
@@ -64,7 +66,8 @@ struct __align__(16) RoundDesc {
     uint8_t reg_phys[4];      // physical position of register slot s (global I/O rounds)
     uint16_t op_begin, op_end;
     double scale;             // real scalar applied in this round (product of folded H scales)
-    uint8_t pad[8];
+    uint16_t dt_end;          // ops [op_begin, dt_end) are DIAG_T (they commute with the whole round)
+    uint8_t pad[6];
 };
 static_assert(sizeof(RoundDesc) == 32, "RoundDesc layout");
 
@@ -76,8 +79,8 @@ struct RegTileParams {
     int n_ops;
     int n_runs;               // runs of consecutive non-tile positions
     uint64_t shard_bits;
-    uint8_t run_start[16];
-    uint8_t run_len[16];
+    uint64_t run_start;       // 8 x 8 bits: start position of each run
+    uint64_t run_len;         // 8 x 8 bits: length of each run
     const RoundDesc* rounds;
     const HotOp* hot;
     const ColdOp* cold;
@@ -194,6 +197,32 @@ __device__ __forceinline__ void reg_diag1(double2 (&a)[16], double2 d0, double2 
         if ((p & crm) == want) a[p] = cmul(((p >> B) & 1) ? d1 : d0, a[p]);
 }
 
+// scalar d on the 8 slots whose logical bit B is 1 (physical bit B is 0 when the slot is relabelled)
+template <int B>
+__device__ __forceinline__ void reg_diag_s1(double2 (&a)[16], const double2 d, const uint32_t xm) {
+    if ((xm >> B) & 1u) {
+#pragma unroll
+        for (int p = 0; p < 16; ++p)
+            if (!((p >> B) & 1)) a[p] = cmul(d, a[p]);
+    } else {
+#pragma unroll
+        for (int p = 0; p < 16; ++p)
+            if ((p >> B) & 1) a[p] = cmul(d, a[p]);
+    }
+}
+
+// d0 / d1 on every slot by its logical bit B, no controls
+template <int B>
+__device__ __forceinline__ void reg_diag1_nc(double2 (&a)[16], double2 d0, double2 d1, const uint32_t xm) {
+    if ((xm >> B) & 1u) {
+        const double2 t = d0;
+        d0 = d1;
+        d1 = t;
+    }
+#pragma unroll
+    for (int p = 0; p < 16; ++p) a[p] = cmul(((p >> B) & 1) ? d1 : d0, a[p]);
+}
+
 __host__ __device__ inline size_t regtile_smem_bytes(int k, int n_rounds, int n_ops) {
     size_t b = n_rounds > 1 ? ((size_t)16 << k) : 0;
     b += (size_t)n_ops * sizeof(HotOp);
@@ -218,8 +247,8 @@ regtile_kernel(double2* __restrict__ state, const RegTileParams P) {
     {
         uint64_t t = blockIdx.x;
         for (int r = 0; r < P.n_runs; ++r) {
-            const uint32_t len = P.run_len[r];
-            base |= (t & ((1ull << len) - 1ull)) << P.run_start[r];
+            const uint32_t len = (uint32_t)(P.run_len >> (8 * r)) & 0xFFu;
+            base |= (t & ((1ull << len) - 1ull)) << ((uint32_t)(P.run_start >> (8 * r)) & 0xFFu);
             t >>= len;
         }
     }
@@ -267,6 +296,7 @@ regtile_kernel(double2* __restrict__ state, const RegTileParams P) {
         const uint32_t J0 = 1u << (rw.x & 0xFFu), J1 = 1u << ((rw.x >> 8) & 0xFFu), J2 = 1u << ((rw.x >> 16) & 0xFFu),
                        J3 = 1u << (rw.x >> 24);
         const uint32_t op_begin = rw.w & 0xFFFFu, op_end = rw.w >> 16;
+        const uint32_t dt_end = *reinterpret_cast<const uint16_t*>(reinterpret_cast<const unsigned char*>(&rounds[r]) + 24);
 
         if (r == 0) {
             const uint64_t gT = (uint64_t)(T & low_mask) | __ldg(&P.hi_off[T >> P.low]);
@@ -288,7 +318,20 @@ regtile_kernel(double2* __restrict__ state, const RegTileParams P) {
         bool ts_dirty = rscale != 1.0;
         uint32_t xm = 0;                          // physical register p holds logical slot p ^ xm
 
-        for (uint32_t o = op_begin; o < op_end; ++o) {
+        // DIAG_T ops touch no register qubit of this round, so they commute with all of its ops:
+        // the host sorts them first and they run as one tight batch into the thread scalar.
+#pragma unroll 2
+        for (uint32_t o = op_begin; o < dt_end; ++o) {
+            const uint4 w = *reinterpret_cast<const uint4*>(&hot[o]);
+            const uint32_t cthr = w.y & 0xFFFFu;
+            if ((tid & cthr) != cthr) continue;
+            const uint32_t idx = (w.w & 0xFFu) | (((tid >> ((w.y >> 16) & 0xFFu)) & 1u) << ((w.x >> 16) & 0xFFu)) |
+                                 (((tid >> (w.y >> 24)) & 1u) << (w.x >> 24));
+            ts = cmul(__ldg(&P.mats[w.z + idx]), ts);
+            ts_dirty = true;
+        }
+
+        for (uint32_t o = dt_end; o < op_end; ++o) {
             const uint4 w = *reinterpret_cast<const uint4*>(&hot[o]);
             const uint32_t cthr = w.y & 0xFFFFu;
             if ((tid & cthr) != cthr) continue;           // a control on a thread bit is 0, or op inactive here
@@ -344,12 +387,27 @@ regtile_kernel(double2* __restrict__ state, const RegTileParams P) {
                     }
                     break;
                 }
-                default: {      // OPC_DIAG_T, OPC_DIAG_S, OPC_DIAG1_0 + slot
+                default: {      // thread-indexed diagonals: DIAG_T, DIAG_S, DIAG_S1 + slot, DIAG1 + slot, DIAG1NC + slot
                     // index bits from (at most two) thread-bit targets; position 31 means "none"
                     const uint32_t idx = (w.w & 0xFFu) | (((tid >> ((w.y >> 16) & 0xFFu)) & 1u) << ((w.x >> 16) & 0xFFu)) |
                                          (((tid >> (w.y >> 24)) & 1u) << (w.x >> 24));
                     const double2 d0 = __ldg(&mat[idx]);
-                    if (opc == OPC_DIAG_T) {
+                    if (opc >= OPC_DIAG_S1_0 && opc < OPC_DIAG_S1_0 + 4) {
+                        switch (opc - OPC_DIAG_S1_0) {
+                            case 0: reg_diag_s1<0>(a, d0, xm); break;
+                            case 1: reg_diag_s1<1>(a, d0, xm); break;
+                            case 2: reg_diag_s1<2>(a, d0, xm); break;
+                            default: reg_diag_s1<3>(a, d0, xm); break;
+                        }
+                    } else if (opc >= OPC_DIAG1NC_0) {
+                        const double2 d1 = __ldg(&mat[idx | (1u << ((w.w >> 8) & 0xFFu))]);
+                        switch (opc - OPC_DIAG1NC_0) {
+                            case 0: reg_diag1_nc<0>(a, d0, d1, xm); break;
+                            case 1: reg_diag1_nc<1>(a, d0, d1, xm); break;
+                            case 2: reg_diag1_nc<2>(a, d0, d1, xm); break;
+                            default: reg_diag1_nc<3>(a, d0, d1, xm); break;
+                        }
+                    } else if (opc == OPC_DIAG_T) {
                         ts = cmul(d0, ts);
                         ts_dirty = true;
                     } else if (opc == OPC_DIAG_S) {

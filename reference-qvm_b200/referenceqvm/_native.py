@@ -52,6 +52,7 @@ _SIGNATURES = {
     "qvm_set_stream": (C.c_int, [_P, _P]),
     "qvm_set_tile_bits": (C.c_int, [_P, C.c_int, C.c_int]),
     "qvm_set_kernel_path": (C.c_int, [_P, C.c_int]),
+    "qvm_debug_opcode_hist": (C.c_int, [_P, _P]),
     "qvm_n_local": (C.c_int, [_P]),
     "qvm_device_ptr": (_P, [_P]),
     "qvm_stream": (_P, [_P]),
@@ -229,6 +230,11 @@ class DeviceState(object):
 
     def set_kernel_path(self, use_regtile):
         check(lib().qvm_set_kernel_path(self.handle, 1 if use_regtile else 0))
+
+    def opcode_hist(self):
+        out = np.zeros(32, dtype=np.uint64)
+        check(lib().qvm_debug_opcode_hist(self.handle, out.ctypes.data))
+        return out
 
     def device_ptr(self):
         return int(lib().qvm_device_ptr(self.handle) or 0)
