@@ -440,14 +440,15 @@ bool is_h_matrix(const double* m) {      // s * [[1, 1], [1, -1]] with real s
     return s != 0.0 && m[1] == 0.0 && m[2] == s && m[3] == 0.0 && m[4] == s && m[5] == 0.0 && m[6] == -s && m[7] == 0.0;
 }
 
-template <int T, int B>
+template <int T, int B, bool FULL>
 int launch_regtile(qvm_state* q, unsigned grid, unsigned threads, size_t smem, const RegTileParams& P) {
     static bool attr_set[64] = {};
     if (!attr_set[q->device & 63]) {
-        QVM_CUDA(q, cudaFuncSetAttribute(regtile_kernel<T, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        QVM_CUDA(q, cudaFuncSetAttribute(regtile_kernel<T, B, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024));
         attr_set[q->device & 63] = true;
     }
-    regtile_kernel<T, B><<<grid, threads, smem, q->stream>>>(q->amps, P);
+    regtile_kernel<T, B, FULL><<<grid, threads, smem, q->stream>>>(q->amps, P);
     QVM_CUDA(q, cudaGetLastError());
     return QVM_OK;
 }
@@ -787,12 +788,19 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
     const uint64_t n_tiles = q->n_elems >> n_tile;
     if (n_tiles > 0x7fffffffull) return fail(QVM_ERR_UNSUPPORTED, "too many tiles for one launch");
     const unsigned threads = 1u << (n_tile - 4);
-    if (threads > 256) rc = launch_regtile<512, 1>(q, (unsigned)n_tiles, threads, smem, P);
-#ifdef QVM_REGTILE_ONE_CTA
-    else rc = launch_regtile<256, 1>(q, (unsigned)n_tiles, threads, smem, P);
-#else
-    else rc = launch_regtile<256, 2>(q, (unsigned)n_tiles, threads, smem, P);
-#endif
+    bool need_full = false;
+    for (const HotOp& h : hot) {
+        const uint32_t opc = h.x & 0xFFu;
+        if ((opc >= OPC_D1_0 && opc < OPC_XS_0) || opc == OPC_D2_0 || opc == OPC_D2_0 + 1 || opc == OPC_DIAG_G)
+            need_full = true;
+    }
+    if (threads > 256) {
+        rc = need_full ? launch_regtile<512, 1, true>(q, (unsigned)n_tiles, threads, smem, P)
+                       : launch_regtile<512, 1, false>(q, (unsigned)n_tiles, threads, smem, P);
+    } else {
+        rc = need_full ? launch_regtile<256, 2, true>(q, (unsigned)n_tiles, threads, smem, P)
+                       : launch_regtile<256, 2, false>(q, (unsigned)n_tiles, threads, smem, P);
+    }
     if (rc) return rc;
     q->stats.kernel_launches += 1;
     q->stats.gate_ops += (uint64_t)n;

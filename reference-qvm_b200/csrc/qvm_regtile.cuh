@@ -230,7 +230,9 @@ __host__ __device__ inline size_t regtile_smem_bytes(int k, int n_rounds, int n_
     return b;
 }
 
-template <int MAX_THREADS, int MIN_BLOCKS>
+// FULL = false drops the generic dense 2x2 / 4x4 and generic-diagonal handlers (the host launches
+// that lean variant when a group has none of them): ~40% less code, friendlier to the I-cache.
+template <int MAX_THREADS, int MIN_BLOCKS, bool FULL>
 __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
 regtile_kernel(double2* __restrict__ state, const RegTileParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -320,7 +322,7 @@ regtile_kernel(double2* __restrict__ state, const RegTileParams P) {
 
         // DIAG_T ops touch no register qubit of this round, so they commute with all of its ops:
         // the host sorts them first and they run as one tight batch into the thread scalar.
-#pragma unroll 2
+#pragma unroll 1
         for (uint32_t o = op_begin; o < dt_end; ++o) {
             const uint4 w = *reinterpret_cast<const uint4*>(&hot[o]);
             const uint32_t cthr = w.y & 0xFFFFu;
@@ -329,6 +331,11 @@ regtile_kernel(double2* __restrict__ state, const RegTileParams P) {
                                  (((tid >> (w.y >> 24)) & 1u) << (w.x >> 24));
             ts = cmul(__ldg(&P.mats[w.z + idx]), ts);
             ts_dirty = true;
+        }
+
+        if (ts_dirty) {          // scalars commute with everything: apply now, so ts is dead in the main loop
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = cmul(ts, a[j]);
         }
 
         for (uint32_t o = dt_end; o < op_end; ++o) {
@@ -346,47 +353,55 @@ regtile_kernel(double2* __restrict__ state, const RegTileParams P) {
                 else { reg_h<3>(a, (xm & 8u) << 28); xm &= ~8u; }
                 continue;
             }
+            if (FULL && opc >= OPC_D1_0 && opc < OPC_XS_0) {
+                switch (opc - OPC_D1_0) {
+                    case 0: reg_dense1<0>(a, mat, crm, xm); break;
+                    case 1: reg_dense1<1>(a, mat, crm, xm); break;
+                    case 2: reg_dense1<2>(a, mat, crm, xm); break;
+                    default: reg_dense1<3>(a, mat, crm, xm); break;
+                }
+                continue;
+            }
+            if (FULL && (opc == OPC_D2_0 || opc == OPC_D2_0 + 1)) {
+                if (opc == OPC_D2_0) reg_dense2<0>(a, mat, crm, xm);
+                else reg_dense2<1>(a, mat, crm, xm);
+                continue;
+            }
+            if (FULL && opc == OPC_DIAG_G) {
+                const ColdOp* c = &P.cold[o];
+                const uint32_t kk = c->k;
+                uint32_t idx = w.w & 0xFFu;
+                uint32_t rm0 = 0, rm1 = 0, rm2 = 0, rm3 = 0, rs0 = 0, rs1 = 0, rs2 = 0, rs3 = 0;
+                for (uint32_t t = 0; t < kk; ++t) {
+                    const uint32_t loc = c->loc[t];
+                    const uint32_t cls = loc & LOC_CLASS;
+                    const uint32_t sh = 1u << (kk - 1 - t);
+                    if (cls == LOC_THR) idx |= ((tid >> (loc & LOC_INDEX)) & 1u) ? sh : 0u;
+                    else if (cls == LOC_REG) {
+                        const uint32_t slot = loc & LOC_INDEX;       // each slot appears at most once
+                        if (slot == 0) { rm0 = 1u; rs0 = sh; }
+                        else if (slot == 1) { rm1 = 2u; rs1 = sh; }
+                        else if (slot == 2) { rm2 = 4u; rs2 = sh; }
+                        else { rm3 = 8u; rs3 = sh; }
+                    }
+                }
+                const uint32_t want = crm & ~xm;
+#pragma unroll
+                for (int p = 0; p < 16; ++p) {
+                    if ((p & crm) == want) {
+                        const uint32_t j = (uint32_t)p ^ xm;         // logical slot
+                        const uint32_t ij = idx | ((j & rm0) ? rs0 : 0u) | ((j & rm1) ? rs1 : 0u) |
+                                            ((j & rm2) ? rs2 : 0u) | ((j & rm3) ? rs3 : 0u);
+                        a[p] = cmul(__ldg(&mat[ij]), a[p]);
+                    }
+                }
+                continue;
+            }
             switch (opc) {
-                case OPC_D1_0 + 0: reg_dense1<0>(a, mat, crm, xm); break;
-                case OPC_D1_0 + 1: reg_dense1<1>(a, mat, crm, xm); break;
-                case OPC_D1_0 + 2: reg_dense1<2>(a, mat, crm, xm); break;
-                case OPC_D1_0 + 3: reg_dense1<3>(a, mat, crm, xm); break;
                 case OPC_XS_0 + 0: reg_xswap<0>(a, crm, xm); break;
                 case OPC_XS_0 + 1: reg_xswap<1>(a, crm, xm); break;
                 case OPC_XS_0 + 2: reg_xswap<2>(a, crm, xm); break;
                 case OPC_XS_0 + 3: reg_xswap<3>(a, crm, xm); break;
-                case OPC_D2_0 + 0: reg_dense2<0>(a, mat, crm, xm); break;
-                case OPC_D2_0 + 1: reg_dense2<1>(a, mat, crm, xm); break;
-                case OPC_DIAG_G: {
-                    const ColdOp* c = &P.cold[o];
-                    const uint32_t kk = c->k;
-                    uint32_t idx = w.w & 0xFFu;
-                    uint32_t rm0 = 0, rm1 = 0, rm2 = 0, rm3 = 0, rs0 = 0, rs1 = 0, rs2 = 0, rs3 = 0;
-                    for (uint32_t t = 0; t < kk; ++t) {
-                        const uint32_t loc = c->loc[t];
-                        const uint32_t cls = loc & LOC_CLASS;
-                        const uint32_t sh = 1u << (kk - 1 - t);
-                        if (cls == LOC_THR) idx |= ((tid >> (loc & LOC_INDEX)) & 1u) ? sh : 0u;
-                        else if (cls == LOC_REG) {
-                            const uint32_t slot = loc & LOC_INDEX;       // each slot appears at most once
-                            if (slot == 0) { rm0 = 1u; rs0 = sh; }
-                            else if (slot == 1) { rm1 = 2u; rs1 = sh; }
-                            else if (slot == 2) { rm2 = 4u; rs2 = sh; }
-                            else { rm3 = 8u; rs3 = sh; }
-                        }
-                    }
-                    const uint32_t want = crm & ~xm;
-#pragma unroll
-                    for (int p = 0; p < 16; ++p) {
-                        if ((p & crm) == want) {
-                            const uint32_t j = (uint32_t)p ^ xm;         // logical slot
-                            const uint32_t ij = idx | ((j & rm0) ? rs0 : 0u) | ((j & rm1) ? rs1 : 0u) |
-                                                ((j & rm2) ? rs2 : 0u) | ((j & rm3) ? rs3 : 0u);
-                            a[p] = cmul(__ldg(&mat[ij]), a[p]);
-                        }
-                    }
-                    break;
-                }
                 default: {      // thread-indexed diagonals: DIAG_T, DIAG_S, DIAG_S1 + slot, DIAG1 + slot, DIAG1NC + slot
                     // index bits from (at most two) thread-bit targets; position 31 means "none"
                     const uint32_t idx = (w.w & 0xFFu) | (((tid >> ((w.y >> 16) & 0xFFu)) & 1u) << ((w.x >> 16) & 0xFFu)) |
@@ -407,9 +422,6 @@ regtile_kernel(double2* __restrict__ state, const RegTileParams P) {
                             case 2: reg_diag1_nc<2>(a, d0, d1, xm); break;
                             default: reg_diag1_nc<3>(a, d0, d1, xm); break;
                         }
-                    } else if (opc == OPC_DIAG_T) {
-                        ts = cmul(d0, ts);
-                        ts_dirty = true;
                     } else if (opc == OPC_DIAG_S) {
                         const uint32_t want = crm & ~xm;
 #pragma unroll
@@ -429,16 +441,18 @@ regtile_kernel(double2* __restrict__ state, const RegTileParams P) {
             }
         }
 
-        if (ts_dirty) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] = cmul(ts, a[j]);
-        }
-
+        // recompute the thread mapping here rather than keeping it live across the op loop
+        const uint4 sw_ = *reinterpret_cast<const uint4*>(&rounds[r]);
+        uint32_t T2 = tid;
+        T2 = insert_zero32(T2, sw_.y & 0xFFu);
+        T2 = insert_zero32(T2, (sw_.y >> 8) & 0xFFu);
+        T2 = insert_zero32(T2, (sw_.y >> 16) & 0xFFu);
+        T2 = insert_zero32(T2, sw_.y >> 24);
         if (r == P.n_rounds - 1) {
-            const uint64_t g0 = 1ull << (rw.z & 0xFFu), g1 = 1ull << ((rw.z >> 8) & 0xFFu),
-                           g2 = 1ull << ((rw.z >> 16) & 0xFFu), g3 = 1ull << (rw.z >> 24);
+            const uint64_t g0 = 1ull << (sw_.z & 0xFFu), g1 = 1ull << ((sw_.z >> 8) & 0xFFu),
+                           g2 = 1ull << ((sw_.z >> 16) & 0xFFu), g3 = 1ull << (sw_.z >> 24);
             // register p holds logical slot p ^ xm; the slot -> address map is XOR-linear
-            const uint64_t gT = ((uint64_t)(T & low_mask) | __ldg(&P.hi_off[T >> P.low])) ^
+            const uint64_t gT = ((uint64_t)(T2 & low_mask) | __ldg(&P.hi_off[T2 >> P.low])) ^
                                 (((xm & 1) ? g0 : 0) | ((xm & 2) ? g1 : 0) | ((xm & 4) ? g2 : 0) | ((xm & 8) ? g3 : 0));
             double2* dst = gbase;
 #pragma unroll
@@ -446,8 +460,9 @@ regtile_kernel(double2* __restrict__ state, const RegTileParams P) {
                 dst[gT ^ (((j & 1) ? g0 : 0) | ((j & 2) ? g1 : 0) | ((j & 4) ? g2 : 0) | ((j & 8) ? g3 : 0))] = a[j];
         } else {
             // same mapping as this round's load: every thread rewrites exactly the slots it read
-            const uint32_t s0 = swz(J0), s1 = swz(J1), s2 = swz(J2), s3 = swz(J3);
-            const uint32_t sT = swz(T) ^ ((xm & 1) ? s0 : 0) ^ ((xm & 2) ? s1 : 0) ^ ((xm & 4) ? s2 : 0) ^ ((xm & 8) ? s3 : 0);
+            const uint32_t s0 = swz(1u << (sw_.x & 0xFFu)), s1 = swz(1u << ((sw_.x >> 8) & 0xFFu)),
+                           s2 = swz(1u << ((sw_.x >> 16) & 0xFFu)), s3 = swz(1u << (sw_.x >> 24));
+            const uint32_t sT = swz(T2) ^ ((xm & 1) ? s0 : 0) ^ ((xm & 2) ? s1 : 0) ^ ((xm & 4) ? s2 : 0) ^ ((xm & 8) ? s3 : 0);
 #pragma unroll
             for (int j = 0; j < 16; ++j)
                 tile[sT ^ ((j & 1) ? s0 : 0) ^ ((j & 2) ? s1 : 0) ^ ((j & 4) ? s2 : 0) ^ ((j & 8) ? s3 : 0)] = a[j];
