@@ -174,8 +174,8 @@ def main():
     ap.add_argument("--qubits", type=int, default=int(os.environ.get("QVM_BENCH_QUBITS", "33")))
     ap.add_argument("--depth", type=int, default=int(os.environ.get("QVM_BENCH_DEPTH", "40")))
     ap.add_argument("--shots", type=int, default=1000000)
-    ap.add_argument("--ref-qubits", type=int, default=12)
-    ap.add_argument("--ref-depth", type=int, default=10)
+    ap.add_argument("--ref-qubits", type=int, default=18)
+    ap.add_argument("--ref-depth", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -189,17 +189,32 @@ def main():
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus %d needs torchrun (one rank per GPU)" % args.gpus)
-    if world > 1:
-        raise SystemExit("sharded bench not wired yet")
 
     import torch
-    from referenceqvm import _engine, _native
+    from referenceqvm import _engine, _native, _sharded
     from referenceqvm.api import QVMConnection
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     os.environ["QVM_B200_DEVICE"] = str(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        _sharded.enable(device=local_rank)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     n, depth = args.qubits, args.depth
     spec = circuit(n, depth)
@@ -213,6 +228,8 @@ def main():
     from referenceqvm.unitary_generator import resolve_gate
     ops = [_engine.compile_gate(*resolve_gate(qvm.gate_set, {}, ins)) for ins in prog]
     stream = torch.cuda.ExternalStream(eng.state.stream_ptr(), device=local_rank)
+    sharded = world > 1
+    n_local = n - (world.bit_length() - 1)
 
     def step():
         eng.reset()
@@ -228,10 +245,13 @@ def main():
     for _ in range(args.warmup):
         step()
     eng.sync()
-    torch.cuda.synchronize()
+    barrier()
 
     eng.state.stats_reset()
     groups_before = eng.groups_launched
+    swaps_before = getattr(eng, "swaps", 0)
+    if sharded:
+        eng.timing = {"batch": [], "swap": []}
     sampler = ClockSampler(local_rank)
     sampler.start()
     t_begin = torch.cuda.Event(enable_timing=True)
@@ -240,25 +260,41 @@ def main():
     pairs = [step() for _ in range(args.steps)]
     t_end.record(stream)
     eng.sync()
-    torch.cuda.synchronize()
+    barrier()
     clocks = sampler.stop()
-    total_ms = t_begin.elapsed_time(t_end)
-    kernel_ms = sum(a.elapsed_time(b) for a, b in pairs)
+    total_ms = max_over_ranks(t_begin.elapsed_time(t_end))
     stats = eng.state.stats()
     groups = eng.groups_launched - groups_before
+    swaps = getattr(eng, "swaps", 0) - swaps_before
+    swap_ms = 0.0
+    if sharded:
+        kernel_ms = sum(a.elapsed_time(b) for a, b in eng.timing["batch"])
+        swap_ms = sum(a.elapsed_time(b) for a, b in eng.timing["swap"])
+        eng.timing = None
+    else:
+        kernel_ms = sum(a.elapsed_time(b) for a, b in pairs)
     ms_per_step = total_ms / args.steps
     value = n_gates * args.steps / (total_ms * 1e-3)
 
     peak, peak_src = measured_peaks()
-    bytes_per_launch = 32.0 * 2 ** n
+    bytes_per_launch = 32.0 * 2 ** n_local
     avg_launch_ms = kernel_ms / max(groups, 1)
     achieved = bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "regtile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_launch_ms,
                 "launches_per_step": groups / float(args.steps),
+                "gates_per_launch": n_gates * args.steps / float(max(groups, 1)),
                 "regtile_rounds_per_launch": stats.get("regtile_rounds", 0) / float(max(groups, 1)),
-                "effective_gbs": n_gates * args.steps * bytes_per_launch / (total_ms * 1e-3) / 1e9}
+                "effective_gbs": n_gates * args.steps * bytes_per_launch * world / (total_ms * 1e-3) / 1e9,
+                "note": "per GPU (rank 0): one launch = one read + one write of the local shard"}
+    if sharded and swaps:
+        swap_bytes = 8.0 * 2 ** n_local          # sent (and received) per GPU per swap
+        roofline["nvlink"] = {"bound": "nvlink", "achieved": swap_bytes * swaps / (swap_ms * 1e-3) / 1e9, "peak": 900.0,
+                              "unit": "GB/s per direction per GPU", "swaps_per_step": swaps / float(args.steps),
+                              "bytes_per_swap_per_direction": swap_bytes, "avg_swap_ms": swap_ms / swaps,
+                              "share_of_step": swap_ms / (total_ms if total_ms else 1.0)}
+        roofline["nvlink"]["frac"] = roofline["nvlink"]["achieved"] / 900.0
 
     # ---- e2e: the call a user makes -----------------------------------------------------------
     e2e = None
@@ -266,15 +302,15 @@ def main():
         qubits = list(range(n))
         eng.state.stats_reset()
         qvm.run_and_measure(prog, qubits, trials=args.shots)          # warm (allocations, caches)
-        torch.cuda.synchronize()
+        barrier()
         eng2 = qvm._engine
         eng2.state.stats_reset()
         t0 = time.perf_counter()
         e2e_steps = max(1, min(args.steps, 3))
         for _ in range(e2e_steps):
             res = qvm.run_and_measure(prog, qubits, trials=args.shots)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
         assert len(res) == args.shots and len(res[0]) == n
         s2 = eng2.state.stats()
         e2e = {"value": n_gates * e2e_steps / dt, "unit": METRIC,
@@ -283,7 +319,7 @@ def main():
                "call": "QVMConnection().run_and_measure(program, qubits=all, trials=%d)" % args.shots}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         v, dt, g = cpu_reference_sample(args.ref_qubits, args.ref_depth)
         cpu = {"value": v, "unit": METRIC, "cores": 1, "kind": "port",
                "sample": "n=%d depth=%d random circuit (seed %d, %d gates, %.1f s): oracle restatement of the "
@@ -296,11 +332,16 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args), "qubits": n, "depth": depth, "gates_per_step": n_gates,
                    "l2_policy": "state (%.1f GiB) is far larger than the 126 MB L2" % (16.0 * 2 ** n / 2 ** 30),
-                   "tile_bits": eng.tile_bits, "low_bits": eng.low_bits},
+                   "tile_bits": eng.tile_bits, "low_bits": eng.low_bits,
+                   "sharding": ("top %d qubits select the GPU; %d global<->local swaps per step over NCCL send/recv"
+                                % (world.bit_length() - 1, swaps // max(args.steps, 1))) if sharded else "single shard"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": stats["kernel_launches"], "clocks": clocks,
     }
-    print(json.dumps(line))
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -155,6 +155,16 @@ class Engine(object):
         return s
 
 
+def make_engine(n_positions, device=0):
+    """Engine for an ``n_positions``-bit state: sharded over the process group when
+    ``_sharded.enable()`` was called in this process (one rank per GPU), single-GPU otherwise."""
+    from referenceqvm import _sharded
+    ctx = _sharded.context()
+    if ctx is not None and ctx.world > 1:
+        return _sharded.ShardedEngine(n_positions, ctx)
+    return Engine(n_positions, device=device)
+
+
 class DeviceAmplitudes(object):
     """Lazy, sliceable view of amplitudes that stay in HBM (used when 2^n * 16 B is too large to
     hand back as one ndarray; reference returns ``self.wf`` itself, qvm_wavefunction.py:367)."""

@@ -1,0 +1,445 @@
+"""Sharded engine: one process per GPU, amplitudes split by the top log2(G) qubits.
+
+The reference has no distributed path.  Here each rank holds 2^(n-g) contiguous
+amplitudes (g = log2 world size); physical positions >= n-g are *global*: their value is a bit of
+the rank.  A host-side logical->physical qubit layout tracks remaps.
+
+* Diagonal gates and controls on global positions need no communication: the kernels read the bit
+  from the shard index (``qvm_set_shard``).
+* A dense target on a global position triggers a global<->local swap: ranks that differ in that
+  global bit exchange the half of their shard whose local bit differs from their own global bit
+  (``B_swap = 8 * 2^(n-g)`` bytes each way per GPU), chunked through two staging buffers with
+  torch.distributed send/recv (NCCL over NVLink on GPUs; gloo in the CPU tests).  The victim local
+  qubit is the one whose next dense use is farthest away.
+* MEASURE = local partial p0 -> all-reduce -> local collapse.  Sampling = local two-level CDF,
+  all-gather of the shard totals, each rank resolves the shots that fall in its range.
+
+All ranks run the same program (SPMD) and make identical planning decisions; random draws are
+broadcast from rank 0.
+"""
+import numpy as np
+
+from referenceqvm import _native as nat
+from referenceqvm import _planner
+from referenceqvm._engine import _LOW_BITS, _TILE_BITS, compile_gate, validate_qubits
+
+_context = None      # set by enable(); consulted by _engine.make_engine()
+
+
+class ShardContext(object):
+    def __init__(self, group, rank, world, device):
+        self.group, self.rank, self.world, self.device = group, rank, world, device
+        self.n_global = int(world).bit_length() - 1
+        if (1 << self.n_global) != world:
+            raise ValueError("world size %d is not a power of two" % world)
+
+
+def enable(device=None, group=None):
+    """Shard every engine created from now on across the ranks of ``group`` (default: WORLD)."""
+    global _context
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised")
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    _context = ShardContext(group, rank, world, 0 if device is None else device)
+    return _context
+
+
+def disable():
+    global _context
+    _context = None
+
+
+def context():
+    return _context
+
+
+class CudaShard(object):
+    """Local backend of the product path: one DeviceState + torch CUDA staging tensors."""
+
+    def __init__(self, n_local, ctx):
+        import torch
+        self.torch = torch
+        self.ctx = ctx
+        self.n_local = n_local
+        torch.cuda.set_device(ctx.device)
+        self.state = nat.DeviceState(n_local, ctx.device)
+        self.state.set_shard(ctx.n_global, ctx.rank)
+        # run the library's kernels on torch's current stream so they order with NCCL operations
+        self.state.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.device = torch.device("cuda", ctx.device)
+
+    def close(self):
+        self.state.close()
+
+    def alloc(self, n_amps):
+        return self.torch.empty(2 * n_amps, dtype=self.torch.float64, device=self.device)
+
+    def scalar_tensor(self, values, dtype=None):
+        return self.torch.tensor(values, dtype=dtype or self.torch.float64, device=self.device)
+
+    def apply_groups(self, ops, tile_bits, low_bits):
+        n = 0
+        for group in _planner.plan(ops, self.n_local, tile_bits, low_bits):
+            self.state.apply_group(group.tile, group.ops)
+            n += 1
+        return n
+
+    def pack_half(self, bit, value, off, cnt, buf):
+        self.state.pack_half(bit, value, off, cnt, buf.data_ptr())
+
+    def unpack_half(self, bit, value, off, cnt, buf):
+        self.state.unpack_half(bit, value, off, cnt, buf.data_ptr())
+
+    def reset_zero(self, set_amp0):
+        self.state.reset_zero(set_amp0)
+
+    def set_state(self, amps):
+        self.state.set_state(amps)
+
+    def get_state(self, offset=0, count=None):
+        return self.state.get_state(offset, count)
+
+    def norm2(self):
+        return self.state.norm2()
+
+    def prob_zero(self, position):
+        return self.state.prob_zero(position)
+
+    def collapse(self, position, outcome, scale):
+        self.state.collapse(position, outcome, scale)
+
+    def probs_prepare(self):
+        return self.state.probs_prepare(0, 0)
+
+    def sample(self, uniforms):
+        return self.state.sample(uniforms)
+
+    def sync(self):
+        self.state.sync()
+
+    def stats(self):
+        return self.state.stats()
+
+    def record_event(self):
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+
+class ShardedEngine(object):
+    """Same surface as ``_engine.Engine`` for a state spread over all ranks."""
+
+    CHUNK_AMPS = 1 << 26          # 1 GiB per staging buffer
+
+    def __init__(self, n_positions, ctx=None, tile_bits=None, low_bits=None, backend_factory=None,
+                 chunk_amps=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.ctx = ctx or _context
+        if self.ctx is None:
+            raise RuntimeError("sharding is not enabled")
+        self.n = int(n_positions)
+        self.g = self.ctx.n_global
+        self.n_local = self.n - self.g
+        if self.n_local < 1:
+            raise ValueError("%d qubits cannot be sharded over %d ranks" % (self.n, self.ctx.world))
+        self.tile_bits = _TILE_BITS if tile_bits is None else tile_bits
+        self.low_bits = _LOW_BITS if low_bits is None else low_bits
+        self.shard = (backend_factory or CudaShard)(self.n_local, self.ctx)
+        self.chunk_amps = min(chunk_amps or self.CHUNK_AMPS, 1 << (self.n_local - 1))
+        self._send = self._recv = None
+        self.pos_of = list(range(self.n))         # logical qubit -> physical position
+        self.pending = []                         # ClassifiedOps in LOGICAL coordinates
+        self.gates_queued = 0
+        self.groups_launched = 0
+        self.swaps = 0
+        self.swap_bytes = 0
+        #: when a dict {"batch": [], "swap": []}: (start, end) device events around every kernel batch
+        #: and every exchange are appended (bench.py reads them after a sync)
+        self.timing = None
+
+    # -- lifetime / state ------------------------------------------------------------------------
+    @property
+    def state(self):
+        return self.shard.state
+
+    def close(self):
+        self.pending = []
+        self._send = self._recv = None
+        if self.shard is not None:
+            self.shard.close()
+            self.shard = None
+
+    def reset(self):
+        self.pending = []
+        self.pos_of = list(range(self.n))
+        self.shard.reset_zero(self.ctx.rank == 0)
+
+    def set_amplitudes(self, amplitudes):
+        """Every rank passes the FULL vector (tests / small states); each keeps its shard."""
+        a = np.asarray(amplitudes).reshape(-1)
+        if a.size != (1 << self.n):
+            raise ValueError("state size mismatch")
+        self.pending = []
+        self.pos_of = list(range(self.n))
+        lo = self.ctx.rank << self.n_local
+        self.shard.set_state(a[lo:lo + (1 << self.n_local)])
+
+    def local_amplitudes(self):
+        self.flush()
+        return self.shard.get_state()
+
+    def amplitudes(self, offset=0, count=None):
+        """Amplitudes [offset, offset+count) in LOGICAL order, on every rank.  Each rank fills the
+        part of the range it owns and the pieces are summed (x + 0 is exact)."""
+        self.flush()
+        self.restore_layout()
+        total = 1 << self.n
+        count = total - offset if count is None else int(count)
+        if offset < 0 or count < 0 or offset + count > total:
+            raise ValueError("range outside the state")
+        out = np.zeros(count, dtype=np.complex128)
+        lo = self.ctx.rank << self.n_local
+        a, b = max(offset, lo), min(offset + count, lo + (1 << self.n_local))
+        if b > a:
+            out[a - offset:b - offset] = self.shard.get_state(a - lo, b - a)
+        return self._allreduce_array(out.view(np.float64)).view(np.complex128)
+
+    def strided(self, offset, stride, count):
+        self.flush()
+        self.restore_layout()
+        idx = offset + stride * np.arange(int(count), dtype=np.int64)
+        out = np.zeros(int(count), dtype=np.complex128)
+        mine = np.nonzero((idx >> self.n_local) == self.ctx.rank)[0]
+        if mine.size:
+            first = int(idx[mine[0]]) - (self.ctx.rank << self.n_local)
+            out[mine] = self.shard.state.get_strided(first, stride, mine.size)
+        return self._allreduce_array(out.view(np.float64)).view(np.complex128)
+
+    def _allreduce_array(self, values):
+        t = self.shard.scalar_tensor(values)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.ctx.group)
+        return t.cpu().numpy()
+
+    def norm2(self):
+        self.flush()
+        return self._allreduce_sum(self.shard.norm2())
+
+    # -- gates -------------------------------------------------------------------------------------
+    def queue_matrix(self, matrix, qubits):
+        qubits = [int(q) for q in qubits]
+        validate_qubits(qubits, self.n)
+        self.queue(compile_gate(matrix, qubits))
+
+    def queue(self, op):
+        self.gates_queued += 1
+        if op.kind != nat.OP_NOP:
+            self.pending.append(op)
+
+    def _next_dense_use(self, ops, start):
+        """For every logical qubit: index of the next op (>= start) that needs it local."""
+        nxt = {}
+        for i in range(len(ops) - 1, start - 1, -1):
+            op = ops[i]
+            if op.kind == nat.OP_DENSE:
+                for t in op.targets:
+                    nxt[t] = i
+        return nxt
+
+    def flush(self):
+        if not self.pending:
+            return
+        ops, self.pending = self.pending, []
+        batch = []              # physical-coordinate ops whose dense targets are all local
+        i = 0
+        while i < len(ops):
+            op = ops[i]
+            need = [t for t in op.targets if self.pos_of[t] >= self.n_local] if op.kind == nat.OP_DENSE else []
+            if need:
+                self._run_batch(batch)
+                batch = []
+                nxt = self._next_dense_use(ops, i)
+                busy = set(op.targets)
+                for q in need:
+                    victim = self._pick_victim(nxt, busy, len(ops))
+                    self._swap_global_local(q, victim)
+                    busy.add(victim)
+            batch.append(op.remapped(self.pos_of))
+            i += 1
+        self._run_batch(batch)
+
+    def _run_batch(self, batch):
+        if batch:
+            e0 = self.shard.record_event() if self.timing is not None else None
+            self.groups_launched += self.shard.apply_groups(batch, self.tile_bits, self.low_bits)
+            if e0 is not None:
+                self.timing["batch"].append((e0, self.shard.record_event()))
+
+    def _pick_victim(self, next_use, busy, horizon):
+        """Local logical qubit to push out: the one whose next dense use is farthest (Belady).
+        The lowest local positions are kept (they are every tile's coalescing bits)."""
+        best, best_key = None, None
+        for q in range(self.n):
+            p = self.pos_of[q]
+            if p >= self.n_local or q in busy:
+                continue
+            key = (next_use.get(q, horizon + 1), p)     # farthest use first, then highest position
+            if p < min(self.low_bits, self.n_local - 1):
+                key = (-1, p)                            # avoid unless nothing else is left
+            if best_key is None or key > best_key:
+                best, best_key = q, key
+        if best is None:
+            raise RuntimeError("no local qubit available for a global<->local swap")
+        return best
+
+    # -- the exchange --------------------------------------------------------------------------------
+    def _buffers(self):
+        if self._send is None:
+            self._send = [self.shard.alloc(self.chunk_amps) for _ in range(2)]
+            self._recv = [self.shard.alloc(self.chunk_amps) for _ in range(2)]
+        return self._send, self._recv
+
+    def _swap_global_local(self, q_global, q_local):
+        """Swap the physical positions of logical qubits q_global (on a global position) and q_local."""
+        pg, pl = self.pos_of[q_global], self.pos_of[q_local]
+        assert pg >= self.n_local > pl
+        gbit = pg - self.n_local
+        mine = (self.ctx.rank >> gbit) & 1
+        partner = self.ctx.rank ^ (1 << gbit)
+        send, recv = self._buffers()
+        e0 = self.shard.record_event() if self.timing is not None else None
+        half = 1 << (self.n_local - 1)
+        moving = 1 - mine           # the half whose local bit differs from my global bit changes owner
+        dist = self.dist
+        pending = None              # (requests, offset, count, buffer index) of the chunk in flight
+        k = 0
+        for off in range(0, half, self.chunk_amps):
+            cnt = min(self.chunk_amps, half - off)
+            b = k & 1
+            self.shard.pack_half(pl, moving, off, cnt, send[b])
+            ops = [dist.P2POp(dist.isend, send[b][:2 * cnt], self._global_rank(partner), self.ctx.group),
+                   dist.P2POp(dist.irecv, recv[b][:2 * cnt], self._global_rank(partner), self.ctx.group)]
+            if mine:                # fixed order on both sides of a pair keeps gloo from deadlocking
+                ops.reverse()
+            reqs = dist.batch_isend_irecv(ops)
+            if pending is not None:
+                self._finish_chunk(pl, moving, pending)
+            pending = (reqs, off, cnt, b)
+            k += 1
+        if pending is not None:
+            self._finish_chunk(pl, moving, pending)
+        self.pos_of[q_global], self.pos_of[q_local] = pl, pg
+        self.swaps += 1
+        self.swap_bytes += 16 * half
+        if e0 is not None:
+            self.timing["swap"].append((e0, self.shard.record_event()))
+
+    def _finish_chunk(self, pl, moving, pending):
+        reqs, off, cnt, b = pending
+        for r in reqs:
+            r.wait()
+        self.shard.unpack_half(pl, moving, off, cnt, self._recv[b])
+
+    def _global_rank(self, group_rank):
+        if self.ctx.group is None:
+            return group_rank
+        return self.dist.get_global_rank(self.ctx.group, group_rank)
+
+    def restore_layout(self):
+        """Bring every logical qubit back to its own position (before a full readback)."""
+        self.flush()
+        # 1. global positions: swap each misplaced global qubit through a local slot
+        for p in range(self.n - 1, self.n_local - 1, -1):
+            holder = self.pos_of.index(p)
+            if holder == p:
+                continue
+            # logical qubit p currently sits at some other position
+            cur = self.pos_of[p]
+            if cur >= self.n_local:
+                # both global: route through a local victim
+                victim = self._pick_victim({}, {p, holder}, 0)
+                self._swap_global_local(p, victim)          # p becomes local
+                cur = self.pos_of[p]
+            self._swap_global_local(holder, p)              # holder (global at position p) <-> p (local)
+        # 2. local permutation: plain SWAP gates on physical positions
+        swap = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
+        batch = []
+        for q in range(self.n_local):
+            p = self.pos_of[q]
+            if p == q:
+                continue
+            other = self.pos_of.index(q)
+            batch.append(compile_gate(swap, [p, q]))
+            self.pos_of[q], self.pos_of[other] = q, p
+        self._run_batch(batch)
+        assert self.pos_of == list(range(self.n))
+
+    # -- reductions ------------------------------------------------------------------------------------
+    def _allreduce_sum(self, value):
+        t = self.shard.scalar_tensor([float(value)])
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.ctx.group)
+        return float(t.cpu()[0])
+
+    def _broadcast_floats(self, values):
+        t = self.shard.scalar_tensor(np.asarray(values, dtype=np.float64))
+        self.dist.broadcast(t, src=self._global_rank(0), group=self.ctx.group)
+        return t.cpu().numpy()
+
+    def measure(self, qubit, r):
+        """MEASURE: partial p0 on every rank, all-reduce, same decision everywhere, local collapse."""
+        self.flush()
+        r = float(self._broadcast_floats([r])[0])
+        pos = self.pos_of[int(qubit)]
+        p0 = self._allreduce_sum(self.shard.prob_zero(pos))
+        outcome = 0 if r < p0 else 1
+        scale = 1.0 / np.sqrt(p0 if outcome == 0 else 1.0 - p0)
+        self.shard.collapse(pos, outcome, scale)
+        return outcome, p0
+
+    def prob_zero(self, qubit):
+        self.flush()
+        return self._allreduce_sum(self.shard.prob_zero(self.pos_of[int(qubit)]))
+
+    def sample(self, uniforms, mode=0, n_rho=0):
+        """Inverse-CDF draws of LOGICAL basis-state indices, identical on every rank."""
+        if mode != 0:
+            raise NotImplementedError("sharded density sampling")
+        self.flush()
+        self.restore_layout()       # CDF in logical index order: draws match the single-GPU path
+        import torch
+        u = self._broadcast_floats(uniforms)
+        local_total = self.shard.probs_prepare()
+        totals = self.shard.scalar_tensor([0.0] * self.ctx.world)
+        mine = self.shard.scalar_tensor([local_total])
+        pieces = list(totals.split(1))
+        self.dist.all_gather(pieces, mine, group=self.ctx.group)
+        totals = np.array([float(p.cpu()[0]) for p in pieces])
+        cum = np.cumsum(totals)
+        grand = cum[-1]
+        target = u * grand
+        owner = np.minimum(np.searchsorted(cum, target, side="right"), self.ctx.world - 1)
+        sel = np.nonzero(owner == self.ctx.rank)[0]
+        phys = np.zeros(u.size, dtype=np.int64)
+        if sel.size:
+            start = cum[self.ctx.rank] - totals[self.ctx.rank]
+            lu = np.clip((target[sel] - start) / totals[self.ctx.rank], 0.0, np.nextafter(1.0, 0.0))
+            local_idx = self.shard.sample(lu).astype(np.int64)
+            phys[sel] = (np.int64(self.ctx.rank) << np.int64(self.n_local)) | local_idx
+        t = self.shard.scalar_tensor(phys, dtype=torch.int64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.ctx.group)
+        phys = t.cpu().numpy().astype(np.uint64)
+        logical = np.zeros_like(phys)
+        for q in range(self.n):
+            logical |= ((phys >> np.uint64(self.pos_of[q])) & np.uint64(1)) << np.uint64(q)
+        return logical, grand
+
+    def sync(self):
+        self.flush()
+        self.shard.sync()
+
+    def stats(self):
+        s = self.shard.stats()
+        s.update(gates_queued=self.gates_queued, groups_launched=self.groups_launched, swaps=self.swaps,
+                 swap_bytes=self.swap_bytes)
+        return s

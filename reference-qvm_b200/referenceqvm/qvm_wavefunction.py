@@ -61,7 +61,7 @@ class QVM_Wavefunction(QAM):
         return self._engine
 
     def _make_engine(self, n):
-        return _engine.Engine(n, device=self.device)
+        return _engine.make_engine(n, device=self.device)
 
     @property
     def wf(self):

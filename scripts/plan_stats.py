@@ -1,0 +1,67 @@
+"""Dry run of the host-side planning for a sharded random circuit: how many kernel groups and
+global<->local swaps the engine would issue (no device, no process group)."""
+import os
+import sys
+import time
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (REPO, os.path.join(REPO, "reference-qvm_b200")):
+    sys.path.insert(0, p)
+
+import referenceqvm  # noqa: E402,F401
+from oracle.qvm_oracle import random_circuit_spec  # noqa: E402
+from referenceqvm import _engine, _planner, _sharded, gates as G  # noqa: E402
+
+
+class NullShard(object):
+    def __init__(self, n_local, ctx):
+        self.n_local = n_local
+        self.ops_per_group = []
+
+    def apply_groups(self, ops, tile_bits, low_bits):
+        groups = _planner.plan(ops, self.n_local, tile_bits, low_bits)
+        self.ops_per_group += [len(g.ops) for g in groups]
+        return len(groups)
+
+    def alloc(self, n):
+        return None
+
+    def pack_half(self, *a):
+        pass
+
+    unpack_half = pack_half
+
+    def record_event(self):
+        return None
+
+
+def main():
+    n, depth, world = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+    spec = random_circuit_spec(n, depth, 1234)
+    ops = []
+    for name, params, qubits in spec:
+        m = G.gate_matrix[name]
+        ops.append(_engine.compile_gate(m(*params) if params else m, qubits))
+    if world == 1:
+        t0 = time.time()
+        groups = _planner.plan(ops, n, 12, 5)
+        print("groups", len(groups), "ops", len(ops), "plan s", time.time() - t0)
+        return
+    ctx = _sharded.ShardContext(None, 0, world, 0)
+    eng = _sharded.ShardedEngine(n, ctx, backend_factory=NullShard)
+    eng._swap_global_local_real = eng._swap_global_local
+
+    def fake_swap(qg, ql):
+        pg, pl = eng.pos_of[qg], eng.pos_of[ql]
+        eng.pos_of[qg], eng.pos_of[ql] = pl, pg
+        eng.swaps += 1
+    eng._swap_global_local = fake_swap
+    t0 = time.time()
+    for op in ops:
+        eng.queue(op)
+    eng.flush()
+    print("world", world, "groups", eng.groups_launched, "swaps", eng.swaps, "ops", len(ops), "plan s", time.time() - t0)
+
+
+if __name__ == "__main__":
+    main()

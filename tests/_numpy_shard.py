@@ -1,0 +1,142 @@
+"""Numpy stand-in for ``_sharded.CudaShard`` (tests only): lets the sharded engine's HOST logic --
+layout tracking, victim choice, chunked half-shard exchange, reductions, sampling ownership -- run
+under gloo on CPU ranks.  The arithmetic is the oracle's closed form; the CUDA path never sees this
+file."""
+import numpy as np
+import torch
+
+from oracle import qvm_oracle as orc
+from referenceqvm import _native as nat
+from referenceqvm import _planner
+
+
+def localise(op, n_local, shard_index):
+    """Rewrite a physical-coordinate op for one shard: global controls / diagonal targets are
+    resolved from the shard index.  Returns None when the op is inactive on this shard."""
+    ctrl_local = 0
+    for p in op.ctrl_positions:
+        if p >= n_local:
+            if not (shard_index >> (p - n_local)) & 1:
+                return None
+        else:
+            ctrl_local |= 1 << p
+    if op.kind == nat.OP_DENSE:
+        assert all(t < n_local for t in op.targets)
+        return nat.ClassifiedOp(op.kind, op.targets, ctrl_local, op.mat)
+    k = len(op.targets)
+    keep = [j for j, t in enumerate(op.targets) if t < n_local]
+    diag = np.empty(1 << len(keep), dtype=np.complex128)
+    for idx in range(diag.size):
+        full = 0
+        for j, t in enumerate(op.targets):
+            if t >= n_local:
+                bit = (shard_index >> (t - n_local)) & 1
+            else:
+                bit = (idx >> (len(keep) - 1 - keep.index(j))) & 1
+            full |= bit << (k - 1 - j)
+        diag[idx] = op.mat[full]
+    return nat.ClassifiedOp(op.kind, tuple(op.targets[j] for j in keep), ctrl_local, diag)
+
+
+def apply_local(psi, op, n_local):
+    ctrls = op.ctrl_positions
+    k = len(op.targets)
+    if op.kind == nat.OP_DENSE:
+        block = op.mat.reshape(1 << k, 1 << k)
+    else:
+        block = np.diag(op.mat)
+    qubits = list(ctrls) + list(op.targets)
+    if not qubits:
+        return psi * block[0, 0]
+    dim = 1 << len(qubits)
+    full = np.eye(dim, dtype=np.complex128)
+    full[dim - (1 << k):, dim - (1 << k):] = block
+    return orc.fast_apply_gate(psi, full, qubits, n_local)
+
+
+class _FakeState(object):
+    def __init__(self):
+        self.n_global = 0
+
+
+class NumpyShard(object):
+    def __init__(self, n_local, ctx):
+        self.n_local = n_local
+        self.ctx = ctx
+        self.psi = np.zeros(1 << n_local, dtype=np.complex128)
+        self.launches = 0
+        self.state = _FakeState()
+        self._cdf = None
+
+    def close(self):
+        self.psi = None
+
+    def alloc(self, n_amps):
+        return torch.empty(2 * n_amps, dtype=torch.float64)
+
+    def scalar_tensor(self, values, dtype=None):
+        return torch.tensor(np.asarray(values), dtype=dtype or torch.float64)
+
+    def apply_groups(self, ops, tile_bits, low_bits):
+        n = 0
+        for group in _planner.plan(ops, self.n_local, tile_bits, low_bits):
+            for op in group.ops:
+                lop = localise(op, self.n_local, self.ctx.rank)
+                if lop is not None:
+                    self.psi = apply_local(self.psi, lop, self.n_local)
+            n += 1
+        self.launches += n
+        return n
+
+    def _half_index(self, bit, value, off, cnt):
+        j = np.arange(off, off + cnt, dtype=np.int64)
+        lo = j & ((1 << bit) - 1)
+        return ((j >> bit) << (bit + 1)) | lo | (value << bit)
+
+    def pack_half(self, bit, value, off, cnt, buf):
+        buf[:2 * cnt] = torch.from_numpy(self.psi[self._half_index(bit, value, off, cnt)].view(np.float64).copy())
+
+    def unpack_half(self, bit, value, off, cnt, buf):
+        self.psi[self._half_index(bit, value, off, cnt)] = buf[:2 * cnt].numpy().view(np.complex128)
+
+    def reset_zero(self, set_amp0):
+        self.psi[:] = 0
+        if set_amp0:
+            self.psi[0] = 1.0
+
+    def set_state(self, amps):
+        self.psi = np.array(amps, dtype=np.complex128)
+
+    def get_state(self, offset=0, count=None):
+        count = self.psi.size - offset if count is None else count
+        return self.psi[offset:offset + count].copy()
+
+    def norm2(self):
+        return float(np.sum(np.abs(self.psi) ** 2))
+
+    def prob_zero(self, position):
+        if position >= self.n_local:
+            return 0.0 if (self.ctx.rank >> (position - self.n_local)) & 1 else self.norm2()
+        return orc.fast_prob_zero(self.psi, position, self.n_local)
+
+    def collapse(self, position, outcome, scale):
+        if position >= self.n_local:
+            mine = (self.ctx.rank >> (position - self.n_local)) & 1
+            self.psi = self.psi * (scale if mine == outcome else 0.0)
+            return
+        keep = ((np.arange(self.psi.size) >> position) & 1) == outcome
+        self.psi = np.where(keep, self.psi * scale, 0.0)
+
+    def probs_prepare(self):
+        self._cdf = np.cumsum(np.abs(self.psi) ** 2)
+        return float(self._cdf[-1])
+
+    def sample(self, uniforms):
+        target = np.asarray(uniforms) * self._cdf[-1]
+        return np.minimum(np.searchsorted(self._cdf, target, side="right"), self.psi.size - 1).astype(np.uint64)
+
+    def sync(self):
+        pass
+
+    def stats(self):
+        return {"kernel_launches": self.launches}

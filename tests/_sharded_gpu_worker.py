@@ -1,0 +1,81 @@
+"""Worker of tests/test_gpu_sharded.py: one rank (= one GPU) of an NCCL group running the product
+sharded path (CudaShard: libqvm_b200 kernels + NCCL send/recv), diffed against the oracle."""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+for p in (REPO, os.path.join(REPO, "reference-qvm_b200"), HERE):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import referenceqvm  # noqa: E402,F401
+from _programs import spec_program  # noqa: E402
+from oracle import qvm_oracle as orc  # noqa: E402
+from referenceqvm import _sharded, gates as G  # noqa: E402
+from referenceqvm.api import QVMConnection  # noqa: E402
+
+
+def oracle_ops(spec):
+    out = []
+    for name, params, qubits in spec:
+        m = G.gate_matrix[name]
+        out.append(("gate", np.asarray(m(*params) if params else m, dtype=complex), qubits))
+    return out
+
+
+def main():
+    rank, world = int(os.environ["QVM_TEST_RANK"]), int(os.environ["QVM_TEST_WORLD"])
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%s" % os.environ["QVM_TEST_PORT"], rank=rank,
+                            world_size=world, device_id=torch.device("cuda", rank))
+    ctx = _sharded.enable(device=rank)
+    for n, depth, seed, chunk in ((12, 6, 1, 64), (16, 8, 2, 1 << 20), (20, 5, 1234, 1 << 12), (14, 10, 5, 1 << 9)):
+        spec = orc.random_circuit_spec(n, depth, seed)
+        eng = _sharded.ShardedEngine(n, ctx, chunk_amps=chunk)
+        eng.reset()
+        for name, params, qubits in spec:
+            m = G.gate_matrix[name]
+            eng.queue_matrix(m(*params) if params else m, qubits)
+        want, _ = orc.fast_run_wavefunction(oracle_ops(spec), n)
+        eng.flush()
+        assert eng.swaps > 0
+        assert abs(eng.norm2() - 1.0) < 1e-12
+        got = eng.amplitudes()
+        err = float(np.max(np.abs(got - want)))
+        assert err < 1e-12, (n, depth, seed, err)
+        psi = want
+        for q, r in ((n - 1, 0.3), (0, 0.8), (n // 2, 0.5)):
+            outcome, p0 = eng.measure(q, r if rank == 0 else -1.0)
+            o_want, p_want, psi = orc.fast_measure(psi, q, n, r)
+            assert outcome == o_want and abs(p0 - p_want) < 1e-12
+        err = float(np.max(np.abs(eng.amplitudes() - psi)))
+        assert err < 1e-12, ("after measure", err)
+        eng.close()
+
+    # the public API, sharded: QVMConnection on every rank (SPMD)
+    n = 15
+    spec = orc.random_circuit_spec(n, 6, 7)
+    qvm = QVMConnection()
+    qvm.device = rank
+    wf, _ = qvm.wavefunction(spec_program(spec))
+    want, _ = orc.fast_run_wavefunction(oracle_ops(spec), n)
+    assert isinstance(qvm._engine, _sharded.ShardedEngine)
+    assert float(np.max(np.abs(wf.amplitudes - want))) < 1e-12
+    np.random.seed(11)
+    shots = np.asarray(qvm.run_and_measure(spec_program(spec), list(range(n)), trials=20000))
+    idx = (shots << np.arange(n)).sum(axis=1)
+    u = np.random.RandomState(11).random_sample(20000)
+    ref = orc.inverse_cdf_sample(np.abs(want) ** 2, u)
+    assert np.mean(idx == ref) > 0.999          # same uniforms (rank 0's), same CDF order
+    dist.barrier()
+    dist.destroy_process_group()
+    print("rank %d/%d ok" % (rank, world))
+
+
+if __name__ == "__main__":
+    main()
