@@ -154,6 +154,18 @@ int qvm_pack_half(qvm_t* q, int local_bit, int bit_value, uint64_t elem_offset, 
 int qvm_unpack_half(qvm_t* q, int local_bit, int bit_value, uint64_t elem_offset, uint64_t count,
                     const void* device_src);
 
+/* ---- peer-memory exchange: the same swap as ONE kernel over NVLink P2P, no staging ----------------- */
+/* One process per GPU: export this shard's allocation as a 64-byte CUDA IPC handle / map a peer's. */
+int qvm_ipc_export(qvm_t* q, void* handle64);
+int qvm_ipc_open(qvm_t* q, const void* handle64, void** peer_device_ptr);
+int qvm_ipc_close(qvm_t* q, void* peer_device_ptr);
+/* For j in [elem_offset, elem_offset+count): swap my amp[insert(j, local_bit, mine_value)] with the
+ * peer's amp[insert(j, local_bit, 1 - mine_value)].  The two ranks of a pair call it on disjoint j
+ * ranges (each half of [0, 2^(n_local-1))); the caller brackets it with a cross-rank barrier on the
+ * stream.  `peer_amps` may also be another shard on the same device (tests). */
+int qvm_exchange_half(qvm_t* q, int local_bit, int mine_value, void* peer_amps, uint64_t elem_offset,
+                      uint64_t count);
+
 #ifdef __cplusplus
 }
 #endif

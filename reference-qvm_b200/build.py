@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "referenceqvm", "libqvm_b200.so")
 SOURCES = ["qvm_capi.cu"]
-DEPS = ["qvm_capi.cu", "qvm_kernels.cuh", "qvm_regtile.cuh", os.path.join("..", "..", "include", "qvm_b200.h")]
+DEPS = ["qvm_capi.cu", "qvm_kernels.cuh", "qvm_regtile.cuh", "qvm_encode.h", os.path.join("..", "..", "include", "qvm_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--compiler-options", "-fPIC,-Wall,-Wno-unused-function", "-shared", "-cudart", "static"]
 

@@ -4,12 +4,14 @@
 // qvm_create fails.
 #include "qvm_kernels.cuh"
 #include "qvm_regtile.cuh"
+#include "qvm_encode.h"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -72,6 +74,7 @@ struct qvm_state {
     int measure_grid = 0;
     qvm_stats_t stats{};
     uint64_t opc_hist[32] = {};
+    EncodedGroup enc;                 // scratch of the register-tile encoder (reused across launches)
 };
 
 namespace {
@@ -368,78 +371,7 @@ int launch_group(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, 
 }
 
 
-// ---- register-tiled path: round planning + encoding ---------------------------------------------
-struct LocalOp {
-    int kind = 0, k = 0;
-    int tgt[QVM_MAX_TARGETS];        // dense: tile-local bit; diag: tile-local bit, or -(1 + physical) when outer
-    uint32_t ctrl_tile = 0;
-    uint64_t ctrl_outer = 0;
-    uint32_t mat_off = 0;
-    uint32_t dense_mask = 0;         // tile-local bits touched densely
-    uint32_t diag_mask = 0;          // tile-local bits touched diagonally (controls, diagonal targets)
-};
-
-struct PlannedRound {
-    int slot_bit[4] = {-1, -1, -1, -1};      // tile-local bit held by register slot s
-    std::vector<int> ops;                    // indices into the LocalOp list, execution order
-    uint32_t regmask() const {
-        uint32_t m = 0;
-        for (int s = 0; s < 4; ++s)
-            if (slot_bit[s] >= 0) m |= 1u << slot_bit[s];
-        return m;
-    }
-    int slot_of(int bit) const {
-        for (int s = 0; s < 4; ++s)
-            if (slot_bit[s] == bit) return s;
-        return -1;
-    }
-};
-
-// Try to give the dense targets of `op` register slots in `rd`; `allowed` = tile bits that may
-// become register bits in this round.  Dense2 targets must share a slot pair {0,1} or {2,3}.
-bool place_dense(PlannedRound& rd, const LocalOp& op, uint32_t allowed) {
-    if (op.k == 1) {
-        const int b = op.tgt[0];
-        if (rd.slot_of(b) >= 0) return true;
-        if (!((allowed >> b) & 1u)) return false;
-        static const int pref[4] = {3, 2, 1, 0};
-        for (int s : pref)
-            if (rd.slot_bit[s] < 0) {
-                rd.slot_bit[s] = b;
-                return true;
-            }
-        return false;
-    }
-    const int a = op.tgt[0], b = op.tgt[1];
-    const int sa = rd.slot_of(a), sb = rd.slot_of(b);
-    if (sa >= 0 && sb >= 0) return (sa >> 1) == (sb >> 1);
-    if (sa >= 0 || sb >= 0) {
-        const int have = sa >= 0 ? sa : sb;
-        const int other_bit = sa >= 0 ? b : a;
-        const int partner = have ^ 1;
-        if (rd.slot_bit[partner] >= 0 || !((allowed >> other_bit) & 1u)) return false;
-        rd.slot_bit[partner] = other_bit;
-        return true;
-    }
-    if (!((allowed >> a) & 1u) || !((allowed >> b) & 1u)) return false;
-    for (int p = 0; p < 2; ++p)
-        if (rd.slot_bit[2 * p] < 0 && rd.slot_bit[2 * p + 1] < 0) {
-            rd.slot_bit[2 * p + 1] = a;      // msb -> odd slot
-            rd.slot_bit[2 * p] = b;
-            return true;
-        }
-    return false;
-}
-
-bool is_x_matrix(const double* m) {
-    static const double x[8] = {0, 0, 1, 0, 1, 0, 0, 0};
-    return memcmp(m, x, sizeof(x)) == 0;
-}
-bool is_h_matrix(const double* m) {      // s * [[1, 1], [1, -1]] with real s
-    const double s = m[0];
-    return s != 0.0 && m[1] == 0.0 && m[2] == s && m[3] == 0.0 && m[4] == s && m[5] == 0.0 && m[6] == -s && m[7] == 0.0;
-}
-
+// ---- register-tiled path: encode (qvm_encode.h), upload, launch ------------------------------------
 template <int T, int B, bool FULL>
 int launch_regtile(qvm_state* q, unsigned grid, unsigned threads, size_t smem, const RegTileParams& P) {
     static bool attr_set[64] = {};
@@ -456,358 +388,60 @@ int launch_regtile(qvm_state* q, unsigned grid, unsigned threads, size_t smem, c
 int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops,
                          const double* mats, uint64_t mats_entries, bool* handled) {
     *handled = false;
-    if (n_tile < 9 || n_tile > 13) return QVM_OK;
-    const int npos = total_positions(q);
-    int8_t local_of[64];
-    memset(local_of, -1, sizeof(local_of));
-    RegTileParams P{};
-    P.n_local = q->n_local;
-    P.k = n_tile;
-    P.shard_bits = q->shard_index << q->n_local;
-    uint64_t P_tile_mask = 0;
-    for (int j = 0; j < n_tile; ++j) {
-        P_tile_mask |= 1ull << tile_bits[j];
-        local_of[tile_bits[j]] = (int8_t)j;
-    }
-
-    // tile-relative view (validation mirrors the v1 path; anything unusual falls back to it)
-    std::vector<LocalOp> lops;
-    lops.reserve(n_ops);
-    for (int i = 0; i < n_ops; ++i) {
-        const qvm_op_t& op = ops[i];
-        if (op.kind == QVM_OP_NOP) continue;
-        if (op.kind != QVM_OP_DENSE && op.kind != QVM_OP_DIAG) return QVM_OK;
-        if (op.k < 0 || op.k > QVM_MAX_TARGETS) return QVM_OK;
-        if (op.kind == QVM_OP_DENSE && (op.k < 1 || op.k > 2)) return QVM_OK;
-        const uint64_t want = op.kind == QVM_OP_DENSE ? (1ull << (2 * op.k)) : (1ull << op.k);
-        if (op.mat_entries != want || (uint64_t)op.mat_offset + want > mats_entries) return QVM_OK;
-        if (npos < 64 && (op.ctrl_mask >> npos)) return QVM_OK;
-        LocalOp l;
-        l.kind = op.kind;
-        l.k = op.k;
-        l.mat_off = op.mat_offset;
-        uint64_t used = op.ctrl_mask;
-        for (int p = 0; p < q->n_local; ++p)
-            if (((op.ctrl_mask >> p) & 1ull) && local_of[p] >= 0) l.ctrl_tile |= 1u << local_of[p];
-        l.ctrl_outer = op.ctrl_mask & ~P_tile_mask;
-        l.diag_mask = l.ctrl_tile;
-        for (int j = 0; j < op.k; ++j) {
-            const int p = op.targets[j];
-            if (p < 0 || p >= npos || ((used >> p) & 1ull)) return QVM_OK;
-            used |= 1ull << p;
-            const bool in_tile = p < q->n_local && local_of[p] >= 0;
-            if (op.kind == QVM_OP_DENSE) {
-                if (!in_tile) return QVM_OK;
-                l.tgt[j] = local_of[p];
-                l.dense_mask |= 1u << local_of[p];
-            } else if (in_tile) {
-                l.tgt[j] = local_of[p];
-                l.diag_mask |= 1u << local_of[p];
-            } else {
-                l.tgt[j] = -(1 + p);
-            }
-        }
-        lops.push_back(l);
-    }
-    if (lops.empty()) {
+    EncodedGroup& g = q->enc;
+    const int erc = encode_group(q->n_local, q->n_global, q->shard_index, n_tile, tile_bits, n_ops, ops, mats,
+                                 mats_entries, g);
+    if (erc == ENC_ERROR) return fail(QVM_ERR_CUDA, "round planner made no progress");
+    if (erc == ENC_FALLBACK) return QVM_OK;          // the shared-memory kernel (or its error) handles it
+    if (g.cold.empty()) {
         *handled = true;
         return QVM_OK;
     }
+    if (g.n_tiles > 0x7fffffffull) return fail(QVM_ERR_UNSUPPORTED, "too many tiles for one launch");
+    for (int i = 0; i < 32; ++i) q->opc_hist[i] += g.opc_hist[i];
 
-    // ---- rounds: greedy, commutation aware ------------------------------------------------------
-    // Dense ops choose the rounds (each needs its targets in register slots).  Diagonal ops float:
-    // they commute with everything except dense ops on their own qubits, so each is placed, inside
-    // the window those neighbours leave, in the round where it touches the fewest register bits
-    // (ideally none: then it is one scalar per thread instead of work on all 16 slots).
-    const uint32_t all_bits = (1u << n_tile) - 1u;
-    const uint32_t high_bits = all_bits & ~0x1Fu;          // lanes keep the five lowest tile bits in I/O rounds
-    const int n = (int)lops.size();
-    std::vector<int> dense_idx;
-    for (int i = 0; i < n; ++i)
-        if (lops[i].kind == QVM_OP_DENSE) dense_idx.push_back(i);
-    std::vector<int> round_of(n, -1);          // earliest legal round of every op (all-ops greedy)
-    std::vector<PlannedRound> rounds;
-    {
-        std::vector<char> done(n, 0);
-        int remaining = n;
-        while (remaining > 0) {
-            PlannedRound rd;
-            const uint32_t allowed = rounds.empty() ? high_bits : all_bits;
-            uint32_t blocked_dense = 0, blocked_diag = 0;
-            int placed = 0;
-            for (int i = 0; i < n; ++i) {
-                if (done[i]) continue;
-                const LocalOp& op = lops[i];
-                const bool clash = (op.dense_mask & (blocked_dense | blocked_diag)) || (op.diag_mask & blocked_dense);
-                bool ok = !clash;
-                if (ok && op.kind == QVM_OP_DENSE) {
-                    PlannedRound trial = rd;
-                    ok = place_dense(trial, op, allowed);
-                    if (ok) memcpy(rd.slot_bit, trial.slot_bit, sizeof(rd.slot_bit));
-                }
-                if (!ok) {
-                    blocked_dense |= op.dense_mask;
-                    blocked_diag |= op.diag_mask;
-                    continue;
-                }
-                round_of[i] = (int)rounds.size();
-                done[i] = 1;
-                ++placed;
-            }
-            remaining -= placed;
-            if (placed == 0 && !rounds.empty()) return fail(QVM_ERR_CUDA, "round planner made no progress");
-            rounds.push_back(rd);
-        }
-    }
-    if (rounds.size() > 1 && (rounds.back().regmask() & 0x1Fu)) rounds.push_back(PlannedRound());   // store round
-    if (rounds.size() > 4096) return QVM_OK;
-    // fill unused register slots with the highest free tile bits
-    for (PlannedRound& rd : rounds) {
-        uint32_t used = rd.regmask();
-        for (int s = 0; s < 4; ++s)
-            if (rd.slot_bit[s] < 0)
-                for (int b = n_tile - 1; b >= 0; --b)
-                    if (!((used >> b) & 1u)) {
-                        rd.slot_bit[s] = b;
-                        used |= 1u << b;
-                        break;
-                    }
-    }
-
-    // place the floating diagonal ops
-    {
-        const int n_rounds = (int)rounds.size();
-        std::vector<uint32_t> regmask(n_rounds);
-        for (int r = 0; r < n_rounds; ++r) regmask[r] = rounds[r].regmask();
-        for (int i = 0; i < n; ++i) {
-            if (lops[i].kind == QVM_OP_DENSE) continue;
-            const uint32_t touched = lops[i].diag_mask;
-            const int lo = round_of[i];                 // earliest round that respects every dependency
-            int hi = n_rounds - 1;
-            for (int j : dense_idx)
-                if (j > i && (lops[j].dense_mask & touched)) hi = std::min(hi, round_of[j]);
-            if (hi < lo) hi = lo;      // cannot happen: a later conflicting dense op waits for this op
-            int best = lo, best_cost = 99;
-            for (int r = hi; r >= lo; --r) {       // prefer late rounds on ties: keeps early rounds lean
-                const int cost = __builtin_popcount(touched & regmask[r]);
-                if (cost < best_cost) {
-                    best_cost = cost;
-                    best = r;
-                }
-            }
-            round_of[i] = best;
-        }
-        for (int i = 0; i < n; ++i) rounds[round_of[i]].ops.push_back(i);     // ascending original index
-    }
-
-    // ---- encode ---------------------------------------------------------------------------------
-    std::vector<double> pool(mats, mats + 2 * mats_entries);
-    std::vector<RoundDesc> rdesc(rounds.size());
-    std::vector<HotOp> hot;
-    std::vector<ColdOp> cold;
-    double group_scale = 1.0;        // all folded H scales, applied once in the last round
-    hot.reserve(n);
-    cold.reserve(n);
-    for (size_t r = 0; r < rounds.size(); ++r) {
-        const PlannedRound& rd = rounds[r];
-        RoundDesc& d = rdesc[r];
-        memset(&d, 0, sizeof(d));
-        d.scale = 1.0;
-        int8_t slot_of[16], thr_of[16];
-        memset(slot_of, -1, sizeof(slot_of));
-        memset(thr_of, -1, sizeof(thr_of));
-        int sorted[4];
-        for (int s = 0; s < 4; ++s) {
-            d.reg_bit[s] = (uint8_t)rd.slot_bit[s];
-            d.reg_phys[s] = (uint8_t)tile_bits[rd.slot_bit[s]];
-            slot_of[rd.slot_bit[s]] = (int8_t)s;
-            sorted[s] = rd.slot_bit[s];
-        }
-        std::sort(sorted, sorted + 4);
-        for (int s = 0; s < 4; ++s) d.reg_sorted[s] = (uint8_t)sorted[s];
-        int nt = 0;
-        for (int b = 0; b < n_tile; ++b)
-            if (slot_of[b] < 0) thr_of[b] = (int8_t)nt++;
-        d.op_begin = (uint16_t)hot.size();
-        // DIAG_T ops (no register-slot involvement in this round) commute with the whole round: emit
-        // them first so the kernel can run them as one batch
-        std::vector<int> order;
-        order.reserve(rd.ops.size());
-        auto is_diag_t = [&](const LocalOp& l) {
-            if (l.kind != QVM_OP_DIAG) return false;
-            int nthr = 0;
-            for (int b = 0; b < n_tile; ++b)
-                if (((l.ctrl_tile >> b) & 1u) && slot_of[b] >= 0) return false;
-            for (int t = 0; t < l.k; ++t) {
-                if (l.tgt[t] < 0) continue;
-                if (slot_of[l.tgt[t]] >= 0) return false;
-                ++nthr;
-            }
-            return nthr <= 2;
-        };
-        for (int i : rd.ops)
-            if (is_diag_t(lops[i])) order.push_back(i);
-        d.dt_end = (uint16_t)(hot.size() + order.size());
-        for (int i : rd.ops)
-            if (!is_diag_t(lops[i])) order.push_back(i);
-        for (int i : order) {
-            const LocalOp& l = lops[i];
-            HotOp h{0, 0, 0, 0};
-            ColdOp c;
-            memset(&c, 0, sizeof(c));
-            c.ctrl_outer = l.ctrl_outer;
-            uint32_t mat_off = l.mat_off;
-            uint32_t opc = 0, crm = 0, cthr = 0, xb = 0, s0 = 0, s1 = 0, p0 = 31, p1 = 31, shr = 0;
-            for (int b = 0; b < n_tile; ++b)
-                if ((l.ctrl_tile >> b) & 1u) {
-                    if (slot_of[b] >= 0) crm |= 1u << slot_of[b];
-                    else cthr |= 1u << thr_of[b];
-                }
-            if (l.kind == QVM_OP_DENSE && l.k == 1) {
-                const uint32_t slot = (uint32_t)slot_of[l.tgt[0]];
-                const double* m = &pool[2 * (size_t)l.mat_off];
-                if (is_x_matrix(m)) {
-                    if (crm == 0) {
-                        opc = OPC_X_RELABEL;
-                        xb = slot;
-                    } else opc = OPC_XS_0 + slot;
-                } else if (!l.ctrl_tile && !l.ctrl_outer && is_h_matrix(m)) {
-                    opc = OPC_H0 + slot;
-                    group_scale *= m[0];
-                } else opc = OPC_D1_0 + slot;
-            } else if (l.kind == QVM_OP_DENSE) {
-                const int sa = slot_of[l.tgt[0]];
-                opc = OPC_D2_0 + (uint32_t)(sa >> 1);
-                if (!(sa & 1)) {
-                    // msb target sits in the even slot: swap the roles of the two index bits
-                    static const int perm[4] = {0, 2, 1, 3};
-                    const size_t off = pool.size() / 2;
-                    pool.resize(pool.size() + 32);
-                    for (int rr = 0; rr < 4; ++rr)
-                        for (int cc = 0; cc < 4; ++cc) {
-                            const size_t src = 2 * ((size_t)l.mat_off + perm[rr] * 4 + perm[cc]);
-                            pool[2 * (off + rr * 4 + cc)] = pool[src];
-                            pool[2 * (off + rr * 4 + cc) + 1] = pool[src + 1];
-                        }
-                    mat_off = (uint32_t)off;
-                }
-            } else {
-                c.k = (uint8_t)l.k;
-                int nreg = 0, nthr = 0;
-                uint32_t reg_slot = 0;
-                for (int t = 0; t < l.k; ++t) {
-                    const int b = l.tgt[t];
-                    const uint32_t wshift = (uint32_t)(l.k - 1 - t);
-                    if (b < 0) c.loc[t] = (uint8_t)(LOC_OUT | (-(b + 1)));
-                    else if (slot_of[b] >= 0) {
-                        c.loc[t] = (uint8_t)(LOC_REG | slot_of[b]);
-                        reg_slot = (uint32_t)slot_of[b];
-                        shr = wshift;
-                        ++nreg;
-                    } else {
-                        c.loc[t] = (uint8_t)(LOC_THR | thr_of[b]);
-                        if (nthr == 0) { p0 = (uint32_t)thr_of[b]; s0 = wshift; }
-                        else if (nthr == 1) { p1 = (uint32_t)thr_of[b]; s1 = wshift; }
-                        ++nthr;
-                    }
-                }
-                if (nreg >= 2 || nthr > 2) opc = OPC_DIAG_G;
-                else if (nreg == 1) opc = (crm ? OPC_DIAG1_0 : OPC_DIAG1NC_0) + reg_slot;
-                else if (!crm) opc = OPC_DIAG_T;
-                else if ((crm & (crm - 1)) == 0) opc = OPC_DIAG_S1_0 + (uint32_t)__builtin_ctz(crm);
-                else opc = OPC_DIAG_S;
-            }
-            h.x = opc | (crm << 8) | (xb << 12) | (s0 << 16) | (s1 << 24);
-            h.y = cthr | (p0 << 16) | (p1 << 24);
-            h.z = mat_off;
-            h.w = (shr << 8);
-            q->opc_hist[opc & 31] += 1;
-            hot.push_back(h);
-            cold.push_back(c);
-        }
-        d.op_end = (uint16_t)hot.size();
-    }
-
-    rdesc.back().scale = group_scale;
-
-    // launch parameters that replace per-thread bit loops
-    int low = 0;
-    while (low < n_tile && tile_bits[low] == low) ++low;
-    if (low > 5) low = 5;                       // keeps the offset table at >= 2^(k-5) entries, <= 2^13
-    P.low = low;
-    {
-        int nr = 0;
-        int p = 0;
-        while (p < q->n_local) {
-            if ((P_tile_mask >> p) & 1ull) { ++p; continue; }
-            int e = p;
-            while (e < q->n_local && !((P_tile_mask >> e) & 1ull)) ++e;
-            if (nr >= 8) return QVM_OK;         // pathological tile shape: let the v1 kernel take it
-            P.run_start |= (uint64_t)p << (8 * nr);
-            P.run_len |= (uint64_t)(e - p) << (8 * nr);
-            ++nr;
-            p = e;
-        }
-        P.n_runs = nr;
-    }
-    std::vector<uint64_t> hi_off((size_t)1 << (n_tile - low));
-    for (size_t j = 0; j < hi_off.size(); ++j) {
-        uint64_t off = 0;
-        for (int b = 0; b < n_tile - low; ++b)
-            if ((j >> b) & 1u) off |= 1ull << tile_bits[low + b];
-        hi_off[j] = off;
-    }
-
-    const size_t rounds_bytes = (rdesc.size() * sizeof(RoundDesc) + 255) & ~(size_t)255;
-    const size_t hot_bytes = (hot.size() * sizeof(HotOp) + 255) & ~(size_t)255;
-    const size_t cold_bytes = (cold.size() * sizeof(ColdOp) + 255) & ~(size_t)255;
-    const size_t hi_bytes = (hi_off.size() * sizeof(uint64_t) + 255) & ~(size_t)255;
-    const size_t mats_bytes = pool.size() * sizeof(double);
+    const size_t rounds_bytes = (g.rounds.size() * sizeof(RoundDesc) + 255) & ~(size_t)255;
+    const size_t hot_bytes = (g.hot.size() * sizeof(uint4) + 255) & ~(size_t)255;
+    const size_t cold_bytes = (g.cold.size() * sizeof(ColdOp) + 255) & ~(size_t)255;
+    const size_t hi_bytes = (g.hi_off.size() * sizeof(uint64_t) + 255) & ~(size_t)255;
+    const size_t mats_bytes = g.pool.size() * sizeof(double);
     const size_t total_bytes = rounds_bytes + hot_bytes + cold_bytes + hi_bytes + mats_bytes;
     size_t off = 0;
     int rc = ring_alloc(q, total_bytes, &off);
     if (rc) return rc;
     unsigned char* hp = q->ring_host + off;
-    memcpy(hp, rdesc.data(), rdesc.size() * sizeof(RoundDesc));
-    memcpy(hp + rounds_bytes, hot.data(), hot.size() * sizeof(HotOp));
-    memcpy(hp + rounds_bytes + hot_bytes, cold.data(), cold.size() * sizeof(ColdOp));
-    memcpy(hp + rounds_bytes + hot_bytes + cold_bytes, hi_off.data(), hi_off.size() * sizeof(uint64_t));
-    memcpy(hp + rounds_bytes + hot_bytes + cold_bytes + hi_bytes, pool.data(), mats_bytes);
+    memcpy(hp, g.rounds.data(), g.rounds.size() * sizeof(RoundDesc));
+    memcpy(hp + rounds_bytes, g.hot.data(), g.hot.size() * sizeof(uint4));
+    memcpy(hp + rounds_bytes + hot_bytes, g.cold.data(), g.cold.size() * sizeof(ColdOp));
+    memcpy(hp + rounds_bytes + hot_bytes + cold_bytes, g.hi_off.data(), g.hi_off.size() * sizeof(uint64_t));
+    memcpy(hp + rounds_bytes + hot_bytes + cold_bytes + hi_bytes, g.pool.data(), mats_bytes);
     QVM_CUDA(q, cudaMemcpyAsync(q->ring_dev + off, hp, total_bytes, cudaMemcpyHostToDevice, q->stream));
     unsigned char* dp = q->ring_dev + off;
-    P.n_rounds = (int)rdesc.size();
-    P.n_ops = (int)hot.size();
+    RegTileParams P = g.P;
     P.rounds = reinterpret_cast<const RoundDesc*>(dp);
-    P.hot = reinterpret_cast<const HotOp*>(dp + rounds_bytes);
+    P.hot = reinterpret_cast<const uint4*>(dp + rounds_bytes);
     P.cold = reinterpret_cast<const ColdOp*>(dp + rounds_bytes + hot_bytes);
     P.hi_off = reinterpret_cast<const uint64_t*>(dp + rounds_bytes + hot_bytes + cold_bytes);
     P.mats = reinterpret_cast<const double2*>(dp + rounds_bytes + hot_bytes + cold_bytes + hi_bytes);
 
-    const size_t smem = regtile_smem_bytes(P.k, P.n_rounds, P.n_ops);
-    if (smem > 227 * 1024) return QVM_OK;          // let the v1 path (or its error) handle it
-    const uint64_t n_tiles = q->n_elems >> n_tile;
-    if (n_tiles > 0x7fffffffull) return fail(QVM_ERR_UNSUPPORTED, "too many tiles for one launch");
-    const unsigned threads = 1u << (n_tile - 4);
-    bool need_full = false;
-    for (const HotOp& h : hot) {
-        const uint32_t opc = h.x & 0xFFu;
-        if ((opc >= OPC_D1_0 && opc < OPC_XS_0) || opc == OPC_D2_0 || opc == OPC_D2_0 + 1 || opc == OPC_DIAG_G)
-            need_full = true;
-    }
-    if (threads > 256) {
-        rc = need_full ? launch_regtile<512, 1, true>(q, (unsigned)n_tiles, threads, smem, P)
-                       : launch_regtile<512, 1, false>(q, (unsigned)n_tiles, threads, smem, P);
+    static const int occ5 = getenv("QVM_B200_OCC5") ? atoi(getenv("QVM_B200_OCC5")) : 0;
+    if (g.threads > 256) {
+        rc = g.need_full ? launch_regtile<512, 1, true>(q, (unsigned)g.n_tiles, g.threads, g.smem, P)
+                         : launch_regtile<512, 1, false>(q, (unsigned)g.n_tiles, g.threads, g.smem, P);
+    } else if (g.threads <= 128 && occ5 && !g.need_full) {
+        // experiment: cap registers at 102 so that five 128-thread CTAs (20 warps) fit on an SM
+        rc = launch_regtile<128, 5, false>(q, (unsigned)g.n_tiles, g.threads, g.smem, P);
     } else {
-        rc = need_full ? launch_regtile<256, 2, true>(q, (unsigned)n_tiles, threads, smem, P)
-                       : launch_regtile<256, 2, false>(q, (unsigned)n_tiles, threads, smem, P);
+        rc = g.need_full ? launch_regtile<256, 2, true>(q, (unsigned)g.n_tiles, g.threads, g.smem, P)
+                         : launch_regtile<256, 2, false>(q, (unsigned)g.n_tiles, g.threads, g.smem, P);
     }
     if (rc) return rc;
     q->stats.kernel_launches += 1;
-    q->stats.gate_ops += (uint64_t)n;
+    q->stats.gate_ops += (uint64_t)g.n_gate_ops;
     q->stats.hbm_passes += 1;
     q->stats.hbm_bytes += 32ull * q->n_elems;
     q->stats.h2d_bytes += total_bytes;
-    q->stats.regtile_rounds += (uint64_t)rdesc.size();
+    q->stats.regtile_rounds += (uint64_t)g.rounds.size();
     *handled = true;
     return QVM_OK;
 }
@@ -1323,6 +957,52 @@ int qvm_unpack_half(qvm_t* q, int local_bit, int bit_value, uint64_t elem_offset
     if (!count) return QVM_OK;
     unpack_half_kernel<<<grid_for(q, count, 256, 16), 256, 0, q->stream>>>(q->amps, local_bit, bit_value, elem_offset,
                                                                            count, static_cast<const double2*>(device_src));
+    QVM_CUDA(q, cudaGetLastError());
+    q->sample_mode = -1;
+    q->stats.kernel_launches += 1;
+    q->stats.hbm_bytes += 32ull * count;
+    return QVM_OK;
+}
+
+// ---- peer-memory exchange (one process per GPU: CUDA IPC over NVLink) -----------------------------------
+int qvm_ipc_export(qvm_t* q, void* handle64) {
+    QVM_CHECK_HANDLE(q);
+    if (!handle64) return fail(QVM_ERR_INVALID, "null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    QVM_CUDA(q, cudaIpcGetMemHandle(&h, q->amps));
+    memcpy(handle64, &h, sizeof(h));
+    return QVM_OK;
+}
+
+int qvm_ipc_open(qvm_t* q, const void* handle64, void** peer_ptr) {
+    QVM_CHECK_HANDLE(q);
+    if (!handle64 || !peer_ptr) return fail(QVM_ERR_INVALID, "null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    *peer_ptr = nullptr;
+    QVM_CUDA(q, cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return QVM_OK;
+}
+
+int qvm_ipc_close(qvm_t* q, void* peer_ptr) {
+    QVM_CHECK_HANDLE(q);
+    if (!peer_ptr) return QVM_OK;
+    QVM_CUDA(q, cudaStreamSynchronize(q->stream));
+    QVM_CUDA(q, cudaIpcCloseMemHandle(peer_ptr));
+    return QVM_OK;
+}
+
+int qvm_exchange_half(qvm_t* q, int local_bit, int mine_value, void* peer_amps, uint64_t elem_offset, uint64_t count) {
+    QVM_CHECK_HANDLE(q);
+    if (local_bit < 0 || local_bit >= q->n_local || (mine_value | 1) != 1) return fail(QVM_ERR_INVALID, "bad bit");
+    if (!peer_amps) return fail(QVM_ERR_INVALID, "null peer pointer");
+    const uint64_t half = q->n_elems >> 1;
+    if (elem_offset > half || count > half - elem_offset) return fail(QVM_ERR_INVALID, "range outside the half-shard");
+    if (!count) return QVM_OK;
+    const int grid = grid_for(q, (count + kExchangeUnroll - 1) / kExchangeUnroll, 256, 8);
+    exchange_half_kernel<<<grid, 256, 0, q->stream>>>(q->amps, static_cast<double2*>(peer_amps), local_bit, mine_value,
+                                                      elem_offset, count);
     QVM_CUDA(q, cudaGetLastError());
     q->sample_mode = -1;
     q->stats.kernel_launches += 1;

@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "qvm_regtile.cuh"      // cmul / cfma / insert_zero helpers live there (shared with the CPU emulator)
+
 namespace cg = cooperative_groups;
 
 namespace qvm {
@@ -47,26 +49,6 @@ struct TileParams {
     const DevOp* ops;
     const double2* mats;
 };
-
-__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
-    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ double2 cfma(double2 m, double2 a, double2 acc) {
-    acc.x = fma(m.x, a.x, acc.x);
-    acc.x = fma(-m.y, a.y, acc.x);
-    acc.y = fma(m.x, a.y, acc.y);
-    acc.y = fma(m.y, a.x, acc.y);
-    return acc;
-}
-
-__host__ __device__ __forceinline__ uint32_t insert_zero32(uint32_t x, uint32_t pos) {
-    uint32_t lo = x & ((1u << pos) - 1u);
-    return ((x >> pos) << (pos + 1)) | lo;
-}
-__host__ __device__ __forceinline__ uint64_t insert_zero64(uint64_t x, uint32_t pos) {
-    uint64_t lo = x & ((1ull << pos) - 1ull);
-    return ((x >> pos) << (pos + 1)) | lo;
-}
 
 __device__ __forceinline__ uint32_t expand_fixed(uint32_t p, const uint8_t* fix, int nfix) {
     for (int j = 0; j < nfix; ++j) p = insert_zero32(p, fix[j]);
@@ -579,6 +561,44 @@ __global__ void unpack_half_kernel(double2* __restrict__ state, int local_bit, i
     for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < count;
          j += (uint64_t)gridDim.x * blockDim.x)
         state[insert_zero64(off + j, local_bit) | vbit] = src[j];
+}
+
+// Global<->local qubit swap as ONE kernel over peer memory (NVLink P2P): element j of my moving
+// half (local bit == mine_value) trades places with element j of the peer's moving half (local bit
+// == 1 - mine_value).  Each rank of a pair runs this on its own half of the j range, so every link
+// direction carries reads issued by one side and writes issued by the other.  No staging buffers:
+// HBM sees one read + one write per moved amplitude on each side.
+constexpr int kExchangeUnroll = 4;
+__global__ void __launch_bounds__(256) exchange_half_kernel(double2* __restrict__ mine, double2* __restrict__ peer,
+                                                            int local_bit, int mine_value, uint64_t off,
+                                                            uint64_t count) {
+    const uint64_t mbit = (uint64_t)mine_value << local_bit, pbit = (uint64_t)(1 - mine_value) << local_bit;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    for (; j + (kExchangeUnroll - 1) * stride < count; j += kExchangeUnroll * stride) {
+        double2 x[kExchangeUnroll], y[kExchangeUnroll];
+        uint64_t im[kExchangeUnroll], ip[kExchangeUnroll];
+#pragma unroll
+        for (int u = 0; u < kExchangeUnroll; ++u) {
+            const uint64_t e = insert_zero64(off + j + u * stride, local_bit);
+            im[u] = e | mbit;
+            ip[u] = e | pbit;
+        }
+#pragma unroll
+        for (int u = 0; u < kExchangeUnroll; ++u) y[u] = __ldcs(&peer[ip[u]]);
+#pragma unroll
+        for (int u = 0; u < kExchangeUnroll; ++u) x[u] = __ldcs(&mine[im[u]]);
+#pragma unroll
+        for (int u = 0; u < kExchangeUnroll; ++u) __stcs(&mine[im[u]], y[u]);
+#pragma unroll
+        for (int u = 0; u < kExchangeUnroll; ++u) __stcs(&peer[ip[u]], x[u]);
+    }
+    for (; j < count; j += stride) {
+        const uint64_t e = insert_zero64(off + j, local_bit);
+        const double2 y = peer[e | pbit], x = mine[e | mbit];
+        mine[e | mbit] = y;
+        peer[e | pbit] = x;
+    }
 }
 
 }  // namespace qvm

@@ -1,96 +1,191 @@
 // Register-tiled tile kernel (the fast path of qvm_apply_group).
 //
 // A CTA owns a tile of 2^k amplitudes (k tile bits, 9 <= k <= 13) and runs 2^(k-4) threads; each
-// thread keeps 16 amplitudes in registers.  The group's gates are split (host side) into ROUNDS.
-// In a round, 4 of the tile bits are "register bits" (they index the 16 register slots of a
-// thread) and the other k-4 are "thread bits".  A gate whose dense targets are register bits is
-// applied with no addressing at all; controls and diagonal factors may sit on register, thread or
-// outer bits (thread/outer ones cost a predicate or one per-thread scalar).  Changing the set of
-// register bits is a shared-memory transposition (XOR-swizzled against bank conflicts).  The first
-// round loads global -> registers directly and the last stores registers -> global, with the lane
-// bits on the five lowest tile bits so every warp access is a run of contiguous 16-byte elements.
+// thread keeps 16 amplitudes in registers.  The group's gates are split (host side, qvm_encode.h)
+// into ROUNDS.  In a round, 4 of the tile bits are "register bits" (they index the 16 register
+// slots of a thread) and the other k-4 are "thread bits".  A gate whose dense targets are register
+// bits is applied with no addressing at all; controls and diagonal factors may sit on register,
+// thread or outer bits (thread/outer ones cost a predicate or one per-thread scalar).  Changing the
+// set of register bits is a shared-memory transposition (XOR-swizzled against bank conflicts).
+// The first round loads global -> registers directly and the last stores registers -> global, with
+// the lane bits on the five lowest tile bits so every warp access is a run of contiguous 16-byte
+// elements.
 //
 // HBM traffic per launch: one read + one write of the shard, independent of the number of gates.
 //
-// The op stream is interpreted, so instruction economy per op matters more than anything else
-// (profiles/): one 16-byte "hot" word per op, a dense opcode for a jump table, ops that are
-// inactive for this CTA encoded as an impossible thread mask, everything CTA-uniform precomputed by
-// the prologue.
+// The op stream is interpreted, and round-1 profiles (profiles/README.md) showed the interpreter,
+// not HBM, bounds the kernel.  Hence this layout:
+//   * the prologue resolves everything that is uniform over the CTA (outer controls, outer index
+//     bits) and writes one 48-byte record per op to shared memory: a 16-byte header plus the (at
+//     most two) complex factors the op can need -- no global loads and no pointer chasing in the
+//     op loop; generic ops (dense matrices, wide diagonals) still index the global matrix pool;
+//   * the next op's header and first factor are fetched while the current op executes;
+//   * one flat opcode switch (a jump table); handlers are in-place on the register file (the
+//     Hadamard butterfly is a += b; b = a - 2b, so no moves and no sign fix-ups);
+//   * all per-round address ingredients (sorted register bits, swizzled strides) come precomputed.
+//
+// The per-thread round body is __host__ __device__: tests/native/emu_regtile.cu runs the very same
+// code on the CPU (threads looped sequentially between barriers) so that the planner, the encoder
+// and the interpreter can be diffed against the oracle without a GPU.  That emulator is test
+// infrastructure and is not part of libqvm_b200.so.
 #pragma once
-#include "qvm_kernels.cuh"
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define QVM_HD __host__ __device__ __forceinline__
+#else
+#define QVM_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define QVM_LDG(p) __ldg(p)
+#else
+#define QVM_LDG(p) (*(p))
+#endif
 
 namespace qvm {
 
-// Dense opcode space (host assigns; the switch compiles to a jump table).
+// Opcodes.
 enum : uint32_t {
+    // single-slot ops: the encoder always packs them into LAYERs; these codes only label them on the host
     OPC_X_RELABEL = 0,    // X / CNOT with no register-slot control: flips a bit of the slot relabel mask
     OPC_H0 = 1,           // +slot: uncontrolled Hadamard butterfly (scale folded into the round scalar)
-    OPC_D1_0 = 5,         // +slot: generic 2x2
-    OPC_XS_0 = 9,         // +slot: X with a control on a register slot: real pair swaps
-    OPC_D2_0 = 13,        // +pair: generic 4x4 on slots (1,0) / (3,2)
-    OPC_DIAG_T = 15,      // diagonal, no register-slot involvement: one scalar for the thread
-    OPC_DIAG_S = 16,      // per-thread scalar on the slots selected by register-slot controls
-    OPC_DIAG1_0 = 17,     // +slot: one diagonal target on a register slot
-    OPC_DIAG_G = 21,      // generic diagonal (several register-slot targets or > 2 thread targets)
-    OPC_DIAG_S1_0 = 22,   // +slot: DIAG_S whose only register-slot control is that slot (8 multiplies)
-    OPC_DIAG1NC_0 = 26,   // +slot: DIAG1 without register-slot controls (16 multiplies, no predicates)
-    OPC_COUNT = 30,
+    OPC_XS_0 = 5,         // +slot: X on that slot with register-slot controls crm: pair swaps
+    OPC_S1_0 = 9,         // +slot: factor f on the 8 slots whose logical bit is 1
+    OPC_DS = 13,          // factor f on the slots selected by the register-slot control mask crm
+    OPC_D1_0 = 14,        // +slot: (d0, d1) by the logical bit of that slot, optional crm
+    OPC_DIAG_G = 18,      // generic diagonal through the matrix pool (FULL kernels only)
+    OPC_M1_0 = 19,        // +slot: dense 2x2 from the pool (FULL)
+    OPC_M2_0 = 23,        // +pair: dense 4x4 on slots (1,0) / (3,2) from the pool (FULL)
+    OPC_T = 25,           // thread scalar: f0 / f1 by one thread bit (only in the DIAG_T batch)
+    OPC_TG = 26,          // thread scalar through the pool: two thread-bit targets (DIAG_T batch)
+    OPC_S1T_0 = 27,       // +slot: S1 whose factor is f0 / f1 by thread bit p0
+    OPC_DST = 31,         // DS whose factor is f0 / f1 by thread bit p0
+    OPC_LAYER = 32,       // up to 12 single-slot ops in one dispatch: per slot [S1] -> [H] -> [X relabel]
+    OPC_COUNT = 33,
 };
 
-// x: [7:0] opcode | [11:8] crm (register-slot control mask) | [15:12] b (slot for X_RELABEL)
-//    | [23:16] s0 | [31:24] s1           (index weights, as shifts, of the two thread-bit targets)
-// y: [15:0] cthr (thread-bit control mask; 0xFFFF = op inactive for this CTA)
-//    | [23:16] p0 | [31:24] p1           (thread-bit positions of those targets; 31 = none)
-// z: mat_off (double2 units)
-// w: [7:0] oi (index bits from outer targets, patched per CTA) | [15:8] shr (DIAG1: weight shift of
-//    the register-slot target)
-struct __align__(16) HotOp {
-    uint32_t x, y, z, w;
+// The op stream is a sequence of 16-byte words in shared memory.  A plain op is 3 words
+// (header, f0, f1); a LAYER is 6 words (header, thread-control masks, one S1 factor per slot).
+//
+// Header word of an op.
+// x: [7:0] opcode | [11:8] crm (register-slot control mask) | [15:12] xb (slot of X_RELABEL)
+//    | [23:16] p0 | [31:24] p1     thread-bit positions of up to two thread targets (31 = none)
+//    LAYER: [7:0] opcode | [11:8] slots with an S1 | [15:12] slots with an H | [19:16] slots with an X
+// y: [15:0] cthr (thread-bit control mask; 0xFFFF = op inactive for this CTA) | [16] HAS_F1
+//    | [23:20] size of this op in words
+// z: mat_off (double2 units into the pool; generic ops)
+// w: [7:0] oi (pool index bits from outer targets, patched per CTA) | [15:8] s0 | [23:16] s1
+//    (index weights, as shifts, of the thread targets p0 / p1) | [31:24] shr (weight shift of the
+//    register-slot target, D1 / DIAG_G)
+// LAYER word 1: x = cthr of the S1 on slot 0 | slot 1 << 16, y = slots 2 | 3, z / w = the same for X.
+constexpr uint32_t HDR_HAS_F1 = 1u << 16;
+constexpr uint32_t HDR_SIZE_SHIFT = 20;
+constexpr int kOpWords = 3, kLayerWords = 6;
+
+union __align__(16) OpWord {      // one 16-byte word of the op stream
+    uint4 u;
+    double2 d;
 };
+static_assert(sizeof(OpWord) == 16, "OpWord layout");
 
 // Read only by the prologue (one thread per op) and by the generic diagonal path.
 struct __align__(16) ColdOp {
     uint64_t ctrl_outer;      // physical control mask outside the tile (incl. global positions)
     uint8_t loc[6];           // diagonal targets MSB first: class | index
-    uint8_t k;
-    uint8_t pad[1];
-    uint64_t pad2[2];
+    uint8_t k;                // number of diagonal targets
+    uint8_t fsel;             // weight shift of the one non-outer target that selects f0 / f1; 0xFF = none
+    uint32_t mat_off;         // pool offset (double2 units) of the op's diagonal / matrix
+    uint8_t prefetch;         // 1: the prologue copies pool[mat_off + oi (| 1 << fsel)] into f0 (f1)
+    uint8_t n_words;          // words this op occupies in the stream (3, or 6 for a LAYER)
+    uint8_t kind;             // COLD_*
+    uint8_t slot;             // patches: the layer slot they belong to
+    uint32_t word_off;        // first word of the op (patches: of the layer they patch)
+    uint32_t pad1;
 };
 static_assert(sizeof(ColdOp) == 32, "ColdOp layout");
 
+// plain op | layer (verbatim copy) | patches of a layer's S1 / X sub-op that depends on outer bits
+enum : uint8_t { COLD_PLAIN = 0, COLD_LAYER = 1, COLD_PATCH_S1 = 2, COLD_PATCH_X = 3 };
 enum : uint8_t { LOC_REG = 0x00, LOC_THR = 0x40, LOC_OUT = 0x80, LOC_CLASS = 0xC0, LOC_INDEX = 0x3F };
 
 struct __align__(16) RoundDesc {
-    uint8_t reg_bit[4];       // tile-local bit of register slot s
-    uint8_t reg_sorted[4];    // the same four bits, ascending (for the insert-zero thread mapping)
+    uint8_t reg_sorted[4];    // the four register bits (tile-local), ascending: insert-zero thread mapping
     uint8_t reg_phys[4];      // physical position of register slot s (global I/O rounds)
-    uint16_t op_begin, op_end;
-    double scale;             // real scalar applied in this round (product of folded H scales)
-    uint16_t dt_end;          // ops [op_begin, dt_end) are DIAG_T (they commute with the whole round)
-    uint8_t pad[6];
+    uint16_t swz_j[4];        // swz(1 << tile-local bit of slot s): shared-memory stride of slot s
+    double2 scale;            // complex scalar applied in this round (folded H scales, RZ phases)
+    uint16_t op_begin, dt_end, op_end;   // WORD offsets: [op_begin, dt_end) thread-scalar batch; [dt_end, op_end) slot ops
+    uint16_t flags;           // bit 0: scale != 1
+    uint8_t pad[8];
 };
-static_assert(sizeof(RoundDesc) == 32, "RoundDesc layout");
+static_assert(sizeof(RoundDesc) == 48, "RoundDesc layout");
 
 struct RegTileParams {
     int n_local;
     int k;
     int low;                  // tile_pos[j] == j for j < low
     int n_rounds;
-    int n_ops;
+    int n_ops;                // cold entries that produce stream words (plain ops and layers)
+    int n_patches;            // cold entries [n_ops, n_ops + n_patches) patch layer sub-ops afterwards
+    int n_words;              // length of the op stream in 16-byte words
     int n_runs;               // runs of consecutive non-tile positions
     uint64_t shard_bits;
     uint64_t run_start;       // 8 x 8 bits: start position of each run
     uint64_t run_len;         // 8 x 8 bits: length of each run
     const RoundDesc* rounds;
-    const HotOp* hot;
-    const ColdOp* cold;
-    const double2* mats;
+    const uint4* hot;         // [n_words] the op stream as encoded on the host
+    const ColdOp* cold;       // [n_ops + n_patches]
+    const double2* mats;      // matrix pool
     const uint64_t* hi_off;   // [2^(k-low)] global offset contributed by tile-index bits >= low
 };
 
+// ---- small helpers ----------------------------------------------------------------------------
+QVM_HD double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// a <- f * a with two temporaries and no moves: the imaginary part is finished before the real part is
+// overwritten
+QVM_HD void cmul_ip(double2& a, const double2 f) {
+#if defined(__CUDA_ARCH__)
+    // same virtual register as source and destination: keeps ptxas from rotating the 16 amplitudes
+    // through temporaries (which costs two moves per multiply at every handler exit)
+    asm("{\n\t"
+        ".reg .f64 t;\n\t"
+        "mul.rn.f64 t, %1, %3;\n\t"
+        "mul.rn.f64 %1, %1, %2;\n\t"
+        "fma.rn.f64 %1, %0, %3, %1;\n\t"
+        "neg.f64 t, t;\n\t"
+        "fma.rn.f64 %0, %0, %2, t;\n\t"
+        "}"
+        : "+d"(a.x), "+d"(a.y)
+        : "d"(f.x), "d"(f.y));
+#else
+    const double t1 = a.y * f.y, t2 = a.y * f.x;
+    a.y = fma(a.x, f.y, t2);
+    a.x = fma(a.x, f.x, -t1);
+#endif
+}
+QVM_HD double2 cfma(double2 m, double2 a, double2 acc) {
+    acc.x = fma(m.x, a.x, acc.x);
+    acc.x = fma(-m.y, a.y, acc.x);
+    acc.y = fma(m.x, a.y, acc.y);
+    acc.y = fma(m.y, a.x, acc.y);
+    return acc;
+}
+QVM_HD uint32_t insert_zero32(uint32_t x, uint32_t pos) {
+    const uint32_t lo = x & ((1u << pos) - 1u);
+    return ((x >> pos) << (pos + 1)) | lo;
+}
+QVM_HD uint64_t insert_zero64(uint64_t x, uint32_t pos) {
+    const uint64_t lo = x & ((1ull << pos) - 1ull);
+    return ((x >> pos) << (pos + 1)) | lo;
+}
+
 // Bank-conflict swizzle for the double2 tile: XOR index bits 3..6 into bits 0..2 so that (almost)
 // any three "lowest thread bits" land in distinct 16-byte bank groups.  Linear over XOR.
-__device__ __forceinline__ uint32_t swz(uint32_t i) {
+QVM_HD uint32_t swz(uint32_t i) {
     uint32_t x = i;
     x ^= ((i >> 3) & 1u) * 3u;
     x ^= ((i >> 4) & 1u) * 6u;
@@ -99,33 +194,157 @@ __device__ __forceinline__ uint32_t swz(uint32_t i) {
     return x;
 }
 
-__device__ __forceinline__ double flip_sign(double v, uint32_t sign_bit) {
-    return __hiloint2double(__double2hiint(v) ^ (int)sign_bit, __double2loint(v));
+__host__ __device__ inline size_t regtile_smem_bytes(int k, int low, int n_rounds, int n_words) {
+    size_t b = n_rounds > 1 ? ((size_t)16 << k) : 0;
+    b += (size_t)(n_words + 1) * sizeof(OpWord);     // +1: the prefetch of the header after the last op
+    b += (size_t)n_rounds * sizeof(RoundDesc);
+    b += (size_t)8 << (k - low);
+    return b;
 }
 
+// Per-CTA view handed to the round body.
+struct RtCta {
+    double2* tile;            // shared: 2^k amplitudes (unused when n_rounds == 1)
+    const OpWord* ops;        // shared: resolved op stream
+    const RoundDesc* rounds;  // shared
+    const uint64_t* hi_off;   // shared
+    double2* gbase;           // state + outer-bit offset of this tile
+    const double2* mats;      // global pool
+    const ColdOp* cold;       // global
+    int low;
+    int n_rounds;
+};
+
+// ---- prologue: resolve op j for this CTA ---------------------------------------------------------
+// `full` = physical index bits fixed for this CTA (outer tile position | shard bits).
+QVM_HD void rt_resolve_op(const RegTileParams& P, uint32_t j, uint64_t full, OpWord* stream) {
+    const ColdOp* c = &P.cold[j];
+    const uint32_t w0 = c->word_off;
+    OpWord* dst = stream + w0;
+    if (c->n_words == kLayerWords) {               // layers carry no outer-dependent data: verbatim copy
+        for (int i = 0; i < kLayerWords; ++i) dst[i].u = QVM_LDG(&P.hot[w0 + i]);
+        return;
+    }
+    uint4 h = QVM_LDG(&P.hot[w0]);
+    const uint64_t co = c->ctrl_outer;
+    if ((full & co) != co) h.y |= 0xFFFFu;           // inactive here: impossible thread mask
+    const uint32_t kk = c->k;
+    uint32_t oi = 0;
+    for (uint32_t t = 0; t < kk; ++t) {
+        const uint32_t loc = c->loc[t];
+        if ((loc & LOC_CLASS) == LOC_OUT) oi |= (uint32_t)((full >> (loc & LOC_INDEX)) & 1ull) << (kk - 1 - t);
+    }
+    h.w |= oi;
+    double2 f0 = make_double2(1.0, 0.0), f1 = make_double2(1.0, 0.0);
+    if (c->prefetch) {
+        const double2* m = P.mats + c->mat_off;
+        f0 = QVM_LDG(&m[oi]);
+        if (c->fsel != 0xFF) f1 = QVM_LDG(&m[oi | (1u << c->fsel)]);
+    }
+    dst[0].u = h;
+    dst[1].d = f0;
+    dst[2].d = f1;
+}
+
+// Second prologue pass (after a barrier): a layer sub-op whose control sits outside the tile is
+// switched off for CTAs where that control is 0 (impossible thread mask), and an S1 factor that
+// depends on outer target bits is fetched for this CTA's bits.
+QVM_HD void rt_patch_op(const RegTileParams& P, uint32_t j, uint64_t full, OpWord* stream) {
+    const ColdOp* c = &P.cold[j];
+    OpWord* layer = stream + c->word_off;
+    uint16_t* masks = reinterpret_cast<uint16_t*>(&layer[1]);       // cs[0..3], cx[0..3]
+    const uint64_t co = c->ctrl_outer;
+    const bool active = (full & co) == co;
+    if (c->kind == COLD_PATCH_X) {
+        if (!active) masks[4 + c->slot] = 0xFFFFu;
+        return;
+    }
+    if (!active) {
+        masks[c->slot] = 0xFFFFu;
+        return;
+    }
+    const uint32_t kk = c->k;
+    if (kk) {
+        uint32_t oi = 0;
+        for (uint32_t t = 0; t < kk; ++t) {
+            const uint32_t loc = c->loc[t];
+            if ((loc & LOC_CLASS) == LOC_OUT) oi |= (uint32_t)((full >> (loc & LOC_INDEX)) & 1ull) << (kk - 1 - t);
+        }
+        layer[2 + c->slot].d = QVM_LDG(&P.mats[c->mat_off + oi]);
+    }
+}
+
+// ---- slot handlers (all in place) ----------------------------------------------------------------
 // Physical register p holds logical slot (p ^ xm): thread-uniform X / CNOT only flips bits of xm.
 // A register-slot control mask crm is tested on the logical index:
 //   ((p ^ xm) & crm) == crm  <=>  (p & crm) == (crm & ~xm) =: want.
 
+// Unnormalised Hadamard on slot B.  LO = physical half that holds logical 0.
+template <int B, int LO>
+QVM_HD void reg_h_half(double2 (&a)[16]) {
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        const int i0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1)) | (LO << B);     // logical 0
+        const int i1 = i0 ^ (1 << B);                                                // logical 1
+        a[i0].x += a[i1].x;
+        a[i0].y += a[i1].y;
+        a[i1].x = fma(-2.0, a[i1].x, a[i0].x);       // (l0 + l1) - 2 l1 = l0 - l1
+        a[i1].y = fma(-2.0, a[i1].y, a[i0].y);
+    }
+}
 template <int B>
-__device__ __forceinline__ void reg_h(double2 (&a)[16], const uint32_t sign_bit) {
+QVM_HD void reg_h(double2 (&a)[16], const uint32_t xm) {
+    if ((xm >> B) & 1u) reg_h_half<B, 1>(a);
+    else reg_h_half<B, 0>(a);
+}
+
+template <int B>
+QVM_HD void reg_xswap(double2 (&a)[16], const uint32_t crm, const uint32_t xm) {
+    const uint32_t want = crm & ~xm;
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
         const int i0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1));
         const int i1 = i0 | (1 << B);
-        const double2 x0 = a[i0], x1 = a[i1];
-        a[i0] = make_double2(x0.x + x1.x, x0.y + x1.y);
-        // logical (l0 - l1): the physical difference, negated when slots 0/1 are relabelled
-        a[i1] = make_double2(flip_sign(x0.x - x1.x, sign_bit), flip_sign(x0.y - x1.y, sign_bit));
+        if ((i0 & crm) == want) {
+            const double2 x0 = a[i0];
+            a[i0] = a[i1];
+            a[i1] = x0;
+        }
+    }
+}
+
+// factor f on the 8 slots whose logical bit B is 1
+template <int B>
+QVM_HD void reg_s1(double2 (&a)[16], const double2 f, const uint32_t xm) {
+    if ((xm >> B) & 1u) {
+#pragma unroll
+        for (int p = 0; p < 16; ++p)
+            if (!((p >> B) & 1)) cmul_ip(a[p], f);
+    } else {
+#pragma unroll
+        for (int p = 0; p < 16; ++p)
+            if ((p >> B) & 1) cmul_ip(a[p], f);
     }
 }
 
 template <int B>
-__device__ __forceinline__ void reg_dense1(double2 (&a)[16], const double2* __restrict__ mat, const uint32_t crm,
-                                           const uint32_t xm) {
+QVM_HD void reg_d1(double2 (&a)[16], double2 d0, double2 d1, const uint32_t crm, const uint32_t xm) {
+    if ((xm >> B) & 1u) {
+        const double2 t = d0;
+        d0 = d1;
+        d1 = t;
+    }
+    const uint32_t want = crm & ~xm;
+#pragma unroll
+    for (int p = 0; p < 16; ++p)
+        if ((p & crm) == want) cmul_ip(a[p], ((p >> B) & 1) ? d1 : d0);
+}
+
+template <int B>
+QVM_HD void reg_dense1(double2 (&a)[16], const double2* __restrict__ mat, const uint32_t crm, const uint32_t xm) {
     const uint32_t flip = ((xm >> B) & 1u) ? 3u : 0u;      // relabelled slots: index-flipped matrix
-    const double2 m00 = __ldg(&mat[0 ^ flip]), m01 = __ldg(&mat[1 ^ flip]), m10 = __ldg(&mat[2 ^ flip]),
-                  m11 = __ldg(&mat[3 ^ flip]);
+    const double2 m00 = QVM_LDG(&mat[0 ^ flip]), m01 = QVM_LDG(&mat[1 ^ flip]), m10 = QVM_LDG(&mat[2 ^ flip]),
+                  m11 = QVM_LDG(&mat[3 ^ flip]);
     const uint32_t want = crm & ~xm;
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
@@ -142,25 +361,9 @@ __device__ __forceinline__ void reg_dense1(double2 (&a)[16], const double2* __re
     }
 }
 
-template <int B>
-__device__ __forceinline__ void reg_xswap(double2 (&a)[16], const uint32_t crm, const uint32_t xm) {
-    const uint32_t want = crm & ~xm;
-#pragma unroll
-    for (int p = 0; p < 8; ++p) {
-        const int i0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1));
-        const int i1 = i0 | (1 << B);
-        if ((i0 & crm) == want) {
-            const double2 x0 = a[i0];
-            a[i0] = a[i1];
-            a[i1] = x0;
-        }
-    }
-}
-
 // pair P: slots (msb = 2P+1, lsb = 2P)
 template <int P>
-__device__ __forceinline__ void reg_dense2(double2 (&a)[16], const double2* __restrict__ m, const uint32_t crm,
-                                           const uint32_t xm) {
+QVM_HD void reg_dense2(double2 (&a)[16], const double2* __restrict__ m, const uint32_t crm, const uint32_t xm) {
     constexpr int LO = 2 * P, HI = 2 * P + 1;
     const uint32_t x2 = (xm >> LO) & 3u;
     const uint32_t want = crm & ~xm;
@@ -173,302 +376,259 @@ __device__ __forceinline__ void reg_dense2(double2 (&a)[16], const double2* __re
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const double2* row = m + ((r ^ x2) << 2);          // index-flipped matrix for relabelled slots
-                double2 acc = cmul(__ldg(&row[0 ^ x2]), x0);
-                acc = cfma(__ldg(&row[1 ^ x2]), x1, acc);
-                acc = cfma(__ldg(&row[2 ^ x2]), x2v, acc);
-                acc = cfma(__ldg(&row[3 ^ x2]), x3, acc);
+                double2 acc = cmul(QVM_LDG(&row[0 ^ x2]), x0);
+                acc = cfma(QVM_LDG(&row[1 ^ x2]), x1, acc);
+                acc = cfma(QVM_LDG(&row[2 ^ x2]), x2v, acc);
+                acc = cfma(QVM_LDG(&row[3 ^ x2]), x3, acc);
                 a[idx[r]] = acc;
             }
         }
     }
 }
 
-template <int B>
-__device__ __forceinline__ void reg_diag1(double2 (&a)[16], double2 d0, double2 d1, const uint32_t crm,
-                                          const uint32_t xm) {
-    if ((xm >> B) & 1u) {
-        const double2 t = d0;
-        d0 = d1;
-        d1 = t;
-    }
-    const uint32_t want = crm & ~xm;
-#pragma unroll
-    for (int p = 0; p < 16; ++p)
-        if ((p & crm) == want) a[p] = cmul(((p >> B) & 1) ? d1 : d0, a[p]);
-}
+// ---- one round of one thread ----------------------------------------------------------------------
+// FULL = false drops the generic dense 2x2 / 4x4 and generic-diagonal handlers (the host launches
+// that lean variant when a group has none of them): less code, friendlier to the I-cache.
+template <bool FULL>
+QVM_HD void rt_thread_round(const RtCta& c, const int r, const uint32_t tid) {
+    const RoundDesc* rd = &c.rounds[r];
+    const uint4 rw = *reinterpret_cast<const uint4*>(rd);      // x: reg_sorted | y: reg_phys | z,w: swz_j
+    const uint2 rr = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(rd) + 32);
+    const uint32_t op_begin = rr.x & 0xFFFFu, dt_end = rr.x >> 16, op_end = rr.y & 0xFFFFu;
+    const bool scaled = (rr.y >> 16) & 1u;
+    const bool first = r == 0, last = r == c.n_rounds - 1;
 
-// scalar d on the 8 slots whose logical bit B is 1 (physical bit B is 0 when the slot is relabelled)
-template <int B>
-__device__ __forceinline__ void reg_diag_s1(double2 (&a)[16], const double2 d, const uint32_t xm) {
-    if ((xm >> B) & 1u) {
+    // tile index of this thread: tid with zeros inserted at the (ascending) register-bit positions
+    uint32_t T = tid;
+    T = insert_zero32(T, rw.x & 0xFFu);
+    T = insert_zero32(T, (rw.x >> 8) & 0xFFu);
+    T = insert_zero32(T, (rw.x >> 16) & 0xFFu);
+    T = insert_zero32(T, rw.x >> 24);
+    const uint32_t s0 = rw.z & 0xFFFFu, s1 = rw.z >> 16, s2 = rw.w & 0xFFFFu, s3 = rw.w >> 16;
+    const uint32_t sT = swz(T);
+    const uint32_t low_mask = (1u << c.low) - 1u;
+
+    double2 a[16];
+    if (first) {
+        const uint64_t gT = (uint64_t)(T & low_mask) | c.hi_off[T >> c.low];
+        const uint64_t g0 = 1ull << (rw.y & 0xFFu), g1 = 1ull << ((rw.y >> 8) & 0xFFu),
+                       g2 = 1ull << ((rw.y >> 16) & 0xFFu), g3 = 1ull << (rw.y >> 24);
+        const double2* src = c.gbase + gT;
 #pragma unroll
-        for (int p = 0; p < 16; ++p)
-            if (!((p >> B) & 1)) a[p] = cmul(d, a[p]);
+        for (int j = 0; j < 16; ++j)
+            a[j] = src[((j & 1) ? g0 : 0) | ((j & 2) ? g1 : 0) | ((j & 4) ? g2 : 0) | ((j & 8) ? g3 : 0)];
     } else {
 #pragma unroll
-        for (int p = 0; p < 16; ++p)
-            if ((p >> B) & 1) a[p] = cmul(d, a[p]);
+        for (int j = 0; j < 16; ++j)
+            a[j] = c.tile[sT ^ ((j & 1) ? s0 : 0) ^ ((j & 2) ? s1 : 0) ^ ((j & 4) ? s2 : 0) ^ ((j & 8) ? s3 : 0)];
     }
-}
 
-// d0 / d1 on every slot by its logical bit B, no controls
-template <int B>
-__device__ __forceinline__ void reg_diag1_nc(double2 (&a)[16], double2 d0, double2 d1, const uint32_t xm) {
-    if ((xm >> B) & 1u) {
-        const double2 t = d0;
-        d0 = d1;
-        d1 = t;
+    // Thread-scalar batch: these ops touch no register qubit of this round, so they commute with all
+    // of its ops; the host sorts them first and they fold into one scalar per thread.
+    double2 ts = rd->scale;
+    bool ts_dirty = scaled;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (const OpWord* op = &c.ops[op_begin]; op != &c.ops[dt_end]; op += kOpWords) {
+        const uint2 w = *reinterpret_cast<const uint2*>(op);
+        const uint32_t cthr = w.y & 0xFFFFu;
+        if ((tid & cthr) != cthr) continue;
+        double2 f;
+        if ((w.x & 0xFFu) == OPC_T) {
+            f = op[1 + ((tid >> ((w.x >> 16) & 0xFFu)) & 1u)].d;
+        } else {      // OPC_TG: two thread-bit targets, factors from the pool
+            const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(op) + 8);
+            const uint32_t idx = (v.y & 0xFFu) | (((tid >> ((w.x >> 16) & 0xFFu)) & 1u) << ((v.y >> 8) & 0xFFu)) |
+                                 (((tid >> (w.x >> 24)) & 1u) << ((v.y >> 16) & 0xFFu));
+            f = QVM_LDG(&c.mats[v.x + idx]);
+        }
+        cmul_ip(ts, f);
+        ts_dirty = true;
     }
+    if (ts_dirty) {          // scalars commute with everything: apply now, so ts is dead in the main loop
 #pragma unroll
-    for (int p = 0; p < 16; ++p) a[p] = cmul(((p >> B) & 1) ? d1 : d0, a[p]);
+        for (int j = 0; j < 16; ++j) cmul_ip(a[j], ts);
+    }
+
+    uint32_t xm = 0;         // physical register p holds logical slot p ^ xm
+    if (dt_end < op_end) {
+        const OpWord* op = &c.ops[dt_end];
+        const OpWord* const op_last = &c.ops[op_end];
+        uint2 hn = *reinterpret_cast<const uint2*>(op);           // header words x, y of the NEXT op to run
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        while (op != op_last) {
+            const OpWord* const cur = op;
+            const uint32_t hx = hn.x, opc = hx & 0xFFu, cthr = hn.y & 0xFFFFu;
+            op += (hn.y >> HDR_SIZE_SHIFT) & 0xFu;
+            hn = *reinterpret_cast<const uint2*>(op);             // prefetch (one spare word follows the last op)
+            if (opc == OPC_LAYER) {
+                // per slot: [S1 factor] -> [H] -> [X relabel]; sub-ops on different slots commute
+                const uint4 m = cur[1].u;
+#define QVM_LAYER_SLOT(S, CS, CX)                                                        \
+                if (hx & (0x100u << S)) {                                                   \
+                    const uint32_t cm = (CS);                                               \
+                    if ((tid & cm) == cm) reg_s1<S>(a, cur[2 + S].d, xm);                   \
+                }                                                                           \
+                if (hx & (0x1000u << S)) reg_h<S>(a, xm);                                   \
+                if (hx & (0x10000u << S)) {                                                 \
+                    const uint32_t cm = (CX);                                               \
+                    if ((tid & cm) == cm) xm ^= 1u << S;                                    \
+                }
+                QVM_LAYER_SLOT(0, m.x & 0xFFFFu, m.z & 0xFFFFu)
+                QVM_LAYER_SLOT(1, m.x >> 16, m.z >> 16)
+                QVM_LAYER_SLOT(2, m.y & 0xFFFFu, m.w & 0xFFFFu)
+                QVM_LAYER_SLOT(3, m.y >> 16, m.w >> 16)
+#undef QVM_LAYER_SLOT
+                continue;
+            }
+            if ((tid & cthr) != cthr) continue;   // a control on a thread bit is 0, or op inactive here
+            double2 f = cur[1].d;
+            const uint32_t crm = (hx >> 8) & 0xFu, p0 = (hx >> 16) & 0xFFu;
+            switch (opc) {
+                case OPC_XS_0 + 0: reg_xswap<0>(a, crm, xm); break;
+                case OPC_XS_0 + 1: reg_xswap<1>(a, crm, xm); break;
+                case OPC_XS_0 + 2: reg_xswap<2>(a, crm, xm); break;
+                case OPC_XS_0 + 3: reg_xswap<3>(a, crm, xm); break;
+                case OPC_DST:
+                    f = cur[1 + ((tid >> p0) & 1u)].d;
+                    // fall through
+                case OPC_DS: {
+                    const uint32_t want = crm & ~xm;
+#pragma unroll
+                    for (int p = 0; p < 16; ++p)
+                        if ((p & crm) == want) cmul_ip(a[p], f);
+                    break;
+                }
+                case OPC_D1_0 + 0: reg_d1<0>(a, f, cur[2].d, crm, xm); break;
+                case OPC_D1_0 + 1: reg_d1<1>(a, f, cur[2].d, crm, xm); break;
+                case OPC_D1_0 + 2: reg_d1<2>(a, f, cur[2].d, crm, xm); break;
+                case OPC_D1_0 + 3: reg_d1<3>(a, f, cur[2].d, crm, xm); break;
+                default:
+                    if (FULL) {
+                        const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(cur) + 8);
+                        const double2* mat = c.mats + v.x;
+                        if (opc == OPC_DIAG_G) {
+                            const ColdOp* cd = &c.cold[(v.y >> 8) & 0xFFFFu];        // DIAG_G keeps its cold index in w[23:8]
+                            const uint32_t kk = cd->k;
+                            uint32_t idx = v.y & 0xFFu;
+                            uint32_t rm0 = 0, rm1 = 0, rm2 = 0, rm3 = 0, rs0 = 0, rs1 = 0, rs2 = 0, rs3 = 0;
+                            for (uint32_t t = 0; t < kk; ++t) {
+                                const uint32_t loc = cd->loc[t];
+                                const uint32_t cls = loc & LOC_CLASS;
+                                const uint32_t sh = 1u << (kk - 1 - t);
+                                if (cls == LOC_THR) idx |= ((tid >> (loc & LOC_INDEX)) & 1u) ? sh : 0u;
+                                else if (cls == LOC_REG) {
+                                    const uint32_t slot = loc & LOC_INDEX;       // each slot appears at most once
+                                    if (slot == 0) { rm0 = 1u; rs0 = sh; }
+                                    else if (slot == 1) { rm1 = 2u; rs1 = sh; }
+                                    else if (slot == 2) { rm2 = 4u; rs2 = sh; }
+                                    else { rm3 = 8u; rs3 = sh; }
+                                }
+                            }
+                            const uint32_t want = crm & ~xm;
+#pragma unroll
+                            for (int p = 0; p < 16; ++p) {
+                                if ((p & crm) == want) {
+                                    const uint32_t j = (uint32_t)p ^ xm;         // logical slot
+                                    const uint32_t ij = idx | ((j & rm0) ? rs0 : 0u) | ((j & rm1) ? rs1 : 0u) |
+                                                        ((j & rm2) ? rs2 : 0u) | ((j & rm3) ? rs3 : 0u);
+                                    a[p] = cmul(QVM_LDG(&mat[ij]), a[p]);
+                                }
+                            }
+                        } else if (opc >= OPC_M1_0 && opc < OPC_M1_0 + 4) {
+                            switch (opc - OPC_M1_0) {
+                                case 0: reg_dense1<0>(a, mat, crm, xm); break;
+                                case 1: reg_dense1<1>(a, mat, crm, xm); break;
+                                case 2: reg_dense1<2>(a, mat, crm, xm); break;
+                                default: reg_dense1<3>(a, mat, crm, xm); break;
+                            }
+                        } else if (opc == OPC_M2_0) reg_dense2<0>(a, mat, crm, xm);
+                        else if (opc == OPC_M2_0 + 1) reg_dense2<1>(a, mat, crm, xm);
+                    }
+                    break;
+            }
+        }
+    }
+
+    if (last) {
+        const uint64_t g0 = 1ull << (rw.y & 0xFFu), g1 = 1ull << ((rw.y >> 8) & 0xFFu),
+                       g2 = 1ull << ((rw.y >> 16) & 0xFFu), g3 = 1ull << (rw.y >> 24);
+        // register p holds logical slot p ^ xm; the slot -> address map is XOR-linear
+        const uint64_t gT = ((uint64_t)(T & low_mask) | c.hi_off[T >> c.low]) ^
+                            (((xm & 1) ? g0 : 0) | ((xm & 2) ? g1 : 0) | ((xm & 4) ? g2 : 0) | ((xm & 8) ? g3 : 0));
+        double2* dst = c.gbase;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            dst[gT ^ (((j & 1) ? g0 : 0) | ((j & 2) ? g1 : 0) | ((j & 4) ? g2 : 0) | ((j & 8) ? g3 : 0))] = a[j];
+    } else {
+        // same mapping as this round's load: every thread rewrites exactly the slots it read
+        const uint32_t sX = sT ^ ((xm & 1) ? s0 : 0) ^ ((xm & 2) ? s1 : 0) ^ ((xm & 4) ? s2 : 0) ^ ((xm & 8) ? s3 : 0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            c.tile[sX ^ ((j & 1) ? s0 : 0) ^ ((j & 2) ? s1 : 0) ^ ((j & 4) ? s2 : 0) ^ ((j & 8) ? s3 : 0)] = a[j];
+    }
 }
 
-__host__ __device__ inline size_t regtile_smem_bytes(int k, int n_rounds, int n_ops) {
-    size_t b = n_rounds > 1 ? ((size_t)16 << k) : 0;
-    b += (size_t)n_ops * sizeof(HotOp);
-    b += (size_t)n_rounds * sizeof(RoundDesc);
-    return b;
+// outer bits of tile `tile_index`: deposit it into the runs of non-tile positions
+QVM_HD uint64_t rt_tile_base(const RegTileParams& P, uint64_t tile_index) {
+    uint64_t base = 0, t = tile_index;
+    for (int r = 0; r < P.n_runs; ++r) {
+        const uint32_t len = (uint32_t)(P.run_len >> (8 * r)) & 0xFFu;
+        base |= (t & ((1ull << len) - 1ull)) << ((uint32_t)(P.run_start >> (8 * r)) & 0xFFu);
+        t >>= len;
+    }
+    return base;
 }
 
-// FULL = false drops the generic dense 2x2 / 4x4 and generic-diagonal handlers (the host launches
-// that lean variant when a group has none of them): ~40% less code, friendlier to the I-cache.
+#if defined(__CUDACC__)
 template <int MAX_THREADS, int MIN_BLOCKS, bool FULL>
 __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
 regtile_kernel(double2* __restrict__ state, const RegTileParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const size_t tile_bytes = P.n_rounds > 1 ? ((size_t)16 << P.k) : 0;
-    double2* tile = reinterpret_cast<double2*>(smem_raw);
-    HotOp* hot = reinterpret_cast<HotOp*>(smem_raw + tile_bytes);
-    RoundDesc* rounds = reinterpret_cast<RoundDesc*>(hot + P.n_ops);
+    OpWord* ops = reinterpret_cast<OpWord*>(smem_raw + tile_bytes);
+    RoundDesc* rounds = reinterpret_cast<RoundDesc*>(ops + P.n_words + 1);
+    uint64_t* hi_off = reinterpret_cast<uint64_t*>(rounds + P.n_rounds);
 
     const uint32_t tid = threadIdx.x;
     const uint32_t nthreads = blockDim.x;
-
-    // outer bits of this tile: deposit blockIdx into the runs of non-tile positions
-    uint64_t base = 0;
-    {
-        uint64_t t = blockIdx.x;
-        for (int r = 0; r < P.n_runs; ++r) {
-            const uint32_t len = (uint32_t)(P.run_len >> (8 * r)) & 0xFFu;
-            base |= (t & ((1ull << len) - 1ull)) << ((uint32_t)(P.run_start >> (8 * r)) & 0xFFu);
-            t >>= len;
-        }
-    }
+    const uint64_t base = rt_tile_base(P, blockIdx.x);
     const uint64_t full = base | P.shard_bits;
 
-    // stage descriptors; one thread per op evaluates what is uniform over the CTA
-    for (uint32_t j = tid; j < (uint32_t)P.n_ops; j += nthreads) {
-        uint4 h = __ldg(reinterpret_cast<const uint4*>(&P.hot[j]));
-        const ColdOp* c = &P.cold[j];
-        const uint64_t co = __ldg(&c->ctrl_outer);
-        if ((full & co) != co) h.y |= 0xFFFFu;           // inactive here: impossible thread mask
-        const uint32_t opc = h.x & 0xFFu;
-        if (opc >= OPC_DIAG_T) {
-            const uint32_t kk = c->k;
-            uint32_t oi = 0;
-            for (uint32_t t = 0; t < kk; ++t) {
-                const uint32_t loc = c->loc[t];
-                if ((loc & LOC_CLASS) == LOC_OUT) oi |= (uint32_t)((full >> (loc & LOC_INDEX)) & 1ull) << (kk - 1 - t);
-            }
-            h.w |= oi;
-        }
-        *reinterpret_cast<uint4*>(&hot[j]) = h;
+    for (uint32_t j = tid; j < (uint32_t)P.n_ops; j += nthreads) rt_resolve_op(P, j, full, ops);
+    if (tid == 0) ops[P.n_words].u = make_uint4(0, 0, 0, 0);          // the word the last prefetch reads
+    if (P.n_patches) {
+        __syncthreads();
+        for (uint32_t j = tid; j < (uint32_t)P.n_patches; j += nthreads) rt_patch_op(P, P.n_ops + j, full, ops);
     }
     {
         const uint32_t rwords = (uint32_t)(P.n_rounds * (sizeof(RoundDesc) / 16));
         const uint4* rsrc = reinterpret_cast<const uint4*>(P.rounds);
         uint4* rdst = reinterpret_cast<uint4*>(rounds);
         for (uint32_t w = tid; w < rwords; w += nthreads) rdst[w] = __ldg(&rsrc[w]);
+        const uint32_t n_hi = 1u << (P.k - P.low);
+        for (uint32_t w = tid; w < n_hi; w += nthreads) hi_off[w] = __ldg(&P.hi_off[w]);
     }
     __syncthreads();
 
-    double2 a[16];
-    double2* gbase = state + base;
-    const uint32_t low_mask = (1u << P.low) - 1u;
-
+    RtCta c;
+    c.tile = reinterpret_cast<double2*>(smem_raw);
+    c.ops = ops;
+    c.rounds = rounds;
+    c.hi_off = hi_off;
+    c.gbase = state + base;
+    c.mats = P.mats;
+    c.cold = P.cold;
+    c.low = P.low;
+    c.n_rounds = P.n_rounds;
     for (int r = 0; r < P.n_rounds; ++r) {
-        const uint4 rw = *reinterpret_cast<const uint4*>(&rounds[r]);      // reg_bit | reg_sorted | reg_phys | op range
-        const uint2 rw2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(&rounds[r]) + 16);
-        // tile index of this thread: tid with zeros inserted at the (ascending) register-bit positions
-        uint32_t T = tid;
-        T = insert_zero32(T, rw.y & 0xFFu);
-        T = insert_zero32(T, (rw.y >> 8) & 0xFFu);
-        T = insert_zero32(T, (rw.y >> 16) & 0xFFu);
-        T = insert_zero32(T, rw.y >> 24);
-        const uint32_t J0 = 1u << (rw.x & 0xFFu), J1 = 1u << ((rw.x >> 8) & 0xFFu), J2 = 1u << ((rw.x >> 16) & 0xFFu),
-                       J3 = 1u << (rw.x >> 24);
-        const uint32_t op_begin = rw.w & 0xFFFFu, op_end = rw.w >> 16;
-        const uint32_t dt_end = *reinterpret_cast<const uint16_t*>(reinterpret_cast<const unsigned char*>(&rounds[r]) + 24);
-
-        if (r == 0) {
-            const uint64_t gT = (uint64_t)(T & low_mask) | __ldg(&P.hi_off[T >> P.low]);
-            const uint64_t g0 = 1ull << (rw.z & 0xFFu), g1 = 1ull << ((rw.z >> 8) & 0xFFu),
-                           g2 = 1ull << ((rw.z >> 16) & 0xFFu), g3 = 1ull << (rw.z >> 24);
-            const double2* src = gbase + gT;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                a[j] = src[((j & 1) ? g0 : 0) | ((j & 2) ? g1 : 0) | ((j & 4) ? g2 : 0) | ((j & 8) ? g3 : 0)];
-        } else {
-            const uint32_t sT = swz(T), s0 = swz(J0), s1 = swz(J1), s2 = swz(J2), s3 = swz(J3);
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                a[j] = tile[sT ^ ((j & 1) ? s0 : 0) ^ ((j & 2) ? s1 : 0) ^ ((j & 4) ? s2 : 0) ^ ((j & 8) ? s3 : 0)];
-        }
-
-        const double rscale = __hiloint2double((int)rw2.y, (int)rw2.x);
-        double2 ts = make_double2(rscale, 0.0);   // per-thread scalar: folded H scales and DIAG_T factors
-        bool ts_dirty = rscale != 1.0;
-        uint32_t xm = 0;                          // physical register p holds logical slot p ^ xm
-
-        // DIAG_T ops touch no register qubit of this round, so they commute with all of its ops:
-        // the host sorts them first and they run as one tight batch into the thread scalar.
-#pragma unroll 1
-        for (uint32_t o = op_begin; o < dt_end; ++o) {
-            const uint4 w = *reinterpret_cast<const uint4*>(&hot[o]);
-            const uint32_t cthr = w.y & 0xFFFFu;
-            if ((tid & cthr) != cthr) continue;
-            const uint32_t idx = (w.w & 0xFFu) | (((tid >> ((w.y >> 16) & 0xFFu)) & 1u) << ((w.x >> 16) & 0xFFu)) |
-                                 (((tid >> (w.y >> 24)) & 1u) << (w.x >> 24));
-            ts = cmul(__ldg(&P.mats[w.z + idx]), ts);
-            ts_dirty = true;
-        }
-
-        if (ts_dirty) {          // scalars commute with everything: apply now, so ts is dead in the main loop
-#pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] = cmul(ts, a[j]);
-        }
-
-        for (uint32_t o = dt_end; o < op_end; ++o) {
-            const uint4 w = *reinterpret_cast<const uint4*>(&hot[o]);
-            const uint32_t cthr = w.y & 0xFFFFu;
-            if ((tid & cthr) != cthr) continue;           // a control on a thread bit is 0, or op inactive here
-            const uint32_t opc = w.x & 0xFFu;
-            const uint32_t crm = (w.x >> 8) & 0xFu;
-            const double2* mat = P.mats + w.z;
-            if (opc == OPC_X_RELABEL) { xm ^= 1u << ((w.x >> 12) & 0xFu); continue; }
-            if (opc < OPC_D1_0) {                 // Hadamard butterfly on slot opc - OPC_H0
-                if (opc == OPC_H0 + 0) { reg_h<0>(a, (xm & 1u) << 31); xm &= ~1u; }
-                else if (opc == OPC_H0 + 1) { reg_h<1>(a, (xm & 2u) << 30); xm &= ~2u; }
-                else if (opc == OPC_H0 + 2) { reg_h<2>(a, (xm & 4u) << 29); xm &= ~4u; }
-                else { reg_h<3>(a, (xm & 8u) << 28); xm &= ~8u; }
-                continue;
-            }
-            if (FULL && opc >= OPC_D1_0 && opc < OPC_XS_0) {
-                switch (opc - OPC_D1_0) {
-                    case 0: reg_dense1<0>(a, mat, crm, xm); break;
-                    case 1: reg_dense1<1>(a, mat, crm, xm); break;
-                    case 2: reg_dense1<2>(a, mat, crm, xm); break;
-                    default: reg_dense1<3>(a, mat, crm, xm); break;
-                }
-                continue;
-            }
-            if (FULL && (opc == OPC_D2_0 || opc == OPC_D2_0 + 1)) {
-                if (opc == OPC_D2_0) reg_dense2<0>(a, mat, crm, xm);
-                else reg_dense2<1>(a, mat, crm, xm);
-                continue;
-            }
-            if (FULL && opc == OPC_DIAG_G) {
-                const ColdOp* c = &P.cold[o];
-                const uint32_t kk = c->k;
-                uint32_t idx = w.w & 0xFFu;
-                uint32_t rm0 = 0, rm1 = 0, rm2 = 0, rm3 = 0, rs0 = 0, rs1 = 0, rs2 = 0, rs3 = 0;
-                for (uint32_t t = 0; t < kk; ++t) {
-                    const uint32_t loc = c->loc[t];
-                    const uint32_t cls = loc & LOC_CLASS;
-                    const uint32_t sh = 1u << (kk - 1 - t);
-                    if (cls == LOC_THR) idx |= ((tid >> (loc & LOC_INDEX)) & 1u) ? sh : 0u;
-                    else if (cls == LOC_REG) {
-                        const uint32_t slot = loc & LOC_INDEX;       // each slot appears at most once
-                        if (slot == 0) { rm0 = 1u; rs0 = sh; }
-                        else if (slot == 1) { rm1 = 2u; rs1 = sh; }
-                        else if (slot == 2) { rm2 = 4u; rs2 = sh; }
-                        else { rm3 = 8u; rs3 = sh; }
-                    }
-                }
-                const uint32_t want = crm & ~xm;
-#pragma unroll
-                for (int p = 0; p < 16; ++p) {
-                    if ((p & crm) == want) {
-                        const uint32_t j = (uint32_t)p ^ xm;         // logical slot
-                        const uint32_t ij = idx | ((j & rm0) ? rs0 : 0u) | ((j & rm1) ? rs1 : 0u) |
-                                            ((j & rm2) ? rs2 : 0u) | ((j & rm3) ? rs3 : 0u);
-                        a[p] = cmul(__ldg(&mat[ij]), a[p]);
-                    }
-                }
-                continue;
-            }
-            switch (opc) {
-                case OPC_XS_0 + 0: reg_xswap<0>(a, crm, xm); break;
-                case OPC_XS_0 + 1: reg_xswap<1>(a, crm, xm); break;
-                case OPC_XS_0 + 2: reg_xswap<2>(a, crm, xm); break;
-                case OPC_XS_0 + 3: reg_xswap<3>(a, crm, xm); break;
-                default: {      // thread-indexed diagonals: DIAG_T, DIAG_S, DIAG_S1 + slot, DIAG1 + slot, DIAG1NC + slot
-                    // index bits from (at most two) thread-bit targets; position 31 means "none"
-                    const uint32_t idx = (w.w & 0xFFu) | (((tid >> ((w.y >> 16) & 0xFFu)) & 1u) << ((w.x >> 16) & 0xFFu)) |
-                                         (((tid >> (w.y >> 24)) & 1u) << (w.x >> 24));
-                    const double2 d0 = __ldg(&mat[idx]);
-                    if (opc >= OPC_DIAG_S1_0 && opc < OPC_DIAG_S1_0 + 4) {
-                        switch (opc - OPC_DIAG_S1_0) {
-                            case 0: reg_diag_s1<0>(a, d0, xm); break;
-                            case 1: reg_diag_s1<1>(a, d0, xm); break;
-                            case 2: reg_diag_s1<2>(a, d0, xm); break;
-                            default: reg_diag_s1<3>(a, d0, xm); break;
-                        }
-                    } else if (opc >= OPC_DIAG1NC_0) {
-                        const double2 d1 = __ldg(&mat[idx | (1u << ((w.w >> 8) & 0xFFu))]);
-                        switch (opc - OPC_DIAG1NC_0) {
-                            case 0: reg_diag1_nc<0>(a, d0, d1, xm); break;
-                            case 1: reg_diag1_nc<1>(a, d0, d1, xm); break;
-                            case 2: reg_diag1_nc<2>(a, d0, d1, xm); break;
-                            default: reg_diag1_nc<3>(a, d0, d1, xm); break;
-                        }
-                    } else if (opc == OPC_DIAG_S) {
-                        const uint32_t want = crm & ~xm;
-#pragma unroll
-                        for (int p = 0; p < 16; ++p)
-                            if ((p & crm) == want) a[p] = cmul(d0, a[p]);
-                    } else {
-                        const double2 d1 = __ldg(&mat[idx | (1u << ((w.w >> 8) & 0xFFu))]);
-                        switch (opc - OPC_DIAG1_0) {
-                            case 0: reg_diag1<0>(a, d0, d1, crm, xm); break;
-                            case 1: reg_diag1<1>(a, d0, d1, crm, xm); break;
-                            case 2: reg_diag1<2>(a, d0, d1, crm, xm); break;
-                            default: reg_diag1<3>(a, d0, d1, crm, xm); break;
-                        }
-                    }
-                    break;
-                }
-            }
-        }
-
-        // recompute the thread mapping here rather than keeping it live across the op loop
-        const uint4 sw_ = *reinterpret_cast<const uint4*>(&rounds[r]);
-        uint32_t T2 = tid;
-        T2 = insert_zero32(T2, sw_.y & 0xFFu);
-        T2 = insert_zero32(T2, (sw_.y >> 8) & 0xFFu);
-        T2 = insert_zero32(T2, (sw_.y >> 16) & 0xFFu);
-        T2 = insert_zero32(T2, sw_.y >> 24);
-        if (r == P.n_rounds - 1) {
-            const uint64_t g0 = 1ull << (sw_.z & 0xFFu), g1 = 1ull << ((sw_.z >> 8) & 0xFFu),
-                           g2 = 1ull << ((sw_.z >> 16) & 0xFFu), g3 = 1ull << (sw_.z >> 24);
-            // register p holds logical slot p ^ xm; the slot -> address map is XOR-linear
-            const uint64_t gT = ((uint64_t)(T2 & low_mask) | __ldg(&P.hi_off[T2 >> P.low])) ^
-                                (((xm & 1) ? g0 : 0) | ((xm & 2) ? g1 : 0) | ((xm & 4) ? g2 : 0) | ((xm & 8) ? g3 : 0));
-            double2* dst = gbase;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                dst[gT ^ (((j & 1) ? g0 : 0) | ((j & 2) ? g1 : 0) | ((j & 4) ? g2 : 0) | ((j & 8) ? g3 : 0))] = a[j];
-        } else {
-            // same mapping as this round's load: every thread rewrites exactly the slots it read
-            const uint32_t s0 = swz(1u << (sw_.x & 0xFFu)), s1 = swz(1u << ((sw_.x >> 8) & 0xFFu)),
-                           s2 = swz(1u << ((sw_.x >> 16) & 0xFFu)), s3 = swz(1u << (sw_.x >> 24));
-            const uint32_t sT = swz(T2) ^ ((xm & 1) ? s0 : 0) ^ ((xm & 2) ? s1 : 0) ^ ((xm & 4) ? s2 : 0) ^ ((xm & 8) ? s3 : 0);
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                tile[sT ^ ((j & 1) ? s0 : 0) ^ ((j & 2) ? s1 : 0) ^ ((j & 4) ? s2 : 0) ^ ((j & 8) ? s3 : 0)] = a[j];
-            __syncthreads();
-        }
+        rt_thread_round<FULL>(c, r, tid);
+        if (r + 1 < P.n_rounds) __syncthreads();
     }
 }
+#endif  // __CUDACC__
 
 }  // namespace qvm

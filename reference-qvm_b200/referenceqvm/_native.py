@@ -77,6 +77,10 @@ _SIGNATURES = {
     "qvm_sample": (C.c_int, [_P, C.c_uint64, _P, _P]),
     "qvm_pack_half": (C.c_int, [_P, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _P]),
     "qvm_unpack_half": (C.c_int, [_P, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _P]),
+    "qvm_ipc_export": (C.c_int, [_P, _P]),
+    "qvm_ipc_open": (C.c_int, [_P, _P, C.POINTER(_P)]),
+    "qvm_ipc_close": (C.c_int, [_P, _P]),
+    "qvm_exchange_half": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_uint64, C.c_uint64]),
 }
 EXPORTED = tuple(sorted(_SIGNATURES))
 
@@ -367,6 +371,24 @@ class DeviceState(object):
     # -- exchange plumbing -------------------------------------------------------------------
     def pack_half(self, local_bit, bit_value, elem_offset, count, device_dst_ptr):
         check(lib().qvm_pack_half(self.handle, local_bit, bit_value, elem_offset, count, _P(device_dst_ptr)))
+
+    def ipc_export(self):
+        """64-byte CUDA IPC handle of this shard's allocation (bytes)."""
+        buf = C.create_string_buffer(64)
+        check(lib().qvm_ipc_export(self.handle, buf))
+        return buf.raw
+
+    def ipc_open(self, handle_bytes):
+        """Map a peer process's shard; returns its device pointer in this process."""
+        ptr = _P()
+        check(lib().qvm_ipc_open(self.handle, C.c_char_p(bytes(handle_bytes)), C.byref(ptr)))
+        return int(ptr.value)
+
+    def ipc_close(self, peer_ptr):
+        check(lib().qvm_ipc_close(self.handle, _P(peer_ptr)))
+
+    def exchange_half(self, local_bit, mine_value, peer_ptr, elem_offset, count):
+        check(lib().qvm_exchange_half(self.handle, local_bit, mine_value, _P(peer_ptr), elem_offset, count))
 
     def unpack_half(self, local_bit, bit_value, elem_offset, count, device_src_ptr):
         check(lib().qvm_unpack_half(self.handle, local_bit, bit_value, elem_offset, count, _P(device_src_ptr)))

@@ -17,6 +17,8 @@ the rank.  A host-side logical->physical qubit layout tracks remaps.
 All ranks run the same program (SPMD) and make identical planning decisions; random draws are
 broadcast from rank 0.
 """
+import os
+
 import numpy as np
 
 from referenceqvm import _native as nat
@@ -65,11 +67,22 @@ class CudaShard(object):
         torch.cuda.set_device(ctx.device)
         self.state = nat.DeviceState(n_local, ctx.device)
         self.state.set_shard(ctx.n_global, ctx.rank)
-        # run the library's kernels on torch's current stream so they order with NCCL operations
-        self.state.set_stream(torch.cuda.current_stream().cuda_stream)
+        # One dedicated stream carries the library's kernels AND is torch's current stream, so NCCL
+        # operations (which order themselves against the current stream) see packs / unpacks in order.
+        # (The legacy default stream has handle 0, which qvm_set_stream reads as "own stream".)
+        self.stream = torch.cuda.Stream(device=ctx.device)
+        torch.cuda.set_stream(self.stream)
+        self.state.set_stream(self.stream.cuda_stream)
         self.device = torch.device("cuda", ctx.device)
 
     def close(self):
+        if getattr(self, "peers", None):
+            for ptr in self.peers.values():
+                try:
+                    self.state.ipc_close(ptr)
+                except Exception:
+                    pass
+            self.peers = None
         self.state.close()
 
     def alloc(self, n_amps):
@@ -84,6 +97,26 @@ class CudaShard(object):
             self.state.apply_group(group.tile, group.ops)
             n += 1
         return n
+
+    def open_peers(self, dist, group):
+        """Map every peer's shard into this process (CUDA IPC) so that a global<->local swap is one
+        kernel over NVLink peer memory.  Returns False when IPC is unavailable (NCCL path is kept)."""
+        torch = self.torch
+        try:
+            mine = torch.tensor(list(self.state.ipc_export()), dtype=torch.uint8, device=self.device)
+            handles = [torch.empty_like(mine) for _ in range(self.ctx.world)]
+            dist.all_gather(handles, mine, group=group)
+            self.peers = {}
+            for r, h in enumerate(handles):
+                if r != self.ctx.rank:
+                    self.peers[r] = self.state.ipc_open(bytes(h.cpu().numpy().tobytes()))
+            return True
+        except Exception:
+            self.peers = None
+            return False
+
+    def exchange_half(self, bit, mine_value, partner, off, cnt):
+        self.state.exchange_half(bit, mine_value, self.peers[partner], off, cnt)
 
     def pack_half(self, bit, value, off, cnt, buf):
         self.state.pack_half(bit, value, off, cnt, buf.data_ptr())
@@ -123,7 +156,7 @@ class CudaShard(object):
 
     def record_event(self):
         e = self.torch.cuda.Event(enable_timing=True)
-        e.record()
+        e.record(self.stream)
         return e
 
 
@@ -149,6 +182,15 @@ class ShardedEngine(object):
         self.shard = (backend_factory or CudaShard)(self.n_local, self.ctx)
         self.chunk_amps = min(chunk_amps or self.CHUNK_AMPS, 1 << (self.n_local - 1))
         self._send = self._recv = None
+        # peer-memory swaps (one kernel over NVLink) when the backend can map its peers; the staged
+        # NCCL send/recv exchange otherwise (and under QVM_B200_SWAP=nccl, for A/B runs)
+        self.p2p = False
+        if os.environ.get("QVM_B200_SWAP", "p2p") == "p2p" and hasattr(self.shard, "open_peers"):
+            self.p2p = bool(self.shard.open_peers(self.dist, self.ctx.group))
+            flag = self.shard.scalar_tensor([1.0 if self.p2p else 0.0])
+            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.ctx.group)
+            self.p2p = bool(float(flag.cpu()[0]) > 0.5)
+            self._token = self.shard.scalar_tensor([0.0])
         self.pos_of = list(range(self.n))         # logical qubit -> physical position
         self.pending = []                         # ClassifiedOps in LOGICAL coordinates
         self.gates_queued = 0
@@ -307,9 +349,23 @@ class ShardedEngine(object):
         gbit = pg - self.n_local
         mine = (self.ctx.rank >> gbit) & 1
         partner = self.ctx.rank ^ (1 << gbit)
-        send, recv = self._buffers()
         e0 = self.shard.record_event() if self.timing is not None else None
         half = 1 << (self.n_local - 1)
+        if self.p2p:
+            # stream-ordered cross-rank barrier (a tiny all-reduce), the swap kernel on my half of the
+            # element range, barrier again: nobody touches a shard its partner is still working on
+            self.dist.all_reduce(self._token, group=self.ctx.group)
+            lo = 0 if mine == 0 else half // 2
+            cnt = half // 2 if mine == 0 else half - half // 2
+            self.shard.exchange_half(pl, 1 - mine, partner, lo, cnt)
+            self.dist.all_reduce(self._token, group=self.ctx.group)
+            self.pos_of[q_global], self.pos_of[q_local] = pl, pg
+            self.swaps += 1
+            self.swap_bytes += 16 * half
+            if e0 is not None:
+                self.timing["swap"].append((e0, self.shard.record_event()))
+            return
+        send, recv = self._buffers()
         moving = 1 - mine           # the half whose local bit differs from my global bit changes owner
         dist = self.dist
         pending = None              # (requests, offset, count, buffer index) of the chunk in flight

@@ -1,16 +1,50 @@
+"""Opcode histogram of the register-tile encoder on the benchmark circuit (host only: runs the
+product encoder through the test emulator's shared object on a small state with the same tiling)."""
+import os
 import sys
-import os; R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "reference-qvm_b200"))
-import numpy as np
-from referenceqvm import _engine, gates as G
-from oracle.qvm_oracle import random_circuit_spec
-n = 28
-eng = _engine.Engine(n)
-eng.reset()
-for name, params, qubits in random_circuit_spec(n, 40, 1234):
-    m = G.gate_matrix[name]
-    eng.queue_matrix(m(*params) if params else m, qubits)
-eng.flush(); eng.sync()
-h = eng.state.opcode_hist()
-names = {0: "X_RELABEL", 1: "H0", 2: "H1", 3: "H2", 4: "H3", 5: "D1_0", 6: "D1_1", 7: "D1_2", 8: "D1_3", 9: "XS0", 10: "XS1", 11: "XS2", 12: "XS3", 13: "D2_0", 14: "D2_1", 15: "DIAG_T", 16: "DIAG_S", 17: "DIAG1_0", 18: "DIAG1_1", 19: "DIAG1_2", 20: "DIAG1_3", 21: "DIAG_G"}
-st = eng.stats()
-print({names[i]: int(v) for i, v in enumerate(h) if v}, "groups", st["groups_launched"], "rounds", st["regtile_rounds"])
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (REPO, os.path.join(REPO, "reference-qvm_b200"), os.path.join(REPO, "tests")):
+    sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import referenceqvm  # noqa: E402,F401
+import _emu  # noqa: E402
+from oracle.qvm_oracle import random_circuit_spec  # noqa: E402
+from referenceqvm import _engine, _planner, gates as G  # noqa: E402
+
+NAMES = {0: "X_RELABEL", 1: "H", 5: "XS", 9: "S1", 13: "DS", 14: "D1", 18: "DIAG_G", 19: "M1", 23: "M2", 25: "T", 26: "TG"}
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+    depth = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+    tile = int(sys.argv[3]) if len(sys.argv) > 3 else 12
+    spec = random_circuit_spec(n, depth, 1234)
+    ops = []
+    for name, params, qubits in spec:
+        m = G.gate_matrix[name]
+        ops.append(_engine.compile_gate(m(*params) if params else m, qubits))
+    psi = np.zeros(1 << n, dtype=np.complex128)
+    psi[0] = 1
+    hist = np.zeros(32, dtype=np.int64)
+    groups = _planner.plan(ops, n, tile, 5)
+    rounds = 0
+    layers = 0
+    for g in groups:
+        psi, info = _emu.apply_group(psi, n, g.tile, g.ops)
+        hist += info["opc_hist"]
+        rounds += info["rounds"]
+        layers += info["layers"]
+    print("n=%d depth=%d tile=%d: %d gates, %d groups, %d rounds, %d layers" % (n, depth, tile, len(ops), len(groups), rounds, layers))
+    agg = {}
+    for opc in range(32):
+        base = max(k for k in NAMES if k <= opc)
+        agg[NAMES[base]] = agg.get(NAMES[base], 0) + int(hist[opc])
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1]):
+        if v:
+            print("  %-10s %5d  (%.1f per group)" % (k, v, v / len(groups)))
+
+
+if __name__ == "__main__":
+    main()

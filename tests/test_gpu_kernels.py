@@ -331,3 +331,27 @@ def test_regtile_mixed_ops_one_group():
         got = st.get_state()
         st.close()
         assert np.max(np.abs(got - want)) < TOL, tile
+
+
+def test_exchange_half_between_two_shards_on_one_device():
+    """qvm_exchange_half (the peer-memory swap kernel) with the "peer" being a second shard on the
+    same GPU: after both sides ran their half of the range, the moving halves have traded places."""
+    n = 14
+    for bit in (0, 3, 7, 13):
+        a, b = random_state(n, 1), random_state(n, 2)
+        sa, sb = fresh(n, a), fresh(n, b)
+        half = 1 << (n - 1)
+        # rank "0" owns global bit 0: its local-bit-1 half moves; rank "1": its local-bit-0 half moves
+        sa.exchange_half(bit, 1, sb.device_ptr(), 0, half // 2)
+        sa.sync()
+        sb.exchange_half(bit, 0, sa.device_ptr(), half // 2, half - half // 2)
+        sb.sync()
+        ga, gb = sa.get_state(), sb.get_state()
+        sa.close()
+        sb.close()
+        idx = np.arange(1 << n)
+        one = ((idx >> bit) & 1) == 1
+        want_a, want_b = a.copy(), b.copy()
+        want_a[one] = b[~one]
+        want_b[~one] = a[one]
+        assert np.array_equal(ga, want_a) and np.array_equal(gb, want_b), bit

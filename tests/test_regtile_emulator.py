@@ -1,0 +1,162 @@
+"""The register-tiled kernel's encoder and round body, executed on the CPU (tests/native), against
+the oracle: same source as the CUDA kernel (qvm_regtile.cuh is __host__ __device__), so opcode
+selection, round planning, relabelling and the op handlers are all covered without a GPU."""
+import numpy as np
+import pytest
+
+import _emu
+from _model import apply_op, random_state, random_unitary
+from _numpy_shard import localise, apply_local
+from oracle import qvm_oracle as orc
+from referenceqvm import _engine, _native as nat, _planner
+from referenceqvm import gates as G
+
+TOL = 1e-12
+
+
+def compile_spec(spec):
+    ops = []
+    for name, params, qubits in spec:
+        m = G.gate_matrix[name]
+        ops.append(_engine.compile_gate(m(*params) if params else m, qubits))
+    return ops
+
+
+def run_emulated(psi, ops, n, tile_bits, low_bits, force_full=False):
+    stats = {"groups": 0, "rounds": 0, "fallback": 0}
+    for g in _planner.plan(ops, n, tile_bits, low_bits):
+        new, info = _emu.apply_group(psi, n, g.tile, g.ops, force_full=force_full)
+        if info["status"] == 1:                 # outside the register-tile encoder: model the fallback
+            stats["fallback"] += 1
+            for op in g.ops:
+                psi = apply_op(psi, op, n)
+            continue
+        assert info["status"] == 0
+        psi = new
+        stats["groups"] += 1
+        stats["rounds"] += info["rounds"]
+    return psi, stats
+
+
+@pytest.mark.parametrize("n,depth,seed,tile", [(12, 12, 1, 12), (13, 10, 2, 12), (14, 8, 3, 12), (14, 6, 1234, 13),
+                                               (11, 20, 5, 9), (15, 5, 7, 12), (13, 12, 11, 10)])
+def test_random_circuit_through_emulated_kernel(n, depth, seed, tile):
+    spec = orc.random_circuit_spec(n, depth, seed)
+    ops = compile_spec(spec)
+    psi0 = random_state(n, seed)
+    want = psi0
+    for name, params, qubits in spec:
+        m = G.gate_matrix[name]
+        want = orc.fast_apply_gate(want, np.asarray(m(*params) if params else m, dtype=complex), qubits, n)
+    for force_full in (False, True):
+        got, stats = run_emulated(psi0, ops, n, tile, 5, force_full)
+        assert stats["fallback"] == 0 and stats["groups"] >= 1
+        err = np.max(np.abs(got - want))
+        assert err < TOL, (n, depth, seed, force_full, err)
+
+
+def test_qft_and_inverse():
+    n = 13
+    spec = orc.qft_spec(n)
+    ops = compile_spec(spec)
+    psi0 = random_state(n, 4)
+    want = psi0
+    for name, params, qubits in spec:
+        m = G.gate_matrix[name]
+        want = orc.fast_apply_gate(want, np.asarray(m(*params) if params else m, dtype=complex), qubits, n)
+    got, stats = run_emulated(psi0, ops, n, 12, 5)
+    assert np.max(np.abs(got - want)) < TOL
+
+
+def test_every_gate_kind_and_position():
+    """Dense 1q/2q (incl. non-unitary), controlled, diagonal k = 1..3, scalars, projectors."""
+    rs = np.random.RandomState(0)
+    n = 12
+    g1 = rs.standard_normal((2, 2)) + 1j * rs.standard_normal((2, 2))
+    g2 = rs.standard_normal((4, 4)) + 1j * rs.standard_normal((4, 4))
+    d3 = np.diag(np.exp(1j * rs.uniform(0, 6, 8)))
+    d2 = np.diag(rs.standard_normal(4) + 1j * rs.standard_normal(4))
+    cg1 = np.eye(4, dtype=complex)
+    cg1[2:, 2:] = g1
+    crz = np.diag([1, 1, np.exp(0.3j), 0.5 * np.exp(-1.1j)])                   # control + diag(a, b)
+    ccrz = np.diag([1, 1, 1, 1, 1, 1, np.exp(0.7j), np.exp(-0.2j)])            # two controls + diag(a, b)
+    mats = []
+    for q in range(n):
+        mats += [(g1, [q]), (G.H, [q]), (G.RZ(0.3 + q), [q]), (G.X, [q]), (G.P0 + 0.5 * G.P1, [q]), (G.P1, [(q + 3) % n])]
+        mats[-1:] = []          # keep the state away from zero: drop the projector
+        a, b, c = q, (q + 5) % n, (q + 7) % n
+        mats += [(g2, [a, b]), (G.CNOT, [a, b]), (G.CNOT, [b, a]), (G.CPHASE(0.7), [a, c]), (cg1, [c, a]),
+                 (d2, [b, c]), (G.CPHASE00(1.1), [a, b]), (G.CPHASE01(0.4), [c, b]), (G.SWAP, [a, c]),
+                 (G.CCNOT, [a, b, c]), (d3, [c, a, b]), (G.ISWAP, [b, a]), (G.CZ, [a, b]), (np.diag([1, 1j]), [c]),
+                 (2.0 * np.eye(2), [a]), (crz, [a, b]), (crz, [c, a]), (ccrz, [a, b, c]), (ccrz, [c, b, a])]
+    ops = [_engine.compile_gate(m, q) for m, q in mats]
+    psi0 = random_state(n, 9)
+    want = psi0
+    for m, q in mats:
+        want = orc.fast_apply_gate(want, np.asarray(m, dtype=complex), q, n)
+    scale = np.max(np.abs(want))
+    for tile, low in ((12, 5), (10, 5), (9, 3)):
+        got, stats = run_emulated(psi0, ops, n, tile, low)
+        assert np.max(np.abs(got - want)) / scale < TOL, (tile, low)
+
+
+def test_projector_diagonal_with_zero_entry():
+    """diag(0, 1) / diag(1, 0) on register slots must not be normalised by a zero d0."""
+    n = 12
+    mats = [(G.H, [q]) for q in range(n)] + [(G.P1, [11]), (G.H, [11]), (G.P0, [10]), (G.H, [10]), (G.P1, [0])]
+    ops = [_engine.compile_gate(m, q) for m, q in mats]
+    psi0 = random_state(n, 2)
+    want = psi0
+    for m, q in mats:
+        want = orc.fast_apply_gate(want, np.asarray(m, dtype=complex), q, n)
+    got, _ = run_emulated(psi0, ops, n, 12, 5)
+    assert np.max(np.abs(got - want)) < TOL
+
+
+def test_sharded_group_with_global_controls_and_diagonals():
+    """Ops whose controls / diagonal targets sit on global positions, per shard index."""
+    n_local, n_global = 11, 2
+    n = n_local + n_global
+    spec = orc.random_circuit_spec(n, 8, 21)
+    ops = []
+    for name, params, qubits in spec:
+        m = G.gate_matrix[name]
+        op = _engine.compile_gate(m(*params) if params else m, qubits)
+        if op.kind == nat.OP_DENSE and any(t >= n_local for t in op.targets):
+            continue                # dense targets on global positions need the exchange step
+        ops.append(op)
+    for shard in range(1 << n_global):
+        psi0 = random_state(n_local, shard)
+        want = psi0
+        for op in ops:
+            lop = localise(op, n_local, shard)
+            if lop is not None:
+                want = apply_local(want, lop, n_local)
+        psi = psi0
+        for g in _planner.plan(ops, n_local, 10, 5):
+            psi, info = _emu.apply_group(psi, n_local, g.tile, g.ops, n_global=n_global, shard_index=shard)
+            assert info["status"] == 0
+        assert np.max(np.abs(psi - want)) < TOL, shard
+
+
+def test_density_style_superoperators():
+    """Non-unitary 4x4 Kraus superoperators and conj(U) pairs as the density QVM queues them."""
+    from referenceqvm.qvm_density import kraus_superoperator
+    from referenceqvm.gates import dephasing, relaxation, depolarizing
+    nq = 6
+    n = 2 * nq
+    mats = []
+    rs = np.random.RandomState(5)
+    for q in range(nq):
+        u = random_unitary(2, rs)
+        mats += [(u, [q + nq]), (np.conj(u), [q])]
+        for kraus in (relaxation(0.1), dephasing(0.2), depolarizing(0.05)):
+            mats.append((kraus_superoperator(kraus), [q + nq, q]))
+    mats += [(G.CNOT, [0 + nq, 3 + nq]), (np.conj(G.CNOT), [0, 3])]
+    ops = [_engine.compile_gate(m, q) for m, q in mats]
+    psi0 = random_state(n, 3)
+    want = psi0
+    for m, q in mats:
+        want = orc.fast_apply_gate(want, np.asarray(m, dtype=complex), q, n)
+    got, stats = run_emulated(psi0, ops, n, 12, 5)
+    assert np.max(np.abs(got - want)) < TOL
