@@ -250,6 +250,7 @@ def main():
     eng.state.stats_reset()
     groups_before = eng.groups_launched
     swaps_before = getattr(eng, "swaps", 0)
+    swap_bytes_before = getattr(eng, "swap_bytes", 0)
     if sharded:
         eng.timing = {"batch": [], "swap": []}
     sampler = ClockSampler(local_rank)
@@ -289,10 +290,12 @@ def main():
                 "effective_gbs": n_gates * args.steps * bytes_per_launch * world / (total_ms * 1e-3) / 1e9,
                 "note": "per GPU (rank 0): one launch = one read + one write of the local shard"}
     if sharded and swaps:
-        swap_bytes = 8.0 * 2 ** n_local          # sent (and received) per GPU per swap
-        roofline["nvlink"] = {"bound": "nvlink", "achieved": swap_bytes * swaps / (swap_ms * 1e-3) / 1e9, "peak": 900.0,
+        swap_bytes = float(eng.swap_bytes - swap_bytes_before)      # sent (= received) per GPU, all exchanges
+        roofline["nvlink"] = {"bound": "nvlink", "achieved": swap_bytes / (swap_ms * 1e-3) / 1e9, "peak": 900.0,
                               "unit": "GB/s per direction per GPU", "swaps_per_step": swaps / float(args.steps),
-                              "bytes_per_swap_per_direction": swap_bytes, "avg_swap_ms": swap_ms / swaps,
+                              "bytes_per_swap_per_direction": swap_bytes / swaps, "avg_swap_ms": swap_ms / swaps,
+                              "exchange": "one kernel over NVLink peer memory (CUDA IPC), several global qubits per "
+                                          "exchange" if getattr(eng, "p2p", False) else "staged NCCL send/recv",
                               "share_of_step": swap_ms / (total_ms if total_ms else 1.0)}
         roofline["nvlink"]["frac"] = roofline["nvlink"]["achieved"] / 900.0
 

@@ -165,6 +165,12 @@ int qvm_ipc_close(qvm_t* q, void* peer_device_ptr);
  * stream.  `peer_amps` may also be another shard on the same device (tests). */
 int qvm_exchange_half(qvm_t* q, int local_bit, int mine_value, void* peer_amps, uint64_t elem_offset,
                       uint64_t count);
+/* m victim bits at once (m global qubits swapped with m local ones in a single pass): my sub-block
+ * "victim bits == mine_value" trades places with the peer's sub-block "victim bits == peer_value"
+ * (bit i of the values belongs to local_bits[i], ascending).  A rank calls it once per peer of its
+ * 2^m-rank subgroup with mine_value = the peer's global bits and peer_value = its own. */
+int qvm_exchange_block(qvm_t* q, int m, const int32_t* local_bits, uint32_t mine_value, uint32_t peer_value,
+                       void* peer_amps, uint64_t elem_offset, uint64_t count);
 
 #ifdef __cplusplus
 }

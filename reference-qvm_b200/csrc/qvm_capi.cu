@@ -993,21 +993,39 @@ int qvm_ipc_close(qvm_t* q, void* peer_ptr) {
     return QVM_OK;
 }
 
-int qvm_exchange_half(qvm_t* q, int local_bit, int mine_value, void* peer_amps, uint64_t elem_offset, uint64_t count) {
+int qvm_exchange_block(qvm_t* q, int m, const int32_t* local_bits, uint32_t mine_value, uint32_t peer_value,
+                       void* peer_amps, uint64_t elem_offset, uint64_t count) {
     QVM_CHECK_HANDLE(q);
-    if (local_bit < 0 || local_bit >= q->n_local || (mine_value | 1) != 1) return fail(QVM_ERR_INVALID, "bad bit");
+    if (m < 1 || m > 8 || m > q->n_local || !local_bits) return fail(QVM_ERR_INVALID, "bad victim bit count %d", m);
     if (!peer_amps) return fail(QVM_ERR_INVALID, "null peer pointer");
-    const uint64_t half = q->n_elems >> 1;
-    if (elem_offset > half || count > half - elem_offset) return fail(QVM_ERR_INVALID, "range outside the half-shard");
+    if ((mine_value >> m) || (peer_value >> m) || mine_value == peer_value)
+        return fail(QVM_ERR_INVALID, "sub-block selectors must be distinct %d-bit values", m);
+    ExchangeBits b{};
+    b.m = m;
+    for (int i = 0; i < m; ++i) {
+        const int p = local_bits[i];
+        if (p < 0 || p >= q->n_local || (i && p <= local_bits[i - 1]))
+            return fail(QVM_ERR_INVALID, "victim bits must be ascending local positions");
+        b.pos[i] = (uint8_t)p;
+        b.mine_bits |= (uint64_t)((mine_value >> i) & 1u) << p;
+        b.peer_bits |= (uint64_t)((peer_value >> i) & 1u) << p;
+    }
+    const uint64_t block = q->n_elems >> m;
+    if (elem_offset > block || count > block - elem_offset) return fail(QVM_ERR_INVALID, "range outside the sub-block");
     if (!count) return QVM_OK;
     const int grid = grid_for(q, (count + kExchangeUnroll - 1) / kExchangeUnroll, 256, 8);
-    exchange_half_kernel<<<grid, 256, 0, q->stream>>>(q->amps, static_cast<double2*>(peer_amps), local_bit, mine_value,
-                                                      elem_offset, count);
+    exchange_block_kernel<<<grid, 256, 0, q->stream>>>(q->amps, static_cast<double2*>(peer_amps), b, elem_offset, count);
     QVM_CUDA(q, cudaGetLastError());
     q->sample_mode = -1;
     q->stats.kernel_launches += 1;
     q->stats.hbm_bytes += 32ull * count;
     return QVM_OK;
+}
+
+int qvm_exchange_half(qvm_t* q, int local_bit, int mine_value, void* peer_amps, uint64_t elem_offset, uint64_t count) {
+    if ((mine_value | 1) != 1) return fail(QVM_ERR_INVALID, "bad bit");
+    const int32_t bit = local_bit;
+    return qvm_exchange_block(q, 1, &bit, (uint32_t)mine_value, (uint32_t)(1 - mine_value), peer_amps, elem_offset, count);
 }
 
 }  // extern "C"

@@ -563,41 +563,47 @@ __global__ void unpack_half_kernel(double2* __restrict__ state, int local_bit, i
         state[insert_zero64(off + j, local_bit) | vbit] = src[j];
 }
 
-// Global<->local qubit swap as ONE kernel over peer memory (NVLink P2P): element j of my moving
-// half (local bit == mine_value) trades places with element j of the peer's moving half (local bit
-// == 1 - mine_value).  Each rank of a pair runs this on its own half of the j range, so every link
-// direction carries reads issued by one side and writes issued by the other.  No staging buffers:
-// HBM sees one read + one write per moved amplitude on each side.
+// Global<->local qubit swap as ONE kernel over peer memory (NVLink P2P).  Swapping m global bits
+// with m local bits sends amplitude (rank R, local victim bits L) to (rank L, bits R): rank R trades
+// its sub-block L = P with peer P's sub-block L = R, for each of the 2^m - 1 peers P.  Element j of my
+// sub-block (victim bits == peer_value) trades places with element j of the peer's sub-block (victim
+// bits == mine_value).  The two ranks of a pair run this on disjoint halves of the j range, so every
+// link direction carries reads issued by one side and writes issued by the other.  No staging
+// buffers: HBM sees one read + one write per moved amplitude on each side.
+struct ExchangeBits {
+    int m;                  // victim bits
+    uint8_t pos[8];         // their local positions, ascending
+    uint64_t mine_bits;     // the victim bits set to the value selecting MY moving sub-block
+    uint64_t peer_bits;     // ... and the PEER's moving sub-block
+};
 constexpr int kExchangeUnroll = 4;
-__global__ void __launch_bounds__(256) exchange_half_kernel(double2* __restrict__ mine, double2* __restrict__ peer,
-                                                            int local_bit, int mine_value, uint64_t off,
-                                                            uint64_t count) {
-    const uint64_t mbit = (uint64_t)mine_value << local_bit, pbit = (uint64_t)(1 - mine_value) << local_bit;
+__device__ __forceinline__ uint64_t exchange_expand(uint64_t j, const ExchangeBits& b) {
+    for (int i = 0; i < b.m; ++i) j = insert_zero64(j, b.pos[i]);
+    return j;
+}
+__global__ void __launch_bounds__(256) exchange_block_kernel(double2* __restrict__ mine, double2* __restrict__ peer,
+                                                             const ExchangeBits b, uint64_t off, uint64_t count) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     for (; j + (kExchangeUnroll - 1) * stride < count; j += kExchangeUnroll * stride) {
         double2 x[kExchangeUnroll], y[kExchangeUnroll];
-        uint64_t im[kExchangeUnroll], ip[kExchangeUnroll];
+        uint64_t e[kExchangeUnroll];
 #pragma unroll
-        for (int u = 0; u < kExchangeUnroll; ++u) {
-            const uint64_t e = insert_zero64(off + j + u * stride, local_bit);
-            im[u] = e | mbit;
-            ip[u] = e | pbit;
-        }
+        for (int u = 0; u < kExchangeUnroll; ++u) e[u] = exchange_expand(off + j + u * stride, b);
 #pragma unroll
-        for (int u = 0; u < kExchangeUnroll; ++u) y[u] = __ldcs(&peer[ip[u]]);
+        for (int u = 0; u < kExchangeUnroll; ++u) y[u] = __ldcs(&peer[e[u] | b.peer_bits]);
 #pragma unroll
-        for (int u = 0; u < kExchangeUnroll; ++u) x[u] = __ldcs(&mine[im[u]]);
+        for (int u = 0; u < kExchangeUnroll; ++u) x[u] = __ldcs(&mine[e[u] | b.mine_bits]);
 #pragma unroll
-        for (int u = 0; u < kExchangeUnroll; ++u) __stcs(&mine[im[u]], y[u]);
+        for (int u = 0; u < kExchangeUnroll; ++u) __stcs(&mine[e[u] | b.mine_bits], y[u]);
 #pragma unroll
-        for (int u = 0; u < kExchangeUnroll; ++u) __stcs(&peer[ip[u]], x[u]);
+        for (int u = 0; u < kExchangeUnroll; ++u) __stcs(&peer[e[u] | b.peer_bits], x[u]);
     }
     for (; j < count; j += stride) {
-        const uint64_t e = insert_zero64(off + j, local_bit);
-        const double2 y = peer[e | pbit], x = mine[e | mbit];
-        mine[e | mbit] = y;
-        peer[e | pbit] = x;
+        const uint64_t e = exchange_expand(off + j, b);
+        const double2 y = peer[e | b.peer_bits], x = mine[e | b.mine_bits];
+        mine[e | b.mine_bits] = y;
+        peer[e | b.peer_bits] = x;
     }
 }
 

@@ -12,8 +12,8 @@ import numpy as np
 from referenceqvm import _native as nat
 from referenceqvm import _planner
 
-_TILE_BITS = int(os.environ.get("QVM_B200_TILE_BITS", "12"))
-_LOW_BITS = int(os.environ.get("QVM_B200_LOW_BITS", "5"))
+_TILE_BITS = int(os.environ.get("QVM_B200_TILE_BITS", "11"))     # 11 / 4: best gate-apps/s in the round-1 A/B (profiles/)
+_LOW_BITS = int(os.environ.get("QVM_B200_LOW_BITS", "4"))
 
 _classify_cache = {}
 

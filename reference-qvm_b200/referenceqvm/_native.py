@@ -81,6 +81,7 @@ _SIGNATURES = {
     "qvm_ipc_open": (C.c_int, [_P, _P, C.POINTER(_P)]),
     "qvm_ipc_close": (C.c_int, [_P, _P]),
     "qvm_exchange_half": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_uint64, C.c_uint64]),
+    "qvm_exchange_block": (C.c_int, [_P, C.c_int, _P, C.c_uint32, C.c_uint32, _P, C.c_uint64, C.c_uint64]),
 }
 EXPORTED = tuple(sorted(_SIGNATURES))
 
@@ -389,6 +390,11 @@ class DeviceState(object):
 
     def exchange_half(self, local_bit, mine_value, peer_ptr, elem_offset, count):
         check(lib().qvm_exchange_half(self.handle, local_bit, mine_value, _P(peer_ptr), elem_offset, count))
+
+    def exchange_block(self, local_bits, mine_value, peer_value, peer_ptr, elem_offset, count):
+        bits = np.ascontiguousarray(local_bits, dtype=np.int32)
+        check(lib().qvm_exchange_block(self.handle, bits.size, bits.ctypes.data, mine_value, peer_value,
+                                       _P(peer_ptr), elem_offset, count))
 
     def unpack_half(self, local_bit, bit_value, elem_offset, count, device_src_ptr):
         check(lib().qvm_unpack_half(self.handle, local_bit, bit_value, elem_offset, count, _P(device_src_ptr)))

@@ -118,6 +118,9 @@ class CudaShard(object):
     def exchange_half(self, bit, mine_value, partner, off, cnt):
         self.state.exchange_half(bit, mine_value, self.peers[partner], off, cnt)
 
+    def exchange_block(self, local_bits, mine_value, peer_value, partner, off, cnt):
+        self.state.exchange_block(local_bits, mine_value, peer_value, self.peers[partner], off, cnt)
+
     def pack_half(self, bit, value, off, cnt, buf):
         self.state.pack_half(bit, value, off, cnt, buf.data_ptr())
 
@@ -290,26 +293,93 @@ class ShardedEngine(object):
         return nxt
 
     def flush(self):
+        """Run every queued gate.  Ops whose dense targets are all local run in fused batches; an op
+        with a dense target on a global position blocks (with everything that depends on it) until an
+        exchange epoch brings all currently wanted global qubits in -- one multi-bit swap per epoch
+        instead of one swap (and one broken batch) per gate."""
         if not self.pending:
             return
         ops, self.pending = self.pending, []
-        batch = []              # physical-coordinate ops whose dense targets are all local
-        i = 0
-        while i < len(ops):
-            op = ops[i]
-            need = [t for t in op.targets if self.pos_of[t] >= self.n_local] if op.kind == nat.OP_DENSE else []
-            if need:
-                self._run_batch(batch)
-                batch = []
-                nxt = self._next_dense_use(ops, i)
-                busy = set(op.targets)
-                for q in need:
-                    victim = self._pick_victim(nxt, busy, len(ops))
-                    self._swap_global_local(q, victim)
-                    busy.add(victim)
-            batch.append(op.remapped(self.pos_of))
-            i += 1
-        self._run_batch(batch)
+        deps = _planner.dependencies(ops)
+        n = len(ops)
+        done = [False] * n
+        remaining = n
+        while remaining:
+            batch, in_batch, wanted = [], set(), []
+            for i in range(n):
+                if done[i]:
+                    continue
+                if any(not (done[d] or d in in_batch) for d in deps[i]):
+                    continue
+                op = ops[i]
+                if op.kind == nat.OP_DENSE:
+                    need = [t for t in op.targets if self.pos_of[t] >= self.n_local]
+                    if need:
+                        wanted.extend(t for t in need if t not in wanted)
+                        continue
+                batch.append(i)
+                in_batch.add(i)
+            self._run_batch([ops[i].remapped(self.pos_of) for i in batch])
+            for i in batch:
+                done[i] = True
+            remaining -= len(batch)
+            if remaining:
+                if not wanted:
+                    raise RuntimeError("sharded scheduler made no progress")
+                self._bring_local(wanted, ops, done)
+
+    def _bring_local(self, wanted, ops, done):
+        """Swap the logical qubits in ``wanted`` (all on global positions) with local victims: the
+        local qubits whose next dense use lies farthest ahead (Belady), lowest positions kept."""
+        nxt = {}
+        for i in range(len(ops) - 1, -1, -1):
+            if not done[i] and ops[i].kind == nat.OP_DENSE:
+                for t in ops[i].targets:
+                    nxt[t] = i
+        busy = set(wanted)
+        for i, op in enumerate(ops):          # targets that must stay local next to the wanted ones
+            if not done[i] and op.kind == nat.OP_DENSE and any(t in busy for t in op.targets):
+                busy.update(op.targets)
+        victims = []
+        for q in wanted:
+            v = self._pick_victim(nxt, busy, len(ops))
+            victims.append(v)
+            busy.add(v)
+        if self.p2p and len(wanted) > 1:
+            self._swap_many(wanted, victims)
+        else:
+            for q, v in zip(wanted, victims):
+                self._swap_global_local(q, v)
+
+    def _swap_many(self, globals_, victims):
+        """One exchange for m (global qubit, local victim) pairs: with every peer P of my 2^m-rank
+        subgroup I trade my sub-block "victim bits == P's global bits" for P's sub-block "victim bits
+        == my global bits" -- (2^m - 1) / 2^m of the shard moves, once."""
+        m = len(globals_)
+        pairs = sorted(zip(victims, globals_), key=lambda vg: self.pos_of[vg[0]])       # victim positions ascending
+        vpos = [self.pos_of[v] for v, _ in pairs]
+        gbit = [self.pos_of[g] - self.n_local for _, g in pairs]
+        rank = self.ctx.rank
+        mine = sum(((rank >> gb) & 1) << i for i, gb in enumerate(gbit))
+        base_rank = rank
+        for gb in gbit:
+            base_rank &= ~(1 << gb)
+        block = 1 << (self.n_local - m)
+        e0 = self.shard.record_event() if self.timing is not None else None
+        self.dist.all_reduce(self._token, group=self.ctx.group)
+        for value in range(1 << m):
+            if value == mine:
+                continue
+            peer = base_rank | sum(((value >> i) & 1) << gb for i, gb in enumerate(gbit))
+            lo, cnt = (0, block // 2) if rank < peer else (block // 2, block - block // 2)
+            self.shard.exchange_block(vpos, value, mine, peer, lo, cnt)
+        self.dist.all_reduce(self._token, group=self.ctx.group)
+        for v, g in pairs:
+            self.pos_of[g], self.pos_of[v] = self.pos_of[v], self.pos_of[g]
+        self.swaps += 1
+        self.swap_bytes += 16 * block * ((1 << m) - 1)
+        if e0 is not None:
+            self.timing["swap"].append((e0, self.shard.record_event()))
 
     def _run_batch(self, batch):
         if batch:

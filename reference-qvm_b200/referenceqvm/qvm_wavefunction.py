@@ -34,6 +34,12 @@ from referenceqvm.unitary_generator import lifted_gate, resolve_gate, tensor_gat
 LAZY_QUBITS = int(os.environ.get("QVM_B200_LAZY_QUBITS", "30"))
 
 
+def _index_bits(indices):
+    """(trials, 64) uint8 matrix of the little-endian bits of sampled basis-state indices."""
+    by = np.ascontiguousarray(indices, dtype="<u8").view(np.uint8).reshape(-1, 8)
+    return np.unpackbits(by, axis=1, bitorder="little")
+
+
 class QVM_Wavefunction(QAM):
     """Supports run(), run_and_measure() and wavefunction()."""
 
@@ -184,9 +190,10 @@ class QVM_Wavefunction(QAM):
             self.transition(self.current_instruction())
         indices, _ = self._engine.sample(np.random.random_sample(trials))
         memory = np.repeat(self.classical_memory[None, :], trials, axis=0)
+        bits = _index_bits(indices)
         for instr in list(pyquil_program)[split:]:
             q, c = value_get(instr.qubit), value_get(instr.classical_reg)
-            memory[:, c] = (indices >> np.uint64(q)) & np.uint64(1)
+            memory[:, c] = bits[:, q]
         self.program_counter = len(self.program)
         self.classical_memory = memory[-1].copy()
         picked = memory if mask is None else memory[:, mask]
@@ -207,13 +214,10 @@ class QVM_Wavefunction(QAM):
         if self.sampling_fast_path and deterministic and trials > 1 and len(qubits) > 0:
             self._simulate(pyquil_program, None)
             indices, _ = self._engine.sample(np.random.random_sample(trials))
-            cols = []
-            for q in qubits:
-                if q < self.num_qubits:
-                    cols.append(((indices >> np.uint64(q)) & np.uint64(1)).astype(np.int64))
-                else:
-                    cols.append(np.zeros(trials, dtype=np.int64))
-            return np.stack(cols, axis=1).tolist()
+            bits = _index_bits(indices)
+            # bit 63 is never set (q_limit = 51): it stands in for qubits beyond the register
+            sel = [q if 0 <= q < self.num_qubits else 63 for q in qubits]
+            return bits[:, sel].tolist()
 
         results = []
         for _ in range(trials):

@@ -56,11 +56,27 @@ def main():
         eng.pos_of[qg], eng.pos_of[ql] = pl, pg
         eng.swaps += 1
     eng._swap_global_local = fake_swap
+    eng.p2p = True
+    moved = [0.0]
+
+    def fake_many(gl, vi):
+        for g, v in zip(gl, vi):
+            eng.pos_of[g], eng.pos_of[v] = eng.pos_of[v], eng.pos_of[g]
+        eng.swaps += 1
+        moved[0] += 1.0 - 0.5 ** len(gl)
+    eng._swap_many = fake_many
+    real_fake = fake_swap
+
+    def fake_swap2(qg, ql):
+        real_fake(qg, ql)
+        moved[0] += 0.5
+    eng._swap_global_local = fake_swap2
     t0 = time.time()
     for op in ops:
         eng.queue(op)
     eng.flush()
-    print("world", world, "groups", eng.groups_launched, "swaps", eng.swaps, "ops", len(ops), "plan s", time.time() - t0)
+    print("world", world, "groups", eng.groups_launched, "exchanges", eng.swaps, "shards moved per GPU %.2f" % moved[0],
+          "ops", len(ops), "plan s %.3f" % (time.time() - t0))
 
 
 if __name__ == "__main__":

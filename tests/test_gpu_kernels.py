@@ -355,3 +355,32 @@ def test_exchange_half_between_two_shards_on_one_device():
         want_a[one] = b[~one]
         want_b[~one] = a[one]
         assert np.array_equal(ga, want_a) and np.array_equal(gb, want_b), bit
+
+
+def test_exchange_block_two_global_bits_on_one_device():
+    """qvm_exchange_block with m = 2: four shards on one GPU play the four ranks of a subgroup.  After
+    every rank traded sub-blocks with its three peers, global bits (g0, g1) and the victim local bits
+    have swapped places in the full state."""
+    n_local, m = 12, 2
+    for vpos in ([3, 9], [0, 11], [5, 6]):
+        full = random_state(n_local + m, 5)
+        shards = [fresh(n_local, full[r << n_local:(r + 1) << n_local]) for r in range(4)]
+        block = 1 << (n_local - m)
+        for r in range(4):
+            for p in range(4):
+                if p == r:
+                    continue
+                lo, cnt = (0, block // 2) if r < p else (block // 2, block - block // 2)
+                shards[r].exchange_block(vpos, p, r, shards[p].device_ptr(), lo, cnt)
+            shards[r].sync()
+        got = np.concatenate([s.get_state() for s in shards])
+        for s in shards:
+            s.close()
+        idx = np.arange(1 << (n_local + m))
+        # new index: global bit i <-> local bit vpos[i]
+        src = idx.copy()
+        for i, lp in enumerate(vpos):
+            gp = n_local + i
+            lb, gb = (idx >> lp) & 1, (idx >> gp) & 1
+            src = src & ~((1 << lp) | (1 << gp)) | (gb << lp) | (lb << gp)
+        assert np.array_equal(got, full[src]), vpos
