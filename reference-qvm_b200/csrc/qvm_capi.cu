@@ -424,13 +424,9 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
     P.hi_off = reinterpret_cast<const uint64_t*>(dp + rounds_bytes + hot_bytes + cold_bytes);
     P.mats = reinterpret_cast<const double2*>(dp + rounds_bytes + hot_bytes + cold_bytes + hi_bytes);
 
-    static const int occ5 = getenv("QVM_B200_OCC5") ? atoi(getenv("QVM_B200_OCC5")) : 0;
     if (g.threads > 256) {
         rc = g.need_full ? launch_regtile<512, 1, true>(q, (unsigned)g.n_tiles, g.threads, g.smem, P)
                          : launch_regtile<512, 1, false>(q, (unsigned)g.n_tiles, g.threads, g.smem, P);
-    } else if (g.threads <= 128 && occ5 && !g.need_full) {
-        // experiment: cap registers at 102 so that five 128-thread CTAs (20 warps) fit on an SM
-        rc = launch_regtile<128, 5, false>(q, (unsigned)g.n_tiles, g.threads, g.smem, P);
     } else {
         rc = g.need_full ? launch_regtile<256, 2, true>(q, (unsigned)g.n_tiles, g.threads, g.smem, P)
                          : launch_regtile<256, 2, false>(q, (unsigned)g.n_tiles, g.threads, g.smem, P);

@@ -55,6 +55,7 @@ struct EncodedGroup {
     int n_gate_ops = 0;                      // ops of the group that were encoded (NOPs excluded)
     uint32_t opc_hist[32] = {};
     int n_layers = 0;                        // LAYER dispatches emitted (several single-slot ops each)
+    int n_dirty_rounds = 0;                  // rounds that apply a thread scalar (16 multiplies per thread)
 };
 
 enum { ENC_OK = 0, ENC_FALLBACK = 1, ENC_ERROR = 2 };
@@ -250,6 +251,7 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
     {
         const int n_rounds = (int)rounds.size();
         std::vector<uint32_t> regmask(n_rounds);
+        std::vector<int> ts_ops(n_rounds, 0);     // thread-scalar ops already placed in each round
         for (int r = 0; r < n_rounds; ++r) regmask[r] = rounds[r].regmask();
         for (int i = 0; i < n; ++i) {
             if (lops[i].kind == QVM_OP_DENSE) continue;
@@ -259,14 +261,20 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
             for (int j : dense_idx)
                 if (j > i && (lops[j].dense_mask & touched)) hi = std::min(hi, round_of[j]);
             if (hi < lo) hi = lo;      // cannot happen: a later conflicting dense op waits for this op
-            int best = lo, best_cost = 99;
-            for (int r = hi; r >= lo; --r) {       // prefer late rounds on ties: keeps early rounds lean
+            // fewest register bits touched first; among those, a round that already applies a thread
+            // scalar (each such round costs 16 complex multiplies per thread once, however many ops
+            // share it); then the latest round
+            int best = lo, best_cost = 99, best_dirty = -1;
+            for (int r = hi; r >= lo; --r) {
                 const int cost = __builtin_popcount(touched & regmask[r]);
-                if (cost < best_cost) {
+                const int dirty = cost == 0 ? ts_ops[r] : 0;
+                if (cost < best_cost || (cost == best_cost && dirty > best_dirty)) {
                     best_cost = cost;
+                    best_dirty = dirty;
                     best = r;
                 }
             }
+            if (best_cost == 0) ++ts_ops[best];
             round_of[i] = best;
         }
         for (int i = 0; i < n; ++i) rounds[round_of[i]].ops.push_back(i);     // ascending original index
@@ -299,7 +307,10 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
             sorted[s] = rd.slot_bit[s];
         }
         std::sort(sorted, sorted + 4);
-        for (int s = 0; s < 4; ++s) d.reg_sorted[s] = (uint8_t)sorted[s];
+        for (int s = 0; s < 4; ++s) {
+            d.reg_sorted[s] = (uint8_t)sorted[s];
+            d.ins_mask[s] = (uint16_t)~((1u << sorted[s]) - 1u);
+        }
         int nt = 0;
         for (int b = 0; b < n_tile; ++b)
             if (slot_of[b] < 0) thr_of[b] = (int8_t)nt++;
@@ -421,6 +432,7 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
                     c.prefetch = 1;
                     if (nthr == 1) {
                         opc = OPC_DST;
+                        out.need_full = true;
                         c.fsel = (uint8_t)s0;
                         flags |= HDR_HAS_F1;
                     }
@@ -446,6 +458,7 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
                         c.prefetch = 1;
                     } else {
                         opc = OPC_D1_0 + reg_slot;
+                        out.need_full = true;
                         c.prefetch = 1;
                         c.fsel = (uint8_t)shr;
                         flags |= HDR_HAS_F1;
@@ -495,12 +508,22 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
             hot.push_back(make_uint4(0, 0x3FF00000u, 0, 0));      // f1 = 1.0  when the op prefetches)
             cold.push_back(e.c);
         };
-        for (size_t i = 0; i < n_ts; ++i) emit_plain(enc[i]);
+        {
+            unsigned n_tg = 0;
+            for (size_t i = 0; i < n_ts; ++i)
+                if ((enc[i].h.x & 0xFFu) == OPC_T) emit_plain(enc[i]);
+            for (size_t i = 0; i < n_ts; ++i)
+                if ((enc[i].h.x & 0xFFu) != OPC_T) {
+                    emit_plain(enc[i]);
+                    ++n_tg;
+                }
+            d.flags |= (uint16_t)(n_tg << 1);
+        }
         d.dt_end = (uint16_t)hot.size();
 
         struct Layer {
             uint32_t s1 = 0, h = 0, x = 0;
-            uint32_t cs[4] = {0, 0, 0, 0}, cx[4] = {0, 0, 0, 0};
+            uint32_t cs[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu}, cx[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};   // absent
             double f[4][2] = {{1, 0}, {1, 0}, {1, 0}, {1, 0}};
             int stage[4] = {0, 0, 0, 0};
             int count = 0;
@@ -607,6 +630,9 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
         d.scale = make_double2(gs_re, gs_im);
         d.flags |= 1u;
     }
+    out.n_dirty_rounds = 0;
+    for (const RoundDesc& rd : out.rounds)
+        if (rd.dt_end > rd.op_begin || (rd.flags & 1u)) ++out.n_dirty_rounds;
     if (hot.size() > 0xFFFFu) return ENC_FALLBACK;
 
     // launch parameters that replace per-thread bit loops

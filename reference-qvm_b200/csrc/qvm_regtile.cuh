@@ -117,8 +117,8 @@ struct __align__(16) RoundDesc {
     uint16_t swz_j[4];        // swz(1 << tile-local bit of slot s): shared-memory stride of slot s
     double2 scale;            // complex scalar applied in this round (folded H scales, RZ phases)
     uint16_t op_begin, dt_end, op_end;   // WORD offsets: [op_begin, dt_end) thread-scalar batch; [dt_end, op_end) slot ops
-    uint16_t flags;           // bit 0: scale != 1
-    uint8_t pad[8];
+    uint16_t flags;           // bit 0: scale != 1; bits 15..1: number of OPC_TG ops at the end of the batch
+    uint16_t ins_mask[4];     // ~((1 << reg_sorted[i]) - 1): x + (x & mask) inserts a zero bit at that position
 };
 static_assert(sizeof(RoundDesc) == 48, "RoundDesc layout");
 
@@ -298,6 +298,12 @@ QVM_HD void reg_h(double2 (&a)[16], const uint32_t xm) {
     else reg_h_half<B, 0>(a);
 }
 
+#if defined(__CUDA_ARCH__)
+#define QVM_NO_IFCVT() ((void)0)
+#else
+#define QVM_NO_IFCVT() ((void)0)
+#endif
+
 template <int B>
 QVM_HD void reg_xswap(double2 (&a)[16], const uint32_t crm, const uint32_t xm) {
     const uint32_t want = crm & ~xm;
@@ -305,7 +311,8 @@ QVM_HD void reg_xswap(double2 (&a)[16], const uint32_t crm, const uint32_t xm) {
     for (int p = 0; p < 8; ++p) {
         const int i0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1));
         const int i1 = i0 | (1 << B);
-        if ((i0 & crm) == want) {
+        if ((i0 & crm) == want) {        // warp-uniform: a real branch beats 12 selects per pair
+            QVM_NO_IFCVT();
             const double2 x0 = a[i0];
             a[i0] = a[i1];
             a[i1] = x0;
@@ -337,7 +344,10 @@ QVM_HD void reg_d1(double2 (&a)[16], double2 d0, double2 d1, const uint32_t crm,
     const uint32_t want = crm & ~xm;
 #pragma unroll
     for (int p = 0; p < 16; ++p)
-        if ((p & crm) == want) cmul_ip(a[p], ((p >> B) & 1) ? d1 : d0);
+        if ((p & crm) == want) {
+            QVM_NO_IFCVT();
+            cmul_ip(a[p], ((p >> B) & 1) ? d1 : d0);
+        }
 }
 
 template <int B>
@@ -399,24 +409,35 @@ QVM_HD void rt_thread_round(const RtCta& c, const int r, const uint32_t tid) {
     const bool first = r == 0, last = r == c.n_rounds - 1;
 
     // tile index of this thread: tid with zeros inserted at the (ascending) register-bit positions
+    const uint2 im = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(rd) + 40);
     uint32_t T = tid;
-    T = insert_zero32(T, rw.x & 0xFFu);
-    T = insert_zero32(T, (rw.x >> 8) & 0xFFu);
-    T = insert_zero32(T, (rw.x >> 16) & 0xFFu);
-    T = insert_zero32(T, rw.x >> 24);
+    T += T & (im.x & 0xFFFFu);
+    T += T & (im.x >> 16);
+    T += T & (im.y & 0xFFFFu);
+    T += T & (im.y >> 16);
     const uint32_t s0 = rw.z & 0xFFFFu, s1 = rw.z >> 16, s2 = rw.w & 0xFFFFu, s3 = rw.w >> 16;
     const uint32_t sT = swz(T);
     const uint32_t low_mask = (1u << c.low) - 1u;
 
     double2 a[16];
     if (first) {
+        // register-bit positions carry zeros in gT, so the 16 addresses are sums: an add tree on byte
+        // offsets (two instructions per address) instead of 64-bit OR + scale per element
         const uint64_t gT = (uint64_t)(T & low_mask) | c.hi_off[T >> c.low];
-        const uint64_t g0 = 1ull << (rw.y & 0xFFu), g1 = 1ull << ((rw.y >> 8) & 0xFFu),
-                       g2 = 1ull << ((rw.y >> 16) & 0xFFu), g3 = 1ull << (rw.y >> 24);
-        const double2* src = c.gbase + gT;
+        const char* p0 = reinterpret_cast<const char*>(c.gbase + gT);
+        const uint64_t b0 = 16ull << (rw.y & 0xFFu), b1 = 16ull << ((rw.y >> 8) & 0xFFu),
+                       b2 = 16ull << ((rw.y >> 16) & 0xFFu), b3 = 16ull << (rw.y >> 24);
+        const char* q[16];
+        q[0] = p0;
+        q[1] = p0 + b0;
+        q[2] = p0 + b1;
+        q[3] = q[1] + b1;
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            a[j] = src[((j & 1) ? g0 : 0) | ((j & 2) ? g1 : 0) | ((j & 4) ? g2 : 0) | ((j & 8) ? g3 : 0)];
+        for (int j = 0; j < 4; ++j) q[4 + j] = q[j] + b2;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q[8 + j] = q[j] + b3;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = *reinterpret_cast<const double2*>(q[j]);
     } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
@@ -430,20 +451,22 @@ QVM_HD void rt_thread_round(const RtCta& c, const int r, const uint32_t tid) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (const OpWord* op = &c.ops[op_begin]; op != &c.ops[dt_end]; op += kOpWords) {
-        const uint2 w = *reinterpret_cast<const uint2*>(op);
-        const uint32_t cthr = w.y & 0xFFFFu;
-        if ((tid & cthr) != cthr) continue;
-        double2 f;
-        if ((w.x & 0xFFu) == OPC_T) {
-            f = op[1 + ((tid >> ((w.x >> 16) & 0xFFu)) & 1u)].d;
-        } else {      // OPC_TG: two thread-bit targets, factors from the pool
-            const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(op) + 8);
-            const uint32_t idx = (v.y & 0xFFu) | (((tid >> ((w.x >> 16) & 0xFFu)) & 1u) << ((v.y >> 8) & 0xFFu)) |
-                                 (((tid >> (w.x >> 24)) & 1u) << ((v.y >> 16) & 0xFFu));
-            f = QVM_LDG(&c.mats[v.x + idx]);
-        }
-        cmul_ip(ts, f);
+    const uint32_t tg_begin = dt_end - kOpWords * (rr.y >> 17);          // the (rare) pool-indexed ops come last
+    for (const OpWord* op = &c.ops[op_begin]; op != &c.ops[tg_begin]; op += kOpWords) {
+        const uint2 w = *reinterpret_cast<const uint2*>(op);         // OPC_T: f0 / f1 by thread bit p0
+        if ((tid & w.y & 0xFFFFu) != (w.y & 0xFFFFu)) continue;
+        cmul_ip(ts, op[1 + ((tid >> ((w.x >> 16) & 0xFFu)) & 1u)].d);
+        ts_dirty = true;
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (const OpWord* op = &c.ops[tg_begin]; op != &c.ops[dt_end]; op += kOpWords) {
+        const uint4 w = op->u;                                       // OPC_TG: two thread-bit targets, pool factors
+        if ((tid & w.y & 0xFFFFu) != (w.y & 0xFFFFu)) continue;
+        const uint32_t idx = (w.w & 0xFFu) | (((tid >> ((w.x >> 16) & 0xFFu)) & 1u) << ((w.w >> 8) & 0xFFu)) |
+                             (((tid >> (w.x >> 24)) & 1u) << ((w.w >> 16) & 0xFFu));
+        cmul_ip(ts, QVM_LDG(&c.mats[w.z + idx]));
         ts_dirty = true;
     }
     if (ts_dirty) {          // scalars commute with everything: apply now, so ts is dead in the main loop
@@ -466,22 +489,24 @@ QVM_HD void rt_thread_round(const RtCta& c, const int r, const uint32_t tid) {
             hn = *reinterpret_cast<const uint2*>(op);             // prefetch (one spare word follows the last op)
             if (opc == OPC_LAYER) {
                 // per slot: [S1 factor] -> [H] -> [X relabel]; sub-ops on different slots commute
+                // word 1: thread-control masks of the S1 (x, y) and X (z, w) sub-ops, 16 bits per slot; an
+                // absent sub-op carries the impossible mask 0xFFFF.  (t & m) ^ m == 0  <=>  all controls set.
                 const uint4 m = cur[1].u;
-#define QVM_LAYER_SLOT(S, CS, CX)                                                        \
-                if (hx & (0x100u << S)) {                                                   \
-                    const uint32_t cm = (CS);                                               \
-                    if ((tid & cm) == cm) reg_s1<S>(a, cur[2 + S].d, xm);                   \
-                }                                                                           \
-                if (hx & (0x1000u << S)) reg_h<S>(a, xm);                                   \
-                if (hx & (0x10000u << S)) {                                                 \
-                    const uint32_t cm = (CX);                                               \
-                    if ((tid & cm) == cm) xm ^= 1u << S;                                    \
-                }
-                QVM_LAYER_SLOT(0, m.x & 0xFFFFu, m.z & 0xFFFFu)
-                QVM_LAYER_SLOT(1, m.x >> 16, m.z >> 16)
-                QVM_LAYER_SLOT(2, m.y & 0xFFFFu, m.w & 0xFFFFu)
-                QVM_LAYER_SLOT(3, m.y >> 16, m.w >> 16)
-#undef QVM_LAYER_SLOT
+                const uint32_t t2 = tid | (tid << 16);
+                const uint32_t s01 = (t2 & m.x) ^ m.x, s23 = (t2 & m.y) ^ m.y;
+                const uint32_t x01 = (t2 & m.z) ^ m.z, x23 = (t2 & m.w) ^ m.w;
+                if (!(s01 & 0xFFFFu)) reg_s1<0>(a, cur[2].d, xm);
+                if (hx & 0x1000u) reg_h<0>(a, xm);
+                if (!(x01 & 0xFFFFu)) xm ^= 1u;
+                if (!(s01 >> 16)) reg_s1<1>(a, cur[3].d, xm);
+                if (hx & 0x2000u) reg_h<1>(a, xm);
+                if (!(x01 >> 16)) xm ^= 2u;
+                if (!(s23 & 0xFFFFu)) reg_s1<2>(a, cur[4].d, xm);
+                if (hx & 0x4000u) reg_h<2>(a, xm);
+                if (!(x23 & 0xFFFFu)) xm ^= 4u;
+                if (!(s23 >> 16)) reg_s1<3>(a, cur[5].d, xm);
+                if (hx & 0x8000u) reg_h<3>(a, xm);
+                if (!(x23 >> 16)) xm ^= 8u;
                 continue;
             }
             if ((tid & cthr) != cthr) continue;   // a control on a thread bit is 0, or op inactive here
@@ -492,22 +517,36 @@ QVM_HD void rt_thread_round(const RtCta& c, const int r, const uint32_t tid) {
                 case OPC_XS_0 + 1: reg_xswap<1>(a, crm, xm); break;
                 case OPC_XS_0 + 2: reg_xswap<2>(a, crm, xm); break;
                 case OPC_XS_0 + 3: reg_xswap<3>(a, crm, xm); break;
-                case OPC_DST:
-                    f = cur[1 + ((tid >> p0) & 1u)].d;
-                    // fall through
                 case OPC_DS: {
                     const uint32_t want = crm & ~xm;
 #pragma unroll
                     for (int p = 0; p < 16; ++p)
-                        if ((p & crm) == want) cmul_ip(a[p], f);
+                        if ((p & crm) == want) {
+                            QVM_NO_IFCVT();
+                            cmul_ip(a[p], f);
+                        }
                     break;
                 }
-                case OPC_D1_0 + 0: reg_d1<0>(a, f, cur[2].d, crm, xm); break;
-                case OPC_D1_0 + 1: reg_d1<1>(a, f, cur[2].d, crm, xm); break;
-                case OPC_D1_0 + 2: reg_d1<2>(a, f, cur[2].d, crm, xm); break;
-                case OPC_D1_0 + 3: reg_d1<3>(a, f, cur[2].d, crm, xm); break;
                 default:
                     if (FULL) {
+                        // rare shapes live in the FULL variant only: the lean kernel stays small for the I-cache
+                        if (opc == OPC_DST) {
+                            f = cur[1 + ((tid >> p0) & 1u)].d;
+                            const uint32_t want = crm & ~xm;
+#pragma unroll
+                            for (int p = 0; p < 16; ++p)
+                                if ((p & crm) == want) cmul_ip(a[p], f);
+                            break;
+                        }
+                        if (opc >= OPC_D1_0 && opc < OPC_D1_0 + 4) {
+                            switch (opc - OPC_D1_0) {
+                                case 0: reg_d1<0>(a, f, cur[2].d, crm, xm); break;
+                                case 1: reg_d1<1>(a, f, cur[2].d, crm, xm); break;
+                                case 2: reg_d1<2>(a, f, cur[2].d, crm, xm); break;
+                                default: reg_d1<3>(a, f, cur[2].d, crm, xm); break;
+                            }
+                            break;
+                        }
                         const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(cur) + 8);
                         const double2* mat = c.mats + v.x;
                         if (opc == OPC_DIAG_G) {
@@ -554,15 +593,27 @@ QVM_HD void rt_thread_round(const RtCta& c, const int r, const uint32_t tid) {
     }
 
     if (last) {
-        const uint64_t g0 = 1ull << (rw.y & 0xFFu), g1 = 1ull << ((rw.y >> 8) & 0xFFu),
-                       g2 = 1ull << ((rw.y >> 16) & 0xFFu), g3 = 1ull << (rw.y >> 24);
-        // register p holds logical slot p ^ xm; the slot -> address map is XOR-linear
-        const uint64_t gT = ((uint64_t)(T & low_mask) | c.hi_off[T >> c.low]) ^
-                            (((xm & 1) ? g0 : 0) | ((xm & 2) ? g1 : 0) | ((xm & 4) ? g2 : 0) | ((xm & 8) ? g3 : 0));
-        double2* dst = c.gbase;
+        // register p holds logical slot p ^ xm: start from the address of logical slot xm and walk with
+        // signed strides (a set xm bit turns +stride into -stride); sums again, no per-element masking
+        const uint64_t gT = (uint64_t)(T & low_mask) | c.hi_off[T >> c.low];
+        char* p0 = reinterpret_cast<char*>(c.gbase + gT);
+        int64_t b0 = (int64_t)(16ull << (rw.y & 0xFFu)), b1 = (int64_t)(16ull << ((rw.y >> 8) & 0xFFu)),
+                b2 = (int64_t)(16ull << ((rw.y >> 16) & 0xFFu)), b3 = (int64_t)(16ull << (rw.y >> 24));
+        if (xm & 1u) { p0 += b0; b0 = -b0; }
+        if (xm & 2u) { p0 += b1; b1 = -b1; }
+        if (xm & 4u) { p0 += b2; b2 = -b2; }
+        if (xm & 8u) { p0 += b3; b3 = -b3; }
+        char* q[16];
+        q[0] = p0;
+        q[1] = p0 + b0;
+        q[2] = p0 + b1;
+        q[3] = q[1] + b1;
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            dst[gT ^ (((j & 1) ? g0 : 0) | ((j & 2) ? g1 : 0) | ((j & 4) ? g2 : 0) | ((j & 8) ? g3 : 0))] = a[j];
+        for (int j = 0; j < 4; ++j) q[4 + j] = q[j] + b2;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q[8 + j] = q[j] + b3;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) *reinterpret_cast<double2*>(q[j]) = a[j];
     } else {
         // same mapping as this round's load: every thread rewrites exactly the slots it read
         const uint32_t sX = sT ^ ((xm & 1) ? s0 : 0) ^ ((xm & 2) ? s1 : 0) ^ ((xm & 4) ? s2 : 0) ^ ((xm & 8) ? s3 : 0);

@@ -31,12 +31,14 @@ def main():
     groups = _planner.plan(ops, n, tile, 5)
     rounds = 0
     layers = 0
+    dirty = 0
     for g in groups:
         psi, info = _emu.apply_group(psi, n, g.tile, g.ops)
         hist += info["opc_hist"]
         rounds += info["rounds"]
         layers += info["layers"]
-    print("n=%d depth=%d tile=%d: %d gates, %d groups, %d rounds, %d layers" % (n, depth, tile, len(ops), len(groups), rounds, layers))
+        dirty += info["dirty_rounds"]
+    print("n=%d depth=%d tile=%d: %d gates, %d groups, %d rounds (%d with a thread scalar), %d layers" % (n, depth, tile, len(ops), len(groups), rounds, dirty, layers))
     agg = {}
     for opc in range(32):
         base = max(k for k in NAMES if k <= opc)

@@ -54,9 +54,9 @@ def apply_group(psi, n_local, tile_bits, ops, n_global=0, shard_index=0, force_f
         pool[off:off + o.mat.size] = o.mat
         off += o.mat.size
     tb = np.ascontiguousarray(sorted(tile_bits), dtype=np.int32)
-    info = np.zeros(37, dtype=np.int32)
+    info = np.zeros(38, dtype=np.int32)
     rc = lib().qvm_emu_apply_group(out.ctypes.data, n_local, n_global, shard_index, tb.size, tb.ctypes.data,
                                    len(ops), C.cast(arr, C.c_void_p), pool.ctypes.data, total,
                                    1 if force_full else 0, info.ctypes.data)
     return out, {"rounds": int(info[0]), "need_full": bool(info[1]), "status": rc, "n_ops": int(info[3]),
-                 "opc_hist": info[4:36].copy(), "layers": int(info[36])}
+                 "opc_hist": info[4:36].copy(), "layers": int(info[36]), "dirty_rounds": int(info[37])}

@@ -15,7 +15,7 @@ using namespace qvm;
 
 extern "C" int qvm_emu_apply_group(double* amps, int n_local, int n_global, uint64_t shard_index, int n_tile,
                                    const int32_t* tile_bits, int n_ops, const qvm_op_t* ops, const double* mats,
-                                   uint64_t mats_entries, int force_full, int* info /* 37 ints */) {
+                                   uint64_t mats_entries, int force_full, int* info /* 38 ints */) {
     EncodedGroup g;
     const int erc = encode_group(n_local, n_global, shard_index, n_tile, tile_bits, n_ops, ops, mats, mats_entries, g);
     if (info) {
@@ -25,6 +25,7 @@ extern "C" int qvm_emu_apply_group(double* amps, int n_local, int n_global, uint
         info[3] = (int)g.cold.size();
         for (int i = 0; i < 32; ++i) info[4 + i] = (int)g.opc_hist[i];
         info[36] = g.n_layers;
+        info[37] = g.n_dirty_rounds;
     }
     if (erc != ENC_OK) return erc;
     if (g.cold.empty()) return 0;
