@@ -424,12 +424,14 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
     P.hi_off = reinterpret_cast<const uint64_t*>(dp + rounds_bytes + hot_bytes + cold_bytes);
     P.mats = reinterpret_cast<const double2*>(dp + rounds_bytes + hot_bytes + cold_bytes + hi_bytes);
 
+    // (capping registers to fit 5 or 6 CTAs of 128 threads per SM was measured slower: profiles/README.md)
+    const unsigned grid = (unsigned)g.n_tiles;
     if (g.threads > 256) {
-        rc = g.need_full ? launch_regtile<512, 1, true>(q, (unsigned)g.n_tiles, g.threads, g.smem, P)
-                         : launch_regtile<512, 1, false>(q, (unsigned)g.n_tiles, g.threads, g.smem, P);
+        rc = g.need_full ? launch_regtile<512, 1, true>(q, grid, g.threads, g.smem, P)
+                         : launch_regtile<512, 1, false>(q, grid, g.threads, g.smem, P);
     } else {
-        rc = g.need_full ? launch_regtile<256, 2, true>(q, (unsigned)g.n_tiles, g.threads, g.smem, P)
-                         : launch_regtile<256, 2, false>(q, (unsigned)g.n_tiles, g.threads, g.smem, P);
+        rc = g.need_full ? launch_regtile<256, 2, true>(q, grid, g.threads, g.smem, P)
+                         : launch_regtile<256, 2, false>(q, grid, g.threads, g.smem, P);
     }
     if (rc) return rc;
     q->stats.kernel_launches += 1;

@@ -504,8 +504,29 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
             e.c.word_off = (uint32_t)hot.size();
             if ((e.h.x & 0xFFu) == OPC_DIAG_G) e.h.w = (uint32_t)cold.size() << 8;      // its cold index
             hot.push_back(e.h);
-            hot.push_back(make_uint4(0, 0x3FF00000u, 0, 0));      // f0 = 1.0 (the prologue overwrites it
-            hot.push_back(make_uint4(0, 0x3FF00000u, 0, 0));      // f1 = 1.0  when the op prefetches)
+            double f[2][2] = {{1.0, 0.0}, {1.0, 0.0}};
+            if (e.c.prefetch) {
+                bool outer_dep = false;
+                for (int t = 0; t < e.c.k; ++t)
+                    if ((e.c.loc[t] & LOC_CLASS) == LOC_OUT) outer_dep = true;
+                if (!outer_dep) {           // factors known here: the prologue just copies them
+                    const size_t m0 = (size_t)e.c.mat_off;
+                    f[0][0] = pool[2 * m0];
+                    f[0][1] = pool[2 * m0 + 1];
+                    if (e.c.fsel != 0xFF) {
+                        const size_t m1 = m0 + ((size_t)1 << e.c.fsel);
+                        f[1][0] = pool[2 * m1];
+                        f[1][1] = pool[2 * m1 + 1];
+                    }
+                    e.c.prefetch = 0;
+                }
+            }
+            for (int i = 0; i < 2; ++i) {
+                uint4 w;
+                memcpy(&w.x, &f[i][0], 8);
+                memcpy(&w.z, &f[i][1], 8);
+                hot.push_back(w);
+            }
             cold.push_back(e.c);
         };
         {
@@ -663,6 +684,12 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
         out.hi_off[j] = off;
     }
     P.n_rounds = (int)out.rounds.size();
+    {
+        const RoundDesc& r0 = out.rounds[0];
+        P.first_reg_phys = r0.reg_phys[0] | (r0.reg_phys[1] << 8) | (r0.reg_phys[2] << 16) | ((uint32_t)r0.reg_phys[3] << 24);
+        P.first_ins[0] = r0.ins_mask[0] | ((uint32_t)r0.ins_mask[1] << 16);
+        P.first_ins[1] = r0.ins_mask[2] | ((uint32_t)r0.ins_mask[3] << 16);
+    }
     P.n_ops = (int)cold.size();
     P.n_patches = (int)patches.size();
     cold.insert(cold.end(), patches.begin(), patches.end());

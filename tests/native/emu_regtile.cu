@@ -55,10 +55,19 @@ extern "C" int qvm_emu_apply_group(double* amps, int n_local, int n_global, uint
         c.cold = P.cold;
         c.low = P.low;
         c.n_rounds = P.n_rounds;
+        // round 0's amplitudes are loaded at kernel entry on the device; per thread here
+        std::vector<double2> pre((size_t)g.threads * 16);
+        for (uint32_t tid = 0; tid < g.threads; ++tid) {
+            double2 a[16];
+            rt_first_load(P, state + base, tid, a);
+            memcpy(&pre[(size_t)tid * 16], a, sizeof(a));
+        }
         for (int r = 0; r < P.n_rounds; ++r)
             for (uint32_t tid = 0; tid < g.threads; ++tid) {
-                if (full_variant) rt_thread_round<true>(c, r, tid);
-                else rt_thread_round<false>(c, r, tid);
+                double2 a[16];
+                if (r == 0) memcpy(a, &pre[(size_t)tid * 16], sizeof(a));
+                if (full_variant) rt_thread_round<true>(c, r, tid, a);
+                else rt_thread_round<false>(c, r, tid, a);
             }
     }
     return 0;
