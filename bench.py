@@ -336,8 +336,10 @@ def main():
         "config": {"workload": workload_name(args), "qubits": n, "depth": depth, "gates_per_step": n_gates,
                    "l2_policy": "state (%.1f GiB) is far larger than the 126 MB L2" % (16.0 * 2 ** n / 2 ** 30),
                    "tile_bits": eng.tile_bits, "low_bits": eng.low_bits,
-                   "sharding": ("top %d qubits select the GPU; %d global<->local swaps per step over NCCL send/recv"
-                                % (world.bit_length() - 1, swaps // max(args.steps, 1))) if sharded else "single shard"},
+                   "sharding": ("top %d qubits select the GPU; %d global<->local exchanges per step (%s)"
+                                % (world.bit_length() - 1, swaps // max(args.steps, 1),
+                                   "peer-memory kernel over NVLink" if getattr(eng, "p2p", False) else "staged NCCL send/recv"))
+                   if sharded else "single shard"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": stats["kernel_launches"], "clocks": clocks,
     }

@@ -367,9 +367,10 @@ class ShardedEngine(object):
         block = 1 << (self.n_local - m)
         e0 = self.shard.record_event() if self.timing is not None else None
         self.dist.all_reduce(self._token, group=self.ctx.group)
-        for value in range(1 << m):
-            if value == mine:
-                continue
+        for step in range(1, 1 << m):
+            # XOR schedule: at every step the 2^m ranks of the subgroup pair up perfectly, so no GPU is
+            # the target of two peers at once (all NVLink ports stay evenly loaded)
+            value = mine ^ step
             peer = base_rank | sum(((value >> i) & 1) << gb for i, gb in enumerate(gbit))
             lo, cnt = (0, block // 2) if rank < peer else (block // 2, block - block // 2)
             self.shard.exchange_block(vpos, value, mine, peer, lo, cnt)

@@ -143,6 +143,14 @@ class QVM_Wavefunction(QAM):
         self.kernel()
         return mask
 
+    def _run_once(self, pyquil_program, classical_addresses):
+        """One full execution; the classical bits only (the reference's run() calls wavefunction() and
+        drops the amplitudes, :279-283 -- here they simply stay on the device)."""
+        mask = self._simulate(pyquil_program, classical_addresses)
+        self._engine.sync()
+        memory = self.classical_memory if mask is None else self.classical_memory[mask]
+        return [int(x) for x in memory]
+
     def wavefunction(self, pyquil_program, classical_addresses=None):
         """Simulate a program; returns (Wavefunction, [classical bits at ``classical_addresses``])."""
         mask = self._simulate(pyquil_program, classical_addresses)
@@ -173,14 +181,10 @@ class QVM_Wavefunction(QAM):
         split = self._terminal_measure_block(pyquil_program) if self.sampling_fast_path else None
         if split is not None and split == len(pyquil_program) and trials > 1:
             # no MEASURE at all: every trial is the same deterministic run
-            _, classical_vals = self.wavefunction(pyquil_program, classical_addresses=classical_addresses)
+            classical_vals = self._run_once(pyquil_program, classical_addresses)
             return [list(classical_vals) for _ in range(trials)]
         if split is None or trials <= 1:
-            results = []
-            for _ in range(trials):
-                _, classical_vals = self.wavefunction(pyquil_program, classical_addresses=classical_addresses)
-                results.append(classical_vals)
-            return results
+            return [self._run_once(pyquil_program, classical_addresses) for _ in range(trials)]
 
         # simulate the measurement-free prefix once, then sample the terminal MEASURE block
         self.load_program(pyquil_program)
