@@ -159,6 +159,18 @@ def run_reference_arm(args, rank):
     print(json.dumps(line))
 
 
+def measured_traffic_ratio():
+    """DRAM bytes actually moved by one regtile_kernel launch / algorithmic bytes, from the committed
+    ncu capture (profiles/regtile_traffic.json); None when the file is absent."""
+    path = os.path.join(REPO, "profiles", "regtile_traffic.json")
+    try:
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["traffic_over_algorithmic"]), d["source"]
+    except Exception:
+        return None, None
+
+
 def workload_name(args):
     return "%d-qubit random circuit depth %d (H/RZ/CNOT/CPHASE, seed %d), complex128 state %.1f GiB" % (
         args.qubits, args.depth, SEED, 16.0 * 2 ** args.qubits / 2 ** 30)
@@ -289,6 +301,11 @@ def main():
                 "regtile_rounds_per_launch": stats.get("regtile_rounds", 0) / float(max(groups, 1)),
                 "effective_gbs": n_gates * args.steps * bytes_per_launch * world / (total_ms * 1e-3) / 1e9,
                 "note": "per GPU (rank 0): one launch = one read + one write of the local shard"}
+    ratio, ratio_src = measured_traffic_ratio()
+    if ratio is not None:
+        roofline["traffic"] = ratio * bytes_per_launch
+        roofline["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum = %.4f x algorithmic in %s, "
+                                      "scaled to this shard size" % (ratio, ratio_src))
     if sharded and swaps:
         swap_bytes = float(eng.swap_bytes - swap_bytes_before)      # sent (= received) per GPU, all exchanges
         roofline["nvlink"] = {"bound": "nvlink", "achieved": swap_bytes / (swap_ms * 1e-3) / 1e9, "peak": 900.0,
