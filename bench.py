@@ -98,7 +98,7 @@ class ClockSampler(object):
 
 # ---------------------------------------------------------------------------------------------
 def circuit(n, depth):
-    from oracle.qvm_oracle import random_circuit_spec      # generator only (no arithmetic)
+    from workloads import random_circuit_spec
     return random_circuit_spec(n, depth, SEED)
 
 

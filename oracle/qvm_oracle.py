@@ -314,37 +314,11 @@ def bits_big_endian(index, width):
     return [(int(index) >> (width - 1 - b)) & 1 for b in range(width)]
 
 
-# -- the benchmark circuit generator (SURVEY.md 8d / BASELINE.md section 3) ----------------------
-def random_circuit_spec(num_qubits, depth, seed):
-    """[(name, params, qubits)] for the H/RZ/CNOT/CPHASE random circuit the metric is quoted on."""
-    rng = np.random.RandomState(seed)
-    spec = []
-    for _ in range(depth):
-        for q in range(num_qubits):
-            kind = rng.randint(4)
-            if kind == 0:
-                spec.append(("H", [], [q]))
-            elif kind == 1:
-                spec.append(("RZ", [float(rng.uniform(0, 2 * np.pi))], [q]))
-            else:
-                b = int(rng.randint(num_qubits - 1))
-                b += b >= q
-                if kind == 2:
-                    spec.append(("CNOT", [], [q, b]))
-                else:
-                    spec.append(("CPHASE", [float(rng.uniform(0, 2 * np.pi))], [q, b]))
-    return spec
+# -- circuit generators: kept importable from here for the tests; they live in /workloads.py -------
+import os as _os
+import sys as _sys
 
-
-def qft_spec(num_qubits):
-    """QFT in the gate ordering of the reference's QFT-8 fixture
-    (``tests/test_data/data_containers.py:3-44``), generalised to n qubits."""
-    spec = []
-    n = num_qubits
-    for q in range(n - 1, -1, -1):
-        for j in range(n - 1, q, -1):
-            spec.append(("CPHASE", [float(np.pi / 2 ** (j - q))], [q, j]))
-        spec.append(("H", [], [q]))
-    for q in range(n // 2):
-        spec.append(("SWAP", [], [q, n - 1 - q]))
-    return spec
+_root = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+if _root not in _sys.path:
+    _sys.path.insert(0, _root)
+from workloads import qft_spec, random_circuit_spec  # noqa: E402,F401

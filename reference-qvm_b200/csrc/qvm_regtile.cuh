@@ -16,13 +16,20 @@
 // The op stream is interpreted, and round-1 profiles (profiles/README.md) showed the interpreter,
 // not HBM, bounds the kernel.  Hence this layout:
 //   * the prologue resolves everything that is uniform over the CTA (outer controls, outer index
-//     bits) and writes one 48-byte record per op to shared memory: a 16-byte header plus the (at
-//     most two) complex factors the op can need -- no global loads and no pointer chasing in the
-//     op loop; generic ops (dense matrices, wide diagonals) still index the global matrix pool;
-//   * the next op's header and first factor are fetched while the current op executes;
-//   * one flat opcode switch (a jump table); handlers are in-place on the register file (the
-//     Hadamard butterfly is a += b; b = a - 2b, so no moves and no sign fix-ups);
-//   * all per-round address ingredients (sorted register bits, swizzled strides) come precomputed.
+//     bits) and writes the op stream to shared memory as 16-byte words: a plain op is a header plus
+//     the (at most two) complex factors it can need -- no global loads and no pointer chasing in
+//     the op loop; generic ops (dense matrices, wide diagonals) still index the global matrix pool;
+//   * single-slot ops (H, the 8-amplitude phase S1, X relabels) commute across slots and are packed
+//     by the host into LAYER records: per slot [S1] -> [H] -> [X], up to 12 gates per dispatch, the
+//     thread-control tests of all sub-ops done by two vectorised mask operations;
+//   * the next op's header is fetched while the current op executes;
+//   * handlers are in place on the register file: the Hadamard butterfly is a += b; b = a - 2b, the
+//     complex multiply is inline PTX that reuses its operands' registers (ptxas otherwise rotates
+//     the amplitudes through temporaries and pays two moves per multiply);
+//   * all per-round address ingredients (insert masks, swizzled strides) come precomputed and the
+//     global addresses of a thread's 16 amplitudes are built by an add tree;
+//   * rare op shapes live in the FULL template variant only, the lean variant stays small for the
+//     instruction cache.
 //
 // The per-thread round body is __host__ __device__: tests/native/emu_regtile.cu runs the very same
 // code on the CPU (threads looped sequentially between barriers) so that the planner, the encoder

@@ -282,16 +282,6 @@ class ShardedEngine(object):
         if op.kind != nat.OP_NOP:
             self.pending.append(op)
 
-    def _next_dense_use(self, ops, start):
-        """For every logical qubit: index of the next op (>= start) that needs it local."""
-        nxt = {}
-        for i in range(len(ops) - 1, start - 1, -1):
-            op = ops[i]
-            if op.kind == nat.OP_DENSE:
-                for t in op.targets:
-                    nxt[t] = i
-        return nxt
-
     def flush(self):
         """Run every queued gate.  Ops whose dense targets are all local run in fused batches; an op
         with a dense target on a global position blocks (with everything that depends on it) until an

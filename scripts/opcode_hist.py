@@ -10,7 +10,7 @@ for p in (REPO, os.path.join(REPO, "reference-qvm_b200"), os.path.join(REPO, "te
 import numpy as np  # noqa: E402
 import referenceqvm  # noqa: E402,F401
 import _emu  # noqa: E402
-from oracle.qvm_oracle import random_circuit_spec  # noqa: E402
+from workloads import random_circuit_spec  # noqa: E402
 from referenceqvm import _engine, _planner, gates as G  # noqa: E402
 
 NAMES = {0: "X_RELABEL", 1: "H", 5: "XS", 9: "S1", 13: "DS", 14: "D1", 18: "DIAG_G", 19: "M1", 23: "M2", 25: "T", 26: "TG"}

@@ -9,7 +9,7 @@ for p in (REPO, os.path.join(REPO, "reference-qvm_b200")):
     sys.path.insert(0, p)
 
 import referenceqvm  # noqa: E402,F401
-from oracle.qvm_oracle import random_circuit_spec  # noqa: E402
+from workloads import random_circuit_spec  # noqa: E402
 from referenceqvm import _engine, _planner, _sharded, gates as G  # noqa: E402
 
 

@@ -10,7 +10,7 @@ for p in (REPO, os.path.join(REPO, "reference-qvm_b200"), os.path.join(REPO, "te
 import numpy as np  # noqa: E402
 import referenceqvm  # noqa: E402,F401
 from _programs import spec_program  # noqa: E402
-from oracle import qvm_oracle as orc  # noqa: E402
+import workloads as orc  # noqa: E402
 from referenceqvm.api import QVMConnection  # noqa: E402
 from referenceqvm.qvm_density import INFINITY, NoiseModel  # noqa: E402
 
