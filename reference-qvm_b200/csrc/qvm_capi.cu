@@ -50,6 +50,7 @@ struct qvm_state {
     int tile_bits = 12;
     int low_bits = 5;
     int use_regtile = 1;
+    int reg_bits = 4;                 // register bits per round of the register-tiled kernel (4 or 5)
     int sticky = 0;
     // op ring
     unsigned char* ring_host = nullptr;
@@ -372,15 +373,15 @@ int launch_group(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, 
 
 
 // ---- register-tiled path: encode (qvm_encode.h), upload, launch ------------------------------------
-template <int T, int B, bool FULL>
+template <int T, int B, bool FULL, int R>
 int launch_regtile(qvm_state* q, unsigned grid, unsigned threads, size_t smem, const RegTileParams& P) {
     static bool attr_set[64] = {};
     if (!attr_set[q->device & 63]) {
-        QVM_CUDA(q, cudaFuncSetAttribute(regtile_kernel<T, B, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        QVM_CUDA(q, cudaFuncSetAttribute(regtile_kernel<T, B, FULL, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024));
         attr_set[q->device & 63] = true;
     }
-    regtile_kernel<T, B, FULL><<<grid, threads, smem, q->stream>>>(q->amps, P);
+    regtile_kernel<T, B, FULL, R><<<grid, threads, smem, q->stream>>>(q->amps, P);
     QVM_CUDA(q, cudaGetLastError());
     return QVM_OK;
 }
@@ -390,7 +391,7 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
     *handled = false;
     EncodedGroup& g = q->enc;
     const int erc = encode_group(q->n_local, q->n_global, q->shard_index, n_tile, tile_bits, n_ops, ops, mats,
-                                 mats_entries, g);
+                                 mats_entries, g, q->reg_bits);
     if (erc == ENC_ERROR) return fail(QVM_ERR_CUDA, "round planner made no progress");
     if (erc == ENC_FALLBACK) return QVM_OK;          // the shared-memory kernel (or its error) handles it
     if (g.cold.empty()) {
@@ -426,12 +427,24 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
 
     // (capping registers to fit 5 or 6 CTAs of 128 threads per SM was measured slower: profiles/README.md)
     const unsigned grid = (unsigned)g.n_tiles;
-    if (g.threads > 256) {
-        rc = g.need_full ? launch_regtile<512, 1, true>(q, grid, g.threads, g.smem, P)
-                         : launch_regtile<512, 1, false>(q, grid, g.threads, g.smem, P);
+    if (g.P.R == 5) {
+        // 32 amplitudes per thread need ~190+ registers: 64-thread CTAs at 4 per SM, 128 at 2, 256 at 1.
+        // Measured slower than R = 4 on B200 (fewer resident warps; profiles/README.md), kept selectable.
+        if (g.threads > 128)
+            rc = g.need_full ? launch_regtile<256, 1, true, 5>(q, grid, g.threads, g.smem, P)
+                             : launch_regtile<256, 1, false, 5>(q, grid, g.threads, g.smem, P);
+        else if (g.threads > 64)
+            rc = g.need_full ? launch_regtile<128, 2, true, 5>(q, grid, g.threads, g.smem, P)
+                             : launch_regtile<128, 2, false, 5>(q, grid, g.threads, g.smem, P);
+        else
+            rc = g.need_full ? launch_regtile<64, 4, true, 5>(q, grid, g.threads, g.smem, P)
+                             : launch_regtile<64, 4, false, 5>(q, grid, g.threads, g.smem, P);
+    } else if (g.threads > 256) {
+        rc = g.need_full ? launch_regtile<512, 1, true, 4>(q, grid, g.threads, g.smem, P)
+                         : launch_regtile<512, 1, false, 4>(q, grid, g.threads, g.smem, P);
     } else {
-        rc = g.need_full ? launch_regtile<256, 2, true>(q, grid, g.threads, g.smem, P)
-                         : launch_regtile<256, 2, false>(q, grid, g.threads, g.smem, P);
+        rc = g.need_full ? launch_regtile<256, 2, true, 4>(q, grid, g.threads, g.smem, P)
+                         : launch_regtile<256, 2, false, 4>(q, grid, g.threads, g.smem, P);
     }
     if (rc) return rc;
     q->stats.kernel_launches += 1;
@@ -500,6 +513,7 @@ static int create_impl(int n_local, int device, void* external, qvm_t** out) {
     q->device = device;
     q->n_local = n_local;
     q->n_elems = 1ull << n_local;
+    if (const char* rb = getenv("QVM_B200_REG_BITS")) q->reg_bits = atoi(rb) == 5 ? 5 : 4;      // A/B runs
 #define QVM_CREATE_CUDA(expr)                                                                          \
     do {                                                                                               \
         cudaError_t _e = (expr);                                                                       \

@@ -26,16 +26,16 @@ struct LocalOp {
 };
 
 struct PlannedRound {
-    int slot_bit[4] = {-1, -1, -1, -1};      // tile-local bit held by register slot s
+    int slot_bit[kMaxRegBits] = {-1, -1, -1, -1, -1};      // tile-local bit held by register slot s
     std::vector<int> ops;                    // indices into the LocalOp list, execution order
     uint32_t regmask() const {
         uint32_t m = 0;
-        for (int s = 0; s < 4; ++s)
+        for (int s = 0; s < kMaxRegBits; ++s)
             if (slot_bit[s] >= 0) m |= 1u << slot_bit[s];
         return m;
     }
     int slot_of(int bit) const {
-        for (int s = 0; s < 4; ++s)
+        for (int s = 0; s < kMaxRegBits; ++s)
             if (slot_bit[s] == bit) return s;
         return -1;
     }
@@ -62,13 +62,12 @@ enum { ENC_OK = 0, ENC_FALLBACK = 1, ENC_ERROR = 2 };
 
 // Try to give the dense targets of `op` register slots in `rd`; `allowed` = tile bits that may
 // become register bits in this round.  Dense2 targets must share a slot pair {0,1} or {2,3}.
-inline bool place_dense(PlannedRound& rd, const LocalOp& op, uint32_t allowed) {
+inline bool place_dense(PlannedRound& rd, const LocalOp& op, uint32_t allowed, int R) {
     if (op.k == 1) {
         const int b = op.tgt[0];
         if (rd.slot_of(b) >= 0) return true;
         if (!((allowed >> b) & 1u)) return false;
-        static const int pref[4] = {3, 2, 1, 0};
-        for (int s : pref)
+        for (int s = R - 1; s >= 0; --s)        // the unpaired top slot first: pairs stay free for 2q gates
             if (rd.slot_bit[s] < 0) {
                 rd.slot_bit[s] = b;
                 return true;
@@ -80,6 +79,7 @@ inline bool place_dense(PlannedRound& rd, const LocalOp& op, uint32_t allowed) {
     if (sa >= 0 && sb >= 0) return (sa >> 1) == (sb >> 1);
     if (sa >= 0 || sb >= 0) {
         const int have = sa >= 0 ? sa : sb;
+        if (have >= 4) return false;         // the fifth slot has no partner
         const int other_bit = sa >= 0 ? b : a;
         const int partner = have ^ 1;
         if (rd.slot_bit[partner] >= 0 || !((allowed >> other_bit) & 1u)) return false;
@@ -108,8 +108,11 @@ inline bool is_h_matrix(const double* m) {      // s * [[1, 1], [1, -1]] with re
 // ENC_OK: `out` is ready to launch.  ENC_FALLBACK: group is valid-looking but outside what the
 // register-tiled kernel encodes (the shared-memory kernel takes it and reports real errors).
 inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_tile, const int32_t* tile_bits,
-                        int n_ops, const qvm_op_t* ops, const double* mats, uint64_t mats_entries, EncodedGroup& out) {
+                        int n_ops, const qvm_op_t* ops, const double* mats, uint64_t mats_entries, EncodedGroup& out,
+                        int R = 4) {
     if (n_tile < 9 || n_tile > 13) return ENC_FALLBACK;
+    if (R != 4 && R != 5) return ENC_FALLBACK;
+    if (R == 5 && n_tile < 10) R = 4;          // a 2^9 tile would leave half a warp per CTA
     const int npos = n_local + n_global;
     int8_t local_of[64];
     memset(local_of, -1, sizeof(local_of));
@@ -117,6 +120,7 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
     P = RegTileParams{};
     P.n_local = n_local;
     P.k = n_tile;
+    P.R = R;
     P.shard_bits = shard_index << n_local;
     uint64_t tile_mask = 0;
     for (int j = 0; j < n_tile; ++j) {
@@ -201,7 +205,7 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
                 bool ok = !clash;
                 if (ok && op.kind == QVM_OP_DENSE) {
                     PlannedRound trial = rd;
-                    ok = place_dense(trial, op, allowed);
+                    ok = place_dense(trial, op, allowed, R);
                     if (ok) memcpy(rd.slot_bit, trial.slot_bit, sizeof(rd.slot_bit));
                 }
                 if (!ok) {
@@ -233,7 +237,7 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
                     if ((lops[i].diag_mask >> b) & 1u) ++touch[b];
         const bool io_round = r == 0 || r + 1 == rounds.size();
         uint32_t used = rd.regmask();
-        for (int s = 0; s < 4; ++s) {
+        for (int s = 0; s < R; ++s) {
             if (rd.slot_bit[s] >= 0) continue;
             int best = -1;
             for (int pass = 0; pass < 2 && best < 0; ++pass)
@@ -299,18 +303,15 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
         int8_t slot_of[16], thr_of[16];
         memset(slot_of, -1, sizeof(slot_of));
         memset(thr_of, -1, sizeof(thr_of));
-        int sorted[4];
-        for (int s = 0; s < 4; ++s) {
+        int sorted[kMaxRegBits];
+        for (int s = 0; s < R; ++s) {
             d.reg_phys[s] = (uint8_t)tile_bits[rd.slot_bit[s]];
             d.swz_j[s] = (uint16_t)swz(1u << rd.slot_bit[s]);
             slot_of[rd.slot_bit[s]] = (int8_t)s;
             sorted[s] = rd.slot_bit[s];
         }
-        std::sort(sorted, sorted + 4);
-        for (int s = 0; s < 4; ++s) {
-            d.reg_sorted[s] = (uint8_t)sorted[s];
-            d.ins_mask[s] = (uint16_t)~((1u << sorted[s]) - 1u);
-        }
+        std::sort(sorted, sorted + R);
+        for (int s = 0; s < R; ++s) d.ins_mask[s] = (uint16_t)~((1u << sorted[s]) - 1u);
         int nt = 0;
         for (int b = 0; b < n_tile; ++b)
             if (slot_of[b] < 0) thr_of[b] = (int8_t)nt++;
@@ -469,7 +470,7 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
                 }
             }
             EncOp e;
-            e.h.x = opc | (crm << 8) | (xb << 12) | (p0 << 16) | (p1 << 24);
+            e.h.x = opc | (crm << 8) | (xb << 13) | (p0 << 16) | (p1 << 24);
             e.h.y = cthr | flags | ((uint32_t)kOpWords << HDR_SIZE_SHIFT);
             e.h.z = mat_off;
             e.h.w = (s0 << 8) | (s1 << 16) | (shr << 24);
@@ -480,13 +481,13 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
             e.f_im = 0.0;
             // single-slot ops share LAYER dispatches (outer dependence is patched in by the prologue)
             if (!in_batch) {
-                if (opc >= OPC_H0 && opc < OPC_H0 + 4) {
+                if (opc >= OPC_H0 && opc < OPC_H0 + kMaxRegBits) {
                     e.lay_type = 2;
                     e.lay_slot = (int)(opc - OPC_H0);
                 } else if (opc == OPC_X_RELABEL) {
                     e.lay_type = 3;
                     e.lay_slot = (int)xb;
-                } else if (opc >= OPC_S1_0 && opc < OPC_S1_0 + 4) {
+                } else if (opc >= OPC_S1_0 && opc < OPC_S1_0 + kMaxRegBits) {
                     e.lay_type = 1;
                     e.lay_slot = (int)(opc - OPC_S1_0);
                     e.f_re = pool[2 * (size_t)mat_off];          // right when no outer target selects it
@@ -544,9 +545,10 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
 
         struct Layer {
             uint32_t s1 = 0, h = 0, x = 0;
-            uint32_t cs[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu}, cx[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};   // absent
-            double f[4][2] = {{1, 0}, {1, 0}, {1, 0}, {1, 0}};
-            int stage[4] = {0, 0, 0, 0};
+            uint32_t cs[kMaxRegBits] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};      // 0xFFFF: absent
+            uint32_t cx[kMaxRegBits] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};
+            double f[kMaxRegBits][2] = {{1, 0}, {1, 0}, {1, 0}, {1, 0}, {1, 0}};
+            int stage[kMaxRegBits] = {0, 0, 0, 0, 0};
             int count = 0;
             std::vector<ColdOp> pending;     // patches of sub-ops that depend on outer bits (word_off set at emit)
         };
@@ -555,7 +557,7 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
             ColdOp c;
             memset(&c, 0, sizeof(c));
             c.fsel = 0xFF;
-            c.n_words = (uint8_t)kLayerWords;
+            c.n_words = (uint8_t)layer_words(R);
             c.kind = COLD_LAYER;
             c.word_off = (uint32_t)hot.size();
             for (ColdOp& pc : L.pending) {
@@ -563,13 +565,14 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
                 patches.push_back(pc);
             }
             uint4 h;
-            h.x = OPC_LAYER | (L.s1 << 8) | (L.h << 12) | (L.x << 16);
-            h.y = (uint32_t)kLayerWords << HDR_SIZE_SHIFT;
+            h.x = OPC_LAYER | (L.h << 12);
+            h.y = (uint32_t)layer_words(R) << HDR_SIZE_SHIFT;
             h.z = h.w = 0;
             hot.push_back(h);
             hot.push_back(make_uint4(L.cs[0] | (L.cs[1] << 16), L.cs[2] | (L.cs[3] << 16), L.cx[0] | (L.cx[1] << 16),
                                      L.cx[2] | (L.cx[3] << 16)));
-            for (int sl = 0; sl < 4; ++sl) {
+            if (R == 5) hot.push_back(make_uint4(L.cs[4] | (L.cx[4] << 16), 0, 0, 0));
+            for (int sl = 0; sl < R; ++sl) {
                 uint4 w;
                 memcpy(&w.x, &L.f[sl][0], 8);
                 memcpy(&w.z, &L.f[sl][1], 8);
@@ -585,24 +588,24 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
             // the last layer those slots have used, and their later sub-ops start in the layer after it.
             std::vector<Layer> layers;
             std::vector<std::vector<size_t>> after(1);      // after[i]: plain ops emitted before layer i
-            int last[4] = {-1, -1, -1, -1}, min_layer[4] = {0, 0, 0, 0};
+            int last[kMaxRegBits] = {-1, -1, -1, -1, -1}, min_layer[kMaxRegBits] = {0, 0, 0, 0, 0};
             auto slots_of = [&](const EncOp& e) -> uint32_t {
-                const uint32_t opc = e.h.x & 0xFFu, crm = (e.h.x >> 8) & 0xFu;
-                if (opc >= OPC_XS_0 && opc < OPC_XS_0 + 4) return crm | (1u << (opc - OPC_XS_0));
+                const uint32_t opc = e.h.x & 0xFFu, crm = (e.h.x >> 8) & 0x1Fu;
+                if (opc >= OPC_XS_0 && opc < OPC_XS_0 + kMaxRegBits) return crm | (1u << (opc - OPC_XS_0));
                 if (opc == OPC_DS || opc == OPC_DST) return crm;
-                if (opc >= OPC_D1_0 && opc < OPC_D1_0 + 4) return crm | (1u << (opc - OPC_D1_0));
-                return 0xFu;
+                if (opc >= OPC_D1_0 && opc < OPC_D1_0 + kMaxRegBits) return crm | (1u << (opc - OPC_D1_0));
+                return 0x1Fu;
             };
             for (size_t i = n_ts; i < enc.size(); ++i) {
                 EncOp& e = enc[i];
                 if (!e.lay_type) {
                     const uint32_t m = slots_of(e);
                     int pos = -1;
-                    for (int sl = 0; sl < 4; ++sl)
+                    for (int sl = 0; sl < R; ++sl)
                         if ((m >> sl) & 1u) pos = std::max(pos, std::max(last[sl], min_layer[sl] - 1));
                     if ((int)after.size() < pos + 2) after.resize(pos + 2);
                     after[pos + 1].push_back(i);
-                    for (int sl = 0; sl < 4; ++sl)
+                    for (int sl = 0; sl < R; ++sl)
                         if ((m >> sl) & 1u) {
                             min_layer[sl] = pos + 1;
                             last[sl] = -1;
@@ -686,9 +689,10 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
     P.n_rounds = (int)out.rounds.size();
     {
         const RoundDesc& r0 = out.rounds[0];
-        P.first_reg_phys = r0.reg_phys[0] | (r0.reg_phys[1] << 8) | (r0.reg_phys[2] << 16) | ((uint32_t)r0.reg_phys[3] << 24);
-        P.first_ins[0] = r0.ins_mask[0] | ((uint32_t)r0.ins_mask[1] << 16);
-        P.first_ins[1] = r0.ins_mask[2] | ((uint32_t)r0.ins_mask[3] << 16);
+        for (int sl = 0; sl < R; ++sl) {
+            P.first_reg_phys[sl] = r0.reg_phys[sl];
+            P.first_ins[sl] = r0.ins_mask[sl];
+        }
     }
     P.n_ops = (int)cold.size();
     P.n_patches = (int)patches.size();
@@ -697,7 +701,7 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
     out.smem = regtile_smem_bytes(P.k, P.low, P.n_rounds, P.n_words);
     if (out.smem > 227 * 1024) return ENC_FALLBACK;
     out.n_tiles = (1ull << n_local) >> n_tile;
-    out.threads = 1u << (n_tile - 4);
+    out.threads = 1u << (n_tile - R);
     return ENC_OK;
 }
 

@@ -1,9 +1,9 @@
 // Register-tiled tile kernel (the fast path of qvm_apply_group).
 //
-// A CTA owns a tile of 2^k amplitudes (k tile bits, 9 <= k <= 13) and runs 2^(k-4) threads; each
-// thread keeps 16 amplitudes in registers.  The group's gates are split (host side, qvm_encode.h)
-// into ROUNDS.  In a round, 4 of the tile bits are "register bits" (they index the 16 register
-// slots of a thread) and the other k-4 are "thread bits".  A gate whose dense targets are register
+// A CTA owns a tile of 2^k amplitudes (k tile bits, 9 <= k <= 13) and runs 2^(k-R) threads; each
+// thread keeps 2^R amplitudes in registers (R = 4: 16 amplitudes, the default; R = 5: 32).  The group's gates are split (host side, qvm_encode.h)
+// into ROUNDS.  In a round, R of the tile bits are "register bits" (they index the 2^R register
+// slots of a thread) and the other k-R are "thread bits".  A gate whose dense targets are register
 // bits is applied with no addressing at all; controls and diagonal factors may sit on register,
 // thread or outer bits (thread/outer ones cost a predicate or one per-thread scalar).  Changing the
 // set of register bits is a shared-memory transposition (XOR-swizzled against bank conflicts).
@@ -54,43 +54,47 @@
 
 namespace qvm {
 
-// Opcodes.
+// Opcodes.  "+slot" families reserve 5 codes (R <= 5 register slots).
 enum : uint32_t {
     // single-slot ops: the encoder always packs them into LAYERs; these codes only label them on the host
     OPC_X_RELABEL = 0,    // X / CNOT with no register-slot control: flips a bit of the slot relabel mask
     OPC_H0 = 1,           // +slot: uncontrolled Hadamard butterfly (scale folded into the round scalar)
-    OPC_XS_0 = 5,         // +slot: X on that slot with register-slot controls crm: pair swaps
-    OPC_S1_0 = 9,         // +slot: factor f on the 8 slots whose logical bit is 1
-    OPC_DS = 13,          // factor f on the slots selected by the register-slot control mask crm
-    OPC_D1_0 = 14,        // +slot: (d0, d1) by the logical bit of that slot, optional crm
-    OPC_DIAG_G = 18,      // generic diagonal through the matrix pool (FULL kernels only)
-    OPC_M1_0 = 19,        // +slot: dense 2x2 from the pool (FULL)
-    OPC_M2_0 = 23,        // +pair: dense 4x4 on slots (1,0) / (3,2) from the pool (FULL)
-    OPC_T = 25,           // thread scalar: f0 / f1 by one thread bit (only in the DIAG_T batch)
-    OPC_TG = 26,          // thread scalar through the pool: two thread-bit targets (DIAG_T batch)
-    OPC_S1T_0 = 27,       // +slot: S1 whose factor is f0 / f1 by thread bit p0
-    OPC_DST = 31,         // DS whose factor is f0 / f1 by thread bit p0
-    OPC_LAYER = 32,       // up to 12 single-slot ops in one dispatch: per slot [S1] -> [H] -> [X relabel]
-    OPC_COUNT = 33,
+    OPC_S1_0 = 6,         // +slot: factor f on the slots whose logical bit is 1
+    OPC_XS_0 = 11,        // +slot: X on that slot with register-slot controls crm: pair swaps
+    OPC_DS = 16,          // factor f on the slots selected by the register-slot control mask crm
+    OPC_DST = 17,         // DS whose factor is f0 / f1 by thread bit p0 (FULL)
+    OPC_D1_0 = 18,        // +slot: (d0, d1) by the logical bit of that slot, optional crm (FULL)
+    OPC_DIAG_G = 23,      // generic diagonal through the matrix pool (FULL)
+    OPC_M1_0 = 24,        // +slot: dense 2x2 from the pool (FULL)
+    OPC_M2_0 = 29,        // +pair: dense 4x4 on slots (1,0) / (3,2) from the pool (FULL)
+    OPC_T = 31,           // thread scalar: f0 / f1 by one thread bit (only in the thread-scalar batch)
+    OPC_TG = 32,          // thread scalar through the pool: two thread-bit targets (thread-scalar batch)
+    OPC_LAYER = 33,       // up to 3R single-slot ops in one dispatch: per slot [S1] -> [H] -> [X relabel]
+    OPC_COUNT = 34,
 };
+constexpr int kMaxRegBits = 5;
 
 // The op stream is a sequence of 16-byte words in shared memory.  A plain op is 3 words
-// (header, f0, f1); a LAYER is 6 words (header, thread-control masks, one S1 factor per slot).
+// (header, f0, f1); a LAYER is header + thread-control masks (1 word for R = 4, 2 for R = 5) + one
+// S1 factor per slot.
 //
 // Header word of an op.
-// x: [7:0] opcode | [11:8] crm (register-slot control mask) | [15:12] xb (slot of X_RELABEL)
+// x: [7:0] opcode | [12:8] crm (register-slot control mask) | [15:13] xb (slot of X_RELABEL)
 //    | [23:16] p0 | [31:24] p1     thread-bit positions of up to two thread targets (31 = none)
-//    LAYER: [7:0] opcode | [11:8] slots with an S1 | [15:12] slots with an H | [19:16] slots with an X
+//    LAYER: [7:0] opcode | [12 + s] slot s has an H
 // y: [15:0] cthr (thread-bit control mask; 0xFFFF = op inactive for this CTA) | [16] HAS_F1
 //    | [23:20] size of this op in words
 // z: mat_off (double2 units into the pool; generic ops)
 // w: [7:0] oi (pool index bits from outer targets, patched per CTA) | [15:8] s0 | [23:16] s1
 //    (index weights, as shifts, of the thread targets p0 / p1) | [31:24] shr (weight shift of the
 //    register-slot target, D1 / DIAG_G)
-// LAYER word 1: x = cthr of the S1 on slot 0 | slot 1 << 16, y = slots 2 | 3, z / w = the same for X.
+// LAYER word 1: x = cthr of the S1 on slot 0 | slot 1 << 16, y = slots 2 | 3, z / w = the same for X;
+// word 2 (R = 5 only): x = S1 mask of slot 4 | X mask of slot 4 << 16.  0xFFFF = no such sub-op.
 constexpr uint32_t HDR_HAS_F1 = 1u << 16;
 constexpr uint32_t HDR_SIZE_SHIFT = 20;
-constexpr int kOpWords = 3, kLayerWords = 6;
+constexpr int kOpWords = 3;
+__host__ __device__ constexpr int layer_words(int R) { return R == 5 ? 8 : 6; }
+__host__ __device__ constexpr int layer_factor_word(int R) { return R == 5 ? 3 : 2; }
 
 union __align__(16) OpWord {      // one 16-byte word of the op stream
     uint4 u;
@@ -106,7 +110,7 @@ struct __align__(16) ColdOp {
     uint8_t fsel;             // weight shift of the one non-outer target that selects f0 / f1; 0xFF = none
     uint32_t mat_off;         // pool offset (double2 units) of the op's diagonal / matrix
     uint8_t prefetch;         // 1: the prologue copies pool[mat_off + oi (| 1 << fsel)] into f0 (f1)
-    uint8_t n_words;          // words this op occupies in the stream (3, or 6 for a LAYER)
+    uint8_t n_words;          // words this op occupies in the stream
     uint8_t kind;             // COLD_*
     uint8_t slot;             // patches: the layer slot they belong to
     uint32_t word_off;        // first word of the op (patches: of the layer they patch)
@@ -119,28 +123,28 @@ enum : uint8_t { COLD_PLAIN = 0, COLD_LAYER = 1, COLD_PATCH_S1 = 2, COLD_PATCH_X
 enum : uint8_t { LOC_REG = 0x00, LOC_THR = 0x40, LOC_OUT = 0x80, LOC_CLASS = 0xC0, LOC_INDEX = 0x3F };
 
 struct __align__(16) RoundDesc {
-    uint8_t reg_sorted[4];    // the four register bits (tile-local), ascending: insert-zero thread mapping
-    uint8_t reg_phys[4];      // physical position of register slot s (global I/O rounds)
-    uint16_t swz_j[4];        // swz(1 << tile-local bit of slot s): shared-memory stride of slot s
-    double2 scale;            // complex scalar applied in this round (folded H scales, RZ phases)
-    uint16_t op_begin, dt_end, op_end;   // WORD offsets: [op_begin, dt_end) thread-scalar batch; [dt_end, op_end) slot ops
-    uint16_t flags;           // bit 0: scale != 1; bits 15..1: number of OPC_TG ops at the end of the batch
-    uint16_t ins_mask[4];     // ~((1 << reg_sorted[i]) - 1): x + (x & mask) inserts a zero bit at that position
+    double2 scale;            //  0: complex scalar applied in this round (folded H scales, RZ phases)
+    uint16_t swz_j[5];        // 16: swz(1 << tile-local bit of slot s): shared-memory stride of slot s
+    uint16_t op_begin, dt_end, op_end;   // 26: WORD offsets: [op_begin, dt_end) thread-scalar batch; [dt_end, op_end) slot ops
+    uint16_t ins_mask[5];     // 32: ~((1 << b) - 1) for the register bits b ascending: x + (x & mask) inserts a zero bit
+    uint16_t flags;           // 42: bit 0: scale != 1; bits 15..1: number of OPC_TG ops at the end of the batch
+    uint8_t reg_phys[5];      // 44: physical position of register slot s (global I/O rounds)
+    uint8_t pad[15];
 };
-static_assert(sizeof(RoundDesc) == 48, "RoundDesc layout");
+static_assert(sizeof(RoundDesc) == 64, "RoundDesc layout");
 
 struct RegTileParams {
     int n_local;
     int k;
+    int R;                    // register bits per round (4 or 5)
     int low;                  // tile_pos[j] == j for j < low
     int n_rounds;
     int n_ops;                // cold entries that produce stream words (plain ops and layers)
     int n_patches;            // cold entries [n_ops, n_ops + n_patches) patch layer sub-ops afterwards
     int n_words;              // length of the op stream in 16-byte words
     int n_runs;               // runs of consecutive non-tile positions
-    uint32_t first_reg_phys;  // round 0: physical positions of the register slots (4 x 8 bits) ...
-    uint32_t first_ins[2];    // ... and its four insert masks (4 x 16 bits): lets the tile load start
-                              // before the prologue has staged anything
+    uint8_t first_reg_phys[8];   // round 0: physical positions of the register slots ...
+    uint16_t first_ins[8];       // ... and its insert masks: the tile load needs nothing staged
     uint64_t shard_bits;
     uint64_t run_start;       // 8 x 8 bits: start position of each run
     uint64_t run_len;         // 8 x 8 bits: length of each run
@@ -159,7 +163,7 @@ QVM_HD double2 cmul(double2 a, double2 b) {
 // overwritten
 QVM_HD void cmul_ip(double2& a, const double2 f) {
 #if defined(__CUDA_ARCH__)
-    // same virtual register as source and destination: keeps ptxas from rotating the 16 amplitudes
+    // same virtual register as source and destination: keeps ptxas from rotating the amplitudes
     // through temporaries (which costs two moves per multiply at every handler exit)
     asm("{\n\t"
         ".reg .f64 t;\n\t"
@@ -231,8 +235,9 @@ QVM_HD void rt_resolve_op(const RegTileParams& P, uint32_t j, uint64_t full, OpW
     const ColdOp* c = &P.cold[j];
     const uint32_t w0 = c->word_off;
     OpWord* dst = stream + w0;
-    if (c->n_words == kLayerWords) {               // layers carry no outer-dependent data: verbatim copy
-        for (int i = 0; i < kLayerWords; ++i) dst[i].u = QVM_LDG(&P.hot[w0 + i]);
+    if (c->kind == COLD_LAYER) {                   // outer-dependent sub-ops are patched afterwards
+        const int nw = c->n_words;
+        for (int i = 0; i < nw; ++i) dst[i].u = QVM_LDG(&P.hot[w0 + i]);
         return;
     }
     uint4 h = QVM_LDG(&P.hot[w0]);
@@ -266,15 +271,19 @@ QVM_HD void rt_resolve_op(const RegTileParams& P, uint32_t j, uint64_t full, OpW
 QVM_HD void rt_patch_op(const RegTileParams& P, uint32_t j, uint64_t full, OpWord* stream) {
     const ColdOp* c = &P.cold[j];
     OpWord* layer = stream + c->word_off;
-    uint16_t* masks = reinterpret_cast<uint16_t*>(&layer[1]);       // cs[0..3], cx[0..3]
+    const uint32_t slot = c->slot;
+    // word 1: cs[0..3], cx[0..3]; word 2 (R = 5): cs[4], cx[4]
+    uint16_t* m16 = reinterpret_cast<uint16_t*>(&layer[slot < 4 ? 1 : 2]);
+    uint16_t* ms = slot < 4 ? &m16[slot] : &m16[0];
+    uint16_t* mx = slot < 4 ? &m16[4 + slot] : &m16[1];
     const uint64_t co = c->ctrl_outer;
     const bool active = (full & co) == co;
     if (c->kind == COLD_PATCH_X) {
-        if (!active) masks[4 + c->slot] = 0xFFFFu;
+        if (!active) *mx = 0xFFFFu;
         return;
     }
     if (!active) {
-        masks[c->slot] = 0xFFFFu;
+        *ms = 0xFFFFu;
         return;
     }
     const uint32_t kk = c->k;
@@ -284,20 +293,20 @@ QVM_HD void rt_patch_op(const RegTileParams& P, uint32_t j, uint64_t full, OpWor
             const uint32_t loc = c->loc[t];
             if ((loc & LOC_CLASS) == LOC_OUT) oi |= (uint32_t)((full >> (loc & LOC_INDEX)) & 1ull) << (kk - 1 - t);
         }
-        layer[2 + c->slot].d = QVM_LDG(&P.mats[c->mat_off + oi]);
+        layer[layer_factor_word(P.R) + slot].d = QVM_LDG(&P.mats[c->mat_off + oi]);
     }
 }
 
-// ---- slot handlers (all in place) ----------------------------------------------------------------
+// ---- slot handlers (all in place; NA = 2^R amplitudes per thread) ---------------------------------
 // Physical register p holds logical slot (p ^ xm): thread-uniform X / CNOT only flips bits of xm.
 // A register-slot control mask crm is tested on the logical index:
 //   ((p ^ xm) & crm) == crm  <=>  (p & crm) == (crm & ~xm) =: want.
 
 // Unnormalised Hadamard on slot B.  LO = physical half that holds logical 0.
-template <int B, int LO>
-QVM_HD void reg_h_half(double2 (&a)[16]) {
+template <int B, int LO, int NA>
+QVM_HD void reg_h_half(double2 (&a)[NA]) {
 #pragma unroll
-    for (int p = 0; p < 8; ++p) {
+    for (int p = 0; p < NA / 2; ++p) {
         const int i0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1)) | (LO << B);     // logical 0
         const int i1 = i0 ^ (1 << B);                                                // logical 1
         a[i0].x += a[i1].x;
@@ -306,27 +315,20 @@ QVM_HD void reg_h_half(double2 (&a)[16]) {
         a[i1].y = fma(-2.0, a[i1].y, a[i0].y);
     }
 }
-template <int B>
-QVM_HD void reg_h(double2 (&a)[16], const uint32_t xm) {
-    if ((xm >> B) & 1u) reg_h_half<B, 1>(a);
-    else reg_h_half<B, 0>(a);
+template <int B, int NA>
+QVM_HD void reg_h(double2 (&a)[NA], const uint32_t xm) {
+    if ((xm >> B) & 1u) reg_h_half<B, 1, NA>(a);
+    else reg_h_half<B, 0, NA>(a);
 }
 
-#if defined(__CUDA_ARCH__)
-#define QVM_NO_IFCVT() ((void)0)
-#else
-#define QVM_NO_IFCVT() ((void)0)
-#endif
-
-template <int B>
-QVM_HD void reg_xswap(double2 (&a)[16], const uint32_t crm, const uint32_t xm) {
+template <int B, int NA>
+QVM_HD void reg_xswap(double2 (&a)[NA], const uint32_t crm, const uint32_t xm) {
     const uint32_t want = crm & ~xm;
 #pragma unroll
-    for (int p = 0; p < 8; ++p) {
+    for (int p = 0; p < NA / 2; ++p) {
         const int i0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1));
         const int i1 = i0 | (1 << B);
-        if ((i0 & crm) == want) {        // warp-uniform: a real branch beats 12 selects per pair
-            QVM_NO_IFCVT();
+        if ((i0 & crm) == want) {
             const double2 x0 = a[i0];
             a[i0] = a[i1];
             a[i1] = x0;
@@ -334,22 +336,22 @@ QVM_HD void reg_xswap(double2 (&a)[16], const uint32_t crm, const uint32_t xm) {
     }
 }
 
-// factor f on the 8 slots whose logical bit B is 1
-template <int B>
-QVM_HD void reg_s1(double2 (&a)[16], const double2 f, const uint32_t xm) {
+// factor f on the NA / 2 slots whose logical bit B is 1
+template <int B, int NA>
+QVM_HD void reg_s1(double2 (&a)[NA], const double2 f, const uint32_t xm) {
     if ((xm >> B) & 1u) {
 #pragma unroll
-        for (int p = 0; p < 16; ++p)
+        for (int p = 0; p < NA; ++p)
             if (!((p >> B) & 1)) cmul_ip(a[p], f);
     } else {
 #pragma unroll
-        for (int p = 0; p < 16; ++p)
+        for (int p = 0; p < NA; ++p)
             if ((p >> B) & 1) cmul_ip(a[p], f);
     }
 }
 
-template <int B>
-QVM_HD void reg_d1(double2 (&a)[16], double2 d0, double2 d1, const uint32_t crm, const uint32_t xm) {
+template <int B, int NA>
+QVM_HD void reg_d1(double2 (&a)[NA], double2 d0, double2 d1, const uint32_t crm, const uint32_t xm) {
     if ((xm >> B) & 1u) {
         const double2 t = d0;
         d0 = d1;
@@ -357,21 +359,18 @@ QVM_HD void reg_d1(double2 (&a)[16], double2 d0, double2 d1, const uint32_t crm,
     }
     const uint32_t want = crm & ~xm;
 #pragma unroll
-    for (int p = 0; p < 16; ++p)
-        if ((p & crm) == want) {
-            QVM_NO_IFCVT();
-            cmul_ip(a[p], ((p >> B) & 1) ? d1 : d0);
-        }
+    for (int p = 0; p < NA; ++p)
+        if ((p & crm) == want) cmul_ip(a[p], ((p >> B) & 1) ? d1 : d0);
 }
 
-template <int B>
-QVM_HD void reg_dense1(double2 (&a)[16], const double2* __restrict__ mat, const uint32_t crm, const uint32_t xm) {
+template <int B, int NA>
+QVM_HD void reg_dense1(double2 (&a)[NA], const double2* __restrict__ mat, const uint32_t crm, const uint32_t xm) {
     const uint32_t flip = ((xm >> B) & 1u) ? 3u : 0u;      // relabelled slots: index-flipped matrix
     const double2 m00 = QVM_LDG(&mat[0 ^ flip]), m01 = QVM_LDG(&mat[1 ^ flip]), m10 = QVM_LDG(&mat[2 ^ flip]),
                   m11 = QVM_LDG(&mat[3 ^ flip]);
     const uint32_t want = crm & ~xm;
 #pragma unroll
-    for (int p = 0; p < 8; ++p) {
+    for (int p = 0; p < NA / 2; ++p) {
         const int i0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1));
         const int i1 = i0 | (1 << B);
         if ((i0 & crm) == want) {
@@ -386,14 +385,14 @@ QVM_HD void reg_dense1(double2 (&a)[16], const double2* __restrict__ mat, const 
 }
 
 // pair P: slots (msb = 2P+1, lsb = 2P)
-template <int P>
-QVM_HD void reg_dense2(double2 (&a)[16], const double2* __restrict__ m, const uint32_t crm, const uint32_t xm) {
+template <int P, int NA>
+QVM_HD void reg_dense2(double2 (&a)[NA], const double2* __restrict__ m, const uint32_t crm, const uint32_t xm) {
     constexpr int LO = 2 * P, HI = 2 * P + 1;
     const uint32_t x2 = (xm >> LO) & 3u;
     const uint32_t want = crm & ~xm;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int i0 = (P == 0) ? (q << 2) : q;      // the two slot bits outside the pair
+    for (int q = 0; q < NA / 4; ++q) {
+        const int i0 = ((q >> LO) << (LO + 2)) | (q & ((1 << LO) - 1));      // the slot bits outside the pair
         if ((i0 & crm) == want) {
             const int idx[4] = {i0, i0 | (1 << LO), i0 | (1 << HI), i0 | (1 << LO) | (1 << HI)};
             const double2 x0 = a[idx[0]], x1 = a[idx[1]], x2v = a[idx[2]], x3 = a[idx[3]];
@@ -410,73 +409,88 @@ QVM_HD void reg_dense2(double2 (&a)[16], const double2* __restrict__ m, const ui
     }
 }
 
-// ---- one round of one thread ----------------------------------------------------------------------
-// FULL = false drops the generic dense 2x2 / 4x4 and generic-diagonal handlers (the host launches
-// that lean variant when a group has none of them): less code, friendlier to the I-cache.
-// Round 0's tile load, issued at kernel entry: everything it needs comes from kernel parameters and
-// one L2-resident table, so the HBM requests are in flight while the prologue stages the op stream.
-QVM_HD void rt_first_load(const RegTileParams& P, const double2* gbase, const uint32_t tid, double2 (&a)[16]) {
-    uint32_t T = tid;
-    T += T & (P.first_ins[0] & 0xFFFFu);
-    T += T & (P.first_ins[0] >> 16);
-    T += T & (P.first_ins[1] & 0xFFFFu);
-    T += T & (P.first_ins[1] >> 16);
-    // register-bit positions carry zeros in gT, so the 16 addresses are sums: an add tree on byte
-    // offsets (two instructions per address) instead of 64-bit OR + scale per element
-    const uint64_t gT = (uint64_t)(T & ((1u << P.low) - 1u)) | QVM_LDG(&P.hi_off[T >> P.low]);
-    const char* p0 = reinterpret_cast<const char*>(gbase + gT);
-    const uint32_t ph = P.first_reg_phys;
-    const uint64_t b0 = 16ull << (ph & 0xFFu), b1 = 16ull << ((ph >> 8) & 0xFFu), b2 = 16ull << ((ph >> 16) & 0xFFu),
-                   b3 = 16ull << (ph >> 24);
-    const char* q[16];
-    q[0] = p0;
-    q[1] = p0 + b0;
-    q[2] = p0 + b1;
-    q[3] = q[1] + b1;
+// XOR-combination of the strides selected by the bits of j (j is a compile-time constant at every use)
+template <int R>
+QVM_HD uint32_t xor_combo(const uint32_t (&st)[R], int j) {
+    uint32_t x = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) q[4 + j] = q[j] + b2;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) q[8 + j] = q[j] + b3;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) a[j] = *reinterpret_cast<const double2*>(q[j]);
+    for (int s = 0; s < R; ++s)
+        if ((j >> s) & 1) x ^= st[s];
+    return x;
 }
 
-template <bool FULL>
-QVM_HD void rt_thread_round(const RtCta& c, const int r, const uint32_t tid, double2 (&a)[16]) {
+// Global addresses of a thread's 2^R amplitudes: register-bit positions carry zeros in the thread's
+// own offset, so they are sums -- an add tree on byte offsets (two instructions per address).
+template <int R, typename PTR>
+QVM_HD void add_tree(PTR p0, const int64_t (&b)[R], PTR (&q)[1 << R]) {
+    q[0] = p0;
+#pragma unroll
+    for (int s = 0; s < R; ++s)
+#pragma unroll
+        for (int j = 0; j < (1 << s); ++j) q[(1 << s) + j] = q[j] + b[s];
+}
+
+// Round 0's tile load: everything it needs comes from kernel parameters and one L2-resident table.
+template <int R>
+QVM_HD void rt_first_load(const RegTileParams& P, const double2* gbase, const uint32_t tid, double2 (&a)[1 << R]) {
+    uint32_t T = tid;
+#pragma unroll
+    for (int s = 0; s < R; ++s) T += T & P.first_ins[s];
+    const uint64_t gT = (uint64_t)(T & ((1u << P.low) - 1u)) | QVM_LDG(&P.hi_off[T >> P.low]);
+    int64_t b[R];
+#pragma unroll
+    for (int s = 0; s < R; ++s) b[s] = (int64_t)(16ull << P.first_reg_phys[s]);
+    const char* q[1 << R];
+    add_tree<R>(reinterpret_cast<const char*>(gbase + gT), b, q);
+#pragma unroll
+    for (int j = 0; j < (1 << R); ++j) a[j] = *reinterpret_cast<const double2*>(q[j]);
+}
+
+// ---- one round of one thread ----------------------------------------------------------------------
+// FULL = false drops the rare handlers (generic dense 2x2 / 4x4, generic and thread-selected
+// diagonals; the host launches that lean variant when a group has none of them).
+template <bool FULL, int R>
+QVM_HD void rt_thread_round(const RtCta& c, const int r, const uint32_t tid, double2 (&a)[1 << R]) {
+    constexpr int NA = 1 << R;
     const RoundDesc* rd = &c.rounds[r];
-    const uint4 rw = *reinterpret_cast<const uint4*>(rd);      // x: reg_sorted | y: reg_phys | z,w: swz_j
-    const uint2 rr = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(rd) + 32);
-    const uint32_t op_begin = rr.x & 0xFFFFu, dt_end = rr.x >> 16, op_end = rr.y & 0xFFFFu;
-    const bool scaled = (rr.y >> 16) & 1u;
+    const uint4 w1 = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(rd) + 16);
+    const uint4 w2 = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(rd) + 32);
+    // w1: swz_j[0..4] (x, y, z.lo) | op_begin (z.hi) | dt_end (w.lo) | op_end (w.hi)
+    // w2: ins_mask[0..4] (x, y, z.lo) | flags (z.hi) | reg_phys[0..3] (w)
+    const uint32_t op_begin = w1.z >> 16, dt_end = w1.w & 0xFFFFu, op_end = w1.w >> 16;
+    const uint32_t flags = w2.z >> 16;
+    const bool scaled = flags & 1u;
     const bool first = r == 0, last = r == c.n_rounds - 1;
 
     // tile index of this thread: tid with zeros inserted at the (ascending) register-bit positions
-    const uint2 im = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(rd) + 40);
     uint32_t T = tid;
-    T += T & (im.x & 0xFFFFu);
-    T += T & (im.x >> 16);
-    T += T & (im.y & 0xFFFFu);
-    T += T & (im.y >> 16);
-    const uint32_t s0 = rw.z & 0xFFFFu, s1 = rw.z >> 16, s2 = rw.w & 0xFFFFu, s3 = rw.w >> 16;
+    T += T & (w2.x & 0xFFFFu);
+    T += T & (w2.x >> 16);
+    T += T & (w2.y & 0xFFFFu);
+    T += T & (w2.y >> 16);
+    if (R == 5) T += T & (w2.z & 0xFFFFu);
+    uint32_t st[R];
+    st[0] = w1.x & 0xFFFFu;
+    st[1] = w1.x >> 16;
+    st[2] = w1.y & 0xFFFFu;
+    st[3] = w1.y >> 16;
+    if (R == 5) st[R - 1] = w1.z & 0xFFFFu;
     const uint32_t sT = swz(T);
     const uint32_t low_mask = (1u << c.low) - 1u;
 
-    if (first) {
-        // loaded by rt_first_load before the prologue (the HBM latency hides behind the op staging)
-    } else {
+    if (!first) {        // (round 0's amplitudes were loaded from HBM by rt_first_load)
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            a[j] = c.tile[sT ^ ((j & 1) ? s0 : 0) ^ ((j & 2) ? s1 : 0) ^ ((j & 4) ? s2 : 0) ^ ((j & 8) ? s3 : 0)];
+        for (int j = 0; j < NA; ++j) a[j] = c.tile[sT ^ xor_combo<R>(st, j)];
     }
 
     // Thread-scalar batch: these ops touch no register qubit of this round, so they commute with all
     // of its ops; the host sorts them first and they fold into one scalar per thread.
     double2 ts = rd->scale;
     bool ts_dirty = scaled;
+    const uint32_t tg_begin = dt_end - kOpWords * (flags >> 1);          // the (rare) pool-indexed ops come last
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    const uint32_t tg_begin = dt_end - kOpWords * (rr.y >> 17);          // the (rare) pool-indexed ops come last
     for (const OpWord* op = &c.ops[op_begin]; op != &c.ops[tg_begin]; op += kOpWords) {
         const uint2 w = *reinterpret_cast<const uint2*>(op);         // OPC_T: f0 / f1 by thread bit p0
         if ((tid & w.y & 0xFFFFu) != (w.y & 0xFFFFu)) continue;
@@ -496,7 +510,7 @@ QVM_HD void rt_thread_round(const RtCta& c, const int r, const uint32_t tid, dou
     }
     if (ts_dirty) {          // scalars commute with everything: apply now, so ts is dead in the main loop
 #pragma unroll
-        for (int j = 0; j < 16; ++j) cmul_ip(a[j], ts);
+        for (int j = 0; j < NA; ++j) cmul_ip(a[j], ts);
     }
 
     uint32_t xm = 0;         // physical register p holds logical slot p ^ xm
@@ -513,106 +527,116 @@ QVM_HD void rt_thread_round(const RtCta& c, const int r, const uint32_t tid, dou
             op += (hn.y >> HDR_SIZE_SHIFT) & 0xFu;
             hn = *reinterpret_cast<const uint2*>(op);             // prefetch (one spare word follows the last op)
             if (opc == OPC_LAYER) {
-                // per slot: [S1 factor] -> [H] -> [X relabel]; sub-ops on different slots commute
-                // word 1: thread-control masks of the S1 (x, y) and X (z, w) sub-ops, 16 bits per slot; an
-                // absent sub-op carries the impossible mask 0xFFFF.  (t & m) ^ m == 0  <=>  all controls set.
+                // per slot: [S1 factor] -> [H] -> [X relabel]; sub-ops on different slots commute.
+                // (t & m) ^ m == 0  <=>  every thread-bit control of that sub-op is set; absent = 0xFFFF.
+                constexpr int FW = layer_factor_word(R);
                 const uint4 m = cur[1].u;
                 const uint32_t t2 = tid | (tid << 16);
                 const uint32_t s01 = (t2 & m.x) ^ m.x, s23 = (t2 & m.y) ^ m.y;
                 const uint32_t x01 = (t2 & m.z) ^ m.z, x23 = (t2 & m.w) ^ m.w;
-                if (!(s01 & 0xFFFFu)) reg_s1<0>(a, cur[2].d, xm);
-                if (hx & 0x1000u) reg_h<0>(a, xm);
+                if (!(s01 & 0xFFFFu)) reg_s1<0, NA>(a, cur[FW + 0].d, xm);
+                if (hx & 0x1000u) reg_h<0, NA>(a, xm);
                 if (!(x01 & 0xFFFFu)) xm ^= 1u;
-                if (!(s01 >> 16)) reg_s1<1>(a, cur[3].d, xm);
-                if (hx & 0x2000u) reg_h<1>(a, xm);
+                if (!(s01 >> 16)) reg_s1<1, NA>(a, cur[FW + 1].d, xm);
+                if (hx & 0x2000u) reg_h<1, NA>(a, xm);
                 if (!(x01 >> 16)) xm ^= 2u;
-                if (!(s23 & 0xFFFFu)) reg_s1<2>(a, cur[4].d, xm);
-                if (hx & 0x4000u) reg_h<2>(a, xm);
+                if (!(s23 & 0xFFFFu)) reg_s1<2, NA>(a, cur[FW + 2].d, xm);
+                if (hx & 0x4000u) reg_h<2, NA>(a, xm);
                 if (!(x23 & 0xFFFFu)) xm ^= 4u;
-                if (!(s23 >> 16)) reg_s1<3>(a, cur[5].d, xm);
-                if (hx & 0x8000u) reg_h<3>(a, xm);
+                if (!(s23 >> 16)) reg_s1<3, NA>(a, cur[FW + 3].d, xm);
+                if (hx & 0x8000u) reg_h<3, NA>(a, xm);
                 if (!(x23 >> 16)) xm ^= 8u;
+                if (R == 5) {
+                    const uint32_t mb = cur[2].u.x;
+                    const uint32_t sx4 = (t2 & mb) ^ mb;
+                    if (!(sx4 & 0xFFFFu)) reg_s1<R - 1, NA>(a, cur[FW + R - 1].d, xm);
+                    if (hx & 0x10000u) reg_h<R - 1, NA>(a, xm);
+                    if (!(sx4 >> 16)) xm ^= 16u;
+                }
                 continue;
             }
             if ((tid & cthr) != cthr) continue;   // a control on a thread bit is 0, or op inactive here
             double2 f = cur[1].d;
-            const uint32_t crm = (hx >> 8) & 0xFu, p0 = (hx >> 16) & 0xFFu;
-            switch (opc) {
-                case OPC_XS_0 + 0: reg_xswap<0>(a, crm, xm); break;
-                case OPC_XS_0 + 1: reg_xswap<1>(a, crm, xm); break;
-                case OPC_XS_0 + 2: reg_xswap<2>(a, crm, xm); break;
-                case OPC_XS_0 + 3: reg_xswap<3>(a, crm, xm); break;
-                case OPC_DS: {
+            const uint32_t crm = (hx >> 8) & 0x1Fu, p0 = (hx >> 16) & 0xFFu;
+            if (opc >= OPC_XS_0 && opc < OPC_XS_0 + 5) {
+                switch (opc - OPC_XS_0) {
+                    case 0: reg_xswap<0, NA>(a, crm, xm); break;
+                    case 1: reg_xswap<1, NA>(a, crm, xm); break;
+                    case 2: reg_xswap<2, NA>(a, crm, xm); break;
+                    case 3: reg_xswap<3, NA>(a, crm, xm); break;
+                    default: if (R == 5) reg_xswap<R - 1, NA>(a, crm, xm); break;
+                }
+                continue;
+            }
+            if (opc == OPC_DS) {
+                const uint32_t want = crm & ~xm;
+#pragma unroll
+                for (int p = 0; p < NA; ++p)
+                    if ((p & crm) == want) cmul_ip(a[p], f);
+                continue;
+            }
+            if (FULL) {
+                // rare shapes live in the FULL variant only: the lean kernel stays small for the I-cache
+                if (opc == OPC_DST) {
+                    f = cur[1 + ((tid >> p0) & 1u)].d;
                     const uint32_t want = crm & ~xm;
 #pragma unroll
-                    for (int p = 0; p < 16; ++p)
-                        if ((p & crm) == want) {
-                            QVM_NO_IFCVT();
-                            cmul_ip(a[p], f);
-                        }
-                    break;
+                    for (int p = 0; p < NA; ++p)
+                        if ((p & crm) == want) cmul_ip(a[p], f);
+                    continue;
                 }
-                default:
-                    if (FULL) {
-                        // rare shapes live in the FULL variant only: the lean kernel stays small for the I-cache
-                        if (opc == OPC_DST) {
-                            f = cur[1 + ((tid >> p0) & 1u)].d;
-                            const uint32_t want = crm & ~xm;
-#pragma unroll
-                            for (int p = 0; p < 16; ++p)
-                                if ((p & crm) == want) cmul_ip(a[p], f);
-                            break;
-                        }
-                        if (opc >= OPC_D1_0 && opc < OPC_D1_0 + 4) {
-                            switch (opc - OPC_D1_0) {
-                                case 0: reg_d1<0>(a, f, cur[2].d, crm, xm); break;
-                                case 1: reg_d1<1>(a, f, cur[2].d, crm, xm); break;
-                                case 2: reg_d1<2>(a, f, cur[2].d, crm, xm); break;
-                                default: reg_d1<3>(a, f, cur[2].d, crm, xm); break;
-                            }
-                            break;
-                        }
-                        const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(cur) + 8);
-                        const double2* mat = c.mats + v.x;
-                        if (opc == OPC_DIAG_G) {
-                            const ColdOp* cd = &c.cold[(v.y >> 8) & 0xFFFFu];        // DIAG_G keeps its cold index in w[23:8]
-                            const uint32_t kk = cd->k;
-                            uint32_t idx = v.y & 0xFFu;
-                            uint32_t rm0 = 0, rm1 = 0, rm2 = 0, rm3 = 0, rs0 = 0, rs1 = 0, rs2 = 0, rs3 = 0;
-                            for (uint32_t t = 0; t < kk; ++t) {
-                                const uint32_t loc = cd->loc[t];
-                                const uint32_t cls = loc & LOC_CLASS;
-                                const uint32_t sh = 1u << (kk - 1 - t);
-                                if (cls == LOC_THR) idx |= ((tid >> (loc & LOC_INDEX)) & 1u) ? sh : 0u;
-                                else if (cls == LOC_REG) {
-                                    const uint32_t slot = loc & LOC_INDEX;       // each slot appears at most once
-                                    if (slot == 0) { rm0 = 1u; rs0 = sh; }
-                                    else if (slot == 1) { rm1 = 2u; rs1 = sh; }
-                                    else if (slot == 2) { rm2 = 4u; rs2 = sh; }
-                                    else { rm3 = 8u; rs3 = sh; }
-                                }
-                            }
-                            const uint32_t want = crm & ~xm;
-#pragma unroll
-                            for (int p = 0; p < 16; ++p) {
-                                if ((p & crm) == want) {
-                                    const uint32_t j = (uint32_t)p ^ xm;         // logical slot
-                                    const uint32_t ij = idx | ((j & rm0) ? rs0 : 0u) | ((j & rm1) ? rs1 : 0u) |
-                                                        ((j & rm2) ? rs2 : 0u) | ((j & rm3) ? rs3 : 0u);
-                                    a[p] = cmul(QVM_LDG(&mat[ij]), a[p]);
-                                }
-                            }
-                        } else if (opc >= OPC_M1_0 && opc < OPC_M1_0 + 4) {
-                            switch (opc - OPC_M1_0) {
-                                case 0: reg_dense1<0>(a, mat, crm, xm); break;
-                                case 1: reg_dense1<1>(a, mat, crm, xm); break;
-                                case 2: reg_dense1<2>(a, mat, crm, xm); break;
-                                default: reg_dense1<3>(a, mat, crm, xm); break;
-                            }
-                        } else if (opc == OPC_M2_0) reg_dense2<0>(a, mat, crm, xm);
-                        else if (opc == OPC_M2_0 + 1) reg_dense2<1>(a, mat, crm, xm);
+                if (opc >= OPC_D1_0 && opc < OPC_D1_0 + 5) {
+                    switch (opc - OPC_D1_0) {
+                        case 0: reg_d1<0, NA>(a, f, cur[2].d, crm, xm); break;
+                        case 1: reg_d1<1, NA>(a, f, cur[2].d, crm, xm); break;
+                        case 2: reg_d1<2, NA>(a, f, cur[2].d, crm, xm); break;
+                        case 3: reg_d1<3, NA>(a, f, cur[2].d, crm, xm); break;
+                        default: if (R == 5) reg_d1<R - 1, NA>(a, f, cur[2].d, crm, xm); break;
                     }
-                    break;
+                    continue;
+                }
+                const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(cur) + 8);
+                const double2* mat = c.mats + v.x;
+                if (opc == OPC_DIAG_G) {
+                    const ColdOp* cd = &c.cold[(v.y >> 8) & 0xFFFFu];        // DIAG_G keeps its cold index in w[23:8]
+                    const uint32_t kk = cd->k;
+                    uint32_t idx = v.y & 0xFFu;
+                    uint32_t rs[R];          // index weight of the target on register slot s (0: none)
+#pragma unroll
+                    for (int s = 0; s < R; ++s) rs[s] = 0;
+                    for (uint32_t t = 0; t < kk; ++t) {
+                        const uint32_t loc = cd->loc[t];
+                        const uint32_t cls = loc & LOC_CLASS;
+                        const uint32_t sh = 1u << (kk - 1 - t);
+                        if (cls == LOC_THR) idx |= ((tid >> (loc & LOC_INDEX)) & 1u) ? sh : 0u;
+                        else if (cls == LOC_REG) {
+                            const uint32_t slot = loc & LOC_INDEX;       // each slot appears at most once
+#pragma unroll
+                            for (int s = 0; s < R; ++s)
+                                if (slot == (uint32_t)s) rs[s] = sh;
+                        }
+                    }
+                    const uint32_t want = crm & ~xm;
+#pragma unroll
+                    for (int p = 0; p < NA; ++p) {
+                        if ((p & crm) == want) {
+                            const uint32_t j = (uint32_t)p ^ xm;         // logical slot
+                            uint32_t ij = idx;
+#pragma unroll
+                            for (int s = 0; s < R; ++s) ij |= ((j >> s) & 1u) ? rs[s] : 0u;
+                            a[p] = cmul(QVM_LDG(&mat[ij]), a[p]);
+                        }
+                    }
+                } else if (opc >= OPC_M1_0 && opc < OPC_M1_0 + 5) {
+                    switch (opc - OPC_M1_0) {
+                        case 0: reg_dense1<0, NA>(a, mat, crm, xm); break;
+                        case 1: reg_dense1<1, NA>(a, mat, crm, xm); break;
+                        case 2: reg_dense1<2, NA>(a, mat, crm, xm); break;
+                        case 3: reg_dense1<3, NA>(a, mat, crm, xm); break;
+                        default: if (R == 5) reg_dense1<R - 1, NA>(a, mat, crm, xm); break;
+                    }
+                } else if (opc == OPC_M2_0) reg_dense2<0, NA>(a, mat, crm, xm);
+                else if (opc == OPC_M2_0 + 1) reg_dense2<1, NA>(a, mat, crm, xm);
             }
         }
     }
@@ -622,29 +646,27 @@ QVM_HD void rt_thread_round(const RtCta& c, const int r, const uint32_t tid, dou
         // signed strides (a set xm bit turns +stride into -stride); sums again, no per-element masking
         const uint64_t gT = (uint64_t)(T & low_mask) | c.hi_off[T >> c.low];
         char* p0 = reinterpret_cast<char*>(c.gbase + gT);
-        int64_t b0 = (int64_t)(16ull << (rw.y & 0xFFu)), b1 = (int64_t)(16ull << ((rw.y >> 8) & 0xFFu)),
-                b2 = (int64_t)(16ull << ((rw.y >> 16) & 0xFFu)), b3 = (int64_t)(16ull << (rw.y >> 24));
-        if (xm & 1u) { p0 += b0; b0 = -b0; }
-        if (xm & 2u) { p0 += b1; b1 = -b1; }
-        if (xm & 4u) { p0 += b2; b2 = -b2; }
-        if (xm & 8u) { p0 += b3; b3 = -b3; }
-        char* q[16];
-        q[0] = p0;
-        q[1] = p0 + b0;
-        q[2] = p0 + b1;
-        q[3] = q[1] + b1;
+        int64_t b[R];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) q[4 + j] = q[j] + b2;
+        for (int s = 0; s < R; ++s) {
+            b[s] = (int64_t)(16ull << rd->reg_phys[s]);
+            if ((xm >> s) & 1u) {
+                p0 += b[s];
+                b[s] = -b[s];
+            }
+        }
+        char* q[NA];
+        add_tree<R>(p0, b, q);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) q[8 + j] = q[j] + b3;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) *reinterpret_cast<double2*>(q[j]) = a[j];
+        for (int j = 0; j < NA; ++j) *reinterpret_cast<double2*>(q[j]) = a[j];
     } else {
         // same mapping as this round's load: every thread rewrites exactly the slots it read
-        const uint32_t sX = sT ^ ((xm & 1) ? s0 : 0) ^ ((xm & 2) ? s1 : 0) ^ ((xm & 4) ? s2 : 0) ^ ((xm & 8) ? s3 : 0);
+        uint32_t sX = sT;
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            c.tile[sX ^ ((j & 1) ? s0 : 0) ^ ((j & 2) ? s1 : 0) ^ ((j & 4) ? s2 : 0) ^ ((j & 8) ? s3 : 0)] = a[j];
+        for (int s = 0; s < R; ++s)
+            if ((xm >> s) & 1u) sX ^= st[s];
+#pragma unroll
+        for (int j = 0; j < NA; ++j) c.tile[sX ^ xor_combo<R>(st, j)] = a[j];
     }
 }
 
@@ -660,7 +682,7 @@ QVM_HD uint64_t rt_tile_base(const RegTileParams& P, uint64_t tile_index) {
 }
 
 #if defined(__CUDACC__)
-template <int MAX_THREADS, int MIN_BLOCKS, bool FULL>
+template <int MAX_THREADS, int MIN_BLOCKS, bool FULL, int R>
 __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
 regtile_kernel(double2* __restrict__ state, const RegTileParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -673,16 +695,6 @@ regtile_kernel(double2* __restrict__ state, const RegTileParams P) {
     const uint32_t nthreads = blockDim.x;
     const uint64_t base = rt_tile_base(P, blockIdx.x);
     const uint64_t full = base | P.shard_bits;
-
-// 1: issue round 0's tile load before the prologue.  Measured equal within noise on B200 (the other
-// resident CTAs already cover that latency), and it keeps 64 registers live through the prologue.
-#ifndef QVM_EARLY_LOAD
-#define QVM_EARLY_LOAD 0
-#endif
-    double2 a[16];
-#if QVM_EARLY_LOAD
-    rt_first_load(P, state + base, tid, a);
-#endif
 
     for (uint32_t j = tid; j < (uint32_t)P.n_ops; j += nthreads) rt_resolve_op(P, j, full, ops);
     if (tid == 0) ops[P.n_words].u = make_uint4(0, 0, 0, 0);          // the word the last prefetch reads
@@ -710,11 +722,10 @@ regtile_kernel(double2* __restrict__ state, const RegTileParams P) {
     c.cold = P.cold;
     c.low = P.low;
     c.n_rounds = P.n_rounds;
-#if !QVM_EARLY_LOAD
-    rt_first_load(P, state + base, tid, a);
-#endif
+    double2 a[1 << R];
+    rt_first_load<R>(P, state + base, tid, a);
     for (int r = 0; r < P.n_rounds; ++r) {
-        rt_thread_round<FULL>(c, r, tid, a);
+        rt_thread_round<FULL, R>(c, r, tid, a);
         if (r + 1 < P.n_rounds) __syncthreads();
     }
 }

@@ -13,13 +13,15 @@ import _emu  # noqa: E402
 from workloads import random_circuit_spec  # noqa: E402
 from referenceqvm import _engine, _planner, gates as G  # noqa: E402
 
-NAMES = {0: "X_RELABEL", 1: "H", 5: "XS", 9: "S1", 13: "DS", 14: "D1", 18: "DIAG_G", 19: "M1", 23: "M2", 25: "T", 26: "TG"}
+NAMES = {0: "X_RELABEL", 1: "H", 6: "S1", 11: "XS", 16: "DS", 17: "DST", 18: "D1", 23: "DIAG_G", 24: "M1", 29: "M2",
+         31: "T"}
 
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
     depth = int(sys.argv[2]) if len(sys.argv) > 2 else 40
     tile = int(sys.argv[3]) if len(sys.argv) > 3 else 12
+    reg_bits = int(sys.argv[4]) if len(sys.argv) > 4 else 4
     spec = random_circuit_spec(n, depth, 1234)
     ops = []
     for name, params, qubits in spec:
@@ -33,7 +35,7 @@ def main():
     layers = 0
     dirty = 0
     for g in groups:
-        psi, info = _emu.apply_group(psi, n, g.tile, g.ops)
+        psi, info = _emu.apply_group(psi, n, g.tile, g.ops, reg_bits=reg_bits)
         hist += info["opc_hist"]
         rounds += info["rounds"]
         layers += info["layers"]

@@ -31,12 +31,12 @@ def lib():
         h = C.CDLL(OUT)
         h.qvm_emu_apply_group.restype = C.c_int
         h.qvm_emu_apply_group.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_int,
-                                          C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+                                          C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
         _lib = h
     return _lib
 
 
-def apply_group(psi, n_local, tile_bits, ops, n_global=0, shard_index=0, force_full=False, encode_only=False):
+def apply_group(psi, n_local, tile_bits, ops, n_global=0, shard_index=0, force_full=False, reg_bits=4):
     """Run one fused group on a host vector through the emulated kernel.  Returns (psi', info)
     with info = dict(rounds, need_full, status, n_ops); status 1 = encoder asked for the fallback."""
     ops = [o for o in ops if o.kind != nat.OP_NOP]
@@ -57,6 +57,6 @@ def apply_group(psi, n_local, tile_bits, ops, n_global=0, shard_index=0, force_f
     info = np.zeros(38, dtype=np.int32)
     rc = lib().qvm_emu_apply_group(out.ctypes.data, n_local, n_global, shard_index, tb.size, tb.ctypes.data,
                                    len(ops), C.cast(arr, C.c_void_p), pool.ctypes.data, total,
-                                   1 if force_full else 0, info.ctypes.data)
+                                   1 if force_full else 0, reg_bits, info.ctypes.data)
     return out, {"rounds": int(info[0]), "need_full": bool(info[1]), "status": rc, "n_ops": int(info[3]),
                  "opc_hist": info[4:36].copy(), "layers": int(info[36]), "dirty_rounds": int(info[37])}

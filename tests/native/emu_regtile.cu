@@ -13,11 +13,31 @@
 
 using namespace qvm;
 
+// one tile: every round runs all threads one after another (the loop boundary is the barrier)
+template <int R>
+static void run_tile(const RegTileParams& P, const RtCta& c, const double2* gbase, unsigned threads, bool full_variant) {
+    constexpr int NA = 1 << R;
+    std::vector<double2> pre((size_t)threads * NA);          // round 0's amplitudes (loaded at kernel entry)
+    for (uint32_t tid = 0; tid < threads; ++tid) {
+        double2 a[NA];
+        rt_first_load<R>(P, gbase, tid, a);
+        memcpy(&pre[(size_t)tid * NA], a, sizeof(a));
+    }
+    for (int r = 0; r < P.n_rounds; ++r)
+        for (uint32_t tid = 0; tid < threads; ++tid) {
+            double2 a[NA];
+            if (r == 0) memcpy(a, &pre[(size_t)tid * NA], sizeof(a));
+            if (full_variant) rt_thread_round<true, R>(c, r, tid, a);
+            else rt_thread_round<false, R>(c, r, tid, a);
+        }
+}
+
 extern "C" int qvm_emu_apply_group(double* amps, int n_local, int n_global, uint64_t shard_index, int n_tile,
                                    const int32_t* tile_bits, int n_ops, const qvm_op_t* ops, const double* mats,
-                                   uint64_t mats_entries, int force_full, int* info /* 38 ints */) {
+                                   uint64_t mats_entries, int force_full, int reg_bits, int* info /* 38 ints */) {
     EncodedGroup g;
-    const int erc = encode_group(n_local, n_global, shard_index, n_tile, tile_bits, n_ops, ops, mats, mats_entries, g);
+    const int erc = encode_group(n_local, n_global, shard_index, n_tile, tile_bits, n_ops, ops, mats, mats_entries, g,
+                                 reg_bits);
     if (info) {
         info[0] = (int)g.rounds.size();
         info[1] = g.need_full ? 1 : 0;
@@ -55,20 +75,8 @@ extern "C" int qvm_emu_apply_group(double* amps, int n_local, int n_global, uint
         c.cold = P.cold;
         c.low = P.low;
         c.n_rounds = P.n_rounds;
-        // round 0's amplitudes are loaded at kernel entry on the device; per thread here
-        std::vector<double2> pre((size_t)g.threads * 16);
-        for (uint32_t tid = 0; tid < g.threads; ++tid) {
-            double2 a[16];
-            rt_first_load(P, state + base, tid, a);
-            memcpy(&pre[(size_t)tid * 16], a, sizeof(a));
-        }
-        for (int r = 0; r < P.n_rounds; ++r)
-            for (uint32_t tid = 0; tid < g.threads; ++tid) {
-                double2 a[16];
-                if (r == 0) memcpy(a, &pre[(size_t)tid * 16], sizeof(a));
-                if (full_variant) rt_thread_round<true>(c, r, tid, a);
-                else rt_thread_round<false>(c, r, tid, a);
-            }
+        if (P.R == 5) run_tile<5>(P, c, state + base, g.threads, full_variant);
+        else run_tile<4>(P, c, state + base, g.threads, full_variant);
     }
     return 0;
 }

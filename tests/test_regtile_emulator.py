@@ -22,10 +22,22 @@ def compile_spec(spec):
     return ops
 
 
+REG_BITS = 4      # overridden by the parametrised fixture below
+
+
+@pytest.fixture(autouse=True, params=[4, 5])
+def reg_bits(request):
+    """Every test of this file runs for 16 and for 32 amplitudes per thread."""
+    global REG_BITS
+    REG_BITS = request.param
+    yield request.param
+    REG_BITS = 4
+
+
 def run_emulated(psi, ops, n, tile_bits, low_bits, force_full=False):
     stats = {"groups": 0, "rounds": 0, "fallback": 0}
     for g in _planner.plan(ops, n, tile_bits, low_bits):
-        new, info = _emu.apply_group(psi, n, g.tile, g.ops, force_full=force_full)
+        new, info = _emu.apply_group(psi, n, g.tile, g.ops, force_full=force_full, reg_bits=REG_BITS)
         if info["status"] == 1:                 # outside the register-tile encoder: model the fallback
             stats["fallback"] += 1
             for op in g.ops:
@@ -134,7 +146,8 @@ def test_sharded_group_with_global_controls_and_diagonals():
                 want = apply_local(want, lop, n_local)
         psi = psi0
         for g in _planner.plan(ops, n_local, 10, 5):
-            psi, info = _emu.apply_group(psi, n_local, g.tile, g.ops, n_global=n_global, shard_index=shard)
+            psi, info = _emu.apply_group(psi, n_local, g.tile, g.ops, n_global=n_global, shard_index=shard,
+                                         reg_bits=REG_BITS)
             assert info["status"] == 0
         assert np.max(np.abs(psi - want)) < TOL, shard
 
