@@ -201,8 +201,8 @@ def main():
     ap.add_argument("--qubits", type=int, default=int(os.environ.get("QVM_BENCH_QUBITS", "33")))
     ap.add_argument("--depth", type=int, default=int(os.environ.get("QVM_BENCH_DEPTH", "40")))
     ap.add_argument("--shots", type=int, default=1000000)
-    ap.add_argument("--ref-qubits", type=int, default=18)
-    ap.add_argument("--ref-depth", type=int, default=2)
+    ap.add_argument("--ref-qubits", type=int, default=20)
+    ap.add_argument("--ref-depth", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
