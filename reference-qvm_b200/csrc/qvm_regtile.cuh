@@ -302,23 +302,30 @@ QVM_HD void rt_patch_op(const RegTileParams& P, uint32_t j, uint64_t full, OpWor
 // A register-slot control mask crm is tested on the logical index:
 //   ((p ^ xm) & crm) == crm  <=>  (p & crm) == (crm & ~xm) =: want.
 
-// Unnormalised Hadamard on slot B.  LO = physical half that holds logical 0.
-template <int B, int LO, int NA>
-QVM_HD void reg_h_half(double2 (&a)[NA]) {
-#pragma unroll
-    for (int p = 0; p < NA / 2; ++p) {
-        const int i0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1)) | (LO << B);     // logical 0
-        const int i1 = i0 ^ (1 << B);                                                // logical 1
-        a[i0].x += a[i1].x;
-        a[i0].y += a[i1].y;
-        a[i1].x = fma(-2.0, a[i1].x, a[i0].x);       // (l0 + l1) - 2 l1 = l0 - l1
-        a[i1].y = fma(-2.0, a[i1].y, a[i0].y);
-    }
+// Unnormalised Hadamard on slot B, in place and branch-free: a0 += a1; a1 = a0 - 2 a1 gives the
+// physical (sum, difference).  If the slot is relabelled (physical 0 holds logical 1) the logical
+// difference is the negated physical one: flip the sign bit of a1 and drop the relabel bit (the
+// caller clears it) -- one integer op per double instead of a divergent pair of code variants.
+QVM_HD double flip_sign(double v, uint32_t sign_bit) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(v) ^ (int)sign_bit, __double2loint(v));
+#else
+    return sign_bit ? -v : v;
+#endif
 }
 template <int B, int NA>
-QVM_HD void reg_h(double2 (&a)[NA], const uint32_t xm) {
-    if ((xm >> B) & 1u) reg_h_half<B, 1, NA>(a);
-    else reg_h_half<B, 0, NA>(a);
+QVM_HD void reg_h(double2 (&a)[NA], uint32_t& xm) {
+    const uint32_t sign_bit = ((xm >> B) & 1u) << 31;
+#pragma unroll
+    for (int p = 0; p < NA / 2; ++p) {
+        const int i0 = ((p >> B) << (B + 1)) | (p & ((1 << B) - 1));
+        const int i1 = i0 | (1 << B);
+        a[i0].x += a[i1].x;
+        a[i0].y += a[i1].y;
+        a[i1].x = flip_sign(fma(-2.0, a[i1].x, a[i0].x), sign_bit);       // (x0 + x1) - 2 x1 = x0 - x1
+        a[i1].y = flip_sign(fma(-2.0, a[i1].y, a[i0].y), sign_bit);
+    }
+    xm &= ~(1u << B);
 }
 
 template <int B, int NA>
