@@ -46,6 +46,9 @@
 #define QVM_HD inline
 #endif
 
+// absent sub-ops are the common case: keep their tests fall-through and the bodies out of line
+#define QVM_UNLIKELY(x) __builtin_expect(!!(x), 0)
+
 #if defined(__CUDA_ARCH__)
 #define QVM_LDG(p) __ldg(p)
 #else
@@ -541,23 +544,23 @@ QVM_HD void rt_thread_round(const RtCta& c, const int r, const uint32_t tid, dou
                 const uint32_t t2 = tid | (tid << 16);
                 const uint32_t s01 = (t2 & m.x) ^ m.x, s23 = (t2 & m.y) ^ m.y;
                 const uint32_t x01 = (t2 & m.z) ^ m.z, x23 = (t2 & m.w) ^ m.w;
-                if (!(s01 & 0xFFFFu)) reg_s1<0, NA>(a, cur[FW + 0].d, xm);
-                if (hx & 0x1000u) reg_h<0, NA>(a, xm);
+                if (QVM_UNLIKELY(!(s01 & 0xFFFFu))) reg_s1<0, NA>(a, cur[FW + 0].d, xm);
+                if (QVM_UNLIKELY(hx & 0x1000u)) reg_h<0, NA>(a, xm);
                 if (!(x01 & 0xFFFFu)) xm ^= 1u;
-                if (!(s01 >> 16)) reg_s1<1, NA>(a, cur[FW + 1].d, xm);
-                if (hx & 0x2000u) reg_h<1, NA>(a, xm);
+                if (QVM_UNLIKELY(!(s01 >> 16))) reg_s1<1, NA>(a, cur[FW + 1].d, xm);
+                if (QVM_UNLIKELY(hx & 0x2000u)) reg_h<1, NA>(a, xm);
                 if (!(x01 >> 16)) xm ^= 2u;
-                if (!(s23 & 0xFFFFu)) reg_s1<2, NA>(a, cur[FW + 2].d, xm);
-                if (hx & 0x4000u) reg_h<2, NA>(a, xm);
+                if (QVM_UNLIKELY(!(s23 & 0xFFFFu))) reg_s1<2, NA>(a, cur[FW + 2].d, xm);
+                if (QVM_UNLIKELY(hx & 0x4000u)) reg_h<2, NA>(a, xm);
                 if (!(x23 & 0xFFFFu)) xm ^= 4u;
-                if (!(s23 >> 16)) reg_s1<3, NA>(a, cur[FW + 3].d, xm);
-                if (hx & 0x8000u) reg_h<3, NA>(a, xm);
+                if (QVM_UNLIKELY(!(s23 >> 16))) reg_s1<3, NA>(a, cur[FW + 3].d, xm);
+                if (QVM_UNLIKELY(hx & 0x8000u)) reg_h<3, NA>(a, xm);
                 if (!(x23 >> 16)) xm ^= 8u;
                 if (R == 5) {
                     const uint32_t mb = cur[2].u.x;
                     const uint32_t sx4 = (t2 & mb) ^ mb;
-                    if (!(sx4 & 0xFFFFu)) reg_s1<R - 1, NA>(a, cur[FW + R - 1].d, xm);
-                    if (hx & 0x10000u) reg_h<R - 1, NA>(a, xm);
+                    if (QVM_UNLIKELY(!(sx4 & 0xFFFFu))) reg_s1<R - 1, NA>(a, cur[FW + R - 1].d, xm);
+                    if (QVM_UNLIKELY(hx & 0x10000u)) reg_h<R - 1, NA>(a, xm);
                     if (!(sx4 >> 16)) xm ^= 16u;
                 }
                 continue;

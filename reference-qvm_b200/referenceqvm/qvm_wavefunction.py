@@ -40,6 +40,9 @@ def _index_bits(indices):
     return np.unpackbits(by, axis=1, bitorder="little")
 
 
+_SWAP = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
+
+
 class QVM_Wavefunction(QAM):
     """Supports run(), run_and_measure() and wavefunction()."""
 
@@ -54,6 +57,10 @@ class QVM_Wavefunction(QAM):
         self.device = int(os.environ.get("QVM_B200_DEVICE", "0"))
         #: set False to force the reference's per-trial re-simulation in run()/run_and_measure()
         self.sampling_fast_path = True
+        #: SWAP gates are not executed: they exchange two entries of this program-qubit -> engine-qubit
+        #: table, and later instructions are routed through it.  The table is undone (with real SWAPs)
+        #: only when amplitudes are read back; MEASURE and sampling just look bits up through it.
+        self._virt = []
 
     # -- device state --------------------------------------------------------------------------
     def _fresh_engine(self):
@@ -64,7 +71,25 @@ class QVM_Wavefunction(QAM):
         if self._engine is None:
             self._engine = self._make_engine(self.num_qubits)
         self._engine.reset()
+        self._virt = list(range(self.num_qubits))
         return self._engine
+
+    def _materialise_swaps(self):
+        """Bring the engine state back to program-qubit order (real SWAP gates, then identity table)."""
+        virt = self._virt
+        if virt == list(range(len(virt))):
+            return
+        # engine qubit virt[q] currently plays program qubit q; sort by transpositions
+        holder = {e: q for q, e in enumerate(virt)}          # engine qubit -> program qubit it plays
+        for q in range(len(virt)):
+            e = virt[q]
+            if e == q:
+                continue
+            other = holder[q]                                 # program qubit currently played by engine qubit q
+            self._engine.queue_matrix(_SWAP, [e, q])          # after this engine qubit q plays program qubit q
+            virt[q], virt[other] = q, e
+            holder[q], holder[e] = q, other
+        assert virt == list(range(len(virt)))
 
     def _make_engine(self, n):
         return _engine.make_engine(n, device=self.device)
@@ -74,6 +99,7 @@ class QVM_Wavefunction(QAM):
         """Host copy of the amplitudes (the reference keeps ``self.wf`` as an ndarray)."""
         if self._engine is None:
             return None
+        self._materialise_swaps()
         return self._engine.amplitudes()
 
     @wf.setter
@@ -90,6 +116,7 @@ class QVM_Wavefunction(QAM):
                 self._engine.close()
             self._engine = self._make_engine(n)
         self._engine.set_amplitudes(amplitudes)
+        self._virt = list(range(n))
 
     # -- transitions -----------------------------------------------------------------------------
     def measurement(self, qubit_index, psi=None):
@@ -100,7 +127,7 @@ class QVM_Wavefunction(QAM):
         signature compatibility: a host vector is uploaded first."""
         if psi is not None:
             self.wf = psi
-        return self._engine.measure(qubit_index, np.random.random())
+        return self._engine.measure(self._virt[qubit_index], np.random.random())
 
     def _transition(self, instruction):
         if isinstance(instruction, Measurement):
@@ -109,7 +136,12 @@ class QVM_Wavefunction(QAM):
             self.program_counter += 1
         elif isinstance(instruction, Gate):
             matrix, qubits = resolve_gate(self.gate_set, self.defgate_set, instruction)
-            self._engine.queue_matrix(matrix, qubits)
+            _engine.validate_qubits(qubits, self.num_qubits)
+            if len(qubits) == 2 and matrix.shape == (4, 4) and np.array_equal(matrix, _SWAP):
+                a, b = qubits                                   # a relabel, not a pass over the state
+                self._virt[a], self._virt[b] = self._virt[b], self._virt[a]
+            else:
+                self._engine.queue_matrix(matrix, [self._virt[q] for q in qubits])
             self.program_counter += 1
         elif not self._classical_transition(instruction):
             raise self._unsupported(instruction)
@@ -156,6 +188,7 @@ class QVM_Wavefunction(QAM):
         mask = self._simulate(pyquil_program, classical_addresses)
         memory = self.classical_memory if mask is None else self.classical_memory[mask]
         results = [int(x) for x in memory]
+        self._materialise_swaps()
         if self.num_qubits > LAZY_QUBITS:
             self._engine.flush()
             return Wavefunction(_engine.DeviceAmplitudes(self._engine)), results
@@ -197,7 +230,7 @@ class QVM_Wavefunction(QAM):
         bits = _index_bits(indices)
         for instr in list(pyquil_program)[split:]:
             q, c = value_get(instr.qubit), value_get(instr.classical_reg)
-            memory[:, c] = bits[:, q]
+            memory[:, c] = bits[:, self._virt[q]]
         self.program_counter = len(self.program)
         self.classical_memory = memory[-1].copy()
         picked = memory if mask is None else memory[:, mask]
@@ -220,7 +253,7 @@ class QVM_Wavefunction(QAM):
             indices, _ = self._engine.sample(np.random.random_sample(trials))
             bits = _index_bits(indices)
             # bit 63 is never set (q_limit = 51): it stands in for qubits beyond the register
-            sel = [q if 0 <= q < self.num_qubits else 63 for q in qubits]
+            sel = [self._virt[q] if 0 <= q < self.num_qubits else 63 for q in qubits]
             return bits[:, sel].tolist()
 
         results = []
@@ -229,7 +262,7 @@ class QVM_Wavefunction(QAM):
             trial_results = []
             for qubit_index in qubits:
                 if qubit_index < self.num_qubits:
-                    measured_val, _ = self._engine.measure(qubit_index, np.random.random())
+                    measured_val, _ = self._engine.measure(self._virt[qubit_index], np.random.random())
                 else:
                     measured_val = 0
                 trial_results.append(measured_val)

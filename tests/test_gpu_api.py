@@ -479,3 +479,41 @@ def test_density_config2_shape_vs_oracle():
     got = np.asarray(rho.todense())
     assert np.max(np.abs(got - orc.vec_to_rho(vec, n))) < TOL
     assert abs(np.trace(got) - 1.0) < 1e-12
+
+
+def test_swap_gates_are_relabels_with_identical_results(qvm):
+    """SWAP instructions never touch the amplitudes (the QVM routes later gates, MEASURE and sampling
+    through a program-qubit -> engine-qubit table); every observable result must equal the oracle's."""
+    from pyquil.gates import CNOT, H, MEASURE, RY, SWAP, X
+    n = 6
+    prog = Program(X(0), H(1), SWAP(0, 3), CNOT(1, 4), SWAP(1, 5), RY(0.7, 2), SWAP(2, 3), SWAP(0, 5), CNOT(3, 0),
+                   SWAP(4, 1))
+    ops = []
+    for ins in prog:
+        m = G.gate_matrix[ins.name]
+        ops.append(("gate", np.asarray(m(*ins.params) if ins.params else m, dtype=complex),
+                    [q.index if hasattr(q, "index") else q for q in ins.qubits]))
+    want, _ = orc.fast_run_wavefunction(ops, n)
+    wf, _ = qvm.wavefunction(prog)
+    assert np.max(np.abs(wf.amplitudes - want)) < 1e-12
+    passes_with_readback = qvm._engine.stats()["hbm_passes"]
+    # MEASURE after swaps: deterministic bits (X(0) travels 0 -> 3 -> 2, then CNOT(3,0) does nothing ...)
+    probs = np.abs(want) ** 2
+    mprog = Program().inst(prog)
+    for q in range(n):
+        mprog.measure(q, [q])
+    np.random.seed(5)
+    _, mem = qvm.wavefunction(mprog, list(range(n)))
+    rng = np.random.RandomState(5)
+    _, cmem = orc.fast_run_wavefunction(ops + [("measure", q, q) for q in range(n)], n, rng)
+    assert mem == [cmem[q] for q in range(n)]
+    # sampling fast path honours the relabelling and the caller's qubit order
+    np.random.seed(6)
+    order = [5, 0, 3, 2, 4, 1, 9]
+    shots = np.asarray(qvm.run_and_measure(prog, order, trials=4000))
+    u = np.random.RandomState(6).random_sample(4000)
+    # the engine samples in ENGINE index order: compare distributions, not streams
+    idx = sum(shots[:, j].astype(np.int64) << q for j, q in enumerate(order) if q < n)
+    freq = np.bincount(idx, minlength=1 << n) / 4000.0
+    assert np.max(np.abs(freq - probs)) < 0.05 and not shots[:, -1].any()
+    assert passes_with_readback >= 1
