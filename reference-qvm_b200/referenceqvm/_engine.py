@@ -31,6 +31,32 @@ def compile_gate(matrix, qubits):
     return op
 
 
+def expand_op(op):
+    """Cheaper equivalents of a classified op, in execution order.
+
+    A two-target diagonal d = (d00, d01, d10, d11) without zero entries factorises exactly into
+    diag(d00, d01) on the low target, diag(1, d10/d00) on the high target and the doubly controlled
+    scalar d11 d00 / (d01 d10).  Those are the kernel's cheapest op shapes (a per-thread scalar, or
+    8 multiplies on one register slot), whereas a general two-target diagonal may need the generic
+    table-driven handler.  Dephasing superoperators diag(1, f, f, 1) on (q+n, q) -- n of them after
+    every instruction of a noisy density run (reference qvm_density.py:298-313) -- are the main user."""
+    if op.kind != nat.OP_DIAG or len(op.targets) != 2:
+        return (op,)
+    d00, d01, d10, d11 = op.mat
+    if d00 == 0 or d01 == 0 or d10 == 0 or d11 == 0:
+        return (op,)
+    hi, lo = op.targets
+    out = [nat.ClassifiedOp(nat.OP_DIAG, (lo,), op.ctrl_mask, np.array([d00, d01], dtype=np.complex128))]
+    r = d10 / d00
+    if r != 1:
+        out.append(nat.ClassifiedOp(nat.OP_DIAG, (hi,), op.ctrl_mask, np.array([1.0, r], dtype=np.complex128)))
+    c = d11 * d00 / (d01 * d10)
+    if c != 1:
+        out.append(nat.ClassifiedOp(nat.OP_DIAG, (), op.ctrl_mask | (1 << hi) | (1 << lo),
+                                    np.array([c], dtype=np.complex128)))
+    return tuple(out)
+
+
 def validate_qubits(qubits, n_positions):
     """Index checks of the reference's permutation_arbitrary (unitary_generator.py:200-203);
     duplicates are rejected too (the reference's duplicate check :205-208 is dead code and a
@@ -114,7 +140,7 @@ class Engine(object):
     def queue(self, op):
         self.gates_queued += 1
         if op.kind != nat.OP_NOP:
-            self.pending.append(op)
+            self.pending.extend(expand_op(op))
 
     def flush(self):
         if not self.pending:

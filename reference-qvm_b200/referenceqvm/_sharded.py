@@ -23,7 +23,7 @@ import numpy as np
 
 from referenceqvm import _native as nat
 from referenceqvm import _planner
-from referenceqvm._engine import _LOW_BITS, _TILE_BITS, compile_gate, validate_qubits
+from referenceqvm._engine import _LOW_BITS, _TILE_BITS, compile_gate, expand_op, validate_qubits
 
 _context = None      # set by enable(); consulted by _engine.make_engine()
 
@@ -280,7 +280,7 @@ class ShardedEngine(object):
     def queue(self, op):
         self.gates_queued += 1
         if op.kind != nat.OP_NOP:
-            self.pending.append(op)
+            self.pending.extend(expand_op(op))
 
     def flush(self):
         """Run every queued gate.  Ops whose dense targets are all local run in fused batches; an op

@@ -152,6 +152,26 @@ def test_sharded_group_with_global_controls_and_diagonals():
         assert np.max(np.abs(psi - want)) < TOL, shard
 
 
+def test_expanded_two_target_diagonals():
+    """_engine.expand_op: diag(d00..d11) -> two 1-qubit diagonals + a doubly controlled scalar."""
+    rs = np.random.RandomState(3)
+    n = 12
+    mats = [(G.H, [q]) for q in range(n)]
+    for a, b in ((0, 11), (11, 0), (5, 6), (3, 9), (10, 2)):
+        d = np.diag(rs.standard_normal(4) + 1j * rs.standard_normal(4))
+        mats += [(d, [a, b]), (G.H, [a]), (np.diag([1, 0.9, 0.9, 1]), [b, a]), (G.CPHASE00(0.4), [a, b])]
+    ops = []
+    for m, q in mats:
+        ops.extend(_engine.expand_op(_engine.compile_gate(m, q)))
+    assert len(ops) > len(mats)
+    psi0 = random_state(n, 8)
+    want = psi0
+    for m, q in mats:
+        want = orc.fast_apply_gate(want, np.asarray(m, dtype=complex), q, n)
+    got, _ = run_emulated(psi0, ops, n, 12, 5)
+    assert np.max(np.abs(got - want)) / np.max(np.abs(want)) < TOL
+
+
 def test_density_style_superoperators():
     """Non-unitary 4x4 Kraus superoperators and conj(U) pairs as the density QVM queues them."""
     from referenceqvm.qvm_density import kraus_superoperator
