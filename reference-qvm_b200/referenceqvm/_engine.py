@@ -57,6 +57,46 @@ def expand_op(op):
     return tuple(out)
 
 
+class DiagonalMerger(object):
+    """Peephole over a pending op list: an uncontrolled one-qubit diagonal (or a controlled scalar)
+    is multiplied into the previous one on the same qubit (same control set) when no dense gate on
+    those qubits was queued in between -- everything in between then commutes with it.  Noisy density
+    runs queue the same dephasing factors on every qubit after every instruction; this keeps one op
+    per qubit per stretch instead of one per instruction.  Factors are multiplied on the host (one
+    rounding per merge, ~1e-16)."""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self._d1 = {}        # target position -> index in pending of the last mergeable diag(d0, d1)
+        self._cc = {}        # control mask -> index in pending of the last mergeable controlled scalar
+
+    def absorb(self, pending, op):
+        """True when ``op`` was merged into ``pending`` (nothing to append)."""
+        if op.kind == nat.OP_DENSE:
+            for t in op.targets:
+                self._d1.pop(t, None)
+                for mask in [m for m in self._cc if (m >> t) & 1]:
+                    del self._cc[mask]
+            return False
+        if op.kind != nat.OP_DIAG:
+            return False
+        if len(op.targets) == 1 and not op.ctrl_mask:
+            table, key = self._d1, op.targets[0]
+        elif not op.targets and op.ctrl_mask:
+            table, key = self._cc, op.ctrl_mask
+        else:
+            return False
+        i = table.get(key)
+        if i is None:
+            table[key] = len(pending)
+            return False
+        prev = pending[i]
+        pending[i] = nat.ClassifiedOp(prev.kind, prev.targets, prev.ctrl_mask, prev.mat * op.mat)
+        return True
+
+
 def validate_qubits(qubits, n_positions):
     """Index checks of the reference's permutation_arbitrary (unitary_generator.py:200-203);
     duplicates are rejected too (the reference's duplicate check :205-208 is dead code and a
@@ -80,6 +120,7 @@ class Engine(object):
         self.low_bits = _LOW_BITS if low_bits is None else low_bits
         self.state = nat.DeviceState(self.n, device) if _state is None else _state
         self.pending = []
+        self._merger = DiagonalMerger()
         self.gates_queued = 0
         self.groups_launched = 0
 
@@ -91,6 +132,7 @@ class Engine(object):
     # -- lifetime ----------------------------------------------------------------------------
     def close(self):
         self.pending = []
+        self._merger.reset()
         if self.state is not None:
             self.state.close()
             self.state = None
@@ -99,16 +141,19 @@ class Engine(object):
         """Replace the state buffer (same shape) -- used by the density QVM's ``_density`` setter."""
         assert device_state.n_local == self.n
         self.pending = []
+        self._merger.reset()
         self.state.close()
         self.state = device_state
 
     # -- state -------------------------------------------------------------------------------
     def reset(self):
         self.pending = []
+        self._merger.reset()
         self.state.reset_zero(True)
 
     def set_amplitudes(self, amplitudes):
         self.pending = []
+        self._merger.reset()
         a = np.asarray(amplitudes).reshape(-1)
         if a.size != (1 << self.n):
             raise ValueError("state of %d amplitudes does not match %d positions" % (a.size, self.n))
@@ -140,9 +185,12 @@ class Engine(object):
     def queue(self, op):
         self.gates_queued += 1
         if op.kind != nat.OP_NOP:
-            self.pending.extend(expand_op(op))
+            for piece in expand_op(op):
+                if not self._merger.absorb(self.pending, piece):
+                    self.pending.append(piece)
 
     def flush(self):
+        self._merger.reset()
         if not self.pending:
             return
         ops, self.pending = self.pending, []

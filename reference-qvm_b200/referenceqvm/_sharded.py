@@ -23,7 +23,7 @@ import numpy as np
 
 from referenceqvm import _native as nat
 from referenceqvm import _planner
-from referenceqvm._engine import _LOW_BITS, _TILE_BITS, compile_gate, expand_op, validate_qubits
+from referenceqvm._engine import _LOW_BITS, _TILE_BITS, DiagonalMerger, compile_gate, expand_op, validate_qubits
 
 _context = None      # set by enable(); consulted by _engine.make_engine()
 
@@ -196,6 +196,7 @@ class ShardedEngine(object):
             self._token = self.shard.scalar_tensor([0.0])
         self.pos_of = list(range(self.n))         # logical qubit -> physical position
         self.pending = []                         # ClassifiedOps in LOGICAL coordinates
+        self._merger = DiagonalMerger()
         self.gates_queued = 0
         self.groups_launched = 0
         self.swaps = 0
@@ -211,6 +212,7 @@ class ShardedEngine(object):
 
     def close(self):
         self.pending = []
+        self._merger.reset()
         self._send = self._recv = None
         if self.shard is not None:
             self.shard.close()
@@ -218,6 +220,7 @@ class ShardedEngine(object):
 
     def reset(self):
         self.pending = []
+        self._merger.reset()
         self.pos_of = list(range(self.n))
         self.shard.reset_zero(self.ctx.rank == 0)
 
@@ -227,6 +230,7 @@ class ShardedEngine(object):
         if a.size != (1 << self.n):
             raise ValueError("state size mismatch")
         self.pending = []
+        self._merger.reset()
         self.pos_of = list(range(self.n))
         lo = self.ctx.rank << self.n_local
         self.shard.set_state(a[lo:lo + (1 << self.n_local)])
@@ -280,13 +284,16 @@ class ShardedEngine(object):
     def queue(self, op):
         self.gates_queued += 1
         if op.kind != nat.OP_NOP:
-            self.pending.extend(expand_op(op))
+            for piece in expand_op(op):
+                if not self._merger.absorb(self.pending, piece):
+                    self.pending.append(piece)
 
     def flush(self):
         """Run every queued gate.  Ops whose dense targets are all local run in fused batches; an op
         with a dense target on a global position blocks (with everything that depends on it) until an
         exchange epoch brings all currently wanted global qubits in -- one multi-bit swap per epoch
         instead of one swap (and one broken batch) per gate."""
+        self._merger.reset()
         if not self.pending:
             return
         ops, self.pending = self.pending, []

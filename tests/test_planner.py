@@ -91,3 +91,36 @@ def test_headline_circuit_fuses_well():
 def test_dense_target_outside_register_is_rejected():
     with pytest.raises(ValueError):
         _planner.plan([_engine.compile_gate(G.H, [5])], 4, 12, 5)
+
+
+def test_diagonal_merger_is_exact_up_to_rounding():
+    """Engine.queue's peephole: repeated one-qubit diagonals / controlled scalars on the same qubits
+    merge unless a dense gate on them intervenes; the merged stream equals the original."""
+    rs = np.random.RandomState(4)
+    n = 6
+    mats = []
+    for rep in range(5):
+        for q in range(n):
+            mats.append((np.diag([1.0, 0.97 + 0.01 * q]), [q]))
+        mats.append((np.diag([1, 0.9, 0.9, 1]), [1, 4]))
+        mats.append((G.CPHASE(0.3 * (rep + 1)), [0, 5]))
+        if rep % 2:
+            mats.append((G.H, [rep]))
+            mats.append((G.CNOT, [2, 4]))
+    merger = _engine.DiagonalMerger()
+    pending = []
+    raw = 0
+    for m, q in mats:
+        for piece in _engine.expand_op(_engine.compile_gate(m, q)):
+            raw += 1
+            if not merger.absorb(pending, piece):
+                pending.append(piece)
+    assert len(pending) < raw / 2
+    psi0 = random_state(n, 2)
+    want = psi0
+    for m, q in mats:
+        want = orc.fast_apply_gate(want, np.asarray(m, dtype=complex), q, n)
+    got = psi0
+    for op in pending:
+        got = apply_op(got, op, n)
+    assert np.max(np.abs(got - want)) < 1e-14
