@@ -65,6 +65,8 @@ typedef struct qvm_stats {
     uint64_t h2d_bytes;
     uint64_t d2h_bytes;
     uint64_t regtile_rounds;              /* register-tile rounds run by those launches            */
+    uint64_t jit_launches;                /* launches that ran a specialised (NVRTC-built) kernel  */
+    uint64_t jit_compiles;                /* group structures submitted for compilation (process)  */
 } qvm_stats_t;
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
@@ -85,6 +87,18 @@ int qvm_set_stream(qvm_t* q, void* cuda_stream);
 int qvm_set_tile_bits(qvm_t* q, int tile_bits, int low_bits);   /* tuning: defaults 12 / 5      */
 /* 1 (default): register-tiled kernel where eligible; 0: shared-memory kernel only (testing).   */
 int qvm_set_kernel_path(qvm_t* q, int use_regtile);
+/* Specialised kernels for recurring group structures (NVRTC, cached by structure; new angles reuse
+ * them): 0 never, 1 (default) compile a structure in the background from its second sighting on, 2 at
+ * first sight, synchronously.  The interpreted kernel runs whatever has no ready kernel.  Env QVM_B200_JIT overrides the default. */
+int qvm_set_jit(qvm_t* q, int policy);
+/* Block until every background compilation has finished (benchmarks: once, after warm-up). */
+int qvm_jit_wait(void);
+/* Diagnostics (no device needed): encode the group, generate its specialised source and compile it to
+ * an sm_100a cubin with NVRTC.  0 = compiled, 1 = this group is left to the interpreter, < 0 = the
+ * generated source failed to compile (`log` receives the NVRTC log). */
+int qvm_spec_compile_check(int n_local, int n_global, uint64_t shard_index, int n_tile, const int32_t* tile_bits,
+                           int n_ops, const qvm_op_t* ops, const double* mats, uint64_t mats_entries, char* log,
+                           uint64_t log_cap);
 /* Debug: how many ops of each register-tile opcode were encoded so far (32 counters). */
 int qvm_debug_opcode_hist(qvm_t* q, uint64_t* out32);
 int qvm_n_local(const qvm_t* q);

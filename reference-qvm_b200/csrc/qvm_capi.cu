@@ -5,6 +5,8 @@
 #include "qvm_kernels.cuh"
 #include "qvm_regtile.cuh"
 #include "qvm_encode.h"
+#include "qvm_jit.h"
+#include "qvm_regtile_src.inc"
 
 #include <algorithm>
 #include <cmath>
@@ -76,6 +78,8 @@ struct qvm_state {
     qvm_stats_t stats{};
     uint64_t opc_hist[32] = {};
     EncodedGroup enc;                 // scratch of the register-tile encoder (reused across launches)
+    SpecSource spec;                  // scratch of the specialised-kernel generator
+    int jit_policy = 1;               // 0 never, 1 compile a group structure at its second sighting, 2 at once
 };
 
 namespace {
@@ -401,6 +405,34 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
     if (g.n_tiles > 0x7fffffffull) return fail(QVM_ERR_UNSUPPORTED, "too many tiles for one launch");
     for (int i = 0; i < 32; ++i) q->opc_hist[i] += g.opc_hist[i];
 
+    // a structure that has been seen before runs as a specialised straight-line kernel (qvm_jit.h)
+    if (q->jit_policy > 0 && !g.need_full && g.P.R == 4 && generate_spec(g, q->spec)) {
+        const CompiledSpec* cs = SpecCache::instance().get(q->spec.src, q->jit_policy, q->device);
+        q->stats.jit_compiles = (uint64_t)SpecCache::instance().compiles();
+        if (cs) {
+            const SpecSource& ss = q->spec;
+            if (ss.smem > 48 * 1024 && const_cast<CompiledSpec*>(cs)->smem_attr < ss.smem) {
+                QVM_CUDA(q, cudaFuncSetAttribute((const void*)cs->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)ss.smem));
+                const_cast<CompiledSpec*>(cs)->smem_attr = ss.smem;
+            }
+            double2* amps = q->amps;
+            SpecParams sp = ss.params;
+            void* args[3] = {&amps, &sp, const_cast<double*>(ss.factors.data())};
+            QVM_CUDA(q, cudaLaunchKernel((const void*)cs->kernel, dim3((unsigned)g.n_tiles), dim3(ss.threads), args, ss.smem,
+                                         q->stream));
+            q->stats.kernel_launches += 1;
+            q->stats.jit_launches += 1;
+            q->stats.gate_ops += (uint64_t)g.n_gate_ops;
+            q->stats.hbm_passes += 1;
+            q->stats.hbm_bytes += 32ull * q->n_elems;
+            q->stats.h2d_bytes += ss.factors.size() * sizeof(double);
+            q->stats.regtile_rounds += (uint64_t)g.rounds.size();
+            *handled = true;
+            return QVM_OK;
+        }
+    }
+
     const size_t rounds_bytes = (g.rounds.size() * sizeof(RoundDesc) + 255) & ~(size_t)255;
     const size_t hot_bytes = (g.hot.size() * sizeof(uint4) + 255) & ~(size_t)255;
     const size_t cold_bytes = (g.cold.size() * sizeof(ColdOp) + 255) & ~(size_t)255;
@@ -514,6 +546,7 @@ static int create_impl(int n_local, int device, void* external, qvm_t** out) {
     q->n_local = n_local;
     q->n_elems = 1ull << n_local;
     if (const char* rb = getenv("QVM_B200_REG_BITS")) q->reg_bits = atoi(rb) == 5 ? 5 : 4;      // A/B runs
+    if (const char* jp = getenv("QVM_B200_JIT")) q->jit_policy = std::max(0, std::min(2, atoi(jp)));
 #define QVM_CREATE_CUDA(expr)                                                                          \
     do {                                                                                               \
         cudaError_t _e = (expr);                                                                       \
@@ -603,6 +636,37 @@ int qvm_set_tile_bits(qvm_t* q, int tile_bits, int low_bits) {
         return fail(QVM_ERR_INVALID, "bad tile configuration (%d, %d)", tile_bits, low_bits);
     q->tile_bits = tile_bits;
     q->low_bits = low_bits;
+    return QVM_OK;
+}
+
+int qvm_spec_compile_check(int n_local, int n_global, uint64_t shard_index, int n_tile, const int32_t* tile_bits,
+                           int n_ops, const qvm_op_t* ops, const double* mats, uint64_t mats_entries, char* log,
+                           uint64_t log_cap) {
+    if (log && log_cap) log[0] = 0;
+    if ((n_tile && !tile_bits) || (n_ops && !ops)) return fail(QVM_ERR_INVALID, "null pointer");
+    EncodedGroup g;
+    SpecSource ss;
+    if (encode_group(n_local, n_global, shard_index, n_tile, tile_bits, n_ops, ops, mats, mats_entries, g, 4) != ENC_OK ||
+        !generate_spec(g, ss))
+        return 1;
+    std::vector<char> cubin;
+    std::string err;
+    if (!SpecCache::instance().to_cubin(ss.src, cubin, &err)) {
+        if (log && log_cap) snprintf(log, (size_t)log_cap, "%s", err.c_str());
+        return fail(QVM_ERR_UNSUPPORTED, "specialised kernel did not compile: %.300s", err.c_str());
+    }
+    return QVM_OK;
+}
+
+int qvm_jit_wait(void) {
+    SpecCache::instance().wait_idle();
+    return QVM_OK;
+}
+
+int qvm_set_jit(qvm_t* q, int policy) {
+    QVM_CHECK_HANDLE(q);
+    if (policy < 0 || policy > 2) return fail(QVM_ERR_INVALID, "JIT policy must be 0, 1 or 2");
+    q->jit_policy = policy;
     return QVM_OK;
 }
 

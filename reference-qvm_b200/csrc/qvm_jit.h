@@ -1,0 +1,431 @@
+// Specialised kernels for fused groups that come back: the interpreter of qvm_regtile.cuh spends most
+// of its time on control flow (profiles/README.md), so a group whose *structure* has been seen before
+// is turned into straight-line CUDA source -- the very same device functions (reg_h, reg_s1,
+// cmul_ip, add_tree ...) called with compile-time slots, masks and strides, the complex factors
+// passed at launch time through the kernel-parameter constant bank -- compiled for sm_100a with
+// NVRTC and cached by source text.  New angles on an old structure reuse the kernel.
+//
+// Policy (QVM_B200_JIT): 0 = never, 1 (default) = compile a structure in the background when it shows
+// up for the second time (the interpreter keeps serving it until the kernel is ready), 2 = compile at
+// first sight and wait for it.  The interpreted kernel stays the path for everything that
+// is new, that NVRTC cannot build (library missing) or that the generator does not cover (FULL
+// groups): this is a GPU path selection, never a CPU fallback.
+#pragma once
+#include <dlfcn.h>
+
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "qvm_encode.h"
+
+namespace qvm {
+
+struct SpecParams {
+    int n_runs;
+    uint64_t shard_bits, run_start, run_len;
+};
+
+struct SpecSource {
+    std::string src;                 // the whole translation unit (without the embedded header)
+    std::vector<double> factors;     // launch-time values of F.v[]
+    unsigned threads = 0;
+    size_t smem = 0;
+    uint64_t n_tiles = 0;
+    SpecParams params{};
+};
+
+namespace specgen {
+
+inline std::string hexu(uint64_t v) {
+    char buf[32];
+    snprintf(buf, sizeof(buf), "0x%llxull", (unsigned long long)v);
+    return buf;
+}
+inline std::string outer_cond(uint64_t co) { return co ? "((full & " + hexu(co) + ") == " + hexu(co) + ")" : ""; }
+inline std::string thr_cond(uint32_t cthr) {
+    char buf[64];
+    if (!cthr) return "";
+    snprintf(buf, sizeof(buf), "((tid & 0x%xu) == 0x%xu)", cthr, cthr);
+    return buf;
+}
+inline std::string both(const std::string& a, const std::string& b) {
+    if (a.empty()) return b;
+    if (b.empty()) return a;
+    return a + " && " + b;
+}
+inline std::string oi_expr(const ColdOp& c) {
+    std::string e;
+    for (int t = 0; t < c.k; ++t)
+        if ((c.loc[t] & LOC_CLASS) == LOC_OUT) {
+            char buf[96];
+            snprintf(buf, sizeof(buf), "(((uint32_t)(full >> %d) & 1u) << %d)", c.loc[t] & LOC_INDEX, c.k - 1 - t);
+            e += (e.empty() ? "" : " | ") + std::string(buf);
+        }
+    return e.empty() ? "0u" : "(" + e + ")";
+}
+
+}  // namespace specgen
+
+// Source for one encoded group (lean R = 4 groups only).  Factors never appear as literals: F.v[i]
+// indexes a by-value kernel argument -- first the encoder's matrix pool, then the factors the encoder
+// inlined into the op stream, then the round scalars.
+inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
+    using namespace specgen;
+    const RegTileParams& P = g.P;
+    if (g.cold.empty() || g.need_full || P.R != 4) return false;
+    std::vector<double>& F = out.factors;
+    F.assign(g.pool.begin(), g.pool.end());
+    auto fconst = [&](double re, double im) -> std::string {          // a new launch-time complex factor
+        const size_t i = F.size();
+        F.push_back(re);
+        F.push_back(im);
+        return "make_double2(F.v[" + std::to_string(i) + "], F.v[" + std::to_string(i + 1) + "])";
+    };
+    auto fword = [&](uint32_t w) -> std::string {                     // factor stored in stream word w
+        double re, im;
+        memcpy(&re, &g.hot[w].x, 8);
+        memcpy(&im, &g.hot[w].z, 8);
+        return fconst(re, im);
+    };
+    auto fpool = [&](const std::string& index) -> std::string {       // pool[index] with a run-time index
+        return "make_double2(F.v[2 * (" + index + ")], F.v[2 * (" + index + ") + 1])";
+    };
+    std::ostringstream o;
+    std::vector<int> cold_of_word(g.hot.size(), -1);
+    for (int j = 0; j < P.n_ops; ++j) cold_of_word[g.cold[j].word_off] = j;
+    auto find_patch = [&](uint32_t word, int slot, int kind) -> const ColdOp* {
+        for (int j = P.n_ops; j < P.n_ops + P.n_patches; ++j)
+            if (g.cold[j].word_off == word && g.cold[j].slot == slot && g.cold[j].kind == kind) return &g.cold[j];
+        return nullptr;
+    };
+    std::ostringstream body;
+    for (int r = 0; r < P.n_rounds; ++r) {
+        const RoundDesc& rd = g.rounds[r];
+        const bool first = r == 0, last = r == P.n_rounds - 1;
+        body << "  {  // ---- round " << r << "\n    uint32_t T = tid;\n";
+        for (int s = 0; s < 4; ++s) body << "    T += T & 0x" << std::hex << rd.ins_mask[s] << std::dec << "u;\n";
+        body << "    const uint32_t sT = swz(T);\n    const uint32_t st[4] = {" << rd.swz_j[0] << "u, " << rd.swz_j[1] << "u, "
+             << rd.swz_j[2] << "u, " << rd.swz_j[3] << "u};\n";
+        if (first) {
+            body << "    {\n      const uint64_t gT = (uint64_t)(T & " << ((1u << P.low) - 1u) << "u) | hi_off[T >> " << P.low
+                 << "];\n      const int64_t b[4] = {";
+            for (int s = 0; s < 4; ++s) body << (s ? ", " : "") << "(int64_t)(16ull << " << (int)rd.reg_phys[s] << ")";
+            body << "};\n      const char* q[16];\n      add_tree<4>(reinterpret_cast<const char*>(gbase + gT), b, q);\n"
+                    "#pragma unroll\n      for (int j = 0; j < 16; ++j) a[j] = *reinterpret_cast<const double2*>(q[j]);\n    }\n";
+        } else {
+            body << "#pragma unroll\n    for (int j = 0; j < 16; ++j) a[j] = tile[sT ^ xor_combo<4>(st, j)];\n";
+        }
+        if ((rd.flags & 1u) || rd.dt_end > rd.op_begin) {
+            body << "    double2 ts = " << fconst(rd.scale.x, rd.scale.y) << ";\n";
+            for (uint32_t w = rd.op_begin; w < rd.dt_end; w += kOpWords) {
+                const uint4 h = g.hot[w];
+                const ColdOp& c = g.cold[cold_of_word[w]];
+                const uint32_t opc = h.x & 0xFFu, cthr = h.y & 0xFFFFu, p0 = (h.x >> 16) & 0xFFu, p1 = h.x >> 24;
+                const std::string cond = both(outer_cond(c.ctrl_outer), thr_cond(cthr));
+                std::string f;
+                if (opc == OPC_T) {
+                    if (c.prefetch) {
+                        const std::string i0 = std::to_string(c.mat_off) + "u + " + oi_expr(c);
+                        if (c.fsel != 0xFF)
+                            f = fpool(i0 + " + ((((tid >> " + std::to_string(p0) + ") & 1u)) << " + std::to_string(c.fsel) + ")");
+                        else f = fpool(i0);
+                    } else if (p0 != 31 && c.fsel != 0xFF) {
+                        const std::string f0 = fword(w + 1), f1 = fword(w + 2);
+                        f = "(((tid >> " + std::to_string(p0) + ") & 1u) ? " + f1 + " : " + f0 + ")";
+                    } else f = fword(w + 1);
+                } else {      // OPC_TG
+                    const uint32_t s0 = (h.w >> 8) & 0xFFu, s1 = (h.w >> 16) & 0xFFu;
+                    f = fpool(std::to_string(h.z) + "u + (" + oi_expr(c) + " | (((tid >> " + std::to_string(p0) + ") & 1u) << " +
+                              std::to_string(s0) + ") | (((tid >> " + std::to_string(p1) + ") & 1u) << " + std::to_string(s1) + "))");
+                }
+                body << "    " << (cond.empty() ? "" : "if (" + cond + ") ") << "cmul_ip(ts, " << f << ");\n";
+            }
+            body << "#pragma unroll\n    for (int j = 0; j < 16; ++j) cmul_ip(a[j], ts);\n";
+        }
+        body << "    uint32_t xm = 0;\n";
+        for (uint32_t w = rd.dt_end; w < rd.op_end;) {
+            const uint4 h = g.hot[w];
+            const uint32_t opc = h.x & 0xFFu, size = (h.y >> HDR_SIZE_SHIFT) & 0xFu;
+            if (opc == OPC_LAYER) {
+                const uint4 m = g.hot[w + 1];
+                const uint32_t cs[4] = {m.x & 0xFFFFu, m.x >> 16, m.y & 0xFFFFu, m.y >> 16};
+                const uint32_t cx[4] = {m.z & 0xFFFFu, m.z >> 16, m.w & 0xFFFFu, m.w >> 16};
+                for (int s = 0; s < 4; ++s) {
+                    if (cs[s] != 0xFFFFu) {
+                        const ColdOp* pc = find_patch(w, s, COLD_PATCH_S1);
+                        const std::string f = (pc && pc->k) ? fpool(std::to_string(pc->mat_off) + "u + " + oi_expr(*pc))
+                                                            : fword(w + 2 + s);
+                        const std::string cond = both(pc ? outer_cond(pc->ctrl_outer) : "", thr_cond(cs[s]));
+                        body << "    " << (cond.empty() ? "" : "if (" + cond + ") ") << "reg_s1<" << s << ", 16>(a, " << f << ", xm);\n";
+                    }
+                    if (h.x & (0x1000u << s)) body << "    reg_h<" << s << ", 16>(a, xm);\n";
+                    if (cx[s] != 0xFFFFu) {
+                        const ColdOp* pc = find_patch(w, s, COLD_PATCH_X);
+                        const std::string cond = both(pc ? outer_cond(pc->ctrl_outer) : "", thr_cond(cx[s]));
+                        body << "    " << (cond.empty() ? "" : "if (" + cond + ") ") << "xm ^= " << (1u << s) << "u;\n";
+                    }
+                }
+            } else {
+                const ColdOp& c = g.cold[cold_of_word[w]];
+                const uint32_t cthr = h.y & 0xFFFFu, crm = (h.x >> 8) & 0x1Fu;
+                const std::string cond = both(outer_cond(c.ctrl_outer), thr_cond(cthr));
+                body << "    " << (cond.empty() ? "" : "if (" + cond + ") ") << "{\n";
+                if (opc >= OPC_XS_0 && opc < OPC_XS_0 + 4) {
+                    body << "      reg_xswap<" << (opc - OPC_XS_0) << ", 16>(a, " << crm << "u, xm);\n";
+                } else if (opc == OPC_DS) {
+                    const std::string f = c.prefetch ? fpool(std::to_string(c.mat_off) + "u + " + oi_expr(c)) : fword(w + 1);
+                    body << "      const double2 f = " << f << ";\n      const uint32_t want = " << crm << "u & ~xm;\n"
+                         << "#pragma unroll\n      for (int p = 0; p < 16; ++p) if ((p & " << crm << "u) == want) cmul_ip(a[p], f);\n";
+                } else {
+                    return false;      // not a lean op: leave the group to the interpreter
+                }
+                body << "    }\n";
+            }
+            w += size;
+        }
+        if (last) {
+            body << "    {\n      const uint64_t gT = (uint64_t)(T & " << ((1u << P.low) - 1u) << "u) | hi_off[T >> " << P.low
+                 << "];\n      char* p0 = reinterpret_cast<char*>(gbase + gT);\n      int64_t b[4] = {";
+            for (int s = 0; s < 4; ++s) body << (s ? ", " : "") << "(int64_t)(16ull << " << (int)rd.reg_phys[s] << ")";
+            body << "};\n#pragma unroll\n      for (int s = 0; s < 4; ++s) if ((xm >> s) & 1u) { p0 += b[s]; b[s] = -b[s]; }\n"
+                    "      char* q[16];\n      add_tree<4>(p0, b, q);\n"
+                    "#pragma unroll\n      for (int j = 0; j < 16; ++j) *reinterpret_cast<double2*>(q[j]) = a[j];\n    }\n";
+        } else {
+            body << "    uint32_t sX = sT;\n#pragma unroll\n    for (int s = 0; s < 4; ++s) if ((xm >> s) & 1u) sX ^= st[s];\n"
+                    "#pragma unroll\n    for (int j = 0; j < 16; ++j) tile[sX ^ xor_combo<4>(st, j)] = a[j];\n";
+        }
+        body << "  }\n";
+        if (!last) body << "  __syncthreads();\n";
+    }
+    if (F.empty()) F.push_back(0.0);
+    if (F.size() > 3900) return false;          // kernel parameters are limited to 32 KB
+    o << "#include \"qvm_regtile.cuh\"\nusing namespace qvm;\n"
+         "struct SpecParams { int n_runs; uint64_t shard_bits, run_start, run_len; };\n"
+         "struct SpecFactors { double v[" << F.size() << "]; };\n"
+         "__device__ const uint64_t hi_off[" << g.hi_off.size() << "] = {";
+    for (size_t j = 0; j < g.hi_off.size(); ++j) o << (j ? ", " : "") << hexu(g.hi_off[j]);
+    o << "};\n";
+    o << "extern \"C\" __global__ void __launch_bounds__(" << g.threads << ", " << (g.threads <= 128 ? 4 : (g.threads <= 256 ? 2 : 1))
+      << ") spec_kernel(double2* __restrict__ state, const SpecParams SP, const SpecFactors F) {\n"
+         "  extern __shared__ __align__(16) unsigned char smem_raw[];\n  double2* tile = reinterpret_cast<double2*>(smem_raw);\n"
+         "  const uint32_t tid = threadIdx.x;\n  uint64_t base = 0;\n  {\n    uint64_t t = blockIdx.x;\n"
+         "    for (int r = 0; r < SP.n_runs; ++r) {\n      const uint32_t len = (uint32_t)(SP.run_len >> (8 * r)) & 0xFFu;\n"
+         "      base |= (t & ((1ull << len) - 1ull)) << ((uint32_t)(SP.run_start >> (8 * r)) & 0xFFu);\n      t >>= len;\n    }\n  }\n"
+         "  const uint64_t full = base | SP.shard_bits;\n  double2* gbase = state + base;\n  double2 a[16];\n"
+      << body.str() << "}\n";
+    out.src = o.str();
+    out.threads = g.threads;
+    out.smem = P.n_rounds > 1 ? ((size_t)16 << P.k) : 0;
+    out.n_tiles = g.n_tiles;
+    out.params = SpecParams{P.n_runs, P.shard_bits, P.run_start, P.run_len};
+    return true;
+}
+
+// ---- NVRTC + cudaLibrary plumbing -----------------------------------------------------------------
+extern const char* const kRegtileHeaderSource;      // qvm_regtile.cuh, embedded by build.py
+
+struct CompiledSpec {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kernel = nullptr;
+    size_t smem_attr = 0;
+};
+
+// Process-wide cache of compiled structures.  Compilation (about a second of NVRTC per group) runs on
+// background threads, so nobody waits for it: a structure keeps running through the interpreter until
+// its kernel is ready.  qvm_jit_wait() drains the queue (benchmarks do that once after warm-up).
+class SpecCache {
+public:
+    static SpecCache& instance() {
+        static SpecCache* c = new SpecCache();       // never destroyed: workers may outlive static destructors
+        return *c;
+    }
+    // nullptr: not compiled (yet) under the policy, still compiling, or compilation impossible
+    const CompiledSpec* get(const std::string& src, int policy, int device) {
+        std::unique_lock<std::mutex> lock(mu_);
+        auto it = cache_.find(src);
+        if (it != cache_.end()) return it->second->state == READY ? &it->second->cs : nullptr;
+        if (policy < 2 && ++seen_[std::hash<std::string>()(src)] < 2) return nullptr;
+        Entry* e = new Entry();
+        cache_.emplace(src, std::unique_ptr<Entry>(e));
+        ++compiles_;
+        if (policy >= 2) {                          // synchronous (tests, ahead-of-time warm-up)
+            lock.unlock();
+            std::string err;
+            compile(src, e->cs, &err);
+            lock.lock();
+            e->state = e->cs.kernel ? READY : FAILED;
+            if (!e->cs.kernel) last_error_ = err;
+            return e->cs.kernel ? &e->cs : nullptr;
+        }
+        jobs_.push_back(Job{src, e, device});
+        ++outstanding_;
+        start_workers();
+        cv_.notify_one();
+        return nullptr;
+    }
+    void wait_idle() {
+        std::unique_lock<std::mutex> lock(mu_);
+        idle_cv_.wait(lock, [&] { return outstanding_ == 0; });
+    }
+    int compiles() {
+        std::lock_guard<std::mutex> lock(mu_);
+        return compiles_;
+    }
+    std::string last_error() {
+        std::lock_guard<std::mutex> lock(mu_);
+        return last_error_;
+    }
+
+    // source -> sm_100a cubin (needs no device: also used by the CPU test suite)
+    bool to_cubin(const std::string& src, std::vector<char>& cubin, std::string* err) {
+        if (!load_nvrtc(err)) return false;
+        void* prog = nullptr;
+        const char* headers[] = {kRegtileHeaderSource};
+        const char* names[] = {"qvm_regtile.cuh"};
+        if (create_(&prog, src.c_str(), "qvm_spec.cu", 1, headers, names) != 0) {
+            if (err) *err = "nvrtcCreateProgram failed";
+            return false;
+        }
+        const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device"};
+        const int rc = compile_(prog, 3, opts);
+        if (rc != 0) {
+            if (err) {
+                size_t n = 0;
+                if (log_size_ && log_ && log_size_(prog, &n) == 0 && n > 1) {
+                    std::vector<char> log(n);
+                    log_(prog, log.data());
+                    *err = std::string("nvrtc: ") + log.data();
+                } else *err = "nvrtcCompileProgram failed";
+            }
+            destroy_(&prog);
+            return false;
+        }
+        size_t n = 0;
+        cubin_size_(prog, &n);
+        cubin.resize(n);
+        cubin_(prog, cubin.data());
+        destroy_(&prog);
+        return n > 0;
+    }
+
+private:
+    enum { PENDING = 0, READY = 1, FAILED = 2 };
+    struct Entry {
+        int state = PENDING;
+        CompiledSpec cs;
+    };
+    struct Job {
+        std::string src;
+        Entry* entry;
+        int device;
+    };
+    typedef int (*fn_create)(void**, const char*, const char*, int, const char* const*, const char* const*);
+    typedef int (*fn_compile)(void*, int, const char* const*);
+    typedef int (*fn_size)(void*, size_t*);
+    typedef int (*fn_get)(void*, char*);
+    typedef int (*fn_destroy)(void**);
+
+    void start_workers() {                       // mu_ held
+        if (workers_started_) return;
+        workers_started_ = true;
+        unsigned n = std::thread::hardware_concurrency() / 2;
+        n = n < 1 ? 1 : (n > 8 ? 8 : n);
+        for (unsigned i = 0; i < n; ++i) std::thread([this] { worker(); }).detach();
+    }
+    void worker() {
+        for (;;) {
+            Job job;
+            {
+                std::unique_lock<std::mutex> lock(mu_);
+                cv_.wait(lock, [&] { return !jobs_.empty(); });
+                job = std::move(jobs_.front());
+                jobs_.pop_front();
+            }
+            cudaSetDevice(job.device);
+            CompiledSpec cs;
+            std::string err;
+            compile(job.src, cs, &err);
+            {
+                std::lock_guard<std::mutex> lock(mu_);
+                job.entry->cs = cs;
+                job.entry->state = cs.kernel ? READY : FAILED;
+                if (!cs.kernel) last_error_ = err;
+                if (--outstanding_ == 0) idle_cv_.notify_all();
+            }
+        }
+    }
+    bool load_nvrtc(std::string* err) {
+        std::lock_guard<std::mutex> lock(nvrtc_mu_);
+        if (tried_) {
+            if (!nvrtc_ && err) *err = "libnvrtc not available";
+            return nvrtc_ != nullptr;
+        }
+        tried_ = true;
+        for (const char* name : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"}) {
+            nvrtc_ = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (nvrtc_) break;
+        }
+        if (!nvrtc_) {
+            if (err) *err = "libnvrtc not found";
+            return false;
+        }
+        create_ = (fn_create)dlsym(nvrtc_, "nvrtcCreateProgram");
+        compile_ = (fn_compile)dlsym(nvrtc_, "nvrtcCompileProgram");
+        cubin_size_ = (fn_size)dlsym(nvrtc_, "nvrtcGetCUBINSize");
+        cubin_ = (fn_get)dlsym(nvrtc_, "nvrtcGetCUBIN");
+        log_size_ = (fn_size)dlsym(nvrtc_, "nvrtcGetProgramLogSize");
+        log_ = (fn_get)dlsym(nvrtc_, "nvrtcGetProgramLog");
+        destroy_ = (fn_destroy)dlsym(nvrtc_, "nvrtcDestroyProgram");
+        if (!create_ || !compile_ || !cubin_size_ || !cubin_ || !destroy_) {
+            nvrtc_ = nullptr;
+            if (err) *err = "libnvrtc lacks the expected entry points";
+            return false;
+        }
+        return true;
+    }
+    void compile(const std::string& src, CompiledSpec& cs, std::string* err) {
+        std::vector<char> cubin;
+        if (!to_cubin(src, cubin, err)) return;
+        cudaLibrary_t lib = nullptr;
+        if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (err) *err = "cudaLibraryLoadData failed";
+            return;
+        }
+        cudaKernel_t k = nullptr;
+        if (cudaLibraryGetKernel(&k, lib, "spec_kernel") != cudaSuccess) {
+            cudaGetLastError();
+            cudaLibraryUnload(lib);
+            if (err) *err = "spec_kernel not found in the compiled module";
+            return;
+        }
+        cs.lib = lib;
+        cs.kernel = k;
+    }
+    std::mutex mu_, nvrtc_mu_;
+    std::condition_variable cv_, idle_cv_;
+    std::unordered_map<std::string, std::unique_ptr<Entry>> cache_;
+    std::unordered_map<size_t, int> seen_;
+    std::deque<Job> jobs_;
+    int outstanding_ = 0, compiles_ = 0;
+    bool workers_started_ = false;
+    std::string last_error_;
+    void* nvrtc_ = nullptr;
+    bool tried_ = false;
+    fn_create create_ = nullptr;
+    fn_compile compile_ = nullptr;
+    fn_size cubin_size_ = nullptr, log_size_ = nullptr;
+    fn_get cubin_ = nullptr, log_ = nullptr;
+    fn_destroy destroy_ = nullptr;
+};
+
+}  // namespace qvm

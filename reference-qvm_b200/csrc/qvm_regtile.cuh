@@ -36,9 +36,20 @@
 // and the interpreter can be diffed against the oracle without a GPU.  That emulator is test
 // infrastructure and is not part of libqvm_b200.so.
 #pragma once
+#if defined(__CUDACC_RTC__)
+// compiled at run time by NVRTC (qvm_jit.h): no host headers, the vector types are built in
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#endif
 
 #if defined(__CUDACC__)
 #define QVM_HD __host__ __device__ __forceinline__

@@ -34,7 +34,8 @@ class Op(C.Structure):
 class Stats(C.Structure):
     """``qvm_stats_t``"""
     _fields_ = [(name, C.c_uint64) for name in
-                ("kernel_launches", "gate_ops", "hbm_passes", "hbm_bytes", "h2d_bytes", "d2h_bytes", "regtile_rounds")]
+                ("kernel_launches", "gate_ops", "hbm_passes", "hbm_bytes", "h2d_bytes", "d2h_bytes", "regtile_rounds",
+                 "jit_launches", "jit_compiles")]
 
     def as_dict(self):
         return {name: int(getattr(self, name)) for name, _ in self._fields_}
@@ -52,6 +53,10 @@ _SIGNATURES = {
     "qvm_set_stream": (C.c_int, [_P, _P]),
     "qvm_set_tile_bits": (C.c_int, [_P, C.c_int, C.c_int]),
     "qvm_set_kernel_path": (C.c_int, [_P, C.c_int]),
+    "qvm_set_jit": (C.c_int, [_P, C.c_int]),
+    "qvm_jit_wait": (C.c_int, []),
+    "qvm_spec_compile_check": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_int, _P, C.c_int, _P, _P, C.c_uint64, _P,
+                                         C.c_uint64]),
     "qvm_debug_opcode_hist": (C.c_int, [_P, _P]),
     "qvm_n_local": (C.c_int, [_P]),
     "qvm_device_ptr": (_P, [_P]),
@@ -185,6 +190,41 @@ def classify(matrix, qubits):
                         out[:op.mat_entries].copy())
 
 
+def marshal_ops(ops):
+    """ClassifiedOps -> (qvm_op_t array, matrix pool, entries) as the C ABI takes them."""
+    arr = (Op * max(len(ops), 1))()
+    total = sum(o.mat.size for o in ops)
+    pool = np.empty(max(total, 1), dtype=np.complex128)
+    off = 0
+    for i, o in enumerate(ops):
+        a = arr[i]
+        a.kind, a.k, a.ctrl_mask = o.kind, len(o.targets), o.ctrl_mask
+        for j in range(MAX_TARGETS):
+            a.targets[j] = o.targets[j] if j < len(o.targets) else -1
+        a.mat_offset, a.mat_entries = off, o.mat.size
+        pool[off:off + o.mat.size] = o.mat
+        off += o.mat.size
+    return arr, pool, total
+
+
+def jit_wait():
+    """Block until all background compilations of specialised kernels have finished."""
+    check(lib().qvm_jit_wait())
+
+
+def spec_compile_check(n_local, tile_bits, ops, n_global=0, shard_index=0):
+    """``qvm_spec_compile_check``: 0 compiled, 1 left to the interpreter; raises with the NVRTC log."""
+    ops = [o for o in ops if o.kind != OP_NOP]
+    arr, pool, total = marshal_ops(ops)
+    tb = np.ascontiguousarray(sorted(tile_bits), dtype=np.int32)
+    log = C.create_string_buffer(1 << 16)
+    code = lib().qvm_spec_compile_check(n_local, n_global, shard_index, tb.size, tb.ctypes.data, len(ops),
+                                        C.cast(arr, _P), pool.ctypes.data, total, log, len(log))
+    if code < 0:
+        raise NativeError(code, log.value.decode("utf-8", "replace") or last_error())
+    return code
+
+
 class DeviceState(object):
     """Owner of one ``qvm_t``: a shard of 2^n_local complex128 amplitudes in HBM."""
 
@@ -232,6 +272,9 @@ class DeviceState(object):
 
     def set_tile_bits(self, tile_bits, low_bits):
         check(lib().qvm_set_tile_bits(self.handle, tile_bits, low_bits))
+
+    def set_jit(self, policy):
+        check(lib().qvm_set_jit(self.handle, int(policy)))
 
     def set_kernel_path(self, use_regtile):
         check(lib().qvm_set_kernel_path(self.handle, 1 if use_regtile else 0))

@@ -384,3 +384,73 @@ def test_exchange_block_two_global_bits_on_one_device():
             lb, gb = (idx >> lp) & 1, (idx >> gp) & 1
             src = src & ~((1 << lp) | (1 << gp)) | (gb << lp) | (lb << gp)
         assert np.array_equal(got, full[src]), vpos
+
+
+def _run_circuit_state(n, spec, jit, repeats=1):
+    eng = _engine.Engine(n)
+    eng.state.set_jit(jit)
+    out = None
+    for _ in range(repeats):
+        eng.reset()
+        for name, params, qubits in spec:
+            m = G.gate_matrix[name]
+            eng.queue_matrix(m(*params) if params else m, qubits)
+        out = eng.amplitudes()
+    stats = eng.stats()
+    eng.close()
+    return out, stats
+
+
+@pytest.mark.parametrize("n,depth,seed", [(14, 10, 1), (17, 8, 2), (20, 6, 1234)])
+def test_specialised_kernels_match_oracle_and_interpreter(n, depth, seed):
+    """JIT path (policy 2: compile every group at first sight): same amplitudes as the interpreted kernel
+    bit for bit (same device functions, same order) and as the oracle within 1e-12."""
+    spec = orc.random_circuit_spec(n, depth, seed)
+    want = random_state(n, 0) * 0
+    want[0] = 1.0
+    for name, params, qubits in spec:
+        m = G.gate_matrix[name]
+        want = orc.fast_apply_gate(want, np.asarray(m(*params) if params else m, dtype=complex), qubits, n)
+    interp, s0 = _run_circuit_state(n, spec, jit=0)
+    jitted, s2 = _run_circuit_state(n, spec, jit=2)
+    assert s0["jit_launches"] == 0 and s2["jit_launches"] > 0
+    assert np.max(np.abs(jitted - want)) < TOL
+    assert np.array_equal(jitted, interp)
+
+
+def test_specialised_kernels_background_policy_and_new_angles():
+    """Default policy: first run interpreted, second run submits the structures, after qvm_jit_wait the
+    third run uses the compiled kernels; a circuit with the same structure but other angles reuses them."""
+    n = 16
+    spec = orc.random_circuit_spec(n, 6, 9)
+    eng = _engine.Engine(n)
+    eng.state.set_jit(1)
+
+    def run(sp):
+        eng.reset()
+        for name, params, qubits in sp:
+            m = G.gate_matrix[name]
+            eng.queue_matrix(m(*params) if params else m, qubits)
+        return eng.amplitudes()
+
+    a1 = run(spec)
+    assert eng.stats()["jit_launches"] == 0
+    a2 = run(spec)
+    nat.jit_wait()
+    before = eng.stats()["jit_launches"]
+    a3 = run(spec)
+    assert eng.stats()["jit_launches"] > before
+    assert np.array_equal(a1, a2) and np.array_equal(a1, a3)
+    # same gates, other rotation angles: the structure (and therefore the kernels) is the same
+    other = [(name, [p + 0.37 for p in params], qubits) for name, params, qubits in spec]
+    compiles = eng.stats()["jit_compiles"]
+    mid = eng.stats()["jit_launches"]
+    got = run(other)
+    assert eng.stats()["jit_launches"] > mid and eng.stats()["jit_compiles"] == compiles
+    want = np.zeros(1 << n, dtype=complex)
+    want[0] = 1.0
+    for name, params, qubits in other:
+        m = G.gate_matrix[name]
+        want = orc.fast_apply_gate(want, np.asarray(m(*params) if params else m, dtype=complex), qubits, n)
+    assert np.max(np.abs(got - want)) < TOL
+    eng.close()

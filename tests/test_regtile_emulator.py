@@ -193,3 +193,25 @@ def test_density_style_superoperators():
         want = orc.fast_apply_gate(want, np.asarray(m, dtype=complex), q, n)
     got, stats = run_emulated(psi0, ops, n, 12, 5)
     assert np.max(np.abs(got - want)) < TOL
+
+
+def test_specialised_source_compiles_with_nvrtc():
+    """The JIT path's generated source (qvm_jit.h) for real planner groups compiles to an sm_100a cubin
+    with NVRTC -- no device needed.  Execution parity of those kernels is a GPU test."""
+    if REG_BITS != 4:
+        pytest.skip("specialised kernels exist for 16 amplitudes per thread")
+    n = 16
+    ops = compile_spec(orc.random_circuit_spec(n, 10, 3))
+    groups = _planner.plan(ops, n, 11, 4)
+    codes = [nat.spec_compile_check(n, g.tile, g.ops) for g in groups[:2]]
+    assert codes == [0, 0]
+    # sharded group: controls / diagonal targets on global positions
+    n_local, n_global = 11, 2
+    ops = [o for o in compile_spec(orc.random_circuit_spec(n_local + n_global, 6, 21))
+           if not (o.kind == nat.OP_DENSE and any(t >= n_local for t in o.targets))]
+    g = _planner.plan(ops, n_local, 10, 4)[0]
+    assert nat.spec_compile_check(n_local, g.tile, g.ops, n_global=n_global, shard_index=3) == 0
+    # a group with generic dense matrices is left to the interpreter
+    rs = np.random.RandomState(0)
+    dense = [_engine.compile_gate(rs.standard_normal((4, 4)) + 0j, [3, 9])]
+    assert nat.spec_compile_check(12, tuple(range(12)), dense) == 1
