@@ -98,7 +98,7 @@ int qvm_jit_wait(void);
  * generated source failed to compile (`log` receives the NVRTC log). */
 int qvm_spec_compile_check(int n_local, int n_global, uint64_t shard_index, int n_tile, const int32_t* tile_bits,
                            int n_ops, const qvm_op_t* ops, const double* mats, uint64_t mats_entries, char* log,
-                           uint64_t log_cap);
+                           uint64_t log_cap, int n_low, int n_bring, const int32_t* bring_low);
 /* Debug: how many ops of each register-tile opcode were encoded so far (32 counters). */
 int qvm_debug_opcode_hist(qvm_t* q, uint64_t* out32);
 int qvm_n_local(const qvm_t* q);
@@ -114,6 +114,11 @@ int qvm_set_state(qvm_t* q, uint64_t offset, uint64_t count, const double* re_im
 int qvm_get_state(qvm_t* q, uint64_t offset, uint64_t count, double* re_im);
 /* Strided gather of `count` amplitudes: element j is amp[offset + j*stride] (diag of rho). */
 int qvm_get_strided(qvm_t* q, uint64_t offset, uint64_t stride, uint64_t count, double* re_im);
+/* Readback through a qubit layout (see qvm_apply_group_relabel): re_im[j] = amplitude of the LOGICAL
+ * index offset + j*stride, where logical bit i lives at physical position pos_of[i] (a permutation of
+ * 0..n_local-1).  The reference has no layout: its self.wf is always in program order. */
+int qvm_get_state_layout(qvm_t* q, uint64_t offset, uint64_t stride, uint64_t count, int n_pos,
+                         const int32_t* pos_of, double* re_im);
 int qvm_copy_state(qvm_t* dst, qvm_t* src);
 int qvm_norm2(qvm_t* q, double* out);           /* sum |amp|^2 over the shard                    */
 
@@ -138,6 +143,18 @@ int qvm_apply(qvm_t* q, int k, const int32_t* qubits, const double* matrix);
  * matrix pool the ops' mat_offset index (complex entries, interleaved re/im). */
 int qvm_apply_group(qvm_t* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops,
                     const double* mats, uint64_t mats_entries);
+
+/* Same pass, plus an in-tile qubit relabelling on the way out: the qubits now at the positions
+ * `bring_low[0..n_bring)` (members of `tile_bits`) are to leave the pass on positions < n_low -- the
+ * coalescing bits every tile contains -- trading places with qubits there that were not asked for.  The
+ * permutation costs no extra HBM traffic (the tile is transposed in shared memory between rounds anyway).
+ * new_pos[j] (n_tile entries) = position after the pass of the qubit that was at tile_bits[j]; the
+ * caller tracks the layout.  The library may relabel less than asked (new_pos says what happened).
+ * There is no counterpart in the reference: it never reorders qubits (SWAP is an explicit operator,
+ * unitary_generator.py:91-150); this only changes where amplitudes live between passes. */
+int qvm_apply_group_relabel(qvm_t* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops,
+                            const double* mats, uint64_t mats_entries, int n_low, int n_bring,
+                            const int32_t* bring_low, int32_t* new_pos);
 
 /* rho[i,j] *= f^popcount((i xor j) & mask) on a 2n-qubit vectorised rho (n = n_total/2): the fused
  * form of `dephasing` Kraus pairs on every qubit in `mask` (qvm_density.py:298-313, :350-361). */

@@ -264,12 +264,20 @@ int ring_alloc(qvm_state* q, size_t bytes, size_t* off) {
     return QVM_OK;
 }
 
+// Relabelling request of one group: tile bits (tile-local mask) whose qubits should leave the pass on the
+// n_low lowest tile bits; sigma[b] = tile bit on which the qubit of tile bit b does leave it.
+struct RelabelReq {
+    uint32_t low_in = 0;
+    int n_low = 0;
+    uint8_t sigma[16] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15};
+};
+
 int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops,
-                         const double* mats, uint64_t mats_entries, bool* handled);
+                         const double* mats, uint64_t mats_entries, bool* handled, RelabelReq* relabel);
 
 // Encode ops in tile-local coordinates and launch one tile kernel.
 int launch_group(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops, const double* mats,
-                 uint64_t mats_entries) {
+                 uint64_t mats_entries, RelabelReq* relabel = nullptr) {
     if (n_tile < 0 || n_tile > q->n_local || n_tile > QVM_MAX_TILE_BITS)
         return fail(QVM_ERR_INVALID, "tile of %d bits is outside [0, min(n_local=%d, %d)]", n_tile, q->n_local,
                     QVM_MAX_TILE_BITS);
@@ -295,9 +303,10 @@ int launch_group(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, 
 
     if (q->use_regtile) {
         bool handled = false;
-        int rc2 = launch_group_regtile(q, n_tile, tile_bits, n_ops, ops, mats, mats_entries, &handled);
+        int rc2 = launch_group_regtile(q, n_tile, tile_bits, n_ops, ops, mats, mats_entries, &handled, relabel);
         if (rc2 != QVM_OK || handled) return rc2;
     }
+    // (the shared-memory kernel below never relabels: relabel->sigma is still the identity)
 
     std::vector<DevOp> dev;
     dev.reserve(n_ops);
@@ -391,14 +400,15 @@ int launch_regtile(qvm_state* q, unsigned grid, unsigned threads, size_t smem, c
 }
 
 int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops,
-                         const double* mats, uint64_t mats_entries, bool* handled) {
+                         const double* mats, uint64_t mats_entries, bool* handled, RelabelReq* relabel) {
     *handled = false;
     EncodedGroup& g = q->enc;
     const int erc = encode_group(q->n_local, q->n_global, q->shard_index, n_tile, tile_bits, n_ops, ops, mats,
-                                 mats_entries, g, q->reg_bits);
+                                 mats_entries, g, q->reg_bits, relabel ? relabel->low_in : 0u, relabel ? relabel->n_low : 0);
     if (erc == ENC_ERROR) return fail(QVM_ERR_CUDA, "round planner made no progress");
     if (erc == ENC_FALLBACK) return QVM_OK;          // the shared-memory kernel (or its error) handles it
-    if (g.cold.empty()) {
+    if (relabel) memcpy(relabel->sigma, g.sigma, sizeof(g.sigma));
+    if (g.cold.empty() && !g.relabelled) {
         *handled = true;
         return QVM_OK;
     }
@@ -415,6 +425,11 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
                 QVM_CUDA(q, cudaFuncSetAttribute((const void*)cs->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)ss.smem));
                 const_cast<CompiledSpec*>(cs)->smem_attr = ss.smem;
+            }
+            if (!cs->carveout_set) {      // several 32-64 KB tiles per SM: ask for the largest shared-memory carve-out
+                cudaFuncSetAttribute((const void*)cs->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+                cudaGetLastError();
+                const_cast<CompiledSpec*>(cs)->carveout_set = true;
             }
             double2* amps = q->amps;
             SpecParams sp = ss.params;
@@ -641,12 +656,17 @@ int qvm_set_tile_bits(qvm_t* q, int tile_bits, int low_bits) {
 
 int qvm_spec_compile_check(int n_local, int n_global, uint64_t shard_index, int n_tile, const int32_t* tile_bits,
                            int n_ops, const qvm_op_t* ops, const double* mats, uint64_t mats_entries, char* log,
-                           uint64_t log_cap) {
+                           uint64_t log_cap, int n_low, int n_bring, const int32_t* bring_low) {
     if (log && log_cap) log[0] = 0;
-    if ((n_tile && !tile_bits) || (n_ops && !ops)) return fail(QVM_ERR_INVALID, "null pointer");
+    if ((n_tile && !tile_bits) || (n_ops && !ops) || (n_bring && !bring_low)) return fail(QVM_ERR_INVALID, "null pointer");
+    uint32_t low_in = 0;
+    for (int i = 0; i < n_bring; ++i)
+        for (int j = 0; j < n_tile; ++j)
+            if (tile_bits[j] == bring_low[i]) low_in |= 1u << j;
     EncodedGroup g;
     SpecSource ss;
-    if (encode_group(n_local, n_global, shard_index, n_tile, tile_bits, n_ops, ops, mats, mats_entries, g, 4) != ENC_OK ||
+    if (encode_group(n_local, n_global, shard_index, n_tile, tile_bits, n_ops, ops, mats, mats_entries, g, 4, low_in,
+                     n_low) != ENC_OK ||
         !generate_spec(g, ss))
         return 1;
     std::vector<char> cubin;
@@ -768,6 +788,39 @@ int qvm_get_strided(qvm_t* q, uint64_t offset, uint64_t stride, uint64_t count, 
     return rc;
 }
 
+int qvm_get_state_layout(qvm_t* q, uint64_t offset, uint64_t stride, uint64_t count, int n_pos, const int32_t* pos_of,
+                         double* re_im) {
+    QVM_CHECK_HANDLE(q);
+    if (!count) return QVM_OK;
+    if (!re_im || !pos_of) return fail(QVM_ERR_INVALID, "null pointer");
+    if (n_pos != q->n_local) return fail(QVM_ERR_INVALID, "layout of %d positions on a %d-position shard", n_pos, q->n_local);
+    if (offset >= q->n_elems || (count - 1) > (q->n_elems - 1 - offset) / (stride ? stride : 1))
+        return fail(QVM_ERR_INVALID, "range outside the shard");
+    LayoutPerm perm{};
+    perm.n = n_pos;
+    uint64_t seen = 0;
+    for (int i = 0; i < n_pos; ++i) {
+        if (pos_of[i] < 0 || pos_of[i] >= n_pos || ((seen >> pos_of[i]) & 1ull))
+            return fail(QVM_ERR_INVALID, "layout is not a permutation of the local positions");
+        seen |= 1ull << pos_of[i];
+        perm.pos[i] = (uint8_t)pos_of[i];
+    }
+    const uint64_t chunk = std::min<uint64_t>(count, (uint64_t)1 << 24);       // 256 MiB of staging at most
+    double2* tmp = nullptr;
+    QVM_CUDA(q, cudaMallocAsync(&tmp, chunk * 16, q->stream));
+    int rc = QVM_OK;
+    for (uint64_t done = 0; done < count && rc == QVM_OK; done += chunk) {
+        const uint64_t n = std::min<uint64_t>(chunk, count - done);
+        gather_layout_kernel<<<grid_for(q, n, 256), 256, 0, q->stream>>>(q->amps, offset + done * stride, stride, n, perm, tmp);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(QVM_ERR_CUDA, "gather_layout_kernel launch failed");
+        q->stats.kernel_launches += 1;
+        if (rc == QVM_OK) rc = copy_chunked(q, tmp, re_im + 2 * done, n, false);
+    }
+    cudaFreeAsync(tmp, q->stream);
+    q->stats.d2h_bytes += count * 16;
+    return rc;
+}
+
 int qvm_copy_state(qvm_t* dst, qvm_t* src) {
     QVM_CHECK_HANDLE(dst);
     if (!src) return fail(QVM_ERR_INVALID, "null source");
@@ -840,6 +893,29 @@ int qvm_apply_group(qvm_t* q, int n_tile, const int32_t* tile_bits, int n_ops, c
     if (mats_entries && !mats) return fail(QVM_ERR_INVALID, "null matrix pool");
     q->sample_mode = -1;
     return launch_group(q, n_tile, tile_bits, n_ops, ops, mats, mats_entries);
+}
+
+int qvm_apply_group_relabel(qvm_t* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops,
+                            const double* mats, uint64_t mats_entries, int n_low, int n_bring, const int32_t* bring_low,
+                            int32_t* new_pos) {
+    QVM_CHECK_HANDLE(q);
+    if (n_ops < 0 || (n_ops && !ops) || (n_tile && !tile_bits) || !new_pos || (n_bring && !bring_low))
+        return fail(QVM_ERR_INVALID, "null pointer");
+    if (mats_entries && !mats) return fail(QVM_ERR_INVALID, "null matrix pool");
+    if (n_tile < 0 || n_tile > 16 || n_bring < 0 || n_low < 0) return fail(QVM_ERR_INVALID, "bad relabelling request");
+    RelabelReq req;
+    req.n_low = n_low;
+    for (int i = 0; i < n_bring; ++i) {
+        int j = 0;
+        while (j < n_tile && tile_bits[j] != bring_low[i]) ++j;
+        if (j == n_tile) return fail(QVM_ERR_INVALID, "position %d is not in the tile", bring_low[i]);
+        req.low_in |= 1u << j;
+    }
+    q->sample_mode = -1;
+    const int rc = launch_group(q, n_tile, tile_bits, n_ops, ops, mats, mats_entries, &req);
+    if (rc != QVM_OK) return rc;
+    for (int j = 0; j < n_tile; ++j) new_pos[j] = tile_bits[req.sigma[j]];
+    return QVM_OK;
 }
 
 int qvm_dephase_all(qvm_t* q, int n_rho, uint64_t qubit_mask, double factor) {

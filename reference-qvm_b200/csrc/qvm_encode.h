@@ -56,6 +56,10 @@ struct EncodedGroup {
     uint32_t opc_hist[32] = {};
     int n_layers = 0;                        // LAYER dispatches emitted (several single-slot ops each)
     int n_dirty_rounds = 0;                  // rounds that apply a thread scalar (16 multiplies per thread)
+    // In-tile relabelling: the qubit that entered the pass on tile bit b leaves it on tile bit sigma[b]
+    // (identity unless the caller asked for qubits to be brought to the low positions).
+    uint8_t sigma[16] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15};
+    bool relabelled = false;
 };
 
 enum { ENC_OK = 0, ENC_FALLBACK = 1, ENC_ERROR = 2 };
@@ -109,7 +113,7 @@ inline bool is_h_matrix(const double* m) {      // s * [[1, 1], [1, -1]] with re
 // register-tiled kernel encodes (the shared-memory kernel takes it and reports real errors).
 inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_tile, const int32_t* tile_bits,
                         int n_ops, const qvm_op_t* ops, const double* mats, uint64_t mats_entries, EncodedGroup& out,
-                        int R = 4) {
+                        int R = 4, uint32_t low_in = 0, int n_low = 0) {
     if (n_tile < 9 || n_tile > 13) return ENC_FALLBACK;
     if (R != 4 && R != 5) return ENC_FALLBACK;
     if (R == 5 && n_tile < 10) R = 4;          // a 2^9 tile would leave half a warp per CTA
@@ -175,7 +179,31 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
     out.pool.clear();
     out.need_full = false;
     out.n_layers = 0;
-    if (lops.empty()) return ENC_OK;
+    out.relabelled = false;
+    for (int b = 0; b < 16; ++b) out.sigma[b] = (uint8_t)b;
+    P.perm_round = -1;
+    memset(P.perm_swz, 0, sizeof(P.perm_swz));
+
+    // ---- in-tile relabelling request --------------------------------------------------------------
+    // `low_in`: tile bits whose qubits the caller wants on the n_low lowest tile bits when the pass ends
+    // (the next group's coalescing bits).  Those already there stay; each of the others trades places with
+    // a low bit that is not wanted (sigma = disjoint transpositions).  The pairing is fixed further down,
+    // once the thread bits of the writing round are known (shared-memory bank conflicts depend on it).
+    int n_in = 0, n_vic = 0;
+    int in_bit[8], vic_bit[8];
+    if (low_in && n_low > 0 && n_low <= 5 && n_low < n_tile) {
+        for (int b = n_low; b < n_tile && n_in < 8; ++b)
+            if ((low_in >> b) & 1u) in_bit[n_in++] = b;
+        for (int b = n_low - 1; b >= 0 && n_vic < n_in; --b)
+            if (!((low_in >> b) & 1u)) vic_bit[n_vic++] = b;
+        n_in = std::min(n_in, n_vic);            // more requests than low bits: the first ones win
+    }
+    const bool relabel = n_in > 0;
+    // tile bits (old coordinates) whose qubits end on the five lowest tile bits: the last round keeps those
+    // for its lanes, as round 0 keeps the five lowest old bits
+    uint32_t low5_last = 0x1Fu;
+    for (int i = 0; i < n_in; ++i) low5_last = (low5_last & ~(1u << vic_bit[i])) | (1u << in_bit[i]);
+    if (lops.empty() && !relabel) return ENC_OK;
 
     // ---- rounds: greedy, commutation aware ------------------------------------------------------
     // Dense ops choose the rounds (each needs its targets in register slots).  Diagonal ops float:
@@ -222,7 +250,9 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
             rounds.push_back(rd);
         }
     }
-    if (rounds.size() > 1 && (rounds.back().regmask() & 0x1Fu)) rounds.push_back(PlannedRound());   // store round
+    if (rounds.empty()) rounds.push_back(PlannedRound());            // pure relabelling pass
+    if ((rounds.size() > 1 && (rounds.back().regmask() & low5_last)) || (relabel && rounds.size() == 1))
+        rounds.push_back(PlannedRound());   // store round
     if (rounds.size() > 4096) return ENC_FALLBACK;
     // Fill unused register slots.  A filler bit turns every control / diagonal factor on it into
     // register-slot work (pair swaps instead of a relabel, 8 multiplies instead of one per thread), so
@@ -236,6 +266,7 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
                 for (int b = 0; b < n_tile; ++b)
                     if ((lops[i].diag_mask >> b) & 1u) ++touch[b];
         const bool io_round = r == 0 || r + 1 == rounds.size();
+        const uint32_t lanes = (r + 1 == rounds.size() && r > 0) ? low5_last : 0x1Fu;
         uint32_t used = rd.regmask();
         for (int s = 0; s < R; ++s) {
             if (rd.slot_bit[s] >= 0) continue;
@@ -243,12 +274,57 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
             for (int pass = 0; pass < 2 && best < 0; ++pass)
                 for (int b = n_tile - 1; b >= 0; --b) {
                     if ((used >> b) & 1u) continue;
-                    if (pass == 0 && io_round && b < 5) continue;
+                    if (pass == 0 && io_round && ((lanes >> b) & 1u)) continue;
                     if (best < 0 || touch[b] < touch[best]) best = b;
                 }
             rd.slot_bit[s] = best;
             used |= 1u << best;
         }
+    }
+
+    // ---- fix the relabelling permutation ----------------------------------------------------------
+    // The round before the last one writes the tile in the new coordinates.  Its quarter-warps (lanes on
+    // its three lowest thread bits) store 8 x 16 bytes at once: conflict-free when the swizzle patterns of
+    // the three images under sigma are linearly independent.  Try every pairing of incoming and outgoing
+    // bits and keep the best.
+    uint8_t* sigma = out.sigma;
+    if (relabel) {
+        const PlannedRound& wr = rounds[rounds.size() - 2];
+        int lane_bit[3], nl = 0;
+        for (int b = 0; b < n_tile && nl < 3; ++b)
+            if (wr.slot_of(b) < 0) lane_bit[nl++] = b;
+        int perm[8], best_perm[8], best_rank = -1;
+        for (int i = 0; i < n_in; ++i) perm[i] = best_perm[i] = i;
+        do {
+            uint8_t sg[16];
+            for (int b = 0; b < 16; ++b) sg[b] = (uint8_t)b;
+            for (int i = 0; i < n_in; ++i) {
+                sg[in_bit[i]] = (uint8_t)vic_bit[perm[i]];
+                sg[vic_bit[perm[i]]] = (uint8_t)in_bit[i];
+            }
+            uint32_t span[8] = {1, 0, 0, 0, 0, 0, 0, 0};      // span[v] = 1: v is a XOR of the patterns so far
+            int rank = 0;
+            for (int j = 0; j < nl; ++j) {
+                const uint32_t pat = swz(1u << sg[lane_bit[j]]) & 7u;
+                if (span[pat]) continue;
+                ++rank;
+                for (uint32_t v = 0; v < 8; ++v)
+                    if (span[v] == 1) span[v ^ pat] = 2;
+                for (uint32_t v = 0; v < 8; ++v)
+                    if (span[v]) span[v] = 1;
+            }
+            if (rank > best_rank) {
+                best_rank = rank;
+                memcpy(best_perm, perm, sizeof(perm));
+            }
+        } while (best_rank < nl && std::next_permutation(perm, perm + n_in));
+        for (int i = 0; i < n_in; ++i) {
+            sigma[in_bit[i]] = (uint8_t)vic_bit[best_perm[i]];
+            sigma[vic_bit[best_perm[i]]] = (uint8_t)in_bit[i];
+        }
+        out.relabelled = true;
+        P.perm_round = (int)rounds.size() - 2;
+        for (int b = 0; b < n_tile; ++b) P.perm_swz[b] = (uint16_t)swz(1u << sigma[b]);
     }
 
     // place the floating diagonal ops
@@ -292,13 +368,37 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
     std::vector<ColdOp>& cold = out.cold;
     std::vector<ColdOp> patches;             // appended to `cold` once all plain ops / layers are known
     double gs_re = 1.0, gs_im = 0.0;     // global complex scalar: folded H scales and RZ d0 phases
+    const std::vector<LocalOp>& lops_old = lops;
     hot.reserve(n);
     cold.reserve(n);
     int dirty_round = -1, dirty_best = -1;
+    std::vector<LocalOp> lops_new;       // the ops in the tile coordinates of the last round (after sigma)
+    if (relabel) {
+        auto map_mask = [&](uint32_t m) {
+            uint32_t o = 0;
+            for (int b = 0; b < n_tile; ++b)
+                if ((m >> b) & 1u) o |= 1u << sigma[b];
+            return o;
+        };
+        lops_new = lops;
+        for (LocalOp& l : lops_new) {
+            for (int t = 0; t < l.k; ++t)
+                if (l.tgt[t] >= 0) l.tgt[t] = sigma[l.tgt[t]];
+            l.ctrl_tile = map_mask(l.ctrl_tile);
+            l.dense_mask = map_mask(l.dense_mask);
+            l.diag_mask = map_mask(l.diag_mask);
+        }
+    }
     for (size_t r = 0; r < rounds.size(); ++r) {
+        const bool new_coords = relabel && r + 1 == rounds.size();
+        if (new_coords)
+            for (int s = 0; s < R; ++s) rounds[r].slot_bit[s] = sigma[rounds[r].slot_bit[s]];
+        const std::vector<LocalOp>& lops = new_coords ? lops_new : lops_old;
         const PlannedRound& rd = rounds[r];
         RoundDesc& d = out.rounds[r];
         memset(&d, 0, sizeof(d));
+        if (relabel && (int)r == P.perm_round)
+            for (int s = 0; s < R; ++s) d.wr_swz[s] = (uint16_t)swz(1u << sigma[rd.slot_bit[s]]);
         d.scale = make_double2(1.0, 0.0);
         int8_t slot_of[16], thr_of[16];
         memset(slot_of, -1, sizeof(slot_of));

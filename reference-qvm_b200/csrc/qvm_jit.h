@@ -15,6 +15,7 @@
 
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <memory>
@@ -75,13 +76,25 @@ inline std::string oi_expr(const ColdOp& c) {
 
 }  // namespace specgen
 
+// Resident CTAs per SM the specialised kernels are compiled for, in units of 128-thread CTAs
+// (QVM_B200_SPEC_OCC): the register budget per thread follows from it (65536 / threads per SM).
+inline unsigned spec_min_blocks(unsigned threads) {
+    static const int occ = [] {
+        const char* e = getenv("QVM_B200_SPEC_OCC");
+        const int v = e ? atoi(e) : 4;
+        return v < 1 ? 1 : (v > 8 ? 8 : v);
+    }();
+    const unsigned b = (unsigned)occ * 128u / (threads ? threads : 128u);
+    return b < 1 ? 1 : b;
+}
+
 // Source for one encoded group (lean R = 4 groups only).  Factors never appear as literals: F.v[i]
 // indexes a by-value kernel argument -- first the encoder's matrix pool, then the factors the encoder
 // inlined into the op stream, then the round scalars.
 inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
     using namespace specgen;
     const RegTileParams& P = g.P;
-    if (g.cold.empty() || g.need_full || P.R != 4) return false;
+    if ((g.cold.empty() && !g.relabelled) || g.need_full || P.R != 4) return false;
     std::vector<double>& F = out.factors;
     F.assign(g.pool.begin(), g.pool.end());
     auto fconst = [&](double re, double im) -> std::string {          // a new launch-time complex factor
@@ -199,6 +212,15 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
             body << "};\n#pragma unroll\n      for (int s = 0; s < 4; ++s) if ((xm >> s) & 1u) { p0 += b[s]; b[s] = -b[s]; }\n"
                     "      char* q[16];\n      add_tree<4>(p0, b, q);\n"
                     "#pragma unroll\n      for (int j = 0; j < 16; ++j) *reinterpret_cast<double2*>(q[j]) = a[j];\n    }\n";
+        } else if (r == P.perm_round) {
+            // relabelling round: the tile is written in the last round's coordinates (qvm_encode.h)
+            if (!first) body << "    __syncthreads();\n";
+            body << "    uint32_t sX = 0u;\n";
+            for (int b = 0; b < P.k; ++b)
+                body << "    sX ^= (0u - ((T >> " << b << ") & 1u)) & " << P.perm_swz[b] << "u;\n";
+            body << "    const uint32_t wst[4] = {" << rd.wr_swz[0] << "u, " << rd.wr_swz[1] << "u, " << rd.wr_swz[2] << "u, "
+                 << rd.wr_swz[3] << "u};\n#pragma unroll\n    for (int s = 0; s < 4; ++s) if ((xm >> s) & 1u) sX ^= wst[s];\n"
+                    "#pragma unroll\n    for (int j = 0; j < 16; ++j) tile[sX ^ xor_combo<4>(wst, j)] = a[j];\n";
         } else {
             body << "    uint32_t sX = sT;\n#pragma unroll\n    for (int s = 0; s < 4; ++s) if ((xm >> s) & 1u) sX ^= st[s];\n"
                     "#pragma unroll\n    for (int j = 0; j < 16; ++j) tile[sX ^ xor_combo<4>(st, j)] = a[j];\n";
@@ -214,7 +236,7 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
          "__device__ const uint64_t hi_off[" << g.hi_off.size() << "] = {";
     for (size_t j = 0; j < g.hi_off.size(); ++j) o << (j ? ", " : "") << hexu(g.hi_off[j]);
     o << "};\n";
-    o << "extern \"C\" __global__ void __launch_bounds__(" << g.threads << ", " << (g.threads <= 128 ? 4 : (g.threads <= 256 ? 2 : 1))
+    o << "extern \"C\" __global__ void __launch_bounds__(" << g.threads << ", " << spec_min_blocks(g.threads)
       << ") spec_kernel(double2* __restrict__ state, const SpecParams SP, const SpecFactors F) {\n"
          "  extern __shared__ __align__(16) unsigned char smem_raw[];\n  double2* tile = reinterpret_cast<double2*>(smem_raw);\n"
          "  const uint32_t tid = threadIdx.x;\n  uint64_t base = 0;\n  {\n    uint64_t t = blockIdx.x;\n"
@@ -237,6 +259,7 @@ struct CompiledSpec {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t kernel = nullptr;
     size_t smem_attr = 0;
+    bool carveout_set = false;
 };
 
 // Process-wide cache of compiled structures.  Compilation (about a second of NVRTC per group) runs on
@@ -287,6 +310,14 @@ public:
 
     // source -> sm_100a cubin (needs no device: also used by the CPU test suite)
     bool to_cubin(const std::string& src, std::vector<char>& cubin, std::string* err) {
+        if (const char* dir = getenv("QVM_B200_SPEC_DUMP")) {       // debugging aid: keep the generated sources
+            char path[512];
+            snprintf(path, sizeof(path), "%s/spec_%016zx.cu", dir, std::hash<std::string>()(src));
+            if (FILE* fh = fopen(path, "w")) {
+                fwrite(src.data(), 1, src.size(), fh);
+                fclose(fh);
+            }
+        }
         if (!load_nvrtc(err)) return false;
         void* prog = nullptr;
         const char* headers[] = {kRegtileHeaderSource};
@@ -295,8 +326,8 @@ public:
             if (err) *err = "nvrtcCreateProgram failed";
             return false;
         }
-        const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device"};
-        const int rc = compile_(prog, 3, opts);
+        const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-lineinfo"};
+        const int rc = compile_(prog, 4, opts);
         if (rc != 0) {
             if (err) {
                 size_t n = 0;

@@ -546,6 +546,23 @@ __global__ void gather_strided_kernel(const double2* __restrict__ state, uint64_
         dst[j] = state[offset + j * stride];
 }
 
+// Readback through a qubit layout: element j of the result is the amplitude of LOGICAL index
+// offset + j * stride, which lives at the physical index whose bit pos[q] is logical bit q.
+struct LayoutPerm {
+    uint8_t pos[64];
+    int n;
+};
+__global__ void gather_layout_kernel(const double2* __restrict__ state, uint64_t offset, uint64_t stride,
+                                     uint64_t count, const LayoutPerm perm, double2* __restrict__ dst) {
+    for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < count;
+         j += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t logical = offset + j * stride;
+        uint64_t phys = 0;
+        for (int q = 0; q < perm.n; ++q) phys |= ((logical >> q) & 1ull) << perm.pos[q];
+        dst[j] = state[phys];
+    }
+}
+
 // half-shard pack / unpack (global<->local qubit exchange): element j of the half whose bit
 // `local_bit` == bit_value lives at insert(j, local_bit, bit_value).
 __global__ void pack_half_kernel(const double2* __restrict__ state, int local_bit, int bit_value, uint64_t off,

@@ -143,7 +143,9 @@ struct __align__(16) RoundDesc {
     uint16_t ins_mask[5];     // 32: ~((1 << b) - 1) for the register bits b ascending: x + (x & mask) inserts a zero bit
     uint16_t flags;           // 42: bit 0: scale != 1; bits 15..1: number of OPC_TG ops at the end of the batch
     uint8_t reg_phys[5];      // 44: physical position of register slot s (global I/O rounds)
-    uint8_t pad[15];
+    uint8_t pad0;
+    uint16_t wr_swz[5];       // 50: relabelling round only: shared-memory stride of slot s on the WRITE side
+    uint8_t pad[4];
 };
 static_assert(sizeof(RoundDesc) == 64, "RoundDesc layout");
 
@@ -159,6 +161,11 @@ struct RegTileParams {
     int n_runs;               // runs of consecutive non-tile positions
     uint8_t first_reg_phys[8];   // round 0: physical positions of the register slots ...
     uint16_t first_ins[8];       // ... and its insert masks: the tile load needs nothing staged
+    // In-tile qubit relabelling (qvm_encode.h): round `perm_round` (= n_rounds - 2, or -1: none) writes
+    // the amplitude of tile index i to shared-memory slot swz(sigma(i)); the last round then runs in the
+    // new tile coordinates, so the qubit of tile bit b leaves the pass on tile bit sigma(b).
+    int perm_round;
+    uint16_t perm_swz[16];    // swz(1 << sigma(b)) for every tile bit b
     uint64_t shard_bits;
     uint64_t run_start;       // 8 x 8 bits: start position of each run
     uint64_t run_len;         // 8 x 8 bits: length of each run
@@ -211,14 +218,22 @@ QVM_HD uint64_t insert_zero64(uint64_t x, uint32_t pos) {
     return ((x >> pos) << (pos + 1)) | lo;
 }
 
-// Bank-conflict swizzle for the double2 tile: XOR index bits 3..6 into bits 0..2 so that (almost)
-// any three "lowest thread bits" land in distinct 16-byte bank groups.  Linear over XOR.
+// Bank-conflict swizzle for the double2 tile: XOR index bits >= 3 into bits 0..2 so that (almost)
+// any three "lowest thread bits" land in distinct 16-byte bank groups.  Linear over XOR.  Bits 3..6 get
+// the four remaining non-zero patterns; bits 7..12 repeat the cycle (they only become lane bits on the
+// write side of a relabelling round, where the encoder picks an independent triple).
 QVM_HD uint32_t swz(uint32_t i) {
     uint32_t x = i;
     x ^= ((i >> 3) & 1u) * 3u;
     x ^= ((i >> 4) & 1u) * 6u;
     x ^= ((i >> 5) & 1u) * 5u;
     x ^= ((i >> 6) & 1u) * 7u;
+    x ^= ((i >> 7) & 1u) * 1u;
+    x ^= ((i >> 8) & 1u) * 2u;
+    x ^= ((i >> 9) & 1u) * 4u;
+    x ^= ((i >> 10) & 1u) * 3u;
+    x ^= ((i >> 11) & 1u) * 6u;
+    x ^= ((i >> 12) & 1u) * 5u;
     return x;
 }
 
@@ -233,6 +248,8 @@ __host__ __device__ inline size_t regtile_smem_bytes(int k, int low, int n_round
 // Per-CTA view handed to the round body.
 struct RtCta {
     double2* tile;            // shared: 2^k amplitudes (unused when n_rounds == 1)
+    double2* tile_w;          // where rounds write: the same array (the sequential CPU emulator alone reads the
+                              // relabelling round from a snapshot, in place of that round's barrier)
     const OpWord* ops;        // shared: resolved op stream
     const RoundDesc* rounds;  // shared
     const uint64_t* hi_off;   // shared
@@ -241,6 +258,8 @@ struct RtCta {
     const ColdOp* cold;       // global
     int low;
     int n_rounds;
+    int perm_round;           // see RegTileParams
+    const uint16_t* perm_swz;
 };
 
 // ---- prologue: resolve op j for this CTA ---------------------------------------------------------
@@ -681,13 +700,29 @@ QVM_HD void rt_thread_round(const RtCta& c, const int r, const uint32_t tid, dou
 #pragma unroll
         for (int j = 0; j < NA; ++j) *reinterpret_cast<double2*>(q[j]) = a[j];
     } else {
-        // same mapping as this round's load: every thread rewrites exactly the slots it read
+        // same mapping as this round's load: every thread rewrites exactly the slots it read ...
         uint32_t sX = sT;
+        if (r == c.perm_round) {
+            // ... except in the relabelling round: the tile is written in the next round's coordinates
+            // (bit permutation sigma; swz and sigma are linear over XOR, so strides stay constants)
+#if defined(__CUDA_ARCH__)
+            if (!first) __syncthreads();     // every thread has read its slots before any slot is overwritten
+#endif
+            sX = 0;
+            for (uint32_t b = 0, t = T; t; ++b, t >>= 1)
+                if (t & 1u) sX ^= c.perm_swz[b];
+            const uint4 w3 = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(rd) + 48);
+            st[0] = w3.x >> 16;
+            st[1] = w3.y & 0xFFFFu;
+            st[2] = w3.y >> 16;
+            st[3] = w3.z & 0xFFFFu;
+            if (R == 5) st[R - 1] = w3.z >> 16;
+        }
 #pragma unroll
         for (int s = 0; s < R; ++s)
             if ((xm >> s) & 1u) sX ^= st[s];
 #pragma unroll
-        for (int j = 0; j < NA; ++j) c.tile[sX ^ xor_combo<R>(st, j)] = a[j];
+        for (int j = 0; j < NA; ++j) c.tile_w[sX ^ xor_combo<R>(st, j)] = a[j];
     }
 }
 
@@ -705,7 +740,7 @@ QVM_HD uint64_t rt_tile_base(const RegTileParams& P, uint64_t tile_index) {
 #if defined(__CUDACC__)
 template <int MAX_THREADS, int MIN_BLOCKS, bool FULL, int R>
 __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
-regtile_kernel(double2* __restrict__ state, const RegTileParams P) {
+regtile_kernel(double2* __restrict__ state, const __grid_constant__ RegTileParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const size_t tile_bytes = P.n_rounds > 1 ? ((size_t)16 << P.k) : 0;
     OpWord* ops = reinterpret_cast<OpWord*>(smem_raw + tile_bytes);
@@ -734,7 +769,9 @@ regtile_kernel(double2* __restrict__ state, const RegTileParams P) {
     __syncthreads();
 
     RtCta c;
-    c.tile = reinterpret_cast<double2*>(smem_raw);
+    c.tile = c.tile_w = reinterpret_cast<double2*>(smem_raw);
+    c.perm_round = P.perm_round;
+    c.perm_swz = P.perm_swz;
     c.ops = ops;
     c.rounds = rounds;
     c.hi_off = hi_off;

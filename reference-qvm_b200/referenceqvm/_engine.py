@@ -14,6 +14,10 @@ from referenceqvm import _planner
 
 _TILE_BITS = int(os.environ.get("QVM_B200_TILE_BITS", "11"))     # 11 / 4: best gate-apps/s in the round-1 A/B (profiles/)
 _LOW_BITS = int(os.environ.get("QVM_B200_LOW_BITS", "4"))
+#: in-tile qubit relabelling (``_planner.run_relabelled``): passes hand the qubits the next group needs
+#: over to the low positions, so the layout (logical qubit -> physical position) changes as gates run
+_RELABEL = os.environ.get("QVM_B200_RELABEL", "1") != "0"
+_SWAP_MATRIX = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
 
 _classify_cache = {}
 
@@ -123,6 +127,9 @@ class Engine(object):
         self._merger = DiagonalMerger()
         self.gates_queued = 0
         self.groups_launched = 0
+        self.relabel = _RELABEL
+        #: logical qubit -> physical position (bit of the amplitude index in HBM)
+        self.pos_of = list(range(self.n))
 
     @classmethod
     def from_state(cls, device_state, tile_bits=None, low_bits=None):
@@ -142,6 +149,7 @@ class Engine(object):
         assert device_state.n_local == self.n
         self.pending = []
         self._merger.reset()
+        self.pos_of = list(range(self.n))
         self.state.close()
         self.state = device_state
 
@@ -149,6 +157,7 @@ class Engine(object):
     def reset(self):
         self.pending = []
         self._merger.reset()
+        self.pos_of = list(range(self.n))
         self.state.reset_zero(True)
 
     def set_amplitudes(self, amplitudes):
@@ -157,22 +166,58 @@ class Engine(object):
         a = np.asarray(amplitudes).reshape(-1)
         if a.size != (1 << self.n):
             raise ValueError("state of %d amplitudes does not match %d positions" % (a.size, self.n))
+        self.pos_of = list(range(self.n))
         self.state.set_state(a)
 
+    def layout_is_identity(self):
+        return all(p == q for q, p in enumerate(self.pos_of))
+
+    def position(self, qubit):
+        """Physical position (index bit) of a logical qubit: for bit look-ups in ``sample(physical=True)``."""
+        return self.pos_of[qubit]
+
     def amplitudes(self, offset=0, count=None):
+        """Amplitudes in LOGICAL index order (read through the layout; HBM is not rearranged)."""
         self.flush()
-        return self.state.get_state(offset, count)
+        if self.layout_is_identity():
+            return self.state.get_state(offset, count)
+        if count is None:
+            count = (1 << self.n) - offset
+        return self.state.get_layout(offset, 1, count, self.pos_of)
 
     def strided(self, offset, stride, count):
         self.flush()
-        return self.state.get_strided(offset, stride, count)
+        if self.layout_is_identity():
+            return self.state.get_strided(offset, stride, count)
+        return self.state.get_layout(offset, stride, count, self.pos_of)
+
+    def restore_layout(self):
+        """Put every qubit back on its own position (SWAP passes) -- for the few consumers that address
+        the raw buffer: clones, the density-matrix trace / diagonal kernels."""
+        self.flush()
+        if self.layout_is_identity():
+            return
+        pos = list(self.pos_of)
+        at = {p: q for q, p in enumerate(pos)}
+        swaps = []
+        for q in range(self.n):
+            p = pos[q]
+            if p != q:
+                other = at[q]                   # the qubit sitting on q's home position
+                swaps.append(compile_gate(_SWAP_MATRIX, [p, q]))
+                pos[q], pos[other] = q, p
+                at[q], at[p] = q, other
+        for group in _planner.plan(swaps, self.n, self.tile_bits, self.low_bits):
+            self.state.apply_group(group.tile, group.ops)
+            self.groups_launched += 1
+        self.pos_of = list(range(self.n))
 
     def norm2(self):
         self.flush()
         return self.state.norm2()
 
     def clone_state(self):
-        self.flush()
+        self.restore_layout()
         return self.state.clone()
 
     # -- gates -------------------------------------------------------------------------------
@@ -194,29 +239,50 @@ class Engine(object):
         if not self.pending:
             return
         ops, self.pending = self.pending, []
+        if self.relabel and self.n > self.tile_bits:
+            self.groups_launched += _planner.run_relabelled(ops, self.n, self.pos_of, self._launch_relabelled,
+                                                            self.tile_bits, self.low_bits)
+            return
+        if not self.layout_is_identity():
+            ops = [o.remapped(self.pos_of) for o in ops]
         for group in _planner.plan(ops, self.n, self.tile_bits, self.low_bits):
             self.state.apply_group(group.tile, group.ops)
             self.groups_launched += 1
+
+    def _launch_relabelled(self, tile_positions, ops, bring_low):
+        return self.state.apply_group(tile_positions, ops, bring_low=bring_low if bring_low else [],
+                                      n_low=self.low_bits)
 
     # -- measurement -------------------------------------------------------------------------
     def measure(self, qubit, r):
         """MEASURE with a host-drawn uniform r: outcome 0 iff r < p0; collapse + renormalise."""
         self.flush()
-        return self.state.measure(int(qubit), float(r))
+        return self.state.measure(self.pos_of[int(qubit)], float(r))
 
     def prob_zero(self, qubit):
         self.flush()
-        return self.state.prob_zero(int(qubit))
+        return self.state.prob_zero(self.pos_of[int(qubit)])
 
     def density_prob_zero(self, n_rho, qubit):
-        self.flush()
+        self.restore_layout()
         return self.state.density_prob_zero(n_rho, int(qubit))
 
-    def sample(self, uniforms, mode=0, n_rho=0):
-        """Inverse-CDF draws of basis-state indices from |psi|^2 (mode 0) or diag(rho) (mode 1)."""
+    def sample(self, uniforms, mode=0, n_rho=0, physical=False):
+        """Inverse-CDF draws of basis-state indices from |psi|^2 (mode 0) or diag(rho) (mode 1).
+
+        Draws walk the CDF in HBM order.  With ``physical=True`` the raw indices come back (bit
+        ``position(q)`` is qubit q); otherwise they are converted to logical indices."""
+        if mode == 1:
+            self.restore_layout()
         self.flush()
         total = self.state.probs_prepare(mode, n_rho)
-        return self.state.sample(uniforms), total
+        indices = self.state.sample(uniforms)
+        if not physical and not self.layout_is_identity():
+            phys = np.asarray(indices, dtype=np.uint64)
+            indices = np.zeros_like(phys)
+            for q, p in enumerate(self.pos_of):
+                indices |= ((phys >> np.uint64(p)) & np.uint64(1)) << np.uint64(q)
+        return indices, total
 
     def sync(self):
         self.flush()

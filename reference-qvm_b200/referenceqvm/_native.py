@@ -56,7 +56,7 @@ _SIGNATURES = {
     "qvm_set_jit": (C.c_int, [_P, C.c_int]),
     "qvm_jit_wait": (C.c_int, []),
     "qvm_spec_compile_check": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_int, _P, C.c_int, _P, _P, C.c_uint64, _P,
-                                         C.c_uint64]),
+                                         C.c_uint64, C.c_int, C.c_int, _P]),
     "qvm_debug_opcode_hist": (C.c_int, [_P, _P]),
     "qvm_n_local": (C.c_int, [_P]),
     "qvm_device_ptr": (_P, [_P]),
@@ -68,6 +68,8 @@ _SIGNATURES = {
     "qvm_set_state": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P]),
     "qvm_get_state": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P]),
     "qvm_get_strided": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
+    "qvm_get_state_layout": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, _P, _P]),
+    "qvm_apply_group_relabel": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, C.c_uint64, C.c_int, C.c_int, _P, _P]),
     "qvm_copy_state": (C.c_int, [_P, _P]),
     "qvm_norm2": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "qvm_classify": (C.c_int, [C.c_int, _P, _P, C.POINTER(Op), _P]),
@@ -212,14 +214,16 @@ def jit_wait():
     check(lib().qvm_jit_wait())
 
 
-def spec_compile_check(n_local, tile_bits, ops, n_global=0, shard_index=0):
+def spec_compile_check(n_local, tile_bits, ops, n_global=0, shard_index=0, bring_low=(), n_low=0):
     """``qvm_spec_compile_check``: 0 compiled, 1 left to the interpreter; raises with the NVRTC log."""
     ops = [o for o in ops if o.kind != OP_NOP]
     arr, pool, total = marshal_ops(ops)
     tb = np.ascontiguousarray(sorted(tile_bits), dtype=np.int32)
     log = C.create_string_buffer(1 << 16)
+    bl = np.ascontiguousarray(list(bring_low), dtype=np.int32)
     code = lib().qvm_spec_compile_check(n_local, n_global, shard_index, tb.size, tb.ctypes.data, len(ops),
-                                        C.cast(arr, _P), pool.ctypes.data, total, log, len(log))
+                                        C.cast(arr, _P), pool.ctypes.data, total, log, len(log), n_low, bl.size,
+                                        bl.ctypes.data)
     if code < 0:
         raise NativeError(code, log.value.decode("utf-8", "replace") or last_error())
     return code
@@ -322,6 +326,16 @@ class DeviceState(object):
         check(lib().qvm_get_strided(self.handle, offset, stride, count, out.ctypes.data))
         return out
 
+    def get_layout(self, offset, stride, count, pos_of):
+        """Amplitudes of the logical indices offset + j*stride under the layout ``pos_of``."""
+        out = np.empty(int(count), dtype=np.complex128)
+        pos = np.ascontiguousarray(pos_of, dtype=np.int32)
+        code = lib().qvm_get_state_layout(self.handle, offset, stride, count, pos.size, pos.ctypes.data, out.ctypes.data)
+        if code == QVM_ERR_INVALID:
+            raise ValueError(last_error())
+        check(code)
+        return out
+
     def copy_from(self, other):
         check(lib().qvm_copy_state(self.handle, other.handle))
 
@@ -349,11 +363,14 @@ class DeviceState(object):
             raise NotImplementedError(last_error())
         check(code)
 
-    def apply_group(self, tile_bits, ops):
-        """A run of ClassifiedOps in one HBM pass (``qvm_apply_group``)."""
+    def apply_group(self, tile_bits, ops, bring_low=None, n_low=0):
+        """A run of ClassifiedOps in one HBM pass (``qvm_apply_group``).
+
+        With ``bring_low`` (positions of the tile) the pass also relabels qubits inside the tile
+        (``qvm_apply_group_relabel``) and the new position of every tile position is returned."""
         ops = [o for o in ops if o.kind != OP_NOP]
-        if not ops:
-            return
+        if not ops and not bring_low:
+            return None if bring_low is None else sorted(tile_bits)
         arr = (Op * len(ops))()
         total = sum(o.mat.size for o in ops)
         pool = np.empty(max(total, 1), dtype=np.complex128)
@@ -367,13 +384,22 @@ class DeviceState(object):
             pool[off:off + o.mat.size] = o.mat
             off += o.mat.size
         tb = np.ascontiguousarray(sorted(tile_bits), dtype=np.int32)
-        code = lib().qvm_apply_group(self.handle, tb.size, tb.ctypes.data, len(ops), C.cast(arr, _P),
-                                     pool.ctypes.data, total)
+        new_pos = None
+        if bring_low is None:
+            code = lib().qvm_apply_group(self.handle, tb.size, tb.ctypes.data, len(ops), C.cast(arr, _P),
+                                         pool.ctypes.data, total)
+        else:
+            bl = np.ascontiguousarray(bring_low, dtype=np.int32)
+            new_pos = np.empty(tb.size, dtype=np.int32)
+            code = lib().qvm_apply_group_relabel(self.handle, tb.size, tb.ctypes.data, len(ops), C.cast(arr, _P),
+                                                 pool.ctypes.data, total, n_low, bl.size, bl.ctypes.data,
+                                                 new_pos.ctypes.data)
         if code == QVM_ERR_INVALID:
             raise ValueError(last_error())
         if code == QVM_ERR_UNSUPPORTED:
             raise NotImplementedError(last_error())
         check(code)
+        return None if new_pos is None else new_pos.tolist()
 
     def dephase_all(self, n_rho, qubit_mask, factor):
         check(lib().qvm_dephase_all(self.handle, n_rho, qubit_mask, factor))

@@ -136,3 +136,142 @@ def plan(ops, n_local, tile_bits=12, low_bits=5, max_group_ops=MAX_GROUP_OPS):
 def summarize(groups):
     n_ops = sum(len(g.ops) for g in groups)
     return {"groups": len(groups), "ops": n_ops, "ops_per_group": (n_ops / float(len(groups))) if groups else 0.0}
+
+
+# ---------------------------------------------------------------------------------------------
+# Planning with in-tile qubit relabelling
+#
+# Every tile contains the `low` lowest physical positions (256-byte coalescing), so with a fixed layout
+# only k - low tile bits are free to follow the circuit and the qubits parked on the low positions run
+# out of work.  `qvm_apply_group_relabel` lets a pass hand any qubits of its tile over to the low
+# positions on the way out (the tile is transposed in shared memory between rounds anyway), which turns
+# the constraint into: a group may use k qubits, of which at most k - low were not in the previous
+# group's tile.  On the benchmark circuits that takes a quarter off the number of HBM passes.
+#
+# The layout (logical qubit -> physical position) therefore changes from pass to pass, and planning is
+# online: the next group is chosen (in logical qubits) before the current one is launched, the current
+# launch is asked to bring the qubits both groups share to the low positions, and the next group's tile
+# follows from the layout the library reports back.
+
+def _choose_group(ops, deps, done, first, k, max_new, is_old, seed_tile, max_group_ops):
+    """Greedy group in LOGICAL qubits: ops whose dependencies are met and whose dense targets fit a tile
+    of k qubits with at most ``max_new`` qubits q for which ``is_old(q)`` is false."""
+    tile = set(seed_tile)
+    new_count = sum(1 for q in tile if not is_old(q))
+    chosen, in_group = [], set()
+    for i in range(first, min(len(ops), first + LOOKAHEAD)):
+        if done[i]:
+            continue
+        if any(not (done[d] or d in in_group) for d in deps[i]):
+            continue
+        op = ops[i]
+        if op.kind == OP_DENSE:
+            need = [t for t in op.targets if t not in tile]
+            if need:
+                nn = sum(1 for t in need if not is_old(t))
+                if len(tile) + len(need) > k or new_count + nn > max_new:
+                    continue
+                tile.update(need)
+                new_count += nn
+        chosen.append(i)
+        in_group.add(i)
+        if len(chosen) >= max_group_ops:
+            break
+    return tile, chosen
+
+
+def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_group_ops=MAX_GROUP_OPS):
+    """Run ``ops`` (ClassifiedOps on LOGICAL qubits; every dense target currently on a local position)
+    as fused groups with in-tile relabelling.  ``pos_of`` (logical -> physical, mutated in place) is the
+    layout; ``launch(tile_positions, physical_ops, bring_low_positions)`` runs one pass and returns the
+    new position of every tile position (same order as the sorted tile).  Returns the number of passes."""
+    ops = [o for o in ops if o.kind != OP_NOP]
+    n = len(ops)
+    if not n:
+        return 0
+    for o in ops:
+        if o.kind == OP_DENSE:
+            for t in o.targets:
+                if not (0 <= pos_of[t] < n_local):
+                    raise ValueError("dense target %d is not on a local position" % t)
+    k = min(n_local, max(tile_bits, max([len(o.targets) for o in ops if o.kind == OP_DENSE] or [0])))
+    low = min(low_bits, k)
+    if n_local <= k:
+        whole = list(range(n_local))
+        for i in range(0, n, max_group_ops):
+            launch(whole, [o.remapped(pos_of) for o in ops[i:i + max_group_ops]], None)
+        return (n + max_group_ops - 1) // max_group_ops
+
+    deps = dependencies(ops)
+    done = [False] * n
+    qubit_at = {p: q for q, p in enumerate(pos_of)}
+    first = 0
+    passes = 0
+
+    def low_qubits():
+        return [qubit_at[p] for p in range(low)]
+
+    def fixed_choice():
+        """The layout as it is: the qubits on the low positions are in, k - low more may join."""
+        lq = set(low_qubits())
+        return _choose_group(ops, deps, done, first, k, k - low, lambda q: q in lq, lq, max_group_ops)
+
+    cur_tile, cur_ops = fixed_choice()
+    while True:
+        if not cur_ops:
+            raise RuntimeError("planner made no progress at op %d" % first)
+        # physical tile: the low positions, the group's qubits, then the lowest unused positions
+        positions = set(range(low)) | set(pos_of[q] for q in cur_tile)
+        if len(positions) > k:
+            # a gate wider than k - low targets: keep as many low positions as fit (lowest first)
+            positions = set(pos_of[q] for q in cur_tile)
+            for p in range(low):
+                if len(positions) < k:
+                    positions.add(p)
+        p = 0
+        while len(positions) < k:
+            positions.add(p)
+            p += 1
+        tile_positions = sorted(positions)
+        tile_qubits = set(qubit_at[p] for p in tile_positions)
+        for i in cur_ops:
+            done[i] = True
+        while first < n and done[first]:
+            first += 1
+        # the next group, free to take any `low` of this tile's qubits along
+        nxt_tile, nxt_ops = (set(), [])
+        bring = []
+        contiguous = all(tile_positions[j] == j for j in range(low))
+        if first < n and contiguous:
+            nxt_tile, nxt_ops = _choose_group(ops, deps, done, first, k, k - low, lambda q: q in tile_qubits, (),
+                                              max_group_ops)
+            shared = [q for q in nxt_tile if q in tile_qubits]
+            if len(shared) > low:
+                # keep the qubits with the most dense work ahead on the low positions: they are in every tile
+                work = {}
+                for i in range(first, min(n, first + 4 * max(len(nxt_ops), 64))):
+                    if not done[i] and ops[i].kind == OP_DENSE:
+                        for t in ops[i].targets:
+                            work[t] = work.get(t, 0) + 1
+                shared.sort(key=lambda q: (-work.get(q, 0), q))
+                shared = shared[:low]
+            bring = [pos_of[q] for q in shared]
+        phys_ops = [ops[i].remapped(pos_of) for i in cur_ops]
+        new_pos = launch(tile_positions, phys_ops, bring if bring else None)
+        passes += 1
+        if new_pos is not None:
+            moved = [(qubit_at[p], np_) for p, np_ in zip(tile_positions, new_pos) if p != np_]
+            for q, np_ in moved:
+                pos_of[q] = np_
+                qubit_at[np_] = q
+        if first >= n:
+            return passes
+        # the planned next group stands if it fits the layout that came back
+        ok = bool(nxt_ops)
+        if ok:
+            need = set(range(low)) | set(pos_of[q] for q in nxt_tile)
+            ok = len(need) <= k
+        if ok:
+            cur_tile, cur_ops = nxt_tile, nxt_ops
+        else:
+            cur_tile, cur_ops = fixed_choice()

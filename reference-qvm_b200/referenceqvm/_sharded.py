@@ -23,7 +23,7 @@ import numpy as np
 
 from referenceqvm import _native as nat
 from referenceqvm import _planner
-from referenceqvm._engine import _LOW_BITS, _TILE_BITS, DiagonalMerger, compile_gate, expand_op, validate_qubits
+from referenceqvm._engine import _LOW_BITS, _RELABEL, _TILE_BITS, DiagonalMerger, compile_gate, expand_op, validate_qubits
 
 _context = None      # set by enable(); consulted by _engine.make_engine()
 
@@ -97,6 +97,10 @@ class CudaShard(object):
             self.state.apply_group(group.tile, group.ops)
             n += 1
         return n
+
+    def apply_group(self, tile_positions, ops, bring_low, n_low):
+        """One pass with in-tile relabelling; returns the new position of every tile position."""
+        return self.state.apply_group(tile_positions, ops, bring_low=bring_low, n_low=n_low)
 
     def open_peers(self, dist, group):
         """Map every peer's shard into this process (CUDA IPC) so that a global<->local swap is one
@@ -195,6 +199,8 @@ class ShardedEngine(object):
             self.p2p = bool(float(flag.cpu()[0]) > 0.5)
             self._token = self.shard.scalar_tensor([0.0])
         self.pos_of = list(range(self.n))         # logical qubit -> physical position
+        #: in-tile relabelling of local qubits (``_planner.run_relabelled``) when the backend offers it
+        self.relabel = _RELABEL and hasattr(self.shard, "apply_group")
         self.pending = []                         # ClassifiedOps in LOGICAL coordinates
         self._merger = DiagonalMerger()
         self.gates_queued = 0
@@ -316,7 +322,7 @@ class ShardedEngine(object):
                         continue
                 batch.append(i)
                 in_batch.add(i)
-            self._run_batch([ops[i].remapped(self.pos_of) for i in batch])
+            self._run_logical([ops[i] for i in batch])
             for i in batch:
                 done[i] = True
             remaining -= len(batch)
@@ -379,7 +385,22 @@ class ShardedEngine(object):
         if e0 is not None:
             self.timing["swap"].append((e0, self.shard.record_event()))
 
+    def _run_logical(self, batch):
+        """Ops in LOGICAL coordinates whose dense targets are all local right now."""
+        if not batch:
+            return
+        if not (self.relabel and self.n_local > self.tile_bits):
+            return self._run_batch([op.remapped(self.pos_of) for op in batch])
+        e0 = self.shard.record_event() if self.timing is not None else None
+        self.groups_launched += _planner.run_relabelled(
+            batch, self.n_local, self.pos_of,
+            lambda tile, ops, bring: self.shard.apply_group(tile, ops, bring if bring else [], self.low_bits),
+            self.tile_bits, self.low_bits)
+        if e0 is not None:
+            self.timing["batch"].append((e0, self.shard.record_event()))
+
     def _run_batch(self, batch):
+        """Ops in PHYSICAL coordinates, fixed layout."""
         if batch:
             e0 = self.shard.record_event() if self.timing is not None else None
             self.groups_launched += self.shard.apply_groups(batch, self.tile_bits, self.low_bits)
@@ -525,7 +546,11 @@ class ShardedEngine(object):
         self.flush()
         return self._allreduce_sum(self.shard.prob_zero(self.pos_of[int(qubit)]))
 
-    def sample(self, uniforms, mode=0, n_rho=0):
+    def position(self, qubit):
+        """``sample`` returns logical indices here, whatever ``physical`` says: bit q is qubit q."""
+        return qubit
+
+    def sample(self, uniforms, mode=0, n_rho=0, physical=False):
         """Inverse-CDF draws of LOGICAL basis-state indices, identical on every rank."""
         if mode != 0:
             raise NotImplementedError("sharded density sampling")

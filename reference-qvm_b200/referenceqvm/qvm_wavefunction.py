@@ -34,10 +34,11 @@ from referenceqvm.unitary_generator import lifted_gate, resolve_gate, tensor_gat
 LAZY_QUBITS = int(os.environ.get("QVM_B200_LAZY_QUBITS", "30"))
 
 
-def _index_bits(indices):
-    """(trials, 64) uint8 matrix of the little-endian bits of sampled basis-state indices."""
+def _index_bits(indices, num_qubits=63):
+    """(trials, >= num_qubits + 1) uint8 matrix of the little-endian bits of sampled basis-state
+    indices; only the bytes that can hold a set bit are unpacked, column ``num_qubits`` is always 0."""
     by = np.ascontiguousarray(indices, dtype="<u8").view(np.uint8).reshape(-1, 8)
-    return np.unpackbits(by, axis=1, bitorder="little")
+    return np.unpackbits(by[:, :num_qubits // 8 + 1], axis=1, bitorder="little")
 
 
 _SWAP = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
@@ -225,12 +226,12 @@ class QVM_Wavefunction(QAM):
         self._fresh_engine()
         while self.program_counter < split:
             self.transition(self.current_instruction())
-        indices, _ = self._engine.sample(np.random.random_sample(trials))
+        indices, _ = self._engine.sample(np.random.random_sample(trials), physical=True)
         memory = np.repeat(self.classical_memory[None, :], trials, axis=0)
-        bits = _index_bits(indices)
+        bits = _index_bits(indices, self.num_qubits)
         for instr in list(pyquil_program)[split:]:
             q, c = value_get(instr.qubit), value_get(instr.classical_reg)
-            memory[:, c] = bits[:, self._virt[q]]
+            memory[:, c] = bits[:, self._engine.position(self._virt[q])]
         self.program_counter = len(self.program)
         self.classical_memory = memory[-1].copy()
         picked = memory if mask is None else memory[:, mask]
@@ -250,11 +251,12 @@ class QVM_Wavefunction(QAM):
         deterministic = not any(isinstance(i, Measurement) for i in pyquil_program)
         if self.sampling_fast_path and deterministic and trials > 1 and len(qubits) > 0:
             self._simulate(pyquil_program, None)
-            indices, _ = self._engine.sample(np.random.random_sample(trials))
-            bits = _index_bits(indices)
-            # bit 63 is never set (q_limit = 51): it stands in for qubits beyond the register
-            sel = [self._virt[q] if 0 <= q < self.num_qubits else 63 for q in qubits]
-            return bits[:, sel].tolist()
+            indices, _ = self._engine.sample(np.random.random_sample(trials), physical=True)
+            bits = _index_bits(indices, self.num_qubits)
+            # column num_qubits is never set: it stands in for qubits beyond the register
+            sel = [self._engine.position(self._virt[q]) if 0 <= q < self.num_qubits else self.num_qubits
+                   for q in qubits]
+            return np.take(bits, sel, axis=1).tolist()
 
         results = []
         for _ in range(trials):

@@ -1,4 +1,4 @@
-"""Wall-clock timings of BASELINE.json configs 2 and 3 through the public API (not bench lines)."""
+"""Wall-clock timings of BASELINE.json configs 1, 2 and 3 through the public API (not bench lines)."""
 import os
 import sys
 import time
@@ -15,7 +15,26 @@ from referenceqvm.api import QVMConnection  # noqa: E402
 from referenceqvm.qvm_density import INFINITY, NoiseModel  # noqa: E402
 
 
+def config1():
+    # config 1: 10-qubit random circuit, depth 20, QVMConnection.wavefunction (16 KiB state: latency-bound)
+    n, depth = 10, 20
+    spec = orc.random_circuit_spec(n, depth, 1234)
+    prog = spec_program(spec)
+    qvm = QVMConnection()
+    best = None
+    for rep in range(20):
+        t0 = time.perf_counter()
+        wf, _ = qvm.wavefunction(prog)
+        amps = np.asarray(wf.amplitudes)
+        dt = time.perf_counter() - t0
+        best = dt if best is None or dt < best else best
+    st = qvm._engine.stats()
+    print("config1 wavefunction n=10 depth=20: %d gates, best of 20 %.3f ms (%.0f gate-apps/s), norm %.15f, launches %d"
+          % (len(spec), 1e3 * best, len(spec) / best, float(np.vdot(amps, amps).real), st["kernel_launches"]))
+
+
 def main():
+    config1()
     # config 2: 14-qubit density matrix, T2 dephasing on every qubit after every instruction
     n = 14
     spec = [("H", [], [q]) for q in range(n)] + orc.random_circuit_spec(n, 4, 1234)

@@ -23,7 +23,7 @@ def lib():
         stale = not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS)
         if stale:
             nvcc = "/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else "nvcc"
-            cmd = [nvcc, "-std=c++17", "-O2", "-x", "cu", "-shared", "-Xcompiler", "-fPIC",
+            cmd = [nvcc, "-std=c++17", "-O2", "-x", "cu", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
                    "-Wno-deprecated-gpu-targets", "-o", OUT, SRC]
             proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
             if proc.returncode != 0:
@@ -31,14 +31,18 @@ def lib():
         h = C.CDLL(OUT)
         h.qvm_emu_apply_group.restype = C.c_int
         h.qvm_emu_apply_group.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_int,
-                                          C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
+                                          C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p,
+                                          C.c_uint, C.c_int, C.c_void_p]
         _lib = h
     return _lib
 
 
-def apply_group(psi, n_local, tile_bits, ops, n_global=0, shard_index=0, force_full=False, reg_bits=4):
+def apply_group(psi, n_local, tile_bits, ops, n_global=0, shard_index=0, force_full=False, reg_bits=4,
+                bring_low=(), n_low=0):
     """Run one fused group on a host vector through the emulated kernel.  Returns (psi', info)
-    with info = dict(rounds, need_full, status, n_ops); status 1 = encoder asked for the fallback."""
+    with info = dict(rounds, need_full, status, n_ops); status 1 = encoder asked for the fallback.
+    ``bring_low``: positions (members of the tile) whose qubits should leave the pass on positions
+    < n_low; info["new_pos"][j] = position after the pass of the qubit that was at sorted(tile)[j]."""
     ops = [o for o in ops if o.kind != nat.OP_NOP]
     out = np.array(psi, dtype=np.complex128)
     arr = (nat.Op * max(len(ops), 1))()
@@ -55,8 +59,14 @@ def apply_group(psi, n_local, tile_bits, ops, n_global=0, shard_index=0, force_f
         off += o.mat.size
     tb = np.ascontiguousarray(sorted(tile_bits), dtype=np.int32)
     info = np.zeros(38, dtype=np.int32)
+    sigma = np.zeros(16, dtype=np.int32)
+    low_in = 0
+    for p in bring_low:
+        low_in |= 1 << list(tb).index(p)
     rc = lib().qvm_emu_apply_group(out.ctypes.data, n_local, n_global, shard_index, tb.size, tb.ctypes.data,
                                    len(ops), C.cast(arr, C.c_void_p), pool.ctypes.data, total,
-                                   1 if force_full else 0, reg_bits, info.ctypes.data)
-    return out, {"rounds": int(info[0]), "need_full": bool(info[1]), "status": rc, "n_ops": int(info[3]),
+                                   1 if force_full else 0, reg_bits, info.ctypes.data, low_in, n_low,
+                                   sigma.ctypes.data)
+    return out, {"new_pos": [int(tb[sigma[j]]) for j in range(tb.size)],
+                 "rounds": int(info[0]), "need_full": bool(info[1]), "status": rc, "n_ops": int(info[3]),
                  "opc_hist": info[4:36].copy(), "layers": int(info[36]), "dirty_rounds": int(info[37])}

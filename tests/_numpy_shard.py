@@ -88,6 +88,27 @@ class NumpyShard(object):
         self.launches += n
         return n
 
+    def apply_group(self, tile_positions, ops, bring_low, n_low):
+        """One pass with in-tile relabelling, modelled: run the ops, then let every requested position
+        >= n_low trade places with a low position that was not asked for."""
+        for op in ops:
+            lop = localise(op, self.n_local, self.ctx.rank)
+            if lop is not None:
+                self.psi = apply_local(self.psi, lop, self.n_local)
+        self.launches += 1
+        tile = list(tile_positions)
+        new_pos = list(tile)
+        incoming = [p for p in bring_low if p >= n_low]
+        victims = [p for p in range(n_low) if p not in bring_low and p in tile][:len(incoming)]
+        if incoming and victims:
+            idx = np.arange(self.psi.size, dtype=np.int64)
+            for a, b in zip(incoming, victims):
+                new_pos[tile.index(a)], new_pos[tile.index(b)] = b, a
+                differ = ((idx >> a) ^ (idx >> b)) & 1
+                idx = idx ^ (differ * ((1 << a) | (1 << b)))
+            self.psi = self.psi[idx]
+        return new_pos
+
     def _half_index(self, bit, value, off, cnt):
         j = np.arange(off, off + cnt, dtype=np.int64)
         lo = j & ((1 << bit) - 1)

@@ -15,29 +15,41 @@ using namespace qvm;
 
 // one tile: every round runs all threads one after another (the loop boundary is the barrier)
 template <int R>
-static void run_tile(const RegTileParams& P, const RtCta& c, const double2* gbase, unsigned threads, bool full_variant) {
+static void run_tile(const RegTileParams& P, RtCta c, const double2* gbase, unsigned threads, bool full_variant) {
     constexpr int NA = 1 << R;
+    std::vector<double2> snapshot;
     std::vector<double2> pre((size_t)threads * NA);          // round 0's amplitudes (loaded at kernel entry)
     for (uint32_t tid = 0; tid < threads; ++tid) {
         double2 a[NA];
         rt_first_load<R>(P, gbase, tid, a);
         memcpy(&pre[(size_t)tid * NA], a, sizeof(a));
     }
-    for (int r = 0; r < P.n_rounds; ++r)
+    for (int r = 0; r < P.n_rounds; ++r) {
+        // the relabelling round writes other slots than it reads; on the device a barrier separates the
+        // two phases, here the round reads a snapshot of the tile
+        double2* const real_tile = c.tile_w;
+        if (r == P.perm_round && r > 0) {
+            snapshot.assign(real_tile, real_tile + ((size_t)1 << P.k));
+            c.tile = snapshot.data();
+        } else c.tile = real_tile;
         for (uint32_t tid = 0; tid < threads; ++tid) {
             double2 a[NA];
             if (r == 0) memcpy(a, &pre[(size_t)tid * NA], sizeof(a));
             if (full_variant) rt_thread_round<true, R>(c, r, tid, a);
             else rt_thread_round<false, R>(c, r, tid, a);
         }
+    }
 }
 
 extern "C" int qvm_emu_apply_group(double* amps, int n_local, int n_global, uint64_t shard_index, int n_tile,
                                    const int32_t* tile_bits, int n_ops, const qvm_op_t* ops, const double* mats,
-                                   uint64_t mats_entries, int force_full, int reg_bits, int* info /* 38 ints */) {
+                                   uint64_t mats_entries, int force_full, int reg_bits, int* info /* 38 ints */,
+                                   unsigned low_in /* tile-local mask */, int n_low, int* sigma /* 16 ints or null */) {
     EncodedGroup g;
     const int erc = encode_group(n_local, n_global, shard_index, n_tile, tile_bits, n_ops, ops, mats, mats_entries, g,
-                                 reg_bits);
+                                 reg_bits, low_in, n_low);
+    if (sigma)
+        for (int b = 0; b < 16; ++b) sigma[b] = g.sigma[b];
     if (info) {
         info[0] = (int)g.rounds.size();
         info[1] = g.need_full ? 1 : 0;
@@ -48,7 +60,7 @@ extern "C" int qvm_emu_apply_group(double* amps, int n_local, int n_global, uint
         info[37] = g.n_dirty_rounds;
     }
     if (erc != ENC_OK) return erc;
-    if (g.cold.empty()) return 0;
+    if (g.cold.empty() && !g.relabelled) return 0;
     RegTileParams P = g.P;
     P.rounds = g.rounds.data();
     P.hot = g.hot.data();
@@ -66,7 +78,9 @@ extern "C" int qvm_emu_apply_group(double* amps, int n_local, int n_global, uint
         for (int j = 0; j < P.n_patches; ++j) rt_patch_op(P, (uint32_t)(P.n_ops + j), full, recs.data());
         recs[P.n_words].u = make_uint4(0, 0, 0, 0);
         RtCta c;
-        c.tile = tile.data();
+        c.tile = c.tile_w = tile.data();
+        c.perm_round = P.perm_round;
+        c.perm_swz = P.perm_swz;
         c.ops = recs.data();
         c.rounds = g.rounds.data();
         c.hi_off = g.hi_off.data();

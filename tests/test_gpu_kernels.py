@@ -454,3 +454,100 @@ def test_specialised_kernels_background_policy_and_new_angles():
         want = orc.fast_apply_gate(want, np.asarray(m(*params) if params else m, dtype=complex), qubits, n)
     assert np.max(np.abs(got - want)) < TOL
     eng.close()
+
+
+# ---- in-tile qubit relabelling --------------------------------------------------------------------------
+def _logical_view(psi_phys, pos_of):
+    n = len(pos_of)
+    logical = np.arange(1 << n, dtype=np.uint64)
+    phys = np.zeros_like(logical)
+    for q, p in enumerate(pos_of):
+        phys |= ((logical >> np.uint64(q)) & np.uint64(1)) << np.uint64(p)
+    return psi_phys[phys]
+
+
+@pytest.mark.parametrize("jit", [0, 2])
+def test_relabelling_pass_on_device(jit):
+    """qvm_apply_group_relabel: ops are applied and the requested qubits leave the pass on the low
+    positions; the reported layout explains the buffer exactly (interpreted and specialised kernels)."""
+    n, tile = 15, [0, 1, 2, 3, 5, 6, 8, 9, 10, 12, 14]
+    rs = np.random.RandomState(3)
+    psi0 = random_state(n, 17)
+    spec = []
+    for _ in range(30):
+        q = int(rs.choice(tile))
+        c = rs.randint(4)
+        if c == 0:
+            spec.append((G.H, [q]))
+        elif c == 1:
+            spec.append((G.RZ(rs.uniform(0, 6)), [int(rs.randint(n))]))
+        elif c == 2:
+            ctl = int(rs.randint(n))
+            if ctl != q:
+                spec.append((G.CNOT, [ctl, q]))
+        else:
+            a, b = [int(x) for x in rs.permutation(n)[:2]]
+            spec.append((G.CPHASE(rs.uniform(0, 6)), [a, b]))
+    ops = []
+    for m, q in spec:
+        ops += list(_engine.expand_op(_engine.compile_gate(m, q)))
+    want = psi0
+    for m, q in spec:
+        want = orc.fast_apply_gate(want, np.asarray(m, dtype=complex), q, n)
+    for bring, group in (([9, 14, 5], ops), ([12, 1, 6, 10], ops), ([8], []), ([], ops)):
+        st = nat.DeviceState(n)
+        st.set_jit(jit)
+        st.set_state(psi0)
+        new_pos = st.apply_group(tile, group, bring_low=bring, n_low=4)
+        pos_of = list(range(n))
+        for p, np_ in zip(tile, new_pos):
+            pos_of[p] = np_
+        assert sorted(pos_of) == list(range(n)) and all(pos_of[b] < 4 for b in bring)
+        got = st.get_state()
+        expect = want if group else psi0
+        assert np.max(np.abs(_logical_view(got, pos_of) - expect)) < TOL
+        # the layout-aware readback returns logical order directly, whole and strided
+        assert np.array_equal(st.get_layout(0, 1, 1 << n, pos_of), _logical_view(got, pos_of))
+        assert np.array_equal(st.get_layout(5, 7, 1000, pos_of), _logical_view(got, pos_of)[5:5 + 7000:7])
+        if jit == 2 and (group or bring):
+            assert st.stats()["jit_launches"] == 1
+        st.close()
+
+
+@pytest.mark.parametrize("n,depth,seed", [(14, 10, 4), (18, 8, 5), (21, 5, 1234)])
+def test_engine_with_and_without_relabelling(n, depth, seed):
+    """The relabelling planner saves passes and changes nothing else: amplitudes (read through the
+    layout), MEASURE outcomes and the restored buffer all agree with the fixed-layout engine and the oracle."""
+    spec = orc.random_circuit_spec(n, depth, seed)
+    want = np.zeros(1 << n, dtype=complex)
+    want[0] = 1.0
+    for name, params, qubits in spec:
+        m = G.gate_matrix[name]
+        want = orc.fast_apply_gate(want, np.asarray(m(*params) if params else m, dtype=complex), qubits, n)
+    out = {}
+    for relabel in (False, True):
+        eng = _engine.Engine(n)
+        eng.relabel = relabel
+        eng.reset()
+        for name, params, qubits in spec:
+            m = G.gate_matrix[name]
+            eng.queue_matrix(m(*params) if params else m, qubits)
+        amps = eng.amplitudes()
+        assert np.max(np.abs(amps - want)) < TOL
+        assert eng.layout_is_identity() != relabel or n <= eng.tile_bits
+        p0 = [eng.prob_zero(q) for q in range(n)]
+        assert np.max(np.abs(np.array(p0) - [orc.fast_prob_zero(want, q, n) for q in range(n)])) < 1e-12
+        idx, _ = eng.sample(np.random.RandomState(1).random_sample(2000), physical=True)
+        bits = np.stack([(idx >> np.uint64(eng.position(q))) & np.uint64(1) for q in range(n)], axis=1)
+        logical_idx, _ = eng.sample(np.random.RandomState(1).random_sample(2000))
+        assert np.array_equal((bits << np.arange(n, dtype=np.uint64)).sum(axis=1).astype(np.uint64), logical_idx)
+        assert np.all(np.abs(want[logical_idx.astype(np.int64)]) > 0)
+        passes = eng.groups_launched
+        eng.restore_layout()
+        assert eng.layout_is_identity()
+        assert np.max(np.abs(eng.state.get_state() - want)) < TOL
+        outcome, p = eng.measure(n - 1, 0.3)
+        out[relabel] = (passes, outcome, p)
+        eng.close()
+    assert out[True][1:] == pytest.approx(out[False][1:], abs=1e-12)
+    assert out[True][0] <= out[False][0]

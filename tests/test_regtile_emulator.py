@@ -211,7 +211,75 @@ def test_specialised_source_compiles_with_nvrtc():
            if not (o.kind == nat.OP_DENSE and any(t >= n_local for t in o.targets))]
     g = _planner.plan(ops, n_local, 10, 4)[0]
     assert nat.spec_compile_check(n_local, g.tile, g.ops, n_global=n_global, shard_index=3) == 0
+    # relabelling passes (with and without ops): the permuted shared-memory write is generated too
+    g = groups[1]
+    assert nat.spec_compile_check(n, g.tile, g.ops, bring_low=list(g.tile[-3:]), n_low=4) == 0
+    assert nat.spec_compile_check(n, g.tile, [], bring_low=[g.tile[5]], n_low=4) == 0
     # a group with generic dense matrices is left to the interpreter
     rs = np.random.RandomState(0)
     dense = [_engine.compile_gate(rs.standard_normal((4, 4)) + 0j, [3, 9])]
     assert nat.spec_compile_check(12, tuple(range(12)), dense) == 1
+
+
+# ---- in-tile qubit relabelling (qvm_apply_group_relabel / _planner.run_relabelled) --------------------
+def logical_view(psi_phys, pos_of):
+    """Amplitudes in logical index order of a vector stored under the layout pos_of."""
+    n = len(pos_of)
+    logical = np.arange(1 << n, dtype=np.uint64)
+    phys = np.zeros_like(logical)
+    for q, p in enumerate(pos_of):
+        phys |= ((logical >> np.uint64(q)) & np.uint64(1)) << np.uint64(p)
+    return psi_phys[phys]
+
+
+def run_emulated_relabelled(psi, ops, n, tile_bits, low_bits):
+    pos_of = list(range(n))
+    box = {"psi": psi, "moved": 0}
+
+    def launch(tile, phys_ops, bring):
+        new, info = _emu.apply_group(box["psi"], n, tile, phys_ops, reg_bits=REG_BITS, bring_low=bring or (),
+                                     n_low=low_bits)
+        assert info["status"] == 0
+        for p in (bring or ()):
+            assert info["new_pos"][list(tile).index(p)] < low_bits          # the library did what was asked
+        box["moved"] += sum(1 for a, b in zip(tile, info["new_pos"]) if a != b)
+        box["psi"] = new
+        return info["new_pos"]
+
+    passes = _planner.run_relabelled(ops, n, pos_of, launch, tile_bits, low_bits)
+    return box["psi"], pos_of, passes, box["moved"]
+
+
+@pytest.mark.parametrize("n,depth,seed,tile,low", [(14, 10, 1, 9, 4), (15, 8, 2, 10, 4), (14, 12, 3, 11, 4),
+                                                   (15, 6, 1234, 12, 5), (13, 14, 5, 9, 3)])
+def test_relabelled_random_circuit(n, depth, seed, tile, low):
+    spec = orc.random_circuit_spec(n, depth, seed)
+    ops = []
+    for op in compile_spec(spec):
+        ops += list(_engine.expand_op(op))
+    psi0 = random_state(n, seed)
+    want = psi0
+    for name, params, qubits in spec:
+        m = G.gate_matrix[name]
+        want = orc.fast_apply_gate(want, np.asarray(m(*params) if params else m, dtype=complex), qubits, n)
+    got, pos_of, passes, moved = run_emulated_relabelled(psi0, ops, n, tile, low)
+    assert sorted(pos_of) == list(range(n))
+    assert np.max(np.abs(logical_view(got, pos_of) - want)) < TOL
+    fixed = len(_planner.plan(ops, n, tile, low))
+    assert passes <= fixed and moved > 0, (passes, fixed, moved)
+
+
+def test_relabel_only_pass_and_partial_requests():
+    """A pass without ops still relabels; requests for qubits already low, or more requests than low
+    positions, are honoured as far as possible and reported truthfully."""
+    n, tile = 13, [0, 1, 2, 3, 5, 6, 8, 9, 10, 11, 12]
+    psi0 = random_state(n, 21)
+    for bring in ([5], [12, 9, 6, 8], [1, 10], [0, 1, 2, 3], [5, 6, 8, 9, 10], []):
+        got, info = _emu.apply_group(psi0, n, tile, [], reg_bits=REG_BITS, bring_low=bring, n_low=4)
+        assert info["status"] == 0
+        pos_of = list(range(n))
+        for j, p in enumerate(tile):
+            pos_of[p] = info["new_pos"][j]
+        assert sorted(pos_of) == list(range(n))
+        assert sum(1 for b in bring if pos_of[b] < 4) == min(len(bring), 4)
+        assert np.array_equal(logical_view(got, pos_of), psi0)
