@@ -426,11 +426,6 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
                                                  (int)ss.smem));
                 const_cast<CompiledSpec*>(cs)->smem_attr = ss.smem;
             }
-            if (!cs->carveout_set) {      // several 32-64 KB tiles per SM: ask for the largest shared-memory carve-out
-                cudaFuncSetAttribute((const void*)cs->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-                cudaGetLastError();
-                const_cast<CompiledSpec*>(cs)->carveout_set = true;
-            }
             double2* amps = q->amps;
             SpecParams sp = ss.params;
             void* args[3] = {&amps, &sp, const_cast<double*>(ss.factors.data())};

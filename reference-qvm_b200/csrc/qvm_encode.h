@@ -283,13 +283,14 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
     }
 
     // ---- fix the relabelling permutation ----------------------------------------------------------
-    // The round before the last one writes the tile in the new coordinates.  Its quarter-warps (lanes on
-    // its three lowest thread bits) store 8 x 16 bytes at once: conflict-free when the swizzle patterns of
-    // the three images under sigma are linearly independent.  Try every pairing of incoming and outgoing
-    // bits and keep the best.
+    // Round 0 -- which reads HBM, not the tile, so no thread waits for another's slots -- writes the tile
+    // in the new coordinates and every later round runs in them.  Its quarter-warps (lanes on its three
+    // lowest thread bits) store 8 x 16 bytes at once: conflict-free when the swizzle patterns of the three
+    // images under sigma are linearly independent.  Try every pairing of incoming and outgoing bits and
+    // keep the best.
     uint8_t* sigma = out.sigma;
     if (relabel) {
-        const PlannedRound& wr = rounds[rounds.size() - 2];
+        const PlannedRound& wr = rounds[0];
         int lane_bit[3], nl = 0;
         for (int b = 0; b < n_tile && nl < 3; ++b)
             if (wr.slot_of(b) < 0) lane_bit[nl++] = b;
@@ -323,7 +324,7 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
             sigma[vic_bit[best_perm[i]]] = (uint8_t)in_bit[i];
         }
         out.relabelled = true;
-        P.perm_round = (int)rounds.size() - 2;
+        P.perm_round = 0;
         for (int b = 0; b < n_tile; ++b) P.perm_swz[b] = (uint16_t)swz(1u << sigma[b]);
     }
 
@@ -372,7 +373,7 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
     hot.reserve(n);
     cold.reserve(n);
     int dirty_round = -1, dirty_best = -1;
-    std::vector<LocalOp> lops_new;       // the ops in the tile coordinates of the last round (after sigma)
+    std::vector<LocalOp> lops_new;       // the ops in the tile coordinates of rounds >= 1 (after sigma)
     if (relabel) {
         auto map_mask = [&](uint32_t m) {
             uint32_t o = 0;
@@ -390,7 +391,7 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
         }
     }
     for (size_t r = 0; r < rounds.size(); ++r) {
-        const bool new_coords = relabel && r + 1 == rounds.size();
+        const bool new_coords = relabel && r >= 1;
         if (new_coords)
             for (int s = 0; s < R; ++s) rounds[r].slot_bit[s] = sigma[rounds[r].slot_bit[s]];
         const std::vector<LocalOp>& lops = new_coords ? lops_new : lops_old;

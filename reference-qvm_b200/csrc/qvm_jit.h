@@ -88,6 +88,15 @@ inline unsigned spec_min_blocks(unsigned threads) {
     return b < 1 ? 1 : b;
 }
 
+// QVM_B200_SPEC_STREAM=1: tile loads / stores with the evict-first (.cs) cache operator.
+inline bool spec_streaming() {
+    static const bool on = [] {
+        const char* e = getenv("QVM_B200_SPEC_STREAM");
+        return e && atoi(e) != 0;
+    }();
+    return on;
+}
+
 // Source for one encoded group (lean R = 4 groups only).  Factors never appear as literals: F.v[i]
 // indexes a by-value kernel argument -- first the encoder's matrix pool, then the factors the encoder
 // inlined into the op stream, then the round scalars.
@@ -133,7 +142,9 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
                  << "];\n      const int64_t b[4] = {";
             for (int s = 0; s < 4; ++s) body << (s ? ", " : "") << "(int64_t)(16ull << " << (int)rd.reg_phys[s] << ")";
             body << "};\n      const char* q[16];\n      add_tree<4>(reinterpret_cast<const char*>(gbase + gT), b, q);\n"
-                    "#pragma unroll\n      for (int j = 0; j < 16; ++j) a[j] = *reinterpret_cast<const double2*>(q[j]);\n    }\n";
+                    "#pragma unroll\n      for (int j = 0; j < 16; ++j) a[j] = "
+                 << (spec_streaming() ? "__ldcs(reinterpret_cast<const double2*>(q[j]))" : "*reinterpret_cast<const double2*>(q[j])")
+                 << ";\n    }\n";
         } else {
             body << "#pragma unroll\n    for (int j = 0; j < 16; ++j) a[j] = tile[sT ^ xor_combo<4>(st, j)];\n";
         }
@@ -211,7 +222,9 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
             for (int s = 0; s < 4; ++s) body << (s ? ", " : "") << "(int64_t)(16ull << " << (int)rd.reg_phys[s] << ")";
             body << "};\n#pragma unroll\n      for (int s = 0; s < 4; ++s) if ((xm >> s) & 1u) { p0 += b[s]; b[s] = -b[s]; }\n"
                     "      char* q[16];\n      add_tree<4>(p0, b, q);\n"
-                    "#pragma unroll\n      for (int j = 0; j < 16; ++j) *reinterpret_cast<double2*>(q[j]) = a[j];\n    }\n";
+                    "#pragma unroll\n      for (int j = 0; j < 16; ++j) "
+                 << (spec_streaming() ? "__stcs(reinterpret_cast<double2*>(q[j]), a[j])" : "*reinterpret_cast<double2*>(q[j]) = a[j]")
+                 << ";\n    }\n";
         } else if (r == P.perm_round) {
             // relabelling round: the tile is written in the last round's coordinates (qvm_encode.h)
             if (!first) body << "    __syncthreads();\n";
@@ -259,7 +272,6 @@ struct CompiledSpec {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t kernel = nullptr;
     size_t smem_attr = 0;
-    bool carveout_set = false;
 };
 
 // Process-wide cache of compiled structures.  Compilation (about a second of NVRTC per group) runs on

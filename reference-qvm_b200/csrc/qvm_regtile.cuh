@@ -161,9 +161,9 @@ struct RegTileParams {
     int n_runs;               // runs of consecutive non-tile positions
     uint8_t first_reg_phys[8];   // round 0: physical positions of the register slots ...
     uint16_t first_ins[8];       // ... and its insert masks: the tile load needs nothing staged
-    // In-tile qubit relabelling (qvm_encode.h): round `perm_round` (= n_rounds - 2, or -1: none) writes
-    // the amplitude of tile index i to shared-memory slot swz(sigma(i)); the last round then runs in the
-    // new tile coordinates, so the qubit of tile bit b leaves the pass on tile bit sigma(b).
+    // In-tile qubit relabelling (qvm_encode.h): round `perm_round` (0, or -1: none) writes the amplitude
+    // of tile index i to shared-memory slot swz(sigma(i)); the later rounds run in the new tile
+    // coordinates, so the qubit of tile bit b leaves the pass on tile bit sigma(b).
     int perm_round;
     uint16_t perm_swz[16];    // swz(1 << sigma(b)) for every tile bit b
     uint64_t shard_bits;

@@ -550,12 +550,18 @@ class ShardedEngine(object):
         """``sample`` returns logical indices here, whatever ``physical`` says: bit q is qubit q."""
         return qubit
 
-    def sample(self, uniforms, mode=0, n_rho=0, physical=False):
-        """Inverse-CDF draws of LOGICAL basis-state indices, identical on every rank."""
+    def sample(self, uniforms, mode=0, n_rho=0, physical=False, logical_order=False):
+        """Inverse-CDF draws of LOGICAL basis-state indices, identical on every rank.
+
+        The CDF is walked in HBM order (rank-major, then the shard's physical index) and the drawn
+        indices are translated through the layout -- the same distribution as a walk in logical order
+        without moving a single amplitude.  ``logical_order=True`` restores the layout first (exchanges
+        and SWAP passes), so that the draws equal ``searchsorted`` on the logical CDF uniform by uniform."""
         if mode != 0:
             raise NotImplementedError("sharded density sampling")
         self.flush()
-        self.restore_layout()       # CDF in logical index order: draws match the single-GPU path
+        if logical_order:
+            self.restore_layout()
         import torch
         u = self._broadcast_floats(uniforms)
         local_total = self.shard.probs_prepare()

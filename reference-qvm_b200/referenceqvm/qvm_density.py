@@ -122,13 +122,16 @@ class QVM_Density(QAM):
             self._engine = None
         if self._engine is None:
             self._engine = _engine.Engine(2 * n, device=self.device)
+            # rho is handed out as a view of the raw buffer (DeviceDensity) and its trace / diagonal kernels
+            # address rows and columns by position: keep every qubit on its own position
+            self._engine.relabel = False
         return self._engine
 
     @property
     def _density(self):
         if self._engine is None:
             return None
-        self._engine.flush()
+        self._engine.restore_layout()
         return DeviceDensity(self._engine.state, self._engine.n // 2)
 
     @_density.setter
@@ -261,6 +264,7 @@ class QVM_Density(QAM):
             raise ValueError("no density of %r qubits is loaded" % (n,))
         scratch = _engine.Engine.from_state(self._engine.clone_state(), self._engine.tile_bits,
                                             self._engine.low_bits)
+        scratch.relabel = False
         if not (0 <= index < n):
             raise ValueError("Gate index out of range!")
         scratch.queue_matrix(kraus_superoperator(operators), [index + n, index])

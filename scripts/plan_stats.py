@@ -23,6 +23,17 @@ class NullShard(object):
         self.ops_per_group += [len(g.ops) for g in groups]
         return len(groups)
 
+    def apply_group(self, tile, ops, bring_low, n_low):
+        """Relabelling pass, modelled: every request is honoured."""
+        self.ops_per_group.append(len(ops))
+        tile = list(tile)
+        new_pos = list(tile)
+        incoming = [p for p in bring_low if p >= n_low]
+        victims = [p for p in range(n_low - 1, -1, -1) if p not in bring_low][:len(incoming)]
+        for a, b in zip(incoming, victims):
+            new_pos[tile.index(a)], new_pos[tile.index(b)] = b, a
+        return new_pos
+
     def alloc(self, n):
         return None
 
@@ -44,8 +55,12 @@ def main():
         ops.append(_engine.compile_gate(m(*params) if params else m, qubits))
     if world == 1:
         t0 = time.time()
-        groups = _planner.plan(ops, n, 12, 5)
-        print("groups", len(groups), "ops", len(ops), "plan s", time.time() - t0)
+        groups = _planner.plan(ops, n, _engine._TILE_BITS, _engine._LOW_BITS)
+        print("fixed layout: groups", len(groups), "ops", len(ops), "plan s", time.time() - t0)
+        shard = NullShard(n, None)
+        passes = _planner.run_relabelled(ops, n, list(range(n)), lambda t, o, b: shard.apply_group(t, o, b or [], _engine._LOW_BITS),
+                                         _engine._TILE_BITS, _engine._LOW_BITS)
+        print("relabelling: groups", passes)
         return
     ctx = _sharded.ShardContext(None, 0, world, 0)
     eng = _sharded.ShardedEngine(n, ctx, backend_factory=NullShard)

@@ -70,8 +70,17 @@ def main():
     shots = np.asarray(qvm.run_and_measure(spec_program(spec), list(range(n)), trials=20000))
     idx = (shots << np.arange(n)).sum(axis=1)
     u = np.random.RandomState(11).random_sample(20000)
-    ref = orc.inverse_cdf_sample(np.abs(want) ** 2, u)
-    assert np.mean(idx == ref) > 0.999          # same uniforms (rank 0's), same CDF order
+    # same uniforms (rank 0's); the CDF is walked in HBM order, indices come back through the layout
+    logical = np.arange(1 << n, dtype=np.int64)
+    phys = np.zeros_like(logical)
+    for q, p in enumerate(qvm._engine.pos_of):
+        phys |= ((logical >> q) & 1) << p
+    probs_hbm = np.empty(1 << n)
+    probs_hbm[phys] = np.abs(want) ** 2
+    logical_of_phys = np.empty_like(logical)
+    logical_of_phys[phys] = logical
+    ref = logical_of_phys[np.asarray(orc.inverse_cdf_sample(probs_hbm, u), dtype=np.int64)]
+    assert np.mean(idx == ref) > 0.999
     dist.barrier()
     dist.destroy_process_group()
     print("rank %d/%d ok" % (rank, world))

@@ -68,11 +68,24 @@ def main():
             m = G.gate_matrix[name]
             eng.queue_matrix(m(*params) if params else m, qubits)
         u = np.random.RandomState(seed).random_sample(257)
+        probs = np.abs(want) ** 2
+        # default: the CDF is walked in HBM order and indices are translated through the layout
         idx, total = eng.sample(u if rank == 0 else np.zeros(257))
         assert abs(total - 1.0) < 1e-12
-        probs = np.abs(want) ** 2
+        logical = np.arange(1 << n, dtype=np.int64)
+        phys = np.zeros_like(logical)
+        for q, p in enumerate(eng.pos_of):
+            phys |= ((logical >> q) & 1) << p
+        probs_hbm = np.empty_like(probs)
+        probs_hbm[phys] = probs
+        logical_of_phys = np.empty_like(logical)
+        logical_of_phys[phys] = logical
+        ref = logical_of_phys[np.asarray(orc.inverse_cdf_sample(probs_hbm, u), dtype=np.int64)]
+        assert np.array_equal(idx.astype(np.int64), ref)
+        # on request the engine restores the logical layout first: the CDF order is the reference's
+        idx, total = eng.sample(u if rank == 0 else np.zeros(257), logical_order=True)
+        assert eng.pos_of == list(range(n))
         ref = orc.inverse_cdf_sample(probs, u)
-        # the engine restores the logical layout first, so the CDF order is the reference's
         assert np.array_equal(idx.astype(np.int64), np.asarray(ref, dtype=np.int64))
         eng.close()
         checked += 1
