@@ -220,20 +220,22 @@ QVM_HD uint64_t insert_zero64(uint64_t x, uint32_t pos) {
 
 // Bank-conflict swizzle for the double2 tile: XOR index bits >= 3 into bits 0..2 so that (almost)
 // any three "lowest thread bits" land in distinct 16-byte bank groups.  Linear over XOR.  Bits 3..6 get
-// the four remaining non-zero patterns; bits 7..12 repeat the cycle (they only become lane bits on the
-// write side of a relabelling round, where the encoder picks an independent triple).
+// the four remaining non-zero patterns.  Bits 7..12 only become lane bits on the write side of a
+// relabelling round, next to the lowest old lane bits (patterns 1, 2): they get patterns with bit 2 set
+// (any of those completes {1, 2} to a basis, and any three distinct ones are a basis themselves); the
+// encoder picks the pairing.
 QVM_HD uint32_t swz(uint32_t i) {
     uint32_t x = i;
     x ^= ((i >> 3) & 1u) * 3u;
     x ^= ((i >> 4) & 1u) * 6u;
     x ^= ((i >> 5) & 1u) * 5u;
     x ^= ((i >> 6) & 1u) * 7u;
-    x ^= ((i >> 7) & 1u) * 1u;
-    x ^= ((i >> 8) & 1u) * 2u;
-    x ^= ((i >> 9) & 1u) * 4u;
-    x ^= ((i >> 10) & 1u) * 3u;
-    x ^= ((i >> 11) & 1u) * 6u;
-    x ^= ((i >> 12) & 1u) * 5u;
+    x ^= ((i >> 7) & 1u) * 4u;
+    x ^= ((i >> 8) & 1u) * 6u;
+    x ^= ((i >> 9) & 1u) * 5u;
+    x ^= ((i >> 10) & 1u) * 7u;
+    x ^= ((i >> 11) & 1u) * 4u;
+    x ^= ((i >> 12) & 1u) * 6u;
     return x;
 }
 
