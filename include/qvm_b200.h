@@ -164,6 +164,13 @@ int qvm_dephase_all(qvm_t* q, int n_rho_qubits, uint64_t qubit_mask, double fact
 /* One cooperative kernel: p0 = sum_{bit=0} |amp|^2 (warp-shuffle + block reduce), outcome 0 iff
  * r < p0, zero the other half and scale by 1/sqrt(p_outcome).  Single-shard handles only. */
 int qvm_measure(qvm_t* q, int qubit, double r, int* outcome, double* p0);
+/* Batched trials (qvm_wavefunction.py:266-283: run() re-simulates the program once per trial).  The
+ * handle's 2^n_local amplitudes are read as 2^(n_local - n_per_trial) independent n_per_trial-qubit
+ * states, one per trial; gates applied to positions < n_per_trial act on all of them in the same pass.
+ * qvm_reset_batched sets every trial to |0..0>; qvm_measure_batched measures `qubit` in every trial
+ * with that trial's own uniform (uniforms / outcomes / p0: one entry per trial slot). */
+int qvm_reset_batched(qvm_t* q, int n_per_trial);
+int qvm_measure_batched(qvm_t* q, int n_per_trial, int qubit, const double* uniforms, int32_t* outcomes, double* p0);
 /* The two halves of the above for sharded states (host all-reduces p0 in between). */
 int qvm_prob_zero(qvm_t* q, int qubit, double* p0_partial);
 int qvm_collapse(qvm_t* q, int qubit, int outcome, double scale);

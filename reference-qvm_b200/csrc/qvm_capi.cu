@@ -955,6 +955,57 @@ int qvm_measure(qvm_t* q, int qubit, double r, int* outcome, double* p0) {
     return QVM_OK;
 }
 
+// ---- batched trials ------------------------------------------------------------------------------------
+int qvm_reset_batched(qvm_t* q, int n_per_trial) {
+    QVM_CHECK_HANDLE(q);
+    if (q->n_global) return fail(QVM_ERR_INVALID, "batched trials are single-shard");
+    if (n_per_trial < 1 || n_per_trial > q->n_local) return fail(QVM_ERR_INVALID, "bad qubits per trial %d", n_per_trial);
+    batched_reset_kernel<<<grid_for(q, q->n_elems, 256, 4), 256, 0, q->stream>>>(q->amps, q->n_elems, n_per_trial);
+    QVM_CUDA(q, cudaGetLastError());
+    q->sample_mode = -1;
+    q->stats.kernel_launches += 1;
+    q->stats.hbm_bytes += 16ull * q->n_elems;
+    return QVM_OK;
+}
+
+int qvm_measure_batched(qvm_t* q, int n_per_trial, int qubit, const double* uniforms, int32_t* outcomes, double* p0) {
+    QVM_CHECK_HANDLE(q);
+    if (!uniforms || !outcomes) return fail(QVM_ERR_INVALID, "null pointer");
+    if (q->n_global) return fail(QVM_ERR_INVALID, "batched trials are single-shard");
+    if (n_per_trial < 1 || n_per_trial > q->n_local) return fail(QVM_ERR_INVALID, "bad qubits per trial %d", n_per_trial);
+    if (qubit < 0 || qubit >= n_per_trial) return fail(QVM_ERR_INVALID, "qubit %d out of range", qubit);
+    const uint64_t segs = 1ull << (q->n_local - n_per_trial);
+    if (segs > (1ull << 20)) return fail(QVM_ERR_UNSUPPORTED, "too many segments");
+    const size_t bytes = (size_t)segs * (sizeof(double) * 2 + sizeof(int32_t));
+    unsigned char* dev = nullptr;
+    QVM_CUDA(q, cudaMallocAsync(&dev, bytes, q->stream));
+    double* d_r = reinterpret_cast<double*>(dev);
+    double* d_p0 = d_r + segs;
+    int32_t* d_out = reinterpret_cast<int32_t*>(d_p0 + segs);
+    int rc = QVM_OK;
+    std::vector<double> host_p0(segs);
+    if (cudaMemcpyAsync(d_r, uniforms, segs * sizeof(double), cudaMemcpyHostToDevice, q->stream) != cudaSuccess)
+        rc = fail(QVM_ERR_CUDA, "upload of the uniforms failed");
+    if (rc == QVM_OK) {
+        const int threads = n_per_trial >= 12 ? 256 : (n_per_trial >= 8 ? 64 : 32);
+        batched_measure_kernel<<<(unsigned)segs, threads, 0, q->stream>>>(q->amps, n_per_trial, qubit, d_r, d_out, d_p0);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(QVM_ERR_CUDA, "batched_measure_kernel launch failed");
+    }
+    if (rc == QVM_OK && (cudaMemcpyAsync(outcomes, d_out, segs * sizeof(int32_t), cudaMemcpyDeviceToHost, q->stream) != cudaSuccess ||
+                         cudaMemcpyAsync(host_p0.data(), d_p0, segs * sizeof(double), cudaMemcpyDeviceToHost, q->stream) != cudaSuccess ||
+                         cudaStreamSynchronize(q->stream) != cudaSuccess))
+        rc = fail(QVM_ERR_CUDA, "readback of the outcomes failed");
+    cudaFreeAsync(dev, q->stream);
+    if (rc != QVM_OK) return rc;
+    if (p0) memcpy(p0, host_p0.data(), segs * sizeof(double));
+    q->sample_mode = -1;
+    q->stats.kernel_launches += 1;
+    q->stats.hbm_bytes += 40ull * q->n_elems;
+    q->stats.h2d_bytes += segs * sizeof(double);
+    q->stats.d2h_bytes += segs * (sizeof(double) + sizeof(int32_t));
+    return QVM_OK;
+}
+
 int qvm_prob_zero(qvm_t* q, int qubit, double* p0_partial) {
     QVM_CHECK_HANDLE(q);
     if (!p0_partial) return fail(QVM_ERR_INVALID, "null pointer");

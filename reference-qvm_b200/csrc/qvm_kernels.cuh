@@ -421,6 +421,33 @@ __global__ void measure_kernel(double2* __restrict__ state, uint64_t n_elems, in
     }
 }
 
+// Batched trials: the shard holds 2^(n_local - n) independent n-qubit states ("segments", one per
+// trial of run()); each block owns one segment.  Same arithmetic as measure_kernel, per segment, with
+// that trial's own uniform: p0 -> outcome 0 iff r < p0 -> zero the other half, scale by 1/sqrt(p).
+__global__ void batched_measure_kernel(double2* __restrict__ state, int n, int qubit, const double* __restrict__ r,
+                                       int32_t* __restrict__ outcomes, double* __restrict__ p0_out) {
+    __shared__ double scratch[33];
+    const uint64_t seg = blockIdx.x;
+    double2* s = state + (seg << n);
+    const uint64_t n_elems = 1ull << n;
+    double acc = partial_prob(s, n_elems, n, qubit, 0, 0, 0, threadIdx.x, blockDim.x);
+    const double p0 = block_sum(acc, scratch);
+    const int outcome = (r[seg] < p0) ? 0 : 1;
+    const double scale = 1.0 / sqrt(outcome ? (1.0 - p0) : p0);
+    collapse_range(s, n_elems, qubit, outcome, scale, threadIdx.x, blockDim.x);
+    if (threadIdx.x == 0) {
+        outcomes[seg] = outcome;
+        p0_out[seg] = p0;
+    }
+}
+
+// every segment := |0...0>
+__global__ void batched_reset_kernel(double2* __restrict__ state, uint64_t n_elems, int n) {
+    const uint64_t mask = (1ull << n) - 1ull;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_elems; i += (uint64_t)gridDim.x * blockDim.x)
+        state[i] = make_double2((i & mask) ? 0.0 : 1.0, 0.0);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Sampling: two-level CDF + per-shot binary search
 // ---------------------------------------------------------------------------------------------

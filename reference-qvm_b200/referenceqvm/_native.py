@@ -67,6 +67,8 @@ _SIGNATURES = {
     "qvm_reset_zero": (C.c_int, [_P, C.c_int]),
     "qvm_set_state": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P]),
     "qvm_get_state": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P]),
+    "qvm_reset_batched": (C.c_int, [_P, C.c_int]),
+    "qvm_measure_batched": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "qvm_get_strided": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
     "qvm_get_state_layout": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, _P, _P]),
     "qvm_apply_group_relabel": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, C.c_uint64, C.c_int, C.c_int, _P, _P]),
@@ -413,6 +415,25 @@ class DeviceState(object):
             raise ValueError(last_error())
         check(code)
         return outcome.value, p0.value
+
+    def reset_batched(self, n_per_trial):
+        """Every 2^n_per_trial-amplitude segment := |0..0> (one segment per trial of a batched run())."""
+        check(lib().qvm_reset_batched(self.handle, n_per_trial))
+
+    def measure_batched(self, n_per_trial, qubit, uniforms):
+        """MEASURE ``qubit`` in every segment with that segment's own uniform: (outcomes, p0) arrays."""
+        segs = 1 << (self.n_local - n_per_trial)
+        u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        if u.size != segs:
+            raise ValueError("%d uniforms for %d trial slots" % (u.size, segs))
+        outcomes = np.empty(segs, dtype=np.int32)
+        p0 = np.empty(segs, dtype=np.float64)
+        code = lib().qvm_measure_batched(self.handle, n_per_trial, qubit, u.ctypes.data, outcomes.ctypes.data,
+                                         p0.ctypes.data)
+        if code == QVM_ERR_INVALID:
+            raise ValueError(last_error())
+        check(code)
+        return outcomes, p0
 
     def prob_zero(self, qubit):
         v = C.c_double(0.0)

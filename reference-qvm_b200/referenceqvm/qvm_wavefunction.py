@@ -21,7 +21,9 @@ import os
 import numpy as np
 
 from pyquil.quil import Program  # noqa: F401  (kept for parity with the reference's namespace)
-from pyquil.quilbase import (Gate, Halt, Jump, JumpConditional, JumpTarget, Measurement)
+from pyquil.quilbase import (BinaryClassicalInstruction, ClassicalAnd, ClassicalExchange, ClassicalFalse,
+                             ClassicalMove, ClassicalNot, ClassicalOr, ClassicalTrue, Gate, Halt, Jump,
+                             JumpConditional, JumpTarget, Measurement, UnaryClassicalInstruction)
 from pyquil.wavefunction import Wavefunction
 
 from referenceqvm import _engine
@@ -217,6 +219,8 @@ class QVM_Wavefunction(QAM):
             # no MEASURE at all: every trial is the same deterministic run
             classical_vals = self._run_once(pyquil_program, classical_addresses)
             return [list(classical_vals) for _ in range(trials)]
+        if split is None and trials > 1 and self.sampling_fast_path and self._batchable(pyquil_program):
+            return self._run_batched(pyquil_program, classical_addresses, trials)
         if split is None or trials <= 1:
             return [self._run_once(pyquil_program, classical_addresses) for _ in range(trials)]
 
@@ -236,6 +240,110 @@ class QVM_Wavefunction(QAM):
         self.classical_memory = memory[-1].copy()
         picked = memory if mask is None else memory[:, mask]
         return picked.astype(np.int64).tolist()
+
+    # -- batched trials: MEASURE in mid-circuit, no control flow ---------------------------------------
+    #: a batch holds at most 2^BATCH_BITS amplitudes (1 GiB); one CUDA block measures one trial, so
+    #: trials of more than 2^BATCH_MAX_QUBITS amplitudes keep the per-trial loop
+    BATCH_BITS = 26
+    BATCH_MAX_QUBITS = 20
+
+    def _batchable(self, program):
+        """run(trials) can execute all trials side by side when every trial walks the same instruction
+        sequence: gates, MEASUREs and classical bit operations only (the reference re-simulates per
+        trial, :279-283; with jumps the trials may diverge and the per-trial loop is kept)."""
+        from referenceqvm import _sharded
+        if _sharded.context() is not None and _sharded.context().world > 1:
+            return False
+        allowed = (Gate, Measurement, UnaryClassicalInstruction, BinaryClassicalInstruction)
+        instrs = list(program)
+        if not instrs or not all(isinstance(i, allowed) for i in instrs):
+            return False
+        n = 1 + max([value_get(q) for i in instrs if isinstance(i, (Gate, Measurement)) for q in i.get_qubits()] or [0])
+        return n <= self.BATCH_MAX_QUBITS
+
+    def _run_batched(self, pyquil_program, classical_addresses, trials):
+        """All trials as independent segments of one device buffer: every gate group is one pass over
+        all of them, every MEASURE one kernel with one uniform per trial.  The uniforms are drawn up
+        front in the order the per-trial loop would draw them (trial-major, one per MEASURE), so a
+        seeded run returns the same bits as the reference's loop."""
+        self.load_program(pyquil_program)
+        mask = self._address_mask(classical_addresses)
+        n = self.num_qubits
+        instrs = list(pyquil_program)
+        n_meas = sum(1 for i in instrs if isinstance(i, Measurement))
+        uniforms = np.random.random_sample(trials * n_meas).reshape(trials, n_meas)
+        t_bits = max(0, min((trials - 1).bit_length(), self.BATCH_BITS - n))
+        cap = 1 << t_bits
+        memory = np.repeat(self.classical_memory[None, :], trials, axis=0)
+        eng = _engine.Engine(n + t_bits, device=self.device)
+        eng.relabel = False                   # the trial index must stay on the top positions
+        last = None
+        try:
+            for lo in range(0, trials, cap):
+                cnt = min(cap, trials - lo)
+                eng.pending = []
+                eng.state.reset_batched(n)
+                virt = list(range(n))
+                mem = memory[lo:lo + cnt]
+                m = 0
+                for instruction in instrs:
+                    if isinstance(instruction, Measurement):
+                        eng.flush()
+                        u = np.full(cap, 0.5)
+                        u[:cnt] = uniforms[lo:lo + cnt, m]
+                        outcomes, _ = eng.state.measure_batched(n, virt[value_get(instruction.qubit)], u)
+                        mem[:, value_get(instruction.classical_reg)] = outcomes[:cnt] != 0
+                        m += 1
+                    elif isinstance(instruction, Gate):
+                        matrix, qubits = resolve_gate(self.gate_set, self.defgate_set, instruction)
+                        _engine.validate_qubits(qubits, n)
+                        if len(qubits) == 2 and matrix.shape == (4, 4) and np.array_equal(matrix, _SWAP):
+                            a, b = qubits
+                            virt[a], virt[b] = virt[b], virt[a]
+                        else:
+                            eng.queue_matrix(matrix, [virt[q] for q in qubits])
+                    else:
+                        self._batched_classical(instruction, mem)
+                eng.flush()
+                if lo + cnt == trials:          # the reference leaves the last trial's state in self.wf
+                    last = (eng.amplitudes((cnt - 1) << n, 1 << n), virt)
+        finally:
+            eng.close()
+        self._fresh_engine()
+        if last is not None:
+            self._engine.set_amplitudes(last[0])
+            self._virt = list(last[1])
+        self.program_counter = len(self.program)
+        self.classical_memory = memory[-1].copy()
+        out = memory if mask is None else memory[:, mask]
+        return out.astype(np.int64).tolist()
+
+    @staticmethod
+    def _batched_classical(instruction, mem):
+        """qam.py's classical transitions on a (trials, addresses) bit matrix."""
+        if isinstance(instruction, UnaryClassicalInstruction):
+            t = value_get(instruction.target)
+            if isinstance(instruction, ClassicalTrue):
+                mem[:, t] = True
+            elif isinstance(instruction, ClassicalFalse):
+                mem[:, t] = False
+            elif isinstance(instruction, ClassicalNot):
+                mem[:, t] = ~mem[:, t]
+            else:
+                raise TypeError("Invalid UnaryClassicalInstruction")
+        else:
+            left, right = value_get(instruction.left), value_get(instruction.right)
+            lv, rv = mem[:, left].copy(), mem[:, right].copy()
+            if isinstance(instruction, ClassicalAnd):
+                mem[:, right] = lv & rv
+            elif isinstance(instruction, ClassicalOr):
+                mem[:, right] = lv | rv
+            elif isinstance(instruction, ClassicalMove):
+                mem[:, right] = lv
+            elif isinstance(instruction, ClassicalExchange):
+                mem[:, left], mem[:, right] = rv, lv
+            else:
+                raise TypeError("Invalid BinaryClassicalInstruction")
 
     def run_and_measure(self, pyquil_program, qubits=None, trials=1):
         """Simulate, then measure ``qubits`` (in the given order) ``trials`` times.

@@ -517,3 +517,73 @@ def test_swap_gates_are_relabels_with_identical_results(qvm):
     freq = np.bincount(idx, minlength=1 << n) / 4000.0
     assert np.max(np.abs(freq - probs)) < 0.05 and not shots[:, -1].any()
     assert passes_with_readback >= 1
+
+
+# ---- batched trials: mid-circuit MEASURE without control flow ------------------------------
+def test_run_with_midcircuit_measure_batches_trials_and_matches_the_per_trial_loop(qvm):
+    """run(trials) on a program that measures in mid-circuit and keeps going: all trials execute side by
+    side (one segment of the device buffer each).  With the same seed the batched path must return exactly
+    the bits of the per-trial loop (the reference's algorithm, qvm_wavefunction.py:279-283)."""
+    from pyquil.gates import AND, EXCHANGE, MEASURE, MOVE, NOT, OR, SWAP
+    prog = Program(H(0), CNOT(0, 1), RY(0.9, 2), MEASURE(0, 0), CNOT(1, 2), H(1), MEASURE(1, 1), NOT(1),
+                   RX(1.1, 3), CZ(2, 3), SWAP(0, 3), MEASURE(2, 2), MOVE(0, 5), AND(1, 2), OR(0, 2), EXCHANGE(1, 5),
+                   H(0), MEASURE(0, 3), TRUE(6), FALSE(7), MEASURE(3, 4))
+    addresses = [0, 1, 2, 3, 4, 5, 6, 7]
+    trials = 300
+    assert qvm._batchable(prog) and qvm._terminal_measure_block(prog) is None
+    np.random.seed(77)
+    batched = qvm.run(prog, addresses, trials=trials)
+    stream_after = np.random.random()
+    batched_state = np.asarray(qvm.wf).copy()
+    batched_memory = qvm.classical_memory.copy()
+    qvm.sampling_fast_path = False
+    try:
+        np.random.seed(77)
+        looped = qvm.run(prog, addresses, trials=trials)
+        assert np.random.random() == stream_after              # same number of draws, same order
+        looped_state = np.asarray(qvm.wf).copy()
+    finally:
+        qvm.sampling_fast_path = True
+    assert batched == looped
+    assert len({tuple(r) for r in batched}) > 4                # the trials really differ
+    # the last trial's wavefunction and classical memory are left behind, as in the reference
+    assert np.max(np.abs(batched_state - looped_state)) < 1e-12
+    assert np.array_equal(batched_memory, qvm.classical_memory)
+    # more trials than one batch holds, and all memory (classical_addresses=None)
+    old = qvm.BATCH_BITS
+    type(qvm).BATCH_BITS = 4 + 5
+    try:
+        np.random.seed(5)
+        chunked = qvm.run(prog, None, trials=70)
+        qvm.sampling_fast_path = False
+        np.random.seed(5)
+        ref = qvm.run(prog, None, trials=70)
+    finally:
+        qvm.sampling_fast_path = True
+        type(qvm).BATCH_BITS = old
+    assert chunked == ref and len(chunked[0]) >= 512
+
+
+def test_batched_measure_kernel_against_oracle():
+    from referenceqvm import _native as nat
+    n, t = 9, 5
+    rs = np.random.RandomState(8)
+    st = nat.DeviceState(n + t)
+    segs = []
+    for s in range(1 << t):
+        v = rs.standard_normal(1 << n) + 1j * rs.standard_normal(1 << n)
+        segs.append(v / np.linalg.norm(v))
+    st.set_state(np.concatenate(segs))
+    for qubit in (0, 4, 8):
+        u = rs.random_sample(1 << t)
+        outcomes, p0 = st.measure_batched(n, qubit, u)
+        got = st.get_state().reshape(1 << t, 1 << n)
+        for s in range(1 << t):
+            o_want, p_want, psi = orc.fast_measure(segs[s], qubit, n, u[s])
+            assert outcomes[s] == o_want and abs(p0[s] - p_want) < 1e-12
+            assert np.max(np.abs(got[s] - psi)) < 1e-12
+            segs[s] = psi
+    st.reset_batched(n)
+    got = st.get_state().reshape(1 << t, 1 << n)
+    assert np.all(got[:, 0] == 1.0) and np.count_nonzero(got) == 1 << t
+    st.close()
