@@ -93,6 +93,8 @@ int qvm_set_kernel_path(qvm_t* q, int use_regtile);
 int qvm_set_jit(qvm_t* q, int policy);
 /* Block until every background compilation has finished (benchmarks: once, after warm-up). */
 int qvm_jit_wait(void);
+/* Process exit: drop queued compilations and wait for those in flight (also registered with atexit). */
+int qvm_jit_shutdown(void);
 /* Diagnostics (no device needed): encode the group, generate its specialised source and compile it to
  * an sm_100a cubin with NVRTC.  0 = compiled, 1 = this group is left to the interpreter, < 0 = the
  * generated source failed to compile (`log` receives the NVRTC log). */

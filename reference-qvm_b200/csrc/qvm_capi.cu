@@ -678,6 +678,11 @@ int qvm_jit_wait(void) {
     return QVM_OK;
 }
 
+int qvm_jit_shutdown(void) {
+    SpecCache::instance().shutdown();
+    return QVM_OK;
+}
+
 int qvm_set_jit(qvm_t* q, int policy) {
     QVM_CHECK_HANDLE(q);
     if (policy < 0 || policy > 2) return fail(QVM_ERR_INVALID, "JIT policy must be 0, 1 or 2");

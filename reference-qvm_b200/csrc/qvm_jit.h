@@ -288,6 +288,7 @@ public:
         std::unique_lock<std::mutex> lock(mu_);
         auto it = cache_.find(src);
         if (it != cache_.end()) return it->second->state == READY ? &it->second->cs : nullptr;
+        if (stopping_) return nullptr;
         if (policy < 2 && ++seen_[std::hash<std::string>()(src)] < 2) return nullptr;
         Entry* e = new Entry();
         cache_.emplace(src, std::unique_ptr<Entry>(e));
@@ -309,6 +310,18 @@ public:
     }
     void wait_idle() {
         std::unique_lock<std::mutex> lock(mu_);
+        idle_cv_.wait(lock, [&] { return outstanding_ == 0; });
+    }
+    // Process exit: drop the queued jobs and wait for the compilations in flight -- a worker inside NVRTC
+    // while the C++ runtime tears that library's statics down corrupts the heap.
+    void shutdown() {
+        std::unique_lock<std::mutex> lock(mu_);
+        stopping_ = true;
+        for (Job& job : jobs_) {
+            job.entry->state = FAILED;
+            --outstanding_;
+        }
+        jobs_.clear();
         idle_cv_.wait(lock, [&] { return outstanding_ == 0; });
     }
     int compiles() {
@@ -380,6 +393,8 @@ private:
     void start_workers() {                       // mu_ held
         if (workers_started_) return;
         workers_started_ = true;
+        load_nvrtc(nullptr);                      // before atexit: handlers run in reverse order of registration
+        std::atexit([] { SpecCache::instance().shutdown(); });
         unsigned n = std::thread::hardware_concurrency() / 2;
         n = n < 1 ? 1 : (n > 8 ? 8 : n);
         for (unsigned i = 0; i < n; ++i) std::thread([this] { worker(); }).detach();
@@ -389,7 +404,7 @@ private:
             Job job;
             {
                 std::unique_lock<std::mutex> lock(mu_);
-                cv_.wait(lock, [&] { return !jobs_.empty(); });
+                cv_.wait(lock, [&] { return !jobs_.empty(); });      // (never returns once shutdown() emptied the queue)
                 job = std::move(jobs_.front());
                 jobs_.pop_front();
             }
@@ -460,7 +475,7 @@ private:
     std::unordered_map<size_t, int> seen_;
     std::deque<Job> jobs_;
     int outstanding_ = 0, compiles_ = 0;
-    bool workers_started_ = false;
+    bool workers_started_ = false, stopping_ = false;
     std::string last_error_;
     void* nvrtc_ = nullptr;
     bool tried_ = false;

@@ -3,6 +3,7 @@
 Signatures follow ``include/qvm_b200.h`` one to one.  There is deliberately no fallback: if the
 shared object is missing or no CUDA device is present, the first call raises ``NativeError``.
 """
+import atexit
 import ctypes as C
 import os
 
@@ -55,6 +56,7 @@ _SIGNATURES = {
     "qvm_set_kernel_path": (C.c_int, [_P, C.c_int]),
     "qvm_set_jit": (C.c_int, [_P, C.c_int]),
     "qvm_jit_wait": (C.c_int, []),
+    "qvm_jit_shutdown": (C.c_int, []),
     "qvm_spec_compile_check": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_int, _P, C.c_int, _P, _P, C.c_uint64, _P,
                                          C.c_uint64, C.c_int, C.c_int, _P]),
     "qvm_debug_opcode_hist": (C.c_int, [_P, _P]),
@@ -110,6 +112,8 @@ def lib():
             fn.restype = restype
             fn.argtypes = argtypes
         _lib = handle
+        # background NVRTC compilations must not be in flight when the interpreter tears libraries down
+        atexit.register(handle.qvm_jit_shutdown)
     return _lib
 
 

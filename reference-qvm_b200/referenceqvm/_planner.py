@@ -180,12 +180,19 @@ def _choose_group(ops, deps, done, first, k, max_new, is_old, seed_tile, max_gro
     return tile, chosen
 
 
-def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_group_ops=MAX_GROUP_OPS):
+def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_group_ops=MAX_GROUP_OPS,
+                   defer_tail_below=0, leftover=None):
     """Run ``ops`` (ClassifiedOps on LOGICAL qubits; every dense target currently on a local position)
     as fused groups with in-tile relabelling.  ``pos_of`` (logical -> physical, mutated in place) is the
     layout; ``launch(tile_positions, physical_ops, bring_low_positions)`` runs one pass and returns the
-    new position of every tile position (same order as the sorted tile).  Returns the number of passes."""
-    ops = [o for o in ops if o.kind != OP_NOP]
+    new position of every tile position (same order as the sorted tile).  Returns the number of passes.
+
+    ``defer_tail_below``: when the LAST group would hold fewer ops than this, it is not launched and the
+    indices (into ``ops``) of its members are appended to the list ``leftover`` instead -- the sharded
+    engine merges such a tail with the ops that become runnable after the next exchange rather than
+    paying a whole pass for it."""
+    origin = [i for i, o in enumerate(ops) if o.kind != OP_NOP]
+    ops = [ops[i] for i in origin]
     n = len(ops)
     if not n:
         return 0
@@ -238,6 +245,9 @@ def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_g
             done[i] = True
         while first < n and done[first]:
             first += 1
+        if first >= n and leftover is not None and len(cur_ops) < defer_tail_below:
+            leftover.extend(origin[i] for i in cur_ops)
+            return passes
         # the next group, free to take any `low` of this tile's qubits along
         nxt_tile, nxt_ops = (set(), [])
         bring = []

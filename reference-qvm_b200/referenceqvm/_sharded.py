@@ -322,7 +322,13 @@ class ShardedEngine(object):
                         continue
                 batch.append(i)
                 in_batch.add(i)
-            self._run_logical([ops[i] for i in batch])
+            # a thin last group is not worth a pass of its own when an exchange follows: its ops stay
+            # pending and merge with what the exchange unblocks (they are logical ops, the layout is looked
+            # up when they finally run)
+            deferred = self._run_logical([ops[i] for i in batch], defer=bool(wanted) and len(batch) < remaining)
+            if deferred:
+                keep = set(deferred)              # positions within `batch`
+                batch = [i for j, i in enumerate(batch) if j not in keep]
             for i in batch:
                 done[i] = True
             remaining -= len(batch)
@@ -385,19 +391,27 @@ class ShardedEngine(object):
         if e0 is not None:
             self.timing["swap"].append((e0, self.shard.record_event()))
 
-    def _run_logical(self, batch):
-        """Ops in LOGICAL coordinates whose dense targets are all local right now."""
+    #: a batch's last group is deferred across the following exchange when it holds fewer ops than this
+    DEFER_TAIL_BELOW = int(os.environ.get("QVM_B200_DEFER_TAIL", "16"))
+
+    def _run_logical(self, batch, defer=False):
+        """Ops in LOGICAL coordinates whose dense targets are all local right now.  Returns the indices
+        (into ``batch``) of the ops that were NOT run (a thin last group, only when ``defer``)."""
         if not batch:
-            return
+            return []
         if not (self.relabel and self.n_local > self.tile_bits):
-            return self._run_batch([op.remapped(self.pos_of) for op in batch])
+            self._run_batch([op.remapped(self.pos_of) for op in batch])
+            return []
+        leftover = []
         e0 = self.shard.record_event() if self.timing is not None else None
         self.groups_launched += _planner.run_relabelled(
             batch, self.n_local, self.pos_of,
             lambda tile, ops, bring: self.shard.apply_group(tile, ops, bring if bring else [], self.low_bits),
-            self.tile_bits, self.low_bits)
+            self.tile_bits, self.low_bits, defer_tail_below=self.DEFER_TAIL_BELOW if defer else 0,
+            leftover=leftover)
         if e0 is not None:
             self.timing["batch"].append((e0, self.shard.record_event()))
+        return leftover
 
     def _run_batch(self, batch):
         """Ops in PHYSICAL coordinates, fixed layout."""
