@@ -561,11 +561,12 @@ class ShardedEngine(object):
         return self._allreduce_sum(self.shard.prob_zero(self.pos_of[int(qubit)]))
 
     def position(self, qubit):
-        """``sample`` returns logical indices here, whatever ``physical`` says: bit q is qubit q."""
-        return qubit
+        """Physical position (index bit) of a logical qubit: for bit look-ups in ``sample(physical=True)``."""
+        return self.pos_of[qubit]
 
     def sample(self, uniforms, mode=0, n_rho=0, physical=False, logical_order=False):
-        """Inverse-CDF draws of LOGICAL basis-state indices, identical on every rank.
+        """Inverse-CDF draws of LOGICAL basis-state indices (``physical=True``: of HBM indices, bit
+        ``position(q)`` being qubit q), identical on every rank.
 
         The CDF is walked in HBM order (rank-major, then the shard's physical index) and the drawn
         indices are translated through the layout -- the same distribution as a walk in logical order
@@ -598,6 +599,8 @@ class ShardedEngine(object):
         t = self.shard.scalar_tensor(phys, dtype=torch.int64)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.ctx.group)
         phys = t.cpu().numpy().astype(np.uint64)
+        if physical:                # the caller looks bits up through position(): no per-qubit pass over the shots
+            return phys, grand
         logical = np.zeros_like(phys)
         for q in range(self.n):
             logical |= ((phys >> np.uint64(self.pos_of[q])) & np.uint64(1)) << np.uint64(q)

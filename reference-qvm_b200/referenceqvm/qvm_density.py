@@ -316,4 +316,5 @@ class QVM_Density(QAM):
             raise ValueError("probabilities do not sum to 1")
         shifts = np.arange(n - 1, -1, -1, dtype=np.uint64)
         bits = (indices[:, None] >> shifts[None, :]) & np.uint64(1)
-        return bits.astype(np.int64).tolist()
+        from referenceqvm.qvm_wavefunction import _rows_to_lists
+        return _rows_to_lists(bits.astype(np.int64))

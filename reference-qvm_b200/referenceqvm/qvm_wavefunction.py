@@ -16,6 +16,7 @@ happens:
   terminal block of MEASUREs and no control flow) the program is simulated once and the trials
   are drawn by the prefix-sum + binary-search kernel; otherwise the per-trial loop is kept.
 """
+import gc
 import os
 
 import numpy as np
@@ -41,6 +42,18 @@ def _index_bits(indices, num_qubits=63):
     indices; only the bytes that can hold a set bit are unpacked, column ``num_qubits`` is always 0."""
     by = np.ascontiguousarray(indices, dtype="<u8").view(np.uint8).reshape(-1, 8)
     return np.unpackbits(by[:, :num_qubits // 8 + 1], axis=1, bitorder="little")
+
+
+def _rows_to_lists(matrix):
+    """``matrix.tolist()`` with the cyclic garbage collector paused: a million row lists are a million
+    tracked containers, and the generational collections they trigger cost a third of the conversion."""
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        return matrix.tolist()
+    finally:
+        if was_enabled:
+            gc.enable()
 
 
 _SWAP = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
@@ -239,7 +252,7 @@ class QVM_Wavefunction(QAM):
         self.program_counter = len(self.program)
         self.classical_memory = memory[-1].copy()
         picked = memory if mask is None else memory[:, mask]
-        return picked.astype(np.int64).tolist()
+        return _rows_to_lists(picked.astype(np.int64))
 
     # -- batched trials: MEASURE in mid-circuit, no control flow ---------------------------------------
     #: a batch holds at most 2^BATCH_BITS amplitudes (1 GiB); one CUDA block measures one trial, so
@@ -316,7 +329,7 @@ class QVM_Wavefunction(QAM):
         self.program_counter = len(self.program)
         self.classical_memory = memory[-1].copy()
         out = memory if mask is None else memory[:, mask]
-        return out.astype(np.int64).tolist()
+        return _rows_to_lists(out.astype(np.int64))
 
     @staticmethod
     def _batched_classical(instruction, mem):
@@ -364,7 +377,7 @@ class QVM_Wavefunction(QAM):
             # column num_qubits is never set: it stands in for qubits beyond the register
             sel = [self._engine.position(self._virt[q]) if 0 <= q < self.num_qubits else self.num_qubits
                    for q in qubits]
-            return np.take(bits, sel, axis=1).tolist()
+            return _rows_to_lists(np.take(bits, sel, axis=1))
 
         results = []
         for _ in range(trials):

@@ -82,6 +82,12 @@ def main():
         logical_of_phys[phys] = logical
         ref = logical_of_phys[np.asarray(orc.inverse_cdf_sample(probs_hbm, u), dtype=np.int64)]
         assert np.array_equal(idx.astype(np.int64), ref)
+        # physical=True: raw HBM indices; bit position(q) is qubit q (what run_and_measure unpacks)
+        raw, _ = eng.sample(u if rank == 0 else np.zeros(257), physical=True)
+        rebuilt = np.zeros(raw.size, dtype=np.int64)
+        for q in range(n):
+            rebuilt |= ((raw.astype(np.int64) >> eng.position(q)) & 1) << q
+        assert np.array_equal(rebuilt, ref)
         # on request the engine restores the logical layout first: the CDF order is the reference's
         idx, total = eng.sample(u if rank == 0 else np.zeros(257), logical_order=True)
         assert eng.pos_of == list(range(n))
