@@ -234,6 +234,17 @@ class Engine(object):
                 if not self._merger.absorb(self.pending, piece):
                     self.pending.append(piece)
 
+    def queue_shifted(self, pieces, shift):
+        """Queue one gate given as already expanded pieces (``expand_op``) whose positions are all to be
+        moved up by ``shift`` -- the same channel on qubit after qubit without re-classifying it."""
+        self.gates_queued += 1
+        for piece in pieces:
+            if shift:
+                piece = nat.ClassifiedOp(piece.kind, tuple(t + shift for t in piece.targets), piece.ctrl_mask << shift,
+                                         piece.mat)
+            if not self._merger.absorb(self.pending, piece):
+                self.pending.append(piece)
+
     def flush(self):
         self._merger.reset()
         if not self.pending:

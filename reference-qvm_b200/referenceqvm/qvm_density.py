@@ -54,6 +54,9 @@ class NoiseModel(object):
         self.bitphaseflip = bitphaseflip
 
 
+_channel_pieces = {}       # (n, Kraus operator bytes) -> expanded ops of the channel on (n, 0)
+
+
 def kraus_superoperator(operators):
     """S = sum_k K_k (x) conj(K_k): the channel as one matrix on vector-qubits (q+n.., q..)."""
     ops = [np.asarray(k, dtype=np.complex128) for k in operators]
@@ -161,11 +164,35 @@ class QVM_Density(QAM):
         self._engine.queue_matrix(matrix, [q + n for q in qubits])
         self._engine.queue_matrix(np.conj(matrix), list(qubits))
 
-    def _queue_channel(self, operators, index):
+    def _queue_channel(self, operators, index, superoperator=None):
         n = self.num_qubits
         if not (0 <= index < n):
             raise ValueError("Gate index out of range!")
-        self._engine.queue_matrix(kraus_superoperator(operators), [index + n, index])
+        if superoperator is None:
+            superoperator = kraus_superoperator(operators)
+        self._engine.queue_matrix(superoperator, [index + n, index])
+
+    def _queue_channel_everywhere(self, operators):
+        """The same channel on every qubit (the noise model after an instruction): one superoperator,
+        classified and expanded once on (n, 0) -- qubit i is the same op with every position + i --
+        and remembered per (Kraus operators, n): a noise model applies the same few channels after
+        every instruction."""
+        n = self.num_qubits
+        if hasattr(self._engine, "queue_shifted"):
+            key = (n,) + tuple(np.asarray(k, dtype=np.complex128).tobytes() for k in operators)
+            pieces = _channel_pieces.get(key)
+            if pieces is None:
+                op = _engine.compile_gate(kraus_superoperator(operators), [n, 0])
+                pieces = () if op.kind == _engine.nat.OP_NOP else _engine.expand_op(op)
+                if len(_channel_pieces) > 4096:
+                    _channel_pieces.clear()
+                _channel_pieces[key] = pieces
+            for i in range(n):
+                self._engine.queue_shifted(pieces, i)
+            return
+        sup = kraus_superoperator(operators)
+        for i in range(n):
+            self._queue_channel(operators, i, sup)
 
     def measurement(self, qubit_index):
         """MEASURE on rho: p0 = tr(P0 rho); one uniform draw; rho <- P_b rho P_b / p_b.
@@ -227,15 +254,13 @@ class QVM_Density(QAM):
                 # the reference leaves `relaxation_ops` unbound here (:292-296) and fails
                 raise UnboundLocalError("relaxation probability is 1: the reference cannot apply this channel")
             ops = noise_gates['relaxation'](p)
-            for i in range(n):
-                self._queue_channel(ops, i)
+            self._queue_channel_everywhere(ops)
 
         if nm.T2 != INFINITY:
             p = decay(nm.gate_time_1q, nm.gate_time_2q, nm.T2)
             if not np.isclose(p, 1.0):
                 ops = noise_gates['dephasing'](p)
-                for i in range(n):
-                    self._queue_channel(ops, i)
+                self._queue_channel_everywhere(ops)
 
         for attr, key, label in (("depolarizing", "depolarizing", "depolarizing"),
                                  ("bitflip", "bit_flip", "bitflip"),
@@ -245,16 +270,14 @@ class QVM_Density(QAM):
                 if not isinstance(value, float):
                     raise TypeError("%s noise value should be None or a float" % label)
                 ops = noise_gates[key](value)
-                for i in range(n):
-                    self._queue_channel(ops, i)
+                self._queue_channel_everywhere(ops)
 
         if nm.bitphaseflip is not None:
             # the reference type-checks `phaseflip` here (:341), kept for identical behaviour
             if not isinstance(nm.phaseflip, float):
                 raise TypeError("bitphaseflip noise value should be None or a float")
             ops = noise_gates['bitphase_flip'](nm.bitphaseflip)
-            for i in range(n):
-                self._queue_channel(ops, i)
+            self._queue_channel_everywhere(ops)
 
     def apply_kraus(self, operators, index):
         """sum_k L_k rho L_k^dagger with L_k = K_k lifted to ``index``; returns the new density and
