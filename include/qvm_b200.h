@@ -166,6 +166,17 @@ int qvm_dephase_all(qvm_t* q, int n_rho_qubits, uint64_t qubit_mask, double fact
 /* One cooperative kernel: p0 = sum_{bit=0} |amp|^2 (warp-shuffle + block reduce), outcome 0 iff
  * r < p0, zero the other half and scale by 1/sqrt(p_outcome).  Single-shard handles only. */
 int qvm_measure(qvm_t* q, int qubit, double r, int* outcome, double* p0);
+/* Runs of MEASURE instructions (the Measurement branch of qvm_wavefunction.py:147-156 executed back to
+ * back).  One pass (a) optionally applies the combined collapse of the previous chunk -- amplitudes whose
+ * index has (index & keep_mask) == keep_value are scaled by `scale`, the others zeroed -- and (b) returns
+ * hist[bin][lane] (32 * 2^n_high doubles): the sum of |amp|^2 over the (collapsed) amplitudes whose bits at
+ * high_pos[0..n_high) (each >= 5) spell `bin` (high_pos[i] = bit i) and whose 5 lowest index bits are
+ * `lane`.  The caller replays the reference's sequential decisions on it -- p0 of each measured qubit given
+ * the outcomes so far, one uniform each, outcome 0 iff r < p0, scale 1/sqrt(p0) or 1/sqrt(1 - p0) -- and
+ * passes the combined projection to the next call (n_high = 0, hist = NULL for a final collapse only).
+ * Summation order is fixed: results are deterministic to the last bit. */
+int qvm_measure_hist(qvm_t* q, int n_high, const int32_t* high_pos, int do_collapse, uint64_t keep_mask,
+                     uint64_t keep_value, double scale, double* hist);
 /* Batched trials (qvm_wavefunction.py:266-283: run() re-simulates the program once per trial).  The
  * handle's 2^n_local amplitudes are read as 2^(n_local - n_per_trial) independent n_per_trial-qubit
  * states, one per trial; gates applied to positions < n_per_trial act on all of them in the same pass.

@@ -960,6 +960,50 @@ int qvm_measure(qvm_t* q, int qubit, double r, int* outcome, double* p0) {
     return QVM_OK;
 }
 
+// ---- runs of MEASURE instructions -----------------------------------------------------------------------
+int qvm_measure_hist(qvm_t* q, int n_high, const int32_t* high_pos, int do_collapse, uint64_t keep_mask,
+                     uint64_t keep_value, double scale, double* hist) {
+    QVM_CHECK_HANDLE(q);
+    if (q->n_global) return fail(QVM_ERR_INVALID, "qvm_measure_hist is single-shard");
+    if (q->n_local < 5) return fail(QVM_ERR_INVALID, "qvm_measure_hist needs at least 5 local positions");
+    if (n_high < 0 || n_high > 5 || (n_high && !high_pos)) return fail(QVM_ERR_INVALID, "0..5 high positions");
+    HistBits hb{};
+    hb.n_high = n_high;
+    for (int i = 0; i < n_high; ++i) {
+        if (high_pos[i] < 5 || high_pos[i] >= q->n_local) return fail(QVM_ERR_INVALID, "high position %d out of range", high_pos[i]);
+        hb.pos[i] = (uint8_t)high_pos[i];
+    }
+    if (keep_value & ~keep_mask) return fail(QVM_ERR_INVALID, "collapse value outside its mask");
+    const int n_entries = 32 << n_high;
+    const uint64_t n_chunks = q->n_elems >> 5;
+    int grid = (int)std::min<uint64_t>((n_chunks + (kHistThreads / 32) - 1) / (kHistThreads / 32), (uint64_t)q->sm_count * 8);
+    if (grid < 1) grid = 1;
+    double* dev = nullptr;
+    QVM_CUDA(q, cudaMallocAsync(&dev, ((size_t)grid + 1) * n_entries * sizeof(double), q->stream));
+    double* d_hist = dev + (size_t)grid * n_entries;
+    int rc = QVM_OK;
+    measure_hist_kernel<<<grid, kHistThreads, 0, q->stream>>>(q->amps, q->n_elems, hb, do_collapse ? 1 : 0, keep_mask,
+                                                              keep_value, scale, dev);
+    if (cudaGetLastError() != cudaSuccess) rc = fail(QVM_ERR_CUDA, "measure_hist_kernel launch failed");
+    if (rc == QVM_OK && hist) {
+        measure_hist_final_kernel<<<(n_entries + 255) / 256, 256, 0, q->stream>>>(dev, grid, n_entries, d_hist);
+        std::vector<double> host(n_entries);
+        if (cudaGetLastError() != cudaSuccess ||
+            cudaMemcpyAsync(host.data(), d_hist, n_entries * sizeof(double), cudaMemcpyDeviceToHost, q->stream) != cudaSuccess ||
+            cudaStreamSynchronize(q->stream) != cudaSuccess)
+            rc = fail(QVM_ERR_CUDA, "histogram readback failed");
+        else memcpy(hist, host.data(), n_entries * sizeof(double));
+        q->stats.kernel_launches += 1;
+        q->stats.d2h_bytes += n_entries * sizeof(double);
+    }
+    cudaFreeAsync(dev, q->stream);
+    if (rc != QVM_OK) return rc;
+    q->sample_mode = -1;
+    q->stats.kernel_launches += 1;
+    q->stats.hbm_bytes += (do_collapse ? 32ull : 16ull) * q->n_elems;
+    return QVM_OK;
+}
+
 // ---- batched trials ------------------------------------------------------------------------------------
 int qvm_reset_batched(qvm_t* q, int n_per_trial) {
     QVM_CHECK_HANDLE(q);

@@ -421,6 +421,60 @@ __global__ void measure_kernel(double2* __restrict__ state, uint64_t n_elems, in
     }
 }
 
+// Runs of MEASURE instructions (qvm_wavefunction.py:147-156 executed back to back): one pass builds the
+// joint distribution of up to 5 "high" measured positions (>= 5) x all 32 values of the 5 lowest index bits,
+// the host replays the reference's sequential decisions on it (one uniform per MEASURE, p0 conditional on
+// the outcomes so far), and the NEXT pass applies the combined collapse + renormalisation while it builds
+// the distribution for the following chunk.  A warp reads 32 consecutive amplitudes, so the high-bin is the
+// same for all its lanes and every lane owns one column of its warp's histogram: no atomics, fixed
+// summation order (deterministic to the last bit).
+constexpr int kHistThreads = 128;          // 4 warps x 32 bins x 32 lanes x 8 B = 32 KB of shared memory
+struct HistBits {
+    int n_high;
+    uint8_t pos[5];
+};
+__global__ void __launch_bounds__(kHistThreads)
+measure_hist_kernel(double2* __restrict__ state, uint64_t n_elems, const HistBits hb, int do_collapse,
+                    uint64_t keep_mask, uint64_t keep_value, double scale, double* __restrict__ partials) {
+    __shared__ double acc[kHistThreads / 32][32][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_bins = 1 << hb.n_high;
+    for (int b = 0; b < n_bins; ++b) acc[warp][b][lane] = 0.0;
+    const uint64_t n_chunks = n_elems >> 5;
+    const uint64_t warps_total = (uint64_t)gridDim.x * (kHistThreads / 32);
+    for (uint64_t c = (uint64_t)blockIdx.x * (kHistThreads / 32) + warp; c < n_chunks; c += warps_total) {
+        const uint64_t x = (c << 5) | (uint64_t)lane;
+        double2 a = state[x];
+        if (do_collapse) {
+            if ((x & keep_mask) == keep_value) {
+                a.x *= scale;
+                a.y *= scale;
+            } else {
+                a = make_double2(0.0, 0.0);
+            }
+            state[x] = a;
+        }
+        int bin = 0;
+        for (int i = 0; i < hb.n_high; ++i) bin |= (int)((x >> hb.pos[i]) & 1ull) << i;
+        acc[warp][bin][lane] += a.x * a.x + a.y * a.y;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n_bins * 32; j += kHistThreads) {
+        double t = 0.0;
+        for (int w = 0; w < kHistThreads / 32; ++w) t += acc[w][j >> 5][j & 31];
+        partials[(size_t)blockIdx.x * (n_bins * 32) + j] = t;
+    }
+}
+// hist[j] = sum over blocks of partials[block][j], blocks in ascending order
+__global__ void measure_hist_final_kernel(const double* __restrict__ partials, int n_blocks, int n_entries,
+                                          double* __restrict__ hist) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_entries) return;
+    double t = 0.0;
+    for (int b = 0; b < n_blocks; ++b) t += partials[(size_t)b * n_entries + j];
+    hist[j] = t;
+}
+
 // Batched trials: the shard holds 2^(n_local - n) independent n-qubit states ("segments", one per
 // trial of run()); each block owns one segment.  Same arithmetic as measure_kernel, per segment, with
 // that trial's own uniform: p0 -> outcome 0 iff r < p0 -> zero the other half, scale by 1/sqrt(p).

@@ -270,6 +270,55 @@ class Engine(object):
         self.flush()
         return self.state.measure(self.pos_of[int(qubit)], float(r))
 
+    #: a run of MEASUREs is fused into joint-distribution passes from this many qubits on (below, the
+    #: state is a few KiB and the single-qubit kernel's launch latency is all there is)
+    MEASURE_MANY_MIN_QUBITS = 10
+
+    def measure_many(self, qubits, uniforms):
+        """A run of MEASUREs on distinct qubits, in order, each with its own host-drawn uniform: the
+        reference's sequence of single measurements (qvm_wavefunction.py:147-156: p0 on the current,
+        already collapsed state; outcome 0 iff r < p0; scale 1/sqrt(p0) or 1/sqrt(1 - p0)) replayed on the
+        joint distribution of the measured bits, which costs one pass per chunk of qubits instead of two
+        per qubit.  Returns [(outcome, p0), ...]."""
+        qubits = [int(q) for q in qubits]
+        if len(set(qubits)) != len(qubits):
+            raise ValueError("measure_many needs distinct qubits")
+        if self.n < self.MEASURE_MANY_MIN_QUBITS or len(qubits) < 2:
+            return [self.measure(q, r) for q, r in zip(qubits, uniforms)]
+        self.flush()
+        positions = [self.pos_of[q] for q in qubits]
+        lanes = np.arange(32)[None, :]
+        results = []
+        pending = None
+        i = 0
+        while i < len(positions):
+            chunk, high = [], []
+            while i + len(chunk) < len(positions):
+                p = positions[i + len(chunk)]
+                if p >= 5:
+                    if len(high) == 5:
+                        break
+                    high.append(p)
+                chunk.append(p)
+            hist = self.state.measure_hist(high, pending)
+            bins = np.arange(1 << len(high))[:, None]
+            consistent = np.ones(hist.shape, dtype=bool)
+            norm_factor, mask, value = 1.0, 0, 0
+            for j, p in enumerate(chunk):
+                bit = ((bins >> high.index(p)) & 1) if p >= 5 else ((lanes >> p) & 1)
+                bit = np.broadcast_to(bit, hist.shape)
+                p0 = norm_factor * float(hist[consistent & (bit == 0)].sum())
+                outcome = 0 if float(uniforms[i + j]) < p0 else 1
+                norm_factor *= 1.0 / (p0 if outcome == 0 else 1.0 - p0)
+                consistent = consistent & (bit == outcome)
+                mask |= 1 << p
+                value |= outcome << p
+                results.append((outcome, p0))
+            pending = (mask, value, float(np.sqrt(norm_factor)))
+            i += len(chunk)
+        self.state.measure_hist([], pending, want_hist=False)
+        return results
+
     def prob_zero(self, qubit):
         self.flush()
         return self.state.prob_zero(self.pos_of[int(qubit)])

@@ -69,6 +69,7 @@ _SIGNATURES = {
     "qvm_reset_zero": (C.c_int, [_P, C.c_int]),
     "qvm_set_state": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P]),
     "qvm_get_state": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P]),
+    "qvm_measure_hist": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_uint64, C.c_uint64, C.c_double, _P]),
     "qvm_reset_batched": (C.c_int, [_P, C.c_int]),
     "qvm_measure_batched": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "qvm_get_strided": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
@@ -419,6 +420,20 @@ class DeviceState(object):
             raise ValueError(last_error())
         check(code)
         return outcome.value, p0.value
+
+    def measure_hist(self, high_positions, collapse=None, want_hist=True):
+        """One pass of a MEASURE run (``qvm_measure_hist``): optionally apply ``collapse`` = (keep_mask,
+        keep_value, scale), then return hist[bin, lane] over ``high_positions`` (each >= 5, at most 5)
+        and the 5 lowest index bits."""
+        hp = np.ascontiguousarray(high_positions, dtype=np.int32)
+        hist = np.empty((1 << hp.size, 32), dtype=np.float64) if want_hist else None
+        mask, value, scale = collapse if collapse is not None else (0, 0, 1.0)
+        code = lib().qvm_measure_hist(self.handle, hp.size, hp.ctypes.data, 0 if collapse is None else 1, mask, value,
+                                      float(scale), hist.ctypes.data if want_hist else None)
+        if code == QVM_ERR_INVALID:
+            raise ValueError(last_error())
+        check(code)
+        return hist
 
     def reset_batched(self, n_per_trial):
         """Every 2^n_per_trial-amplitude segment := |0..0> (one segment per trial of a batched run())."""

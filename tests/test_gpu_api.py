@@ -587,3 +587,31 @@ def test_batched_measure_kernel_against_oracle():
     got = st.get_state().reshape(1 << t, 1 << n)
     assert np.all(got[:, 0] == 1.0) and np.count_nonzero(got) == 1 << t
     st.close()
+
+
+def test_runs_of_measures_are_fused_and_keep_the_seeded_stream(qvm):
+    """wavefunction() on a program that ends in MEASUREs of all qubits (shuffled order, plus a repeated
+    qubit and gates in between): same classical memory, same RNG stream position and same collapsed state
+    as the oracle's one-by-one measurements."""
+    from pyquil.gates import MEASURE
+    n = 12
+    spec = orc.random_circuit_spec(n, 4, 21)
+    rs = np.random.RandomState(2)
+    order = [int(q) for q in rs.permutation(n)]
+    prog = spec_program(spec)
+    ops = list(oracle_ops(prog))
+    for c, q in enumerate(order):
+        prog.inst(MEASURE(q, c))
+        ops.append(("measure", q, c))
+    prog.inst(MEASURE(order[0], 20), H(order[1]), MEASURE(order[1], 21), MEASURE(order[2], 22))
+    ops += [("measure", order[0], 20), ("gate", np.asarray(G.H, dtype=complex), [order[1]]), ("measure", order[1], 21),
+            ("measure", order[2], 22)]
+    np.random.seed(99)
+    wf, mem = qvm.wavefunction(prog, list(range(24)))
+    nxt = np.random.random()
+    rng = np.random.RandomState(99)
+    want, cmem = orc.fast_run_wavefunction(ops, n, rng)
+    assert mem == [int(cmem.get(i, 0)) for i in range(24)]
+    assert nxt == rng.random_sample()
+    assert np.max(np.abs(wf.amplitudes - want)) < TOL
+    assert qvm._engine.stats()["hbm_passes"] < 2 * (n + 3)          # fused: far fewer than two passes per MEASURE

@@ -551,3 +551,68 @@ def test_engine_with_and_without_relabelling(n, depth, seed):
         eng.close()
     assert out[True][1:] == pytest.approx(out[False][1:], abs=1e-12)
     assert out[True][0] <= out[False][0]
+
+
+# ---- runs of MEASUREs ---------------------------------------------------------------------------------------
+def test_measure_hist_kernel_against_numpy():
+    """qvm_measure_hist: joint distribution over up to 5 high positions x the 5 lowest index bits, with and
+    without the fused collapse of the previous chunk; deterministic."""
+    n = 14
+    psi = random_state(n, 31)
+    st = nat.DeviceState(n)
+    st.set_state(psi)
+    idx = np.arange(1 << n, dtype=np.int64)
+
+    def model(vec, high):
+        bins = np.zeros_like(idx)
+        for i, p in enumerate(high):
+            bins |= ((idx >> p) & 1) << i
+        hist = np.zeros((1 << len(high), 32))
+        np.add.at(hist, (bins, idx & 31), np.abs(vec) ** 2)
+        return hist
+
+    for high in ([], [5], [13, 6, 9], [7, 8, 9, 10, 11]):
+        got = st.measure_hist(high)
+        assert got.shape == (1 << len(high), 32)
+        assert np.max(np.abs(got - model(psi, high))) < 1e-14
+        assert np.array_equal(got, st.measure_hist(high))                 # fixed summation order
+    mask, value, scale = (1 << 3) | (1 << 9) | (1 << 12), (1 << 9), 1.7
+    got = st.measure_hist([6, 12], (mask, value, scale))
+    want_vec = np.where((idx & mask) == value, psi * scale, 0.0)
+    assert np.max(np.abs(got - model(want_vec, [6, 12]))) < 1e-13
+    assert np.max(np.abs(st.get_state() - want_vec)) < 1e-15
+    st.measure_hist([], (1 << 6, 0, 0.5), want_hist=False)
+    want_vec = np.where((idx & (1 << 6)) == 0, want_vec * 0.5, 0.0)
+    assert np.max(np.abs(st.get_state() - want_vec)) < 1e-15
+    with pytest.raises(ValueError):
+        st.measure_hist([3])
+    st.close()
+
+
+@pytest.mark.parametrize("n,seed", [(12, 3), (16, 4), (21, 5)])
+def test_measure_many_on_device_matches_sequential_measure(n, seed):
+    """Engine.measure_many == the same MEASUREs one by one (same uniforms): outcomes, p0 and the collapsed
+    state, on a relabelled layout."""
+    spec = orc.random_circuit_spec(n, 5, seed)
+    rs = np.random.RandomState(seed)
+    order = [int(q) for q in rs.permutation(n)]
+    uniforms = rs.random_sample(n)
+    out = {}
+    for fused in (True, False):
+        eng = _engine.Engine(n)
+        eng.reset()
+        for name, params, qubits in spec:
+            m = G.gate_matrix[name]
+            eng.queue_matrix(m(*params) if params else m, qubits)
+        if fused:
+            res = eng.measure_many(order, uniforms)
+        else:
+            res = [eng.measure(q, r) for q, r in zip(order, uniforms)]
+        passes = eng.stats()["hbm_passes"]
+        out[fused] = (res, eng.amplitudes(), passes)
+        eng.close()
+    assert [o for o, _ in out[True][0]] == [o for o, _ in out[False][0]]
+    assert np.max(np.abs(np.array([p for _, p in out[True][0]]) - np.array([p for _, p in out[False][0]]))) < 1e-12
+    assert np.max(np.abs(out[True][1] - out[False][1])) < 1e-12
+    index = sum(o << q for (o, _), q in zip(out[True][0], order))
+    assert abs(abs(out[True][1][index]) - 1.0) < 1e-12

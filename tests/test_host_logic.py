@@ -144,3 +144,59 @@ def test_tensor_up_small():
     assert np.allclose(m, 2 * np.kron(G.Y, G.X))
     with pytest.raises(TypeError):
         ug.tensor_up("X0", 2)
+
+
+# ---- runs of MEASUREs: the host replay of the sequential decisions (Engine.measure_many) -----------------
+class _HistState(object):
+    """numpy model of qvm_measure_hist (tests only): collapse, then |amp|^2 summed per (high-bin, lane)."""
+
+    def __init__(self, psi, n):
+        self.psi = np.array(psi, dtype=np.complex128)
+        self.n_local, self.device, self.passes = n, 0, 0
+
+    def measure_hist(self, high_positions, collapse=None, want_hist=True):
+        self.passes += 1
+        idx = np.arange(self.psi.size, dtype=np.int64)
+        if collapse is not None:
+            mask, value, scale = collapse
+            self.psi = np.where((idx & mask) == value, self.psi * scale, 0.0)
+        if not want_hist:
+            return None
+        bins = np.zeros_like(idx)
+        for i, p in enumerate(high_positions):
+            assert p >= 5
+            bins |= ((idx >> p) & 1) << i
+        hist = np.zeros((1 << len(high_positions), 32))
+        np.add.at(hist, (bins, idx & 31), np.abs(self.psi) ** 2)
+        return hist
+
+    def close(self):
+        pass
+
+
+@pytest.mark.parametrize("n,seed", [(10, 0), (12, 1), (13, 2)])
+def test_measure_many_replays_the_sequential_measurements(n, seed):
+    from referenceqvm import _engine
+    from oracle import qvm_oracle as orc
+    rs = np.random.RandomState(seed)
+    psi = rs.standard_normal(1 << n) + 1j * rs.standard_normal(1 << n)
+    psi /= np.linalg.norm(psi)
+    for order in (list(range(n)), list(rs.permutation(n)), list(rs.permutation(n)[:7]), [n - 1, 0]):
+        eng = _engine.Engine(n, _state=_HistState(psi, n))
+        eng.pos_of = [int(p) for p in rs.permutation(n)]          # a relabelled layout
+        logical = np.arange(1 << n, dtype=np.int64)
+        phys = np.zeros_like(logical)
+        for q, p in enumerate(eng.pos_of):
+            phys |= ((logical >> q) & 1) << p
+        stored = np.empty_like(psi)
+        stored[phys] = psi
+        eng.state.psi = stored
+        uniforms = rs.random_sample(len(order))
+        got = eng.measure_many(order, uniforms)
+        want = psi
+        for (outcome, p0), q, r in zip(got, order, uniforms):
+            o_want, p_want, want = orc.fast_measure(want, int(q), n, r)
+            assert outcome == o_want and abs(p0 - p_want) < 1e-12
+        assert np.max(np.abs(eng.state.psi[phys] - want)) < 1e-12
+        n_high = sum(1 for q in order if eng.pos_of[q] >= 5)
+        assert eng.state.passes <= (n_high + 4) // 5 + 2           # chunks of <= 5 high positions + final collapse
