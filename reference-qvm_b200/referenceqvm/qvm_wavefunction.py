@@ -410,6 +410,14 @@ class QVM_Wavefunction(QAM):
         results = []
         for _ in range(trials):
             self._simulate(pyquil_program, None)
+            inside = [q for q in qubits if q < self.num_qubits]
+            if hasattr(self._engine, "measure_many") and len(set(inside)) == len(inside) > 1:
+                # one uniform per measured qubit, in the order the loop below would draw them
+                uniforms = [np.random.random() for _ in inside]
+                outcomes = iter(self._engine.measure_many([self._virt[q] for q in inside], uniforms))
+                trial_results = [next(outcomes)[0] if q < self.num_qubits else 0 for q in qubits]
+                results.append(trial_results)
+                continue
             trial_results = []
             for qubit_index in qubits:
                 if qubit_index < self.num_qubits:
