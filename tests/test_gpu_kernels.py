@@ -616,3 +616,29 @@ def test_measure_many_on_device_matches_sequential_measure(n, seed):
     assert np.max(np.abs(out[True][1] - out[False][1])) < 1e-12
     index = sum(o << q for (o, _), q in zip(out[True][0], order))
     assert abs(abs(out[True][1][index]) - 1.0) < 1e-12
+
+
+def test_relabel_and_layout_argument_checks():
+    """Bad requests are refused with QVM_ERR_INVALID (ValueError), and the state is left alone."""
+    n = 12
+    psi = random_state(n, 2)
+    st = nat.DeviceState(n)
+    st.set_state(psi)
+    tile = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10]
+    with pytest.raises(ValueError):
+        st.apply_group(tile, [], bring_low=[11], n_low=4)             # position outside the tile
+    with pytest.raises(ValueError):
+        st.get_layout(0, 1, 1 << n, [0] * n)                           # not a permutation
+    with pytest.raises(ValueError):
+        st.get_layout(0, 1, 1 << n, list(range(n - 1)))                # wrong length
+    with pytest.raises(ValueError):
+        st.get_layout(5, 3, 1 << n, list(range(n)))                    # range runs off the shard
+    assert np.array_equal(st.get_state(), psi)
+    # a request for more qubits than there are low positions: the first ones win, the report is truthful
+    new_pos = st.apply_group(tile, [], bring_low=[5, 6, 7, 8, 9, 10], n_low=4)
+    pos_of = list(range(n))
+    for p, q in zip(tile, new_pos):
+        pos_of[p] = q
+    assert sorted(pos_of) == list(range(n)) and sum(1 for p in (5, 6, 7, 8, 9, 10) if pos_of[p] < 4) == 4
+    assert np.array_equal(st.get_layout(0, 1, 1 << n, pos_of), psi)
+    st.close()
