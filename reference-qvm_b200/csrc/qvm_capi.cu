@@ -429,8 +429,10 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
             double2* amps = q->amps;
             SpecParams sp = ss.params;
             void* args[3] = {&amps, &sp, const_cast<double*>(ss.factors.data())};
-            QVM_CUDA(q, cudaLaunchKernel((const void*)cs->kernel, dim3((unsigned)g.n_tiles), dim3(ss.threads), args, ss.smem,
-                                         q->stream));
+            unsigned grid = (unsigned)g.n_tiles;
+            if (ss.ctas_per_sm)      // persistent, pipelined variant
+                grid = (unsigned)std::min<uint64_t>(g.n_tiles, (uint64_t)q->sm_count * ss.ctas_per_sm);
+            QVM_CUDA(q, cudaLaunchKernel((const void*)cs->kernel, dim3(grid), dim3(ss.threads), args, ss.smem, q->stream));
             q->stats.kernel_launches += 1;
             q->stats.jit_launches += 1;
             q->stats.gate_ops += (uint64_t)g.n_gate_ops;

@@ -33,6 +33,7 @@ namespace qvm {
 struct SpecParams {
     int n_runs;
     uint64_t shard_bits, run_start, run_len;
+    uint64_t n_tiles;                // pipelined variant: tiles are walked by a persistent grid
 };
 
 struct SpecSource {
@@ -41,6 +42,7 @@ struct SpecSource {
     unsigned threads = 0;
     size_t smem = 0;
     uint64_t n_tiles = 0;
+    unsigned ctas_per_sm = 0;        // > 0: persistent (pipelined) kernel, grid = min(n_tiles, SMs * ctas_per_sm)
     SpecParams params{};
 };
 
@@ -97,6 +99,16 @@ inline bool spec_streaming() {
     return on;
 }
 
+// QVM_B200_SPEC_PIPE=1: persistent CTAs that prefetch their next tile with cp.async into a second
+// shared-memory buffer while they compute the current one (load, FP64 and store phases of ONE CTA overlap).
+inline bool spec_pipelined() {
+    static const bool on = [] {
+        const char* e = getenv("QVM_B200_SPEC_PIPE");
+        return e && atoi(e) != 0;
+    }();
+    return on;
+}
+
 // Source for one encoded group (lean R = 4 groups only).  Factors never appear as literals: F.v[i]
 // indexes a by-value kernel argument -- first the encoder's matrix pool, then the factors the encoder
 // inlined into the op stream, then the round scalars.
@@ -129,6 +141,7 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
             if (g.cold[j].word_off == word && g.cold[j].slot == slot && g.cold[j].kind == kind) return &g.cold[j];
         return nullptr;
     };
+    const bool pipe = spec_pipelined() && P.k - 4 >= P.low;
     std::ostringstream body;
     for (int r = 0; r < P.n_rounds; ++r) {
         const RoundDesc& rd = g.rounds[r];
@@ -137,7 +150,7 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
         for (int s = 0; s < 4; ++s) body << "    T += T & 0x" << std::hex << rd.ins_mask[s] << std::dec << "u;\n";
         body << "    const uint32_t sT = swz(T);\n    const uint32_t st[4] = {" << rd.swz_j[0] << "u, " << rd.swz_j[1] << "u, "
              << rd.swz_j[2] << "u, " << rd.swz_j[3] << "u};\n";
-        if (first) {
+        if (first && !pipe) {
             body << "    {\n      const uint64_t gT = (uint64_t)(T & " << ((1u << P.low) - 1u) << "u) | hi_off[T >> " << P.low
                  << "];\n      const int64_t b[4] = {";
             for (int s = 0; s < 4; ++s) body << (s ? ", " : "") << "(int64_t)(16ull << " << (int)rd.reg_phys[s] << ")";
@@ -227,7 +240,7 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
                  << ";\n    }\n";
         } else if (r == P.perm_round) {
             // relabelling round: the tile is written in the last round's coordinates (qvm_encode.h)
-            if (!first) body << "    __syncthreads();\n";
+            if (!first || pipe) body << "    __syncthreads();\n";
             body << "    uint32_t sX = 0u;\n";
             for (int b = 0; b < P.k; ++b)
                 body << "    sX ^= (0u - ((T >> " << b << ") & 1u)) & " << P.perm_swz[b] << "u;\n";
@@ -244,24 +257,60 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
     if (F.empty()) F.push_back(0.0);
     if (F.size() > 3900) return false;          // kernel parameters are limited to 32 KB
     o << "#include \"qvm_regtile.cuh\"\nusing namespace qvm;\n"
-         "struct SpecParams { int n_runs; uint64_t shard_bits, run_start, run_len; };\n"
+         "struct SpecParams { int n_runs; uint64_t shard_bits, run_start, run_len, n_tiles; };\n"
          "struct SpecFactors { double v[" << F.size() << "]; };\n"
          "__device__ const uint64_t hi_off[" << g.hi_off.size() << "] = {";
     for (size_t j = 0; j < g.hi_off.size(); ++j) o << (j ? ", " : "") << hexu(g.hi_off[j]);
     o << "};\n";
-    o << "extern \"C\" __global__ void __launch_bounds__(" << g.threads << ", " << spec_min_blocks(g.threads)
-      << ") spec_kernel(double2* __restrict__ state, const SpecParams SP, const SpecFactors F) {\n"
-         "  extern __shared__ __align__(16) unsigned char smem_raw[];\n  double2* tile = reinterpret_cast<double2*>(smem_raw);\n"
-         "  const uint32_t tid = threadIdx.x;\n  uint64_t base = 0;\n  {\n    uint64_t t = blockIdx.x;\n"
-         "    for (int r = 0; r < SP.n_runs; ++r) {\n      const uint32_t len = (uint32_t)(SP.run_len >> (8 * r)) & 0xFFu;\n"
-         "      base |= (t & ((1ull << len) - 1ull)) << ((uint32_t)(SP.run_start >> (8 * r)) & 0xFFu);\n      t >>= len;\n    }\n  }\n"
-         "  const uint64_t full = base | SP.shard_bits;\n  double2* gbase = state + base;\n  double2 a[16];\n"
-      << body.str() << "}\n";
+    const char* tile_base_fn =
+        "__device__ __forceinline__ uint64_t spec_tile_base(const SpecParams& SP, uint64_t t) {\n  uint64_t base = 0;\n"
+        "  for (int r = 0; r < SP.n_runs; ++r) {\n    const uint32_t len = (uint32_t)(SP.run_len >> (8 * r)) & 0xFFu;\n"
+        "    base |= (t & ((1ull << len) - 1ull)) << ((uint32_t)(SP.run_start >> (8 * r)) & 0xFFu);\n    t >>= len;\n  }\n"
+        "  return base;\n}\n";
+    o << tile_base_fn;
+    const unsigned ctas = pipe ? std::max(1u, std::min(spec_min_blocks(g.threads), (unsigned)((220u * 1024u) / ((size_t)32 << P.k))))
+                               : spec_min_blocks(g.threads);
+    if (!pipe) {
+        o << "extern \"C\" __global__ void __launch_bounds__(" << g.threads << ", " << ctas
+          << ") spec_kernel(double2* __restrict__ state, const SpecParams SP, const SpecFactors F) {\n"
+             "  extern __shared__ __align__(16) unsigned char smem_raw[];\n  double2* tile = reinterpret_cast<double2*>(smem_raw);\n"
+             "  const uint32_t tid = threadIdx.x;\n  const uint64_t base = spec_tile_base(SP, blockIdx.x);\n"
+             "  const uint64_t full = base | SP.shard_bits;\n  double2* gbase = state + base;\n  double2 a[16];\n"
+          << body.str() << "}\n";
+    } else {
+        // Persistent CTA, two tile buffers.  Thread `tid` fetches the tile-local indices tid + threads * j
+        // (j = 0..15): consecutive lanes read consecutive amplitudes (256-byte runs), the global offset splits
+        // into a per-thread part (low bits, and the tile bits fed by the upper bits of tid) and a constant per
+        // j, and the shared-memory slot is swz(tid) ^ swz(threads * j) because the swizzle is linear.
+        const uint32_t tbits = (uint32_t)P.k - 4u;                 // bits of the tile index that come from tid
+        o << "__device__ __forceinline__ void spec_prefetch(double2* buf, const double2* gsrc, uint32_t tid) {\n"
+             "  const uint32_t sD = swz(tid);\n"
+             "  const double2* src = gsrc + ((uint64_t)(tid & " << ((1u << P.low) - 1u) << "u) | hi_off[tid >> " << P.low << "]);\n";
+        for (uint32_t j = 0; j < 16; ++j) {
+            const uint32_t i = j << tbits;
+            o << "  cp_async16(&buf[sD ^ " << swz(i) << "u], src + " << hexu(g.hi_off[i >> P.low]) << ");\n";
+        }
+        o << "  asm volatile(\"cp.async.commit_group;\" ::: \"memory\");\n}\n";
+        o << "extern \"C\" __global__ void __launch_bounds__(" << g.threads << ", " << ctas
+          << ") spec_kernel(double2* __restrict__ state, const SpecParams SP, const SpecFactors F) {\n"
+             "  extern __shared__ __align__(16) unsigned char smem_raw[];\n"
+             "  double2* const buf0 = reinterpret_cast<double2*>(smem_raw);\n  double2* const buf1 = buf0 + " << (1u << P.k) << ";\n"
+             "  const uint32_t tid = threadIdx.x;\n  uint64_t t = blockIdx.x;\n  if (t >= SP.n_tiles) return;\n"
+             "  spec_prefetch(buf0, state + spec_tile_base(SP, t), tid);\n  int cur = 0;\n"
+             "  for (; t < SP.n_tiles; t += gridDim.x, cur ^= 1) {\n"
+             "  double2* const tile = cur ? buf1 : buf0;\n"
+             "  asm volatile(\"cp.async.wait_all;\" ::: \"memory\");\n  __syncthreads();\n"
+             "  if (t + gridDim.x < SP.n_tiles) spec_prefetch(cur ? buf0 : buf1, state + spec_tile_base(SP, t + gridDim.x), tid);\n"
+             "  const uint64_t base = spec_tile_base(SP, t);\n"
+             "  const uint64_t full = base | SP.shard_bits;\n  double2* gbase = state + base;\n  double2 a[16];\n"
+          << body.str() << "  }\n}\n";
+    }
     out.src = o.str();
     out.threads = g.threads;
-    out.smem = P.n_rounds > 1 ? ((size_t)16 << P.k) : 0;
+    out.smem = pipe ? ((size_t)32 << P.k) : (P.n_rounds > 1 ? ((size_t)16 << P.k) : 0);
     out.n_tiles = g.n_tiles;
-    out.params = SpecParams{P.n_runs, P.shard_bits, P.run_start, P.run_len};
+    out.ctas_per_sm = pipe ? ctas : 0;
+    out.params = SpecParams{P.n_runs, P.shard_bits, P.run_start, P.run_len, g.n_tiles};
     return true;
 }
 

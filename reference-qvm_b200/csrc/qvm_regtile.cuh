@@ -176,6 +176,14 @@ struct RegTileParams {
     const uint64_t* hi_off;   // [2^(k-low)] global offset contributed by tile-index bits >= low
 };
 
+#if defined(__CUDA_ARCH__)
+// 16-byte asynchronous copy global -> shared (L2 only), used by the pipelined specialised kernels
+__device__ __forceinline__ void cp_async16(double2* smem_dst, const double2* gmem_src) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+#endif
+
 // ---- small helpers ----------------------------------------------------------------------------
 QVM_HD double2 cmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
