@@ -110,6 +110,14 @@ def test_every_gate_kind_and_position():
     for tile, low in ((12, 5), (10, 5), (9, 3)):
         got, stats = run_emulated(psi0, ops, n, tile, low)
         assert np.max(np.abs(got - want)) / scale < TOL, (tile, low)
+    # the same zoo under the relabelling planner (rare handlers, wide gates and relabelling together)
+    expanded = []
+    for op in ops:
+        expanded += list(_engine.expand_op(op))
+    for tile, low in ((10, 4), (9, 3), (11, 5)):
+        got, pos_of, passes, moved = run_emulated_relabelled(psi0, expanded, n, tile, low)
+        assert np.max(np.abs(logical_view(got, pos_of) - want)) / scale < TOL, (tile, low)
+        assert moved > 0
 
 
 def test_projector_diagonal_with_zero_entry():
