@@ -174,7 +174,9 @@ int qvm_measure(qvm_t* q, int qubit, double r, int* outcome, double* p0);
  * `lane`.  The caller replays the reference's sequential decisions on it -- p0 of each measured qubit given
  * the outcomes so far, one uniform each, outcome 0 iff r < p0, scale 1/sqrt(p0) or 1/sqrt(1 - p0) -- and
  * passes the combined projection to the next call (n_high = 0, hist = NULL for a final collapse only).
- * Summation order is fixed: results are deterministic to the last bit. */
+ * Summation order is fixed: results are deterministic to the last bit.  On a shard the positions are
+ * local and the histogram covers the shard; the caller gathers the shards' histograms (a measured global
+ * position is the same bit for a whole shard) and hands every shard its own projection. */
 int qvm_measure_hist(qvm_t* q, int n_high, const int32_t* high_pos, int do_collapse, uint64_t keep_mask,
                      uint64_t keep_value, double scale, double* hist);
 /* Batched trials (qvm_wavefunction.py:266-283: run() re-simulates the program once per trial).  The

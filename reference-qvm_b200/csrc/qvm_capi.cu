@@ -966,7 +966,6 @@ int qvm_measure(qvm_t* q, int qubit, double r, int* outcome, double* p0) {
 int qvm_measure_hist(qvm_t* q, int n_high, const int32_t* high_pos, int do_collapse, uint64_t keep_mask,
                      uint64_t keep_value, double scale, double* hist) {
     QVM_CHECK_HANDLE(q);
-    if (q->n_global) return fail(QVM_ERR_INVALID, "qvm_measure_hist is single-shard");
     if (q->n_local < 5) return fail(QVM_ERR_INVALID, "qvm_measure_hist needs at least 5 local positions");
     if (n_high < 0 || n_high > 5 || (n_high && !high_pos)) return fail(QVM_ERR_INVALID, "0..5 high positions");
     HistBits hb{};

@@ -146,6 +146,9 @@ class CudaShard(object):
     def prob_zero(self, position):
         return self.state.prob_zero(position)
 
+    def measure_hist(self, high_positions, collapse=None, want_hist=True):
+        return self.state.measure_hist(high_positions, collapse, want_hist)
+
     def collapse(self, position, outcome, scale):
         self.state.collapse(position, outcome, scale)
 
@@ -555,6 +558,70 @@ class ShardedEngine(object):
         scale = 1.0 / np.sqrt(p0 if outcome == 0 else 1.0 - p0)
         self.shard.collapse(pos, outcome, scale)
         return outcome, p0
+
+    def measure_many(self, qubits, uniforms):
+        """``Engine.measure_many`` for a sharded state: every rank builds the joint distribution of its own
+        shard (local high positions x the 5 lowest index bits), the histograms are all-gathered -- a measured
+        GLOBAL position is simply a bit of the rank -- and every rank replays the same sequential decisions
+        on the same numbers (rank 0's uniforms), then applies its own part of the projection (a rank whose
+        global bits lost keeps nothing).  Needs a backend with ``measure_hist``."""
+        qubits = [int(q) for q in qubits]
+        if len(set(qubits)) != len(qubits):
+            raise ValueError("measure_many needs distinct qubits")
+        if self.n_local < 10 or len(qubits) < 2 or not hasattr(self.shard, "measure_hist"):
+            return [self.measure(q, r) for q, r in zip(qubits, uniforms)]
+        self.flush()
+        uniforms = self._broadcast_floats(np.asarray(uniforms, dtype=np.float64))
+        rank, world, nl = self.ctx.rank, self.ctx.world, self.n_local
+        positions = [self.pos_of[q] for q in qubits]
+        lanes = np.arange(32)[None, None, :]
+        ranks = np.arange(world)[:, None, None]
+        results = []
+        pending = None
+        i = 0
+        while i < len(positions):
+            chunk, high = [], []
+            while i + len(chunk) < len(positions):
+                p = positions[i + len(chunk)]
+                if 5 <= p < nl:
+                    if len(high) == 5:
+                        break
+                    high.append(p)
+                chunk.append(p)
+            local = self.shard.measure_hist(high, pending)
+            hist = self._allgather_array(local.reshape(-1)).reshape((world,) + local.shape)
+            bins = np.arange(local.shape[0])[None, :, None]
+            consistent = np.ones(hist.shape, dtype=bool)
+            norm_factor, mask, value, alive = 1.0, 0, 0, True
+            for j, p in enumerate(chunk):
+                if p >= nl:
+                    bit = (ranks >> (p - nl)) & 1
+                elif p >= 5:
+                    bit = (bins >> high.index(p)) & 1
+                else:
+                    bit = (lanes >> p) & 1
+                bit = np.broadcast_to(bit, hist.shape)
+                p0 = norm_factor * float(hist[consistent & (bit == 0)].sum())
+                outcome = 0 if float(uniforms[i + j]) < p0 else 1
+                norm_factor *= 1.0 / (p0 if outcome == 0 else 1.0 - p0)
+                consistent = consistent & (bit == outcome)
+                if p >= nl:
+                    alive = alive and ((rank >> (p - nl)) & 1) == outcome
+                else:
+                    mask |= 1 << p
+                    value |= outcome << p
+                results.append((outcome, p0))
+            pending = (mask, value, float(np.sqrt(norm_factor)) if alive else 0.0)
+            i += len(chunk)
+        self.shard.measure_hist([], pending, want_hist=False)
+        return results
+
+    def _allgather_array(self, values):
+        """The same 1-D float64 array from every rank, concatenated in rank order (identical everywhere)."""
+        mine = self.shard.scalar_tensor(np.ascontiguousarray(values, dtype=np.float64))
+        out = self.shard.scalar_tensor(np.zeros(mine.numel() * self.ctx.world))
+        self.dist.all_gather(list(out.split(mine.numel())), mine, group=self.ctx.group)
+        return out.cpu().numpy()
 
     def prob_zero(self, qubit):
         self.flush()

@@ -109,6 +109,23 @@ class NumpyShard(object):
             self.psi = self.psi[idx]
         return new_pos
 
+    def measure_hist(self, high_positions, collapse=None, want_hist=True):
+        """Model of qvm_measure_hist on this shard: optional collapse, then |amp|^2 per (high-bin, lane)."""
+        idx = np.arange(self.psi.size, dtype=np.int64)
+        if collapse is not None:
+            mask, value, scale = collapse
+            self.psi = np.where((idx & mask) == value, self.psi * scale, 0.0)
+        self.launches += 1
+        if not want_hist:
+            return None
+        bins = np.zeros_like(idx)
+        for i, p in enumerate(high_positions):
+            assert 5 <= p < self.n_local
+            bins |= ((idx >> p) & 1) << i
+        hist = np.zeros((1 << len(high_positions), 32))
+        np.add.at(hist, (bins, idx & 31), np.abs(self.psi) ** 2)
+        return hist
+
     def _half_index(self, bit, value, off, cnt):
         j = np.arange(off, off + cnt, dtype=np.int64)
         lo = j & ((1 << bit) - 1)

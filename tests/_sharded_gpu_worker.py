@@ -57,6 +57,26 @@ def main():
         assert err < 1e-12, ("after measure", err)
         eng.close()
 
+    # a run of MEASUREs on the sharded state (measure_hist per shard, all-gathered): all qubits, shuffled
+    for n, depth, seed in ((18, 5, 7), (16, 6, 9)):
+        spec = orc.random_circuit_spec(n, depth, seed)
+        eng = _sharded.ShardedEngine(n, ctx)
+        eng.reset()
+        for name, params, qubits in spec:
+            m = G.gate_matrix[name]
+            eng.queue_matrix(m(*params) if params else m, qubits)
+        psi, _ = orc.fast_run_wavefunction(oracle_ops(spec), n)
+        rs = np.random.RandomState(seed)
+        order = [int(q) for q in rs.permutation(n)]
+        uniforms = rs.random_sample(n)
+        got = eng.measure_many(order, uniforms if rank == 0 else np.zeros(n))
+        for (outcome, p0), q, r in zip(got, order, uniforms):
+            o_want, p_want, psi = orc.fast_measure(psi, q, n, r)
+            assert outcome == o_want and abs(p0 - p_want) < 1e-12
+        err = float(np.max(np.abs(eng.amplitudes() - psi)))
+        assert err < 1e-12, ("after measure_many", err)
+        eng.close()
+
     # the public API, sharded: QVMConnection on every rank (SPMD)
     n = 15
     spec = orc.random_circuit_spec(n, 6, 7)

@@ -95,6 +95,32 @@ def main():
         assert np.array_equal(idx.astype(np.int64), np.asarray(ref, dtype=np.int64))
         eng.close()
         checked += 1
+    # runs of MEASUREs on a sharded state (local shards of >= 10 positions): joint distribution per shard,
+    # all-gathered; measured global positions are rank bits; every rank takes the same decisions
+    for n, depth, seed in ((12, 5, 3), (13, 4, 8)):
+        spec = orc.random_circuit_spec(n, depth, seed)
+        eng = _sharded.ShardedEngine(n, ctx, tile_bits=5, low_bits=2, backend_factory=NumpyShard)
+        eng.reset()
+        for name, params, qubits in spec:
+            m = G.gate_matrix[name]
+            eng.queue_matrix(m(*params) if params else m, qubits)
+        want, _ = orc.fast_run_wavefunction(oracle_ops(spec), n)
+        rs = np.random.RandomState(seed)
+        order = [int(q) for q in rs.permutation(n)]
+        uniforms = rs.random_sample(n)
+        eng.flush()
+        launches = eng.shard.launches
+        got = eng.measure_many(order, uniforms if rank == 0 else np.zeros(n))      # rank 0's draws win
+        assert any(eng.pos_of[q] >= eng.n_local for q in order)
+        assert eng.shard.launches - launches <= (n + 4) // 5 + 2                     # chunks, not 2 passes per qubit
+        psi = want
+        for (outcome, p0), q, r in zip(got, order, uniforms):
+            o_want, p_want, psi = orc.fast_measure(psi, q, n, r)
+            assert outcome == o_want and abs(p0 - p_want) < 1e-12
+        err = float(np.max(np.abs(eng.amplitudes() - psi)))
+        assert err < 1e-12, ("after measure_many", err)
+        eng.close()
+        checked += 1
     dist.barrier()
     dist.destroy_process_group()
     print("rank %d/%d ok (%d circuits)" % (rank, world, checked))
