@@ -124,3 +124,68 @@ def test_diagonal_merger_is_exact_up_to_rounding():
     for op in pending:
         got = apply_op(got, op, n)
     assert np.max(np.abs(got - want)) < 1e-14
+
+
+# ---- the relabelling planner against launchers that do less (or nothing) of what it asks -------------------
+def _run_relabelled_on_model(ops, n, tile_bits, low_bits, honour):
+    """Drive _planner.run_relabelled with a numpy launcher; ``honour(bring)`` picks which requests are granted."""
+    import numpy as np
+    from _model import apply_op, random_state
+    from referenceqvm import _planner
+    psi0 = random_state(n, 3)
+    box = {"psi": psi0.copy(), "launches": 0}
+    pos_of = list(range(n))
+
+    def launch(tile, phys_ops, bring):
+        tile = list(tile)
+        assert tile == sorted(tile) and len(set(tile)) == len(tile)
+        for op in phys_ops:
+            assert op.kind != 1 or all(t in tile for t in op.targets), "dense target outside the tile"
+            box["psi"] = apply_op(box["psi"], op, n)
+        box["launches"] += 1
+        new_pos = list(tile)
+        granted = honour(list(bring or []))
+        incoming = [p for p in granted if p >= low_bits]
+        victims = [p for p in range(low_bits) if p not in (bring or []) and p in tile][:len(incoming)]
+        idx = np.arange(box["psi"].size, dtype=np.int64)
+        for a, b in zip(incoming, victims):
+            new_pos[tile.index(a)], new_pos[tile.index(b)] = b, a
+            differ = ((idx >> a) ^ (idx >> b)) & 1
+            idx = idx ^ (differ * ((1 << a) | (1 << b)))
+        box["psi"] = box["psi"][idx]
+        return new_pos
+
+    passes = _planner.run_relabelled(ops, n, pos_of, launch, tile_bits, low_bits)
+    logical = np.arange(1 << n, dtype=np.int64)
+    phys = np.zeros_like(logical)
+    for q, p in enumerate(pos_of):
+        phys |= ((logical >> q) & 1) << p
+    want = psi0
+    for op in ops:
+        want = apply_op(want, op, n)
+    assert passes == box["launches"]
+    return float(np.max(np.abs(box["psi"][phys] - want))), passes, pos_of
+
+
+def test_relabelling_planner_survives_a_library_that_relabels_less_than_asked():
+    import numpy as np
+    from oracle import qvm_oracle as orc
+    from referenceqvm import _engine, gates as G
+    n = 13
+    ops = []
+    for name, params, qubits in orc.random_circuit_spec(n, 10, 17):
+        m = G.gate_matrix[name]
+        ops += list(_engine.expand_op(_engine.compile_gate(m(*params) if params else m, qubits)))
+    rs = np.random.RandomState(4)
+    dense3 = rs.standard_normal((8, 8)) + 1j * rs.standard_normal((8, 8))
+    ops.insert(len(ops) // 2, _engine.compile_gate(dense3, [11, 2, 7]))        # a gate wider than tile - low
+    results = {}
+    for name, honour in (("all", lambda b: b), ("none", lambda b: []), ("first", lambda b: b[:1]),
+                         ("random", lambda b: [p for p in b if rs.randint(2)])):
+        err, passes, pos_of = _run_relabelled_on_model(ops, n, 5, 3, honour)
+        assert err < 1e-9 * 8 ** 3, (name, err)        # (the random dense 8x8 is not unitary: the norm grows)
+        assert sorted(pos_of) == list(range(n))
+        results[name] = passes
+    fixed = len(_planner.plan(ops, n, 5, 3))
+    assert results["none"] <= fixed + 1             # nothing granted: it degrades to the fixed-layout plan
+    assert results["all"] < results["none"]         # and relabelling is what saves the passes
