@@ -338,6 +338,9 @@ public:
         auto it = cache_.find(src);
         if (it != cache_.end()) return it->second->state == READY ? &it->second->cs : nullptr;
         if (stopping_) return nullptr;
+        // bounded: a service that keeps meeting new structures stops compiling (the interpreter serves them)
+        if (cache_.size() >= kMaxCompiledStructures) return nullptr;
+        if (seen_.size() > (1u << 20)) seen_.clear();
         if (policy < 2 && ++seen_[std::hash<std::string>()(src)] < 2) return nullptr;
         Entry* e = new Entry();
         cache_.emplace(src, std::unique_ptr<Entry>(e));
@@ -423,6 +426,7 @@ public:
     }
 
 private:
+    static constexpr size_t kMaxCompiledStructures = 4096;      // loaded modules kept for the life of the process
     enum { PENDING = 0, READY = 1, FAILED = 2 };
     struct Entry {
         int state = PENDING;
