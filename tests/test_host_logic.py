@@ -200,3 +200,45 @@ def test_measure_many_replays_the_sequential_measurements(n, seed):
         assert np.max(np.abs(eng.state.psi[phys] - want)) < 1e-12
         n_high = sum(1 for q in order if eng.pos_of[q] >= 5)
         assert eng.state.passes <= (n_high + 4) // 5 + 2           # chunks of <= 5 high positions + final collapse
+
+
+# ---- batched trials: host pieces that need no device ---------------------------------------------------------
+def test_batched_classical_matches_the_per_trial_state_machine():
+    """QVM_Wavefunction._batched_classical on a (trials x addresses) bit matrix == QAM._classical_transition
+    applied to every row on its own (qam.py's semantics for TRUE/FALSE/NOT/AND/OR/MOVE/EXCHANGE)."""
+    from pyquil.gates import AND, EXCHANGE, FALSE, MOVE, NOT, OR, TRUE
+    from pyquil.quil import Program
+    from referenceqvm.qvm_wavefunction import QVM_Wavefunction
+    from referenceqvm.gates import gate_matrix
+    rs = np.random.RandomState(0)
+    instrs = [TRUE(0), FALSE(1), NOT(2), AND(0, 3), OR(1, 4), MOVE(2, 5), EXCHANGE(3, 6), NOT(0), AND(5, 5), OR(6, 2),
+              EXCHANGE(1, 1), MOVE(7, 0)]
+    mem = rs.randint(0, 2, size=(64, 8)).astype(bool)
+    batched = mem.copy()
+    for ins in instrs:
+        QVM_Wavefunction._batched_classical(ins, batched)
+    qvm = QVM_Wavefunction(gate_set=gate_matrix, defgate_set={})
+    qvm.program = Program(*instrs)
+    for row in range(mem.shape[0]):
+        qvm.classical_memory = mem[row].copy()
+        qvm.program_counter = 0
+        for ins in instrs:
+            assert qvm._classical_transition(ins)
+        assert np.array_equal(qvm.classical_memory, batched[row]), row
+
+
+def test_batchable_decision():
+    from pyquil.gates import CNOT, H, MEASURE, NOT, X
+    from pyquil.quil import Program
+    from referenceqvm.qvm_wavefunction import QVM_Wavefunction
+    from referenceqvm.gates import gate_matrix
+    qvm = QVM_Wavefunction(gate_set=gate_matrix, defgate_set={})
+    mid = Program(H(0), MEASURE(0, 0), CNOT(0, 1), NOT(0), MEASURE(1, 1))
+    assert qvm._batchable(mid) and qvm._terminal_measure_block(mid) is None
+    assert qvm._terminal_measure_block(Program(H(0), CNOT(0, 1), MEASURE(0, 0), MEASURE(1, 1))) == 2
+    looped = Program(X(0), MEASURE(0, 0)).while_do(0, Program(X(0), MEASURE(0, 0))) if hasattr(Program, "while_do") else None
+    if looped is not None:
+        assert not qvm._batchable(looped)
+    wide = Program(H(QVM_Wavefunction.BATCH_MAX_QUBITS), MEASURE(0, 0), H(0))
+    assert not qvm._batchable(wide)                  # one block per trial: segments above 2^20 amplitudes keep the loop
+    assert not qvm._batchable(Program())
