@@ -71,7 +71,12 @@ class QAM(object):
         the left/right operands of binary classical instructions (:141-144)."""
         q_top, c_top = -1, -1
         for inst in self.program:
-            if isinstance(inst, Measurement):
+            if isinstance(inst, Gate):                      # (first: nearly every instruction is a gate)
+                for q in inst.qubits:
+                    v = value_get(q)
+                    if v > q_top:
+                        q_top = v
+            elif isinstance(inst, Measurement):
                 if value_get(inst.qubit) > q_top:
                     q_top = value_get(inst.qubit)
                 elif value_get(inst.classical_reg) > c_top:
@@ -83,8 +88,6 @@ class QAM(object):
                     c_top = value_get(inst.left)
                 elif value_get(inst.right) > c_top:
                     c_top = value_get(inst.right)
-            elif isinstance(inst, Gate):
-                q_top = max(q_top, max(value_get(q) for q in inst.qubits))
         if q_top + 1 > Q_LIMIT:
             raise RuntimeError("Too many qubits. Maximum qubit number supported: {}".format(Q_LIMIT))
         return (q_top + 1, c_top + 1)
