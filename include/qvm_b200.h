@@ -67,6 +67,8 @@ typedef struct qvm_stats {
     uint64_t regtile_rounds;              /* register-tile rounds run by those launches            */
     uint64_t jit_launches;                /* launches that ran a specialised (NVRTC-built) kernel  */
     uint64_t jit_compiles;                /* group structures submitted for compilation (process)  */
+    uint64_t push_launches;               /* stand-alone out-of-place exchange passes (qvm_exchange_push) */
+    uint64_t fused_push_launches;         /* gate passes whose stores WERE the exchange (qvm_apply_group_push) */
 } qvm_stats_t;
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
@@ -84,7 +86,7 @@ int qvm_destroy(qvm_t* q);
 int qvm_set_shard(qvm_t* q, int n_global, uint64_t shard_index);
 /* Run on a caller-owned cudaStream_t (0 restores the handle's own stream). */
 int qvm_set_stream(qvm_t* q, void* cuda_stream);
-int qvm_set_tile_bits(qvm_t* q, int tile_bits, int low_bits);   /* tuning: defaults 12 / 5      */
+int qvm_set_tile_bits(qvm_t* q, int tile_bits, int low_bits);   /* tuning (the host plans with 11 / 4) */
 /* 1 (default): register-tiled kernel where eligible; 0: shared-memory kernel only (testing).   */
 int qvm_set_kernel_path(qvm_t* q, int use_regtile);
 /* Specialised kernels for recurring group structures (NVRTC, cached by structure; new angles reuse
@@ -224,6 +226,36 @@ int qvm_exchange_half(qvm_t* q, int local_bit, int mine_value, void* peer_amps, 
  * 2^m-rank subgroup with mine_value = the peer's global bits and peer_value = its own. */
 int qvm_exchange_block(qvm_t* q, int m, const int32_t* local_bits, uint32_t mine_value, uint32_t peer_value,
                        void* peer_amps, uint64_t elem_offset, uint64_t count);
+
+
+/* ---- out-of-place exchange: write-only pushes over NVLink, optionally fused into the last gate pass ---- */
+/* The same global<->local swap of m (<= 3) qubit pairs as qvm_exchange_block, but out of place: a second
+ * buffer of the shard's size ("alternate", qvm_alt_alloc; QVM_ERR_NOMEM when it does not fit -- 36 qubits
+ * on 8 GPUs -- and the in-place exchange stays the path).  Every rank reads its current buffer ONCE and
+ * stores each amplitude where it will live: dst_ptrs[L] (2^m entries) is the ALTERNATE buffer of the rank
+ * whose global bits equal L (bit i of L belongs to local_bits[i], ascending local positions, and to the
+ * i-th swapped global bit); dst_ptrs[mine_value] may be NULL (= this handle's own alternate buffer).  The
+ * amplitude at local index x goes to dst_ptrs[victim bits of x] at index (x with the victim bits replaced
+ * by mine_value).  On return (stream-ordered) the handle's current and alternate buffers have swapped
+ * roles; the caller runs ONE cross-rank barrier on the stream before anyone reads its new current buffer
+ * (the previous epoch's barrier already guarantees nobody still reads the buffer being written).
+ * Peer pointers come from qvm_ipc_export / qvm_ipc_export_alt + qvm_ipc_open; all ranks push in the same
+ * epochs, so "peer's alternate buffer" alternates in lock step with the caller's own.
+ * No reference counterpart (the reference has no distributed path). */
+int qvm_alt_alloc(qvm_t* q);
+int qvm_alt_free(qvm_t* q);
+void* qvm_alt_ptr(qvm_t* q);
+int qvm_ipc_export_alt(qvm_t* q, void* handle64);
+int qvm_exchange_push(qvm_t* q, int m, const int32_t* local_bits, uint32_t mine_value, void* const* dst_ptrs);
+/* qvm_apply_group_relabel + qvm_exchange_push as ONE pass: the fused group's last round stores every tile
+ * directly into its destination shard (local HBM or a peer over NVLink), so the exchange costs no pass of
+ * its own.  Needs the victim bits outside the tile; otherwise (or when the group needs no launch / runs on
+ * the shared-memory fallback kernel) the library runs the group in place and the push after it.  *fused
+ * says which happened.  Buffers swap roles as in qvm_exchange_push. */
+int qvm_apply_group_push(qvm_t* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops,
+                         const double* mats, uint64_t mats_entries, int n_low, int n_bring, const int32_t* bring_low,
+                         int32_t* new_pos, int m, const int32_t* local_bits, uint32_t mine_value,
+                         void* const* dst_ptrs, int* fused);
 
 #ifdef __cplusplus
 }

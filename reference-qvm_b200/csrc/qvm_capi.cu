@@ -45,6 +45,7 @@ struct qvm_state {
     uint64_t shard_index = 0;
     uint64_t n_elems = 0;
     double2* amps = nullptr;
+    double2* alt = nullptr;           // second buffer of the same size (out-of-place exchange); roles swap at every push
     bool owns_amps = true;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -273,11 +274,16 @@ struct RelabelReq {
 };
 
 int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops,
-                         const double* mats, uint64_t mats_entries, bool* handled, RelabelReq* relabel);
+                         const double* mats, uint64_t mats_entries, bool* handled, RelabelReq* relabel,
+                         const PushSpec* push, bool* pushed);
 
-// Encode ops in tile-local coordinates and launch one tile kernel.
+// Encode ops in tile-local coordinates and launch one tile kernel.  With `push` (a fused exchange, see
+// PushSpec) the register-tiled kernels store the pass straight into the destination shards and *pushed
+// is set; when the group cannot carry it (no launch needed, shared-memory fallback kernel, victim bit
+// inside the tile) the pass runs in place and the caller pushes separately.
 int launch_group(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops, const double* mats,
-                 uint64_t mats_entries, RelabelReq* relabel = nullptr) {
+                 uint64_t mats_entries, RelabelReq* relabel = nullptr, const PushSpec* push = nullptr,
+                 bool* pushed = nullptr) {
     if (n_tile < 0 || n_tile > q->n_local || n_tile > QVM_MAX_TILE_BITS)
         return fail(QVM_ERR_INVALID, "tile of %d bits is outside [0, min(n_local=%d, %d)]", n_tile, q->n_local,
                     QVM_MAX_TILE_BITS);
@@ -303,7 +309,9 @@ int launch_group(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, 
 
     if (q->use_regtile) {
         bool handled = false;
-        int rc2 = launch_group_regtile(q, n_tile, tile_bits, n_ops, ops, mats, mats_entries, &handled, relabel);
+        if (push && push->m && (P.tile_mask & push->mask)) push = nullptr;     // a victim bit inside the tile: not fusable
+        int rc2 = launch_group_regtile(q, n_tile, tile_bits, n_ops, ops, mats, mats_entries, &handled, relabel, push,
+                                       pushed);
         if (rc2 != QVM_OK || handled) return rc2;
     }
     // (the shared-memory kernel below never relabels: relabel->sigma is still the identity)
@@ -400,7 +408,8 @@ int launch_regtile(qvm_state* q, unsigned grid, unsigned threads, size_t smem, c
 }
 
 int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops,
-                         const double* mats, uint64_t mats_entries, bool* handled, RelabelReq* relabel) {
+                         const double* mats, uint64_t mats_entries, bool* handled, RelabelReq* relabel,
+                         const PushSpec* push, bool* pushed) {
     *handled = false;
     EncodedGroup& g = q->enc;
     const int erc = encode_group(q->n_local, q->n_global, q->shard_index, n_tile, tile_bits, n_ops, ops, mats,
@@ -428,6 +437,10 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
             }
             double2* amps = q->amps;
             SpecParams sp = ss.params;
+            if (push && push->m) {
+                sp.push = *push;
+                if (pushed) *pushed = true;
+            }
             void* args[3] = {&amps, &sp, const_cast<double*>(ss.factors.data())};
             unsigned grid = (unsigned)g.n_tiles;
             if (ss.ctas_per_sm)      // persistent, pipelined variant
@@ -463,6 +476,10 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
     QVM_CUDA(q, cudaMemcpyAsync(q->ring_dev + off, hp, total_bytes, cudaMemcpyHostToDevice, q->stream));
     unsigned char* dp = q->ring_dev + off;
     RegTileParams P = g.P;
+    if (push && push->m) {
+        P.push = *push;
+        if (pushed) *pushed = true;
+    }
     P.rounds = reinterpret_cast<const RoundDesc*>(dp);
     P.hot = reinterpret_cast<const uint4*>(dp + rounds_bytes);
     P.cold = reinterpret_cast<const ColdOp*>(dp + rounds_bytes + hot_bytes);
@@ -612,6 +629,7 @@ int qvm_destroy(qvm_t* q) {
     cudaSetDevice(q->device);
     if (q->stream) cudaStreamSynchronize(q->stream);
     if (q->amps && q->owns_amps) cudaFree(q->amps);
+    if (q->alt) cudaFree(q->alt);
     if (q->ring_host) cudaFreeHost(q->ring_host);
     if (q->ring_dev) cudaFree(q->ring_dev);
     if (q->partials) cudaFree(q->partials);
@@ -1267,6 +1285,123 @@ int qvm_exchange_block(qvm_t* q, int m, const int32_t* local_bits, uint32_t mine
     q->sample_mode = -1;
     q->stats.kernel_launches += 1;
     q->stats.hbm_bytes += 32ull * count;
+    return QVM_OK;
+}
+
+// ---- out-of-place exchange: every rank pushes into its peers' alternate buffers ----------------------------
+int qvm_alt_alloc(qvm_t* q) {
+    QVM_CHECK_HANDLE(q);
+    if (q->alt) return QVM_OK;
+    if (!q->owns_amps) return fail(QVM_ERR_UNSUPPORTED, "handles on caller-owned memory have no alternate buffer");
+    cudaError_t e = cudaMalloc(&q->alt, q->n_elems * sizeof(double2));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        q->alt = nullptr;
+        return fail(e == cudaErrorMemoryAllocation ? QVM_ERR_NOMEM : QVM_ERR_CUDA, "alternate buffer of %llu bytes: %s",
+                    (unsigned long long)(q->n_elems * sizeof(double2)), cudaGetErrorString(e));
+    }
+    return QVM_OK;
+}
+
+int qvm_alt_free(qvm_t* q) {
+    QVM_CHECK_HANDLE(q);
+    if (!q->alt) return QVM_OK;
+    QVM_CUDA(q, cudaStreamSynchronize(q->stream));
+    QVM_CUDA(q, cudaFree(q->alt));
+    q->alt = nullptr;
+    return QVM_OK;
+}
+
+void* qvm_alt_ptr(qvm_t* q) { return q ? q->alt : nullptr; }
+
+int qvm_ipc_export_alt(qvm_t* q, void* handle64) {
+    QVM_CHECK_HANDLE(q);
+    if (!handle64) return fail(QVM_ERR_INVALID, "null pointer");
+    if (!q->alt) return fail(QVM_ERR_INVALID, "no alternate buffer (qvm_alt_alloc)");
+    cudaIpcMemHandle_t h;
+    QVM_CUDA(q, cudaIpcGetMemHandle(&h, q->alt));
+    memcpy(handle64, &h, sizeof(h));
+    return QVM_OK;
+}
+
+static int make_push(qvm_t* q, int m, const int32_t* local_bits, uint32_t mine_value, void* const* dst_ptrs, PushSpec* ps) {
+    if (m < 1 || m > kMaxPushBits || m > q->n_local || !local_bits || !dst_ptrs)
+        return fail(QVM_ERR_INVALID, "push exchange takes 1..%d victim bits", kMaxPushBits);
+    if (!q->alt) return fail(QVM_ERR_INVALID, "no alternate buffer (qvm_alt_alloc)");
+    if (mine_value >> m) return fail(QVM_ERR_INVALID, "own global-bit value outside %d bits", m);
+    *ps = PushSpec{};
+    ps->m = m;
+    for (int i = 0; i < m; ++i) {
+        const int p = local_bits[i];
+        if (p < 0 || p >= q->n_local || (i && p <= local_bits[i - 1]))
+            return fail(QVM_ERR_INVALID, "victim bits must be ascending local positions");
+        ps->pos[i] = (uint8_t)p;
+        ps->mask |= 1ull << p;
+        ps->mine_bits |= (uint64_t)((mine_value >> i) & 1u) << p;
+    }
+    for (uint32_t L = 0; L < (1u << m); ++L) {
+        void* d = L == mine_value ? (dst_ptrs[L] ? dst_ptrs[L] : (void*)q->alt) : dst_ptrs[L];
+        if (!d) return fail(QVM_ERR_INVALID, "null destination for victim value %u", L);
+        if (d == (void*)q->amps) return fail(QVM_ERR_INVALID, "a push must not target the buffer it reads");
+        ps->dst[L] = static_cast<double2*>(d);
+    }
+    return QVM_OK;
+}
+
+static int push_standalone(qvm_t* q, const PushSpec& ps) {
+    const int grid = grid_for(q, (q->n_elems + kPushUnroll - 1) / kPushUnroll, 256, 8);
+    exchange_push_kernel<<<grid, 256, 0, q->stream>>>(q->amps, ps, q->n_elems);
+    QVM_CUDA(q, cudaGetLastError());
+    q->stats.kernel_launches += 1;
+    q->stats.hbm_bytes += 32ull * q->n_elems;
+    q->stats.push_launches += 1;
+    return QVM_OK;
+}
+
+static void push_done(qvm_t* q) {
+    std::swap(q->amps, q->alt);
+    q->sample_mode = -1;
+}
+
+int qvm_exchange_push(qvm_t* q, int m, const int32_t* local_bits, uint32_t mine_value, void* const* dst_ptrs) {
+    QVM_CHECK_HANDLE(q);
+    PushSpec ps;
+    int rc = make_push(q, m, local_bits, mine_value, dst_ptrs, &ps);
+    if (rc) return rc;
+    rc = push_standalone(q, ps);
+    if (rc) return rc;
+    push_done(q);
+    return QVM_OK;
+}
+
+int qvm_apply_group_push(qvm_t* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops,
+                         const double* mats, uint64_t mats_entries, int n_low, int n_bring, const int32_t* bring_low,
+                         int32_t* new_pos, int m, const int32_t* local_bits, uint32_t mine_value, void* const* dst_ptrs,
+                         int* fused) {
+    QVM_CHECK_HANDLE(q);
+    if (n_ops < 0 || (n_ops && !ops) || (n_tile && !tile_bits) || !new_pos || (n_bring && !bring_low))
+        return fail(QVM_ERR_INVALID, "null pointer");
+    if (mats_entries && !mats) return fail(QVM_ERR_INVALID, "null matrix pool");
+    if (n_tile < 0 || n_tile > 16 || n_bring < 0 || n_low < 0) return fail(QVM_ERR_INVALID, "bad relabelling request");
+    PushSpec ps;
+    int rc = make_push(q, m, local_bits, mine_value, dst_ptrs, &ps);
+    if (rc) return rc;
+    RelabelReq req;
+    req.n_low = n_low;
+    for (int i = 0; i < n_bring; ++i) {
+        int j = 0;
+        while (j < n_tile && tile_bits[j] != bring_low[i]) ++j;
+        if (j == n_tile) return fail(QVM_ERR_INVALID, "position %d is not in the tile", bring_low[i]);
+        req.low_in |= 1u << j;
+    }
+    bool pushed = false;
+    rc = launch_group(q, n_tile, tile_bits, n_ops, ops, mats, mats_entries, &req, &ps, &pushed);
+    if (rc != QVM_OK) return rc;
+    for (int j = 0; j < n_tile; ++j) new_pos[j] = tile_bits[req.sigma[j]];
+    if (pushed) q->stats.fused_push_launches += 1;
+    else if ((rc = push_standalone(q, ps)) != QVM_OK) return rc;
+    if (fused) *fused = pushed ? 1 : 0;
+    push_done(q);
     return QVM_OK;
 }
 

@@ -34,6 +34,7 @@ struct SpecParams {
     int n_runs;
     uint64_t shard_bits, run_start, run_len;
     uint64_t n_tiles;                // pipelined variant: tiles are walked by a persistent grid
+    PushSpec push;                   // fused exchange: where the last round stores (launch-time, m == 0: in place)
 };
 
 struct SpecSource {
@@ -231,7 +232,7 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
         }
         if (last) {
             body << "    {\n      const uint64_t gT = (uint64_t)(T & " << ((1u << P.low) - 1u) << "u) | hi_off[T >> " << P.low
-                 << "];\n      char* p0 = reinterpret_cast<char*>(gbase + gT);\n      int64_t b[4] = {";
+                 << "];\n      char* p0 = reinterpret_cast<char*>(gstore + gT);\n      int64_t b[4] = {";
             for (int s = 0; s < 4; ++s) body << (s ? ", " : "") << "(int64_t)(16ull << " << (int)rd.reg_phys[s] << ")";
             body << "};\n#pragma unroll\n      for (int s = 0; s < 4; ++s) if ((xm >> s) & 1u) { p0 += b[s]; b[s] = -b[s]; }\n"
                     "      char* q[16];\n      add_tree<4>(p0, b, q);\n"
@@ -257,7 +258,7 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
     if (F.empty()) F.push_back(0.0);
     if (F.size() > 3900) return false;          // kernel parameters are limited to 32 KB
     o << "#include \"qvm_regtile.cuh\"\nusing namespace qvm;\n"
-         "struct SpecParams { int n_runs; uint64_t shard_bits, run_start, run_len, n_tiles; };\n"
+         "struct SpecParams { int n_runs; uint64_t shard_bits, run_start, run_len, n_tiles; PushSpec push; };\n"
          "struct SpecFactors { double v[" << F.size() << "]; };\n"
          "__device__ const uint64_t hi_off[" << g.hi_off.size() << "] = {";
     for (size_t j = 0; j < g.hi_off.size(); ++j) o << (j ? ", " : "") << hexu(g.hi_off[j]);
@@ -272,10 +273,11 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
                                : spec_min_blocks(g.threads);
     if (!pipe) {
         o << "extern \"C\" __global__ void __launch_bounds__(" << g.threads << ", " << ctas
-          << ") spec_kernel(double2* __restrict__ state, const SpecParams SP, const SpecFactors F) {\n"
+          << ") spec_kernel(double2* __restrict__ state, const __grid_constant__ SpecParams SP, const SpecFactors F) {\n"
              "  extern __shared__ __align__(16) unsigned char smem_raw[];\n  double2* tile = reinterpret_cast<double2*>(smem_raw);\n"
              "  const uint32_t tid = threadIdx.x;\n  const uint64_t base = spec_tile_base(SP, blockIdx.x);\n"
-             "  const uint64_t full = base | SP.shard_bits;\n  double2* gbase = state + base;\n  double2 a[16];\n"
+             "  const uint64_t full = base | SP.shard_bits;\n  double2* gbase = state + base;\n"
+             "  double2* gstore = rt_push_base(SP.push, state, base);\n  double2 a[16];\n"
           << body.str() << "}\n";
     } else {
         // Persistent CTA, two tile buffers.  Thread `tid` fetches the tile-local indices tid + threads * j
@@ -292,7 +294,7 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
         }
         o << "  asm volatile(\"cp.async.commit_group;\" ::: \"memory\");\n}\n";
         o << "extern \"C\" __global__ void __launch_bounds__(" << g.threads << ", " << ctas
-          << ") spec_kernel(double2* __restrict__ state, const SpecParams SP, const SpecFactors F) {\n"
+          << ") spec_kernel(double2* __restrict__ state, const __grid_constant__ SpecParams SP, const SpecFactors F) {\n"
              "  extern __shared__ __align__(16) unsigned char smem_raw[];\n"
              "  double2* const buf0 = reinterpret_cast<double2*>(smem_raw);\n  double2* const buf1 = buf0 + " << (1u << P.k) << ";\n"
              "  const uint32_t tid = threadIdx.x;\n  uint64_t t = blockIdx.x;\n  if (t >= SP.n_tiles) return;\n"
@@ -302,7 +304,8 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
              "  asm volatile(\"cp.async.wait_all;\" ::: \"memory\");\n  __syncthreads();\n"
              "  if (t + gridDim.x < SP.n_tiles) spec_prefetch(cur ? buf0 : buf1, state + spec_tile_base(SP, t + gridDim.x), tid);\n"
              "  const uint64_t base = spec_tile_base(SP, t);\n"
-             "  const uint64_t full = base | SP.shard_bits;\n  double2* gbase = state + base;\n  double2 a[16];\n"
+             "  const uint64_t full = base | SP.shard_bits;\n  double2* gbase = state + base;\n"
+             "  double2* gstore = rt_push_base(SP.push, state, base);\n  double2 a[16];\n"
           << body.str() << "  }\n}\n";
     }
     out.src = o.str();
@@ -310,7 +313,7 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
     out.smem = pipe ? ((size_t)32 << P.k) : (P.n_rounds > 1 ? ((size_t)16 << P.k) : 0);
     out.n_tiles = g.n_tiles;
     out.ctas_per_sm = pipe ? ctas : 0;
-    out.params = SpecParams{P.n_runs, P.shard_bits, P.run_start, P.run_len, g.n_tiles};
+    out.params = SpecParams{P.n_runs, P.shard_bits, P.run_start, P.run_len, g.n_tiles, PushSpec{}};
     return true;
 }
 

@@ -705,4 +705,32 @@ __global__ void __launch_bounds__(256) exchange_block_kernel(double2* __restrict
     }
 }
 
+
+// Out-of-place global<->local qubit exchange: ONE pass that reads this shard and pushes every amplitude
+// to its new owner (PushSpec, qvm_regtile.cuh) -- write-only NVLink traffic, no read of the peer before
+// the write as in the in-place swap above, so each link direction carries plain posted stores.  Every
+// rank runs it at the same time into the peers' ALTERNATE buffers; one barrier afterwards, then the
+// buffers swap roles.  Runs of 2^pos[0] consecutive elements share a destination, so warps store
+// contiguous 512-byte segments.  The fused form of the same exchange is the last round of
+// regtile_kernel / spec_kernel storing through rt_push_base().
+constexpr int kPushUnroll = 8;
+__device__ __forceinline__ double2* push_target(const PushSpec& ps, uint64_t e) {
+    uint32_t L = 0;
+    for (int i = 0; i < ps.m; ++i) L |= (uint32_t)((e >> ps.pos[i]) & 1ull) << i;
+    return ps.dst[L] + ((e & ~ps.mask) | ps.mine_bits);
+}
+__global__ void __launch_bounds__(256) exchange_push_kernel(const double2* __restrict__ src,
+                                                            const __grid_constant__ PushSpec ps, uint64_t n_elems) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    for (; j + (kPushUnroll - 1) * stride < n_elems; j += kPushUnroll * stride) {
+        double2 x[kPushUnroll];
+#pragma unroll
+        for (int u = 0; u < kPushUnroll; ++u) x[u] = __ldcs(&src[j + u * stride]);
+#pragma unroll
+        for (int u = 0; u < kPushUnroll; ++u) __stcs(push_target(ps, j + u * stride), x[u]);
+    }
+    for (; j < n_elems; j += stride) *push_target(ps, j) = src[j];
+}
+
 }  // namespace qvm

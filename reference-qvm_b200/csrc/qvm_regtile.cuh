@@ -149,6 +149,23 @@ struct __align__(16) RoundDesc {
 };
 static_assert(sizeof(RoundDesc) == 64, "RoundDesc layout");
 
+// Fused global<->local qubit exchange (multi-GPU): the pass reads its tiles from this shard and STORES
+// them straight into their owners' shards over NVLink peer memory.  Swapping the m global bits of the
+// rank with the m local "victim" bits pos[] sends the amplitude (rank R, local index x) to the rank whose
+// global bits equal x's victim bits, at local index x with the victim bits replaced by R's global bits:
+// dst[L] is the (alternate) buffer of the rank with global bits L (dst[own bits] = this rank's own
+// alternate buffer), mine_bits = R's global bits deposited at pos[].  The victim positions are outer
+// bits of every tile, so a whole tile goes to one destination: one pointer select per CTA.  m == 0:
+// the pass stores in place.
+constexpr int kMaxPushBits = 3;
+struct PushSpec {
+    int m;
+    uint8_t pos[4];
+    uint64_t mask;
+    uint64_t mine_bits;
+    double2* dst[1 << kMaxPushBits];
+};
+
 struct RegTileParams {
     int n_local;
     int k;
@@ -166,6 +183,7 @@ struct RegTileParams {
     // coordinates, so the qubit of tile bit b leaves the pass on tile bit sigma(b).
     int perm_round;
     uint16_t perm_swz[16];    // swz(1 << sigma(b)) for every tile bit b
+    PushSpec push;            // where the last round stores (fused exchange); m == 0: in place
     uint64_t shard_bits;
     uint64_t run_start;       // 8 x 8 bits: start position of each run
     uint64_t run_len;         // 8 x 8 bits: length of each run
@@ -264,6 +282,7 @@ struct RtCta {
     const RoundDesc* rounds;  // shared
     const uint64_t* hi_off;   // shared
     double2* gbase;           // state + outer-bit offset of this tile
+    double2* gstore;          // where the last round stores this tile (== gbase unless the pass pushes, PushSpec)
     const double2* mats;      // global pool
     const ColdOp* cold;       // global
     int low;
@@ -695,7 +714,7 @@ QVM_HD void rt_thread_round(const RtCta& c, const int r, const uint32_t tid, dou
         // register p holds logical slot p ^ xm: start from the address of logical slot xm and walk with
         // signed strides (a set xm bit turns +stride into -stride); sums again, no per-element masking
         const uint64_t gT = (uint64_t)(T & low_mask) | c.hi_off[T >> c.low];
-        char* p0 = reinterpret_cast<char*>(c.gbase + gT);
+        char* p0 = reinterpret_cast<char*>(c.gstore + gT);
         int64_t b[R];
 #pragma unroll
         for (int s = 0; s < R; ++s) {
@@ -747,6 +766,14 @@ QVM_HD uint64_t rt_tile_base(const RegTileParams& P, uint64_t tile_index) {
     return base;
 }
 
+// store base of the tile whose outer bits are `base` (see PushSpec)
+QVM_HD double2* rt_push_base(const PushSpec& ps, double2* state, uint64_t base) {
+    if (ps.m == 0) return state + base;
+    uint32_t L = 0;
+    for (int i = 0; i < ps.m; ++i) L |= (uint32_t)((base >> ps.pos[i]) & 1ull) << i;
+    return ps.dst[L] + ((base & ~ps.mask) | ps.mine_bits);
+}
+
 #if defined(__CUDACC__)
 template <int MAX_THREADS, int MIN_BLOCKS, bool FULL, int R>
 __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
@@ -786,6 +813,7 @@ regtile_kernel(double2* __restrict__ state, const __grid_constant__ RegTileParam
     c.rounds = rounds;
     c.hi_off = hi_off;
     c.gbase = state + base;
+    c.gstore = rt_push_base(P.push, state, base);
     c.mats = P.mats;
     c.cold = P.cold;
     c.low = P.low;

@@ -191,6 +191,19 @@ class Engine(object):
             return self.state.get_strided(offset, stride, count)
         return self.state.get_layout(offset, stride, count, self.pos_of)
 
+    def probe(self, logical_indices):
+        """Amplitudes at a handful of LOGICAL basis-state indices, read through the layout (no amplitude
+        moves): same meaning as ``ShardedEngine.probe``."""
+        self.flush()
+        idx = np.asarray(logical_indices, dtype=np.int64).reshape(-1)
+        out = np.zeros(idx.size, dtype=np.complex128)
+        for j, logical in enumerate(idx):
+            phys = 0
+            for q in range(self.n):
+                phys |= ((int(logical) >> q) & 1) << self.pos_of[q]
+            out[j] = self.state.get_state(phys, 1)[0]
+        return out
+
     def restore_layout(self):
         """Put every qubit back on its own position (SWAP passes) -- for the few consumers that address
         the raw buffer: clones, the density-matrix trace / diagonal kernels."""

@@ -36,7 +36,7 @@ class Stats(C.Structure):
     """``qvm_stats_t``"""
     _fields_ = [(name, C.c_uint64) for name in
                 ("kernel_launches", "gate_ops", "hbm_passes", "hbm_bytes", "h2d_bytes", "d2h_bytes", "regtile_rounds",
-                 "jit_launches", "jit_compiles")]
+                 "jit_launches", "jit_compiles", "push_launches", "fused_push_launches")]
 
     def as_dict(self):
         return {name: int(getattr(self, name)) for name, _ in self._fields_}
@@ -93,6 +93,13 @@ _SIGNATURES = {
     "qvm_ipc_open": (C.c_int, [_P, _P, C.POINTER(_P)]),
     "qvm_ipc_close": (C.c_int, [_P, _P]),
     "qvm_exchange_half": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_uint64, C.c_uint64]),
+    "qvm_alt_alloc": (C.c_int, [_P]),
+    "qvm_alt_free": (C.c_int, [_P]),
+    "qvm_alt_ptr": (_P, [_P]),
+    "qvm_ipc_export_alt": (C.c_int, [_P, _P]),
+    "qvm_exchange_push": (C.c_int, [_P, C.c_int, _P, C.c_uint32, _P]),
+    "qvm_apply_group_push": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, C.c_uint64, C.c_int, C.c_int, _P, _P, C.c_int, _P,
+                                       C.c_uint32, _P, C.POINTER(C.c_int)]),
     "qvm_exchange_block": (C.c_int, [_P, C.c_int, _P, C.c_uint32, C.c_uint32, _P, C.c_uint64, C.c_uint64]),
 }
 EXPORTED = tuple(sorted(_SIGNATURES))
@@ -252,6 +259,7 @@ class DeviceState(object):
         check(code)
         self.n_global = 0
         self.shard_index = 0
+        self.last_push_fused = False
 
     # -- lifetime --------------------------------------------------------------------------
     def close(self):
@@ -370,29 +378,33 @@ class DeviceState(object):
             raise NotImplementedError(last_error())
         check(code)
 
-    def apply_group(self, tile_bits, ops, bring_low=None, n_low=0):
+    def apply_group(self, tile_bits, ops, bring_low=None, n_low=0, push=None):
         """A run of ClassifiedOps in one HBM pass (``qvm_apply_group``).
 
         With ``bring_low`` (positions of the tile) the pass also relabels qubits inside the tile
-        (``qvm_apply_group_relabel``) and the new position of every tile position is returned."""
+        (``qvm_apply_group_relabel``) and the new position of every tile position is returned.
+        With ``push`` = (victim positions ascending, own global-bit value, destination pointers) the
+        pass's stores are the global<->local exchange (``qvm_apply_group_push``); ``self.last_push_fused``
+        says whether the library could fuse it."""
         ops = [o for o in ops if o.kind != OP_NOP]
-        if not ops and not bring_low:
+        if not ops and not bring_low and push is None:
             return None if bring_low is None else sorted(tile_bits)
-        arr = (Op * len(ops))()
-        total = sum(o.mat.size for o in ops)
-        pool = np.empty(max(total, 1), dtype=np.complex128)
-        off = 0
-        for i, o in enumerate(ops):
-            a = arr[i]
-            a.kind, a.k, a.ctrl_mask = o.kind, len(o.targets), o.ctrl_mask
-            for j in range(MAX_TARGETS):
-                a.targets[j] = o.targets[j] if j < len(o.targets) else -1
-            a.mat_offset, a.mat_entries = off, o.mat.size
-            pool[off:off + o.mat.size] = o.mat
-            off += o.mat.size
+        arr, pool, total = marshal_ops(ops)
         tb = np.ascontiguousarray(sorted(tile_bits), dtype=np.int32)
         new_pos = None
-        if bring_low is None:
+        if push is not None:
+            bl = np.ascontiguousarray(bring_low if bring_low is not None else [], dtype=np.int32)
+            new_pos = np.empty(tb.size, dtype=np.int32)
+            bits, mine, dst = push
+            vb = np.ascontiguousarray(bits, dtype=np.int32)
+            ptrs = (_P * len(dst))(*[_P(int(d)) if d else _P() for d in dst])
+            fused = C.c_int(0)
+            code = lib().qvm_apply_group_push(self.handle, tb.size, tb.ctypes.data, len(ops),
+                                              C.cast(arr, _P) if ops else None, pool.ctypes.data, total, n_low, bl.size,
+                                              bl.ctypes.data, new_pos.ctypes.data, vb.size, vb.ctypes.data, int(mine),
+                                              C.cast(ptrs, _P), C.byref(fused))
+            self.last_push_fused = bool(fused.value)
+        elif bring_low is None:
             code = lib().qvm_apply_group(self.handle, tb.size, tb.ctypes.data, len(ops), C.cast(arr, _P),
                                          pool.ctypes.data, total)
         else:
@@ -504,6 +516,31 @@ class DeviceState(object):
         bits = np.ascontiguousarray(local_bits, dtype=np.int32)
         check(lib().qvm_exchange_block(self.handle, bits.size, bits.ctypes.data, mine_value, peer_value,
                                        _P(peer_ptr), elem_offset, count))
+
+    def alt_alloc(self):
+        """Second buffer for the out-of-place exchange; False when it does not fit in HBM."""
+        code = lib().qvm_alt_alloc(self.handle)
+        if code in (QVM_ERR_NOMEM, QVM_ERR_UNSUPPORTED):
+            return False
+        check(code)
+        return True
+
+    def alt_free(self):
+        check(lib().qvm_alt_free(self.handle))
+
+    def alt_ptr(self):
+        return int(lib().qvm_alt_ptr(self.handle) or 0)
+
+    def ipc_export_alt(self):
+        buf = C.create_string_buffer(64)
+        check(lib().qvm_ipc_export_alt(self.handle, buf))
+        return buf.raw
+
+    def exchange_push(self, local_bits, mine_value, dst_ptrs):
+        """Out-of-place exchange pass (``qvm_exchange_push``); current and alternate buffer swap roles."""
+        bits = np.ascontiguousarray(local_bits, dtype=np.int32)
+        ptrs = (_P * len(dst_ptrs))(*[_P(int(d)) if d else _P() for d in dst_ptrs])
+        check(lib().qvm_exchange_push(self.handle, bits.size, bits.ctypes.data, int(mine_value), C.cast(ptrs, _P)))
 
     def unpack_half(self, local_bit, bit_value, elem_offset, count, device_src_ptr):
         check(lib().qvm_unpack_half(self.handle, local_bit, bit_value, elem_offset, count, _P(device_src_ptr)))

@@ -181,7 +181,7 @@ def _choose_group(ops, deps, done, first, k, max_new, is_old, seed_tile, max_gro
 
 
 def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_group_ops=MAX_GROUP_OPS,
-                   defer_tail_below=0, leftover=None):
+                   defer_tail_below=0, leftover=None, on_last=None):
     """Run ``ops`` (ClassifiedOps on LOGICAL qubits; every dense target currently on a local position)
     as fused groups with in-tile relabelling.  ``pos_of`` (logical -> physical, mutated in place) is the
     layout; ``launch(tile_positions, physical_ops, bring_low_positions)`` runs one pass and returns the
@@ -190,7 +190,11 @@ def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_g
     ``defer_tail_below``: when the LAST group would hold fewer ops than this, it is not launched and the
     indices (into ``ops``) of its members are appended to the list ``leftover`` instead -- the sharded
     engine merges such a tail with the ops that become runnable after the next exchange rather than
-    paying a whole pass for it."""
+    paying a whole pass for it.
+
+    ``on_last(leftover_indices, tile_positions)``: called right before the LAST launch of the call (the
+    thin tail, if any, already set aside); what it returns is handed to that launch as a fourth argument
+    -- the sharded engine's fused exchange: the last pass stores straight into the peers' shards."""
     origin = [i for i, o in enumerate(ops) if o.kind != OP_NOP]
     ops = [ops[i] for i in origin]
     n = len(ops)
@@ -214,6 +218,7 @@ def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_g
     qubit_at = {p: q for q, p in enumerate(pos_of)}
     first = 0
     passes = 0
+    n_done = 0
 
     def low_qubits():
         return [qubit_at[p] for p in range(low)]
@@ -252,9 +257,25 @@ def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_g
         nxt_tile, nxt_ops = (set(), [])
         bring = []
         contiguous = all(tile_positions[j] == j for j in range(low))
+        n_done += len(cur_ops)
         if first < n and contiguous:
             nxt_tile, nxt_ops = _choose_group(ops, deps, done, first, k, k - low, lambda q: q in tile_qubits, (),
                                               max_group_ops)
+            if (on_last is not None and leftover is not None and len(nxt_ops) == n - n_done
+                    and len(nxt_ops) < defer_tail_below):
+                # everything that is left is a thin tail: it will be deferred, so THIS launch is the last one
+                tail = [origin[i] for i in nxt_ops]
+                push = on_last(tail, tile_positions)
+                phys_ops = [ops[i].remapped(pos_of) for i in cur_ops]
+                new_pos = launch(tile_positions, phys_ops, None, push) if push is not None else \
+                    launch(tile_positions, phys_ops, None)
+                passes += 1
+                if new_pos is not None:
+                    for q, np_ in [(qubit_at[p], np_) for p, np_ in zip(tile_positions, new_pos) if p != np_]:
+                        pos_of[q] = np_
+                        qubit_at[np_] = q
+                leftover.extend(tail)
+                return passes
             shared = [q for q in nxt_tile if q in tile_qubits]
             if len(shared) > low:
                 # keep the qubits with the most dense work ahead on the low positions: they are in every tile
@@ -267,7 +288,11 @@ def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_g
                 shared = shared[:low]
             bring = [pos_of[q] for q in shared]
         phys_ops = [ops[i].remapped(pos_of) for i in cur_ops]
-        new_pos = launch(tile_positions, phys_ops, bring if bring else None)
+        push = on_last([], tile_positions) if (on_last is not None and first >= n) else None
+        if push is not None:
+            new_pos = launch(tile_positions, phys_ops, bring if bring else None, push)
+        else:
+            new_pos = launch(tile_positions, phys_ops, bring if bring else None)
         passes += 1
         if new_pos is not None:
             moved = [(qubit_at[p], np_) for p, np_ in zip(tile_positions, new_pos) if p != np_]

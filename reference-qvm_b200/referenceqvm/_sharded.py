@@ -1,4 +1,4 @@
-"""Sharded engine: one process per GPU, amplitudes split by the top log2(G) qubits.
+"""Sharded engine: one rank per GPU, amplitudes split by the top log2(G) qubits.
 
 The reference has no distributed path.  Here each rank holds 2^(n-g) contiguous
 amplitudes (g = log2 world size); physical positions >= n-g are *global*: their value is a bit of
@@ -6,18 +6,31 @@ the rank.  A host-side logical->physical qubit layout tracks remaps.
 
 * Diagonal gates and controls on global positions need no communication: the kernels read the bit
   from the shard index (``qvm_set_shard``).
-* A dense target on a global position triggers a global<->local swap: ranks that differ in that
-  global bit exchange the half of their shard whose local bit differs from their own global bit
-  (``B_swap = 8 * 2^(n-g)`` bytes each way per GPU), chunked through two staging buffers with
-  torch.distributed send/recv (NCCL over NVLink on GPUs; gloo in the CPU tests).  The victim local
-  qubit is the one whose next dense use is farthest away.
+* A dense target on a global position blocks that op (and what depends on it); everything else keeps
+  running in fused passes.  When nothing more can run, ONE exchange epoch swaps all wanted global qubits
+  with local victims (Belady: farthest next dense use).  Three implementations, best first:
+
+  - ``push`` (default): out of place.  Every rank reads its shard once and stores each amplitude where
+    it will live -- its own alternate buffer or a peer's, over NVLink peer memory (CUDA IPC) -- with
+    write-only traffic.  Whenever a fused gate pass precedes the epoch, that pass's own last round does
+    the storing (``qvm_apply_group_push``): the exchange then costs no pass of its own.  One
+    stream-ordered barrier per epoch.  Needs a second buffer of the shard's size.
+  - ``p2p``: in place, one swap kernel per peer over peer memory (``qvm_exchange_block``); used when the
+    alternate buffer does not fit (36 qubits on 8 GPUs: 128 GiB shards).
+  - ``staged``: pack / send / recv / unpack through two staging buffers with torch.distributed
+    (gloo in the CPU tests; ``QVM_B200_SWAP=nccl`` for A/B runs).
+
 * MEASURE = local partial p0 -> all-reduce -> local collapse.  Sampling = local two-level CDF,
   all-gather of the shard totals, each rank resolves the shots that fall in its range.
 
 All ranks run the same program (SPMD) and make identical planning decisions; random draws are
-broadcast from rank 0.
+broadcast from rank 0.  Collectives go through a small ``comm`` object: ``TorchComm``
+(torch.distributed: NCCL on GPUs, gloo on CPU) in production; the single-GPU test suite plugs in an
+in-process communicator that runs the ranks as threads on one device (tests/_thread_comm.py).
 """
 import os
+import threading
+import warnings
 
 import numpy as np
 
@@ -25,39 +38,114 @@ from referenceqvm import _native as nat
 from referenceqvm import _planner
 from referenceqvm._engine import _LOW_BITS, _RELABEL, _TILE_BITS, DiagonalMerger, compile_gate, expand_op, validate_qubits
 
-_context = None      # set by enable(); consulted by _engine.make_engine()
+_tls = threading.local()       # per-thread context (in-process ranks of the test suite)
+_default = None                # context of the process (set from the main thread)
+
+MAX_PUSH_BITS = 3              # kMaxPushBits of the library: the push exchange serves up to 8 ranks
+
+
+class TorchComm(object):
+    """Collectives of the sharded engine on torch.distributed.  Tensors are made by the shard backend
+    (CUDA tensors on the shard's stream for NCCL, CPU tensors for gloo)."""
+
+    same_process = False
+
+    def __init__(self, group=None):
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self._make = None
+        self._token = None
+
+    def bind(self, make_tensor):
+        """``make_tensor(values, dtype=None)`` -> tensor on the device the backend computes on."""
+        self._make = make_tensor
+        self._token = make_tensor([0.0])
+
+    def _global_rank(self, group_rank):
+        return group_rank if self.group is None else self.dist.get_global_rank(self.group, group_rank)
+
+    def allreduce(self, values, op="sum"):
+        t = self._make(np.ascontiguousarray(values, dtype=np.float64))
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN if op == "min" else self.dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
+    def allreduce_int64(self, values):
+        t = self._make(np.ascontiguousarray(values, dtype=np.int64), dtype=self.torch.int64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
+    def allgather(self, values):
+        """The same 1-D float64 array from every rank, concatenated in rank order."""
+        mine = self._make(np.ascontiguousarray(values, dtype=np.float64))
+        out = self._make(np.zeros(mine.numel() * self.world))
+        self.dist.all_gather(list(out.split(mine.numel())), mine, group=self.group)
+        return out.cpu().numpy()
+
+    def allgather_bytes(self, raw):
+        mine = self._make(np.frombuffer(bytes(raw), dtype=np.uint8).copy(), dtype=self.torch.uint8)
+        parts = [self.torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(parts, mine, group=self.group)
+        return [bytes(p.cpu().numpy().tobytes()) for p in parts]
+
+    def broadcast(self, values, src=0):
+        t = self._make(np.ascontiguousarray(values, dtype=np.float64))
+        self.dist.broadcast(t, src=self._global_rank(src), group=self.group)
+        return t.cpu().numpy()
+
+    def stream_barrier(self, shard=None):
+        """Cross-rank barrier ordered on the shard's stream (a one-element all-reduce): kernels queued
+        after it start only when every rank's kernels queued before it have finished.  The host does
+        not wait."""
+        self.dist.all_reduce(self._token, group=self.group)
+
+    def sendrecv(self, send, recv, partner, reverse):
+        dist = self.dist
+        ops = [dist.P2POp(dist.isend, send, self._global_rank(partner), self.group),
+               dist.P2POp(dist.irecv, recv, self._global_rank(partner), self.group)]
+        if reverse:                 # fixed order on both sides of a pair keeps gloo from deadlocking
+            ops.reverse()
+        return dist.batch_isend_irecv(ops)
 
 
 class ShardContext(object):
-    def __init__(self, group, rank, world, device):
-        self.group, self.rank, self.world, self.device = group, rank, world, device
-        self.n_global = int(world).bit_length() - 1
-        if (1 << self.n_global) != world:
-            raise ValueError("world size %d is not a power of two" % world)
+    def __init__(self, comm, device):
+        self.comm, self.device = comm, device
+        self.rank, self.world = comm.rank, comm.world
+        self.group = getattr(comm, "group", None)
+        self.n_global = int(self.world).bit_length() - 1
+        if (1 << self.n_global) != self.world:
+            raise ValueError("world size %d is not a power of two" % self.world)
 
 
-def enable(device=None, group=None):
-    """Shard every engine created from now on across the ranks of ``group`` (default: WORLD)."""
-    global _context
-    import torch.distributed as dist
-    if not dist.is_initialized():
-        raise RuntimeError("torch.distributed is not initialised")
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    _context = ShardContext(group, rank, world, 0 if device is None else device)
-    return _context
+def enable(device=None, group=None, comm=None):
+    """Shard every engine created from now on (by this thread; from the main thread: by the process)
+    across the ranks of ``comm`` (default: a TorchComm on ``group`` / WORLD)."""
+    global _default
+    ctx = ShardContext(comm if comm is not None else TorchComm(group), 0 if device is None else device)
+    _tls.ctx = ctx
+    if threading.current_thread() is threading.main_thread():
+        _default = ctx
+    return ctx
 
 
 def disable():
-    global _context
-    _context = None
+    global _default
+    _tls.ctx = None
+    if threading.current_thread() is threading.main_thread():
+        _default = None
 
 
 def context():
-    return _context
+    ctx = getattr(_tls, "ctx", None)
+    return ctx if ctx is not None else _default
 
 
 class CudaShard(object):
-    """Local backend of the product path: one DeviceState + torch CUDA staging tensors."""
+    """Local backend of the product path: one DeviceState + torch CUDA tensors for the collectives."""
 
     def __init__(self, n_local, ctx):
         import torch
@@ -68,21 +156,18 @@ class CudaShard(object):
         self.state = nat.DeviceState(n_local, ctx.device)
         self.state.set_shard(ctx.n_global, ctx.rank)
         # One dedicated stream carries the library's kernels AND is torch's current stream, so NCCL
-        # operations (which order themselves against the current stream) see packs / unpacks in order.
+        # operations (which order themselves against the current stream) see the kernels in order.
         # (The legacy default stream has handle 0, which qvm_set_stream reads as "own stream".)
         self.stream = torch.cuda.Stream(device=ctx.device)
         torch.cuda.set_stream(self.stream)
         self.state.set_stream(self.stream.cuda_stream)
         self.device = torch.device("cuda", ctx.device)
+        self.peers = None           # rank -> (pointer of its buffer 0, of its buffer 1 or 0)
+        self.peer_error = None
+        self._ipc = False
 
     def close(self):
-        if getattr(self, "peers", None):
-            for ptr in self.peers.values():
-                try:
-                    self.state.ipc_close(ptr)
-                except Exception:
-                    pass
-            self.peers = None
+        self.close_peers()
         self.state.close()
 
     def alloc(self, n_amps):
@@ -98,32 +183,78 @@ class CudaShard(object):
             n += 1
         return n
 
-    def apply_group(self, tile_positions, ops, bring_low, n_low):
+    def apply_group(self, tile_positions, ops, bring_low, n_low, push=None):
         """One pass with in-tile relabelling; returns the new position of every tile position."""
-        return self.state.apply_group(tile_positions, ops, bring_low=bring_low, n_low=n_low)
+        return self.state.apply_group(tile_positions, ops, bring_low=bring_low, n_low=n_low, push=push)
 
-    def open_peers(self, dist, group):
-        """Map every peer's shard into this process (CUDA IPC) so that a global<->local swap is one
-        kernel over NVLink peer memory.  Returns False when IPC is unavailable (NCCL path is kept)."""
-        torch = self.torch
+    def alloc_alt(self):
+        """Second buffer of the shard's size (push exchange); False when it does not fit."""
         try:
-            mine = torch.tensor(list(self.state.ipc_export()), dtype=torch.uint8, device=self.device)
-            handles = [torch.empty_like(mine) for _ in range(self.ctx.world)]
-            dist.all_gather(handles, mine, group=group)
-            self.peers = {}
-            for r, h in enumerate(handles):
-                if r != self.ctx.rank:
-                    self.peers[r] = self.state.ipc_open(bytes(h.cpu().numpy().tobytes()))
-            return True
-        except Exception:
-            self.peers = None
+            return bool(self.state.alt_alloc())
+        except Exception as exc:
+            self.peer_error = "%s: %s" % (type(exc).__name__, exc)
             return False
 
+    def open_peers(self, comm, with_alt):
+        """Make every peer's shard addressable from this rank: CUDA IPC handles between processes (the
+        loads / stores then travel over NVLink), plain device pointers between in-process ranks.  With
+        ``with_alt`` the alternate buffers too (push exchange).  Returns False -- and keeps the reason in
+        ``peer_error`` -- when that is not possible; the caller falls back to the staged exchange.
+        Every rank takes part in every collective of this method whatever fails locally."""
+        me = self.ctx.rank
+        self.close_peers()
+        if comm.same_process:
+            ptrs = comm.allgather_object((self.state.device_ptr(), self.state.alt_ptr() if with_alt else 0))
+            self.peers = {r: ptrs[r] for r in range(comm.world) if r != me}
+            self._ipc = False
+            return True
+        blank = b"\0" * 64
+        try:
+            cur = self.state.ipc_export()
+            alt = self.state.ipc_export_alt() if with_alt else blank
+        except Exception as exc:            # reported by the engine (as a warning), never swallowed
+            self.peer_error = "%s: %s" % (type(exc).__name__, exc)
+            cur = alt = blank
+        all_cur = comm.allgather_bytes(cur)
+        all_alt = comm.allgather_bytes(alt) if with_alt else None
+        if self.peer_error is not None or blank in all_cur or (with_alt and blank in all_alt):
+            self.peer_error = self.peer_error or "a peer could not export its shard"
+            return False
+        self.peers = {}
+        self._ipc = True
+        try:
+            for r in range(comm.world):
+                if r != me:
+                    self.peers[r] = (self.state.ipc_open(all_cur[r]), 0)
+                    if with_alt:
+                        self.peers[r] = (self.peers[r][0], self.state.ipc_open(all_alt[r]))
+        except Exception as exc:
+            self.peer_error = "%s: %s" % (type(exc).__name__, exc)
+            return False
+        return True
+
+    def close_peers(self):
+        if self.peers and self._ipc:
+            for ptrs in self.peers.values():
+                for ptr in ptrs:
+                    if ptr:
+                        try:
+                            self.state.ipc_close(ptr)
+                        except Exception:
+                            pass
+        self.peers = None
+
+    def drop_alt(self):
+        self.state.alt_free()
+
     def exchange_half(self, bit, mine_value, partner, off, cnt):
-        self.state.exchange_half(bit, mine_value, self.peers[partner], off, cnt)
+        self.state.exchange_half(bit, mine_value, self.peers[partner][0], off, cnt)
 
     def exchange_block(self, local_bits, mine_value, peer_value, partner, off, cnt):
-        self.state.exchange_block(local_bits, mine_value, peer_value, self.peers[partner], off, cnt)
+        self.state.exchange_block(local_bits, mine_value, peer_value, self.peers[partner][0], off, cnt)
+
+    def exchange_push(self, local_bits, mine_value, dst_ptrs):
+        self.state.exchange_push(local_bits, mine_value, dst_ptrs)
 
     def pack_half(self, bit, value, off, cnt, buf):
         self.state.pack_half(bit, value, off, cnt, buf.data_ptr())
@@ -176,12 +307,11 @@ class ShardedEngine(object):
     CHUNK_AMPS = 1 << 26          # 1 GiB per staging buffer
 
     def __init__(self, n_positions, ctx=None, tile_bits=None, low_bits=None, backend_factory=None,
-                 chunk_amps=None):
-        import torch.distributed as dist
-        self.dist = dist
-        self.ctx = ctx or _context
+                 chunk_amps=None, exchange=None):
+        self.ctx = ctx or context()
         if self.ctx is None:
             raise RuntimeError("sharding is not enabled")
+        self.comm = self.ctx.comm
         self.n = int(n_positions)
         self.g = self.ctx.n_global
         self.n_local = self.n - self.g
@@ -190,17 +320,38 @@ class ShardedEngine(object):
         self.tile_bits = _TILE_BITS if tile_bits is None else tile_bits
         self.low_bits = _LOW_BITS if low_bits is None else low_bits
         self.shard = (backend_factory or CudaShard)(self.n_local, self.ctx)
+        if hasattr(self.comm, "bind"):
+            self.comm.bind(self.shard.scalar_tensor)
         self.chunk_amps = min(chunk_amps or self.CHUNK_AMPS, 1 << (self.n_local - 1))
         self._send = self._recv = None
-        # peer-memory swaps (one kernel over NVLink) when the backend can map its peers; the staged
-        # NCCL send/recv exchange otherwise (and under QVM_B200_SWAP=nccl, for A/B runs)
-        self.p2p = False
-        if os.environ.get("QVM_B200_SWAP", "p2p") == "p2p" and hasattr(self.shard, "open_peers"):
-            self.p2p = bool(self.shard.open_peers(self.dist, self.ctx.group))
-            flag = self.shard.scalar_tensor([1.0 if self.p2p else 0.0])
-            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.ctx.group)
-            self.p2p = bool(float(flag.cpu()[0]) > 0.5)
-            self._token = self.shard.scalar_tensor([0.0])
+        # how global<->local exchanges run (module docstring): "push" > "p2p" > "staged", each needing
+        # what the next one does not; every rank must agree, so the choice is all-reduced
+        want = exchange or os.environ.get("QVM_B200_SWAP", "push")
+        want = {"nccl": "staged"}.get(want, want)
+        self.exchange = "staged"
+        self.exchange_note = None
+        if want in ("push", "p2p") and hasattr(self.shard, "open_peers"):
+            with_alt = want == "push" and self.g <= MAX_PUSH_BITS
+            if with_alt:
+                have = self.shard.alloc_alt()
+                if not self._all_agree(have):
+                    # the second buffer does not fit somewhere (36 qubits on 8 GPUs): in-place peer-memory swaps
+                    self.exchange_note = "no room for the push exchange's second buffer (%d bytes per rank): " \
+                                         "in-place peer-memory exchange" % (16 << self.n_local)
+                    if have:
+                        self.shard.drop_alt()
+                    self.shard.peer_error = None
+                    with_alt = False
+            ok = bool(self.shard.open_peers(self.comm, with_alt))
+            if self._all_agree(ok):
+                self.exchange = "push" if with_alt else "p2p"
+            else:
+                self.exchange_note = "peer memory unavailable (%s): staged send/recv exchange" % (
+                    self.shard.peer_error or "a peer could not map it")
+            if self.exchange_note:
+                warnings.warn("referenceqvm sharded engine, rank %d: %s" % (self.ctx.rank, self.exchange_note))
+        self.p2p = self.exchange != "staged"       # (kept: bench / older callers read it)
+        self._buf = 0                              # which of the two buffers is current (push mode; same on all ranks)
         self.pos_of = list(range(self.n))         # logical qubit -> physical position
         #: in-tile relabelling of local qubits (``_planner.run_relabelled``) when the backend offers it
         self.relabel = _RELABEL and hasattr(self.shard, "apply_group")
@@ -209,10 +360,15 @@ class ShardedEngine(object):
         self.gates_queued = 0
         self.groups_launched = 0
         self.swaps = 0
+        self.fused_swaps = 0
         self.swap_bytes = 0
-        #: when a dict {"batch": [], "swap": []}: (start, end) device events around every kernel batch
-        #: and every exchange are appended (bench.py reads them after a sync)
+        #: when a dict {"batch": [], "swap": [], "fused": []}: (start, end) device events around every
+        #: kernel batch, every stand-alone exchange and every fused pass+exchange are appended (bench.py
+        #: reads them after a sync)
         self.timing = None
+
+    def _all_agree(self, flag):
+        return bool(self.comm.allreduce([1.0 if flag else 0.0], op="min")[0] > 0.5)
 
     # -- lifetime / state ------------------------------------------------------------------------
     @property
@@ -262,7 +418,7 @@ class ShardedEngine(object):
         a, b = max(offset, lo), min(offset + count, lo + (1 << self.n_local))
         if b > a:
             out[a - offset:b - offset] = self.shard.get_state(a - lo, b - a)
-        return self._allreduce_array(out.view(np.float64)).view(np.complex128)
+        return self.comm.allreduce(out.view(np.float64)).view(np.complex128)
 
     def strided(self, offset, stride, count):
         self.flush()
@@ -273,12 +429,22 @@ class ShardedEngine(object):
         if mine.size:
             first = int(idx[mine[0]]) - (self.ctx.rank << self.n_local)
             out[mine] = self.shard.state.get_strided(first, stride, mine.size)
-        return self._allreduce_array(out.view(np.float64)).view(np.complex128)
+        return self.comm.allreduce(out.view(np.float64)).view(np.complex128)
 
-    def _allreduce_array(self, values):
-        t = self.shard.scalar_tensor(values)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.ctx.group)
-        return t.cpu().numpy()
+    def probe(self, logical_indices):
+        """Amplitudes at a handful of LOGICAL basis-state indices, identical on every rank, read through
+        the layout without moving an amplitude (``amplitudes()`` would restore the layout first): the
+        cross-check between runs on different numbers of GPUs (bench.py ``check.probe``)."""
+        self.flush()
+        idx = np.asarray(logical_indices, dtype=np.int64).reshape(-1)
+        out = np.zeros(idx.size, dtype=np.complex128)
+        for j, logical in enumerate(idx):
+            phys = 0
+            for q in range(self.n):
+                phys |= ((int(logical) >> q) & 1) << self.pos_of[q]
+            if (phys >> self.n_local) == self.ctx.rank:
+                out[j] = self.shard.get_state(phys & ((1 << self.n_local) - 1), 1)[0]
+        return self.comm.allreduce(out.view(np.float64)).view(np.complex128)
 
     def norm2(self):
         self.flush()
@@ -301,7 +467,8 @@ class ShardedEngine(object):
         """Run every queued gate.  Ops whose dense targets are all local run in fused batches; an op
         with a dense target on a global position blocks (with everything that depends on it) until an
         exchange epoch brings all currently wanted global qubits in -- one multi-bit swap per epoch
-        instead of one swap (and one broken batch) per gate."""
+        instead of one swap (and one broken batch) per gate.  In push mode the batch's last pass does
+        the epoch's exchange itself."""
         self._merger.reset()
         if not self.pending:
             return
@@ -325,10 +492,28 @@ class ShardedEngine(object):
                         continue
                 batch.append(i)
                 in_batch.add(i)
+            exchange_follows = bool(wanted) and len(batch) < remaining
+            fused = {}
+
+            def plan_push(leftover, tile_positions, batch=batch, wanted=wanted, fused=fused):
+                """Called by the planner right before the batch's LAST launch: choose the epoch's victims
+                (knowing which ops will have run) and hand the launch its push."""
+                keep = set(leftover)
+                after = list(done)
+                for j, i in enumerate(batch):
+                    if j not in keep:
+                        after[i] = True
+                victims = self._choose_victims(wanted, ops, after, avoid=set(tile_positions))
+                fused["pairs"] = self._push_pairs(wanted, victims)
+                return self._push_args(fused["pairs"])
+
+            use_fused = (exchange_follows and self.exchange == "push" and batch and self.relabel
+                         and self.n_local > self.tile_bits and os.environ.get("QVM_B200_FUSED_PUSH", "1") != "0")
             # a thin last group is not worth a pass of its own when an exchange follows: its ops stay
             # pending and merge with what the exchange unblocks (they are logical ops, the layout is looked
             # up when they finally run)
-            deferred = self._run_logical([ops[i] for i in batch], defer=bool(wanted) and len(batch) < remaining)
+            deferred = self._run_logical([ops[i] for i in batch], defer=exchange_follows,
+                                         on_last=plan_push if use_fused else None)
             if deferred:
                 keep = set(deferred)              # positions within `batch`
                 batch = [i for j, i in enumerate(batch) if j not in keep]
@@ -338,11 +523,15 @@ class ShardedEngine(object):
             if remaining:
                 if not wanted:
                     raise RuntimeError("sharded scheduler made no progress")
-                self._bring_local(wanted, ops, done)
+                if "pairs" in fused:
+                    self._push_finish(fused["pairs"], fused_pass=True)
+                else:
+                    self._bring_local(wanted, ops, done)
 
-    def _bring_local(self, wanted, ops, done):
-        """Swap the logical qubits in ``wanted`` (all on global positions) with local victims: the
-        local qubits whose next dense use lies farthest ahead (Belady), lowest positions kept."""
+    def _choose_victims(self, wanted, ops, done, avoid=()):
+        """Local logical qubits to trade for the global ones in ``wanted``: those whose next dense use
+        lies farthest ahead (Belady), lowest positions kept, positions in ``avoid`` (the tile of the pass
+        that will carry the exchange) only as a last resort."""
         nxt = {}
         for i in range(len(ops) - 1, -1, -1):
             if not done[i] and ops[i].kind == nat.OP_DENSE:
@@ -354,21 +543,72 @@ class ShardedEngine(object):
                 busy.update(op.targets)
         victims = []
         for q in wanted:
-            v = self._pick_victim(nxt, busy, len(ops))
+            v = self._pick_victim(nxt, busy, len(ops), avoid)
             victims.append(v)
             busy.add(v)
-        if self.p2p and len(wanted) > 1:
+        return victims
+
+    def _bring_local(self, wanted, ops, done):
+        """Swap the logical qubits in ``wanted`` (all on global positions) with local victims."""
+        victims = self._choose_victims(wanted, ops, done)
+        if self.exchange == "push":
+            self._swap_push(wanted, victims)
+        elif self.exchange == "p2p" and len(wanted) > 1:
             self._swap_many(wanted, victims)
         else:
             for q, v in zip(wanted, victims):
                 self._swap_global_local(q, v)
 
+    # -- push exchange ---------------------------------------------------------------------------------
+    def _push_pairs(self, globals_, victims):
+        """[(victim qubit, global qubit)] sorted by the victims' positions (the library wants them ascending)."""
+        return sorted(zip(victims, globals_), key=lambda vg: self.pos_of[vg[0]])
+
+    def _push_args(self, pairs):
+        """(victim positions, my global-bit value, destination pointers by victim value) for the library."""
+        vpos = [self.pos_of[v] for v, _ in pairs]
+        gbit = [self.pos_of[g] - self.n_local for _, g in pairs]
+        rank = self.ctx.rank
+        mine = sum(((rank >> gb) & 1) << i for i, gb in enumerate(gbit))
+        base_rank = rank
+        for gb in gbit:
+            base_rank &= ~(1 << gb)
+        alt = 1 - self._buf
+        dst = []
+        for value in range(1 << len(pairs)):
+            peer = base_rank | sum(((value >> i) & 1) << gb for i, gb in enumerate(gbit))
+            dst.append(0 if peer == rank else self.shard.peers[peer][alt])
+        return vpos, mine, dst
+
+    def _push_finish(self, pairs, fused_pass=False):
+        """After the pushing pass: ONE stream-ordered barrier (every rank's stores have landed before
+        anyone reads its new current buffer; the previous epoch's barrier already keeps writers away from
+        a buffer that is still being read), then the bookkeeping."""
+        self.comm.stream_barrier(self.shard)
+        self._buf ^= 1
+        m = len(pairs)
+        for v, g in pairs:
+            self.pos_of[g], self.pos_of[v] = self.pos_of[v], self.pos_of[g]
+        self.swaps += 1
+        self.fused_swaps += 1 if fused_pass else 0
+        self.swap_bytes += 16 * (1 << (self.n_local - m)) * ((1 << m) - 1)
+
+    def _swap_push(self, globals_, victims):
+        e0 = self.shard.record_event() if self.timing is not None else None
+        pairs = self._push_pairs(globals_, victims)
+        vpos, mine, dst = self._push_args(pairs)
+        self.shard.exchange_push(vpos, mine, dst)
+        self._push_finish(pairs)
+        if e0 is not None:
+            self.timing["swap"].append((e0, self.shard.record_event()))
+
+    # -- in-place peer-memory exchange -------------------------------------------------------------------
     def _swap_many(self, globals_, victims):
         """One exchange for m (global qubit, local victim) pairs: with every peer P of my 2^m-rank
         subgroup I trade my sub-block "victim bits == P's global bits" for P's sub-block "victim bits
         == my global bits" -- (2^m - 1) / 2^m of the shard moves, once."""
         m = len(globals_)
-        pairs = sorted(zip(victims, globals_), key=lambda vg: self.pos_of[vg[0]])       # victim positions ascending
+        pairs = self._push_pairs(globals_, victims)
         vpos = [self.pos_of[v] for v, _ in pairs]
         gbit = [self.pos_of[g] - self.n_local for _, g in pairs]
         rank = self.ctx.rank
@@ -378,7 +618,7 @@ class ShardedEngine(object):
             base_rank &= ~(1 << gb)
         block = 1 << (self.n_local - m)
         e0 = self.shard.record_event() if self.timing is not None else None
-        self.dist.all_reduce(self._token, group=self.ctx.group)
+        self.comm.stream_barrier(self.shard)
         for step in range(1, 1 << m):
             # XOR schedule: at every step the 2^m ranks of the subgroup pair up perfectly, so no GPU is
             # the target of two peers at once (all NVLink ports stay evenly loaded)
@@ -386,7 +626,7 @@ class ShardedEngine(object):
             peer = base_rank | sum(((value >> i) & 1) << gb for i, gb in enumerate(gbit))
             lo, cnt = (0, block // 2) if rank < peer else (block // 2, block - block // 2)
             self.shard.exchange_block(vpos, value, mine, peer, lo, cnt)
-        self.dist.all_reduce(self._token, group=self.ctx.group)
+        self.comm.stream_barrier(self.shard)
         for v, g in pairs:
             self.pos_of[g], self.pos_of[v] = self.pos_of[v], self.pos_of[g]
         self.swaps += 1
@@ -397,9 +637,11 @@ class ShardedEngine(object):
     #: a batch's last group is deferred across the following exchange when it holds fewer ops than this
     DEFER_TAIL_BELOW = int(os.environ.get("QVM_B200_DEFER_TAIL", "16"))
 
-    def _run_logical(self, batch, defer=False):
+    def _run_logical(self, batch, defer=False, on_last=None):
         """Ops in LOGICAL coordinates whose dense targets are all local right now.  Returns the indices
-        (into ``batch``) of the ops that were NOT run (a thin last group, only when ``defer``)."""
+        (into ``batch``) of the ops that were NOT run (a thin last group, only when ``defer``).
+        ``on_last(leftover, tile_positions)`` -> push arguments for the batch's last launch (fused
+        exchange)."""
         if not batch:
             return []
         if not (self.relabel and self.n_local > self.tile_bits):
@@ -407,11 +649,19 @@ class ShardedEngine(object):
             return []
         leftover = []
         e0 = self.shard.record_event() if self.timing is not None else None
+
+        def launch(tile, ops, bring, push=None):
+            if push is None:
+                return self.shard.apply_group(tile, ops, bring if bring else [], self.low_bits)
+            f0 = self.shard.record_event() if self.timing is not None else None
+            out = self.shard.apply_group(tile, ops, bring if bring else [], self.low_bits, push=push)
+            if f0 is not None:
+                self.timing["fused"].append((f0, self.shard.record_event()))
+            return out
+
         self.groups_launched += _planner.run_relabelled(
-            batch, self.n_local, self.pos_of,
-            lambda tile, ops, bring: self.shard.apply_group(tile, ops, bring if bring else [], self.low_bits),
-            self.tile_bits, self.low_bits, defer_tail_below=self.DEFER_TAIL_BELOW if defer else 0,
-            leftover=leftover)
+            batch, self.n_local, self.pos_of, launch, self.tile_bits, self.low_bits,
+            defer_tail_below=self.DEFER_TAIL_BELOW if defer else 0, leftover=leftover, on_last=on_last)
         if e0 is not None:
             self.timing["batch"].append((e0, self.shard.record_event()))
         return leftover
@@ -424,7 +674,7 @@ class ShardedEngine(object):
             if e0 is not None:
                 self.timing["batch"].append((e0, self.shard.record_event()))
 
-    def _pick_victim(self, next_use, busy, horizon):
+    def _pick_victim(self, next_use, busy, horizon, avoid=()):
         """Local logical qubit to push out: the one whose next dense use is farthest (Belady).
         The lowest local positions are kept (they are every tile's coalescing bits)."""
         best, best_key = None, None
@@ -432,16 +682,18 @@ class ShardedEngine(object):
             p = self.pos_of[q]
             if p >= self.n_local or q in busy:
                 continue
-            key = (next_use.get(q, horizon + 1), p)     # farthest use first, then highest position
+            key = (0, next_use.get(q, horizon + 1), p)     # farthest use first, then highest position
+            if p in avoid:
+                key = (-1, next_use.get(q, horizon + 1), p)  # inside the carrying pass's tile: would unfuse the push
             if p < min(self.low_bits, self.n_local - 1):
-                key = (-1, p)                            # avoid unless nothing else is left
+                key = (-2, 0, p)                            # avoid unless nothing else is left
             if best_key is None or key > best_key:
                 best, best_key = q, key
         if best is None:
             raise RuntimeError("no local qubit available for a global<->local swap")
         return best
 
-    # -- the exchange --------------------------------------------------------------------------------
+    # -- the staged exchange -----------------------------------------------------------------------------
     def _buffers(self):
         if self._send is None:
             self._send = [self.shard.alloc(self.chunk_amps) for _ in range(2)]
@@ -452,19 +704,22 @@ class ShardedEngine(object):
         """Swap the physical positions of logical qubits q_global (on a global position) and q_local."""
         pg, pl = self.pos_of[q_global], self.pos_of[q_local]
         assert pg >= self.n_local > pl
+        if self.exchange == "push":
+            self._swap_push([q_global], [q_local])
+            return
         gbit = pg - self.n_local
         mine = (self.ctx.rank >> gbit) & 1
         partner = self.ctx.rank ^ (1 << gbit)
         e0 = self.shard.record_event() if self.timing is not None else None
         half = 1 << (self.n_local - 1)
-        if self.p2p:
+        if self.exchange == "p2p":
             # stream-ordered cross-rank barrier (a tiny all-reduce), the swap kernel on my half of the
             # element range, barrier again: nobody touches a shard its partner is still working on
-            self.dist.all_reduce(self._token, group=self.ctx.group)
+            self.comm.stream_barrier(self.shard)
             lo = 0 if mine == 0 else half // 2
             cnt = half // 2 if mine == 0 else half - half // 2
             self.shard.exchange_half(pl, 1 - mine, partner, lo, cnt)
-            self.dist.all_reduce(self._token, group=self.ctx.group)
+            self.comm.stream_barrier(self.shard)
             self.pos_of[q_global], self.pos_of[q_local] = pl, pg
             self.swaps += 1
             self.swap_bytes += 16 * half
@@ -473,18 +728,13 @@ class ShardedEngine(object):
             return
         send, recv = self._buffers()
         moving = 1 - mine           # the half whose local bit differs from my global bit changes owner
-        dist = self.dist
         pending = None              # (requests, offset, count, buffer index) of the chunk in flight
         k = 0
         for off in range(0, half, self.chunk_amps):
             cnt = min(self.chunk_amps, half - off)
             b = k & 1
             self.shard.pack_half(pl, moving, off, cnt, send[b])
-            ops = [dist.P2POp(dist.isend, send[b][:2 * cnt], self._global_rank(partner), self.ctx.group),
-                   dist.P2POp(dist.irecv, recv[b][:2 * cnt], self._global_rank(partner), self.ctx.group)]
-            if mine:                # fixed order on both sides of a pair keeps gloo from deadlocking
-                ops.reverse()
-            reqs = dist.batch_isend_irecv(ops)
+            reqs = self.comm.sendrecv(send[b][:2 * cnt], recv[b][:2 * cnt], partner, reverse=bool(mine))
             if pending is not None:
                 self._finish_chunk(pl, moving, pending)
             pending = (reqs, off, cnt, b)
@@ -502,11 +752,6 @@ class ShardedEngine(object):
         for r in reqs:
             r.wait()
         self.shard.unpack_half(pl, moving, off, cnt, self._recv[b])
-
-    def _global_rank(self, group_rank):
-        if self.ctx.group is None:
-            return group_rank
-        return self.dist.get_global_rank(self.ctx.group, group_rank)
 
     def restore_layout(self):
         """Bring every logical qubit back to its own position (before a full readback)."""
@@ -539,14 +784,10 @@ class ShardedEngine(object):
 
     # -- reductions ------------------------------------------------------------------------------------
     def _allreduce_sum(self, value):
-        t = self.shard.scalar_tensor([float(value)])
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.ctx.group)
-        return float(t.cpu()[0])
+        return float(self.comm.allreduce([float(value)])[0])
 
     def _broadcast_floats(self, values):
-        t = self.shard.scalar_tensor(np.asarray(values, dtype=np.float64))
-        self.dist.broadcast(t, src=self._global_rank(0), group=self.ctx.group)
-        return t.cpu().numpy()
+        return self.comm.broadcast(np.asarray(values, dtype=np.float64))
 
     def measure(self, qubit, r):
         """MEASURE: partial p0 on every rank, all-reduce, same decision everywhere, local collapse."""
@@ -589,7 +830,7 @@ class ShardedEngine(object):
                     high.append(p)
                 chunk.append(p)
             local = self.shard.measure_hist(high, pending)
-            hist = self._allgather_array(local.reshape(-1)).reshape((world,) + local.shape)
+            hist = self.comm.allgather(local.reshape(-1)).reshape((world,) + local.shape)
             bins = np.arange(local.shape[0])[None, :, None]
             consistent = np.ones(hist.shape, dtype=bool)
             norm_factor, mask, value, alive = 1.0, 0, 0, True
@@ -616,13 +857,6 @@ class ShardedEngine(object):
         self.shard.measure_hist([], pending, want_hist=False)
         return results
 
-    def _allgather_array(self, values):
-        """The same 1-D float64 array from every rank, concatenated in rank order (identical everywhere)."""
-        mine = self.shard.scalar_tensor(np.ascontiguousarray(values, dtype=np.float64))
-        out = self.shard.scalar_tensor(np.zeros(mine.numel() * self.ctx.world))
-        self.dist.all_gather(list(out.split(mine.numel())), mine, group=self.ctx.group)
-        return out.cpu().numpy()
-
     def prob_zero(self, qubit):
         self.flush()
         return self._allreduce_sum(self.shard.prob_zero(self.pos_of[int(qubit)]))
@@ -644,14 +878,9 @@ class ShardedEngine(object):
         self.flush()
         if logical_order:
             self.restore_layout()
-        import torch
         u = self._broadcast_floats(uniforms)
         local_total = self.shard.probs_prepare()
-        totals = self.shard.scalar_tensor([0.0] * self.ctx.world)
-        mine = self.shard.scalar_tensor([local_total])
-        pieces = list(totals.split(1))
-        self.dist.all_gather(pieces, mine, group=self.ctx.group)
-        totals = np.array([float(p.cpu()[0]) for p in pieces])
+        totals = self.comm.allgather([local_total])
         cum = np.cumsum(totals)
         grand = cum[-1]
         target = u * grand
@@ -663,9 +892,7 @@ class ShardedEngine(object):
             lu = np.clip((target[sel] - start) / totals[self.ctx.rank], 0.0, np.nextafter(1.0, 0.0))
             local_idx = self.shard.sample(lu).astype(np.int64)
             phys[sel] = (np.int64(self.ctx.rank) << np.int64(self.n_local)) | local_idx
-        t = self.shard.scalar_tensor(phys, dtype=torch.int64)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.ctx.group)
-        phys = t.cpu().numpy().astype(np.uint64)
+        phys = self.comm.allreduce_int64(phys).astype(np.uint64)
         if physical:                # the caller looks bits up through position(): no per-qubit pass over the shots
             return phys, grand
         logical = np.zeros_like(phys)
@@ -680,5 +907,5 @@ class ShardedEngine(object):
     def stats(self):
         s = self.shard.stats()
         s.update(gates_queued=self.gates_queued, groups_launched=self.groups_launched, swaps=self.swaps,
-                 swap_bytes=self.swap_bytes)
+                 fused_swaps=self.fused_swaps, swap_bytes=self.swap_bytes, exchange=self.exchange)
         return s

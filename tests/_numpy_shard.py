@@ -65,11 +65,66 @@ class NumpyShard(object):
         self.ctx = ctx
         self.psi = np.zeros(1 << n_local, dtype=np.complex128)
         self.launches = 0
+        self.fused_pushes = 0
+        self.pushes = 0
         self.state = _FakeState()
         self._cdf = None
+        self.alt = None             # second buffer (push exchange model)
+        self.peers = None
+        self.peer_error = None
 
     def close(self):
         self.psi = None
+
+    # -- push exchange model (in-process ranks only: "pointers" are (shard, which buffer) pairs) ----------
+    def alloc_alt(self):
+        self.alt = np.zeros_like(self.psi)
+        self._which = 0             # psi is buffer 0, alt buffer 1; swapped at every push
+        return True
+
+    def drop_alt(self):
+        self.alt = None
+
+    def close_peers(self):
+        self.peers = None
+
+    def open_peers(self, comm, with_alt):
+        if not getattr(comm, "same_process", False):
+            self.peer_error = "the numpy backend maps peers only between in-process ranks"
+            return False
+        shards = comm.allgather_object(self)
+        self.peers = {r: ((shards[r], 0), (shards[r], 1)) for r in range(comm.world) if r != self.ctx.rank}
+        return True
+
+    def _buffer(self, which):
+        return self.psi if which == self._which else self.alt
+
+    def exchange_push(self, local_bits, mine_value, dst_ptrs):
+        """Model of qvm_exchange_push: every amplitude is written where it will live, then the buffers
+        swap roles."""
+        x = np.arange(self.psi.size, dtype=np.int64)
+        L = np.zeros_like(x)
+        mask = 0
+        mine_bits = 0
+        for i, p in enumerate(local_bits):
+            L |= ((x >> p) & 1) << i
+            mask |= 1 << p
+            mine_bits |= ((mine_value >> i) & 1) << p
+        y = (x & ~mask) | mine_bits
+        for value in range(1 << len(local_bits)):
+            sel = L == value
+            if dst_ptrs[value]:
+                shard, which = dst_ptrs[value]
+                target = shard._buffer(which)
+                assert target is not shard.psi or shard is not self
+            else:
+                assert value == mine_value
+                target = self.alt
+            target[y[sel]] = self.psi[x[sel]]
+        self.psi, self.alt = self.alt, self.psi
+        self._which ^= 1
+        self.pushes += 1
+        self.launches += 1
 
     def alloc(self, n_amps):
         return torch.empty(2 * n_amps, dtype=torch.float64)
@@ -88,9 +143,21 @@ class NumpyShard(object):
         self.launches += n
         return n
 
-    def apply_group(self, tile_positions, ops, bring_low, n_low):
+    def apply_group(self, tile_positions, ops, bring_low, n_low, push=None):
         """One pass with in-tile relabelling, modelled: run the ops, then let every requested position
-        >= n_low trade places with a low position that was not asked for."""
+        >= n_low trade places with a low position that was not asked for.  ``push``: the pass's stores are
+        the exchange (fused when no victim position lies in the tile, as in the library)."""
+        new_pos = self._apply_group(tile_positions, ops, bring_low, n_low)
+        if push is not None:
+            bits, mine, dst = push
+            self.exchange_push(bits, mine, dst)
+            if not (set(bits) & set(tile_positions)):
+                self.fused_pushes += 1
+                self.launches -= 1
+                self.pushes -= 1
+        return new_pos
+
+    def _apply_group(self, tile_positions, ops, bring_low, n_low):
         for op in ops:
             lop = localise(op, self.n_local, self.ctx.rank)
             if lop is not None:

@@ -85,6 +85,7 @@ extern "C" int qvm_emu_apply_group(double* amps, int n_local, int n_global, uint
         c.rounds = g.rounds.data();
         c.hi_off = g.hi_off.data();
         c.gbase = state + base;
+        c.gstore = rt_push_base(P.push, state, base);
         c.mats = P.mats;
         c.cold = P.cold;
         c.low = P.low;

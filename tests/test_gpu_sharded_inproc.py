@@ -1,0 +1,132 @@
+"""The sharded CUDA path on ONE GPU: the real ``ShardedEngine`` + ``CudaShard`` (libqvm_b200 kernels, push /
+in-place exchange kernels over peer pointers, fused pass + exchange, all-gathered MEASURE runs, sharded
+sampling, the public API) with G = 2 / 4 / 8 ranks running as threads of this process on device 0
+(tests/_thread_comm.py).  Every shard is its own ``qvm_t`` on its own stream; "peer memory" is the
+other shards' device pointers.  Amplitudes, MEASURE outcomes and sampled indices are diffed against
+the oracle.  (tests/test_gpu_sharded.py runs the same checks with one process per GPU over NCCL / CUDA
+IPC when the box has several GPUs.)"""
+import numpy as np
+import pytest
+
+from _programs import spec_program
+from _thread_comm import run_ranks
+from oracle import qvm_oracle as orc
+from referenceqvm import _sharded, gates as G
+from referenceqvm.api import QVMConnection
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_ops(spec):
+    out = []
+    for name, params, qubits in spec:
+        m = G.gate_matrix[name]
+        out.append(("gate", np.asarray(m(*params) if params else m, dtype=complex), qubits))
+    return out
+
+
+def queue_spec(eng, spec):
+    for name, params, qubits in spec:
+        m = G.gate_matrix[name]
+        eng.queue_matrix(m(*params) if params else m, qubits)
+
+
+@pytest.mark.parametrize("exchange", ["push", "p2p"])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_engine_on_one_gpu(world, exchange):
+    facts = {}
+
+    def rank_main(comm):
+        rank = comm.rank
+        ctx = _sharded.enable(device=0, comm=comm)
+        try:
+            for case, (n, depth, seed, jit) in enumerate(((14, 6, 1, 1), (16, 8, 2, 2), (20, 5, 1234, 2), (17, 10, 5, 1))):
+                spec = orc.random_circuit_spec(n, depth, seed)
+                eng = _sharded.ShardedEngine(n, ctx, exchange=exchange)
+                assert eng.exchange == exchange, eng.exchange_note
+                eng.shard.state.set_jit(jit)
+                eng.reset()
+                queue_spec(eng, spec)
+                want, _ = orc.fast_run_wavefunction(oracle_ops(spec), n)
+                eng.flush()
+                assert eng.swaps > 0
+                assert abs(eng.norm2() - 1.0) < 1e-12
+                probe_idx = [0, 1, 5, (1 << n) - 1, 1 << (n - 1), 12345]
+                assert np.max(np.abs(eng.probe(probe_idx) - want[probe_idx])) < 1e-12
+                got = eng.amplitudes()
+                err = float(np.max(np.abs(got - want)))
+                assert err < 1e-12, (n, depth, seed, err)
+                if rank == 0:
+                    st = eng.stats()
+                    facts[case] = (eng.swaps, eng.fused_swaps, st["fused_push_launches"], st["push_launches"],
+                                   st["jit_launches"])
+                psi = want
+                for q, r in ((n - 1, 0.3), (0, 0.8), (n // 2, 0.5)):
+                    outcome, p0 = eng.measure(q, r if rank == 0 else -1.0)
+                    o_want, p_want, psi = orc.fast_measure(psi, q, n, r)
+                    assert outcome == o_want and abs(p0 - p_want) < 1e-12
+                err = float(np.max(np.abs(eng.amplitudes() - psi)))
+                assert err < 1e-12, ("after measure", err)
+                eng.close()
+
+            # a run of MEASUREs on the sharded state (measure_hist per shard, all-gathered): all qubits, shuffled
+            for n, depth, seed in ((18, 5, 7), (16, 6, 9)):
+                spec = orc.random_circuit_spec(n, depth, seed)
+                eng = _sharded.ShardedEngine(n, ctx, exchange=exchange)
+                eng.reset()
+                queue_spec(eng, spec)
+                psi, _ = orc.fast_run_wavefunction(oracle_ops(spec), n)
+                rs = np.random.RandomState(seed)
+                order = [int(q) for q in rs.permutation(n)]
+                uniforms = rs.random_sample(n)
+                got = eng.measure_many(order, uniforms if rank == 0 else np.zeros(n))
+                for (outcome, p0), q, r in zip(got, order, uniforms):
+                    o_want, p_want, psi = orc.fast_measure(psi, q, n, r)
+                    assert outcome == o_want and abs(p0 - p_want) < 1e-12
+                err = float(np.max(np.abs(eng.amplitudes() - psi)))
+                assert err < 1e-12, ("after measure_many", err)
+                eng.close()
+
+            # sampling through the layout, and the public API (SPMD: QVMConnection on every rank)
+            n = 15
+            spec = orc.random_circuit_spec(n, 6, 7)
+            want, _ = orc.fast_run_wavefunction(oracle_ops(spec), n)
+            eng = _sharded.ShardedEngine(n, ctx, exchange=exchange)
+            eng.reset()
+            queue_spec(eng, spec)
+            u = np.random.RandomState(11).random_sample(20000)
+            idx, total = eng.sample(u if rank == 0 else np.zeros(u.size))
+            assert abs(total - 1.0) < 1e-12
+            logical = np.arange(1 << n, dtype=np.int64)
+            phys = np.zeros_like(logical)
+            for q, p in enumerate(eng.pos_of):
+                phys |= ((logical >> q) & 1) << p
+            probs_hbm = np.empty(1 << n)
+            probs_hbm[phys] = np.abs(want) ** 2
+            logical_of_phys = np.empty_like(logical)
+            logical_of_phys[phys] = logical
+            ref = logical_of_phys[np.asarray(orc.inverse_cdf_sample(probs_hbm, u), dtype=np.int64)]
+            assert np.mean(idx.astype(np.int64) == ref) > 0.999
+            eng.close()
+
+            qvm = QVMConnection()
+            wf, _ = qvm.wavefunction(spec_program(spec))
+            assert isinstance(qvm._engine, _sharded.ShardedEngine)
+            assert float(np.max(np.abs(wf.amplitudes - want))) < 1e-12
+            shots = np.asarray(qvm.run_and_measure(spec_program(spec), list(range(n)), trials=4000))
+            assert shots.shape == (4000, n)
+            # marginals of the sampled bits against the exact ones (4000 shots: 5 sigma ~ 0.04)
+            probs = np.abs(want) ** 2
+            for q in range(n):
+                p1 = float(probs[((np.arange(1 << n) >> q) & 1) == 1].sum())
+                assert abs(shots[:, q].mean() - p1) < 0.05
+            qvm._engine.close()
+        finally:
+            _sharded.disable()
+
+    run_ranks(world, rank_main)
+    if exchange == "push":
+        # every epoch went through the push path, and some of them rode on a gate pass (fused stores)
+        assert all(f[2] + f[3] >= f[0] for f in facts.values()), facts
+        assert sum(f[1] for f in facts.values()) > 0 and sum(f[2] for f in facts.values()) > 0, facts
+        assert facts[1][4] > 0 or facts[2][4] > 0, facts          # specialised kernels carried pushes too
