@@ -10,6 +10,14 @@ sync.  `value` is device-timed (CUDA events on the library's stream, max over ra
 same metric through the public API (QVMConnection.run_and_measure: host Program in, host bit lists
 out, all host<->device traffic inside the timed region).
 
+Besides the contract's keys the line carries
+  check     proof that the timed state is right: norm, amplitudes at fixed logical indices (identical on
+            1 / 2 / 4 / 8 GPUs), and U then U^dagger returning |0...0>
+  roofline  HBM fraction of the local gate passes; `nvlink` for the exchanges when sharded
+  e2e_cold  the first call of a program this process has never seen (interpreter + first-sight compiles)
+  configs   BASELINE configs 1-3 on one GPU (config 1 with the reference itself on the SAME program),
+            config 5 (36 qubits) on 8 GPUs
+
 Rank 0 prints ONE JSON line.
 """
 import argparse
@@ -30,6 +38,8 @@ import numpy as np  # noqa: E402
 
 SEED = 1234
 METRIC = "gate-apps/s"
+NVLINK_MEASURED = 770.0      # GB/s per direction per GPU: peer copy measured on this pool (B200_PROFILING.md)
+NVLINK_NOMINAL = 900.0
 
 
 def measured_peaks():
@@ -97,9 +107,9 @@ class ClockSampler(object):
 
 
 # ---------------------------------------------------------------------------------------------
-def circuit(n, depth):
+def circuit(n, depth, seed=SEED):
     from workloads import random_circuit_spec
-    return random_circuit_spec(n, depth, SEED)
+    return random_circuit_spec(n, depth, seed)
 
 
 def build_program(spec):
@@ -109,6 +119,30 @@ def build_program(spec):
     for name, params, qubits in spec:
         prog.inst(Gate(name, params, qubits))
     return prog
+
+
+# ---- the CPU arm: the reference itself (staged copy, subprocess) or the oracle port --------------------
+def reference_staged():
+    return os.path.isdir(os.path.join(REPO, "oracle", "_ref", "referenceqvm"))
+
+
+def run_reference_subprocess(n, depth, copies, density=False, out=None, seed=SEED, timeout=900):
+    """oracle/run_reference.py: the unmodified reference through its own public API, `copies` side by side.
+    Returns its JSON dict, or None when the staged copy is missing / the run failed."""
+    cmd = [sys.executable, os.path.join(REPO, "oracle", "run_reference.py"), "--qubits", str(n), "--depth", str(depth),
+           "--seed", str(seed), "--copies", str(copies)]
+    if density:
+        cmd.append("--density")
+    if out:
+        cmd += ["--out", out]
+    try:
+        proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout,
+                              env=dict(os.environ, OMP_NUM_THREADS="1", PYTHONWARNINGS="ignore"))
+        lines = [ln for ln in proc.stdout.splitlines() if ln.startswith("{")]
+        d = json.loads(lines[-1]) if lines else None
+        return d if d and "gate_apps_per_s" in d else None
+    except Exception:
+        return None
 
 
 def _cpu_sample_worker(task):
@@ -125,53 +159,68 @@ def _cpu_sample_worker(task):
     return len(ops), time.perf_counter() - t0
 
 
-def cpu_reference_sample(n, depth, workers=None):
-    """Time the oracle's restatement of the reference's own algorithm (sparse lifted operators,
-    swap chains: oracle.qvm_oracle.ref_*) on a bounded sample of the workload.  The algorithm is
-    serial (scipy.sparse products, as in the reference), so "all host threads" means one independent
-    copy of the sample circuit per core; the figure is their aggregate gate-applications per second.
-    Returns (gate-apps/s, wall seconds, gates per copy, copies)."""
+def cpu_port_sample(n, depth, workers):
+    """The oracle's restatement of the reference's algorithm (oracle.qvm_oracle.ref_*), one copy per core."""
     import multiprocessing as mp
-    workers = workers or max(1, (os.cpu_count() or 1))
-    t0 = time.perf_counter()
     if workers == 1:
         results = [_cpu_sample_worker((n, depth))]
     else:
         with mp.get_context("fork").Pool(workers) as pool:
             results = pool.map(_cpu_sample_worker, [(n, depth)] * workers)
-    del t0
-    wall = max(dt for _, dt in results)           # the copies run side by side; pool start-up is not counted
-    gates = sum(g for g, _ in results)
-    return gates / wall, wall, results[0][0], workers
+    wall = max(dt for _, dt in results)
+    return {"gates": results[0][0], "copies": workers, "seconds": wall,
+            "gate_apps_per_s": sum(g for g, _ in results) / wall}
+
+
+def cpu_reference_sample(n, depth, workers=None):
+    """(result dict, kind): the staged reference when present, else the oracle port.  The algorithm is
+    serial (scipy.sparse products), so "all host threads" means one independent copy per core."""
+    workers = workers or max(1, (os.cpu_count() or 1))
+    if reference_staged():
+        d = run_reference_subprocess(n, depth, workers)
+        if d is not None:
+            return d, "reference"
+    return cpu_port_sample(n, depth, workers), "port"
+
+
+def sample_text(n, depth, d, kind):
+    who = ("the unmodified reference (oracle/_ref/referenceqvm, staged from /root/reference) through "
+           "QVMConnection().wavefunction()" if kind == "reference"
+           else "oracle restatement of the reference's sparse lifted-operator algorithm")
+    return ("n=%d depth=%d random circuit (seed %d, %d gates, %.1f s), one independent copy on each of %d host cores "
+            "(the algorithm is serial: scipy.sparse): %s" % (n, depth, SEED, d["gates"], d["seconds"], d["copies"], who))
 
 
 def run_reference_arm(args, rank):
-    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is pure
-    Python + un-vendored pyquil and /root/reference does not exist on the GPU box)."""
+    """--impl reference: the reference's own CPU implementation on a bounded sample of the workload."""
     if rank != 0:
         return
     n, depth = args.ref_qubits, args.ref_depth
+    kind = "port"
     for _ in range(args.warmup):
         cpu_reference_sample(n, depth)
-    total, total_gates, gates, workers = 0.0, 0, 0, 1
+    total, total_gates, last = 0.0, 0, None
     for _ in range(args.steps):
-        v, dt, gates, workers = cpu_reference_sample(n, depth)
-        total += dt
-        total_gates += gates * workers
+        last, kind = cpu_reference_sample(n, depth)
+        total += last["seconds"]
+        total_gates += last["gates"] * last["copies"]
     value = total_gates / total
-    times = [total / args.steps] * args.steps
-    sample = ("n=%d depth=%d random circuit (seed %d, %d gates), one independent copy on each of %d cores "
-              "(the algorithm itself is serial): same generator as the GPU arm" % (n, depth, SEED, gates, workers))
+    sample = sample_text(n, depth, last, kind) + "; same generator as the GPU arm"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args), "reference_sample": sample},
-        "cpu_baseline": {"value": value, "unit": METRIC, "cores": workers, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": METRIC, "cores": last["copies"], "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def workload_name(args):
+    return "%d-qubit random circuit depth %d (H/RZ/CNOT/CPHASE, seed %d), complex128 state %.1f GiB" % (
+        args.qubits, args.depth, SEED, 16.0 * 2 ** args.qubits / 2 ** 30)
 
 
 def measured_traffic_ratio():
@@ -186,9 +235,304 @@ def measured_traffic_ratio():
         return None, None
 
 
-def workload_name(args):
-    return "%d-qubit random circuit depth %d (H/RZ/CNOT/CPHASE, seed %d), complex128 state %.1f GiB" % (
-        args.qubits, args.depth, SEED, 16.0 * 2 ** args.qubits / 2 ** 30)
+# ---------------------------------------------------------------------------------------------
+class Harness(object):
+    """Process-group plumbing shared by the legs."""
+
+    def __init__(self, args):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+        torch.cuda.set_device(self.local_rank)
+        os.environ["QVM_B200_DEVICE"] = str(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            from referenceqvm import _sharded
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            _sharded.enable(device=self.local_rank)
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def compile_ops(qvm, prog):
+    from referenceqvm import _engine
+    from referenceqvm.unitary_generator import resolve_gate
+    return [_engine.compile_gate(*resolve_gate(qvm.gate_set, {}, ins)) for ins in prog]
+
+
+def timed_circuit(h, args, n, depth, steps, warmup, want_check=True):
+    """The device-timed leg on an n-qubit circuit.  Returns a dict of everything measured."""
+    torch = h.torch
+    from referenceqvm import _native
+    from referenceqvm.api import QVMConnection
+    from workloads import inverse_spec
+
+    spec = circuit(n, depth)
+    prog = build_program(spec)
+    n_gates = len(spec)
+    qvm = QVMConnection()
+    qvm.device = h.local_rank
+    qvm.load_program(prog)
+    eng = qvm._fresh_engine()
+    ops = compile_ops(qvm, prog)
+    stream = torch.cuda.ExternalStream(eng.state.stream_ptr(), device=h.local_rank)
+    sharded = h.world > 1
+    n_local = n - (h.world.bit_length() - 1)
+
+    def step():
+        eng.reset()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for op in ops:
+            eng.queue(op)
+        eng.flush()
+        e1.record(stream)
+        return e0, e1
+
+    for _ in range(warmup):
+        step()
+    eng.sync()
+    # group structures that recur are compiled into specialised kernels on background threads
+    # (qvm_jit.h); the timed region measures the steady state, so wait for them once and run one more
+    # untimed step so that every rank is past its first specialised launches
+    _native.jit_wait()
+    if warmup:
+        step()
+        eng.sync()
+    h.barrier()
+
+    eng.state.stats_reset()
+    groups_before = eng.groups_launched
+    swaps_before = getattr(eng, "swaps", 0)
+    fused_before = getattr(eng, "fused_swaps", 0)
+    swap_bytes_before = getattr(eng, "swap_bytes", 0)
+    if sharded:
+        eng.timing = {"batch": [], "swap": [], "fused": []}
+    sampler = ClockSampler(h.local_rank)
+    sampler.start()
+    t_begin = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_begin.record(stream)
+    pairs = [step() for _ in range(steps)]
+    t_end.record(stream)
+    eng.sync()
+    h.barrier()
+    clocks = sampler.stop()
+    total_ms = h.max_over_ranks(t_begin.elapsed_time(t_end))
+    stats = eng.state.stats()
+    groups = eng.groups_launched - groups_before
+    swaps = getattr(eng, "swaps", 0) - swaps_before
+    fused = getattr(eng, "fused_swaps", 0) - fused_before
+    swap_ms = fused_ms = 0.0
+    if sharded:
+        batch_ms = sum(a.elapsed_time(b) for a, b in eng.timing["batch"])
+        swap_ms = sum(a.elapsed_time(b) for a, b in eng.timing["swap"])          # stand-alone exchanges (+ barrier)
+        fused_ms = sum(a.elapsed_time(b) for a, b in eng.timing["fused"])        # passes whose stores were the exchange
+        eng.timing = None
+        kernel_ms = batch_ms - fused_ms                                          # plain local passes
+        plain_groups = groups - fused
+    else:
+        kernel_ms = sum(a.elapsed_time(b) for a, b in pairs)
+        plain_groups = groups
+    out = {"n": n, "depth": depth, "n_gates": n_gates, "total_ms": total_ms, "steps": steps, "stats": stats,
+           "groups": groups, "plain_groups": plain_groups, "kernel_ms": kernel_ms, "swaps": swaps, "fused": fused,
+           "swap_ms": swap_ms, "fused_ms": fused_ms, "clocks": clocks, "n_local": n_local,
+           "swap_bytes": float(getattr(eng, "swap_bytes", 0) - swap_bytes_before), "eng": eng, "qvm": qvm, "prog": prog,
+           "spec": spec, "tile_bits": eng.tile_bits, "low_bits": eng.low_bits,
+           "exchange": getattr(eng, "exchange", None), "exchange_note": getattr(eng, "exchange_note", None)}
+
+    if want_check:
+        # ---- proof that the state the timed steps produce is right -------------------------------------------
+        check = {}
+        check["norm2_minus_1"] = eng.norm2() - 1.0
+        rs = np.random.RandomState(99)
+        idx = [0, 1, (1 << n) - 1] + [int(rs.randint(0, 1 << 31)) | (int(rs.randint(0, 1 << 31)) << 31) & ((1 << n) - 1)
+                                      for _ in range(13)]
+        idx = [i & ((1 << n) - 1) for i in idx]
+        amps = eng.probe(idx)
+        check["probe"] = {"what": "amplitudes after the circuit at fixed LOGICAL basis states: equal (to rounding) on "
+                                  "1 / 2 / 4 / 8 GPUs",
+                          "indices": idx[:6], "amps": [[float(a.real), float(a.imag)] for a in amps[:6]],
+                          "sum_abs2_16": float(np.sum(np.abs(amps) ** 2)),
+                          "sum_re_im_16": [float(np.sum(amps.real)), float(np.sum(amps.imag))]}
+        inv = compile_ops(qvm, build_program(inverse_spec(spec)))
+        for op in inv:
+            eng.queue(op)
+        eng.flush()
+        back = eng.probe(list(range(1024)))
+        check["inverse"] = {"what": "U then U^dagger on |0...0>", "amp0_minus_1": float(abs(back[0] - 1.0)),
+                            "max_abs_amp_1_to_1023": float(np.max(np.abs(back[1:]))),
+                            "norm2_minus_1": eng.norm2() - 1.0}
+        check["ok"] = bool(abs(check["norm2_minus_1"]) < 1e-10 and check["inverse"]["amp0_minus_1"] < 1e-10
+                           and check["inverse"]["max_abs_amp_1_to_1023"] < 1e-10)
+        out["check"] = check
+    return out
+
+
+def roofline_of(h, r):
+    peak, peak_src = measured_peaks()
+    bytes_per_launch = 32.0 * 2 ** r["n_local"]
+    avg_launch_ms = r["kernel_ms"] / max(r["plain_groups"], 1)
+    achieved = bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
+    stats = r["stats"]
+    jit_share = stats.get("jit_launches", 0) / float(max(r["groups"], 1))
+    dominant = ("spec_kernel (NVRTC-specialised regtile group)" if jit_share >= 0.5 else "regtile_kernel")
+    total_ms, steps, n_gates = r["total_ms"], r["steps"], r["n_gates"]
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_launch_ms,
+                "launches_per_step": r["groups"] / float(steps),
+                "gates_per_launch": n_gates * steps / float(max(r["groups"], 1)),
+                "regtile_rounds_per_launch": stats.get("regtile_rounds", 0) / float(max(r["groups"], 1)),
+                "specialised_launch_share": jit_share,
+                "effective_gbs": n_gates * steps * bytes_per_launch * h.world / (total_ms * 1e-3) / 1e9,
+                "note": "per GPU (rank 0): one launch = one read + one write of the local shard; launches that also "
+                        "carry an exchange (fused pushes) are counted under nvlink, not here"}
+    ratio, ratio_src = measured_traffic_ratio()
+    if ratio is not None:
+        roofline["traffic"] = ratio * bytes_per_launch
+        roofline["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum = %.4f x algorithmic in %s, "
+                                      "scaled to this shard size" % (ratio, ratio_src))
+    if h.world > 1 and r["swaps"]:
+        swaps, fused = r["swaps"], r["fused"]
+        exch_ms = r["swap_ms"] + r["fused_ms"]
+        # what the exchanges cost beyond the gate passes that carried them
+        extra_ms = r["swap_ms"] + r["fused_ms"] - fused * avg_launch_ms
+        achieved_nv = r["swap_bytes"] / (exch_ms * 1e-3) / 1e9
+        how = {"push": "out-of-place pushes over NVLink peer memory (CUDA IPC), write-only; %d of %d exchanges fused into "
+                       "the last gate pass of their batch (its final round stores straight into the peers' shards)"
+                       % (fused, swaps),
+               "p2p": "in-place swap kernel over NVLink peer memory (CUDA IPC)",
+               "staged": "staged NCCL send/recv"}.get(r["exchange"], str(r["exchange"]))
+        roofline["nvlink"] = {
+            "bound": "nvlink", "achieved": achieved_nv, "peak": NVLINK_MEASURED, "peak_nominal": NVLINK_NOMINAL,
+            "frac": achieved_nv / NVLINK_MEASURED, "frac_of_nominal": achieved_nv / NVLINK_NOMINAL,
+            "unit": "GB/s per direction per GPU", "peak_source": "peer copy measured on this pool (B200_PROFILING.md)",
+            "swaps_per_step": swaps / float(steps), "fused_per_step": fused / float(steps),
+            "bytes_per_swap_per_direction": r["swap_bytes"] / swaps,
+            "avg_exchange_ms": exch_ms / swaps, "avg_fused_pass_ms": (r["fused_ms"] / fused) if fused else None,
+            "avg_standalone_exchange_ms": (r["swap_ms"] / (swaps - fused)) if swaps > fused else None,
+            "exchange": how, "note": r["exchange_note"],
+            "share_of_step": exch_ms / (total_ms if total_ms else 1.0),
+            "extra_share_of_step": extra_ms / (total_ms if total_ms else 1.0),
+            "hidden_gate_passes": "each fused exchange hides one gate pass of %.2f ms inside its %.2f ms"
+                                  % (avg_launch_ms, r["fused_ms"] / fused) if fused else None}
+    return roofline
+
+
+# ---- other BASELINE configs (one GPU) ------------------------------------------------------------------
+def config1_leg():
+    """Config 1: 10-qubit random circuit, depth 20, QVMConnection.wavefunction -- and the reference itself on
+    the SAME program on this box's host (the one like-for-like ratio)."""
+    from referenceqvm.api import QVMConnection
+    n, depth = 10, 20
+    spec = circuit(n, depth)
+    prog = build_program(spec)
+    qvm = QVMConnection()
+    times = []
+    amps = None
+    for _ in range(30):
+        t0 = time.perf_counter()
+        wf, _ = qvm.wavefunction(prog)
+        amps = np.asarray(wf.amplitudes)
+        times.append(time.perf_counter() - t0)
+    best, med = min(times), statistics.median(times)
+    out = {"workload": "10-qubit random circuit depth 20 (200 gates), QVMConnection().wavefunction(program)",
+           "ms_per_call_best": 1e3 * best, "ms_per_call_median": 1e3 * med, "first_call_ms": 1e3 * times[0],
+           "gate_apps_per_s": len(spec) / med, "norm2_minus_1": float(np.vdot(amps, amps).real - 1.0),
+           "kernel_launches_per_call": qvm._engine.stats()["kernel_launches"] / 30.0}
+    if reference_staged():
+        with tempfile.TemporaryDirectory() as tmp:
+            path = os.path.join(tmp, "ref.npy")
+            d = run_reference_subprocess(n, depth, 1, out=path)
+            if d is not None:
+                ref = np.load(path)
+                out["reference"] = {"what": "the unmodified reference on the same program, same box, 1 core (it is serial)",
+                                    "ms_per_call": 1e3 * d["seconds"], "gate_apps_per_s": d["gate_apps_per_s"]}
+                out["max_abs_diff_vs_reference"] = float(np.max(np.abs(ref - amps)))
+                out["speedup_same_program"] = d["seconds"] / med
+    return out
+
+
+def config2_leg():
+    """Config 2: 14-qubit density matrix (4 GiB vectorised rho), T2 dephasing on every qubit after every instruction."""
+    from referenceqvm.api import QVMConnection
+    from referenceqvm.qvm_density import INFINITY, NoiseModel
+    from workloads import density_circuit_spec
+    n = 14
+    spec = density_circuit_spec(n, 4, SEED)
+    prog = build_program(spec)
+    nm = NoiseModel(T1=INFINITY, T2=30e-6, gate_time_1q=50e-9, gate_time_2q=150e-9, ro_fidelity=1.0)
+    qvm = QVMConnection(type_trans="density", noise_model=nm)
+    times, rho = [], None
+    for _ in range(4):
+        qvm._engine and qvm._engine.state.stats_reset()
+        t0 = time.perf_counter()
+        rho = qvm.density(prog)
+        qvm._engine.sync()
+        times.append(time.perf_counter() - t0)
+    st = qvm._engine.stats()
+    diag = np.asarray(rho.diagonal())
+    peak, _ = measured_peaks()
+    best = min(times[1:])
+    passes = st["hbm_passes"]
+    out = {"workload": "14-qubit density matrix (2^28 complex128 = 4 GiB), H on all qubits + random circuit depth 4 "
+                       "(70 instructions), T2 dephasing Kraus noise on every qubit after every instruction",
+           "ms_per_call": 1e3 * best, "ms_per_instruction": 1e3 * best / len(spec), "hbm_passes": passes,
+           "achieved_gbs": passes * 32.0 * 2 ** (2 * n) / best / 1e9,
+           "frac_of_hbm_peak": passes * 32.0 * 2 ** (2 * n) / best / 1e9 / peak,
+           "trace_minus_1": float(np.sum(diag).real - 1.0), "min_diag": float(np.min(diag.real))}
+    qvm._density = None
+    return out
+
+
+def config3_leg():
+    """Config 3: 28-qubit QFT (420 gates) + MEASURE all."""
+    from referenceqvm.api import QVMConnection
+    from workloads import qft_spec
+    n = 28
+    prog = build_program(qft_spec(n))
+    for q in range(n):
+        prog.measure(q, [q])
+    qvm = QVMConnection()
+    np.random.seed(1)
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        bits = qvm.run(prog, list(range(n)), trials=1)
+        times.append(time.perf_counter() - t0)
+    shots = 100000
+    qvm.run(prog, list(range(n)), trials=shots)
+    t0 = time.perf_counter()
+    res = np.asarray(qvm.run(prog, list(range(n)), trials=shots))
+    dt = time.perf_counter() - t0
+    passes = qvm._engine.stats()["hbm_passes"]
+    # QFT|0..0> is uniform: every marginal is 1/2 (5 sigma of 10^5 fair coins = 0.008)
+    marg = res.mean(axis=0)
+    out = {"workload": "28-qubit QFT (420 gates) + MEASURE of all 28 qubits, 4 GiB state",
+           "ms_per_trial_run": 1e3 * min(times[1:]), "bits_first_trial": bits[0][:8],
+           "shots": shots, "ms_run_%d_shots" % shots: 1e3 * dt,
+           "max_marginal_deviation_from_half": float(np.max(np.abs(marg - 0.5))),
+           "uniform_ok": bool(np.max(np.abs(marg - 0.5)) < 0.01)}
+    qvm.wf = None
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -205,141 +549,58 @@ def main():
     ap.add_argument("--ref-depth", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--config5-qubits", type=int, default=36, help="the extra leg on 8 GPUs (0: off)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference_arm(args, rank)
         return
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus %d needs torchrun (one rank per GPU)" % args.gpus)
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("--gpus %d needs torchrun (one rank per GPU)" % args.gpus)
 
-    import torch
-    from referenceqvm import _engine, _native, _sharded
-    from referenceqvm.api import QVMConnection
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    os.environ["QVM_B200_DEVICE"] = str(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        _sharded.enable(device=local_rank)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
+    h = Harness(args)
+    from referenceqvm import _native
     n, depth = args.qubits, args.depth
-    spec = circuit(n, depth)
-    prog = build_program(spec)
-    n_gates = len(spec)
 
-    qvm = QVMConnection()
-    qvm.device = local_rank
-    qvm.load_program(prog)
-    eng = qvm._fresh_engine()
-    from referenceqvm.unitary_generator import resolve_gate
-    ops = [_engine.compile_gate(*resolve_gate(qvm.gate_set, {}, ins)) for ins in prog]
-    stream = torch.cuda.ExternalStream(eng.state.stream_ptr(), device=local_rank)
-    sharded = world > 1
-    n_local = n - (world.bit_length() - 1)
+    # ---- e2e_cold FIRST: a program this process has never seen (its own seed), JIT cache of the process empty
+    e2e_cold = None
+    if not args.no_e2e:
+        from referenceqvm.api import QVMConnection
+        cold_spec = circuit(n, depth, seed=4321)
+        cold_prog = build_program(cold_spec)
+        cold_qvm = QVMConnection()
+        cold_qvm.device = h.local_rank
+        cold_qvm.load_program(cold_prog)
+        cold_qvm._fresh_engine()                  # the allocation (cudaMalloc of the state) is not what is measured
+        h.barrier()
+        t0 = time.perf_counter()
+        res = cold_qvm.run_and_measure(cold_prog, list(range(n)), trials=args.shots)
+        h.barrier()
+        dt = h.max_over_ranks(time.perf_counter() - t0)
+        assert len(res) == args.shots
+        del res
+        st = cold_qvm._engine.state.stats()
+        e2e_cold = {"value": len(cold_spec) / dt, "unit": METRIC, "ms": 1e3 * dt,
+                    "what": "first run_and_measure(program, all qubits, trials=%d) of a program never seen by this "
+                            "process (seed 4321; state already allocated): group structures are new, so passes "
+                            "run on the interpreter or wait for a first-sight compile" % args.shots,
+                    "specialised_launch_share": st["jit_launches"] / float(max(st["hbm_passes"], 1)),
+                    "breakdown_s": dict(cold_qvm.last_timing)}
+        if cold_qvm._engine is not None:
+            cold_qvm._engine.close()
+            cold_qvm._engine = None
+        _native.jit_wait()
 
-    def step():
-        eng.reset()
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for op in ops:
-            eng.queue(op)
-        eng.flush()
-        e1.record(stream)
-        return e0, e1
-
-    for _ in range(args.warmup):
-        step()
-    eng.sync()
-    # group structures that recur are compiled into specialised kernels on background threads
-    # (qvm_jit.h); the timed region measures the steady state, so wait for them once and run one more
-    # untimed step so that every rank is past its first specialised launches
-    _native.jit_wait()
-    if args.warmup:
-        step()
-        eng.sync()
-    barrier()
-
-    eng.state.stats_reset()
-    groups_before = eng.groups_launched
-    swaps_before = getattr(eng, "swaps", 0)
-    swap_bytes_before = getattr(eng, "swap_bytes", 0)
-    if sharded:
-        eng.timing = {"batch": [], "swap": []}
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    t_begin = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
-    t_begin.record(stream)
-    pairs = [step() for _ in range(args.steps)]
-    t_end.record(stream)
-    eng.sync()
-    barrier()
-    clocks = sampler.stop()
-    total_ms = max_over_ranks(t_begin.elapsed_time(t_end))
-    stats = eng.state.stats()
-    groups = eng.groups_launched - groups_before
-    swaps = getattr(eng, "swaps", 0) - swaps_before
-    swap_ms = 0.0
-    if sharded:
-        kernel_ms = sum(a.elapsed_time(b) for a, b in eng.timing["batch"])
-        swap_ms = sum(a.elapsed_time(b) for a, b in eng.timing["swap"])
-        eng.timing = None
-    else:
-        kernel_ms = sum(a.elapsed_time(b) for a, b in pairs)
+    r = timed_circuit(h, args, n, depth, args.steps, args.warmup)
+    eng, qvm, prog = r["eng"], r["qvm"], r["prog"]
+    n_gates, total_ms = r["n_gates"], r["total_ms"]
     ms_per_step = total_ms / args.steps
     value = n_gates * args.steps / (total_ms * 1e-3)
-
-    peak, peak_src = measured_peaks()
-    bytes_per_launch = 32.0 * 2 ** n_local
-    avg_launch_ms = kernel_ms / max(groups, 1)
-    achieved = bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
-    jit_share = stats.get("jit_launches", 0) / float(max(groups, 1))
-    dominant = ("spec_kernel (NVRTC-specialised regtile group)" if jit_share >= 0.5 else "regtile_kernel")
-    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_launch_ms,
-                "launches_per_step": groups / float(args.steps),
-                "gates_per_launch": n_gates * args.steps / float(max(groups, 1)),
-                "regtile_rounds_per_launch": stats.get("regtile_rounds", 0) / float(max(groups, 1)),
-                "specialised_launch_share": jit_share,
-                "effective_gbs": n_gates * args.steps * bytes_per_launch * world / (total_ms * 1e-3) / 1e9,
-                "note": "per GPU (rank 0): one launch = one read + one write of the local shard"}
-    ratio, ratio_src = measured_traffic_ratio()
-    if ratio is not None:
-        roofline["traffic"] = ratio * bytes_per_launch
-        roofline["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum = %.4f x algorithmic in %s, "
-                                      "scaled to this shard size" % (ratio, ratio_src))
-    if sharded and swaps:
-        swap_bytes = float(eng.swap_bytes - swap_bytes_before)      # sent (= received) per GPU, all exchanges
-        roofline["nvlink"] = {"bound": "nvlink", "achieved": swap_bytes / (swap_ms * 1e-3) / 1e9, "peak": 900.0,
-                              "unit": "GB/s per direction per GPU", "swaps_per_step": swaps / float(args.steps),
-                              "bytes_per_swap_per_direction": swap_bytes / swaps, "avg_swap_ms": swap_ms / swaps,
-                              "exchange": "one kernel over NVLink peer memory (CUDA IPC), several global qubits per "
-                                          "exchange" if getattr(eng, "p2p", False) else "staged NCCL send/recv",
-                              "share_of_step": swap_ms / (total_ms if total_ms else 1.0)}
-        roofline["nvlink"]["frac"] = roofline["nvlink"]["achieved"] / 900.0
+    roofline = roofline_of(h, r)
+    sharded = world > 1
 
     # ---- e2e: the call a user makes -----------------------------------------------------------
     e2e = None
@@ -347,55 +608,99 @@ def main():
         qubits = list(range(n))
         eng.state.stats_reset()
         qvm.run_and_measure(prog, qubits, trials=args.shots)          # warm (allocations, caches)
-        barrier()
+        h.barrier()
         eng2 = qvm._engine
         eng2.state.stats_reset()
         e2e_steps = max(1, min(args.steps, 3))
         dt = 0.0
+        parts = {}
         for _ in range(e2e_steps):
             # each call is timed on its own (barrier on both sides, max over ranks); the previous call's
             # result -- a million Python lists -- is released between the timed spans, not inside them
-            barrier()
+            h.barrier()
             t0 = time.perf_counter()
             res = qvm.run_and_measure(prog, qubits, trials=args.shots)
-            barrier()
-            dt += max_over_ranks(time.perf_counter() - t0)
+            h.barrier()
+            dt += h.max_over_ranks(time.perf_counter() - t0)
             assert len(res) == args.shots and len(res[0]) == n
             del res
+            for k, v in qvm.last_timing.items():
+                parts[k] = parts.get(k, 0.0) + v / e2e_steps
         s2 = eng2.state.stats()
         e2e = {"value": n_gates * e2e_steps / dt, "unit": METRIC,
                "h2d_bytes_per_step": s2["h2d_bytes"] / e2e_steps, "d2h_bytes_per_step": s2["d2h_bytes"] / e2e_steps,
                "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
-               "call": "QVMConnection().run_and_measure(program, qubits=all, trials=%d)" % args.shots}
+               "call": "QVMConnection().run_and_measure(program, qubits=all, trials=%d)" % args.shots,
+               "breakdown_s": dict(parts, note="rank 0, mean per call: program walk (load + classify + queue), plan + "
+                                               "launch + device time, CDF pass + %d draws, bits -> %d Python lists"
+                                               % (args.shots, args.shots))}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        v, dt, g, workers = cpu_reference_sample(args.ref_qubits, args.ref_depth)
-        cpu = {"value": v, "unit": METRIC, "cores": workers, "kind": "port",
-               "sample": "n=%d depth=%d random circuit (seed %d, %d gates, %.1f s), one independent copy on each of %d "
-                         "host cores: oracle restatement of the reference's sparse lifted-operator algorithm, which "
-                         "is serial (scipy.sparse)" % (args.ref_qubits, args.ref_depth, SEED, g, dt, workers)}
+        d, kind = cpu_reference_sample(args.ref_qubits, args.ref_depth)
+        cpu = {"value": d["gate_apps_per_s"], "unit": METRIC, "cores": d["copies"], "kind": kind,
+               "sample": sample_text(args.ref_qubits, args.ref_depth, d, kind)}
 
+    exchange_text = "single shard"
+    if sharded:
+        exchange_text = "top %d qubits select the GPU; %d global<->local exchanges per step (%s%s)" % (
+            world.bit_length() - 1, r["swaps"] // max(args.steps, 1), r["exchange"],
+            ", %d fused into gate passes" % (r["fused"] // max(args.steps, 1)) if r["fused"] else "")
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args), "qubits": n, "depth": depth, "gates_per_step": n_gates,
                    "l2_policy": "state (%.1f GiB) is far larger than the 126 MB L2" % (16.0 * 2 ** n / 2 ** 30),
-                   "tile_bits": eng.tile_bits, "low_bits": eng.low_bits,
+                   "tile_bits": r["tile_bits"], "low_bits": r["low_bits"],
                    "kernels": "recurring group structures run as NVRTC-specialised kernels (compiled in the background "
-                              "during warm-up, cached by structure); first sightings run the interpreted kernel",
-                   "sharding": ("top %d qubits select the GPU; %d global<->local exchanges per step (%s)"
-                                % (world.bit_length() - 1, swaps // max(args.steps, 1),
-                                   "peer-memory kernel over NVLink" if getattr(eng, "p2p", False) else "staged NCCL send/recv"))
-                   if sharded else "single shard"},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-        "gpu_launches": stats["kernel_launches"], "clocks": clocks,
+                              "during warm-up, cached by structure and on disk); first sightings run the interpreted "
+                              "kernel", "sharding": exchange_text},
+        "roofline": roofline, "check": r.get("check"), "cpu_baseline": cpu, "e2e": e2e, "e2e_cold": e2e_cold,
+        "gpu_launches": r["stats"]["kernel_launches"], "clocks": r["clocks"],
     }
+
+    # ---- the other BASELINE configs ---------------------------------------------------------------------
+    if not args.no_configs:
+        configs = {}
+        if world == 1:
+            for name, leg in (("config1_wavefunction_10q", config1_leg), ("config2_density_14q", config2_leg),
+                              ("config3_qft_28q", config3_leg)):
+                try:
+                    configs[name] = leg()
+                except Exception as exc:          # a leg must not cost the headline line
+                    configs[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        if world == 8 and args.config5_qubits and args.config5_qubits > n:
+            try:
+                eng.close()
+                qvm._engine = None
+                h.barrier()
+                n5 = args.config5_qubits
+                r5 = timed_circuit(h, args, n5, depth, 2, 2)
+                rf5 = roofline_of(h, r5)
+                q5 = r5["qvm"]
+                h.barrier()
+                t0 = time.perf_counter()
+                res = q5.run_and_measure(r5["prog"], list(range(n5)), trials=args.shots)
+                h.barrier()
+                dt5 = h.max_over_ranks(time.perf_counter() - t0)
+                ok = len(res) == args.shots and len(res[0]) == n5
+                del res
+                configs["config5_36q_8gpu"] = {
+                    "workload": "%d-qubit random circuit depth %d (%.0f GiB state, %.0f GiB per GPU), then "
+                                "run_and_measure with %d shots" % (n5, depth, 16.0 * 2 ** n5 / 2 ** 30,
+                                                                   16.0 * 2 ** r5["n_local"] / 2 ** 30, args.shots),
+                    "value": r5["n_gates"] * r5["steps"] / (r5["total_ms"] * 1e-3), "unit": METRIC,
+                    "ms_per_step": r5["total_ms"] / r5["steps"], "roofline": rf5, "check": r5.get("check"),
+                    "run_and_measure_s": dt5, "shots_ok": bool(ok)}
+            except Exception as exc:
+                configs["config5_36q_8gpu"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        line["configs"] = configs
+
     if rank == 0:
         print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    if h.dist is not None:
+        h.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

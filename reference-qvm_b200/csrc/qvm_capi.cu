@@ -1148,8 +1148,22 @@ int qvm_probs_prepare(qvm_t* q, int mode, int n_rho, double* total) {
     const int grid = grid_for(q, n_blocks * 32, threads, 16);
     sample_block_sums_kernel<<<grid, threads, 0, q->stream>>>(q->amps, n_probs, mode, n_rho, row_base, q->cdf, n_blocks);
     QVM_CUDA(q, cudaGetLastError());
-    scan_inclusive_kernel<<<1, 1024, 0, q->stream>>>(q->cdf, n_blocks, q->total_dev);
-    QVM_CUDA(q, cudaGetLastError());
+    if (n_blocks <= (uint64_t)kScanChunk) {
+        scan_inclusive_kernel<<<1, 1024, 0, q->stream>>>(q->cdf, n_blocks, q->total_dev);
+        QVM_CUDA(q, cudaGetLastError());
+    } else {
+        // long CDFs (>= 24 qubits): chunk totals -> scan of the totals -> every chunk scans itself
+        const uint64_t n_chunks = (n_blocks + kScanChunk - 1) / kScanChunk;
+        double* chunk_tot = nullptr;
+        QVM_CUDA(q, cudaMallocAsync(&chunk_tot, n_chunks * sizeof(double), q->stream));
+        scan_chunk_totals_kernel<<<(unsigned)n_chunks, kScanThreads, 0, q->stream>>>(q->cdf, n_blocks, chunk_tot);
+        scan_inclusive_kernel<<<1, 1024, 0, q->stream>>>(chunk_tot, n_chunks, q->total_dev);
+        scan_chunks_kernel<<<(unsigned)n_chunks, kScanThreads, 0, q->stream>>>(q->cdf, n_blocks, chunk_tot);
+        const cudaError_t e = cudaGetLastError();
+        cudaFreeAsync(chunk_tot, q->stream);
+        QVM_CUDA(q, e);
+        q->stats.kernel_launches += 2;
+    }
     QVM_CUDA(q, cudaMemcpyAsync(q->result_host, q->total_dev, sizeof(double), cudaMemcpyDeviceToHost, q->stream));
     QVM_CUDA(q, cudaStreamSynchronize(q->stream));
     if (total) *total = q->result_host[0];
@@ -1172,28 +1186,34 @@ int qvm_sample(qvm_t* q, uint64_t n_shots, const double* uniforms, uint64_t* out
     double* u_dev = nullptr;
     unsigned long long* idx_dev = nullptr;
     const uint64_t chunk = 1ull << 22;
-    QVM_CUDA(q, cudaMallocAsync(&u_dev, std::min(n_shots, chunk) * 8, q->stream));
-    QVM_CUDA(q, cudaMallocAsync(&idx_dev, std::min(n_shots, chunk) * 8, q->stream));
     int rc = ensure_stage(q, std::min<uint64_t>(n_shots, chunk) * 8);
     if (rc) return rc;
-    for (uint64_t done = 0; done < n_shots; done += chunk) {
+    QVM_CUDA(q, cudaMallocAsync(&u_dev, std::min(n_shots, chunk) * 8, q->stream));
+    cudaError_t err = cudaMallocAsync(&idx_dev, std::min(n_shots, chunk) * 8, q->stream);
+    // (from here on every exit path releases the two scratch allocations)
+    for (uint64_t done = 0; err == cudaSuccess && done < n_shots; done += chunk) {
         const uint64_t n = std::min(chunk, n_shots - done);
         memcpy(q->stage, uniforms + done, n * 8);
-        QVM_CUDA(q, cudaMemcpyAsync(u_dev, q->stage, n * 8, cudaMemcpyHostToDevice, q->stream));
+        err = cudaMemcpyAsync(u_dev, q->stage, n * 8, cudaMemcpyHostToDevice, q->stream);
+        if (err != cudaSuccess) break;
         const int threads = 128;
         const int grid = grid_for(q, n * 32, threads, 16);
         sample_kernel<<<grid, threads, 0, q->stream>>>(q->amps, q->sample_n_probs, q->sample_mode, q->sample_n_rho,
                                                        row_base, q->cdf, q->cdf_blocks, q->total_dev, u_dev, n, idx_dev);
-        QVM_CUDA(q, cudaGetLastError());
-        QVM_CUDA(q, cudaMemcpyAsync(q->stage, idx_dev, n * 8, cudaMemcpyDeviceToHost, q->stream));
-        QVM_CUDA(q, cudaStreamSynchronize(q->stream));
+        if ((err = cudaGetLastError()) != cudaSuccess) break;
+        if ((err = cudaMemcpyAsync(q->stage, idx_dev, n * 8, cudaMemcpyDeviceToHost, q->stream)) != cudaSuccess) break;
+        if ((err = cudaStreamSynchronize(q->stream)) != cudaSuccess) break;
         memcpy(out_index + done, q->stage, n * 8);
         q->stats.kernel_launches += 1;
         q->stats.h2d_bytes += n * 8;
         q->stats.d2h_bytes += n * 8;
     }
-    cudaFreeAsync(u_dev, q->stream);
-    cudaFreeAsync(idx_dev, q->stream);
+    if (u_dev) cudaFreeAsync(u_dev, q->stream);
+    if (idx_dev) cudaFreeAsync(idx_dev, q->stream);
+    if (err != cudaSuccess) {
+        q->sticky = QVM_ERR_CUDA;
+        return fail(QVM_ERR_CUDA, "qvm_sample: %s", cudaGetErrorString(err));
+    }
     return QVM_OK;
 }
 

@@ -562,6 +562,51 @@ __global__ void scan_inclusive_kernel(double* __restrict__ v, uint64_t n, double
     }
 }
 
+// Three-phase scan for long arrays (33 qubits: 2^22 block sums): chunks of kScanChunk entries, one CTA
+// each.  (1) chunk totals, (2) the single-block scan above over the (few) totals, (3) every chunk scans
+// itself and adds its offset.  Each thread owns kScanPerThread consecutive entries and sums them in
+// order, thread totals are added in thread order, chunk offsets in chunk order: a fixed association,
+// so results are deterministic to the last bit, and all global accesses are full 128-byte lines.
+constexpr int kScanThreads = 256;
+constexpr int kScanPerThread = 16;
+constexpr int kScanChunk = kScanThreads * kScanPerThread;
+__device__ __forceinline__ double scan_thread_load(const double* __restrict__ v, uint64_t n, uint64_t base,
+                                                   double (&x)[kScanPerThread]) {
+    double run = 0.0;
+#pragma unroll
+    for (int j = 0; j < kScanPerThread; ++j) {
+        x[j] = base + j < n ? v[base + j] : 0.0;
+        run += x[j];
+        x[j] = run;                       // inclusive within the thread
+    }
+    return run;
+}
+__global__ void __launch_bounds__(kScanThreads) scan_chunk_totals_kernel(const double* __restrict__ v, uint64_t n,
+                                                                         double* __restrict__ chunk_tot) {
+    __shared__ double tot[kScanThreads];
+    double x[kScanPerThread];
+    tot[threadIdx.x] = scan_thread_load(v, n, (uint64_t)blockIdx.x * kScanChunk + threadIdx.x * kScanPerThread, x);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double run = 0.0;
+        for (int i = 0; i < kScanThreads; ++i) run += tot[i];
+        chunk_tot[blockIdx.x] = run;
+    }
+}
+__global__ void __launch_bounds__(kScanThreads) scan_chunks_kernel(double* __restrict__ v, uint64_t n,
+                                                                   const double* __restrict__ chunk_cdf) {
+    __shared__ double tot[kScanThreads];
+    double x[kScanPerThread];
+    const uint64_t base = (uint64_t)blockIdx.x * kScanChunk + threadIdx.x * kScanPerThread;
+    tot[threadIdx.x] = scan_thread_load(v, n, base, x);
+    __syncthreads();
+    double before = blockIdx.x ? chunk_cdf[blockIdx.x - 1] : 0.0;      // everything in earlier chunks ...
+    for (int i = 0; i < (int)threadIdx.x; ++i) before += tot[i];        // ... and in earlier threads of this one
+#pragma unroll
+    for (int j = 0; j < kScanPerThread; ++j)
+        if (base + j < n) v[base + j] = before + x[j];
+}
+
 // One warp per shot.  target = u * total; block = first b with cdf[b] > target; then walk the block.
 __global__ void sample_kernel(const double2* __restrict__ state, uint64_t n_probs, int mode, int n_rho,
                               uint64_t row_base, const double* __restrict__ block_cdf, uint64_t n_blocks,

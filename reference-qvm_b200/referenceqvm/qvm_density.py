@@ -65,16 +65,31 @@ def kraus_superoperator(operators):
 
 class DeviceDensity(object):
     """rho resident on the device, quacking enough like the reference's ``csc_matrix`` result
-    (``.todense()``, ``.toarray()``, ``.diagonal()``, ``[i, j]``, ``.shape``)."""
+    (``.todense()``, ``.toarray()``, ``.diagonal()``, ``[i, j]``, ``.shape``).
 
-    def __init__(self, state, num_qubits):
+    Two flavours.  ``density()`` and ``apply_kraus()`` hand out SNAPSHOTS that own their buffer (the
+    reference returns an independent matrix from every call, qvm_density.py:391-394): later calls on
+    the QVM do not change them.  The ``_density`` attribute is a live VIEW of the QVM's buffer (the
+    reference's attribute is the QVM's own matrix too): it flushes the engine's queued gates before
+    every read, follows the QVM as it runs, and raises once the QVM has dropped that buffer."""
+
+    def __init__(self, state, num_qubits, engine=None):
         self._state = state               # _native.DeviceState holding the 2n-qubit vector
+        self._engine = engine             # live view: flush pending gates / restore the layout before reading
         self.num_qubits = num_qubits
         dim = 1 << num_qubits
         self.shape = (dim, dim)
         self.dtype = np.dtype(np.complex128)
 
+    def _sync_view(self):
+        if self._engine is not None:
+            if self._engine.state is not self._state:
+                raise RuntimeError("this view of the QVM's density matrix is stale: the QVM has since replaced its "
+                                   "state (density() returns independent snapshots)")
+            self._engine.restore_layout()
+
     def toarray(self):
+        self._sync_view()
         return self._state.get_state().reshape(self.shape)
 
     def todense(self):
@@ -85,6 +100,7 @@ class DeviceDensity(object):
         return sps.csc_matrix(self.toarray())
 
     def diagonal(self):
+        self._sync_view()
         dim = self.shape[0]
         return self._state.get_strided(0, dim + 1, dim)
 
@@ -95,6 +111,7 @@ class DeviceDensity(object):
         i, j = key
         dim = self.shape[0]
         i, j = int(i) % dim, int(j) % dim
+        self._sync_view()
         return self._state.get_state(i * dim + j, 1)[0]
 
     def __array__(self, dtype=None, copy=None):
@@ -134,8 +151,7 @@ class QVM_Density(QAM):
     def _density(self):
         if self._engine is None:
             return None
-        self._engine.restore_layout()
-        return DeviceDensity(self._engine.state, self._engine.n // 2)
+        return DeviceDensity(self._engine.state, self._engine.n // 2, engine=self._engine)
 
     @_density.setter
     def _density(self, value):
@@ -310,10 +326,13 @@ class QVM_Density(QAM):
 
     def density(self, pyquil_program):
         """Density matrix of a program (starts from |0..0><0..0|)."""
+        self._simulate_density(pyquil_program)
+        return DeviceDensity(self._engine.clone_state(), self.num_qubits)       # an independent snapshot
+
+    def _simulate_density(self, pyquil_program):
         self.load_program(pyquil_program)
         self._engine_for(self.num_qubits).reset()
         self.kernel()
-        return self._density
 
     def expectation(self, pyquil_program, operator_programs=[Program()]):
         raise NotImplementedError()
@@ -322,7 +341,7 @@ class QVM_Density(QAM):
         """Re-simulates per trial and returns the classical memory slices (numpy bool arrays)."""
         results = []
         for _ in range(trials):
-            self.density(pyquil_program)
+            self._simulate_density(pyquil_program)
             results.append(self.classical_memory[classical_addresses])
         return list(results)
 
@@ -331,7 +350,7 @@ class QVM_Density(QAM):
 
         Uses the uniforms numpy's ``np.random.choice(p=)`` would consume (reference :445-447), so a
         seeded call returns the reference's draws; bitstrings are big-endian (:449-451)."""
-        self.density(pyquil_program)
+        self._simulate_density(pyquil_program)
         n = self.num_qubits
         uniforms = np.random.random_sample(trials)
         indices, total = self._engine.sample(uniforms, mode=1, n_rho=n)

@@ -15,9 +15,14 @@ happens:
   that is provably equivalent to sampling one final state (no MEASURE in the program, or a purely
   terminal block of MEASUREs and no control flow) the program is simulated once and the trials
   are drawn by the prefix-sum + binary-search kernel; otherwise the per-trial loop is kept.
+  The sampling fast path draws ONE uniform per trial (the reference: one per MEASURE per trial), so
+  its results are distributed like the reference's but are not its seeded stream, and ``self.wf``
+  afterwards is the un-collapsed final state; draw-for-draw parity with a seeded reference holds on
+  the per-trial and batched paths (``sampling_fast_path = False`` forces them).
 """
 import gc
 import os
+import time
 
 import numpy as np
 
@@ -80,6 +85,7 @@ class QVM_Wavefunction(QAM):
         self.device = int(os.environ.get("QVM_B200_DEVICE", "0"))
         #: set False to force the reference's per-trial re-simulation in run()/run_and_measure()
         self.sampling_fast_path = True
+        self.last_timing = {}
         #: SWAP gates are not executed: they exchange two entries of this program-qubit -> engine-qubit
         #: table, and later instructions are routed through it.  The table is undone (with real SWAPs)
         #: only when amplitudes are read back; MEASURE and sampling just look bits up through it.
@@ -174,7 +180,11 @@ class QVM_Wavefunction(QAM):
         handed to the engine as one request: the same uniforms are drawn in the same order and the same
         sequential decisions are taken, but on the joint distribution of the measured bits -- one pass
         over the state per chunk of qubits instead of two per qubit.  ``transition`` stays single-step."""
-        fused = hasattr(self._engine, "measure_many")
+        # (a subclass that overrides a hook or a transition sees every MEASURE one by one, as in the reference)
+        cls = type(self)
+        fused = hasattr(self._engine, "measure_many") and all(
+            getattr(cls, name) is getattr(QVM_Wavefunction, name)
+            for name in ("pre", "post", "transition", "_transition", "measurement"))
         while self.program_counter < len(self.program):
             instruction = self.current_instruction()
             if fused and isinstance(instruction, Measurement):
@@ -294,6 +304,7 @@ class QVM_Wavefunction(QAM):
     #: trials of more than 2^BATCH_MAX_QUBITS amplitudes keep the per-trial loop
     BATCH_BITS = 26
     BATCH_MAX_QUBITS = 20
+    BATCH_MAX_TRIAL_BITS = 20
 
     def _batchable(self, program):
         """run(trials) can execute all trials side by side when every trial walks the same instruction
@@ -320,7 +331,9 @@ class QVM_Wavefunction(QAM):
         instrs = list(pyquil_program)
         n_meas = sum(1 for i in instrs if isinstance(i, Measurement))
         uniforms = np.random.random_sample(trials * n_meas).reshape(trials, n_meas)
-        t_bits = max(0, min((trials - 1).bit_length(), self.BATCH_BITS - n))
+        # at most 2^20 trial segments per batch (one CUDA block each: qvm_measure_batched's limit); more
+        # trials simply take more batches
+        t_bits = max(0, min((trials - 1).bit_length(), self.BATCH_BITS - n, self.BATCH_MAX_TRIAL_BITS))
         cap = 1 << t_bits
         memory = np.repeat(self.classical_memory[None, :], trials, axis=0)
         eng = _engine.Engine(n + t_bits, device=self.device)
@@ -406,13 +419,22 @@ class QVM_Wavefunction(QAM):
 
         deterministic = not any(isinstance(i, Measurement) for i in pyquil_program)
         if self.sampling_fast_path and deterministic and trials > 1 and len(qubits) > 0:
+            t0 = time.perf_counter()
             self._simulate(pyquil_program, None)
+            t1 = time.perf_counter()
+            self._engine.sync()
+            t2 = time.perf_counter()
             indices, _ = self._engine.sample(np.random.random_sample(trials), physical=True)
+            t3 = time.perf_counter()
             bits = _index_bits(indices, self.num_qubits)
             # column num_qubits is never set: it stands in for qubits beyond the register
             sel = [self._engine.position(self._virt[q]) if 0 <= q < self.num_qubits else self.num_qubits
                    for q in qubits]
-            return _rows_to_lists(np.take(bits, sel, axis=1))
+            out = _rows_to_lists(np.take(bits, sel, axis=1))
+            #: where the last call's wall time went (bench.py reports it as e2e.breakdown)
+            self.last_timing = {"program_walk_s": t1 - t0, "plan_launch_sync_s": t2 - t1, "cdf_and_draws_s": t3 - t2,
+                                "bits_to_lists_s": time.perf_counter() - t3}
+            return out
 
         results = []
         for _ in range(trials):

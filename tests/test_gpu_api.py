@@ -615,3 +615,80 @@ def test_runs_of_measures_are_fused_and_keep_the_seeded_stream(qvm):
     assert nxt == rng.random_sample()
     assert np.max(np.abs(wf.amplitudes - want)) < TOL
     assert qvm._engine.stats()["hbm_passes"] < 2 * (n + 3)          # fused: far fewer than two passes per MEASURE
+
+
+# ---- round-2 review items --------------------------------------------------------------------------------
+def test_batched_run_with_more_than_2_pow_20_trials(qvm):
+    """run() on a tiny program with a mid-circuit MEASURE and more than 2^20 trials: more batches, not an error
+    (the batched MEASURE kernel takes at most 2^20 trial segments per launch)."""
+    prog = Program().inst(H(0)).measure(0, [0]).inst(CNOT(0, 1)).measure(1, [1])
+    trials = (1 << 20) + 1
+    np.random.seed(5)
+    got = np.asarray(qvm.run(prog, [0, 1], trials=trials))
+    assert got.shape == (trials, 2)
+    assert np.array_equal(got[:, 0], got[:, 1])                 # CNOT copies the measured bit
+    assert abs(got[:, 0].mean() - 0.5) < 0.005
+
+
+def test_density_returns_independent_snapshots():
+    """density() hands out snapshots (the reference returns a fresh matrix per call); the `_density` attribute
+    is a live view that follows the QVM and goes stale with an error when the QVM replaces its state."""
+    qvm = QVMConnection(type_trans="density")
+    rho_a = qvm.density(Program().inst(H(0)).inst(CNOT(0, 1)))
+    a = np.array(rho_a.todense())
+    rho_b = qvm.density(Program().inst(X(0)).inst(I(1)))
+    assert np.allclose(np.array(rho_a.todense()), a)            # untouched by the second call
+    assert abs(np.array(rho_b.todense())[1, 1] - 1.0) < 1e-15
+    view = qvm._density
+    assert abs(view[1, 1] - 1.0) < 1e-15
+    qvm.density(Program().inst(X(0)).inst(X(1)).inst(I(2)))      # other size: the old buffer is gone
+    with pytest.raises(RuntimeError):
+        view.toarray()
+
+
+def test_subclass_hooks_see_every_measure():
+    """A subclass that overrides a hook is called around every instruction, MEASURE runs included (the
+    fused joint-distribution path is only taken for the base class)."""
+    from referenceqvm.qvm_wavefunction import QVM_Wavefunction
+
+    class Counting(QVM_Wavefunction):
+        calls = 0
+
+        def post(self):
+            Counting.calls += 1
+
+    n = 12
+    prog = Program()
+    for q in range(n):
+        prog.inst(H(q))
+    for q in range(n):
+        prog.measure(q, [q])
+    qvm = Counting(gate_set=G.gate_matrix)
+    qvm.wavefunction(prog, list(range(n)))
+    assert Counting.calls == 2 * n
+
+
+def test_sampling_cdf_scan_long_arrays_matches_numpy():
+    """The three-phase CDF scan (arrays longer than one chunk of 4096 block sums: >= 24 qubits) against
+    numpy's inverse CDF on the same probabilities."""
+    from referenceqvm import _engine
+    n = 24
+    eng = _engine.Engine(n)
+    try:
+        eng.reset()
+        rs = np.random.RandomState(3)
+        for q in range(n):
+            eng.queue_matrix(G.RY(float(rs.uniform(0.2, 2.9))), [q])
+        eng.flush()
+        probs = np.abs(eng.amplitudes()) ** 2
+        u = rs.random_sample(20000)
+        idx, total = eng.sample(u, physical=True)
+        assert abs(total - 1.0) < 1e-12
+        phys = np.arange(1 << n, dtype=np.int64)
+        logical = np.zeros_like(phys)
+        for q, p in enumerate(eng.pos_of):
+            logical |= ((phys >> p) & 1) << q
+        ref = np.asarray(orc.inverse_cdf_sample(probs[logical], u), dtype=np.int64)      # CDF in HBM order
+        assert np.mean(idx.astype(np.int64) == ref) > 0.999
+    finally:
+        eng.close()

@@ -41,3 +41,22 @@ def qft_spec(num_qubits):
     for q in range(n // 2):
         spec.append(("SWAP", [], [q, n - 1 - q]))
     return spec
+
+
+def density_circuit_spec(num_qubits, depth, seed):
+    """BASELINE config 2: H on every qubit, then the random generator at ``depth``; run
+    under NoiseModel(T1=INFINITY, T2=30e-6, gate_time_1q=50e-9, gate_time_2q=150e-9, ro_fidelity=1.0)."""
+    return [("H", [], [q]) for q in range(num_qubits)] + random_circuit_spec(num_qubits, depth, seed)
+
+
+def inverse_spec(spec):
+    """The adjoint circuit of a spec made of H / RZ / CNOT / CPHASE / SWAP (bench.py's U^dagger check)."""
+    out = []
+    for name, params, qubits in reversed(spec):
+        if name in ("H", "CNOT", "SWAP", "X", "Z", "CZ"):
+            out.append((name, list(params), list(qubits)))
+        elif name in ("RZ", "CPHASE", "RX", "RY", "PHASE"):
+            out.append((name, [-float(params[0])], list(qubits)))
+        else:
+            raise ValueError("no inverse rule for %s" % name)
+    return out
