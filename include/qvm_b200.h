@@ -33,6 +33,7 @@ extern "C" {
 #endif
 
 typedef struct qvm_state qvm_t;
+typedef struct qvm_plan qvm_plan_t;      /* a compiled program: the launches of one flush, kept for replay */
 
 #define QVM_OK               0
 #define QVM_ERR_INVALID     -1   /* bad argument (maps to ValueError / TypeError on the host)  */
@@ -69,6 +70,7 @@ typedef struct qvm_stats {
     uint64_t jit_compiles;                /* group structures submitted for compilation (process)  */
     uint64_t push_launches;               /* stand-alone out-of-place exchange passes (qvm_exchange_push) */
     uint64_t fused_push_launches;         /* gate passes whose stores WERE the exchange (qvm_apply_group_push) */
+    uint64_t graph_launches;              /* compiled programs replayed as one CUDA graph launch (qvm_plan_run) */
 } qvm_stats_t;
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
@@ -159,6 +161,24 @@ int qvm_apply_group(qvm_t* q, int n_tile, const int32_t* tile_bits, int n_ops, c
 int qvm_apply_group_relabel(qvm_t* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops,
                             const double* mats, uint64_t mats_entries, int n_low, int n_bring,
                             const int32_t* bring_low, int32_t* new_pos);
+
+/* ---- compiled programs (the caller side of qam.py:61-107 / :168-181: the reference re-walks, re-builds and
+ * re-multiplies every operator on every call; here a program's gate stream is classified, fused, planned and
+ * encoded ONCE) ------------------------------------------------------------------------------------------ */
+/* Between qvm_record_begin and qvm_record_end every group launched on the handle (qvm_apply_group /
+ * qvm_apply_group_relabel) is executed as usual AND kept, with everything a launch needs: the encoded round
+ * plan, the specialised source and its launch-time factors.  qvm_record_end hands the recording over as a plan
+ * (plan == NULL: discard it).  qvm_plan_run replays the launches in order on the handle's current state
+ * (reset_first != 0: preceded by the reset to |0...0>): each group runs its specialised kernel as soon as
+ * that is compiled, its interpreted form until then.  Once every group has its kernel and the plan has been
+ * run a few times, the sequence is captured into a CUDA graph and a run costs one cudaGraphLaunch
+ * (QVM_B200_GRAPHS=0 turns that off).  A plan is bound to the shard shape it was recorded on; the layout it
+ * leaves the qubits in is what the caller observed while recording.  Exchanges cannot be recorded. */
+int qvm_record_begin(qvm_t* q);
+int qvm_record_end(qvm_t* q, qvm_plan_t** plan);
+int qvm_plan_run(qvm_t* q, qvm_plan_t* plan, int reset_first);
+int qvm_plan_launches(const qvm_plan_t* plan);
+int qvm_plan_destroy(qvm_plan_t* plan);
 
 /* rho[i,j] *= f^popcount((i xor j) & mask) on a 2n-qubit vectorised rho (n = n_total/2): the fused
  * form of `dephasing` Kraus pairs on every qubit in `mask` (qvm_density.py:298-313, :350-361). */

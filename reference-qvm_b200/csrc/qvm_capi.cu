@@ -38,6 +38,35 @@ constexpr int kReduceThreads = 256;
 
 }  // namespace
 
+// One fused group ready to launch (see build_rec / launch_rec below).
+enum { REC_NONE = 0, REC_REGTILE = 1, REC_TILE = 2 };
+struct LaunchRec {
+    int kind = REC_NONE;              // nothing to run | register-tiled (interpreter and / or specialised) | shared-memory kernel
+    EncodedGroup g;                   // REC_REGTILE: what the interpreter reads
+    bool has_spec = false;            // ... and, when the generator covers the group, its specialised form
+    SpecSource spec;
+    const CompiledSpec* cs = nullptr; // resolved lazily (compiled kernels live as long as the process)
+    TileParams tp{};                  // REC_TILE
+    std::vector<DevOp> dev;
+    std::vector<double> mats;
+    uint64_t executed = 0;
+    uint64_t tile_mask = 0;
+};
+
+// A compiled program: the launches of one flush, kept for replay (qvm_record_begin / qvm_plan_run).
+struct qvm_plan {
+    int n_local = 0, n_global = 0;
+    uint64_t shard_index = 0;
+    std::vector<LaunchRec> recs;
+    cudaGraphExec_t graph = nullptr;  // the whole sequence as ONE graph launch once every group has its kernel
+    double2* graph_amps = nullptr;    // buffer the graph was captured on
+    int graph_reset = 0;
+    qvm_stats_t graph_stats{};        // what one graph launch adds to the handle's counters
+    bool all_specialised = false;     // the last plain replay used a specialised kernel for every group
+    bool graph_failed = false;
+    uint64_t runs = 0;
+};
+
 struct qvm_state {
     int device = 0;
     int n_local = 0;
@@ -78,8 +107,8 @@ struct qvm_state {
     int measure_grid = 0;
     qvm_stats_t stats{};
     uint64_t opc_hist[32] = {};
-    EncodedGroup enc;                 // scratch of the register-tile encoder (reused across launches)
-    SpecSource spec;                  // scratch of the specialised-kernel generator
+    LaunchRec rec;                    // scratch: the group being built / launched (reused across launches)
+    qvm_plan* recording = nullptr;    // non-null between qvm_record_begin and qvm_record_end
     int jit_policy = 1;               // 0 never, 1 compile a group structure at its second sighting, 2 at once
 };
 
@@ -273,21 +302,21 @@ struct RelabelReq {
     uint8_t sigma[16] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15};
 };
 
-int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops,
-                         const double* mats, uint64_t mats_entries, bool* handled, RelabelReq* relabel,
-                         const PushSpec* push, bool* pushed);
-
-// Encode ops in tile-local coordinates and launch one tile kernel.  With `push` (a fused exchange, see
-// PushSpec) the register-tiled kernels store the pass straight into the destination shards and *pushed
-// is set; when the group cannot carry it (no launch needed, shared-memory fallback kernel, victim bit
-// inside the tile) the pass runs in place and the caller pushes separately.
-int launch_group(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops, const double* mats,
-                 uint64_t mats_entries, RelabelReq* relabel = nullptr, const PushSpec* push = nullptr,
-                 bool* pushed = nullptr) {
+// ---- one fused group, ready to launch (and to launch again: compiled programs replay these) -----------
+// build_rec() does everything that depends only on the group -- validation, tile-local encoding, the
+// round plan, the specialised source -- and launch_rec() everything that touches the device: pick the
+// specialised kernel when it is ready (else the interpreter), upload, launch.
+int build_rec(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops, const double* mats,
+              uint64_t mats_entries, RelabelReq* relabel, LaunchRec& rec) {
+    rec.kind = REC_NONE;
+    rec.has_spec = false;
+    rec.cs = nullptr;
+    rec.tile_mask = 0;
     if (n_tile < 0 || n_tile > q->n_local || n_tile > QVM_MAX_TILE_BITS)
         return fail(QVM_ERR_INVALID, "tile of %d bits is outside [0, min(n_local=%d, %d)]", n_tile, q->n_local,
                     QVM_MAX_TILE_BITS);
-    TileParams P{};
+    TileParams& P = rec.tp;
+    P = TileParams{};
     P.n_local = q->n_local;
     P.k = n_tile;
     P.shard_bits = q->shard_index << q->n_local;
@@ -301,6 +330,7 @@ int launch_group(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, 
         P.tile_mask |= 1ull << p;
         local_of[p] = (int8_t)j;
     }
+    rec.tile_mask = P.tile_mask;
     int low = 0;
     while (low < n_tile && tile_bits[low] == low) ++low;
     // keep the offset table small: at most 2^8 entries come from the high part
@@ -308,18 +338,29 @@ int launch_group(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, 
     P.low = low;
 
     if (q->use_regtile) {
-        bool handled = false;
-        if (push && push->m && (P.tile_mask & push->mask)) push = nullptr;     // a victim bit inside the tile: not fusable
-        int rc2 = launch_group_regtile(q, n_tile, tile_bits, n_ops, ops, mats, mats_entries, &handled, relabel, push,
-                                       pushed);
-        if (rc2 != QVM_OK || handled) return rc2;
+        EncodedGroup& g = rec.g;
+        const int erc = encode_group(q->n_local, q->n_global, q->shard_index, n_tile, tile_bits, n_ops, ops, mats,
+                                     mats_entries, g, q->reg_bits, relabel ? relabel->low_in : 0u, relabel ? relabel->n_low : 0);
+        if (erc == ENC_ERROR) return fail(QVM_ERR_CUDA, "round planner made no progress");
+        if (erc == ENC_OK) {
+            if (relabel) memcpy(relabel->sigma, g.sigma, sizeof(g.sigma));
+            if (g.cold.empty() && !g.relabelled) return QVM_OK;        // nothing to run
+            if (g.n_tiles > 0x7fffffffull) return fail(QVM_ERR_UNSUPPORTED, "too many tiles for one launch");
+            for (int i = 0; i < 32; ++i) q->opc_hist[i] += g.opc_hist[i];
+            rec.kind = REC_REGTILE;
+            // a structure that comes back runs as a specialised straight-line kernel (qvm_jit.h)
+            rec.has_spec = !g.need_full && g.P.R == 4 && generate_spec(g, rec.spec);
+            return QVM_OK;
+        }
+        // ENC_FALLBACK: the shared-memory kernel below (or its error) handles it
     }
-    // (the shared-memory kernel below never relabels: relabel->sigma is still the identity)
+    // (the shared-memory kernel never relabels: relabel->sigma is still the identity)
 
-    std::vector<DevOp> dev;
+    std::vector<DevOp>& dev = rec.dev;
+    dev.clear();
     dev.reserve(n_ops);
     const int npos = total_positions(q);
-    uint64_t executed = 0;
+    rec.executed = 0;
     for (int i = 0; i < n_ops; ++i) {
         const qvm_op_t& op = ops[i];
         if (op.kind == QVM_OP_NOP) continue;
@@ -360,40 +401,18 @@ int launch_group(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, 
             d.nfix = (uint8_t)nf;
         }
         dev.push_back(d);
-        ++executed;
+        ++rec.executed;
     }
     if (dev.empty()) return QVM_OK;
-
-    const size_t ops_bytes = dev.size() * sizeof(DevOp);
-    const size_t mats_bytes = (size_t)mats_entries * sizeof(double2);
-    const size_t ops_pad = (ops_bytes + 255) & ~(size_t)255;
-    size_t off = 0;
-    int rc = ring_alloc(q, ops_pad + mats_bytes, &off);
-    if (rc) return rc;
-    memcpy(q->ring_host + off, dev.data(), ops_bytes);
-    memcpy(q->ring_host + off + ops_pad, mats, mats_bytes);
-    QVM_CUDA(q, cudaMemcpyAsync(q->ring_dev + off, q->ring_host + off, ops_pad + mats_bytes, cudaMemcpyHostToDevice,
-                                q->stream));
+    rec.mats.assign(mats, mats + 2 * mats_entries);
     P.n_ops = (int)dev.size();
-    P.ops = reinterpret_cast<const DevOp*>(q->ring_dev + off);
-    P.mats = reinterpret_cast<const double2*>(q->ring_dev + off + ops_pad);
-
     const size_t smem = tile_smem_bytes(P.k, P.low, P.n_ops);
     if (smem > 227 * 1024) return fail(QVM_ERR_UNSUPPORTED, "group needs %zu bytes of shared memory (> 227 KiB)", smem);
-    const uint64_t n_tiles = q->n_elems >> n_tile;
-    if (n_tiles > 0x7fffffffull) return fail(QVM_ERR_UNSUPPORTED, "too many tiles for one launch");
-    tile_kernel<<<(unsigned)n_tiles, kTileThreads, smem, q->stream>>>(q->amps, P);
-    QVM_CUDA(q, cudaGetLastError());
-    q->stats.kernel_launches += 1;
-    q->stats.gate_ops += executed;
-    q->stats.hbm_passes += 1;
-    q->stats.hbm_bytes += 32ull * q->n_elems;
-    q->stats.h2d_bytes += ops_pad + mats_bytes;
+    if ((q->n_elems >> n_tile) > 0x7fffffffull) return fail(QVM_ERR_UNSUPPORTED, "too many tiles for one launch");
+    rec.kind = REC_TILE;
     return QVM_OK;
 }
 
-
-// ---- register-tiled path: encode (qvm_encode.h), upload, launch ------------------------------------
 template <int T, int B, bool FULL, int R>
 int launch_regtile(qvm_state* q, unsigned grid, unsigned threads, size_t smem, const RegTileParams& P) {
     static bool attr_set[64] = {};
@@ -407,29 +426,43 @@ int launch_regtile(qvm_state* q, unsigned grid, unsigned threads, size_t smem, c
     return QVM_OK;
 }
 
-int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops,
-                         const double* mats, uint64_t mats_entries, bool* handled, RelabelReq* relabel,
-                         const PushSpec* push, bool* pushed) {
-    *handled = false;
-    EncodedGroup& g = q->enc;
-    const int erc = encode_group(q->n_local, q->n_global, q->shard_index, n_tile, tile_bits, n_ops, ops, mats,
-                                 mats_entries, g, q->reg_bits, relabel ? relabel->low_in : 0u, relabel ? relabel->n_low : 0);
-    if (erc == ENC_ERROR) return fail(QVM_ERR_CUDA, "round planner made no progress");
-    if (erc == ENC_FALLBACK) return QVM_OK;          // the shared-memory kernel (or its error) handles it
-    if (relabel) memcpy(relabel->sigma, g.sigma, sizeof(g.sigma));
-    if (g.cold.empty() && !g.relabelled) {
-        *handled = true;
+// With `push` (a fused exchange, see PushSpec) the register-tiled kernels store the pass straight into the
+// destination shards and *pushed is set; when the group cannot carry it (nothing to launch, shared-memory
+// fallback kernel, victim bit inside the tile) the pass runs in place and the caller pushes separately.
+int launch_rec(qvm_state* q, LaunchRec& rec, const PushSpec* push = nullptr, bool* pushed = nullptr) {
+    if (rec.kind == REC_NONE) return QVM_OK;
+    if (push && push->m && (rec.tile_mask & push->mask)) push = nullptr;     // a victim bit inside the tile: not fusable
+    if (rec.kind == REC_TILE) {
+        const size_t ops_bytes = rec.dev.size() * sizeof(DevOp);
+        const size_t mats_bytes = rec.mats.size() * sizeof(double);
+        const size_t ops_pad = (ops_bytes + 255) & ~(size_t)255;
+        size_t off = 0;
+        int rc = ring_alloc(q, ops_pad + mats_bytes, &off);
+        if (rc) return rc;
+        memcpy(q->ring_host + off, rec.dev.data(), ops_bytes);
+        memcpy(q->ring_host + off + ops_pad, rec.mats.data(), mats_bytes);
+        QVM_CUDA(q, cudaMemcpyAsync(q->ring_dev + off, q->ring_host + off, ops_pad + mats_bytes, cudaMemcpyHostToDevice,
+                                    q->stream));
+        TileParams P = rec.tp;
+        P.ops = reinterpret_cast<const DevOp*>(q->ring_dev + off);
+        P.mats = reinterpret_cast<const double2*>(q->ring_dev + off + ops_pad);
+        const size_t smem = tile_smem_bytes(P.k, P.low, P.n_ops);
+        tile_kernel<<<(unsigned)(q->n_elems >> P.k), kTileThreads, smem, q->stream>>>(q->amps, P);
+        QVM_CUDA(q, cudaGetLastError());
+        q->stats.kernel_launches += 1;
+        q->stats.gate_ops += rec.executed;
+        q->stats.hbm_passes += 1;
+        q->stats.hbm_bytes += 32ull * q->n_elems;
+        q->stats.h2d_bytes += ops_pad + mats_bytes;
         return QVM_OK;
     }
-    if (g.n_tiles > 0x7fffffffull) return fail(QVM_ERR_UNSUPPORTED, "too many tiles for one launch");
-    for (int i = 0; i < 32; ++i) q->opc_hist[i] += g.opc_hist[i];
 
-    // a structure that has been seen before runs as a specialised straight-line kernel (qvm_jit.h)
-    if (q->jit_policy > 0 && !g.need_full && g.P.R == 4 && generate_spec(g, q->spec)) {
-        const CompiledSpec* cs = SpecCache::instance().get(q->spec.src, q->jit_policy, q->device);
+    EncodedGroup& g = rec.g;
+    if (rec.has_spec && q->jit_policy > 0) {
+        if (!rec.cs) rec.cs = SpecCache::instance().get(rec.spec.src, q->jit_policy, q->device);
         q->stats.jit_compiles = (uint64_t)SpecCache::instance().compiles();
-        if (cs) {
-            const SpecSource& ss = q->spec;
+        if (const CompiledSpec* cs = rec.cs) {
+            const SpecSource& ss = rec.spec;
             if (ss.smem > 48 * 1024 && const_cast<CompiledSpec*>(cs)->smem_attr < ss.smem) {
                 QVM_CUDA(q, cudaFuncSetAttribute((const void*)cs->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)ss.smem));
@@ -453,7 +486,6 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
             q->stats.hbm_bytes += 32ull * q->n_elems;
             q->stats.h2d_bytes += ss.factors.size() * sizeof(double);
             q->stats.regtile_rounds += (uint64_t)g.rounds.size();
-            *handled = true;
             return QVM_OK;
         }
     }
@@ -514,7 +546,23 @@ int launch_group_regtile(qvm_state* q, int n_tile, const int32_t* tile_bits, int
     q->stats.hbm_bytes += 32ull * q->n_elems;
     q->stats.h2d_bytes += total_bytes;
     q->stats.regtile_rounds += (uint64_t)g.rounds.size();
-    *handled = true;
+    return QVM_OK;
+}
+
+// Encode ops in tile-local coordinates and launch one tile kernel; while a program is being compiled
+// (qvm_record_begin) the launch is also kept for replay.
+int launch_group(qvm_state* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops, const double* mats,
+                 uint64_t mats_entries, RelabelReq* relabel = nullptr, const PushSpec* push = nullptr,
+                 bool* pushed = nullptr) {
+    LaunchRec& rec = q->rec;
+    int rc = build_rec(q, n_tile, tile_bits, n_ops, ops, mats, mats_entries, relabel, rec);
+    if (rc != QVM_OK) return rc;
+    rc = launch_rec(q, rec, push, pushed);
+    if (rc != QVM_OK) return rc;
+    if (q->recording && rec.kind != REC_NONE) {
+        if (push && push->m) return fail(QVM_ERR_UNSUPPORTED, "exchanges cannot be part of a compiled program");
+        q->recording->recs.push_back(rec);
+    }
     return QVM_OK;
 }
 
@@ -936,6 +984,121 @@ int qvm_apply_group_relabel(qvm_t* q, int n_tile, const int32_t* tile_bits, int 
     if (rc != QVM_OK) return rc;
     for (int j = 0; j < n_tile; ++j) new_pos[j] = tile_bits[req.sigma[j]];
     return QVM_OK;
+}
+
+// ---- compiled programs: record the launches of a flush once, replay them on every later run ----------
+int qvm_record_begin(qvm_t* q) {
+    QVM_CHECK_HANDLE(q);
+    if (q->recording) return fail(QVM_ERR_INVALID, "a recording is already open on this handle");
+    qvm_plan* plan = new (std::nothrow) qvm_plan();
+    if (!plan) return fail(QVM_ERR_NOMEM, "host allocation failed");
+    plan->n_local = q->n_local;
+    plan->n_global = q->n_global;
+    plan->shard_index = q->shard_index;
+    q->recording = plan;
+    return QVM_OK;
+}
+
+int qvm_record_end(qvm_t* q, qvm_plan_t** plan) {
+    if (!q) return fail(QVM_ERR_INVALID, "null handle");
+    if (!q->recording) return fail(QVM_ERR_INVALID, "no recording is open on this handle");
+    qvm_plan* rec = q->recording;
+    q->recording = nullptr;
+    if (plan) *plan = rec;
+    else delete rec;                       // aborted
+    return QVM_OK;
+}
+
+int qvm_plan_launches(const qvm_plan_t* plan) { return plan ? (int)plan->recs.size() : -1; }
+
+int qvm_plan_destroy(qvm_plan_t* plan) {
+    if (!plan) return QVM_OK;
+    if (plan->graph) cudaGraphExecDestroy(plan->graph);
+    delete plan;
+    return QVM_OK;
+}
+
+static int plan_launch_all(qvm_t* q, qvm_plan_t* plan, int reset_first, bool* all_specialised) {
+    if (reset_first) {
+        fill_zero_kernel<<<grid_for(q, q->n_elems, 256), 256, 0, q->stream>>>(q->amps, q->n_elems, 1);
+        QVM_CUDA(q, cudaGetLastError());
+        q->stats.kernel_launches += 1;
+        q->stats.hbm_bytes += 16ull * q->n_elems;
+    }
+    bool all = true;
+    for (LaunchRec& rec : plan->recs) {
+        const int rc = launch_rec(q, rec);
+        if (rc != QVM_OK) return rc;
+        all = all && rec.kind == REC_REGTILE && rec.cs != nullptr && q->jit_policy > 0;
+    }
+    if (all_specialised) *all_specialised = all;
+    return QVM_OK;
+}
+
+int qvm_plan_run(qvm_t* q, qvm_plan_t* plan, int reset_first) {
+    QVM_CHECK_HANDLE(q);
+    if (!plan) return fail(QVM_ERR_INVALID, "null plan");
+    if (q->recording) return fail(QVM_ERR_INVALID, "a recording is open on this handle");
+    if (plan->n_local != q->n_local || plan->n_global != q->n_global || plan->shard_index != q->shard_index)
+        return fail(QVM_ERR_INVALID, "plan was compiled for another shard shape");
+    q->sample_mode = -1;
+    ++plan->runs;
+    if (plan->graph && plan->graph_amps == q->amps && plan->graph_reset == reset_first) {
+        QVM_CUDA(q, cudaGraphLaunch(plan->graph, q->stream));
+        q->stats.kernel_launches += plan->graph_stats.kernel_launches;
+        q->stats.jit_launches += plan->graph_stats.jit_launches;
+        q->stats.gate_ops += plan->graph_stats.gate_ops;
+        q->stats.hbm_passes += plan->graph_stats.hbm_passes;
+        q->stats.hbm_bytes += plan->graph_stats.hbm_bytes;
+        q->stats.regtile_rounds += plan->graph_stats.regtile_rounds;
+        q->stats.graph_launches += 1;
+        return QVM_OK;
+    }
+    // Every group has its specialised kernel (no descriptor uploads left) and the program came back: capture the
+    // whole sequence once -- launch-bound small registers then cost one cudaGraphLaunch per run.
+    static const bool graphs_on = [] {
+        const char* e = getenv("QVM_B200_GRAPHS");
+        return !e || atoi(e) != 0;
+    }();
+    if (graphs_on && plan->runs >= 3 && plan->recs.size() + (reset_first ? 1 : 0) >= 2 && plan->all_specialised &&
+        !plan->graph_failed) {
+        if (plan->graph) {
+            cudaGraphExecDestroy(plan->graph);
+            plan->graph = nullptr;
+        }
+        const qvm_stats_t before = q->stats;
+        cudaGraph_t graph = nullptr;
+        bool ok = cudaStreamBeginCapture(q->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            bool all = false;
+            const int rc = plan_launch_all(q, plan, reset_first, &all);
+            ok = cudaStreamEndCapture(q->stream, &graph) == cudaSuccess && rc == QVM_OK && all && graph;
+        }
+        if (ok) ok = cudaGraphInstantiate(&plan->graph, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        const qvm_stats_t after = q->stats;
+        q->stats = before;
+        if (ok) {
+            plan->graph_amps = q->amps;
+            plan->graph_reset = reset_first;
+            plan->graph_stats = qvm_stats_t{};
+            plan->graph_stats.kernel_launches = after.kernel_launches - before.kernel_launches;
+            plan->graph_stats.jit_launches = after.jit_launches - before.jit_launches;
+            plan->graph_stats.gate_ops = after.gate_ops - before.gate_ops;
+            plan->graph_stats.hbm_passes = after.hbm_passes - before.hbm_passes;
+            plan->graph_stats.hbm_bytes = after.hbm_bytes - before.hbm_bytes;
+            plan->graph_stats.regtile_rounds = after.regtile_rounds - before.regtile_rounds;
+            return qvm_plan_run(q, plan, reset_first);        // (takes the graph branch above)
+        }
+        cudaGetLastError();
+        plan->graph = nullptr;
+        plan->graph_failed = true;
+        q->sticky = 0;
+    }
+    bool all = false;
+    const int rc = plan_launch_all(q, plan, reset_first, &all);
+    plan->all_specialised = all;
+    return rc;
 }
 
 int qvm_dephase_all(qvm_t* q, int n_rho, uint64_t qubit_mask, double factor) {

@@ -114,6 +114,15 @@ def validate_qubits(qubits, n_positions):
         seen.add(q)
 
 
+class CompiledFlush(object):
+    """What ``Engine.end_recording`` returns: the launches of the recorded flushes (a library plan) and the
+    qubit layout they leave behind."""
+    __slots__ = ("plan", "pos_of", "n", "gates", "groups")
+
+    def __init__(self, plan, pos_of, n, gates, groups):
+        self.plan, self.pos_of, self.n, self.gates, self.groups = plan, pos_of, n, gates, groups
+
+
 class Engine(object):
     """Single-GPU engine: every position is local."""
 
@@ -272,6 +281,38 @@ class Engine(object):
         for group in _planner.plan(ops, self.n, self.tile_bits, self.low_bits):
             self.state.apply_group(group.tile, group.ops)
             self.groups_launched += 1
+
+    # -- compiled programs (referenceqvm/_compiled.py) -----------------------------------------------
+    def begin_recording(self):
+        """From a freshly reset state: keep every launch of the flushes that follow for replay."""
+        if self.pending or not self.layout_is_identity():
+            raise RuntimeError("recording starts from a reset engine")
+        self.state.record_begin()
+        self._rec_mark = (self.gates_queued, self.groups_launched)
+
+    def end_recording(self, keep=True):
+        try:
+            if keep:
+                self.flush()
+        except Exception:
+            self.state.record_end(keep=False)
+            raise
+        plan = self.state.record_end(keep=keep)
+        if plan is None:
+            return None
+        return CompiledFlush(plan, list(self.pos_of), self.n, self.gates_queued - self._rec_mark[0],
+                             self.groups_launched - self._rec_mark[1])
+
+    def replay(self, compiled, reset_first=True):
+        """Reset (optionally) and run a compiled gate stream: one library call."""
+        if compiled.n != self.n:
+            raise ValueError("compiled program is for %d positions, engine has %d" % (compiled.n, self.n))
+        self.pending = []
+        self._merger.reset()
+        self.state.plan_run(compiled.plan, reset_first)
+        self.pos_of = list(compiled.pos_of)
+        self.gates_queued += compiled.gates
+        self.groups_launched += compiled.groups
 
     def _launch_relabelled(self, tile_positions, ops, bring_low):
         return self.state.apply_group(tile_positions, ops, bring_low=bring_low if bring_low else [],

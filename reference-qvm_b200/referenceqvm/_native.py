@@ -36,7 +36,7 @@ class Stats(C.Structure):
     """``qvm_stats_t``"""
     _fields_ = [(name, C.c_uint64) for name in
                 ("kernel_launches", "gate_ops", "hbm_passes", "hbm_bytes", "h2d_bytes", "d2h_bytes", "regtile_rounds",
-                 "jit_launches", "jit_compiles", "push_launches", "fused_push_launches")]
+                 "jit_launches", "jit_compiles", "push_launches", "fused_push_launches", "graph_launches")]
 
     def as_dict(self):
         return {name: int(getattr(self, name)) for name, _ in self._fields_}
@@ -93,6 +93,11 @@ _SIGNATURES = {
     "qvm_ipc_open": (C.c_int, [_P, _P, C.POINTER(_P)]),
     "qvm_ipc_close": (C.c_int, [_P, _P]),
     "qvm_exchange_half": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_uint64, C.c_uint64]),
+    "qvm_record_begin": (C.c_int, [_P]),
+    "qvm_record_end": (C.c_int, [_P, C.POINTER(_P)]),
+    "qvm_plan_run": (C.c_int, [_P, _P, C.c_int]),
+    "qvm_plan_launches": (C.c_int, [_P]),
+    "qvm_plan_destroy": (C.c_int, [_P]),
     "qvm_alt_alloc": (C.c_int, [_P]),
     "qvm_alt_free": (C.c_int, [_P]),
     "qvm_alt_ptr": (_P, [_P]),
@@ -241,6 +246,28 @@ def spec_compile_check(n_local, tile_bits, ops, n_global=0, shard_index=0, bring
     if code < 0:
         raise NativeError(code, log.value.decode("utf-8", "replace") or last_error())
     return code
+
+
+class Plan(object):
+    """Owner of one ``qvm_plan_t``: the recorded launches of a compiled program."""
+
+    def __init__(self, pointer):
+        self._p = pointer
+
+    @property
+    def launches(self):
+        return int(lib().qvm_plan_launches(self._p)) if self._p else 0
+
+    def close(self):
+        if self._p:
+            lib().qvm_plan_destroy(self._p)
+            self._p = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # interpreter shutdown
+            pass
 
 
 class DeviceState(object):
@@ -516,6 +543,22 @@ class DeviceState(object):
         bits = np.ascontiguousarray(local_bits, dtype=np.int32)
         check(lib().qvm_exchange_block(self.handle, bits.size, bits.ctypes.data, mine_value, peer_value,
                                        _P(peer_ptr), elem_offset, count))
+
+    # -- compiled programs --------------------------------------------------------------------
+    def record_begin(self):
+        check(lib().qvm_record_begin(self.handle))
+
+    def record_end(self, keep=True):
+        """Close the recording; returns a ``Plan`` (``keep=False``: discards it)."""
+        if not keep:
+            check(lib().qvm_record_end(self.handle, None))
+            return None
+        ptr = _P()
+        check(lib().qvm_record_end(self.handle, C.byref(ptr)))
+        return Plan(ptr)
+
+    def plan_run(self, plan, reset_first=False):
+        check(lib().qvm_plan_run(self.handle, plan._p, 1 if reset_first else 0))
 
     def alt_alloc(self):
         """Second buffer for the out-of-place exchange; False when it does not fit in HBM."""

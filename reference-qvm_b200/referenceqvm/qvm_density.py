@@ -19,7 +19,7 @@ import numpy as np
 from pyquil.quil import Program
 from pyquil.quilbase import Gate, Measurement
 
-from referenceqvm import _engine, _native
+from referenceqvm import _compiled, _engine, _native
 from referenceqvm.gates import noise_gates, utility_gates  # noqa: F401
 from referenceqvm.qam import QAM
 from referenceqvm.unitary_generator import lifted_gate, resolve_gate, tensor_gates, value_get  # noqa: F401
@@ -132,6 +132,8 @@ class QVM_Density(QAM):
         self.all_inst = True
         self._engine = None
         self.device = int(os.environ.get("QVM_B200_DEVICE", "0"))
+        #: compiled programs (referenceqvm/_compiled.py): gate prefix + its noise channels planned once per Program
+        self.plan_cache = _compiled.ENABLED
         if density is not None:
             self._density = density
 
@@ -329,9 +331,47 @@ class QVM_Density(QAM):
         self._simulate_density(pyquil_program)
         return DeviceDensity(self._engine.clone_state(), self.num_qubits)       # an independent snapshot
 
+    _HOOKS = ("_pre", "_post", "transition", "_transition", "measurement", "kernel", "load_program", "apply_kraus")
+
+    def _plan_key(self):
+        nm = self.noise_model
+        noise = None if nm is None else (nm.T1, nm.T2, nm.gate_time_1q, nm.gate_time_2q, nm.ro_fidelity, nm.depolarizing,
+                                         nm.bitflip, nm.phaseflip, nm.bitphaseflip)
+        return ("density", id(self.gate_set), self.device, noise)
+
     def _simulate_density(self, pyquil_program):
+        """load_program, rho = |0..0><0..0|, run.  The program's leading run of Gate instructions -- with the
+        noise channels that follow each of them -- is recorded the first time a Program object comes by and
+        replayed afterwards (referenceqvm/_compiled.py); MEASURE and classical instructions always step."""
+        if not isinstance(pyquil_program, Program):
+            raise TypeError("I can only generate from pyQuil programs")
+        cache = self.plan_cache and _compiled.uses_base_hooks(self, QVM_Density, self._HOOKS)
+        entry = _compiled.lookup(pyquil_program, self._plan_key()) if cache else None
+        if entry is not None:
+            self.defgate_set = entry.defgate_set
+            self.program = pyquil_program
+            self.num_qubits = entry.num_qubits
+            self.classical_memory = np.zeros(entry.n_cbits, dtype=bool)
+            self._engine_for(self.num_qubits).replay(entry.compiled, reset_first=True)
+            self.program_counter = entry.k
+            self.kernel()
+            return
         self.load_program(pyquil_program)
-        self._engine_for(self.num_qubits).reset()
+        eng = self._engine_for(self.num_qubits)
+        eng.reset()
+        k = _compiled.gate_prefix_length(pyquil_program) if cache else 0
+        if k:
+            eng.begin_recording()
+            try:
+                while self.program_counter < k:
+                    self.transition(self.current_instruction())
+            except Exception:
+                eng.end_recording(keep=False)
+                raise
+            compiled = eng.end_recording()
+            _compiled.store(pyquil_program, self._plan_key(),
+                            _compiled.Entry(_compiled.token_of(pyquil_program), k, compiled, None, self.num_qubits,
+                                            len(self.classical_memory), self.defgate_set, True))
         self.kernel()
 
     def expectation(self, pyquil_program, operator_programs=[Program()]):

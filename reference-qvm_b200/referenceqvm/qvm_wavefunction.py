@@ -32,7 +32,7 @@ from pyquil.quilbase import (BinaryClassicalInstruction, ClassicalAnd, Classical
                              JumpConditional, JumpTarget, Measurement, UnaryClassicalInstruction)
 from pyquil.wavefunction import Wavefunction
 
-from referenceqvm import _engine
+from referenceqvm import _compiled, _engine
 from referenceqvm.gates import utility_gates  # noqa: F401
 from referenceqvm.qam import QAM
 from referenceqvm.unitary_generator import lifted_gate, resolve_gate, tensor_gates, value_get  # noqa: F401
@@ -86,22 +86,72 @@ class QVM_Wavefunction(QAM):
         #: set False to force the reference's per-trial re-simulation in run()/run_and_measure()
         self.sampling_fast_path = True
         self.last_timing = {}
+        #: compiled programs (referenceqvm/_compiled.py): the leading run of Gate instructions of a Program is
+        #: planned and encoded once and replayed on later runs of the same Program object
+        self.plan_cache = _compiled.ENABLED
         #: SWAP gates are not executed: they exchange two entries of this program-qubit -> engine-qubit
         #: table, and later instructions are routed through it.  The table is undone (with real SWAPs)
         #: only when amplitudes are read back; MEASURE and sampling just look bits up through it.
         self._virt = []
 
     # -- device state --------------------------------------------------------------------------
-    def _fresh_engine(self):
+    def _fresh_engine(self, reset=True):
         """|0...0> on the device, re-using the allocation when the register size is unchanged."""
         if self._engine is not None and self._engine.n != self.num_qubits:
             self._engine.close()
             self._engine = None
         if self._engine is None:
             self._engine = self._make_engine(self.num_qubits)
-        self._engine.reset()
+        if reset:
+            self._engine.reset()
         self._virt = list(range(self.num_qubits))
         return self._engine
+
+    # -- compiled programs ---------------------------------------------------------------------------
+    _HOOKS = ("pre", "post", "transition", "_transition", "measurement", "kernel", "load_program")
+
+    def _plan_key(self):
+        return ("wavefunction", id(self.gate_set), self.device)
+
+    def _start(self, pyquil_program):
+        """load_program + |0...0> + the program's leading run of Gate instructions, leaving the program
+        counter on the first instruction that is not a Gate.  The first time a Program object comes by, that
+        gate prefix is recorded while it runs; afterwards it is replayed with one library call and neither
+        the program nor its gates are looked at again (referenceqvm/_compiled.py)."""
+        if not isinstance(pyquil_program, Program):
+            raise TypeError("I can only generate from pyQuil programs")
+        cache = self.plan_cache and _compiled.uses_base_hooks(self, QVM_Wavefunction, self._HOOKS)
+        entry = _compiled.lookup(pyquil_program, self._plan_key()) if cache else None
+        if entry is not None and (self._engine is None or isinstance(self._engine, _engine.Engine)):
+            self.defgate_set = entry.defgate_set
+            self.program = pyquil_program
+            self.num_qubits = entry.num_qubits
+            self.classical_memory = np.zeros(entry.n_cbits, dtype=bool)
+            eng = self._fresh_engine(reset=False)
+            if isinstance(eng, _engine.Engine):
+                eng.replay(entry.compiled, reset_first=True)
+                self._virt = list(entry.virt)
+                self.program_counter = entry.k
+                return
+            eng.reset()
+            self.program_counter = 0
+            return
+        self.load_program(pyquil_program)
+        eng = self._fresh_engine()
+        k = _compiled.gate_prefix_length(pyquil_program) if cache and isinstance(eng, _engine.Engine) else 0
+        if k == 0:
+            return
+        eng.begin_recording()
+        try:
+            while self.program_counter < k:
+                self.transition(self.current_instruction())
+        except Exception:
+            eng.end_recording(keep=False)
+            raise
+        compiled = eng.end_recording()
+        _compiled.store(pyquil_program, self._plan_key(),
+                        _compiled.Entry(_compiled.token_of(pyquil_program), k, compiled, list(self._virt), self.num_qubits,
+                                        len(self.classical_memory), self.defgate_set, True))
 
     def _materialise_swaps(self):
         """Bring the engine state back to program-qubit order (real SWAP gates, then identity table)."""
@@ -230,9 +280,8 @@ class QVM_Wavefunction(QAM):
         return np.array(classical_addresses)
 
     def _simulate(self, pyquil_program, classical_addresses):
-        self.load_program(pyquil_program)
+        self._start(pyquil_program)
         mask = self._address_mask(classical_addresses)
-        self._fresh_engine()
         self.kernel()
         return mask
 
@@ -283,9 +332,8 @@ class QVM_Wavefunction(QAM):
             return [self._run_once(pyquil_program, classical_addresses) for _ in range(trials)]
 
         # simulate the measurement-free prefix once, then sample the terminal MEASURE block
-        self.load_program(pyquil_program)
+        self._start(pyquil_program)
         mask = self._address_mask(classical_addresses)
-        self._fresh_engine()
         while self.program_counter < split:
             self.transition(self.current_instruction())
         indices, _ = self._engine.sample(np.random.random_sample(trials), physical=True)

@@ -692,3 +692,81 @@ def test_sampling_cdf_scan_long_arrays_matches_numpy():
         assert np.mean(idx.astype(np.int64) == ref) > 0.999
     finally:
         eng.close()
+
+
+# ---- compiled programs (plan cache + CUDA graph) -------------------------------------------------------------
+def test_compiled_program_replay_matches_first_run_and_the_oracle():
+    """The second and later runs of a Program object replay its compiled gate prefix (one library call, a CUDA
+    graph once every group has its kernel): same amplitudes as the first run, which match the oracle."""
+    from referenceqvm import _compiled
+    n, depth = 16, 10
+    spec = orc.random_circuit_spec(n, depth, 21)
+    prog = spec_program(spec)
+    want, _ = orc.fast_run_wavefunction(oracle_ops(spec), n)
+    qvm = QVMConnection()
+    first = np.asarray(qvm.wavefunction(prog)[0].amplitudes)
+    assert np.max(np.abs(first - want)) < 1e-12
+    entry = _compiled.lookup(prog, qvm._plan_key())
+    assert entry is not None and entry.k == len(prog) and entry.compiled.plan.launches >= 2
+    qvm._engine.state.set_jit(2)                      # kernels at once: every group specialised from the next run on
+    for _ in range(6):
+        again = np.asarray(qvm.wavefunction(prog)[0].amplitudes)
+        assert np.array_equal(again, first)
+    st = qvm._engine.stats()
+    assert st["graph_launches"] >= 1, st               # the launch sequence became one graph launch
+    # appending to the program invalidates the cache; the new program is right too
+    prog.inst(H(3)).inst(CNOT(3, 9))
+    want2, _ = orc.fast_run_wavefunction(oracle_ops(spec + [("H", [], [3]), ("CNOT", [], [3, 9])]), n)
+    got2 = np.asarray(qvm.wavefunction(prog)[0].amplitudes)
+    assert np.max(np.abs(got2 - want2)) < 1e-12
+    # the cache can be switched off per QVM
+    plain = QVMConnection()
+    plain.plan_cache = False
+    assert np.max(np.abs(np.asarray(plain.wavefunction(spec_program(spec))[0].amplitudes) - want)) < 1e-12
+
+
+def test_compiled_prefix_with_measurements_and_swaps_keeps_the_seeded_stream():
+    """Programs whose gate prefix is followed by MEASUREs: the prefix is replayed, MEASUREs step as before;
+    seeded outcomes equal the uncached QVM's.  SWAP relabels inside the prefix are remembered."""
+    n = 12
+    spec = orc.random_circuit_spec(n, 5, 8)
+    prog = spec_program(spec)
+    prog.inst(("SWAP", 0, 7)).inst(("SWAP", 3, 11)).inst(H(7))
+    for q in (7, 0, 5):
+        prog.measure(q, [q])
+    prog.inst(X(2)).measure(2, [2])
+    cached, plain = QVMConnection(), QVMConnection()
+    plain.plan_cache = False
+    for rep in range(3):
+        np.random.seed(100 + rep)
+        a = cached.wavefunction(prog, [7, 0, 5, 2])
+        np.random.seed(100 + rep)
+        b = plain.wavefunction(prog, [7, 0, 5, 2])
+        assert a[1] == b[1]
+        assert np.max(np.abs(np.asarray(a[0].amplitudes) - np.asarray(b[0].amplitudes))) < 1e-13
+    np.random.seed(3)
+    r1 = cached.run(prog, [7, 0, 5, 2], trials=20)
+    np.random.seed(3)
+    r2 = plain.run(prog, [7, 0, 5, 2], trials=20)
+    assert r1 == r2
+
+
+def test_compiled_density_program_matches_uncached():
+    n = 6
+    spec = [("H", [], [q]) for q in range(n)] + orc.random_circuit_spec(n, 3, 4)
+    prog = spec_program(spec)
+    nm = NoiseModel(T1=INFINITY, T2=30e-6, gate_time_1q=50e-9, gate_time_2q=150e-9, ro_fidelity=1.0)
+    cached = QVMConnection(type_trans="density", noise_model=nm)
+    plain = QVMConnection(type_trans="density", noise_model=nm)
+    plain.plan_cache = False
+    want = np.asarray(plain.density(prog).todense())
+    for _ in range(3):
+        got = np.asarray(cached.density(prog).todense())
+        assert np.max(np.abs(got - want)) < 1e-14
+    # another noise model on the same Program object is another plan
+    nm2 = NoiseModel(T1=20e-6, T2=30e-6, gate_time_1q=50e-9, gate_time_2q=150e-9, ro_fidelity=1.0)
+    a = np.asarray(QVMConnection(type_trans="density", noise_model=nm2).density(prog).todense())
+    off = QVMConnection(type_trans="density", noise_model=nm2)
+    off.plan_cache = False
+    assert np.max(np.abs(a - np.asarray(off.density(prog).todense()))) < 1e-14
+    assert np.max(np.abs(a - want)) > 1e-6
