@@ -92,8 +92,10 @@ int qvm_set_tile_bits(qvm_t* q, int tile_bits, int low_bits);   /* tuning (the h
 /* 1 (default): register-tiled kernel where eligible; 0: shared-memory kernel only (testing).   */
 int qvm_set_kernel_path(qvm_t* q, int use_regtile);
 /* Specialised kernels for recurring group structures (NVRTC, cached by structure; new angles reuse
- * them): 0 never, 1 (default) compile a structure in the background from its second sighting on, 2 at
- * first sight, synchronously.  The interpreted kernel runs whatever has no ready kernel.  Env QVM_B200_JIT overrides the default. */
+ * them): 0 never, 1 (default) compile a structure in the background -- from its first sighting on shards of
+ * >= 2^26 amplitudes, from the second on smaller ones -- or load its cubin from the disk cache at once when
+ * an earlier process (or the ahead-of-time build) left it there, 2 at first sight, synchronously.  The
+ * interpreted kernel runs whatever has no ready kernel.  Env QVM_B200_JIT overrides the default. */
 int qvm_set_jit(qvm_t* q, int policy);
 /* Block until every background compilation has finished (benchmarks: once, after warm-up). */
 int qvm_jit_wait(void);
@@ -105,6 +107,18 @@ int qvm_jit_shutdown(void);
 int qvm_spec_compile_check(int n_local, int n_global, uint64_t shard_index, int n_tile, const int32_t* tile_bits,
                            int n_ops, const qvm_op_t* ops, const double* mats, uint64_t mats_entries, char* log,
                            uint64_t log_cap, int n_low, int n_bring, const int32_t* bring_low);
+/* Ahead-of-time form of the same (no device needed): plan the rounds of one group exactly as a launch would,
+ * report where the relabelling leaves every tile position (new_pos, as qvm_apply_group_relabel does) and put
+ * the group's specialised cubin into the disk cache -- <directory of libqvm_b200.so>/_spec_cache unless
+ * QVM_B200_CACHE_DIR names another (or "0": no disk cache).  A process that later meets the same structure
+ * loads the cubin instead of interpreting the group while NVRTC works.  0 = cubin in the cache, 1 = group is
+ * left to the interpreter. */
+int qvm_spec_precompile(int n_local, int n_global, uint64_t shard_index, int n_tile, const int32_t* tile_bits,
+                        int n_ops, const qvm_op_t* ops, const double* mats, uint64_t mats_entries, int n_low,
+                        int n_bring, const int32_t* bring_low, int32_t* new_pos);
+/* out4 = {structures submitted to NVRTC, cubins loaded from the disk cache, cubins written to it, kernels ready} */
+int qvm_jit_counters(uint64_t* out4);
+int qvm_jit_cache_dir(char* out, uint64_t cap);
 /* Debug: how many ops of each register-tile opcode were encoded so far (32 counters). */
 int qvm_debug_opcode_hist(qvm_t* q, uint64_t* out32);
 int qvm_n_local(const qvm_t* q);

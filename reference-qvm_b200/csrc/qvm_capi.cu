@@ -459,7 +459,9 @@ int launch_rec(qvm_state* q, LaunchRec& rec, const PushSpec* push = nullptr, boo
 
     EncodedGroup& g = rec.g;
     if (rec.has_spec && q->jit_policy > 0) {
-        if (!rec.cs) rec.cs = SpecCache::instance().get(rec.spec.src, q->jit_policy, q->device);
+        // large states compile a structure at its first sighting (an interpreted pass there costs more than waiting
+        // for a second call is worth); small ones at the second, so one-off programs do not keep NVRTC busy
+        if (!rec.cs) rec.cs = SpecCache::instance().get(rec.spec.src, q->jit_policy, q->device, q->n_local >= 26);
         q->stats.jit_compiles = (uint64_t)SpecCache::instance().compiles();
         if (const CompiledSpec* cs = rec.cs) {
             const SpecSource& ss = rec.spec;
@@ -738,6 +740,38 @@ int qvm_spec_compile_check(int n_local, int n_global, uint64_t shard_index, int 
         if (log && log_cap) snprintf(log, (size_t)log_cap, "%s", err.c_str());
         return fail(QVM_ERR_UNSUPPORTED, "specialised kernel did not compile: %.300s", err.c_str());
     }
+    return QVM_OK;
+}
+
+int qvm_spec_precompile(int n_local, int n_global, uint64_t shard_index, int n_tile, const int32_t* tile_bits, int n_ops,
+                        const qvm_op_t* ops, const double* mats, uint64_t mats_entries, int n_low, int n_bring,
+                        const int32_t* bring_low, int32_t* new_pos) {
+    if ((n_tile && !tile_bits) || (n_ops && !ops) || (n_bring && !bring_low) || !new_pos) return fail(QVM_ERR_INVALID, "null pointer");
+    uint32_t low_in = 0;
+    for (int i = 0; i < n_bring; ++i)
+        for (int j = 0; j < n_tile; ++j)
+            if (tile_bits[j] == bring_low[i]) low_in |= 1u << j;
+    EncodedGroup g;
+    SpecSource ss;
+    const int erc = encode_group(n_local, n_global, shard_index, n_tile, tile_bits, n_ops, ops, mats, mats_entries, g, 4,
+                                 low_in, n_low);
+    for (int j = 0; j < n_tile; ++j) new_pos[j] = tile_bits[erc == ENC_OK ? g.sigma[j] : j];
+    if (erc != ENC_OK || (g.cold.empty() && !g.relabelled) || g.need_full || !generate_spec(g, ss)) return 1;
+    std::string err;      // compiled on the background threads: qvm_jit_wait() returns when all cubins are on disk
+    if (!SpecCache::instance().precompile_async(ss.src, &err))
+        return fail(QVM_ERR_UNSUPPORTED, "ahead-of-time compile failed: %.300s", err.c_str());
+    return QVM_OK;
+}
+
+int qvm_jit_counters(uint64_t* out4) {
+    if (!out4) return fail(QVM_ERR_INVALID, "null pointer");
+    SpecCache::instance().counters(out4);
+    return QVM_OK;
+}
+
+int qvm_jit_cache_dir(char* out, uint64_t cap) {
+    if (!out || !cap) return fail(QVM_ERR_INVALID, "null pointer");
+    snprintf(out, (size_t)cap, "%s", SpecCache::instance().cache_dir().c_str());
     return QVM_OK;
 }
 

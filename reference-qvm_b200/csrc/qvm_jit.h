@@ -12,6 +12,8 @@
 // groups): this is a GPU path selection, never a CPU fallback.
 #pragma once
 #include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <condition_variable>
 #include <cstdio>
@@ -24,6 +26,7 @@
 #include <sstream>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "qvm_encode.h"
@@ -336,15 +339,31 @@ public:
         return *c;
     }
     // nullptr: not compiled (yet) under the policy, still compiling, or compilation impossible
-    const CompiledSpec* get(const std::string& src, int policy, int device) {
+    // `eager`: compile at the FIRST sighting (large states: one interpreted pass costs more than the structure's
+    // compile time is worth waiting for the second call).
+    const CompiledSpec* get(const std::string& src, int policy, int device, bool eager = false) {
         std::unique_lock<std::mutex> lock(mu_);
         auto it = cache_.find(src);
         if (it != cache_.end()) return it->second->state == READY ? &it->second->cs : nullptr;
         if (stopping_) return nullptr;
         // bounded: a service that keeps meeting new structures stops compiling (the interpreter serves them)
         if (cache_.size() >= kMaxCompiledStructures) return nullptr;
+        // a cubin of this very source on disk (an earlier process, or the ahead-of-time build): load it now,
+        // the launch that asked gets the specialised kernel
+        const std::string path = disk_path(src);
+        if (!path.empty() && access(path.c_str(), R_OK) == 0) {
+            Entry* e = new Entry();
+            cache_.emplace(src, std::unique_ptr<Entry>(e));
+            lock.unlock();
+            std::string err;
+            compile(src, e->cs, &err);
+            lock.lock();
+            e->state = e->cs.kernel ? READY : FAILED;
+            if (!e->cs.kernel) last_error_ = err;
+            return e->cs.kernel ? &e->cs : nullptr;
+        }
         if (seen_.size() > (1u << 20)) seen_.clear();
-        if (policy < 2 && ++seen_[std::hash<std::string>()(src)] < 2) return nullptr;
+        if (policy < 2 && ++seen_[std::hash<std::string>()(src)] < (eager ? 1 : 2)) return nullptr;
         Entry* e = new Entry();
         cache_.emplace(src, std::unique_ptr<Entry>(e));
         ++compiles_;
@@ -373,7 +392,7 @@ public:
         std::unique_lock<std::mutex> lock(mu_);
         stopping_ = true;
         for (Job& job : jobs_) {
-            job.entry->state = FAILED;
+            if (job.entry) job.entry->state = FAILED;
             --outstanding_;
         }
         jobs_.clear();
@@ -382,6 +401,49 @@ public:
     int compiles() {
         std::lock_guard<std::mutex> lock(mu_);
         return compiles_;
+    }
+    // {structures submitted to NVRTC, cubins loaded from the disk cache, cubins written to it, kernels ready}
+    void counters(uint64_t out[4]) {
+        std::lock_guard<std::mutex> lock(mu_);
+        out[0] = (uint64_t)compiles_;
+        out[1] = disk_hits_;
+        out[2] = disk_stores_;
+        uint64_t ready = 0;
+        for (auto& kv : cache_) ready += kv.second->state == READY;
+        out[3] = ready;
+    }
+    // Source -> cubin in the disk cache without a device (ahead-of-time builds); true when the cubin is there now.
+    bool precompile(const std::string& src, std::string* err) {
+        const std::string path = disk_path(src);
+        if (path.empty()) {
+            if (err) *err = "the disk cache is disabled or not writable";
+            return false;
+        }
+        if (access(path.c_str(), R_OK) == 0) return true;
+        std::vector<char> cubin;
+        if (!to_cubin(src, cubin, err)) return false;
+        return write_cubin(path, cubin);
+    }
+    // the same on the background threads (qvm_jit_wait() drains them): ahead-of-time builds of whole programs
+    bool precompile_async(const std::string& src, std::string* err) {
+        const std::string path = disk_path(src);
+        if (path.empty()) {
+            if (err) *err = "the disk cache is disabled or not writable";
+            return false;
+        }
+        if (access(path.c_str(), R_OK) == 0) return true;
+        std::unique_lock<std::mutex> lock(mu_);
+        if (stopping_) return false;
+        if (!aot_queued_.insert(path).second) return true;          // already on its way
+        jobs_.push_back(Job{src, nullptr, -1});
+        ++outstanding_;
+        start_workers();
+        cv_.notify_one();
+        return true;
+    }
+    std::string cache_dir() {
+        std::lock_guard<std::mutex> lock(dir_mu_);
+        return resolve_dir();
     }
     std::string last_error() {
         std::lock_guard<std::mutex> lock(mu_);
@@ -452,7 +514,8 @@ private:
         load_nvrtc(nullptr);                      // before atexit: handlers run in reverse order of registration
         std::atexit([] { SpecCache::instance().shutdown(); });
         unsigned n = std::thread::hardware_concurrency() / 2;
-        n = n < 1 ? 1 : (n > 8 ? 8 : n);
+        if (const char* e = getenv("QVM_B200_JIT_THREADS")) n = (unsigned)atoi(e);
+        n = n < 1 ? 1 : (n > 16 ? 16 : n);
         for (unsigned i = 0; i < n; ++i) std::thread([this] { worker(); }).detach();
     }
     void worker() {
@@ -463,6 +526,14 @@ private:
                 cv_.wait(lock, [&] { return !jobs_.empty(); });      // (never returns once shutdown() emptied the queue)
                 job = std::move(jobs_.front());
                 jobs_.pop_front();
+            }
+            if (!job.entry) {                     // ahead-of-time: source -> cubin on disk, no device involved
+                std::string err;
+                const bool ok = precompile(job.src, &err);
+                std::lock_guard<std::mutex> lock(mu_);
+                if (!ok) last_error_ = err;
+                if (--outstanding_ == 0) idle_cv_.notify_all();
+                continue;
             }
             cudaSetDevice(job.device);
             CompiledSpec cs;
@@ -506,14 +577,113 @@ private:
         }
         return true;
     }
+    // ---- disk cache of cubins: <dir of libqvm_b200.so>/_spec_cache (QVM_B200_CACHE_DIR overrides, "0" disables),
+    // keyed by a 128-bit hash of the embedded header, the generated source, the options and the NVRTC version
+    std::string resolve_dir() {                   // dir_mu_ held
+        if (dir_tried_) return dir_;
+        dir_tried_ = true;
+        std::string d;
+        if (const char* e = getenv("QVM_B200_CACHE_DIR")) {
+            if (!strcmp(e, "0") || !*e) return dir_;
+            d = e;
+        } else {
+            Dl_info info;
+            if (!dladdr((const void*)&kRegtileHeaderSource, &info) || !info.dli_fname) return dir_;
+            d = info.dli_fname;
+            const size_t slash = d.rfind('/');
+            d = (slash == std::string::npos ? std::string(".") : d.substr(0, slash)) + "/_spec_cache";
+        }
+        mkdir(d.c_str(), 0755);
+        if (access(d.c_str(), W_OK) != 0 && access(d.c_str(), R_OK) != 0) return dir_;
+        dir_ = d;
+        return dir_;
+    }
+    static uint64_t fnv(const char* p, size_t n, uint64_t h) {
+        for (size_t i = 0; i < n; ++i) {
+            h ^= (unsigned char)p[i];
+            h *= 1099511628211ull;
+        }
+        return h;
+    }
+    std::string disk_path(const std::string& src) {
+        std::string dir;
+        {
+            std::lock_guard<std::mutex> lock(dir_mu_);
+            dir = resolve_dir();
+        }
+        if (dir.empty()) return "";
+        static const std::string salt = [] {
+            std::string s = "sm_100a|c++17|lineinfo|v2|";
+            s += kRegtileHeaderSource;
+            return s;
+        }();
+        uint64_t a = fnv(salt.data(), salt.size(), 14695981039346656037ull);
+        a = fnv(src.data(), src.size(), a);
+        uint64_t b = fnv(salt.data(), salt.size(), 0x9E3779B97F4A7C15ull);
+        b = fnv(src.data(), src.size(), b);
+        char name[80];
+        snprintf(name, sizeof(name), "/spec_%016llx%016llx.cubin", (unsigned long long)a, (unsigned long long)b);
+        return dir + name;
+    }
+    static bool read_cubin(const std::string& path, std::vector<char>& cubin) {
+        FILE* fh = fopen(path.c_str(), "rb");
+        if (!fh) return false;
+        fseek(fh, 0, SEEK_END);
+        const long n = ftell(fh);
+        fseek(fh, 0, SEEK_SET);
+        bool ok = n > 0;
+        if (ok) {
+            cubin.resize((size_t)n);
+            ok = fread(cubin.data(), 1, (size_t)n, fh) == (size_t)n;
+        }
+        fclose(fh);
+        return ok;
+    }
+    bool write_cubin(const std::string& path, const std::vector<char>& cubin) {
+        char tmp[600];
+        snprintf(tmp, sizeof(tmp), "%s.%d.tmp", path.c_str(), (int)getpid());
+        FILE* fh = fopen(tmp, "wb");
+        if (!fh) return false;
+        const bool ok = fwrite(cubin.data(), 1, cubin.size(), fh) == cubin.size();
+        fclose(fh);
+        if (!ok || rename(tmp, path.c_str()) != 0) {
+            unlink(tmp);
+            return false;
+        }
+        std::lock_guard<std::mutex> lock(mu_count_);
+        ++disk_stores_;
+        return true;
+    }
     void compile(const std::string& src, CompiledSpec& cs, std::string* err) {
         std::vector<char> cubin;
-        if (!to_cubin(src, cubin, err)) return;
+        const std::string path = disk_path(src);
+        bool from_disk = !path.empty() && read_cubin(path, cubin);
+        if (!from_disk) {
+            if (!to_cubin(src, cubin, err)) return;
+            if (!path.empty()) write_cubin(path, cubin);
+        }
         cudaLibrary_t lib = nullptr;
         if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) {
             cudaGetLastError();
-            if (err) *err = "cudaLibraryLoadData failed";
-            return;
+            if (from_disk) {                     // a damaged file: drop it and build from source
+                unlink(path.c_str());
+                cubin.clear();
+                from_disk = false;
+                if (!to_cubin(src, cubin, err)) return;
+                write_cubin(path, cubin);
+                if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) {
+                    cudaGetLastError();
+                    if (err) *err = "cudaLibraryLoadData failed";
+                    return;
+                }
+            } else {
+                if (err) *err = "cudaLibraryLoadData failed";
+                return;
+            }
+        }
+        if (from_disk) {
+            std::lock_guard<std::mutex> lock(mu_count_);
+            ++disk_hits_;
         }
         cudaKernel_t k = nullptr;
         if (cudaLibraryGetKernel(&k, lib, "spec_kernel") != cudaSuccess) {
@@ -525,11 +695,15 @@ private:
         cs.lib = lib;
         cs.kernel = k;
     }
-    std::mutex mu_, nvrtc_mu_;
+    std::mutex mu_, nvrtc_mu_, dir_mu_, mu_count_;
+    std::string dir_;
+    bool dir_tried_ = false;
+    uint64_t disk_hits_ = 0, disk_stores_ = 0;
     std::condition_variable cv_, idle_cv_;
     std::unordered_map<std::string, std::unique_ptr<Entry>> cache_;
     std::unordered_map<size_t, int> seen_;
     std::deque<Job> jobs_;
+    std::unordered_set<std::string> aot_queued_;      // disk paths of ahead-of-time jobs already queued
     int outstanding_ = 0, compiles_ = 0;
     bool workers_started_ = false, stopping_ = false;
     std::string last_error_;

@@ -59,6 +59,10 @@ _SIGNATURES = {
     "qvm_jit_shutdown": (C.c_int, []),
     "qvm_spec_compile_check": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_int, _P, C.c_int, _P, _P, C.c_uint64, _P,
                                          C.c_uint64, C.c_int, C.c_int, _P]),
+    "qvm_spec_precompile": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_int, _P, C.c_int, _P, _P, C.c_uint64, C.c_int, C.c_int,
+                                      _P, _P]),
+    "qvm_jit_counters": (C.c_int, [_P]),
+    "qvm_jit_cache_dir": (C.c_int, [C.c_char_p, C.c_uint64]),
     "qvm_debug_opcode_hist": (C.c_int, [_P, _P]),
     "qvm_n_local": (C.c_int, [_P]),
     "qvm_device_ptr": (_P, [_P]),
@@ -231,6 +235,34 @@ def marshal_ops(ops):
 def jit_wait():
     """Block until all background compilations of specialised kernels have finished."""
     check(lib().qvm_jit_wait())
+
+
+def jit_counters():
+    """{submitted to NVRTC, loaded from the disk cache, written to it, kernels ready} of this process."""
+    out = (C.c_uint64 * 4)()
+    check(lib().qvm_jit_counters(C.cast(out, _P)))
+    return {"nvrtc_compiles": int(out[0]), "disk_hits": int(out[1]), "disk_stores": int(out[2]), "ready": int(out[3])}
+
+
+def jit_cache_dir():
+    buf = C.create_string_buffer(1024)
+    check(lib().qvm_jit_cache_dir(buf, len(buf)))
+    return buf.value.decode("utf-8", "replace")
+
+
+def spec_precompile(n_local, tile_bits, ops, n_global=0, shard_index=0, bring_low=(), n_low=0):
+    """``qvm_spec_precompile`` (no device): (status, new_pos); status 0 = cubin in the disk cache, 1 = the group
+    stays with the interpreter."""
+    ops = [o for o in ops if o.kind != OP_NOP]
+    arr, pool, total = marshal_ops(ops)
+    tb = np.ascontiguousarray(sorted(tile_bits), dtype=np.int32)
+    bl = np.ascontiguousarray(list(bring_low), dtype=np.int32)
+    new_pos = np.empty(tb.size, dtype=np.int32)
+    code = lib().qvm_spec_precompile(n_local, n_global, shard_index, tb.size, tb.ctypes.data, len(ops), C.cast(arr, _P),
+                                     pool.ctypes.data, total, n_low, bl.size, bl.ctypes.data, new_pos.ctypes.data)
+    if code < 0:
+        raise NativeError(code, last_error())
+    return code, new_pos.tolist()
 
 
 def spec_compile_check(n_local, tile_bits, ops, n_global=0, shard_index=0, bring_low=(), n_low=0):
