@@ -426,6 +426,39 @@ int launch_regtile(qvm_state* q, unsigned grid, unsigned threads, size_t smem, c
     return QVM_OK;
 }
 
+// A pushing pass walks its tiles with the victim bits as the FASTEST-varying bits of the tile index (the runs of
+// non-tile positions the block index is deposited into are launch parameters): consecutive CTAs then store to
+// different destinations in turn, so the NVLink stores are spread over the whole kernel instead of all local
+// tiles running first and all remote ones after them.  More than 8 runs: the order is left as it is.
+void runs_for_push(const PushSpec& push, int& n_runs, uint64_t& run_start, uint64_t& run_len) {
+    struct Run { int start, len; };
+    std::vector<Run> runs, head;
+    for (int r = 0; r < n_runs; ++r)
+        runs.push_back(Run{(int)((run_start >> (8 * r)) & 0xFF), (int)((run_len >> (8 * r)) & 0xFF)});
+    for (int i = 0; i < push.m; ++i) {
+        const int p = push.pos[i];
+        for (size_t r = 0; r < runs.size(); ++r) {
+            const Run cur = runs[r];
+            if (p < cur.start || p >= cur.start + cur.len) continue;
+            std::vector<Run> parts;
+            if (p > cur.start) parts.push_back(Run{cur.start, p - cur.start});
+            if (p + 1 < cur.start + cur.len) parts.push_back(Run{p + 1, cur.start + cur.len - p - 1});
+            runs.erase(runs.begin() + r);
+            runs.insert(runs.begin() + r, parts.begin(), parts.end());
+            head.push_back(Run{p, 1});
+            break;
+        }
+    }
+    if (head.empty() || head.size() + runs.size() > 8) return;
+    head.insert(head.end(), runs.begin(), runs.end());
+    n_runs = (int)head.size();
+    run_start = run_len = 0;
+    for (size_t r = 0; r < head.size(); ++r) {
+        run_start |= (uint64_t)head[r].start << (8 * r);
+        run_len |= (uint64_t)head[r].len << (8 * r);
+    }
+}
+
 // With `push` (a fused exchange, see PushSpec) the register-tiled kernels store the pass straight into the
 // destination shards and *pushed is set; when the group cannot carry it (nothing to launch, shared-memory
 // fallback kernel, victim bit inside the tile) the pass runs in place and the caller pushes separately.
@@ -474,6 +507,7 @@ int launch_rec(qvm_state* q, LaunchRec& rec, const PushSpec* push = nullptr, boo
             SpecParams sp = ss.params;
             if (push && push->m) {
                 sp.push = *push;
+                runs_for_push(*push, sp.n_runs, sp.run_start, sp.run_len);
                 if (pushed) *pushed = true;
             }
             void* args[3] = {&amps, &sp, const_cast<double*>(ss.factors.data())};
@@ -512,6 +546,7 @@ int launch_rec(qvm_state* q, LaunchRec& rec, const PushSpec* push = nullptr, boo
     RegTileParams P = g.P;
     if (push && push->m) {
         P.push = *push;
+        runs_for_push(*push, P.n_runs, P.run_start, P.run_len);
         if (pushed) *pushed = true;
     }
     P.rounds = reinterpret_cast<const RoundDesc*>(dp);

@@ -100,9 +100,9 @@ inline bool place_dense(PlannedRound& rd, const LocalOp& op, uint32_t allowed, i
     return false;
 }
 
-inline bool is_x_matrix(const double* m) {
-    static const double x[8] = {0, 0, 1, 0, 1, 0, 0, 0};
-    return memcmp(m, x, sizeof(x)) == 0;
+inline bool is_x_matrix(const double* m) {      // compared as numbers: conj(X) carries -0.0 imaginary parts
+    return m[0] == 0.0 && m[1] == 0.0 && m[2] == 1.0 && m[3] == 0.0 && m[4] == 1.0 && m[5] == 0.0 && m[6] == 0.0 &&
+           m[7] == 0.0;
 }
 inline bool is_h_matrix(const double* m) {      // s * [[1, 1], [1, -1]] with real s
     const double s = m[0];

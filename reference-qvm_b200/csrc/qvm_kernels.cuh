@@ -759,23 +759,40 @@ __global__ void __launch_bounds__(256) exchange_block_kernel(double2* __restrict
 // contiguous 512-byte segments.  The fused form of the same exchange is the last round of
 // regtile_kernel / spec_kernel storing through rt_push_base().
 constexpr int kPushUnroll = 8;
-__device__ __forceinline__ double2* push_target(const PushSpec& ps, uint64_t e) {
-    uint32_t L = 0;
-    for (int i = 0; i < ps.m; ++i) L |= (uint32_t)((e >> ps.pos[i]) & 1ull) << i;
-    return ps.dst[L] + ((e & ~ps.mask) | ps.mine_bits);
+// The loop index j is NOT the element index: its bits [c, c + m) (c = min(pos[0], 7)) are the victim bits, so
+// consecutive 2^c-element runs go to different destinations in turn and the NVLink stores are spread over the
+// whole duration of the kernel (walking the shard in address order would copy the local part first and leave
+// the links idle meanwhile, then leave HBM idle while the links drain).
+__device__ __forceinline__ uint64_t push_element(const PushSpec& ps, uint64_t j, uint32_t c, uint32_t& L) {
+    const uint64_t lo = j & ((1ull << c) - 1ull);
+    L = (uint32_t)(j >> c) & ((1u << ps.m) - 1u);
+    uint64_t e = lo | ((j >> (c + ps.m)) << c);
+    for (int i = 0; i < ps.m; ++i) e = insert_zero64(e, ps.pos[i]) | ((uint64_t)((L >> i) & 1u) << ps.pos[i]);
+    return e;
 }
 __global__ void __launch_bounds__(256) exchange_push_kernel(const double2* __restrict__ src,
                                                             const __grid_constant__ PushSpec ps, uint64_t n_elems) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t c = ps.pos[0] < 7 ? ps.pos[0] : 7;
     uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     for (; j + (kPushUnroll - 1) * stride < n_elems; j += kPushUnroll * stride) {
         double2 x[kPushUnroll];
+        double2* d[kPushUnroll];
 #pragma unroll
-        for (int u = 0; u < kPushUnroll; ++u) x[u] = __ldcs(&src[j + u * stride]);
+        for (int u = 0; u < kPushUnroll; ++u) {
+            uint32_t L;
+            const uint64_t e = push_element(ps, j + u * stride, c, L);
+            x[u] = __ldcs(&src[e]);
+            d[u] = ps.dst[L] + ((e & ~ps.mask) | ps.mine_bits);
+        }
 #pragma unroll
-        for (int u = 0; u < kPushUnroll; ++u) __stcs(push_target(ps, j + u * stride), x[u]);
+        for (int u = 0; u < kPushUnroll; ++u) __stcs(d[u], x[u]);
     }
-    for (; j < n_elems; j += stride) *push_target(ps, j) = src[j];
+    for (; j < n_elems; j += stride) {
+        uint32_t L;
+        const uint64_t e = push_element(ps, j, c, L);
+        ps.dst[L][(e & ~ps.mask) | ps.mine_bits] = src[e];
+    }
 }
 
 }  // namespace qvm

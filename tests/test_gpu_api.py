@@ -702,7 +702,7 @@ def test_compiled_program_replay_matches_first_run_and_the_oracle():
     n, depth = 16, 10
     spec = orc.random_circuit_spec(n, depth, 21)
     prog = spec_program(spec)
-    want, _ = orc.fast_run_wavefunction(oracle_ops(spec), n)
+    want, _ = orc.fast_run_wavefunction(oracle_ops(prog), n)
     qvm = QVMConnection()
     first = np.asarray(qvm.wavefunction(prog)[0].amplitudes)
     assert np.max(np.abs(first - want)) < 1e-12
@@ -716,7 +716,7 @@ def test_compiled_program_replay_matches_first_run_and_the_oracle():
     assert st["graph_launches"] >= 1, st               # the launch sequence became one graph launch
     # appending to the program invalidates the cache; the new program is right too
     prog.inst(H(3)).inst(CNOT(3, 9))
-    want2, _ = orc.fast_run_wavefunction(oracle_ops(spec + [("H", [], [3]), ("CNOT", [], [3, 9])]), n)
+    want2, _ = orc.fast_run_wavefunction(oracle_ops(prog), n)
     got2 = np.asarray(qvm.wavefunction(prog)[0].amplitudes)
     assert np.max(np.abs(got2 - want2)) < 1e-12
     # the cache can be switched off per QVM
