@@ -445,9 +445,15 @@ def config1_leg():
     n, depth = 10, 20
     spec = circuit(n, depth)
     prog = build_program(spec)
+    from referenceqvm import _native
     qvm = QVMConnection()
     times = []
     amps = None
+    t0 = time.perf_counter()
+    qvm.wavefunction(prog)
+    first_ms = 1e3 * (time.perf_counter() - t0)
+    qvm.wavefunction(prog)
+    _native.jit_wait()                    # steady state, as in the headline leg: specialised kernels compiled
     for _ in range(30):
         t0 = time.perf_counter()
         wf, _ = qvm.wavefunction(prog)
@@ -455,9 +461,10 @@ def config1_leg():
         times.append(time.perf_counter() - t0)
     best, med = min(times), statistics.median(times)
     out = {"workload": "10-qubit random circuit depth 20 (200 gates), QVMConnection().wavefunction(program)",
-           "ms_per_call_best": 1e3 * best, "ms_per_call_median": 1e3 * med, "first_call_ms": 1e3 * times[0],
+           "ms_per_call_best": 1e3 * best, "ms_per_call_median": 1e3 * med, "first_call_ms": first_ms,
+           "graph_launches": qvm._engine.stats().get("graph_launches", 0),
            "gate_apps_per_s": len(spec) / med, "norm2_minus_1": float(np.vdot(amps, amps).real - 1.0),
-           "kernel_launches_per_call": qvm._engine.stats()["kernel_launches"] / 30.0}
+           "kernel_launches_per_call": qvm._engine.stats()["kernel_launches"] / 32.0}
     if reference_staged():
         with tempfile.TemporaryDirectory() as tmp:
             path = os.path.join(tmp, "ref.npy")
@@ -481,9 +488,13 @@ def config2_leg():
     prog = build_program(spec)
     nm = NoiseModel(T1=INFINITY, T2=30e-6, gate_time_1q=50e-9, gate_time_2q=150e-9, ro_fidelity=1.0)
     qvm = QVMConnection(type_trans="density", noise_model=nm)
+    from referenceqvm import _native
     times, rho = [], None
-    for _ in range(4):
+    for rep in range(6):
+        if rep == 2:
+            _native.jit_wait()                # steady state: the 5 groups' specialised kernels are compiled
         qvm._engine and qvm._engine.state.stats_reset()
+        rho = None                            # (the previous snapshot is released outside the timed span)
         t0 = time.perf_counter()
         rho = qvm.density(prog)
         qvm._engine.sync()
@@ -491,11 +502,15 @@ def config2_leg():
     st = qvm._engine.stats()
     diag = np.asarray(rho.diagonal())
     peak, _ = measured_peaks()
-    best = min(times[1:])
+    best = min(times[3:])
     passes = st["hbm_passes"]
     out = {"workload": "14-qubit density matrix (2^28 complex128 = 4 GiB), H on all qubits + random circuit depth 4 "
                        "(70 instructions), T2 dephasing Kraus noise on every qubit after every instruction",
            "ms_per_call": 1e3 * best, "ms_per_instruction": 1e3 * best / len(spec), "hbm_passes": passes,
+           "first_call_ms": 1e3 * times[0], "specialised_launches": st.get("jit_launches", 0),
+           "graph_launches": st.get("graph_launches", 0),
+           "call": "QVMConnection(type_trans='density', noise_model=...).density(program): reset, gates + noise, and an "
+                   "independent snapshot of rho (one more 4 GiB copy)",
            "achieved_gbs": passes * 32.0 * 2 ** (2 * n) / best / 1e9,
            "frac_of_hbm_peak": passes * 32.0 * 2 ** (2 * n) / best / 1e9 / peak,
            "trace_minus_1": float(np.sum(diag).real - 1.0), "min_diag": float(np.min(diag.real))}
@@ -512,9 +527,12 @@ def config3_leg():
     for q in range(n):
         prog.measure(q, [q])
     qvm = QVMConnection()
+    from referenceqvm import _native
     np.random.seed(1)
     times = []
-    for _ in range(3):
+    for rep in range(5):
+        if rep == 2:
+            _native.jit_wait()
         t0 = time.perf_counter()
         bits = qvm.run(prog, list(range(n)), trials=1)
         times.append(time.perf_counter() - t0)
@@ -527,7 +545,7 @@ def config3_leg():
     # QFT|0..0> is uniform: every marginal is 1/2 (5 sigma of 10^5 fair coins = 0.008)
     marg = res.mean(axis=0)
     out = {"workload": "28-qubit QFT (420 gates) + MEASURE of all 28 qubits, 4 GiB state",
-           "ms_per_trial_run": 1e3 * min(times[1:]), "bits_first_trial": bits[0][:8],
+           "ms_per_trial_run": 1e3 * min(times[2:]), "first_call_ms": 1e3 * times[0], "bits_first_trial": bits[0][:8],
            "shots": shots, "ms_run_%d_shots" % shots: 1e3 * dt,
            "max_marginal_deviation_from_half": float(np.max(np.abs(marg - 0.5))),
            "uniform_ok": bool(np.max(np.abs(marg - 0.5)) < 0.01)}

@@ -228,8 +228,17 @@ int qvm_collapse(qvm_t* q, int qubit, int outcome, double scale);
 /* Density flavour on a vectorised rho of n_rho_qubits: p0 = tr(P0 rho) over the local rows. */
 int qvm_density_prob_zero(qvm_t* q, int n_rho_qubits, int qubit, double* p0_partial);
 
+/* diag(rho) through a qubit layout (rho relabelled in its tiles and / or sharded by rows; replaces the Python
+ * loop of sparse_trace, qvm_density.py:51-54, and the diagonal read at :444): pos_of[v] (2 n_rho entries) is
+ * the physical position of vector qubit v -- v < n_rho: column qubit v, v >= n_rho: row qubit v - n_rho.
+ * diag_host receives 2^n_rho doubles: Re rho[i,i] for the entries this shard owns, 0.0 for the others (the
+ * shards' arrays add up to the full diagonal exactly). */
+int qvm_density_diag(qvm_t* q, int n_rho_qubits, const int32_t* pos_of, double* diag_host);
+
 /* ---- sampling (qvm_density.py:442-452; statistical meaning of qvm_wavefunction.py:266-321) ----- */
-/* Build the two-level CDF of |amp|^2 (mode 0) or of diag(rho) (mode 1, n_rho_qubits = n). */
+/* Build the two-level CDF of |amp|^2 (mode 0), of diag(rho) (mode 1, n_rho_qubits = n, identity layout, rows
+ * sharded), or of a plain array of 2^(n_local+1) probabilities that the caller stored in the handle's buffer
+ * as raw doubles (mode 2: a diagonal gathered by qvm_density_diag). */
 int qvm_probs_prepare(qvm_t* q, int mode, int n_rho_qubits, double* total);
 /* Inverse-CDF draws: index = first i with cdf[i] > uniforms[s] * total (numpy's searchsorted
  * 'right' on the normalised cdf).  Indices are local to the shard. */

@@ -676,6 +676,16 @@ static int create_impl(int n_local, int device, void* external, qvm_t** out) {
     cudaDeviceProp prop;
     QVM_CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
     q->sm_count = prop.multiProcessorCount;
+    {
+        // stream-ordered scratch allocations (sampling, histograms, readback staging) come from the device's default
+        // pool: keep what it has grown to instead of handing it back to the driver at every synchronisation
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            uint64_t keep = 1ull << 30;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     QVM_CREATE_CUDA(cudaStreamCreateWithFlags(&q->own_stream, cudaStreamNonBlocking));
     q->stream = q->own_stream;
     if (external) {
@@ -1338,6 +1348,43 @@ int qvm_density_prob_zero(qvm_t* q, int n_rho, int qubit, double* p0_partial) {
     return reduce_partials(q, grid, p0_partial);
 }
 
+int qvm_density_diag(qvm_t* q, int n_rho, const int32_t* pos_of, double* diag_host) {
+    QVM_CHECK_HANDLE(q);
+    if (!pos_of || !diag_host) return fail(QVM_ERR_INVALID, "null pointer");
+    if (n_rho < 1 || n_rho > 31 || 2 * n_rho != total_positions(q))
+        return fail(QVM_ERR_INVALID, "state is not a %d-qubit rho", n_rho);
+    DiagLayout lay{};
+    uint64_t seen = 0;
+    for (int v = 0; v < 2 * n_rho; ++v) {
+        const int p = pos_of[v];
+        if (p < 0 || p >= 2 * n_rho || ((seen >> p) & 1ull)) return fail(QVM_ERR_INVALID, "layout is not a permutation");
+        seen |= 1ull << p;
+        (v < n_rho ? lay.pos_col[v] : lay.pos_row[v - n_rho]) = (uint8_t)p;
+    }
+    const uint64_t n = 1ull << n_rho;
+    double* dev = nullptr;
+    QVM_CUDA(q, cudaMallocAsync(&dev, n * sizeof(double), q->stream));
+    density_diag_kernel<<<grid_for(q, n, 256), 256, 0, q->stream>>>(q->amps, n_rho, lay, q->n_local, q->shard_index, dev);
+    cudaError_t e = cudaGetLastError();
+    int rc = QVM_OK;
+    if (e == cudaSuccess) {
+        rc = ensure_stage(q, std::min<size_t>(kStageChunk, n * sizeof(double)));
+        for (uint64_t done = 0; rc == QVM_OK && e == cudaSuccess && done < n;) {
+            const uint64_t cnt = std::min<uint64_t>(n - done, q->stage_bytes / sizeof(double));
+            e = cudaMemcpyAsync(q->stage, dev + done, cnt * sizeof(double), cudaMemcpyDeviceToHost, q->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(q->stream);
+            if (e == cudaSuccess) memcpy(diag_host + done, q->stage, cnt * sizeof(double));
+            done += cnt;
+        }
+    }
+    cudaFreeAsync(dev, q->stream);
+    if (rc != QVM_OK) return rc;
+    QVM_CUDA(q, e);
+    q->stats.kernel_launches += 1;
+    q->stats.d2h_bytes += n * sizeof(double);
+    return QVM_OK;
+}
+
 int qvm_collapse(qvm_t* q, int qubit, int outcome, double scale) {
     QVM_CHECK_HANDLE(q);
     if (qubit < 0 || qubit >= total_positions(q)) return fail(QVM_ERR_INVALID, "qubit %d out of range", qubit);
@@ -1359,9 +1406,10 @@ int qvm_collapse(qvm_t* q, int qubit, int outcome, double scale) {
 // ---- sampling ---------------------------------------------------------------------------------------
 int qvm_probs_prepare(qvm_t* q, int mode, int n_rho, double* total) {
     QVM_CHECK_HANDLE(q);
-    if (mode != 0 && mode != 1) return fail(QVM_ERR_INVALID, "mode must be 0 (|psi|^2) or 1 (diag rho)");
+    if (mode < 0 || mode > 2) return fail(QVM_ERR_INVALID, "mode must be 0 (|psi|^2), 1 (diag rho) or 2 (plain probabilities)");
     uint64_t n_probs = q->n_elems;
     uint64_t row_base = 0;
+    if (mode == 2) n_probs = 2 * q->n_elems;          // the buffer read as doubles
     if (mode == 1) {
         if (2 * n_rho != total_positions(q) || q->n_local < n_rho)
             return fail(QVM_ERR_INVALID, "state is not a %d-qubit rho sharded by rows", n_rho);

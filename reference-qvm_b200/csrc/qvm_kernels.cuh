@@ -507,13 +507,34 @@ __global__ void batched_reset_kernel(double2* __restrict__ state, uint64_t n_ele
 // ---------------------------------------------------------------------------------------------
 constexpr int kSampleBlockBits = 11;      // 2048 probabilities per CDF block
 
+// mode 0: |amp_i|^2; mode 1: Re rho[i,i] of a vectorised rho (row-major, identity layout); mode 2: the buffer IS
+// a plain array of probabilities (doubles): a diagonal gathered through a qubit layout / across shards
 __device__ __forceinline__ double prob_at(const double2* __restrict__ state, uint64_t i, int mode, int n_rho,
                                           uint64_t row_base) {
     if (mode == 0) {
         const double2 a = state[i];
         return a.x * a.x + a.y * a.y;
     }
+    if (mode == 2) return reinterpret_cast<const double*>(state)[i];
     return state[(i << n_rho) | (row_base | i)].x;
+}
+
+// diag(rho) through a qubit layout (density matrices under relabelling / sharding): entry i of the diagonal
+// lives at the physical index whose bits pos_col[q] and pos_row[q] both equal bit q of i.  A shard writes the
+// entries it owns and 0.0 elsewhere, so the shards' outputs add up to the full diagonal exactly.
+struct DiagLayout {
+    uint8_t pos_col[32];
+    uint8_t pos_row[32];
+};
+__global__ void density_diag_kernel(const double2* __restrict__ state, int n_rho, const DiagLayout lay, int n_local,
+                                    uint64_t shard_index, double* __restrict__ out) {
+    const uint64_t n = 1ull << n_rho;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t phys = 0;
+        for (int q = 0; q < n_rho; ++q)
+            if ((i >> q) & 1ull) phys |= (1ull << lay.pos_col[q]) | (1ull << lay.pos_row[q]);
+        out[i] = (phys >> n_local) == shard_index ? state[phys & ((1ull << n_local) - 1ull)].x : 0.0;
+    }
 }
 
 // block_sums[b] = sum of the probabilities in block b.  One warp per block.

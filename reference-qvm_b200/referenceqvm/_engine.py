@@ -114,6 +114,39 @@ def validate_qubits(qubits, n_positions):
         seen.add(q)
 
 
+def host_uniforms(engine, count=None):
+    """The state machine's draws from numpy's global RNG (one per MEASURE, ``trials`` per sampling call --
+    reference qvm_wavefunction.py:120, qvm_density.py:131, :445).  On a sharded engine only rank 0 draws: the
+    engine broadcasts rank 0's numbers anyway, and the other ranks' streams stay untouched."""
+    ctx = getattr(engine, "ctx", None)
+    if ctx is not None and ctx.rank != 0:
+        return 0.0 if count is None else np.zeros(count)
+    return np.random.random() if count is None else np.random.random_sample(count)
+
+
+def shared_uniform(engine, r):
+    """Rank 0's value of a host-drawn uniform, on every rank (identity on a single-GPU engine)."""
+    if hasattr(engine, "_broadcast_floats"):
+        return float(engine._broadcast_floats([r])[0])
+    return r
+
+
+def sample_distribution(probabilities, uniforms, device=0):
+    """Inverse-CDF draws (numpy's ``searchsorted(cumsum, u * total, 'right')``) from a plain array of
+    2^k probabilities with the device sampler (``qvm_probs_prepare`` mode 2): returns (indices, total)."""
+    p = np.ascontiguousarray(probabilities, dtype=np.float64).reshape(-1)
+    k = int(p.size).bit_length() - 1
+    if p.size < 2 or (1 << k) != p.size:
+        raise ValueError("need a power-of-two number (>= 2) of probabilities")
+    scratch = nat.DeviceState(k - 1, device)
+    try:
+        scratch.set_state(p.view(np.complex128))
+        total = scratch.probs_prepare(2, 0)
+        return scratch.sample(uniforms), total
+    finally:
+        scratch.close()
+
+
 class CompiledFlush(object):
     """What ``Engine.end_recording`` returns: the launches of the recorded flushes (a library plan) and the
     qubit layout they leave behind."""
@@ -241,6 +274,12 @@ class Engine(object):
     def clone_state(self):
         self.restore_layout()
         return self.state.clone()
+
+    def clone(self):
+        """An independent engine holding a copy of this state (identity layout)."""
+        dup = Engine.from_state(self.clone_state(), self.tile_bits, self.low_bits)
+        dup.relabel = self.relabel
+        return dup
 
     # -- gates -------------------------------------------------------------------------------
     def queue_matrix(self, matrix, qubits):
@@ -377,18 +416,26 @@ class Engine(object):
         self.flush()
         return self.state.prob_zero(self.pos_of[int(qubit)])
 
+    def density_diag(self, n_rho):
+        """diag(rho) (2^n doubles) of the vectorised rho this engine holds, read through the layout."""
+        self.flush()
+        return self.state.density_diag(n_rho, self.pos_of)
+
     def density_prob_zero(self, n_rho, qubit):
-        self.restore_layout()
-        return self.state.density_prob_zero(n_rho, int(qubit))
+        self.flush()
+        if self.layout_is_identity():
+            return self.state.density_prob_zero(n_rho, int(qubit))
+        diag = self.density_diag(n_rho)
+        return float(diag[((np.arange(diag.size) >> int(qubit)) & 1) == 0].sum())
 
     def sample(self, uniforms, mode=0, n_rho=0, physical=False):
         """Inverse-CDF draws of basis-state indices from |psi|^2 (mode 0) or diag(rho) (mode 1).
 
         Draws walk the CDF in HBM order.  With ``physical=True`` the raw indices come back (bit
         ``position(q)`` is qubit q); otherwise they are converted to logical indices."""
-        if mode == 1:
-            self.restore_layout()
         self.flush()
+        if mode == 1 and not self.layout_is_identity():
+            return sample_distribution(self.density_diag(n_rho), uniforms, self.device)
         total = self.state.probs_prepare(mode, n_rho)
         indices = self.state.sample(uniforms)
         if not physical and not self.layout_is_identity():

@@ -89,6 +89,7 @@ _SIGNATURES = {
     "qvm_prob_zero": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
     "qvm_density_prob_zero": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "qvm_collapse": (C.c_int, [_P, C.c_int, C.c_int, C.c_double]),
+    "qvm_density_diag": (C.c_int, [_P, C.c_int, _P, _P]),
     "qvm_probs_prepare": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "qvm_sample": (C.c_int, [_P, C.c_uint64, _P, _P]),
     "qvm_pack_half": (C.c_int, [_P, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _P]),
@@ -537,6 +538,16 @@ class DeviceState(object):
 
     def collapse(self, qubit, outcome, scale):
         check(lib().qvm_collapse(self.handle, qubit, outcome, scale))
+
+    def density_diag(self, n_rho, pos_of):
+        """This shard's part of diag(rho) under the layout ``pos_of`` (2^n doubles, 0.0 where not owned)."""
+        pos = np.ascontiguousarray(pos_of, dtype=np.int32)
+        out = np.empty(1 << n_rho, dtype=np.float64)
+        code = lib().qvm_density_diag(self.handle, n_rho, pos.ctypes.data, out.ctypes.data)
+        if code == QVM_ERR_INVALID:
+            raise ValueError(last_error())
+        check(code)
+        return out
 
     def probs_prepare(self, mode=0, n_rho=0):
         v = C.c_double(0.0)

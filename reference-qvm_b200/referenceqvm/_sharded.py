@@ -112,8 +112,12 @@ class TorchComm(object):
 
 
 class ShardContext(object):
-    def __init__(self, comm, device):
+    def __init__(self, comm, device, backend_factory=None, engine_options=None):
         self.comm, self.device = comm, device
+        #: shard backend / constructor options of the engines ``_engine.make_engine`` creates under this context
+        #: (tests: the numpy backend with small tiles; production: CudaShard with the defaults)
+        self.backend_factory = backend_factory
+        self.engine_options = dict(engine_options or {})
         self.rank, self.world = comm.rank, comm.world
         self.group = getattr(comm, "group", None)
         self.n_global = int(self.world).bit_length() - 1
@@ -121,11 +125,12 @@ class ShardContext(object):
             raise ValueError("world size %d is not a power of two" % self.world)
 
 
-def enable(device=None, group=None, comm=None):
+def enable(device=None, group=None, comm=None, backend_factory=None, engine_options=None):
     """Shard every engine created from now on (by this thread; from the main thread: by the process)
     across the ranks of ``comm`` (default: a TorchComm on ``group`` / WORLD)."""
     global _default
-    ctx = ShardContext(comm if comm is not None else TorchComm(group), 0 if device is None else device)
+    ctx = ShardContext(comm if comm is not None else TorchComm(group), 0 if device is None else device,
+                       backend_factory, engine_options)
     _tls.ctx = ctx
     if threading.current_thread() is threading.main_thread():
         _default = ctx
@@ -280,6 +285,12 @@ class CudaShard(object):
     def measure_hist(self, high_positions, collapse=None, want_hist=True):
         return self.state.measure_hist(high_positions, collapse, want_hist)
 
+    def density_diag(self, n_rho, pos_of):
+        return self.state.density_diag(n_rho, pos_of)
+
+    def copy_from(self, other):
+        self.state.copy_from(other.state)
+
     def collapse(self, position, outcome, scale):
         self.state.collapse(position, outcome, scale)
 
@@ -317,9 +328,13 @@ class ShardedEngine(object):
         self.n_local = self.n - self.g
         if self.n_local < 1:
             raise ValueError("%d qubits cannot be sharded over %d ranks" % (self.n, self.ctx.world))
+        opts = self.ctx.engine_options
+        tile_bits = opts.get("tile_bits") if tile_bits is None else tile_bits
+        low_bits = opts.get("low_bits") if low_bits is None else low_bits
+        exchange = exchange or opts.get("exchange")
         self.tile_bits = _TILE_BITS if tile_bits is None else tile_bits
         self.low_bits = _LOW_BITS if low_bits is None else low_bits
-        self.shard = (backend_factory or CudaShard)(self.n_local, self.ctx)
+        self.shard = (backend_factory or self.ctx.backend_factory or CudaShard)(self.n_local, self.ctx)
         if hasattr(self.comm, "bind"):
             self.comm.bind(self.shard.scalar_tensor)
         self.chunk_amps = min(chunk_amps or self.CHUNK_AMPS, 1 << (self.n_local - 1))
@@ -449,6 +464,28 @@ class ShardedEngine(object):
     def norm2(self):
         self.flush()
         return self._allreduce_sum(self.shard.norm2())
+
+    def clone(self):
+        """An independent engine holding a copy of this state (same layout): density snapshots, apply_kraus."""
+        self.flush()
+        dup = ShardedEngine(self.n, self.ctx, self.tile_bits, self.low_bits, backend_factory=type(self.shard),
+                            exchange=self.exchange)
+        dup.shard.copy_from(self.shard)
+        dup.pos_of = list(self.pos_of)
+        dup.relabel = self.relabel
+        return dup
+
+    # -- density matrices: the state is a vectorised rho of n_rho qubits (rows = the high n_rho vector qubits, so
+    # the global positions are row bits) ----------------------------------------------------------------------------
+    def density_diag(self, n_rho):
+        """diag(rho), identical on every rank: each shard gathers the entries it owns through the layout
+        (``qvm_density_diag``), the pieces add up exactly (x + 0)."""
+        self.flush()
+        return self.comm.allreduce(self.shard.density_diag(n_rho, self.pos_of))
+
+    def density_prob_zero(self, n_rho, qubit):
+        diag = self.density_diag(n_rho)
+        return float(diag[((np.arange(diag.size) >> int(qubit)) & 1) == 0].sum())
 
     # -- gates -------------------------------------------------------------------------------------
     def queue_matrix(self, matrix, qubits):
@@ -873,8 +910,14 @@ class ShardedEngine(object):
         indices are translated through the layout -- the same distribution as a walk in logical order
         without moving a single amplitude.  ``logical_order=True`` restores the layout first (exchanges
         and SWAP passes), so that the draws equal ``searchsorted`` on the logical CDF uniform by uniform."""
-        if mode != 0:
-            raise NotImplementedError("sharded density sampling")
+        if mode == 1:
+            # diag(rho) is small (2^n_rho doubles): every rank gathers it and runs the same device sampler on it
+            from referenceqvm._engine import sample_distribution
+            u = self._broadcast_floats(uniforms)
+            diag = self.density_diag(n_rho)
+            if hasattr(self.shard, "sample_distribution"):      # (the numpy backend of the CPU tests)
+                return self.shard.sample_distribution(diag, u)
+            return sample_distribution(diag, u, self.ctx.device)
         self.flush()
         if logical_order:
             self.restore_layout()

@@ -64,33 +64,35 @@ def kraus_superoperator(operators):
 
 
 class DeviceDensity(object):
-    """rho resident on the device, quacking enough like the reference's ``csc_matrix`` result
+    """rho resident on the device(s), quacking enough like the reference's ``csc_matrix`` result
     (``.todense()``, ``.toarray()``, ``.diagonal()``, ``[i, j]``, ``.shape``).
 
-    Two flavours.  ``density()`` and ``apply_kraus()`` hand out SNAPSHOTS that own their buffer (the
-    reference returns an independent matrix from every call, qvm_density.py:391-394): later calls on
-    the QVM do not change them.  The ``_density`` attribute is a live VIEW of the QVM's buffer (the
-    reference's attribute is the QVM's own matrix too): it flushes the engine's queued gates before
-    every read, follows the QVM as it runs, and raises once the QVM has dropped that buffer."""
+    Two flavours.  ``density()`` and ``apply_kraus()`` hand out SNAPSHOTS that own an engine of their own (the
+    reference returns an independent matrix from every call, qvm_density.py:391-394): later calls on the QVM
+    do not change them.  The ``_density`` attribute is a live VIEW of the QVM's engine (the reference's
+    attribute is the QVM's own matrix too): it flushes queued gates before every read, follows the QVM as it
+    runs, and raises once the QVM has replaced that engine's state."""
 
-    def __init__(self, state, num_qubits, engine=None):
-        self._state = state               # _native.DeviceState holding the 2n-qubit vector
-        self._engine = engine             # live view: flush pending gates / restore the layout before reading
+    def __init__(self, engine, num_qubits, live=False):
+        self._engine = engine             # Engine / ShardedEngine holding the 2n-qubit vector
+        self._live_state = engine.state if live else None
         self.num_qubits = num_qubits
         dim = 1 << num_qubits
         self.shape = (dim, dim)
         self.dtype = np.dtype(np.complex128)
 
-    def _sync_view(self):
-        if self._engine is not None:
-            if self._engine.state is not self._state:
-                raise RuntimeError("this view of the QVM's density matrix is stale: the QVM has since replaced its "
-                                   "state (density() returns independent snapshots)")
-            self._engine.restore_layout()
+    @property
+    def _state(self):                     # (single-GPU engines: the raw DeviceState; kept for `_density = rho`)
+        return self._engine.state
+
+    def _check(self):
+        if self._live_state is not None and self._engine.state is not self._live_state:
+            raise RuntimeError("this view of the QVM's density matrix is stale: the QVM has since replaced its "
+                               "state (density() returns independent snapshots)")
 
     def toarray(self):
-        self._sync_view()
-        return self._state.get_state().reshape(self.shape)
+        self._check()
+        return self._engine.amplitudes().reshape(self.shape)
 
     def todense(self):
         return np.asmatrix(self.toarray())
@@ -100,9 +102,12 @@ class DeviceDensity(object):
         return sps.csc_matrix(self.toarray())
 
     def diagonal(self):
-        self._sync_view()
+        self._check()
         dim = self.shape[0]
-        return self._state.get_strided(0, dim + 1, dim)
+        eng = self._engine
+        if isinstance(eng, _engine.Engine) and eng.layout_is_identity():
+            return eng.strided(0, dim + 1, dim)
+        return eng.density_diag(self.num_qubits).astype(np.complex128)
 
     def trace(self):
         return np.sum(self.diagonal())
@@ -111,8 +116,8 @@ class DeviceDensity(object):
         i, j = key
         dim = self.shape[0]
         i, j = int(i) % dim, int(j) % dim
-        self._sync_view()
-        return self._state.get_state(i * dim + j, 1)[0]
+        self._check()
+        return self._engine.probe([i * dim + j])[0]
 
     def __array__(self, dtype=None, copy=None):
         a = self.toarray()
@@ -143,17 +148,19 @@ class QVM_Density(QAM):
             self._engine.close()
             self._engine = None
         if self._engine is None:
-            self._engine = _engine.Engine(2 * n, device=self.device)
-            # rho is handed out as a view of the raw buffer (DeviceDensity) and its trace / diagonal kernels
-            # address rows and columns by position: keep every qubit on its own position
-            self._engine.relabel = False
+            # one GPU, or -- when sharding is enabled in this process -- the 2n-qubit vector split by its top
+            # positions, i.e. by rows of rho (reference: one csc_matrix, qvm_density.py:390-391)
+            self._engine = _engine.make_engine(2 * n, device=self.device)
+            if isinstance(self._engine, _engine.Engine):
+                # single GPU: 2n <= 28 positions in practice; relabelling saves no pass there (profiles/README.md)
+                self._engine.relabel = False
         return self._engine
 
     @property
     def _density(self):
         if self._engine is None:
             return None
-        return DeviceDensity(self._engine.state, self._engine.n // 2, engine=self._engine)
+        return DeviceDensity(self._engine, self._engine.n // 2, live=True)
 
     @_density.setter
     def _density(self, value):
@@ -164,8 +171,13 @@ class QVM_Density(QAM):
             return
         if isinstance(value, DeviceDensity):
             eng = self._engine_for(value.num_qubits)
-            if value._state is not eng.state:
-                eng.adopt(value._state)
+            if value._engine is eng:
+                return
+            if isinstance(eng, _engine.Engine) and isinstance(value._engine, _engine.Engine):
+                value._engine.restore_layout()
+                eng.adopt(value._engine.state)          # takes the buffer over (no copy)
+            else:
+                eng.set_amplitudes(value.toarray().reshape(-1))
             return
         dense = value.toarray() if hasattr(value, "toarray") else np.asarray(value)
         if dense.ndim != 2 or dense.shape[0] != dense.shape[1] or dense.shape[0] & (dense.shape[0] - 1):
@@ -218,7 +230,7 @@ class QVM_Density(QAM):
         Returns (outcome, p0).  (Reference :120-143 returns the collapse operator instead.)"""
         n = self.num_qubits
         p0 = self._engine.density_prob_zero(n, qubit_index)
-        if np.random.random() < p0:
+        if _engine.shared_uniform(self._engine, _engine.host_uniforms(self._engine)) < p0:
             outcome, scale = 0, 1.0 / np.sqrt(p0)
         else:
             outcome, scale = 1, 1.0 / np.sqrt(1 - p0)
@@ -303,14 +315,12 @@ class QVM_Density(QAM):
         n = self.num_qubits
         if self._engine is None or self._engine.n != 2 * n:
             raise ValueError("no density of %r qubits is loaded" % (n,))
-        scratch = _engine.Engine.from_state(self._engine.clone_state(), self._engine.tile_bits,
-                                            self._engine.low_bits)
-        scratch.relabel = False
         if not (0 <= index < n):
             raise ValueError("Gate index out of range!")
+        scratch = self._engine.clone()
         scratch.queue_matrix(kraus_superoperator(operators), [index + n, index])
         scratch.flush()
-        return DeviceDensity(scratch.state, n)
+        return DeviceDensity(scratch, n)
 
     def transition(self, instruction):
         self._pre(instruction)
@@ -329,7 +339,7 @@ class QVM_Density(QAM):
     def density(self, pyquil_program):
         """Density matrix of a program (starts from |0..0><0..0|)."""
         self._simulate_density(pyquil_program)
-        return DeviceDensity(self._engine.clone_state(), self.num_qubits)       # an independent snapshot
+        return DeviceDensity(self._engine.clone(), self.num_qubits)             # an independent snapshot
 
     _HOOKS = ("_pre", "_post", "transition", "_transition", "measurement", "kernel", "load_program", "apply_kraus")
 
@@ -345,8 +355,11 @@ class QVM_Density(QAM):
         replayed afterwards (referenceqvm/_compiled.py); MEASURE and classical instructions always step."""
         if not isinstance(pyquil_program, Program):
             raise TypeError("I can only generate from pyQuil programs")
-        cache = self.plan_cache and _compiled.uses_base_hooks(self, QVM_Density, self._HOOKS)
+        cache = (self.plan_cache and _compiled.uses_base_hooks(self, QVM_Density, self._HOOKS)
+                 and (self._engine is None or isinstance(self._engine, _engine.Engine)))
         entry = _compiled.lookup(pyquil_program, self._plan_key()) if cache else None
+        if entry is not None and not isinstance(self._engine_for(entry.num_qubits), _engine.Engine):
+            entry = None
         if entry is not None:
             self.defgate_set = entry.defgate_set
             self.program = pyquil_program
@@ -359,7 +372,7 @@ class QVM_Density(QAM):
         self.load_program(pyquil_program)
         eng = self._engine_for(self.num_qubits)
         eng.reset()
-        k = _compiled.gate_prefix_length(pyquil_program) if cache else 0
+        k = _compiled.gate_prefix_length(pyquil_program) if cache and isinstance(eng, _engine.Engine) else 0
         if k:
             eng.begin_recording()
             try:
@@ -392,7 +405,7 @@ class QVM_Density(QAM):
         seeded call returns the reference's draws; bitstrings are big-endian (:449-451)."""
         self._simulate_density(pyquil_program)
         n = self.num_qubits
-        uniforms = np.random.random_sample(trials)
+        uniforms = _engine.host_uniforms(self._engine, trials)
         indices, total = self._engine.sample(uniforms, mode=1, n_rho=n)
         if abs(total - 1.0) > 1e-8:
             raise ValueError("probabilities do not sum to 1")

@@ -206,7 +206,7 @@ class QVM_Wavefunction(QAM):
         signature compatibility: a host vector is uploaded first."""
         if psi is not None:
             self.wf = psi
-        return self._engine.measure(self._virt[qubit_index], np.random.random())
+        return self._engine.measure(self._virt[qubit_index], _engine.host_uniforms(self._engine))
 
     def _transition(self, instruction):
         if isinstance(instruction, Measurement):
@@ -248,7 +248,7 @@ class QVM_Wavefunction(QAM):
                     run.append(self.program[j])
                     j += 1
                 if len(run) > 1:
-                    uniforms = [np.random.random() for _ in run]
+                    uniforms = [_engine.host_uniforms(self._engine) for _ in run]
                     outcomes = self._engine.measure_many([self._virt[value_get(m.qubit)] for m in run], uniforms)
                     for m, (outcome, _) in zip(run, outcomes):
                         self.classical_memory[value_get(m.classical_reg)] = outcome
@@ -336,7 +336,7 @@ class QVM_Wavefunction(QAM):
         mask = self._address_mask(classical_addresses)
         while self.program_counter < split:
             self.transition(self.current_instruction())
-        indices, _ = self._engine.sample(np.random.random_sample(trials), physical=True)
+        indices, _ = self._engine.sample(_engine.host_uniforms(self._engine, trials), physical=True)
         memory = np.repeat(self.classical_memory[None, :], trials, axis=0)
         bits = _index_bits(indices, self.num_qubits)
         for instr in list(pyquil_program)[split:]:
@@ -472,7 +472,9 @@ class QVM_Wavefunction(QAM):
             t1 = time.perf_counter()
             self._engine.sync()
             t2 = time.perf_counter()
-            indices, _ = self._engine.sample(np.random.random_sample(trials), physical=True)
+            uniforms = _engine.host_uniforms(self._engine, trials)
+            t2b = time.perf_counter()
+            indices, _ = self._engine.sample(uniforms, physical=True)
             t3 = time.perf_counter()
             bits = _index_bits(indices, self.num_qubits)
             # column num_qubits is never set: it stands in for qubits beyond the register
@@ -480,7 +482,8 @@ class QVM_Wavefunction(QAM):
                    for q in qubits]
             out = _rows_to_lists(np.take(bits, sel, axis=1))
             #: where the last call's wall time went (bench.py reports it as e2e.breakdown)
-            self.last_timing = {"program_walk_s": t1 - t0, "plan_launch_sync_s": t2 - t1, "cdf_and_draws_s": t3 - t2,
+            self.last_timing = {"program_walk_s": t1 - t0, "plan_launch_sync_s": t2 - t1, "host_uniforms_s": t2b - t2,
+                                "cdf_and_draws_s": t3 - t2b,
                                 "bits_to_lists_s": time.perf_counter() - t3}
             return out
 
@@ -490,7 +493,7 @@ class QVM_Wavefunction(QAM):
             inside = [q for q in qubits if q < self.num_qubits]
             if hasattr(self._engine, "measure_many") and len(set(inside)) == len(inside) > 1:
                 # one uniform per measured qubit, in the order the loop below would draw them
-                uniforms = [np.random.random() for _ in inside]
+                uniforms = [_engine.host_uniforms(self._engine) for _ in inside]
                 outcomes = iter(self._engine.measure_many([self._virt[q] for q in inside], uniforms))
                 trial_results = [next(outcomes)[0] if q < self.num_qubits else 0 for q in qubits]
                 results.append(trial_results)
@@ -498,7 +501,7 @@ class QVM_Wavefunction(QAM):
             trial_results = []
             for qubit_index in qubits:
                 if qubit_index < self.num_qubits:
-                    measured_val, _ = self._engine.measure(self._virt[qubit_index], np.random.random())
+                    measured_val, _ = self._engine.measure(self._virt[qubit_index], _engine.host_uniforms(self._engine))
                 else:
                     measured_val = 0
                 trial_results.append(measured_val)

@@ -193,6 +193,26 @@ class NumpyShard(object):
         np.add.at(hist, (bins, idx & 31), np.abs(self.psi) ** 2)
         return hist
 
+    def density_diag(self, n_rho, pos_of):
+        """Model of qvm_density_diag: the diagonal entries this shard owns, through the layout."""
+        i = np.arange(1 << n_rho, dtype=np.int64)
+        phys = np.zeros_like(i)
+        for q in range(n_rho):
+            bit = (i >> q) & 1
+            phys |= (bit << pos_of[q]) | (bit << pos_of[q + n_rho])
+        mine = (phys >> self.n_local) == self.ctx.rank
+        out = np.zeros(1 << n_rho)
+        out[mine] = self.psi[phys[mine] & ((1 << self.n_local) - 1)].real
+        return out
+
+    def copy_from(self, other):
+        self.psi = other.psi.copy()
+
+    def sample_distribution(self, probabilities, uniforms):
+        cdf = np.cumsum(probabilities)
+        idx = np.minimum(np.searchsorted(cdf, np.asarray(uniforms) * cdf[-1], side="right"), cdf.size - 1)
+        return idx.astype(np.uint64), float(cdf[-1])
+
     def _half_index(self, bit, value, off, cnt):
         j = np.arange(off, off + cnt, dtype=np.int64)
         lo = j & ((1 << bit) - 1)

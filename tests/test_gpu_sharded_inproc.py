@@ -130,3 +130,70 @@ def test_sharded_engine_on_one_gpu(world, exchange):
         assert all(f[2] + f[3] >= f[0] for f in facts.values()), facts
         assert sum(f[1] for f in facts.values()) > 0 and sum(f[2] for f in facts.values()) > 0, facts
         assert facts[1][4] > 0 or facts[2][4] > 0, facts          # specialised kernels carried pushes too
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_density_qvm_on_one_gpu(world):
+    """QVM_Density with rho sharded by rows over G in-process ranks (CUDA kernels, push exchange): density() under
+    T2 dephasing on every qubit, diagonal / element reads through the layout, seeded sampling from diag(rho)
+    (numpy's choice() stream), MEASURE on rho, apply_kraus -- against the oracle ("Density" row)."""
+    from _programs import oracle_ops as prog_ops
+    from referenceqvm.qvm_density import INFINITY, NoiseModel
+
+    def oracle_vec(prog, n, p1q=None, p2q=None):
+        vec = np.zeros(4 ** n, dtype=complex)
+        vec[0] = 1.0
+        for _, m, q in prog_ops(prog):
+            vec = orc.fast_density_gate(vec, m, q, n)
+            if p1q is not None:
+                p = p1q if len(q) == 1 else p2q
+                for i in range(n):
+                    vec = orc.fast_apply_kraus(vec, G.dephasing(p), i, n)
+        return vec
+
+    def rank_main(comm):
+        _sharded.enable(device=0, comm=comm)
+        try:
+            n = 7
+            spec = [("H", [], [q]) for q in range(n)] + orc.random_circuit_spec(n, 3, 1234)
+            prog = spec_program(spec)
+            nm = NoiseModel(T1=INFINITY, T2=30e-6, gate_time_1q=50e-9, gate_time_2q=150e-9, ro_fidelity=1.0)
+            qvm = QVMConnection(type_trans="density", noise_model=nm)
+            rho = qvm.density(prog)
+            assert isinstance(qvm._engine, _sharded.ShardedEngine) and qvm._engine.swaps > 0
+            p1, p2 = 1.0 - np.exp(-50e-9 / 30e-6), 1.0 - np.exp(-150e-9 / 30e-6)
+            want = orc.vec_to_rho(oracle_vec(prog, n, p1, p2), n)
+            assert np.max(np.abs(np.asarray(rho.todense()) - want)) < 1e-12
+            assert np.max(np.abs(rho.diagonal() - np.diag(want))) < 1e-12
+            assert abs(rho[3, 5] - want[3, 5]) < 1e-12
+            assert abs(np.sum(qvm._density.diagonal()).real - 1.0) < 1e-12
+            np.random.seed(17)
+            shots = qvm.run_and_measure(prog, trials=500)
+            ref = orc.inverse_cdf_sample(np.diag(want).real, np.random.RandomState(17).random_sample(500))
+            assert [int("".join(map(str, s)), 2) for s in shots] == [int(i) for i in ref]
+            plain = QVMConnection(type_trans="density")
+            mprog = spec_program(spec)
+            mprog.measure(2, [0]).measure(6, [1])
+            np.random.seed(5)
+            plain.density(mprog)
+            rs = np.random.RandomState(5)
+            vec = oracle_vec(spec_program(spec), n)
+            outcomes = []
+            for q in (2, 6):
+                p0 = orc.fast_density_prob_zero(vec, q, n)
+                o = 0 if rs.random_sample() < p0 else 1
+                outcomes.append(o)
+                vec = orc.fast_density_collapse(vec, q, o, p0 if o == 0 else 1 - p0, n)
+            assert [int(b) for b in plain.classical_memory[[0, 1]]] == outcomes
+            assert np.max(np.abs(np.asarray(plain._density.todense()) - orc.vec_to_rho(vec, n))) < 1e-12
+            before = np.asarray(plain._density.todense())
+            out = plain.apply_kraus(G.bit_flip(0.2), 1)
+            assert np.max(np.abs(np.asarray(out.todense()) - orc.vec_to_rho(
+                orc.fast_apply_kraus(orc.rho_to_vec(before), G.bit_flip(0.2), 1, n), n))) < 1e-12
+            assert np.max(np.abs(np.asarray(plain._density.todense()) - before)) == 0
+            qvm._engine.close()
+            plain._engine.close()
+        finally:
+            _sharded.disable()
+
+    run_ranks(world, rank_main)

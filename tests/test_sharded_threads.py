@@ -57,3 +57,77 @@ def test_push_exchange_host_logic(world):
     # the fused path was exercised: some epochs rode on a gate pass
     assert sum(v[1] for v in seen.values()) > 0, seen
     assert all(v[1] == v[2] for v in seen.values()), seen
+
+
+def density_oracle(prog, n, p1q=None, p2q=None):
+    from _programs import oracle_ops as prog_ops
+    vec = np.zeros(4 ** n, dtype=complex)
+    vec[0] = 1.0
+    for _, m, q in prog_ops(prog):
+        vec = orc.fast_density_gate(vec, m, q, n)
+        if p1q is not None:
+            p = p1q if len(q) == 1 else p2q
+            for i in range(n):
+                vec = orc.fast_apply_kraus(vec, G.dephasing(p), i, n)
+    return vec
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_density_qvm_host_logic(world):
+    """QVM_Density on a sharded engine (rho split by rows; numpy backend, thread ranks): density(), the layout-aware
+    diagonal, MEASURE on rho, sampling from diag(rho), apply_kraus -- all against the oracle."""
+    from _programs import spec_program
+    from referenceqvm.api import QVMConnection
+    from referenceqvm.qvm_density import INFINITY, NoiseModel
+
+    def rank_main(comm):
+        _sharded.enable(device=0, comm=comm, backend_factory=NumpyShard,
+                        engine_options={"tile_bits": 5, "low_bits": 2, "exchange": "push"})
+        try:
+            n = 5
+            spec = [("H", [], [q]) for q in range(n)] + orc.random_circuit_spec(n, 3, 1234)
+            prog = spec_program(spec)
+            nm = NoiseModel(T1=INFINITY, T2=30e-6, gate_time_1q=50e-9, gate_time_2q=150e-9, ro_fidelity=1.0)
+            qvm = QVMConnection(type_trans="density", noise_model=nm)
+            rho = qvm.density(prog)
+            assert isinstance(qvm._engine, _sharded.ShardedEngine) and qvm._engine.swaps > 0
+            p1, p2 = 1.0 - np.exp(-50e-9 / 30e-6), 1.0 - np.exp(-150e-9 / 30e-6)
+            want = orc.vec_to_rho(density_oracle(prog, n, p1, p2), n)
+            got = np.asarray(rho.todense())
+            assert np.max(np.abs(got - want)) < 1e-12
+            assert np.max(np.abs(rho.diagonal() - np.diag(want))) < 1e-12
+            assert abs(rho[3, 5] - want[3, 5]) < 1e-12
+            # the live view, read through the (non-identity) layout
+            assert np.max(np.abs(qvm._density.diagonal().real - np.diag(want).real)) < 1e-12
+            # sampling from diag(rho): numpy's choice() stream (rank 0's uniforms)
+            np.random.seed(17)
+            shots = qvm.run_and_measure(prog, trials=200)
+            u = np.random.RandomState(17).random_sample(200)
+            ref = orc.inverse_cdf_sample(np.diag(want).real, u)
+            assert [int("".join(map(str, s)), 2) for s in shots] == [int(i) for i in ref]
+            # MEASURE on rho (noise-free QVM): p0 and the collapse follow the oracle with the same uniform
+            plain = QVMConnection(type_trans="density")
+            mprog = spec_program(spec)
+            mprog.measure(2, [0]).measure(4, [1])
+            np.random.seed(5)
+            plain.density(mprog)
+            rs = np.random.RandomState(5)
+            vec = density_oracle(spec_program(spec), n)
+            outcomes = []
+            for q in (2, 4):
+                p0 = orc.fast_density_prob_zero(vec, q, n)
+                o = 0 if rs.random_sample() < p0 else 1
+                outcomes.append(o)
+                vec = orc.fast_density_collapse(vec, q, o, p0 if o == 0 else 1 - p0, n)
+            assert [int(b) for b in plain.classical_memory[[0, 1]]] == outcomes
+            assert np.max(np.abs(np.asarray(plain._density.todense()) - orc.vec_to_rho(vec, n))) < 1e-12
+            # apply_kraus leaves the QVM's rho alone and returns the channel's result
+            before = np.asarray(plain._density.todense())
+            out = plain.apply_kraus(G.bit_flip(0.2), 1)
+            assert np.max(np.abs(np.asarray(out.todense()) - orc.vec_to_rho(
+                orc.fast_apply_kraus(orc.rho_to_vec(before), G.bit_flip(0.2), 1, n), n))) < 1e-12
+            assert np.max(np.abs(np.asarray(plain._density.todense()) - before)) == 0
+        finally:
+            _sharded.disable()
+
+    run_ranks(world, rank_main)
