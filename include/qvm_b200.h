@@ -235,6 +235,20 @@ int qvm_density_prob_zero(qvm_t* q, int n_rho_qubits, int qubit, double* p0_part
  * shards' arrays add up to the full diagonal exactly). */
 int qvm_density_diag(qvm_t* q, int n_rho_qubits, const int32_t* pos_of, double* diag_host);
 
+/* ---- expectation values (the reference declares expectation() and leaves it NotImplementedError:
+ * qvm_density.py:396-408, qvm_unitary.py:99-112; the operator it documents is tensor_up(PauliSum),
+ * unitary_generator.py:366-411) ------------------------------------------------------------------------------ */
+/* One Pauli string on a state vector.  With xmask = positions of its X and Y factors (local positions only) and
+ * zmask = positions of its Z and Y factors (any position), P|x> = i^ny (-1)^popcount(x & zmask) |x ^ xmask>;
+ * re_im_partial receives this shard's sum_x conj(psi[x ^ xmask]) (-1)^popcount(x & zmask) psi[x] (the caller adds
+ * the shards and multiplies by i^ny and the term's coefficient).  One read pass. */
+int qvm_pauli_expectation(qvm_t* q, uint64_t xmask, uint64_t zmask, double* re_im_partial);
+/* rho[i, i ^ col_xor] for all 2^n_rho rows i through a layout (as qvm_density_diag, complex, 0 where not owned):
+ * tr(rho P) = i^ny sum_i (-1)^popcount(i & zmask) rho[i, i ^ xmask]. */
+int qvm_density_offdiag(qvm_t* q, int n_rho_qubits, const int32_t* pos_of, uint64_t col_xor, double* re_im_host);
+/* sum_x conj(a[x]) b[x] over two shards of equal shape on one device (general operator programs: <psi|O psi>). */
+int qvm_inner_product(qvm_t* a, qvm_t* b, double* re_im_partial);
+
 /* ---- sampling (qvm_density.py:442-452; statistical meaning of qvm_wavefunction.py:266-321) ----- */
 /* Build the two-level CDF of |amp|^2 (mode 0), of diag(rho) (mode 1, n_rho_qubits = n, identity layout, rows
  * sharded), or of a plain array of 2^(n_local+1) probabilities that the caller stored in the handle's buffer

@@ -301,6 +301,42 @@ def fast_density_collapse(vec, qubit, outcome, p_outcome, num_qubits):
 
 
 # -- sampling -----------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------------
+# expectation values: the operator is the reference's tensor_up(PauliSum)
+# --------------------------------------------------------------------------------------------
+_PAULI = {"I": np.eye(2, dtype=complex), "X": np.array([[0, 1], [1, 0]], dtype=complex),
+          "Y": np.array([[0, -1j], [1j, 0]]), "Z": np.array([[1, 0], [0, -1]], dtype=complex)}
+
+
+def ref_tensor_up(terms, num_qubits):
+    """Dense matrix of a Pauli sum given as [(coefficient, {qubit: 'X'|'Y'|'Z'})].
+
+    Follows reference ``unitary_generator.py:366-411`` (tensor_up): per term the left Kronecker product
+    kron(P_q, acc) for q = 0 .. n-1 (qubit 0 is the least significant index bit), times the coefficient,
+    summed; IndexError when a term reaches beyond the register (:393-396)."""
+    dim = 2 ** num_qubits
+    total = np.zeros((dim, dim), dtype=complex)
+    for coefficient, ops in terms:
+        if ops and max(ops) >= num_qubits:
+            raise IndexError("pauli_terms has higher index than qubits")
+        acc = np.array([[1.0 + 0j]])
+        for q in range(num_qubits):
+            acc = np.kron(_PAULI[ops.get(q, "I")], acc)
+        total += coefficient * acc
+    return total
+
+
+def expectation_state(psi, terms, num_qubits):
+    """<psi| tensor_up(terms) |psi> (the meaning of the QVM's expectation(); the reference's own methods raise
+    NotImplementedError, qvm_unitary.py:99-112)."""
+    return complex(np.vdot(psi, ref_tensor_up(terms, num_qubits).dot(psi)))
+
+
+def expectation_density(rho, terms, num_qubits):
+    """tr(rho tensor_up(terms))."""
+    return complex(np.trace(np.asarray(rho).dot(ref_tensor_up(terms, num_qubits))))
+
+
 def inverse_cdf_sample(probabilities, uniforms):
     """Index draws the way numpy's legacy ``RandomState.choice(p=)`` makes them (reference
     ``qvm_density.py:445-447``): cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(u, 'right')."""

@@ -1385,6 +1385,72 @@ int qvm_density_diag(qvm_t* q, int n_rho, const int32_t* pos_of, double* diag_ho
     return QVM_OK;
 }
 
+int qvm_density_offdiag(qvm_t* q, int n_rho, const int32_t* pos_of, uint64_t col_xor, double* re_im_host) {
+    QVM_CHECK_HANDLE(q);
+    if (!pos_of || !re_im_host) return fail(QVM_ERR_INVALID, "null pointer");
+    if (n_rho < 1 || n_rho > 31 || 2 * n_rho != total_positions(q))
+        return fail(QVM_ERR_INVALID, "state is not a %d-qubit rho", n_rho);
+    if (col_xor >> n_rho) return fail(QVM_ERR_INVALID, "column mask outside the %d-qubit register", n_rho);
+    DiagLayout lay{};
+    uint64_t seen = 0;
+    for (int v = 0; v < 2 * n_rho; ++v) {
+        const int p = pos_of[v];
+        if (p < 0 || p >= 2 * n_rho || ((seen >> p) & 1ull)) return fail(QVM_ERR_INVALID, "layout is not a permutation");
+        seen |= 1ull << p;
+        (v < n_rho ? lay.pos_col[v] : lay.pos_row[v - n_rho]) = (uint8_t)p;
+    }
+    const uint64_t n = 1ull << n_rho;
+    double2* dev = nullptr;
+    QVM_CUDA(q, cudaMallocAsync(&dev, n * sizeof(double2), q->stream));
+    density_offdiag_kernel<<<grid_for(q, n, 256), 256, 0, q->stream>>>(q->amps, n_rho, lay, q->n_local, q->shard_index,
+                                                                      col_xor, dev);
+    int rc = cudaGetLastError() == cudaSuccess ? QVM_OK : fail(QVM_ERR_CUDA, "density_offdiag_kernel launch failed");
+    if (rc == QVM_OK) rc = copy_chunked(q, dev, re_im_host, n, false);
+    cudaFreeAsync(dev, q->stream);
+    if (rc != QVM_OK) return rc;
+    q->stats.kernel_launches += 1;
+    q->stats.d2h_bytes += n * sizeof(double2);
+    return QVM_OK;
+}
+
+static int reduce_partials2(qvm_state* q, int n_blocks, double* re_im) {
+    final_sum2_kernel<<<1, kReduceThreads, 0, q->stream>>>(q->partials, n_blocks, q->result_dev);
+    QVM_CUDA(q, cudaGetLastError());
+    QVM_CUDA(q, cudaMemcpyAsync(q->result_host, q->result_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, q->stream));
+    QVM_CUDA(q, cudaStreamSynchronize(q->stream));
+    re_im[0] = q->result_host[0];
+    re_im[1] = q->result_host[1];
+    q->stats.kernel_launches += 2;
+    q->stats.d2h_bytes += 2 * sizeof(double);
+    return QVM_OK;
+}
+
+int qvm_pauli_expectation(qvm_t* q, uint64_t xmask, uint64_t zmask, double* re_im_partial) {
+    QVM_CHECK_HANDLE(q);
+    if (!re_im_partial) return fail(QVM_ERR_INVALID, "null pointer");
+    const int npos = total_positions(q);
+    if (xmask >> q->n_local) return fail(QVM_ERR_INVALID, "X / Y factors must sit on local positions (remap them first)");
+    if (npos < 64 && (zmask >> npos)) return fail(QVM_ERR_INVALID, "Z mask outside the register");
+    const int grid = std::min(grid_for(q, q->n_elems, kReduceThreads), kPartialsCap / 2);
+    pauli_partial_kernel<<<grid, kReduceThreads, 0, q->stream>>>(q->amps, q->n_elems, xmask, zmask,
+                                                                 q->shard_index << q->n_local, q->partials);
+    QVM_CUDA(q, cudaGetLastError());
+    q->stats.hbm_bytes += 32ull * q->n_elems;
+    return reduce_partials2(q, grid, re_im_partial);
+}
+
+int qvm_inner_product(qvm_t* a, qvm_t* b, double* re_im_partial) {
+    QVM_CHECK_HANDLE(a);
+    if (!b || !re_im_partial) return fail(QVM_ERR_INVALID, "null pointer");
+    if (a->n_local != b->n_local || a->device != b->device) return fail(QVM_ERR_INVALID, "shards of different shape");
+    QVM_CUDA(b, cudaStreamSynchronize(b->stream));
+    const int grid = std::min(grid_for(a, a->n_elems, kReduceThreads), kPartialsCap / 2);
+    inner_partial_kernel<<<grid, kReduceThreads, 0, a->stream>>>(a->amps, b->amps, a->n_elems, a->partials);
+    QVM_CUDA(a, cudaGetLastError());
+    a->stats.hbm_bytes += 32ull * a->n_elems;
+    return reduce_partials2(a, grid, re_im_partial);
+}
+
 int qvm_collapse(qvm_t* q, int qubit, int outcome, double scale) {
     QVM_CHECK_HANDLE(q);
     if (qubit < 0 || qubit >= total_positions(q)) return fail(QVM_ERR_INVALID, "qubit %d out of range", qubit);

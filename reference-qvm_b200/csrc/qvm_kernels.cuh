@@ -526,6 +526,78 @@ struct DiagLayout {
     uint8_t pos_col[32];
     uint8_t pos_row[32];
 };
+// rho[i, i ^ col_xor] for every row i, through the layout (complex; owned entries, 0 elsewhere): the entries a
+// Pauli string's trace tr(rho P) touches -- P maps |i> to a phase times |i ^ xmask>.  col_xor = 0: the diagonal.
+__global__ void density_offdiag_kernel(const double2* __restrict__ state, int n_rho, const DiagLayout lay, int n_local,
+                                       uint64_t shard_index, uint64_t col_xor, double2* __restrict__ out) {
+    const uint64_t n = 1ull << n_rho;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t col = i ^ col_xor;
+        uint64_t phys = 0;
+        for (int q = 0; q < n_rho; ++q) {
+            if ((i >> q) & 1ull) phys |= 1ull << lay.pos_row[q];
+            if ((col >> q) & 1ull) phys |= 1ull << lay.pos_col[q];
+        }
+        out[i] = (phys >> n_local) == shard_index ? state[phys & ((1ull << n_local) - 1ull)] : make_double2(0.0, 0.0);
+    }
+}
+
+// Expectation of a Pauli string on a state vector (reference: QVM expectation() is NotImplementedError,
+// qvm_unitary.py:99-112; its meaning is <psi| tensor_up(P) |psi>, unitary_generator.py:366-411).
+// P|x> = i^ny (-1)^popcount(x & zmask) |x ^ xmask> (xmask: X and Y qubits, zmask: Z and Y qubits), hence
+// <psi|P|psi> = i^ny * sum_x conj(psi[x ^ xmask]) (-1)^popcount(x & zmask) psi[x]: one pass, the partial sums of
+// the real and imaginary parts go to partials[2 * block], [2 * block + 1].  xmask is local; zmask may reach the
+// shard bits (`full`).
+__global__ void pauli_partial_kernel(const double2* __restrict__ state, uint64_t n_elems, uint64_t xmask, uint64_t zmask,
+                                     uint64_t shard_bits, double* __restrict__ partials) {
+    __shared__ double scratch[33];
+    double re = 0.0, im = 0.0;
+    for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < n_elems; x += (uint64_t)gridDim.x * blockDim.x) {
+        const double2 a = state[x];
+        const double2 b = state[x ^ xmask];
+        const double s = (__popcll((x | shard_bits) & zmask) & 1) ? -1.0 : 1.0;
+        re += s * (b.x * a.x + b.y * a.y);          // conj(b) * a
+        im += s * (b.x * a.y - b.y * a.x);
+    }
+    re = block_sum(re, scratch);
+    im = block_sum(im, scratch);
+    if (threadIdx.x == 0) {
+        partials[2 * blockIdx.x] = re;
+        partials[2 * blockIdx.x + 1] = im;
+    }
+}
+// sum_x conj(a[x]) b[x] of two shards of equal shape (general operator programs: <psi|O psi>)
+__global__ void inner_partial_kernel(const double2* __restrict__ a, const double2* __restrict__ b, uint64_t n_elems,
+                                     double* __restrict__ partials) {
+    __shared__ double scratch[33];
+    double re = 0.0, im = 0.0;
+    for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < n_elems; x += (uint64_t)gridDim.x * blockDim.x) {
+        const double2 u = a[x], v = b[x];
+        re += u.x * v.x + u.y * v.y;
+        im += u.x * v.y - u.y * v.x;
+    }
+    re = block_sum(re, scratch);
+    im = block_sum(im, scratch);
+    if (threadIdx.x == 0) {
+        partials[2 * blockIdx.x] = re;
+        partials[2 * blockIdx.x + 1] = im;
+    }
+}
+// out[0] = sum of partials[2 b], out[1] = sum of partials[2 b + 1] (blocks in ascending order)
+__global__ void final_sum2_kernel(const double* __restrict__ partials, int n, double* __restrict__ out) {
+    __shared__ double scratch[33];
+    double re = 0.0, im = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        re += partials[2 * i];
+        im += partials[2 * i + 1];
+    }
+    re = block_sum(re, scratch);
+    im = block_sum(im, scratch);
+    if (threadIdx.x == 0) {
+        out[0] = re;
+        out[1] = im;
+    }
+}
 __global__ void density_diag_kernel(const double2* __restrict__ state, int n_rho, const DiagLayout lay, int n_local,
                                     uint64_t shard_index, double* __restrict__ out) {
     const uint64_t n = 1ull << n_rho;

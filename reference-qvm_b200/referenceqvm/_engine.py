@@ -131,6 +131,16 @@ def shared_uniform(engine, r):
     return r
 
 
+def _signed_sum(values, zmask):
+    """sum_i (-1)^popcount(i & zmask) values[i]."""
+    i = np.arange(values.size, dtype=np.uint64) & np.uint64(zmask)
+    parity = np.zeros(values.size, dtype=np.uint64)
+    while np.any(i):
+        parity ^= i & np.uint64(1)
+        i >>= np.uint64(1)
+    return complex(np.sum(np.where(parity == 1, -values, values)))
+
+
 def sample_distribution(probabilities, uniforms, device=0):
     """Inverse-CDF draws (numpy's ``searchsorted(cumsum, u * total, 'right')``) from a plain array of
     2^k probabilities with the device sampler (``qvm_probs_prepare`` mode 2): returns (indices, total)."""
@@ -415,6 +425,28 @@ class Engine(object):
     def prob_zero(self, qubit):
         self.flush()
         return self.state.prob_zero(self.pos_of[int(qubit)])
+
+    # -- expectation values (referenceqvm/_expectation.py) -----------------------------------------------
+    def pauli_expectation(self, ops):
+        """<psi|P|psi> for the Pauli string ``ops`` = {logical qubit: 'X'|'Y'|'Z'}: one reduction pass."""
+        from referenceqvm._expectation import masks
+        self.flush()
+        xmask, zmask, ny = masks(ops, lambda q: self.pos_of[q])
+        return self.state.pauli_expectation(xmask, zmask) * (1j) ** ny
+
+    def density_pauli_expectation(self, n_rho, ops):
+        """tr(rho P) for the vectorised rho this engine holds: i^ny sum_i (-1)^popcount(i & zmask) rho[i, i ^ xmask]."""
+        from referenceqvm._expectation import masks
+        self.flush()
+        xmask, zmask, ny = masks(ops, lambda q: q)
+        vals = self.state.density_offdiag(n_rho, self.pos_of, xmask)
+        return _signed_sum(vals, zmask) * (1j) ** ny
+
+    def inner_product(self, other):
+        """<self|other> of two engines of equal shape (both brought to the identity layout)."""
+        self.restore_layout()
+        other.restore_layout()
+        return self.state.inner_product(other.state)
 
     def density_diag(self, n_rho):
         """diag(rho) (2^n doubles) of the vectorised rho this engine holds, read through the layout."""

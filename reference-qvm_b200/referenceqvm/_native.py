@@ -90,6 +90,9 @@ _SIGNATURES = {
     "qvm_density_prob_zero": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "qvm_collapse": (C.c_int, [_P, C.c_int, C.c_int, C.c_double]),
     "qvm_density_diag": (C.c_int, [_P, C.c_int, _P, _P]),
+    "qvm_density_offdiag": (C.c_int, [_P, C.c_int, _P, C.c_uint64, _P]),
+    "qvm_pauli_expectation": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P]),
+    "qvm_inner_product": (C.c_int, [_P, _P, _P]),
     "qvm_probs_prepare": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "qvm_sample": (C.c_int, [_P, C.c_uint64, _P, _P]),
     "qvm_pack_half": (C.c_int, [_P, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _P]),
@@ -538,6 +541,31 @@ class DeviceState(object):
 
     def collapse(self, qubit, outcome, scale):
         check(lib().qvm_collapse(self.handle, qubit, outcome, scale))
+
+    def density_offdiag(self, n_rho, pos_of, col_xor):
+        """rho[i, i ^ col_xor] for all rows i through the layout (complex, 0 where not owned)."""
+        pos = np.ascontiguousarray(pos_of, dtype=np.int32)
+        out = np.empty(1 << n_rho, dtype=np.complex128)
+        code = lib().qvm_density_offdiag(self.handle, n_rho, pos.ctypes.data, int(col_xor), out.ctypes.data)
+        if code == QVM_ERR_INVALID:
+            raise ValueError(last_error())
+        check(code)
+        return out
+
+    def pauli_expectation(self, xmask, zmask):
+        """This shard's sum_x conj(psi[x ^ xmask]) (-1)^popcount(x & zmask) psi[x] (physical masks)."""
+        out = np.zeros(2, dtype=np.float64)
+        code = lib().qvm_pauli_expectation(self.handle, int(xmask), int(zmask), out.ctypes.data)
+        if code == QVM_ERR_INVALID:
+            raise ValueError(last_error())
+        check(code)
+        return complex(out[0], out[1])
+
+    def inner_product(self, other):
+        """sum_x conj(self[x]) other[x]."""
+        out = np.zeros(2, dtype=np.float64)
+        check(lib().qvm_inner_product(self.handle, other.handle, out.ctypes.data))
+        return complex(out[0], out[1])
 
     def density_diag(self, n_rho, pos_of):
         """This shard's part of diag(rho) under the layout ``pos_of`` (2^n doubles, 0.0 where not owned)."""

@@ -288,6 +288,12 @@ class CudaShard(object):
     def density_diag(self, n_rho, pos_of):
         return self.state.density_diag(n_rho, pos_of)
 
+    def density_offdiag(self, n_rho, pos_of, col_xor):
+        return self.state.density_offdiag(n_rho, pos_of, col_xor)
+
+    def pauli_expectation(self, xmask, zmask):
+        return self.state.pauli_expectation(xmask, zmask)
+
     def copy_from(self, other):
         self.state.copy_from(other.state)
 
@@ -474,6 +480,34 @@ class ShardedEngine(object):
         dup.pos_of = list(self.pos_of)
         dup.relabel = self.relabel
         return dup
+
+    # -- expectation values ------------------------------------------------------------------------------------------
+    def ensure_local(self, qubits):
+        """Bring the listed logical qubits onto local positions (one exchange epoch when any of them is global)."""
+        self.flush()
+        wanted = [q for q in qubits if self.pos_of[q] >= self.n_local]
+        if wanted:
+            self._bring_local(wanted, [], [])
+
+    def pauli_expectation(self, ops):
+        """<psi|P|psi> for a Pauli string {logical qubit: letter}: X / Y factors are made local first, every shard
+        reduces its part (``qvm_pauli_expectation``; Z factors on global positions are signs of the shard), the
+        parts are summed."""
+        from referenceqvm._expectation import masks
+        self.ensure_local([q for q, letter in ops.items() if letter in ("X", "Y")])
+        xmask, zmask, ny = masks(ops, lambda q: self.pos_of[q])
+        part = self.shard.pauli_expectation(xmask, zmask)
+        total = self.comm.allreduce([part.real, part.imag])
+        return complex(total[0], total[1]) * (1j) ** ny
+
+    def density_pauli_expectation(self, n_rho, ops):
+        from referenceqvm._engine import _signed_sum
+        from referenceqvm._expectation import masks
+        self.flush()
+        xmask, zmask, ny = masks(ops, lambda q: q)
+        vals = self.shard.density_offdiag(n_rho, self.pos_of, xmask)
+        vals = self.comm.allreduce(vals.view(np.float64)).view(np.complex128)
+        return _signed_sum(vals, zmask) * (1j) ** ny
 
     # -- density matrices: the state is a vectorised rho of n_rho qubits (rows = the high n_rho vector qubits, so
     # the global positions are row bits) ----------------------------------------------------------------------------

@@ -387,8 +387,37 @@ class QVM_Density(QAM):
                                             len(self.classical_memory), self.defgate_set, True))
         self.kernel()
 
-    def expectation(self, pyquil_program, operator_programs=[Program()]):
-        raise NotImplementedError()
+    def expectation(self, pyquil_program, operator_programs=None):
+        """[tr(rho O) for O in operator_programs] with rho the (noisy) state ``pyquil_program`` prepares.
+
+        The reference declares this method and raises NotImplementedError (qvm_density.py:396-408).  Operators:
+        ``PauliTerm`` / ``PauliSum`` (``tensor_up``'s operator, unitary_generator.py:366-411) or Programs of
+        Pauli gates; each Pauli string is a gather of 2^n entries of rho (referenceqvm/_expectation.py)."""
+        from referenceqvm import _expectation
+        if operator_programs is None:
+            operator_programs = [Program()]
+        self._simulate_density(pyquil_program)
+        n, eng = self.num_qubits, self._engine
+
+        def pauli(ops):
+            return eng.density_pauli_expectation(n, ops)
+
+        def general(program):
+            # tr(rho O) = tr(O rho): O on the row qubits of a copy, then the trace of the copy
+            scratch = eng.clone()
+            try:
+                defs = dict((dg.name, dg.matrix) for dg in program.defined_gates)
+                for instruction in program:
+                    if not isinstance(instruction, Gate):
+                        raise TypeError("operator programs may contain gates only")
+                    matrix, qubits = resolve_gate(self.gate_set, defs, instruction)
+                    _engine.validate_qubits(qubits, n)
+                    scratch.queue_matrix(matrix, [q + n for q in qubits])
+                return complex(np.sum(scratch.density_pauli_expectation(n, {})))
+            finally:
+                scratch.close()
+
+        return [_expectation.evaluate(op, n, pauli, general) for op in operator_programs]
 
     def run(self, pyquil_program, classical_addresses=None, trials=1):
         """Re-simulates per trial and returns the classical memory slices (numpy bool arrays)."""

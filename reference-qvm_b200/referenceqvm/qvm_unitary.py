@@ -69,5 +69,37 @@ class QVM_Unitary(QAM):
         self.kernel()
         return self.umat
 
-    def expectation(self, pyquil_program, operator_programs=[Program()]):
-        raise NotImplementedError()
+    def expectation(self, pyquil_program, operator_programs=None):
+        """[<0|U^dagger O U|0> for O in operator_programs], U the unitary of ``pyquil_program``.
+
+        The reference declares this method and raises NotImplementedError (qvm_unitary.py:99-112).  The
+        prepared state is the first column of U, which the device already holds: it is copied into an n-qubit
+        state and the operators are evaluated there (referenceqvm/_expectation.py)."""
+        from referenceqvm import _expectation
+        if operator_programs is None:
+            operator_programs = [Program()]
+        self.load_program(pyquil_program)
+        self.umat = np.eye(2 ** self.num_qubits)
+        self.kernel()
+        n = self.num_qubits
+        dim = 1 << n
+        column = self._engine.strided(0, dim, dim)              # U[:, 0]: vector index (row << n) | 0
+        psi = _engine.Engine(n, device=self.device)
+        try:
+            psi.set_amplitudes(column)
+
+            def general(program):
+                scratch = psi.clone()
+                try:
+                    defs = dict((dg.name, dg.matrix) for dg in program.defined_gates)
+                    for instruction in program:
+                        matrix, qubits = resolve_gate(self.gate_set, defs, instruction)
+                        _engine.validate_qubits(qubits, n)
+                        scratch.queue_matrix(matrix, qubits)
+                    return psi.inner_product(scratch)
+                finally:
+                    scratch.close()
+
+            return [_expectation.evaluate(op, n, psi.pauli_expectation, general) for op in operator_programs]
+        finally:
+            psi.close()

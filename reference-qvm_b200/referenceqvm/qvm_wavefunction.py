@@ -304,6 +304,40 @@ class QVM_Wavefunction(QAM):
             return Wavefunction(_engine.DeviceAmplitudes(self._engine)), results
         return Wavefunction(self._engine.amplitudes()), results
 
+    def expectation(self, pyquil_program, operator_programs=None):
+        """[<psi|O|psi> for O in operator_programs] with |psi> the state ``pyquil_program`` prepares.
+
+        The pyquil QVM call the reference's QVMs declare but leave unimplemented (qvm_unitary.py:99-112,
+        qvm_density.py:396-408).  Operators: ``PauliTerm`` / ``PauliSum`` (the operator ``tensor_up`` builds,
+        unitary_generator.py:366-411) or gate Programs; default: the identity.  Pauli strings cost one reduction
+        pass each and leave the state alone; other programs run on a copy (referenceqvm/_expectation.py)."""
+        from referenceqvm import _expectation
+        if operator_programs is None:
+            operator_programs = [Program()]
+        self._simulate(pyquil_program, None)
+        eng, virt, n = self._engine, self._virt, self.num_qubits
+
+        def pauli(ops):
+            return eng.pauli_expectation({virt[q]: letter for q, letter in ops.items()})
+
+        def general(program):
+            if not isinstance(eng, _engine.Engine):
+                raise NotImplementedError("operator programs that are not Pauli strings need a single-GPU state")
+            scratch = eng.clone()
+            try:
+                defs = dict((dg.name, dg.matrix) for dg in program.defined_gates)
+                for instruction in program:
+                    if not isinstance(instruction, Gate):
+                        raise TypeError("operator programs may contain gates only")
+                    matrix, qubits = resolve_gate(self.gate_set, defs, instruction)
+                    _engine.validate_qubits(qubits, n)
+                    scratch.queue_matrix(matrix, [virt[q] for q in qubits])
+                return eng.inner_product(scratch)
+            finally:
+                scratch.close()
+
+        return [_expectation.evaluate(op, n, pauli, general) for op in operator_programs]
+
     def _terminal_measure_block(self, program):
         """Index where a purely terminal run of MEASUREs starts, or None when sampling the final
         state would not be equivalent to re-running the program per trial."""

@@ -205,6 +205,30 @@ class NumpyShard(object):
         out[mine] = self.psi[phys[mine] & ((1 << self.n_local) - 1)].real
         return out
 
+    def density_offdiag(self, n_rho, pos_of, col_xor):
+        """Model of qvm_density_offdiag: rho[i, i ^ col_xor] for the rows this shard owns, through the layout."""
+        i = np.arange(1 << n_rho, dtype=np.int64)
+        col = i ^ col_xor
+        phys = np.zeros_like(i)
+        for q in range(n_rho):
+            phys |= (((i >> q) & 1) << pos_of[q + n_rho]) | (((col >> q) & 1) << pos_of[q])
+        mine = (phys >> self.n_local) == self.ctx.rank
+        out = np.zeros(1 << n_rho, dtype=np.complex128)
+        out[mine] = self.psi[phys[mine] & ((1 << self.n_local) - 1)]
+        return out
+
+    def pauli_expectation(self, xmask, zmask):
+        """Model of qvm_pauli_expectation on this shard (physical masks; Z bits may be shard bits)."""
+        x = np.arange(self.psi.size, dtype=np.int64)
+        full = x | (self.ctx.rank << self.n_local)
+        par = np.zeros_like(x)
+        m = full & zmask
+        while np.any(m):
+            par ^= m & 1
+            m >>= 1
+        sign = np.where(par == 1, -1.0, 1.0)
+        return complex(np.sum(np.conj(self.psi[x ^ xmask]) * sign * self.psi))
+
     def copy_from(self, other):
         self.psi = other.psi.copy()
 

@@ -18,6 +18,7 @@ Outputs (all under tests/golden/):
   measure.json/.npz    seeded MEASURE programs: classical memory + collapsed state, RNG stream position
   sampling.json/.npz   seeded density run_and_measure draws (np.random.choice stream)
   unitary.json/.npz    QVM_Unitary outputs
+  expectation.json/.npz  psi^dagger tensor_up(PauliSum) psi and tr(rho tensor_up(PauliSum)) from the reference's pieces
 """
 import collections
 import collections.abc
@@ -365,7 +366,46 @@ def golden_unitary():
     dump("unitary", meta, arrays)
 
 
+def golden_expectation():
+    """Expectation values.  The reference's QVMs declare expectation() and raise NotImplementedError
+    (qvm_unitary.py:99-112, qvm_density.py:396-408); what is stored here is assembled from the reference's own
+    pieces only: its wavefunction / density of a program and its tensor_up(PauliSum) operator
+    (unitary_generator.py:366-411): value = psi^dagger . tensor_up . psi, resp. tr(rho . tensor_up)."""
+    from pyquil.paulis import PauliSum, PauliTerm
+    from referenceqvm.unitary_generator import tensor_up
+    meta, arrays = [], {}
+    wq = QVMConnection()
+    nm = NoiseModel(T1=INFINITY, T2=30e-6, gate_time_1q=50e-9, gate_time_2q=150e-9, ro_fidelity=1.0)
+    dq = QVMConnection(type_trans="density", noise_model=nm)
+    rs = np.random.RandomState(77)
+    for case, (n, depth, seed) in enumerate(((3, 4, 2), (5, 5, 9), (6, 3, 1234))):
+        spec = random_circuit_spec(n, depth, seed)
+        prog = spec_program(spec)
+        psi = np.asarray(wq.wavefunction(prog)[0].amplitudes)
+        rho = np.asarray(dq.density(prog).todense())
+        sums = []
+        for k in range(6):
+            terms = []
+            for _ in range(1 + k % 3):
+                term = PauliTerm("I", 0, complex(rs.uniform(-1, 1), 0.0))
+                for q in rs.permutation(n)[:int(rs.randint(0, n + 1))]:
+                    term = term * PauliTerm("XYZ"[int(rs.randint(3))], int(q))
+                terms.append(term)
+            sums.append(PauliSum(terms))
+        for j, ps in enumerate(sums):
+            op = tensor_up(ps, n)
+            key = "c%d_s%d" % (case, j)
+            arrays[key] = np.array([np.vdot(psi, op.dot(psi)), np.trace(rho.dot(op))])
+            meta.append({"key": key, "n": n, "spec": [[a, list(b), list(c)] for a, b, c in spec],
+                         "terms": [{"re": t.coefficient.real, "im": t.coefficient.imag,
+                                    "ops": {str(q): p for q, p in t._ops.items()}} for t in ps.terms]})
+    dump("expectation", meta, arrays)
+
+
 if __name__ == "__main__":
+    golden_expectation() if "--expectation-only" in sys.argv else None
+    if "--expectation-only" in sys.argv:
+        sys.exit(0)
     golden_gates()
     golden_operators()
     golden_wavefunctions()
@@ -373,4 +413,5 @@ if __name__ == "__main__":
     golden_density()
     golden_sampling()
     golden_unitary()
+    golden_expectation()
     os.system("du -sh %s" % HERE)

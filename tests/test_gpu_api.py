@@ -1,6 +1,8 @@
 """GPU parity, API level: QVMConnection(...).wavefunction / run / run_and_measure / density /
 unitary against (a) fixtures produced by the unmodified reference (tests/golden/) and (b) the
 reference's own test-suite, re-expressed here test for test (file:line cited per test)."""
+import json
+
 import numpy as np
 import pytest
 import scipy.sparse as sps
@@ -770,3 +772,65 @@ def test_compiled_density_program_matches_uncached():
     off.plan_cache = False
     assert np.max(np.abs(a - np.asarray(off.density(prog).todense()))) < 1e-14
     assert np.max(np.abs(a - want)) > 1e-6
+
+
+# ---- expectation values -----------------------------------------------------------------------------------------
+def _golden_terms(case):
+    from pyquil.paulis import PauliSum, PauliTerm
+    terms = []
+    for t in case["terms"]:
+        term = PauliTerm("I", 0, complex(t["re"], t["im"]))
+        for q, p in t["ops"].items():
+            term = term * PauliTerm(p, int(q))
+        terms.append(term)
+    return PauliSum(terms)
+
+
+def test_golden_expectation_values(qvm, qvm_unitary):
+    """expectation() of the wavefunction, unitary and density QVMs against values assembled from the reference's
+    own wavefunction / density and tensor_up (the reference's expectation() is NotImplementedError)."""
+    meta, arrays = load_golden("expectation")
+    nm = NoiseModel(T1=INFINITY, T2=30e-6, gate_time_1q=50e-9, gate_time_2q=150e-9, ro_fidelity=1.0)
+    dq = QVMConnection(type_trans="density", noise_model=nm)
+    by_program = {}
+    for case in meta:
+        by_program.setdefault(json.dumps(case["spec"]), []).append(case)
+    for spec_json, cases in by_program.items():
+        prog = spec_program([(a, b, c) for a, b, c in json.loads(spec_json)])
+        sums = [_golden_terms(c) for c in cases]
+        got_w = qvm.expectation(prog, sums)
+        got_u = qvm_unitary.expectation(prog, sums)
+        got_d = dq.expectation(prog, sums)
+        for case, w, u, d in zip(cases, got_w, got_u, got_d):
+            want_psi, want_rho = arrays[case["key"]]
+            assert abs(w - want_psi) < TOL and abs(u - want_psi) < TOL
+            assert abs(d - want_rho) < TOL
+
+
+def test_expectation_of_operator_programs(qvm):
+    """Operator PROGRAMS (the pyquil 1.x call shape): Pauli-gate programs take the reduction path, anything else is
+    applied to a copy of the state; the prepared state stays untouched between operators; default = identity."""
+    from pyquil.paulis import PauliTerm
+    n = 14
+    spec = orc.random_circuit_spec(n, 5, 12)
+    prog = spec_program(spec)
+    psi, _ = orc.fast_run_wavefunction(oracle_ops(prog), n)
+    ops = [Program().inst(X(0)).inst(Z(13)), Program().inst(H(3)).inst(CNOT(3, 9)), Program().inst(RZ(0.3, 5)),
+           Program().inst(X(2)).inst(X(2)).inst(Y(2)), Program(), PauliTerm("Y", 13) * PauliTerm("X", 12, 2.0)]
+    got = qvm.expectation(prog, ops)
+    want = []
+    for op in ops[:5]:
+        phi, _ = orc.fast_run_wavefunction(oracle_ops(op), n, psi0=psi) if len(op) else (psi, None)
+        want.append(np.vdot(psi, phi))
+    want.append(orc.expectation_state(psi, [(2.0, {13: "Y", 12: "X"})], n))
+    for g, w in zip(got, want):
+        assert abs(g - w) < TOL
+    assert qvm.expectation(prog) == [1.0] or abs(qvm.expectation(prog)[0] - 1.0) < TOL
+    with pytest.raises(IndexError):
+        qvm.expectation(prog, [PauliTerm("X", n)])
+    # SWAP relabels in the preparation are honoured
+    sprog = spec_program(spec)
+    sprog.inst(("SWAP", 0, 9))
+    spsi, _ = orc.fast_run_wavefunction(oracle_ops(sprog), n)
+    assert abs(qvm.expectation(sprog, [PauliTerm("Z", 9) * PauliTerm("X", 0)])[0]
+               - orc.expectation_state(spsi, [(1.0, {9: "Z", 0: "X"})], n)) < TOL

@@ -199,3 +199,30 @@ def test_generators_are_the_documented_ones():
     q = orc.qft_spec(8)
     assert len(q) == 8 + 28 + 4 and q[0] == ("H", [], [7]) and q[1][0] == "CPHASE" and q[1][2] == [6, 7]
     assert len(orc.qft_spec(28)) == 420
+
+
+def test_expectation_oracle_against_reference_pieces():
+    """oracle.ref_tensor_up / expectation_state / expectation_density vs values assembled by the reference's own
+    wavefunction, density and tensor_up (tests/golden/make_golden.py::golden_expectation)."""
+    from _programs import load_golden
+    from referenceqvm import gates as G
+    meta, arrays = load_golden("expectation")
+    for case in meta:
+        n = case["n"]
+        terms = [(complex(t["re"], t["im"]), {int(q): p for q, p in t["ops"].items()}) for t in case["terms"]]
+        ops = []
+        for name, params, qubits in case["spec"]:
+            m = G.gate_matrix[name]
+            ops.append(("gate", np.asarray(m(*params) if params else m, dtype=complex), qubits))
+        psi, _ = orc.fast_run_wavefunction(ops, n)
+        want_psi, want_rho = arrays[case["key"]]
+        assert abs(orc.expectation_state(psi, terms, n) - want_psi) < 1e-13
+        # density with T2 dephasing on every qubit after every gate (the fixture's noise model)
+        vec = np.zeros(4 ** n, dtype=complex)
+        vec[0] = 1.0
+        for _, m, q in ops:
+            vec = orc.fast_density_gate(vec, m, q, n)
+            p = 1.0 - np.exp(-(50e-9 if len(q) == 1 else 150e-9) / 30e-6)
+            for i in range(n):
+                vec = orc.fast_apply_kraus(vec, G.dephasing(p), i, n)
+        assert abs(orc.expectation_density(orc.vec_to_rho(vec, n), terms, n) - want_rho) < 1e-13

@@ -131,3 +131,42 @@ def test_sharded_density_qvm_host_logic(world):
             _sharded.disable()
 
     run_ranks(world, rank_main)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_expectation_host_logic(world):
+    """Pauli expectation values on sharded engines (numpy backend, thread ranks): X / Y factors on global qubits
+    trigger an exchange, Z factors on global qubits are signs of the shard; density: gather through the layout."""
+    from _programs import spec_program
+    from pyquil.paulis import PauliSum, PauliTerm
+    from referenceqvm.api import QVMConnection
+
+    def rank_main(comm):
+        _sharded.enable(device=0, comm=comm, backend_factory=NumpyShard,
+                        engine_options={"tile_bits": 5, "low_bits": 2, "exchange": "push"})
+        try:
+            n = 9
+            spec = orc.random_circuit_spec(n, 4, 3)
+            prog = spec_program(spec)
+            psi, _ = orc.fast_run_wavefunction(oracle_ops(spec), n)
+            ops = [PauliTerm("Z", n - 1) * PauliTerm("Z", 0), PauliTerm("X", n - 1) * PauliTerm("Y", n - 2, 0.5),
+                   PauliSum([PauliTerm("Y", 3, 2.0), PauliTerm("X", n - 1) * PauliTerm("Z", n - 2) * PauliTerm("X", 1)]),
+                   spec_program([("X", [], [n - 1]), ("Z", [], [2])]), spec_program([])]
+            terms = [[(1.0, {n - 1: "Z", 0: "Z"})], [(0.5, {n - 1: "X", n - 2: "Y"})],
+                     [(2.0, {3: "Y"}), (1.0, {n - 1: "X", n - 2: "Z", 1: "X"})], [(1.0, {n - 1: "X", 2: "Z"})], [(1.0, {})]]
+            got = QVMConnection().expectation(prog, ops)
+            for g, t in zip(got, terms):
+                assert abs(g - orc.expectation_state(psi, t, n)) < 1e-12
+            nd = 5
+            dspec = orc.random_circuit_spec(nd, 3, 6)
+            rho = orc.vec_to_rho(density_oracle(spec_program(dspec), nd), nd)
+            dops = [PauliTerm("Z", nd - 1) * PauliTerm("X", 0), PauliTerm("Y", nd - 1) * PauliTerm("Y", nd - 2, 0.25),
+                    spec_program([("X", [], [nd - 1])])]
+            dterms = [[(1.0, {nd - 1: "Z", 0: "X"})], [(0.25, {nd - 1: "Y", nd - 2: "Y"})], [(1.0, {nd - 1: "X"})]]
+            got = QVMConnection(type_trans="density").expectation(spec_program(dspec), dops)
+            for g, t in zip(got, dterms):
+                assert abs(g - orc.expectation_density(rho, t, nd)) < 1e-12
+        finally:
+            _sharded.disable()
+
+    run_ranks(world, rank_main)
