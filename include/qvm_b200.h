@@ -221,6 +221,9 @@ int qvm_measure_hist(qvm_t* q, int n_high, const int32_t* high_pos, int do_colla
  * qvm_reset_batched sets every trial to |0..0>; qvm_measure_batched measures `qubit` in every trial
  * with that trial's own uniform (uniforms / outcomes / p0: one entry per trial slot). */
 int qvm_reset_batched(qvm_t* q, int n_per_trial);
+/* Regroup trials (classical control, qvm_wavefunction.py:164-231: trials whose jumps go different ways): segment j of
+ * `dst` := segment src_index[j] of `src` for j < count; both handles on one device, their other segments untouched. */
+int qvm_gather_segments(qvm_t* dst, qvm_t* src, int n_per_trial, uint64_t count, const uint32_t* src_index);
 int qvm_measure_batched(qvm_t* q, int n_per_trial, int qubit, const double* uniforms, int32_t* outcomes, double* p0);
 /* The two halves of the above for sharded states (host all-reduces p0 in between). */
 int qvm_prob_zero(qvm_t* q, int qubit, double* p0_partial);

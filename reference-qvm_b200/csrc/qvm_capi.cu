@@ -1278,6 +1278,36 @@ int qvm_reset_batched(qvm_t* q, int n_per_trial) {
     return QVM_OK;
 }
 
+int qvm_gather_segments(qvm_t* dst, qvm_t* src, int n_per_trial, uint64_t count, const uint32_t* src_index) {
+    QVM_CHECK_HANDLE(dst);
+    if (!src || (count && !src_index)) return fail(QVM_ERR_INVALID, "null pointer");
+    if (dst->device != src->device) return fail(QVM_ERR_INVALID, "segments are gathered on one device");
+    if (n_per_trial < 1 || n_per_trial > dst->n_local || n_per_trial > src->n_local)
+        return fail(QVM_ERR_INVALID, "bad qubits per trial %d", n_per_trial);
+    const uint64_t dst_segs = 1ull << (dst->n_local - n_per_trial), src_segs = 1ull << (src->n_local - n_per_trial);
+    if (count > dst_segs || count > (1ull << 20)) return fail(QVM_ERR_INVALID, "%llu segments do not fit", (unsigned long long)count);
+    for (uint64_t j = 0; j < count; ++j)
+        if (src_index[j] >= src_segs) return fail(QVM_ERR_INVALID, "source segment %u out of range", src_index[j]);
+    if (!count) return QVM_OK;
+    QVM_CUDA(src, cudaStreamSynchronize(src->stream));
+    uint32_t* dev = nullptr;
+    QVM_CUDA(dst, cudaMallocAsync(&dev, count * sizeof(uint32_t), dst->stream));
+    cudaError_t e = cudaMemcpyAsync(dev, src_index, count * sizeof(uint32_t), cudaMemcpyHostToDevice, dst->stream);
+    if (e == cudaSuccess) {
+        const int threads = n_per_trial >= 8 ? 256 : (n_per_trial >= 5 ? 32 : 32);
+        gather_segments_kernel<<<(unsigned)count, threads, 0, dst->stream>>>(dst->amps, src->amps, n_per_trial, dev);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(dst->stream);       // src_index is the caller's (pageable) memory
+    cudaFreeAsync(dev, dst->stream);
+    QVM_CUDA(dst, e);
+    dst->sample_mode = -1;
+    dst->stats.kernel_launches += 1;
+    dst->stats.hbm_bytes += (32ull << n_per_trial) * count;
+    dst->stats.h2d_bytes += count * sizeof(uint32_t);
+    return QVM_OK;
+}
+
 int qvm_measure_batched(qvm_t* q, int n_per_trial, int qubit, const double* uniforms, int32_t* outcomes, double* p0) {
     QVM_CHECK_HANDLE(q);
     if (!uniforms || !outcomes) return fail(QVM_ERR_INVALID, "null pointer");

@@ -495,6 +495,18 @@ __global__ void batched_measure_kernel(double2* __restrict__ state, int n, int q
     }
 }
 
+// Batched trials under classical control: when the trials of a batch take different branches they are
+// regrouped -- dst segment j := src segment index[j] (j < count) -- so that every batch again walks ONE
+// instruction sequence.  One block per destination segment, 128-bit copies.
+__global__ void gather_segments_kernel(double2* __restrict__ dst, const double2* __restrict__ src, int n,
+                                       const uint32_t* __restrict__ index) {
+    const uint64_t seg = blockIdx.x;
+    const double2* s = src + ((uint64_t)index[seg] << n);
+    double2* d = dst + (seg << n);
+    const uint64_t n_elems = 1ull << n;
+    for (uint64_t i = threadIdx.x; i < n_elems; i += blockDim.x) d[i] = s[i];
+}
+
 // every segment := |0...0>
 __global__ void batched_reset_kernel(double2* __restrict__ state, uint64_t n_elems, int n) {
     const uint64_t mask = (1ull << n) - 1ull;

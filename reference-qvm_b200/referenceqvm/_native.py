@@ -76,6 +76,7 @@ _SIGNATURES = {
     "qvm_measure_hist": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_uint64, C.c_uint64, C.c_double, _P]),
     "qvm_reset_batched": (C.c_int, [_P, C.c_int]),
     "qvm_measure_batched": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
+    "qvm_gather_segments": (C.c_int, [_P, _P, C.c_int, C.c_uint64, _P]),
     "qvm_get_strided": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
     "qvm_get_state_layout": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, _P, _P]),
     "qvm_apply_group_relabel": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, C.c_uint64, C.c_int, C.c_int, _P, _P]),
@@ -513,6 +514,14 @@ class DeviceState(object):
     def reset_batched(self, n_per_trial):
         """Every 2^n_per_trial-amplitude segment := |0..0> (one segment per trial of a batched run())."""
         check(lib().qvm_reset_batched(self.handle, n_per_trial))
+
+    def gather_segments(self, src, n_per_trial, src_index):
+        """Segment j of this state := segment ``src_index[j]`` of ``src`` (regrouping of batched trials)."""
+        idx = np.ascontiguousarray(src_index, dtype=np.uint32)
+        code = lib().qvm_gather_segments(self.handle, src.handle, n_per_trial, idx.size, idx.ctypes.data)
+        if code == QVM_ERR_INVALID:
+            raise ValueError(last_error())
+        check(code)
 
     def measure_batched(self, n_per_trial, qubit, uniforms):
         """MEASURE ``qubit`` in every segment with that segment's own uniform: (outcomes, p0) arrays."""

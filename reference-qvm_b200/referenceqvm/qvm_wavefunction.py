@@ -29,7 +29,7 @@ import numpy as np
 from pyquil.quil import Program  # noqa: F401  (kept for parity with the reference's namespace)
 from pyquil.quilbase import (BinaryClassicalInstruction, ClassicalAnd, ClassicalExchange, ClassicalFalse,
                              ClassicalMove, ClassicalNot, ClassicalOr, ClassicalTrue, Gate, Halt, Jump,
-                             JumpConditional, JumpTarget, Measurement, UnaryClassicalInstruction)
+                             JumpConditional, JumpTarget, JumpWhen, Measurement, UnaryClassicalInstruction)
 from pyquil.wavefunction import Wavefunction
 
 from referenceqvm import _compiled, _engine
@@ -361,6 +361,8 @@ class QVM_Wavefunction(QAM):
             classical_vals = self._run_once(pyquil_program, classical_addresses)
             return [list(classical_vals) for _ in range(trials)]
         if split is None and trials > 1 and self.sampling_fast_path and self._batchable(pyquil_program):
+            if self._has_control_flow(pyquil_program):
+                return self._run_batched_flow(pyquil_program, classical_addresses, trials)
             return self._run_batched(pyquil_program, classical_addresses, trials)
         if split is None or trials <= 1:
             return [self._run_once(pyquil_program, classical_addresses) for _ in range(trials)]
@@ -395,12 +397,17 @@ class QVM_Wavefunction(QAM):
         from referenceqvm import _sharded
         if _sharded.context() is not None and _sharded.context().world > 1:
             return False
-        allowed = (Gate, Measurement, UnaryClassicalInstruction, BinaryClassicalInstruction)
+        allowed = (Gate, Measurement, UnaryClassicalInstruction, BinaryClassicalInstruction, Jump, JumpConditional,
+                   JumpTarget, Halt)
         instrs = list(program)
         if not instrs or not all(isinstance(i, allowed) for i in instrs):
             return False
         n = 1 + max([value_get(q) for i in instrs if isinstance(i, (Gate, Measurement)) for q in i.get_qubits()] or [0])
         return n <= self.BATCH_MAX_QUBITS
+
+    @staticmethod
+    def _has_control_flow(program):
+        return any(isinstance(i, (Jump, JumpConditional, JumpTarget, Halt)) for i in program)
 
     def _run_batched(self, pyquil_program, classical_addresses, trials):
         """All trials as independent segments of one device buffer: every gate group is one pass over
@@ -456,6 +463,143 @@ class QVM_Wavefunction(QAM):
         if last is not None:
             self._engine.set_amplitudes(last[0])
             self._virt = list(last[1])
+        self.program_counter = len(self.program)
+        self.classical_memory = memory[-1].copy()
+        out = memory if mask is None else memory[:, mask]
+        return _rows_to_lists(out.astype(np.int64))
+
+    # -- batched trials under classical control: if_then / while_do / jumps ---------------------------------
+    #: a group that runs this many instructions without finishing is taken for a non-terminating program
+    BATCH_FLOW_MAX_STEPS = 1 << 22
+
+    def _run_batched_flow(self, pyquil_program, classical_addresses, trials):
+        """run() for programs WITH jumps (reference: one full re-simulation per trial, :279-283, control flow at
+        :164-231).  Trials start as one batch (one n-qubit segment each, as in ``_run_batched``); a batch walks
+        the program with ONE program counter.  At a conditional jump whose condition bit differs between its
+        trials the batch splits in two -- the segments are regrouped on the device (``qvm_gather_segments``) --
+        and both halves continue independently (loops keep peeling off the trials that leave).  Work is what
+        the per-trial loop does, but every gate pass and every MEASURE serves a whole batch.
+
+        Random numbers: trial t uses row t of a (trials x draws) matrix of uniforms, extended by blocks as some
+        path needs more draws; the distribution of the results is the reference's, but a path-dependent number
+        of draws per trial cannot be laid out like the reference's trial-after-trial stream, so seeded results
+        differ from the per-trial loop (``sampling_fast_path = False`` keeps that loop)."""
+        self.load_program(pyquil_program)
+        mask = self._address_mask(classical_addresses)
+        n = self.num_qubits
+        instrs = list(pyquil_program)
+        labels = {}
+        for index, instruction in enumerate(instrs):
+            if isinstance(instruction, JumpTarget) and instruction.label.name not in labels:
+                labels[instruction.label.name] = index          # first match, as QAM.find_label
+
+        def target(label):
+            if label.name not in labels:
+                raise RuntimeError("Improper program - Jump Target not found in the input program!")
+            return labels[label.name]
+
+        uniforms = [np.random.random_sample((trials, 4))]        # column blocks, drawn as paths ask for them
+
+        def draws(ids, k):
+            have = sum(b.shape[1] for b in uniforms)
+            while k >= have:
+                uniforms.append(np.random.random_sample((trials, 4)))
+                have += 4
+            for block in uniforms:
+                if k < block.shape[1]:
+                    return block[ids, k]
+                k -= block.shape[1]
+
+        t_bits_cap = max(0, min(self.BATCH_BITS - n, self.BATCH_MAX_TRIAL_BITS))
+        memory = np.repeat(self.classical_memory[None, :], trials, axis=0)
+        last_state = [None]
+
+        def make_engine(count):
+            eng = _engine.Engine(n + max(0, (count - 1).bit_length()), device=self.device)
+            eng.relabel = False                   # the trial index must stay on the top positions
+            return eng
+
+        def run_group(eng, ids, pc, virt, mem, k, work):
+            """Walk one batch until it ends or splits; ``k`` = uniforms its trials have used so far."""
+            cap = 1 << (eng.n - n)
+            steps = 0
+            while pc < len(instrs):
+                steps += 1
+                if steps > self.BATCH_FLOW_MAX_STEPS:
+                    raise RuntimeError("program does not terminate (batched run gave up after %d instructions)" % steps)
+                instruction = instrs[pc]
+                if isinstance(instruction, Gate):
+                    matrix, qubits = resolve_gate(self.gate_set, self.defgate_set, instruction)
+                    _engine.validate_qubits(qubits, n)
+                    if _is_swap(matrix, qubits):
+                        a, b = qubits
+                        virt[a], virt[b] = virt[b], virt[a]
+                    else:
+                        eng.queue_matrix(matrix, [virt[q] for q in qubits])
+                    pc += 1
+                elif isinstance(instruction, Measurement):
+                    eng.flush()
+                    u = np.full(cap, 0.5)
+                    u[:ids.size] = draws(ids, k)
+                    k += 1
+                    outcomes, _ = eng.state.measure_batched(n, virt[value_get(instruction.qubit)], u)
+                    mem[:, value_get(instruction.classical_reg)] = outcomes[:ids.size] != 0
+                    pc += 1
+                elif isinstance(instruction, (UnaryClassicalInstruction, BinaryClassicalInstruction)):
+                    self._batched_classical(instruction, mem)
+                    pc += 1
+                elif isinstance(instruction, JumpTarget):
+                    pc += 1
+                elif isinstance(instruction, Jump):
+                    pc = target(instruction.target)
+                elif isinstance(instruction, Halt):
+                    pc = len(instrs)
+                elif isinstance(instruction, JumpConditional):
+                    cond = mem[:, value_get(instruction.condition)].astype(bool)
+                    taken = cond if isinstance(instruction, JumpWhen) else ~cond
+                    dest = target(instruction.target)
+                    if taken.all():
+                        pc = dest
+                    elif not taken.any():
+                        pc += 1
+                    else:
+                        # the batch splits: regroup the segments of each side into an engine of its own
+                        eng.flush()
+                        for side, next_pc in ((taken, dest), (~taken, pc + 1)):
+                            where = np.nonzero(side)[0]
+                            sub = make_engine(where.size)
+                            sub.state.reset_batched(n)
+                            sub.state.gather_segments(eng.state, n, where)
+                            work.append((sub, ids[where], next_pc, list(virt), mem[where].copy(), k))
+                        eng.close()
+                        return
+                else:
+                    eng.close()
+                    raise self._unsupported(instruction)
+            eng.flush()
+            memory[ids] = mem
+            if ids[-1] == trials - 1:                # the reference leaves the last trial's state in self.wf
+                last_state[0] = (eng.amplitudes((ids.size - 1) << n, 1 << n), list(virt))
+            eng.close()
+
+        chunk = 1 << t_bits_cap
+        for lo in range(0, trials, chunk):
+            ids = np.arange(lo, min(lo + chunk, trials))
+            eng = make_engine(ids.size)
+            eng.state.reset_batched(n)
+            work = [(eng, ids, 0, list(range(n)), memory[ids].copy(), 0)]
+            while work:
+                item = work.pop()
+                try:
+                    run_group(*item, work)
+                except Exception:
+                    for other in work:
+                        other[0].close()
+                    raise
+        self._fresh_engine()
+        if last_state[0] is not None:
+            self._engine.set_amplitudes(last_state[0][0])
+            self._virt = list(last_state[0][1])
         self.program_counter = len(self.program)
         self.classical_memory = memory[-1].copy()
         out = memory if mask is None else memory[:, mask]

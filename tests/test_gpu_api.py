@@ -834,3 +834,42 @@ def test_expectation_of_operator_programs(qvm):
     spsi, _ = orc.fast_run_wavefunction(oracle_ops(sprog), n)
     assert abs(qvm.expectation(sprog, [PauliTerm("Z", 9) * PauliTerm("X", 0)])[0]
                - orc.expectation_state(spsi, [(1.0, {9: "Z", 0: "X"})], n)) < TOL
+
+
+# ---- batched trials under classical control ----------------------------------------------------------------------
+def test_batched_run_with_jumps_matches_the_per_trial_distribution(qvm):
+    """run(trials) on programs with if_then / while_do: trials are batched and regrouped at every divergent jump;
+    deterministic consequences are exact, distributions match the per-trial loop (chi-squared)."""
+    from pyquil.gates import MEASURE
+    # if_then: measure a coin, flip another qubit only when it came up 1 -> the two bits are always equal
+    branch = Program().inst(H(0)).measure(0, [0])
+    branch.if_then(0, Program().inst(X(1)), Program().inst(I(1)))
+    branch.measure(1, [1])
+    got = np.asarray(qvm.run(branch, [0, 1], trials=4000))
+    assert np.array_equal(got[:, 0], got[:, 1]) and abs(got[:, 0].mean() - 0.5) < 0.04
+    # while_do: keep tossing until tails; bit 2 counts parity of the tosses -> geometric law
+    loop = Program().inst(X(0)).measure(0, [0])
+    loop.while_do(0, Program().inst(H(0)).measure(0, [0]).inst(X(1)))
+    loop.measure(1, [1])
+    trials = 6000
+    batched = np.asarray(qvm.run(loop, [0, 1], trials=trials))
+    assert not batched[:, 0].any()                          # the loop only ends with bit 0 cleared
+    # parity of the number of iterations: P(odd) = sum_{k odd} 2^-k = 2/3
+    assert abs(batched[:, 1].mean() - 2.0 / 3.0) < 0.03
+    plain = QVMConnection()
+    plain.sampling_fast_path = False
+    ref = np.asarray(plain.run(loop, [0, 1], trials=300))
+    assert not ref[:, 0].any() and abs(ref[:, 1].mean() - 2.0 / 3.0) < 0.12
+    # nested control flow with a rotation: outcome probabilities against the closed form
+    theta = 1.1
+    prog = Program().inst(RX(theta, 0)).measure(0, [0])
+    prog.if_then(0, Program().inst(RX(theta, 1)).measure(1, [1]).if_then(1, Program().inst(X(2))), Program().inst(H(2)))
+    prog.measure(2, [2])
+    res = np.asarray(qvm.run(prog, [0, 1, 2], trials=8000))
+    p1 = np.sin(theta / 2) ** 2
+    assert abs(res[:, 0].mean() - p1) < 0.03
+    assert abs((res[:, 0] & res[:, 1]).mean() - p1 * p1) < 0.03
+    want2 = (1 - p1) * 0.5 + p1 * p1
+    assert abs(res[:, 2].mean() - want2) < 0.03
+    # the last trial's state is left in self.wf like the reference's loop
+    assert abs(np.vdot(qvm.wf, qvm.wf).real - 1.0) < 1e-12

@@ -237,8 +237,8 @@ def test_batchable_decision():
     assert qvm._batchable(mid) and qvm._terminal_measure_block(mid) is None
     assert qvm._terminal_measure_block(Program(H(0), CNOT(0, 1), MEASURE(0, 0), MEASURE(1, 1))) == 2
     looped = Program(X(0), MEASURE(0, 0)).while_do(0, Program(X(0), MEASURE(0, 0))) if hasattr(Program, "while_do") else None
-    if looped is not None:
-        assert not qvm._batchable(looped)
+    if looped is not None:                           # jumps: batched too, through the regrouping flow
+        assert qvm._batchable(looped) and qvm._has_control_flow(looped) and not qvm._has_control_flow(mid)
     wide = Program(H(QVM_Wavefunction.BATCH_MAX_QUBITS), MEASURE(0, 0), H(0))
     assert not qvm._batchable(wide)                  # one block per trial: segments above 2^20 amplitudes keep the loop
     assert not qvm._batchable(Program())
