@@ -103,14 +103,21 @@ inline bool spec_streaming() {
     return on;
 }
 
-// QVM_B200_SPEC_PIPE=1: persistent CTAs that prefetch their next tile with cp.async into a second
-// shared-memory buffer while they compute the current one (load, FP64 and store phases of ONE CTA overlap).
-inline bool spec_pipelined() {
-    static const bool on = [] {
+// QVM_B200_SPEC_PIPE: how a CTA overlaps its load, FP64 and store phases.
+//   0  one tile per CTA: round 0 loads HBM -> registers, the last round stores registers -> HBM; only the other
+//      resident CTAs hide one phase behind another
+//   1  persistent CTAs that prefetch their next tile with cp.async into a second shared-memory buffer (measured
+//      slower in round 1: the staged tile costs one more trip through the LSU pipe)
+//   2  persistent CTAs with TMA: every thread moves one 256/512-byte run of the tile with cp.async.bulk -- the
+//      next tile lands in the second buffer (mbarrier, no registers, no LSU traffic) while this one is computed,
+//      and the finished tile drains to HBM (or to a peer over NVLink) asynchronously from shared memory
+inline int spec_pipe_mode() {
+    static const int mode = [] {
         const char* e = getenv("QVM_B200_SPEC_PIPE");
-        return e && atoi(e) != 0;
+        const int v = e ? atoi(e) : 0;
+        return v < 0 || v > 2 ? 0 : v;
     }();
-    return on;
+    return mode;
 }
 
 // Source for one encoded group (lean R = 4 groups only).  Factors never appear as literals: F.v[i]
@@ -145,7 +152,13 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
             if (g.cold[j].word_off == word && g.cold[j].slot == slot && g.cold[j].kind == kind) return &g.cold[j];
         return nullptr;
     };
-    const bool pipe = spec_pipelined() && P.k - 4 >= P.low;
+    const bool pipe = spec_pipe_mode() == 1 && P.k - 4 >= P.low;
+    const bool tma = spec_pipe_mode() == 2 && P.low >= 4 && P.low <= 5;     // runs of 256 / 512 bytes, <= one per thread
+    auto lin_of = [](uint16_t swz_stride) {                                  // tile-local bit of a slot: swz() keeps the top bit
+        int b = 0;
+        while ((swz_stride >> (b + 1)) != 0) ++b;
+        return 1u << b;
+    };
     std::ostringstream body;
     for (int r = 0; r < P.n_rounds; ++r) {
         const RoundDesc& rd = g.rounds[r];
@@ -154,7 +167,12 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
         for (int s = 0; s < 4; ++s) body << "    T += T & 0x" << std::hex << rd.ins_mask[s] << std::dec << "u;\n";
         body << "    const uint32_t sT = swz(T);\n    const uint32_t st[4] = {" << rd.swz_j[0] << "u, " << rd.swz_j[1] << "u, "
              << rd.swz_j[2] << "u, " << rd.swz_j[3] << "u};\n";
-        if (first && !pipe) {
+        if (first && tma) {
+            // the tile sits in shared memory as TMA delivered it: linear, lanes on the lowest tile bits (conflict-free)
+            body << "    const uint32_t lin[4] = {" << lin_of(rd.swz_j[0]) << "u, " << lin_of(rd.swz_j[1]) << "u, "
+                 << lin_of(rd.swz_j[2]) << "u, " << lin_of(rd.swz_j[3]) << "u};\n"
+                    "#pragma unroll\n    for (int j = 0; j < 16; ++j) a[j] = tile[T ^ xor_combo<4>(lin, j)];\n";
+        } else if (first && !pipe) {
             body << "    {\n      const uint64_t gT = (uint64_t)(T & " << ((1u << P.low) - 1u) << "u) | hi_off[T >> " << P.low
                  << "];\n      const int64_t b[4] = {";
             for (int s = 0; s < 4; ++s) body << (s ? ", " : "") << "(int64_t)(16ull << " << (int)rd.reg_phys[s] << ")";
@@ -233,7 +251,14 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
             }
             w += size;
         }
-        if (last) {
+        if (last && tma) {
+            // back to the linear layout TMA stores from (the last round's lanes hold the lowest tile bits)
+            if (!first) body << "    __syncthreads();\n";
+            body << "    const uint32_t linw[4] = {" << lin_of(rd.swz_j[0]) << "u, " << lin_of(rd.swz_j[1]) << "u, "
+                 << lin_of(rd.swz_j[2]) << "u, " << lin_of(rd.swz_j[3]) << "u};\n    uint32_t sX = T;\n"
+                    "#pragma unroll\n    for (int s = 0; s < 4; ++s) if ((xm >> s) & 1u) sX ^= linw[s];\n"
+                    "#pragma unroll\n    for (int j = 0; j < 16; ++j) tile[sX ^ xor_combo<4>(linw, j)] = a[j];\n";
+        } else if (last) {
             body << "    {\n      const uint64_t gT = (uint64_t)(T & " << ((1u << P.low) - 1u) << "u) | hi_off[T >> " << P.low
                  << "];\n      char* p0 = reinterpret_cast<char*>(gstore + gT);\n      int64_t b[4] = {";
             for (int s = 0; s < 4; ++s) body << (s ? ", " : "") << "(int64_t)(16ull << " << (int)rd.reg_phys[s] << ")";
@@ -244,7 +269,7 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
                  << ";\n    }\n";
         } else if (r == P.perm_round) {
             // relabelling round: the tile is written in the last round's coordinates (qvm_encode.h)
-            if (!first || pipe) body << "    __syncthreads();\n";
+            if (!first || pipe || tma) body << "    __syncthreads();\n";
             body << "    uint32_t sX = 0u;\n";
             for (int b = 0; b < P.k; ++b)
                 body << "    sX ^= (0u - ((T >> " << b << ") & 1u)) & " << P.perm_swz[b] << "u;\n";
@@ -252,6 +277,7 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
                  << rd.wr_swz[3] << "u};\n#pragma unroll\n    for (int s = 0; s < 4; ++s) if ((xm >> s) & 1u) sX ^= wst[s];\n"
                     "#pragma unroll\n    for (int j = 0; j < 16; ++j) tile[sX ^ xor_combo<4>(wst, j)] = a[j];\n";
         } else {
+            if (first && tma) body << "    __syncthreads();\n";       // linear tile read by everyone before it is rewritten swizzled
             body << "    uint32_t sX = sT;\n#pragma unroll\n    for (int s = 0; s < 4; ++s) if ((xm >> s) & 1u) sX ^= st[s];\n"
                     "#pragma unroll\n    for (int j = 0; j < 16; ++j) tile[sX ^ xor_combo<4>(st, j)] = a[j];\n";
         }
@@ -272,9 +298,36 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
         "    base |= (t & ((1ull << len) - 1ull)) << ((uint32_t)(SP.run_start >> (8 * r)) & 0xFFu);\n    t >>= len;\n  }\n"
         "  return base;\n}\n";
     o << tile_base_fn;
-    const unsigned ctas = pipe ? std::max(1u, std::min(spec_min_blocks(g.threads), (unsigned)((220u * 1024u) / ((size_t)32 << P.k))))
-                               : spec_min_blocks(g.threads);
-    if (!pipe) {
+    const unsigned ctas = (pipe || tma)
+                              ? std::max(1u, std::min(spec_min_blocks(g.threads), (unsigned)((220u * 1024u) / ((size_t)32 << P.k))))
+                              : spec_min_blocks(g.threads);
+    if (tma) {
+        const unsigned run_elems = 1u << P.low, n_runs_tile = 1u << (P.k - P.low), run_bytes = 16u << P.low;
+        o << "__device__ __forceinline__ void spec_tma_load(double2* buf, unsigned long long* bar, const double2* gsrc, uint32_t tid) {\n"
+             "  if (tid == 0) mbar_expect_tx(bar, " << ((size_t)16 << P.k) << "u);\n"
+             "  if (tid < " << n_runs_tile << "u) tma_load_run(buf + tid * " << run_elems << "u, gsrc + hi_off[tid], " << run_bytes
+          << "u, bar);\n}\n";
+        o << "extern \"C\" __global__ void __launch_bounds__(" << g.threads << ", " << ctas
+          << ") spec_kernel(double2* __restrict__ state, const __grid_constant__ SpecParams SP, const SpecFactors F) {\n"
+             "  extern __shared__ __align__(128) unsigned char smem_raw[];\n"
+             "  __shared__ __align__(8) unsigned long long mbar[2];\n"
+             "  double2* const buf0 = reinterpret_cast<double2*>(smem_raw);\n  double2* const buf1 = buf0 + " << (1u << P.k) << ";\n"
+             "  const uint32_t tid = threadIdx.x;\n  uint64_t t = blockIdx.x;\n  if (t >= SP.n_tiles) return;\n"
+             "  if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_fence_init(); }\n  __syncthreads();\n"
+             "  spec_tma_load(buf0, &mbar[0], state + spec_tile_base(SP, t), tid);\n  int cur = 0;\n  uint32_t ph0 = 0, ph1 = 0;\n"
+             "  for (; t < SP.n_tiles; t += gridDim.x, cur ^= 1) {\n"
+             "  double2* const tile = cur ? buf1 : buf0;\n"
+             "  tma_wait_read_all();\n  __syncthreads();\n"                      // the other buffer's stores have left shared memory
+             "  if (t + gridDim.x < SP.n_tiles) spec_tma_load(cur ? buf0 : buf1, &mbar[cur ^ 1], state + spec_tile_base(SP, t + gridDim.x), tid);\n"
+             "  if (cur) { mbar_wait(&mbar[1], ph1); ph1 ^= 1u; } else { mbar_wait(&mbar[0], ph0); ph0 ^= 1u; }\n"
+             "  const uint64_t base = spec_tile_base(SP, t);\n"
+             "  const uint64_t full = base | SP.shard_bits;\n  double2* gbase = state + base;\n"
+             "  double2* gstore = rt_push_base(SP.push, state, base);\n  double2 a[16];\n"
+          << body.str()
+          << "  fence_async_smem();\n  __syncthreads();\n"
+             "  if (tid < " << n_runs_tile << "u) tma_store_run(gstore + hi_off[tid], tile + tid * " << run_elems << "u, " << run_bytes
+          << "u);\n  tma_commit();\n  }\n  tma_wait_all();\n}\n";
+    } else if (!pipe) {
         o << "extern \"C\" __global__ void __launch_bounds__(" << g.threads << ", " << ctas
           << ") spec_kernel(double2* __restrict__ state, const __grid_constant__ SpecParams SP, const SpecFactors F) {\n"
              "  extern __shared__ __align__(16) unsigned char smem_raw[];\n  double2* tile = reinterpret_cast<double2*>(smem_raw);\n"
@@ -313,9 +366,9 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
     }
     out.src = o.str();
     out.threads = g.threads;
-    out.smem = pipe ? ((size_t)32 << P.k) : (P.n_rounds > 1 ? ((size_t)16 << P.k) : 0);
+    out.smem = (pipe || tma) ? ((size_t)32 << P.k) : (P.n_rounds > 1 ? ((size_t)16 << P.k) : 0);
     out.n_tiles = g.n_tiles;
-    out.ctas_per_sm = pipe ? ctas : 0;
+    out.ctas_per_sm = (pipe || tma) ? ctas : 0;
     out.params = SpecParams{P.n_runs, P.shard_bits, P.run_start, P.run_len, g.n_tiles, PushSpec{}};
     return true;
 }

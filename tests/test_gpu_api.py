@@ -822,7 +822,7 @@ def test_expectation_of_operator_programs(qvm):
     for op in ops[:5]:
         phi, _ = orc.fast_run_wavefunction(oracle_ops(op), n, psi0=psi) if len(op) else (psi, None)
         want.append(np.vdot(psi, phi))
-    want.append(orc.expectation_state(psi, [(2.0, {13: "Y", 12: "X"})], n))
+    want.append(orc.fast_expectation_state(psi, [(2.0, {13: "Y", 12: "X"})], n))
     for g, w in zip(got, want):
         assert abs(g - w) < TOL
     assert qvm.expectation(prog) == [1.0] or abs(qvm.expectation(prog)[0] - 1.0) < TOL
@@ -833,7 +833,7 @@ def test_expectation_of_operator_programs(qvm):
     sprog.inst(("SWAP", 0, 9))
     spsi, _ = orc.fast_run_wavefunction(oracle_ops(sprog), n)
     assert abs(qvm.expectation(sprog, [PauliTerm("Z", 9) * PauliTerm("X", 0)])[0]
-               - orc.expectation_state(spsi, [(1.0, {9: "Z", 0: "X"})], n)) < TOL
+               - orc.fast_expectation_state(spsi, [(1.0, {9: "Z", 0: "X"})], n)) < TOL
 
 
 # ---- batched trials under classical control ----------------------------------------------------------------------

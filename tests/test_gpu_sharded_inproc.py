@@ -221,7 +221,7 @@ def test_sharded_expectation_on_one_gpu(world):
             qvm = QVMConnection()
             got = qvm.expectation(prog, ops)
             for g, t in zip(got, terms):
-                assert abs(g - orc.expectation_state(psi, t, n)) < 1e-12
+                assert abs(g - orc.fast_expectation_state(psi, t, n)) < 1e-12
             qvm._engine.close()
             nd = 7
             dspec = orc.random_circuit_spec(nd, 3, 6)

@@ -217,6 +217,7 @@ def test_expectation_oracle_against_reference_pieces():
         psi, _ = orc.fast_run_wavefunction(ops, n)
         want_psi, want_rho = arrays[case["key"]]
         assert abs(orc.expectation_state(psi, terms, n) - want_psi) < 1e-13
+        assert abs(orc.fast_expectation_state(psi, terms, n) - want_psi) < 1e-13
         # density with T2 dephasing on every qubit after every gate (the fixture's noise model)
         vec = np.zeros(4 ** n, dtype=complex)
         vec[0] = 1.0
