@@ -181,7 +181,7 @@ def _choose_group(ops, deps, done, first, k, max_new, is_old, seed_tile, max_gro
 
 
 def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_group_ops=MAX_GROUP_OPS,
-                   defer_tail_below=0, leftover=None, on_last=None):
+                   defer_tail_below=0, leftover=None, on_last=None, last_tile_bits=0):
     """Run ``ops`` (ClassifiedOps on LOGICAL qubits; every dense target currently on a local position)
     as fused groups with in-tile relabelling.  ``pos_of`` (logical -> physical, mutated in place) is the
     layout; ``launch(tile_positions, physical_ops, bring_low_positions)`` runs one pass and returns the
@@ -194,7 +194,11 @@ def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_g
 
     ``on_last(leftover_indices, tile_positions)``: called right before the LAST launch of the call (the
     thin tail, if any, already set aside); what it returns is handed to that launch as a fourth argument
-    -- the sharded engine's fused exchange: the last pass stores straight into the peers' shards."""
+    -- the sharded engine's fused exchange: the last pass stores straight into the peers' shards.
+
+    ``last_tile_bits`` (with ``on_last``): a pass that carries an exchange is bound by NVLink, not by HBM or the
+    FP64 pipe, so it may as well do more gate work: as soon as everything that is left fits ONE tile of
+    ``last_tile_bits`` (> tile_bits) qubits, it becomes the last pass."""
     origin = [i for i, o in enumerate(ops) if o.kind != OP_NOP]
     ops = [ops[i] for i in origin]
     n = len(ops)
@@ -228,10 +232,18 @@ def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_g
         lq = set(low_qubits())
         return _choose_group(ops, deps, done, first, k, k - low, lambda q: q in lq, lq, max_group_ops)
 
+    k_normal = k
+    big = min(int(last_tile_bits or 0), n_local - 1) if on_last is not None else 0
     cur_tile, cur_ops = fixed_choice()
     while True:
         if not cur_ops:
             raise RuntimeError("planner made no progress at op %d" % first)
+        k = k_normal
+        if big > k_normal:
+            lq = set(low_qubits())
+            big_tile, big_ops = _choose_group(ops, deps, done, first, big, big - low, lambda q: q in lq, lq, max_group_ops)
+            if len(big_ops) == n - n_done and len(big_ops) > len(cur_ops):
+                cur_tile, cur_ops, k = big_tile, big_ops, big       # the rest of the batch in one (larger) tile
         # physical tile: the low positions, the group's qubits, then the lowest unused positions
         positions = set(range(low)) | set(pos_of[q] for q in cur_tile)
         if len(positions) > k:

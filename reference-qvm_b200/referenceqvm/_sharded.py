@@ -705,6 +705,10 @@ class ShardedEngine(object):
         if e0 is not None:
             self.timing["swap"].append((e0, self.shard.record_event()))
 
+    #: tile size of a pass that carries an exchange: it is bound by NVLink, so it takes everything that is left of
+    #: its batch as soon as that fits one larger tile (0, the default: same tile as every other pass -- on the
+    #: benchmark circuits the carrying pass is thin anyway: everything else is waiting for the exchange)
+    PUSH_TILE_BITS = int(os.environ.get("QVM_B200_PUSH_TILE_BITS", "0"))
     #: a batch's last group is deferred across the following exchange when it holds fewer ops than this
     DEFER_TAIL_BELOW = int(os.environ.get("QVM_B200_DEFER_TAIL", "16"))
 
@@ -732,7 +736,8 @@ class ShardedEngine(object):
 
         self.groups_launched += _planner.run_relabelled(
             batch, self.n_local, self.pos_of, launch, self.tile_bits, self.low_bits,
-            defer_tail_below=self.DEFER_TAIL_BELOW if defer else 0, leftover=leftover, on_last=on_last)
+            defer_tail_below=self.DEFER_TAIL_BELOW if defer else 0, leftover=leftover, on_last=on_last,
+            last_tile_bits=min(self.PUSH_TILE_BITS, self.n_local - self.g - 2))      # (room for the victims outside the tile)
         if e0 is not None:
             self.timing["batch"].append((e0, self.shard.record_event()))
         return leftover
