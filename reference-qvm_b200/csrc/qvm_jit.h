@@ -415,6 +415,8 @@ public:
             if (!e->cs.kernel) last_error_ = err;
             return e->cs.kernel ? &e->cs : nullptr;
         }
+        // an ahead-of-time job for this very source is on its way (precompile_async): its cubin will be on disk soon
+        if (!path.empty() && policy < 2 && aot_queued_.count(path)) return nullptr;
         if (seen_.size() > (1u << 20)) seen_.clear();
         if (policy < 2 && ++seen_[std::hash<std::string>()(src)] < (eager ? 1 : 2)) return nullptr;
         Entry* e = new Entry();

@@ -20,6 +20,7 @@ _RELABEL = os.environ.get("QVM_B200_RELABEL", "1") != "0"
 _SWAP_MATRIX = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
 
 _classify_cache = {}
+_walked_ahead = set()       # signatures of gate streams whose kernels were requested ahead of their run (Engine._compile_ahead)
 
 
 def compile_gate(matrix, qubits):
@@ -316,11 +317,39 @@ class Engine(object):
             if not self._merger.absorb(self.pending, piece):
                 self.pending.append(piece)
 
+    #: Ahead of a long flush on a large state the planner is walked once WITHOUT the device: every group's
+    #: specialised kernel goes to the background NVRTC threads at once (cubins via the disk cache), so that the
+    #: groups launched a second or two into the run already find theirs instead of being interpreted -- the first
+    #: call of a never-seen program then runs mostly on specialised kernels.  Costs one extra planner walk on the
+    #: host (~0.1 s for 1300 gates); skipped when the identity layout is not where the flush starts.
+    AHEAD_MIN_QUBITS = int(os.environ.get("QVM_B200_AHEAD_MIN_QUBITS", "29"))
+    AHEAD_MIN_OPS = 300
+
+    def _compile_ahead(self, ops):
+        if (self.n < self.AHEAD_MIN_QUBITS or len(ops) < self.AHEAD_MIN_OPS or not self.relabel
+                or not self.layout_is_identity() or getattr(self.state, "n_global", 0)):
+            return
+        signature = hash((self.n, self.tile_bits, self.low_bits,
+                          tuple((o.kind, o.targets, o.ctrl_mask) for o in ops)))
+        if signature in _walked_ahead:
+            return                   # this gate stream has been through here before: its kernels exist or are on their way
+        if len(_walked_ahead) > 4096:
+            _walked_ahead.clear()
+        _walked_ahead.add(signature)
+        try:
+            from referenceqvm import precompile
+            if os.environ.get("QVM_B200_JIT", "1") != "1" or not nat.jit_cache_dir():
+                return
+            precompile.walk_pending(ops, self.n, self.tile_bits, self.low_bits, wait=False)
+        except Exception:            # an optimisation only: the run itself reports real errors
+            pass
+
     def flush(self):
         self._merger.reset()
         if not self.pending:
             return
         ops, self.pending = self.pending, []
+        self._compile_ahead(ops)
         if self.relabel and self.n > self.tile_bits:
             self.groups_launched += _planner.run_relabelled(ops, self.n, self.pos_of, self._launch_relabelled,
                                                             self.tile_bits, self.low_bits)

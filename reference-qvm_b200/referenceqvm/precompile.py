@@ -116,6 +116,23 @@ class _DryShard(object):
         return {}
 
 
+def walk_pending(pending, n_qubits, tile_bits, low_bits, wait=True):
+    """Single-GPU planner walk over an already merged op list (what ``Engine.flush`` is about to run): every group
+    goes to ``qvm_spec_precompile``; with ``wait=False`` the compilations are left running on the library's
+    background threads (``Engine.flush`` calls this ahead of a long run on a large state, see there)."""
+    shard = _DryShard(n_qubits, _sharded.ShardContext(_DryComm(1), 0))
+    pos_of = list(range(n_qubits))
+    if _engine._RELABEL and n_qubits > tile_bits:
+        _planner.run_relabelled(pending, n_qubits, pos_of,
+                                lambda tile, gops, bring: shard.apply_group(tile, gops, bring if bring else [], low_bits),
+                                tile_bits, low_bits)
+    else:
+        shard.apply_groups(pending, tile_bits, low_bits)
+    if wait:
+        nat.jit_wait()
+    return shard
+
+
 def precompile_ops(ops, n_qubits, gpus=1, tile_bits=None, low_bits=None, exchange=None):
     """Compile the specialised kernels a run of ``ops`` (ClassifiedOps on logical qubits, in program order) on
     ``gpus`` GPUs would use.  ``exchange``: the exchange mode the run will use ("push" unless the shard's second
@@ -125,20 +142,13 @@ def precompile_ops(ops, n_qubits, gpus=1, tile_bits=None, low_bits=None, exchang
     tile_bits = _engine._TILE_BITS if tile_bits is None else tile_bits
     low_bits = _engine._LOW_BITS if low_bits is None else low_bits
     if gpus == 1:
-        shard = _DryShard(n_qubits, _sharded.ShardContext(_DryComm(1), 0))
         pending, merger = [], _engine.DiagonalMerger()
         for op in ops:
             if op.kind != nat.OP_NOP:
                 for piece in _engine.expand_op(op):
                     if not merger.absorb(pending, piece):
                         pending.append(piece)
-        pos_of = list(range(n_qubits))
-        if _engine._RELABEL and n_qubits > tile_bits:
-            _planner.run_relabelled(pending, n_qubits, pos_of,
-                                    lambda tile, gops, bring: shard.apply_group(tile, gops, bring if bring else [], low_bits),
-                                    tile_bits, low_bits)
-        else:
-            shard.apply_groups(pending, tile_bits, low_bits)
+        shard = walk_pending(pending, n_qubits, tile_bits, low_bits, wait=False)
     else:
         ctx = _sharded.ShardContext(_DryComm(gpus), 0)
         eng = _sharded.ShardedEngine(n_qubits, ctx, tile_bits=tile_bits, low_bits=low_bits, backend_factory=_DryShard,

@@ -85,6 +85,18 @@ class DeviceDensity(object):
     def _state(self):                     # (single-GPU engines: the raw DeviceState; kept for `_density = rho`)
         return self._engine.state
 
+    def close(self):
+        """Release a snapshot's device memory now (otherwise when the object is collected)."""
+        if self._live_state is None and self._engine is not None and not getattr(self, "_adopted", False):
+            try:
+                self._engine.close()
+            except Exception:             # interpreter shutdown
+                pass
+        self._engine = None
+
+    def __del__(self):
+        self.close()
+
     def _check(self):
         if self._live_state is not None and self._engine.state is not self._live_state:
             raise RuntimeError("this view of the QVM's density matrix is stale: the QVM has since replaced its "
@@ -176,6 +188,7 @@ class QVM_Density(QAM):
             if isinstance(eng, _engine.Engine) and isinstance(value._engine, _engine.Engine):
                 value._engine.restore_layout()
                 eng.adopt(value._engine.state)          # takes the buffer over (no copy)
+                value._adopted = True
             else:
                 eng.set_amplitudes(value.toarray().reshape(-1))
             return

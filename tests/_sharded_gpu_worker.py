@@ -101,6 +101,48 @@ def main():
     logical_of_phys[phys] = logical
     ref = logical_of_phys[np.asarray(orc.inverse_cdf_sample(probs_hbm, u), dtype=np.int64)]
     assert np.mean(idx == ref) > 0.999
+    # density matrices sharded by rows ("Density" row): small case against the oracle ...
+    from referenceqvm.qvm_density import INFINITY, NoiseModel
+    from _programs import oracle_ops as prog_ops
+
+    def dephased_plus_state(nq, f):
+        """rho after H(0) .. H(nq-1) with dephasing on every qubit after every instruction, closed form: qubit q is
+        in superposition from instruction q on, so its coherences are damped (nq - q) times."""
+        def entry(i, j):
+            d = i ^ j
+            return 2.0 ** -nq * float(np.prod([f ** (nq - q) for q in range(nq) if (d >> q) & 1] or [1.0]))
+        return entry
+
+    p1 = 1.0 - np.exp(-50e-9 / 30e-6)
+    sup = sum(np.kron(k, np.conj(k)) for k in G.dephasing(p1))
+    f = float(sup[1, 1].real)
+    nm = NoiseModel(T1=INFINITY, T2=30e-6, gate_time_1q=50e-9, gate_time_2q=150e-9, ro_fidelity=1.0)
+    for nq in ((6, 16) if os.environ.get("QVM_TEST_BIG") == "1" and world == 2 else (6,)):
+        dq = QVMConnection(type_trans="density", noise_model=nm)
+        dq.device = rank
+        hprog = spec_program([("H", [], [q]) for q in range(nq)])
+        rho = dq.density(hprog)
+        assert isinstance(dq._engine, _sharded.ShardedEngine)
+        entry = dephased_plus_state(nq, f)
+        if nq <= 8:                        # the closed form itself, against the oracle's Kraus arithmetic
+            vec = np.zeros(4 ** nq, dtype=complex)
+            vec[0] = 1.0
+            for _, m, q in prog_ops(hprog):
+                vec = orc.fast_density_gate(vec, m, q, nq)
+                for i in range(nq):
+                    vec = orc.fast_apply_kraus(vec, G.dephasing(p1), i, nq)
+            want = orc.vec_to_rho(vec, nq)
+            assert np.max(np.abs(np.asarray(rho.todense()) - want)) < 1e-12
+            assert max(abs(want[i, j] - entry(i, j)) for i in range(0, 64, 7) for j in range(0, 64, 5)) < 1e-14
+        rs = np.random.RandomState(nq)
+        pairs = [(int(rs.randint(1 << nq)), int(rs.randint(1 << nq))) for _ in range(48)] + [(0, 0), ((1 << nq) - 1, 0)]
+        worst = max(abs(rho[i, j] - entry(i, j)) for i, j in pairs)
+        assert worst < 1e-13, (nq, worst)
+        assert abs(np.sum(rho.diagonal()).real - 1.0) < 1e-12
+        print("rank %d: %d-qubit rho (%.0f GiB over %d GPUs) matches the closed form, worst %.1e"
+              % (rank, nq, 16.0 * 4 ** nq / 2 ** 30, world, worst))
+        del rho
+        dq._density = None
     dist.barrier()
     dist.destroy_process_group()
     print("rank %d/%d ok" % (rank, world))
