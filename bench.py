@@ -569,6 +569,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
     ap.add_argument("--config5-qubits", type=int, default=36, help="the extra leg on 8 GPUs (0: off)")
+    ap.add_argument("--config5-world", type=int, default=8, help="number of GPUs at which the extra leg runs")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -702,7 +703,7 @@ def main():
                     configs[name] = leg()
                 except Exception as exc:          # a leg must not cost the headline line
                     configs[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
-        if world == 8 and args.config5_qubits and args.config5_qubits > n:
+        if world == args.config5_world and args.config5_qubits and args.config5_qubits > n:
             try:
                 eng.close()
                 qvm._engine = None
@@ -718,7 +719,7 @@ def main():
                 dt5 = h.max_over_ranks(time.perf_counter() - t0)
                 ok = len(res) == args.shots and len(res[0]) == n5
                 del res
-                configs["config5_36q_8gpu"] = {
+                configs["config5_%dq_%dgpu" % (n5, world)] = {
                     "workload": "%d-qubit random circuit depth %d (%.0f GiB state, %.0f GiB per GPU), then "
                                 "run_and_measure with %d shots" % (n5, depth, 16.0 * 2 ** n5 / 2 ** 30,
                                                                    16.0 * 2 ** r5["n_local"] / 2 ** 30, args.shots),
@@ -726,7 +727,7 @@ def main():
                     "ms_per_step": r5["total_ms"] / r5["steps"], "roofline": rf5, "check": r5.get("check"),
                     "run_and_measure_s": dt5, "shots_ok": bool(ok)}
             except Exception as exc:
-                configs["config5_36q_8gpu"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+                configs["config5_%dq_%dgpu" % (n5, world)] = {"error": "%s: %s" % (type(exc).__name__, exc)}
         line["configs"] = configs
 
     if rank == 0:
