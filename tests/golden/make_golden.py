@@ -19,6 +19,7 @@ Outputs (all under tests/golden/):
   sampling.json/.npz   seeded density run_and_measure draws (np.random.choice stream)
   unitary.json/.npz    QVM_Unitary outputs
   expectation.json/.npz  psi^dagger tensor_up(PauliSum) psi and tr(rho tensor_up(PauliSum)) from the reference's pieces
+  stabilizer.json/.npz QVM_Stabilizer: tableaus, projected wavefunctions, densities, seeded run() outcomes
 """
 import collections
 import collections.abc
@@ -402,9 +403,56 @@ def golden_expectation():
     dump("expectation", meta, arrays)
 
 
+def golden_stabilizer():
+    """The reference's tableau simulator (qvm_stabilizer.py) on Clifford programs: final tableau, projected
+    wavefunction, density matrix, and seeded run() outcomes (one np.random.random() per random MEASURE)."""
+    rs = np.random.RandomState(42)
+    meta, arrays = [], {}
+    sq = QVMConnection(type_trans="stabilizer")
+    progs = {"bell": Program().inst(pg.H(0), pg.CNOT(0, 1)),
+             "ghz4_s": Program().inst(pg.H(0), pg.CNOT(0, 1), pg.CNOT(1, 2), pg.CNOT(2, 3), pg.S(3), pg.S(0)),
+             "hs": Program().inst(pg.H(0), pg.S(0), pg.S(0), pg.H(1), pg.S(1), pg.I(2))}
+    for k in range(4):                       # random Clifford circuits (the generators the reference executes)
+        n = 2 + k
+        prog = Program()
+        for _ in range(12 * n):
+            g = rs.randint(3)
+            if g == 0:
+                prog.inst(pg.H(int(rs.randint(n))))
+            elif g == 1:
+                prog.inst(pg.S(int(rs.randint(n))))
+            else:
+                a = int(rs.randint(n))
+                b = int((a + 1 + rs.randint(n - 1)) % n)
+                prog.inst(pg.CNOT(a, b))
+        progs["random%d" % n] = prog
+    for name, prog in progs.items():
+        wf = sq.wavefunction(prog)
+        arrays[name + ":tableau"] = np.array(sq.tableau)
+        arrays[name + ":wf"] = np.asarray(wf.amplitudes, dtype=np.complex128)
+        arrays[name + ":rho"] = np.asarray(sq.density(prog), dtype=np.complex128)
+        mprog = Program().inst(prog)
+        nq = int(sq.num_qubits)
+        for q in range(nq):
+            mprog.measure(q, [q])
+        np.random.seed(1000 + len(meta))
+        try:
+            arrays[name + ":runs"] = np.array(sq.run(mprog, list(range(nq)), trials=25))
+            arrays[name + ":rng_after"] = np.array([np.random.random()])
+            has_runs = True
+        except ValueError:
+            # the reference's rowsum also runs over DESTABILIZER rows, whose products may carry a phase of +-i
+            # (Aaronson-Gottesman ignore those signs); it raises "impossible value for the phase_accumulator"
+            has_runs = False
+        meta.append({"name": name, "n": nq, "program": ser_program(prog), "seed": 1000 + len(meta), "runs": has_runs})
+    dump("stabilizer", meta, arrays)
+
+
 if __name__ == "__main__":
-    golden_expectation() if "--expectation-only" in sys.argv else None
-    if "--expectation-only" in sys.argv:
+    only = [a[2:-5] for a in sys.argv[1:] if a.startswith("--") and a.endswith("-only")]
+    if only:
+        for name in only:
+            globals()["golden_" + name]()
         sys.exit(0)
     golden_gates()
     golden_operators()
@@ -414,4 +462,5 @@ if __name__ == "__main__":
     golden_sampling()
     golden_unitary()
     golden_expectation()
+    golden_stabilizer()
     os.system("du -sh %s" % HERE)

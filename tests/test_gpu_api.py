@@ -873,3 +873,27 @@ def test_batched_run_with_jumps_matches_the_per_trial_distribution(qvm):
     assert abs(res[:, 2].mean() - want2) < 0.03
     # the last trial's state is left in self.wf like the reference's loop
     assert abs(np.vdot(qvm.wf, qvm.wf).real - 1.0) < 1e-12
+
+
+def test_stabilizer_qvm_against_the_wavefunction_qvm(qvm):
+    """Reference tests/test_stabilizer_qvm.py:366-400 (test_random_stabilizer_circuit): a random H / S / CNOT
+    circuit on the tableau simulator and on the (GPU) wavefunction QVM give the same state up to a global phase."""
+    from pyquil.gates import S
+    rs = np.random.RandomState(42)
+    n = 5
+    prog = Program()
+    for _ in range(300):
+        g = rs.randint(3)
+        if g == 0:
+            prog.inst(H(int(rs.randint(n))))
+        elif g == 1:
+            prog.inst(S(int(rs.randint(n))))
+        else:
+            a = int(rs.randint(n))
+            prog.inst(CNOT(a, int((a + 1 + rs.randint(n - 1)) % n)))
+    stab = QVMConnection(type_trans="stabilizer")
+    a = np.asarray(stab.wavefunction(prog).amplitudes)
+    b = np.asarray(qvm.wavefunction(prog)[0].amplitudes)
+    assert abs(abs(np.vdot(a, b)) - 1.0) < 1e-12
+    rho = np.asarray(stab.density(prog))
+    assert np.max(np.abs(rho - np.outer(b, b.conj()))) < 1e-12
