@@ -24,8 +24,8 @@ def test_factory_types_and_errors():
     assert isinstance(d, QVM_Density) and d.noise_model is nm
     with pytest.raises(TypeError):
         QVMConnection(type_trans="tensor-network")
-    with pytest.raises(NotImplementedError):
-        QVMConnection(type_trans="stabilizer")
+    from referenceqvm.qvm_stabilizer import QVM_Stabilizer
+    assert isinstance(QVMConnection(type_trans="stabilizer"), QVM_Stabilizer)
 
 
 def test_identify_bits_like_reference():
