@@ -56,10 +56,12 @@ def test_sharded_engine_on_one_gpu(world, exchange):
                 got = eng.amplitudes()
                 err = float(np.max(np.abs(got - want)))
                 assert err < 1e-12, (n, depth, seed, err)
+                st = eng.stats()
+                # (in-process ranks ask for the same structure at the same moment: one of them compiles it, the others
+                # run that pass interpreted -- so the specialised launches are counted over all ranks)
+                jit_all = int(comm.allreduce([float(st["jit_launches"])])[0])
                 if rank == 0:
-                    st = eng.stats()
-                    facts[case] = (eng.swaps, eng.fused_swaps, st["fused_push_launches"], st["push_launches"],
-                                   st["jit_launches"])
+                    facts[case] = (eng.swaps, eng.fused_swaps, st["fused_push_launches"], st["push_launches"], jit_all)
                 psi = want
                 for q, r in ((n - 1, 0.3), (0, 0.8), (n // 2, 0.5)):
                     outcome, p0 = eng.measure(q, r if rank == 0 else -1.0)
