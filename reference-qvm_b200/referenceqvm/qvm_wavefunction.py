@@ -49,13 +49,35 @@ def _index_bits(indices, num_qubits=63):
     return np.unpackbits(by[:, :num_qubits // 8 + 1], axis=1, bitorder="little")
 
 
+_frozen_rows = [False]
+_GC_FREEZE = os.environ.get("QVM_B200_GC_FREEZE", "1") != "0"
+
+
+def _thaw_rows():
+    """Undo the ``gc.freeze()`` of the previous large result (see ``_rows_to_lists``)."""
+    if _frozen_rows[0]:
+        _frozen_rows[0] = False
+        gc.unfreeze()
+
+
 def _rows_to_lists(matrix):
-    """``matrix.tolist()`` with the cyclic garbage collector paused: a million row lists are a million
-    tracked containers, and the generational collections they trigger cost a third of the conversion."""
+    """``matrix.tolist()`` (the reference's return type: one Python list per trial) without paying the cyclic
+    garbage collector for it.  A million row lists are a million tracked containers: built with the collector
+    running, the generational collections they trigger cost a third of the conversion; built with it paused, the
+    first allocation after it is switched back on starts a full collection that walks all of them (0.15 s per
+    million rows on the GPU box, charged to whoever allocates next).  Rows cannot be part of a cycle, so for large
+    results the collector is told to leave them alone: ``gc.freeze()`` moves everything allocated so far to the
+    permanent generation -- until the next call into the QVM, which thaws (``gc.unfreeze()``) whatever is still
+    alive.  ``QVM_B200_GC_FREEZE=0`` turns this off."""
+    _thaw_rows()
     was_enabled = gc.isenabled()
     gc.disable()
     try:
-        return matrix.tolist()
+        out = matrix.tolist()
+        if _GC_FREEZE and was_enabled and len(out) >= 100000:
+            gc.freeze()
+            _frozen_rows[0] = True
+        return out
     finally:
         if was_enabled:
             gc.enable()
@@ -120,6 +142,7 @@ class QVM_Wavefunction(QAM):
         the program nor its gates are looked at again (referenceqvm/_compiled.py)."""
         if not isinstance(pyquil_program, Program):
             raise TypeError("I can only generate from pyQuil programs")
+        _thaw_rows()
         cache = self.plan_cache and _compiled.uses_base_hooks(self, QVM_Wavefunction, self._HOOKS)
         entry = _compiled.lookup(pyquil_program, self._plan_key()) if cache else None
         if entry is not None and (self._engine is None or isinstance(self._engine, _engine.Engine)):
