@@ -390,21 +390,27 @@ def roofline_of(h, r):
     peak, peak_src = measured_peaks()
     bytes_per_launch = 32.0 * 2 ** r["n_local"]
     avg_launch_ms = r["kernel_ms"] / max(r["plain_groups"], 1)
-    achieved = bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
     stats = r["stats"]
+    # the first pass of a step absorbs the reset (reads nothing: half the bytes); fused exchange passes are not in
+    # kernel_ms at all
+    zero_fused = min(stats.get("zero_fused_launches", 0), r["plain_groups"])
+    plain_bytes = bytes_per_launch * (r["plain_groups"] - 0.5 * zero_fused)
+    achieved = plain_bytes / (r["kernel_ms"] * 1e-3) / 1e9 if r["kernel_ms"] else 0.0
     jit_share = stats.get("jit_launches", 0) / float(max(r["groups"], 1))
     dominant = ("spec_kernel (NVRTC-specialised regtile group)" if jit_share >= 0.5 else "regtile_kernel")
     total_ms, steps, n_gates = r["total_ms"], r["steps"], r["n_gates"]
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_launch_ms,
+                "launches_that_absorbed_the_reset": zero_fused,
                 "launches_per_step": r["groups"] / float(steps),
                 "gates_per_launch": n_gates * steps / float(max(r["groups"], 1)),
                 "regtile_rounds_per_launch": stats.get("regtile_rounds", 0) / float(max(r["groups"], 1)),
                 "specialised_launch_share": jit_share,
                 "effective_gbs": n_gates * steps * bytes_per_launch * h.world / (total_ms * 1e-3) / 1e9,
-                "note": "per GPU (rank 0): one launch = one read + one write of the local shard; launches that also "
-                        "carry an exchange (fused pushes) are counted under nvlink, not here"}
+                "note": "per GPU (rank 0): one launch = one read + one write of the local shard (the launch that absorbs "
+                        "the step's reset reads nothing: counted with half the bytes); launches that also carry an "
+                        "exchange (fused pushes) are counted under nvlink, not here"}
     ratio, ratio_src = measured_traffic_ratio()
     if ratio is not None:
         roofline["traffic"] = ratio * bytes_per_launch

@@ -71,6 +71,7 @@ typedef struct qvm_stats {
     uint64_t push_launches;               /* stand-alone out-of-place exchange passes (qvm_exchange_push) */
     uint64_t fused_push_launches;         /* gate passes whose stores WERE the exchange (qvm_apply_group_push) */
     uint64_t graph_launches;              /* compiled programs replayed as one CUDA graph launch (qvm_plan_run) */
+    uint64_t zero_fused_launches;         /* gate passes that absorbed the reset (read nothing: 16 B per amplitude) */
 } qvm_stats_t;
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
@@ -129,7 +130,9 @@ int qvm_stats(const qvm_t* q, qvm_stats_t* out);
 int qvm_stats_reset(qvm_t* q);
 
 /* ---- state I/O (wavefunction() / density() readback: qvm_wavefunction.py:361-367) ------------ */
-int qvm_reset_zero(qvm_t* q, int set_amp0);     /* all zeros; amp[0] = 1 if set_amp0 (:354-355)   */
+/* all zeros; amp[0] = 1 if set_amp0 (:354-355).  Lazy: the next fused gate pass absorbs it (its first round reads
+ * nothing, the pass costs one write of the shard); any other access to the amplitudes runs the reset kernel first. */
+int qvm_reset_zero(qvm_t* q, int set_amp0);
 int qvm_set_state(qvm_t* q, uint64_t offset, uint64_t count, const double* re_im);
 int qvm_get_state(qvm_t* q, uint64_t offset, uint64_t count, double* re_im);
 /* Strided gather of `count` amplitudes: element j is amp[offset + j*stride] (diag of rho). */

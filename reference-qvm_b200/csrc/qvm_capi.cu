@@ -105,6 +105,7 @@ struct qvm_state {
     unsigned char* stage = nullptr;   // pinned
     size_t stage_bytes = 0;
     int measure_grid = 0;
+    int zero_pending = 0;             // lazy reset: 1 = the shard is (virtually) all zeros, 2 = zeros with amp[0] = 1
     qvm_stats_t stats{};
     uint64_t opc_hist[32] = {};
     LaunchRec rec;                    // scratch: the group being built / launched (reused across launches)
@@ -126,13 +127,26 @@ constexpr int kPartialsCap = 4096;
         }                                                                                              \
     } while (0)
 
-#define QVM_CHECK_HANDLE(q)                                                        \
+#define QVM_CHECK_HANDLE_LAZY(q)                                                   \
     do {                                                                           \
         if (!(q)) return fail(QVM_ERR_INVALID, "null handle");                     \
         if ((q)->sticky) return (q)->sticky; /* message of the original failure is kept */ \
         cudaError_t _e = cudaSetDevice((q)->device);                               \
         if (_e != cudaSuccess) return fail(QVM_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(_e)); \
     } while (0)
+
+// Every entry point that reads or writes amplitudes first makes a pending reset real (materialize_zero below); only
+// the fused-group launches consume it instead (their first round then reads nothing).
+#define QVM_CHECK_HANDLE(q)                                                        \
+    do {                                                                           \
+        QVM_CHECK_HANDLE_LAZY(q);                                                  \
+        if ((q)->zero_pending) {                                                   \
+            const int _rc = materialize_zero(q);                                   \
+            if (_rc != QVM_OK) return _rc;                                         \
+        }                                                                          \
+    } while (0)
+
+int materialize_zero(qvm_state* q);
 
 int grid_for(const qvm_state* q, uint64_t work_items, int threads, int per_sm = 8) {
     uint64_t blocks = (work_items + threads - 1) / threads;
@@ -143,6 +157,18 @@ int grid_for(const qvm_state* q, uint64_t work_items, int threads, int per_sm = 
 }
 
 int total_positions(const qvm_state* q) { return q->n_local + q->n_global; }
+
+// the reset that qvm_reset_zero only noted down, as a kernel
+int materialize_zero(qvm_state* q) {
+    if (!q->zero_pending) return QVM_OK;
+    const int set_amp0 = q->zero_pending == 2;
+    q->zero_pending = 0;
+    fill_zero_kernel<<<grid_for(q, q->n_elems, 256), 256, 0, q->stream>>>(q->amps, q->n_elems, set_amp0);
+    QVM_CUDA(q, cudaGetLastError());
+    q->stats.kernel_launches += 1;
+    q->stats.hbm_bytes += 16ull * q->n_elems;
+    return QVM_OK;
+}
 
 // ---- gate classification -----------------------------------------------------------------------
 struct cplx {
@@ -426,6 +452,15 @@ int launch_regtile(qvm_state* q, unsigned grid, unsigned threads, size_t smem, c
     return QVM_OK;
 }
 
+// QVM_B200_FOLD_RESET=0: always reset with a kernel of its own (A/B runs)
+bool fold_reset_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("QVM_B200_FOLD_RESET");
+        return !e || atoi(e) != 0;
+    }();
+    return on;
+}
+
 // A pushing pass walks its tiles with the victim bits as the FASTEST-varying bits of the tile index (the runs of
 // non-tile positions the block index is deposited into are launch parameters): consecutive CTAs then store to
 // different destinations in turn, so the NVLink stores are spread over the whole kernel instead of all local
@@ -465,6 +500,14 @@ void runs_for_push(const PushSpec& push, int& n_runs, uint64_t& run_start, uint6
 int launch_rec(qvm_state* q, LaunchRec& rec, const PushSpec* push = nullptr, bool* pushed = nullptr) {
     if (rec.kind == REC_NONE) return QVM_OK;
     if (push && push->m && (rec.tile_mask & push->mask)) push = nullptr;     // a victim bit inside the tile: not fusable
+    // a pending reset is folded into this pass when the register-tiled kernels run it (their round 0 then reads
+    // nothing); the other kernels get a real reset first
+    int from_zero = q->zero_pending;
+    if (from_zero && (rec.kind != REC_REGTILE || (rec.has_spec && rec.spec.ctas_per_sm) || !fold_reset_enabled())) {
+        const int rc0 = materialize_zero(q);
+        if (rc0 != QVM_OK) return rc0;
+        from_zero = 0;
+    }
     if (rec.kind == REC_TILE) {
         const size_t ops_bytes = rec.dev.size() * sizeof(DevOp);
         const size_t mats_bytes = rec.mats.size() * sizeof(double);
@@ -505,6 +548,7 @@ int launch_rec(qvm_state* q, LaunchRec& rec, const PushSpec* push = nullptr, boo
             }
             double2* amps = q->amps;
             SpecParams sp = ss.params;
+            sp.from_zero = from_zero;
             if (push && push->m) {
                 sp.push = *push;
                 runs_for_push(*push, sp.n_runs, sp.run_start, sp.run_len);
@@ -515,11 +559,13 @@ int launch_rec(qvm_state* q, LaunchRec& rec, const PushSpec* push = nullptr, boo
             if (ss.ctas_per_sm)      // persistent, pipelined variant
                 grid = (unsigned)std::min<uint64_t>(g.n_tiles, (uint64_t)q->sm_count * ss.ctas_per_sm);
             QVM_CUDA(q, cudaLaunchKernel((const void*)cs->kernel, dim3(grid), dim3(ss.threads), args, ss.smem, q->stream));
+            q->zero_pending = 0;
             q->stats.kernel_launches += 1;
             q->stats.jit_launches += 1;
             q->stats.gate_ops += (uint64_t)g.n_gate_ops;
             q->stats.hbm_passes += 1;
-            q->stats.hbm_bytes += 32ull * q->n_elems;
+            q->stats.hbm_bytes += (from_zero ? 16ull : 32ull) * q->n_elems;
+            q->stats.zero_fused_launches += from_zero ? 1 : 0;
             q->stats.h2d_bytes += ss.factors.size() * sizeof(double);
             q->stats.regtile_rounds += (uint64_t)g.rounds.size();
             return QVM_OK;
@@ -544,6 +590,7 @@ int launch_rec(qvm_state* q, LaunchRec& rec, const PushSpec* push = nullptr, boo
     QVM_CUDA(q, cudaMemcpyAsync(q->ring_dev + off, hp, total_bytes, cudaMemcpyHostToDevice, q->stream));
     unsigned char* dp = q->ring_dev + off;
     RegTileParams P = g.P;
+    P.from_zero = from_zero;
     if (push && push->m) {
         P.push = *push;
         runs_for_push(*push, P.n_runs, P.run_start, P.run_len);
@@ -577,10 +624,12 @@ int launch_rec(qvm_state* q, LaunchRec& rec, const PushSpec* push = nullptr, boo
                          : launch_regtile<256, 2, false, 4>(q, grid, g.threads, g.smem, P);
     }
     if (rc) return rc;
+    q->zero_pending = 0;
     q->stats.kernel_launches += 1;
     q->stats.gate_ops += (uint64_t)g.n_gate_ops;
     q->stats.hbm_passes += 1;
-    q->stats.hbm_bytes += 32ull * q->n_elems;
+    q->stats.hbm_bytes += (from_zero ? 16ull : 32ull) * q->n_elems;
+    q->stats.zero_fused_launches += from_zero ? 1 : 0;
     q->stats.h2d_bytes += total_bytes;
     q->stats.regtile_rounds += (uint64_t)g.rounds.size();
     return QVM_OK;
@@ -740,7 +789,7 @@ int qvm_destroy(qvm_t* q) {
 }
 
 int qvm_set_shard(qvm_t* q, int n_global, uint64_t shard_index) {
-    QVM_CHECK_HANDLE(q);
+    QVM_CHECK_HANDLE_LAZY(q);
     if (n_global < 0 || q->n_local + n_global > 62) return fail(QVM_ERR_INVALID, "bad n_global=%d", n_global);
     if (n_global < 64 && (shard_index >> n_global)) return fail(QVM_ERR_INVALID, "shard index out of range");
     q->n_global = n_global;
@@ -756,7 +805,7 @@ int qvm_set_stream(qvm_t* q, void* cuda_stream) {
 }
 
 int qvm_set_tile_bits(qvm_t* q, int tile_bits, int low_bits) {
-    QVM_CHECK_HANDLE(q);
+    QVM_CHECK_HANDLE_LAZY(q);
     if (tile_bits < 1 || tile_bits > QVM_MAX_TILE_BITS || low_bits < 0 || low_bits > tile_bits)
         return fail(QVM_ERR_INVALID, "bad tile configuration (%d, %d)", tile_bits, low_bits);
     q->tile_bits = tile_bits;
@@ -831,14 +880,14 @@ int qvm_jit_shutdown(void) {
 }
 
 int qvm_set_jit(qvm_t* q, int policy) {
-    QVM_CHECK_HANDLE(q);
+    QVM_CHECK_HANDLE_LAZY(q);
     if (policy < 0 || policy > 2) return fail(QVM_ERR_INVALID, "JIT policy must be 0, 1 or 2");
     q->jit_policy = policy;
     return QVM_OK;
 }
 
 int qvm_set_kernel_path(qvm_t* q, int use_regtile) {
-    QVM_CHECK_HANDLE(q);
+    QVM_CHECK_HANDLE_LAZY(q);
     q->use_regtile = use_regtile ? 1 : 0;
     return QVM_OK;
 }
@@ -850,7 +899,10 @@ int qvm_debug_opcode_hist(qvm_t* q, uint64_t* out32) {
 }
 
 int qvm_n_local(const qvm_t* q) { return q ? q->n_local : -1; }
-void* qvm_device_ptr(qvm_t* q) { return q ? q->amps : nullptr; }
+void* qvm_device_ptr(qvm_t* q) {
+    if (q && q->zero_pending) materialize_zero(q);            // whoever gets the raw pointer sees real zeros
+    return q ? q->amps : nullptr;
+}
 void* qvm_stream(qvm_t* q) { return q ? q->stream : nullptr; }
 
 int qvm_sync(qvm_t* q) {
@@ -873,11 +925,10 @@ int qvm_stats_reset(qvm_t* q) {
 
 // ---- state I/O ------------------------------------------------------------------------------------
 int qvm_reset_zero(qvm_t* q, int set_amp0) {
-    QVM_CHECK_HANDLE(q);
-    fill_zero_kernel<<<grid_for(q, q->n_elems, 256), 256, 0, q->stream>>>(q->amps, q->n_elems, set_amp0);
-    QVM_CUDA(q, cudaGetLastError());
-    q->stats.kernel_launches += 1;
-    q->stats.hbm_bytes += 16ull * q->n_elems;
+    QVM_CHECK_HANDLE_LAZY(q);
+    // lazy: noted down, and folded into the next fused gate pass (whose first round then reads nothing) or made
+    // real by whatever touches the amplitudes first
+    q->zero_pending = set_amp0 ? 2 : 1;
     q->sample_mode = -1;
     return QVM_OK;
 }
@@ -973,6 +1024,11 @@ int qvm_copy_state(qvm_t* dst, qvm_t* src) {
     if (!src) return fail(QVM_ERR_INVALID, "null source");
     if (dst->n_local != src->n_local || dst->device != src->device)
         return fail(QVM_ERR_INVALID, "copy needs equal shapes on one device");
+    dst->zero_pending = 0;                           // overwritten anyway
+    if (src->zero_pending) {
+        const int rc0 = materialize_zero(src);
+        if (rc0 != QVM_OK) return rc0;
+    }
     QVM_CUDA(src, cudaStreamSynchronize(src->stream));
     QVM_CUDA(dst, cudaMemcpyAsync(dst->amps, src->amps, dst->n_elems * 16, cudaMemcpyDeviceToDevice, dst->stream));
     dst->sample_mode = -1;
@@ -998,7 +1054,7 @@ int qvm_classify(int k, const int32_t* qubits, const double* matrix, qvm_op_t* o
 }
 
 int qvm_apply(qvm_t* q, int k, const int32_t* qubits, const double* matrix) {
-    QVM_CHECK_HANDLE(q);
+    QVM_CHECK_HANDLE_LAZY(q);
     if (!qubits || !matrix) return fail(QVM_ERR_INVALID, "null pointer");
     if (k < 1 || k > 10) return fail(QVM_ERR_INVALID, "gate size k=%d outside [1, 10]", k);
     int rc = validate_qubits(q, k, qubits);
@@ -1035,7 +1091,7 @@ int qvm_apply(qvm_t* q, int k, const int32_t* qubits, const double* matrix) {
 
 int qvm_apply_group(qvm_t* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops, const double* mats,
                     uint64_t mats_entries) {
-    QVM_CHECK_HANDLE(q);
+    QVM_CHECK_HANDLE_LAZY(q);
     if (n_ops < 0 || (n_ops && !ops) || (n_tile && !tile_bits)) return fail(QVM_ERR_INVALID, "null pointer");
     if (mats_entries && !mats) return fail(QVM_ERR_INVALID, "null matrix pool");
     q->sample_mode = -1;
@@ -1045,7 +1101,7 @@ int qvm_apply_group(qvm_t* q, int n_tile, const int32_t* tile_bits, int n_ops, c
 int qvm_apply_group_relabel(qvm_t* q, int n_tile, const int32_t* tile_bits, int n_ops, const qvm_op_t* ops,
                             const double* mats, uint64_t mats_entries, int n_low, int n_bring, const int32_t* bring_low,
                             int32_t* new_pos) {
-    QVM_CHECK_HANDLE(q);
+    QVM_CHECK_HANDLE_LAZY(q);
     if (n_ops < 0 || (n_ops && !ops) || (n_tile && !tile_bits) || !new_pos || (n_bring && !bring_low))
         return fail(QVM_ERR_INVALID, "null pointer");
     if (mats_entries && !mats) return fail(QVM_ERR_INVALID, "null matrix pool");
@@ -1067,7 +1123,7 @@ int qvm_apply_group_relabel(qvm_t* q, int n_tile, const int32_t* tile_bits, int 
 
 // ---- compiled programs: record the launches of a flush once, replay them on every later run ----------
 int qvm_record_begin(qvm_t* q) {
-    QVM_CHECK_HANDLE(q);
+    QVM_CHECK_HANDLE_LAZY(q);
     if (q->recording) return fail(QVM_ERR_INVALID, "a recording is already open on this handle");
     qvm_plan* plan = new (std::nothrow) qvm_plan();
     if (!plan) return fail(QVM_ERR_NOMEM, "host allocation failed");
@@ -1098,38 +1154,43 @@ int qvm_plan_destroy(qvm_plan_t* plan) {
 }
 
 static int plan_launch_all(qvm_t* q, qvm_plan_t* plan, int reset_first, bool* all_specialised) {
-    if (reset_first) {
-        fill_zero_kernel<<<grid_for(q, q->n_elems, 256), 256, 0, q->stream>>>(q->amps, q->n_elems, 1);
-        QVM_CUDA(q, cudaGetLastError());
-        q->stats.kernel_launches += 1;
-        q->stats.hbm_bytes += 16ull * q->n_elems;
-    }
+    if (reset_first) q->zero_pending = 2;            // folded into the first launch below
     bool all = true;
     for (LaunchRec& rec : plan->recs) {
         const int rc = launch_rec(q, rec);
         if (rc != QVM_OK) return rc;
         all = all && rec.kind == REC_REGTILE && rec.cs != nullptr && q->jit_policy > 0;
     }
+    if (q->zero_pending) {                           // a plan without launches: the reset is all there is
+        const int rc = materialize_zero(q);
+        if (rc != QVM_OK) return rc;
+    }
     if (all_specialised) *all_specialised = all;
     return QVM_OK;
 }
 
 int qvm_plan_run(qvm_t* q, qvm_plan_t* plan, int reset_first) {
-    QVM_CHECK_HANDLE(q);
+    QVM_CHECK_HANDLE_LAZY(q);
     if (!plan) return fail(QVM_ERR_INVALID, "null plan");
     if (q->recording) return fail(QVM_ERR_INVALID, "a recording is open on this handle");
     if (plan->n_local != q->n_local || plan->n_global != q->n_global || plan->shard_index != q->shard_index)
         return fail(QVM_ERR_INVALID, "plan was compiled for another shard shape");
     q->sample_mode = -1;
     ++plan->runs;
+    if (!reset_first && q->zero_pending) {           // (a replay on top of a reset somebody else asked for)
+        const int rc0 = materialize_zero(q);
+        if (rc0 != QVM_OK) return rc0;
+    }
     if (plan->graph && plan->graph_amps == q->amps && plan->graph_reset == reset_first) {
         QVM_CUDA(q, cudaGraphLaunch(plan->graph, q->stream));
+        q->zero_pending = 0;                         // the captured first pass carries the reset
         q->stats.kernel_launches += plan->graph_stats.kernel_launches;
         q->stats.jit_launches += plan->graph_stats.jit_launches;
         q->stats.gate_ops += plan->graph_stats.gate_ops;
         q->stats.hbm_passes += plan->graph_stats.hbm_passes;
         q->stats.hbm_bytes += plan->graph_stats.hbm_bytes;
         q->stats.regtile_rounds += plan->graph_stats.regtile_rounds;
+        q->stats.zero_fused_launches += plan->graph_stats.zero_fused_launches;
         q->stats.graph_launches += 1;
         return QVM_OK;
     }
@@ -1167,6 +1228,7 @@ int qvm_plan_run(qvm_t* q, qvm_plan_t* plan, int reset_first) {
             plan->graph_stats.hbm_passes = after.hbm_passes - before.hbm_passes;
             plan->graph_stats.hbm_bytes = after.hbm_bytes - before.hbm_bytes;
             plan->graph_stats.regtile_rounds = after.regtile_rounds - before.regtile_rounds;
+            plan->graph_stats.zero_fused_launches = after.zero_fused_launches - before.zero_fused_launches;
             return qvm_plan_run(q, plan, reset_first);        // (takes the graph branch above)
         }
         cudaGetLastError();
@@ -1289,6 +1351,10 @@ int qvm_gather_segments(qvm_t* dst, qvm_t* src, int n_per_trial, uint64_t count,
     for (uint64_t j = 0; j < count; ++j)
         if (src_index[j] >= src_segs) return fail(QVM_ERR_INVALID, "source segment %u out of range", src_index[j]);
     if (!count) return QVM_OK;
+    if (src->zero_pending) {
+        const int rc0 = materialize_zero(src);
+        if (rc0 != QVM_OK) return rc0;
+    }
     QVM_CUDA(src, cudaStreamSynchronize(src->stream));
     uint32_t* dev = nullptr;
     QVM_CUDA(dst, cudaMallocAsync(&dev, count * sizeof(uint32_t), dst->stream));
@@ -1473,6 +1539,10 @@ int qvm_inner_product(qvm_t* a, qvm_t* b, double* re_im_partial) {
     QVM_CHECK_HANDLE(a);
     if (!b || !re_im_partial) return fail(QVM_ERR_INVALID, "null pointer");
     if (a->n_local != b->n_local || a->device != b->device) return fail(QVM_ERR_INVALID, "shards of different shape");
+    if (b->zero_pending) {
+        const int rc0 = materialize_zero(b);
+        if (rc0 != QVM_OK) return rc0;
+    }
     QVM_CUDA(b, cudaStreamSynchronize(b->stream));
     const int grid = std::min(grid_for(a, a->n_elems, kReduceThreads), kPartialsCap / 2);
     inner_partial_kernel<<<grid, kReduceThreads, 0, a->stream>>>(a->amps, b->amps, a->n_elems, a->partials);
@@ -1774,7 +1844,7 @@ int qvm_apply_group_push(qvm_t* q, int n_tile, const int32_t* tile_bits, int n_o
                          const double* mats, uint64_t mats_entries, int n_low, int n_bring, const int32_t* bring_low,
                          int32_t* new_pos, int m, const int32_t* local_bits, uint32_t mine_value, void* const* dst_ptrs,
                          int* fused) {
-    QVM_CHECK_HANDLE(q);
+    QVM_CHECK_HANDLE_LAZY(q);
     if (n_ops < 0 || (n_ops && !ops) || (n_tile && !tile_bits) || !new_pos || (n_bring && !bring_low))
         return fail(QVM_ERR_INVALID, "null pointer");
     if (mats_entries && !mats) return fail(QVM_ERR_INVALID, "null matrix pool");

@@ -38,6 +38,7 @@ struct SpecParams {
     uint64_t shard_bits, run_start, run_len;
     uint64_t n_tiles;                // pipelined variant: tiles are walked by a persistent grid
     PushSpec push;                   // fused exchange: where the last round stores (launch-time, m == 0: in place)
+    int from_zero;                   // the reset folded into this pass (see RegTileParams::from_zero)
 };
 
 struct SpecSource {
@@ -173,6 +174,8 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
                  << lin_of(rd.swz_j[2]) << "u, " << lin_of(rd.swz_j[3]) << "u};\n"
                     "#pragma unroll\n    for (int j = 0; j < 16; ++j) a[j] = tile[T ^ xor_combo<4>(lin, j)];\n";
         } else if (first && !pipe) {
+            body << "    if (SP.from_zero) {\n#pragma unroll\n      for (int j = 0; j < 16; ++j) a[j] = make_double2(0.0, 0.0);\n"
+                    "      if (SP.from_zero == 2 && base == 0 && tid == 0) a[0].x = 1.0;\n    } else\n";
             body << "    {\n      const uint64_t gT = (uint64_t)(T & " << ((1u << P.low) - 1u) << "u) | hi_off[T >> " << P.low
                  << "];\n      const int64_t b[4] = {";
             for (int s = 0; s < 4; ++s) body << (s ? ", " : "") << "(int64_t)(16ull << " << (int)rd.reg_phys[s] << ")";
@@ -287,7 +290,7 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
     if (F.empty()) F.push_back(0.0);
     if (F.size() > 3900) return false;          // kernel parameters are limited to 32 KB
     o << "#include \"qvm_regtile.cuh\"\nusing namespace qvm;\n"
-         "struct SpecParams { int n_runs; uint64_t shard_bits, run_start, run_len, n_tiles; PushSpec push; };\n"
+         "struct SpecParams { int n_runs; uint64_t shard_bits, run_start, run_len, n_tiles; PushSpec push; int from_zero; };\n"
          "struct SpecFactors { double v[" << F.size() << "]; };\n"
          "__device__ const uint64_t hi_off[" << g.hi_off.size() << "] = {";
     for (size_t j = 0; j < g.hi_off.size(); ++j) o << (j ? ", " : "") << hexu(g.hi_off[j]);
@@ -369,7 +372,7 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
     out.smem = (pipe || tma) ? ((size_t)32 << P.k) : (P.n_rounds > 1 ? ((size_t)16 << P.k) : 0);
     out.n_tiles = g.n_tiles;
     out.ctas_per_sm = (pipe || tma) ? ctas : 0;
-    out.params = SpecParams{P.n_runs, P.shard_bits, P.run_start, P.run_len, g.n_tiles, PushSpec{}};
+    out.params = SpecParams{P.n_runs, P.shard_bits, P.run_start, P.run_len, g.n_tiles, PushSpec{}, 0};
     return true;
 }
 

@@ -182,6 +182,10 @@ struct RegTileParams {
     // of tile index i to shared-memory slot swz(sigma(i)); the later rounds run in the new tile
     // coordinates, so the qubit of tile bit b leaves the pass on tile bit sigma(b).
     int perm_round;
+    // The reset folded into the first pass: the shard is known to be all zeros (2: plus amp[0] = 1 on this shard),
+    // so round 0 does not read HBM at all -- the reference's `wf = zeros; wf[0] = 1` (qvm_wavefunction.py:354-355)
+    // followed by its first gate costs one write of the shard instead of a write, a read and a write.
+    int from_zero;
     uint16_t perm_swz[16];    // swz(1 << sigma(b)) for every tile bit b
     PushSpec push;            // where the last round stores (fused exchange); m == 0: in place
     uint64_t shard_bits;
@@ -541,7 +545,14 @@ QVM_HD void add_tree(PTR p0, const int64_t (&b)[R], PTR (&q)[1 << R]) {
 
 // Round 0's tile load: everything it needs comes from kernel parameters and one L2-resident table.
 template <int R>
-QVM_HD void rt_first_load(const RegTileParams& P, const double2* gbase, const uint32_t tid, double2 (&a)[1 << R]) {
+QVM_HD void rt_first_load(const RegTileParams& P, const double2* gbase, const uint32_t tid, double2 (&a)[1 << R],
+                          const bool first_tile = false) {
+    if (P.from_zero) {
+#pragma unroll
+        for (int j = 0; j < (1 << R); ++j) a[j] = make_double2(0.0, 0.0);
+        if (P.from_zero == 2 && first_tile && tid == 0) a[0].x = 1.0;       // thread 0, slot 0 of tile 0 = amplitude 0
+        return;
+    }
     uint32_t T = tid;
 #pragma unroll
     for (int s = 0; s < R; ++s) T += T & P.first_ins[s];
@@ -859,7 +870,7 @@ regtile_kernel(double2* __restrict__ state, const __grid_constant__ RegTileParam
     c.low = P.low;
     c.n_rounds = P.n_rounds;
     double2 a[1 << R];
-    rt_first_load<R>(P, state + base, tid, a);
+    rt_first_load<R>(P, state + base, tid, a, base == 0);
     for (int r = 0; r < P.n_rounds; ++r) {
         rt_thread_round<FULL, R>(c, r, tid, a);
         if (r + 1 < P.n_rounds) __syncthreads();

@@ -36,7 +36,7 @@ class Stats(C.Structure):
     """``qvm_stats_t``"""
     _fields_ = [(name, C.c_uint64) for name in
                 ("kernel_launches", "gate_ops", "hbm_passes", "hbm_bytes", "h2d_bytes", "d2h_bytes", "regtile_rounds",
-                 "jit_launches", "jit_compiles", "push_launches", "fused_push_launches", "graph_launches")]
+                 "jit_launches", "jit_compiles", "push_launches", "fused_push_launches", "graph_launches", "zero_fused_launches")]
 
     def as_dict(self):
         return {name: int(getattr(self, name)) for name, _ in self._fields_}

@@ -689,6 +689,7 @@ class ShardedEngine(object):
             base_rank &= ~(1 << gb)
         block = 1 << (self.n_local - m)
         e0 = self.shard.record_event() if self.timing is not None else None
+        self.shard.sync()          # (also makes a pending lazy reset real before a peer reads this shard)
         self.comm.stream_barrier(self.shard)
         for step in range(1, 1 << m):
             # XOR schedule: at every step the 2^m ranks of the subgroup pair up perfectly, so no GPU is
@@ -791,6 +792,7 @@ class ShardedEngine(object):
         if self.exchange == "p2p":
             # stream-ordered cross-rank barrier (a tiny all-reduce), the swap kernel on my half of the
             # element range, barrier again: nobody touches a shard its partner is still working on
+            self.shard.sync()      # (also makes a pending lazy reset real before a peer reads this shard)
             self.comm.stream_barrier(self.shard)
             lo = 0 if mine == 0 else half // 2
             cnt = half // 2 if mine == 0 else half - half // 2
