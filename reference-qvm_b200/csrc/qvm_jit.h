@@ -287,6 +287,20 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
         body << "  }\n";
         if (!last) body << "  __syncthreads();\n";
     }
+    // The pass that absorbs the reset (SpecParams::from_zero): every tile but the one holding amplitude 0 is all zeros
+    // and stays all zeros under linear gates -- those CTAs store zeros through the last round's addresses and leave.
+    std::ostringstream zero_tile;
+    {
+        const RoundDesc& rl = g.rounds[P.n_rounds - 1];
+        zero_tile << "  if (SP.from_zero && base != 0) {\n    uint32_t T = tid;\n";
+        for (int s = 0; s < 4; ++s) zero_tile << "    T += T & 0x" << std::hex << rl.ins_mask[s] << std::dec << "u;\n";
+        zero_tile << "    const uint64_t gT = (uint64_t)(T & " << ((1u << P.low) - 1u) << "u) | hi_off[T >> " << P.low
+                  << "];\n    const int64_t b[4] = {";
+        for (int s = 0; s < 4; ++s) zero_tile << (s ? ", " : "") << "(int64_t)(16ull << " << (int)rl.reg_phys[s] << ")";
+        zero_tile << "};\n    char* q[16];\n    add_tree<4>(reinterpret_cast<char*>(gstore + gT), b, q);\n"
+                     "#pragma unroll\n    for (int j = 0; j < 16; ++j) *reinterpret_cast<double2*>(q[j]) = make_double2(0.0, 0.0);\n"
+                     "    return;\n  }\n";
+    }
     if (F.empty()) F.push_back(0.0);
     if (F.size() > 3900) return false;          // kernel parameters are limited to 32 KB
     o << "#include \"qvm_regtile.cuh\"\nusing namespace qvm;\n"
@@ -337,7 +351,7 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
              "  const uint32_t tid = threadIdx.x;\n  const uint64_t base = spec_tile_base(SP, blockIdx.x);\n"
              "  const uint64_t full = base | SP.shard_bits;\n  double2* gbase = state + base;\n"
              "  double2* gstore = rt_push_base(SP.push, state, base);\n  double2 a[16];\n"
-          << body.str() << "}\n";
+          << zero_tile.str() << body.str() << "}\n";
     } else {
         // Persistent CTA, two tile buffers.  Thread `tid` fetches the tile-local indices tid + threads * j
         // (j = 0..15): consecutive lanes read consecutive amplitudes (256-byte runs), the global offset splits
@@ -571,9 +585,11 @@ private:
         workers_started_ = true;
         load_nvrtc(nullptr);                      // before atexit: handlers run in reverse order of registration
         std::atexit([] { SpecCache::instance().shutdown(); });
-        unsigned n = std::thread::hardware_concurrency() / 2;
+        // NVRTC is the bottleneck of a first call (~0.5-1 s of front end per structure): all cores but two
+        const unsigned hw = std::thread::hardware_concurrency();
+        unsigned n = hw > 3 ? hw - 2 : 1;
         if (const char* e = getenv("QVM_B200_JIT_THREADS")) n = (unsigned)atoi(e);
-        n = n < 1 ? 1 : (n > 16 ? 16 : n);
+        n = n < 1 ? 1 : (n > 32 ? 32 : n);
         for (unsigned i = 0; i < n; ++i) std::thread([this] { worker(); }).detach();
     }
     void worker() {
