@@ -411,7 +411,12 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
             slot_of[rd.slot_bit[s]] = (int8_t)s;
             sorted[s] = rd.slot_bit[s];
         }
-        std::sort(sorted, sorted + R);
+        for (int s = 1; s < R; ++s) {       // R <= kMaxRegBits: insertion sort
+            const int v = sorted[s];
+            int t = s;
+            for (; t > 0 && sorted[t - 1] > v; --t) sorted[t] = sorted[t - 1];
+            sorted[t] = v;
+        }
         for (int s = 0; s < R; ++s) d.ins_mask[s] = (uint16_t)~((1u << sorted[s]) - 1u);
         int nt = 0;
         for (int b = 0; b < n_tile; ++b)
