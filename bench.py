@@ -620,6 +620,7 @@ def main():
                    "specialised_launch_share": st["jit_launches"] / float(max(st["hbm_passes"], 1)),
                    "cubins_loaded_from_disk_cache": c1["disk_hits"] - c0["disk_hits"],
                    "structures_sent_to_nvrtc": c1["nvrtc_compiles"] - c0["nvrtc_compiles"],
+                   "launches_that_waited_for_their_kernel": st["paced_waits"],
                    "breakdown_s": dict(q1.last_timing)}
             q1._engine.close()
             q1._engine = None
@@ -627,8 +628,10 @@ def main():
             return out
 
         e2e_cold = first_call(4321, "first run_and_measure(program, all qubits, trials=%d) of a program nobody has seen "
-                                    "(seed 4321; state already allocated): every group structure is new, passes run on the "
-                                    "interpreter while NVRTC compiles in the background" % args.shots)
+                                    "(seed 4321; state already allocated): every group structure is new; the program is walked "
+                                    "ahead of the run and NVRTC compiles on the host cores while the first passes go through "
+                                    "the interpreter; a launch waits for a kernel that is on its way only while the GPU still "
+                                    "has earlier passes queued" % args.shots)
         e2e_first = first_call(SEED, "first call of the benchmark program in this process, nothing warmed up; its "
                                      "specialised cubins come from the disk cache that build() filled ahead of time")
 

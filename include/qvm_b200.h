@@ -72,6 +72,8 @@ typedef struct qvm_stats {
     uint64_t fused_push_launches;         /* gate passes whose stores WERE the exchange (qvm_apply_group_push) */
     uint64_t graph_launches;              /* compiled programs replayed as one CUDA graph launch (qvm_plan_run) */
     uint64_t zero_fused_launches;         /* gate passes that absorbed the reset (read nothing: 16 B per amplitude) */
+    uint64_t paced_waits;                 /* launches that waited for their kernel to finish compiling while the GPU
+                                             still had earlier passes queued (no device time lost)                  */
 } qvm_stats_t;
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
@@ -120,6 +122,10 @@ int qvm_spec_precompile(int n_local, int n_global, uint64_t shard_index, int n_t
 /* out4 = {structures submitted to NVRTC, cubins loaded from the disk cache, cubins written to it, kernels ready} */
 int qvm_jit_counters(uint64_t* out4);
 int qvm_jit_cache_dir(char* out, uint64_t cap);
+/* The next n qvm_spec_precompile submissions are compiled after everything queued the normal way: the first passes
+ * of a run that starts right away go through the interpreter before any compilation could finish, so the kernels
+ * of the later passes should come first. */
+int qvm_jit_defer(int n);
 /* Debug: how many ops of each register-tile opcode were encoded so far (32 counters). */
 int qvm_debug_opcode_hist(qvm_t* q, uint64_t* out32);
 int qvm_n_local(const qvm_t* q);

@@ -111,6 +111,11 @@ struct qvm_state {
     LaunchRec rec;                    // scratch: the group being built / launched (reused across launches)
     qvm_plan* recording = nullptr;    // non-null between qvm_record_begin and qvm_record_end
     int jit_policy = 1;               // 0 never, 1 compile a group structure at its second sighting, 2 at once
+    // pacing (launch_rec): events after the last two gate passes, so a launch whose kernel is still compiling can wait
+    // for it exactly as long as the GPU has earlier passes queued
+    cudaEvent_t pace_ev[2] = {nullptr, nullptr};
+    uint64_t pace_n = 0;
+    bool capturing = false;
 };
 
 namespace {
@@ -461,6 +466,40 @@ bool fold_reset_enabled() {
     return on;
 }
 
+// QVM_B200_PATIENT=0: never wait for a kernel that is still compiling (A/B runs)
+bool patient_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("QVM_B200_PATIENT");
+        return !e || atoi(e) != 0;
+    }();
+    return on;
+}
+
+// After a gate pass on a large shard while compilations are in flight: remember where the stream is.
+void pace_mark(qvm_state* q) {
+    if (q->n_local < 26 || q->capturing || q->jit_policy != 1 || !SpecCache::instance().busy()) return;
+    cudaEvent_t& ev = q->pace_ev[q->pace_n & 1];
+    if (!ev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+        ev = nullptr;
+        cudaGetLastError();
+        return;
+    }
+    if (cudaEventRecord(ev, q->stream) == cudaSuccess) ++q->pace_n;
+    else cudaGetLastError();
+}
+
+// true while the pass before the last one is still unfinished, i.e. the GPU has a whole pass queued behind the one
+// it is running: a launch may wait for its kernel without the device ever going idle
+bool pace_backlog(qvm_state* q) {
+    if (q->pace_n < 2) return false;
+    cudaEvent_t ev = q->pace_ev[q->pace_n & 1];       // the older of the two
+    if (!ev) return false;
+    const cudaError_t e = cudaEventQuery(ev);
+    if (e == cudaErrorNotReady) return true;
+    if (e != cudaSuccess) cudaGetLastError();
+    return false;
+}
+
 // A pushing pass walks its tiles with the victim bits as the FASTEST-varying bits of the tile index (the runs of
 // non-tile positions the block index is deposited into are launch parameters): consecutive CTAs then store to
 // different destinations in turn, so the NVLink stores are spread over the whole kernel instead of all local
@@ -538,6 +577,20 @@ int launch_rec(qvm_state* q, LaunchRec& rec, const PushSpec* push = nullptr, boo
         // large states compile a structure at its first sighting (an interpreted pass there costs more than waiting
         // for a second call is worth); small ones at the second, so one-off programs do not keep NVRTC busy
         if (!rec.cs) rec.cs = SpecCache::instance().get(rec.spec.src, q->jit_policy, q->device, q->n_local >= 26);
+        if (!rec.cs && q->n_local >= 26 && q->jit_policy == 1 && !q->capturing && patient_enabled()) {
+            // The kernel of this structure is being compiled (ahead-of-time walk of the program, or queued just now).
+            // The launches before this one are still on the stream: waiting costs no device time until the pass
+            // before this one is the only work left, and a specialised pass is ~half an interpreted one.
+            SpecCache& sc = SpecCache::instance();
+            bool waited = false;
+            while (sc.on_its_way(rec.spec.src) && pace_backlog(q)) {
+                waited = true;
+                usleep(200);
+            }
+            if (waited || !sc.on_its_way(rec.spec.src))
+                rec.cs = sc.get(rec.spec.src, q->jit_policy, q->device, true);
+            q->stats.paced_waits += waited ? 1 : 0;
+        }
         q->stats.jit_compiles = (uint64_t)SpecCache::instance().compiles();
         if (const CompiledSpec* cs = rec.cs) {
             const SpecSource& ss = rec.spec;
@@ -568,6 +621,7 @@ int launch_rec(qvm_state* q, LaunchRec& rec, const PushSpec* push = nullptr, boo
             q->stats.zero_fused_launches += from_zero ? 1 : 0;
             q->stats.h2d_bytes += ss.factors.size() * sizeof(double);
             q->stats.regtile_rounds += (uint64_t)g.rounds.size();
+            pace_mark(q);
             return QVM_OK;
         }
     }
@@ -632,6 +686,7 @@ int launch_rec(qvm_state* q, LaunchRec& rec, const PushSpec* push = nullptr, boo
     q->stats.zero_fused_launches += from_zero ? 1 : 0;
     q->stats.h2d_bytes += total_bytes;
     q->stats.regtile_rounds += (uint64_t)g.rounds.size();
+    pace_mark(q);
     return QVM_OK;
 }
 
@@ -774,6 +829,8 @@ int qvm_destroy(qvm_t* q) {
     if (q->stream) cudaStreamSynchronize(q->stream);
     if (q->amps && q->owns_amps) cudaFree(q->amps);
     if (q->alt) cudaFree(q->alt);
+    for (cudaEvent_t ev : q->pace_ev)
+        if (ev) cudaEventDestroy(ev);
     if (q->ring_host) cudaFreeHost(q->ring_host);
     if (q->ring_dev) cudaFree(q->ring_dev);
     if (q->partials) cudaFree(q->partials);
@@ -860,6 +917,11 @@ int qvm_spec_precompile(int n_local, int n_global, uint64_t shard_index, int n_t
 int qvm_jit_counters(uint64_t* out4) {
     if (!out4) return fail(QVM_ERR_INVALID, "null pointer");
     SpecCache::instance().counters(out4);
+    return QVM_OK;
+}
+
+int qvm_jit_defer(int n) {
+    SpecCache::instance().defer_next(n);
     return QVM_OK;
 }
 
@@ -1211,7 +1273,9 @@ int qvm_plan_run(qvm_t* q, qvm_plan_t* plan, int reset_first) {
         bool ok = cudaStreamBeginCapture(q->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
         if (ok) {
             bool all = false;
+            q->capturing = true;
             const int rc = plan_launch_all(q, plan, reset_first, &all);
+            q->capturing = false;
             ok = cudaStreamEndCapture(q->stream, &graph) == cudaSuccess && rc == QVM_OK && all && graph;
         }
         if (ok) ok = cudaGraphInstantiate(&plan->graph, graph, 0) == cudaSuccess;

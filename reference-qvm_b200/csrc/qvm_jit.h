@@ -454,6 +454,24 @@ public:
         cv_.notify_one();
         return nullptr;
     }
+    // A compilation of this source is queued or running: its kernel will be loadable soon.  launch_rec() waits for it
+    // as long as the GPU still has earlier passes queued (a wait that costs no device time).
+    bool on_its_way(const std::string& src) {
+        std::lock_guard<std::mutex> lock(mu_);
+        if (stopping_) return false;
+        auto it = cache_.find(src);
+        if (it != cache_.end()) return it->second->state == PENDING;
+        const std::string path = disk_path(src);
+        return !path.empty() && aot_queued_.count(path) && access(path.c_str(), R_OK) != 0;
+    }
+    bool busy() {
+        std::lock_guard<std::mutex> lock(mu_);
+        return outstanding_ > 0;
+    }
+    void defer_next(int n) {
+        std::lock_guard<std::mutex> lock(mu_);
+        defer_next_ = n > 0 ? n : 0;
+    }
     void wait_idle() {
         std::unique_lock<std::mutex> lock(mu_);
         idle_cv_.wait(lock, [&] { return outstanding_ == 0; });
@@ -463,11 +481,13 @@ public:
     void shutdown() {
         std::unique_lock<std::mutex> lock(mu_);
         stopping_ = true;
-        for (Job& job : jobs_) {
-            if (job.entry) job.entry->state = FAILED;
-            --outstanding_;
+        for (std::deque<Job>* jobs : {&jobs_, &late_jobs_}) {
+            for (Job& job : *jobs) {
+                if (job.entry) job.entry->state = FAILED;
+                --outstanding_;
+            }
+            jobs->clear();
         }
-        jobs_.clear();
         idle_cv_.wait(lock, [&] { return outstanding_ == 0; });
     }
     int compiles() {
@@ -497,7 +517,9 @@ public:
         return write_cubin(path, cubin);
     }
     // the same on the background threads (qvm_jit_wait() drains them): ahead-of-time builds of whole programs
-    bool precompile_async(const std::string& src, std::string* err) {
+    // `late`: behind every job queued the normal way (the first passes of a run that is about to start: they will have
+    // gone through the interpreter before any compilation can finish, so the later passes' kernels come first)
+    bool precompile_async(const std::string& src, std::string* err, bool late = false) {
         const std::string path = disk_path(src);
         if (path.empty()) {
             if (err) *err = "the disk cache is disabled or not writable";
@@ -507,7 +529,12 @@ public:
         std::unique_lock<std::mutex> lock(mu_);
         if (stopping_) return false;
         if (!aot_queued_.insert(path).second) return true;          // already on its way
-        jobs_.push_back(Job{src, nullptr, -1});
+        if (defer_next_ > 0) {
+            --defer_next_;
+            late = true;
+        }
+        (late ? late_jobs_ : jobs_).push_back(Job{src, nullptr, -1});
+        ++compiles_;
         ++outstanding_;
         start_workers();
         cv_.notify_one();
@@ -597,15 +624,19 @@ private:
             Job job;
             {
                 std::unique_lock<std::mutex> lock(mu_);
-                cv_.wait(lock, [&] { return !jobs_.empty(); });      // (never returns once shutdown() emptied the queue)
-                job = std::move(jobs_.front());
-                jobs_.pop_front();
+                cv_.wait(lock, [&] { return !jobs_.empty() || !late_jobs_.empty(); });      // (never returns once shutdown() emptied the queues)
+                std::deque<Job>& from = jobs_.empty() ? late_jobs_ : jobs_;
+                job = std::move(from.front());
+                from.pop_front();
             }
             if (!job.entry) {                     // ahead-of-time: source -> cubin on disk, no device involved
                 std::string err;
                 const bool ok = precompile(job.src, &err);
                 std::lock_guard<std::mutex> lock(mu_);
-                if (!ok) last_error_ = err;
+                if (!ok) {
+                    last_error_ = err;
+                    aot_queued_.erase(disk_path(job.src));        // nobody should wait for this cubin
+                }
                 if (--outstanding_ == 0) idle_cv_.notify_all();
                 continue;
             }
@@ -776,7 +807,8 @@ private:
     std::condition_variable cv_, idle_cv_;
     std::unordered_map<std::string, std::unique_ptr<Entry>> cache_;
     std::unordered_map<size_t, int> seen_;
-    std::deque<Job> jobs_;
+    std::deque<Job> jobs_, late_jobs_;
+    int defer_next_ = 0;
     std::unordered_set<std::string> aot_queued_;      // disk paths of ahead-of-time jobs already queued
     int outstanding_ = 0, compiles_ = 0;
     bool workers_started_ = false, stopping_ = false;

@@ -324,6 +324,7 @@ class Engine(object):
     #: host (~0.1 s for 1300 gates); skipped when the identity layout is not where the flush starts.
     AHEAD_MIN_QUBITS = int(os.environ.get("QVM_B200_AHEAD_MIN_QUBITS", "29"))
     AHEAD_MIN_OPS = 300
+    AHEAD_COMPILE_S = float(os.environ.get("QVM_B200_AHEAD_COMPILE_S", "0.6"))
 
     def _compile_ahead(self, ops):
         if (self.n < self.AHEAD_MIN_QUBITS or len(ops) < self.AHEAD_MIN_OPS or not self.relabel
@@ -340,7 +341,15 @@ class Engine(object):
             from referenceqvm import precompile
             if os.environ.get("QVM_B200_JIT", "1") != "1" or not nat.jit_cache_dir():
                 return
-            precompile.walk_pending(ops, self.n, self.tile_bits, self.low_bits, wait=False)
+            # the run starts right behind this walk: its first passes will have gone through the interpreter (about
+            # 2^n * 32 B at ~2.7 TB/s each) before the first compilation (~0.6 s) can land, so their kernels are
+            # compiled last and the later passes' first -- launches wait for a kernel that is on its way for as long
+            # as the GPU has earlier passes queued (qvm_capi.cu, launch_rec)
+            nat.jit_defer(int(self.AHEAD_COMPILE_S / (2.0 ** self.n * 32.0 / 2.7e12)))
+            try:
+                precompile.walk_pending(ops, self.n, self.tile_bits, self.low_bits, wait=False)
+            finally:
+                nat.jit_defer(0)
         except Exception:            # an optimisation only: the run itself reports real errors
             pass
 

@@ -36,7 +36,7 @@ class Stats(C.Structure):
     """``qvm_stats_t``"""
     _fields_ = [(name, C.c_uint64) for name in
                 ("kernel_launches", "gate_ops", "hbm_passes", "hbm_bytes", "h2d_bytes", "d2h_bytes", "regtile_rounds",
-                 "jit_launches", "jit_compiles", "push_launches", "fused_push_launches", "graph_launches", "zero_fused_launches")]
+                 "jit_launches", "jit_compiles", "push_launches", "fused_push_launches", "graph_launches", "zero_fused_launches", "paced_waits")]
 
     def as_dict(self):
         return {name: int(getattr(self, name)) for name, _ in self._fields_}
@@ -63,6 +63,7 @@ _SIGNATURES = {
                                       _P, _P]),
     "qvm_jit_counters": (C.c_int, [_P]),
     "qvm_jit_cache_dir": (C.c_int, [C.c_char_p, C.c_uint64]),
+    "qvm_jit_defer": (C.c_int, [C.c_int]),
     "qvm_debug_opcode_hist": (C.c_int, [_P, _P]),
     "qvm_n_local": (C.c_int, [_P]),
     "qvm_device_ptr": (_P, [_P]),
@@ -247,6 +248,11 @@ def jit_counters():
     out = (C.c_uint64 * 4)()
     check(lib().qvm_jit_counters(C.cast(out, _P)))
     return {"nvrtc_compiles": int(out[0]), "disk_hits": int(out[1]), "disk_stores": int(out[2]), "ready": int(out[3])}
+
+
+def jit_defer(n):
+    """The next ``n`` ahead-of-time submissions are compiled after everything queued the normal way."""
+    check(lib().qvm_jit_defer(int(n)))
 
 
 def jit_cache_dir():

@@ -60,20 +60,56 @@ def _thaw_rows():
         gc.unfreeze()
 
 
-def _rows_to_lists(matrix):
-    """``matrix.tolist()`` (the reference's return type: one Python list per trial) without paying the cyclic
-    garbage collector for it.  A million row lists are a million tracked containers: built with the collector
-    running, the generational collections they trigger cost a third of the conversion; built with it paused, the
-    first allocation after it is switched back on starts a full collection that walks all of them (0.15 s per
-    million rows on the GPU box, charged to whoever allocates next).  Rows cannot be part of a cycle, so for large
-    results the collector is told to leave them alone: ``gc.freeze()`` moves everything allocated so far to the
-    permanent generation -- until the next call into the QVM, which thaws (``gc.unfreeze()``) whatever is still
-    alive.  ``QVM_B200_GC_FREEZE=0`` turns this off."""
+_pyrows = [None]
+
+
+def _pyrows_lib():
+    """referenceqvm/_pyrows.so (csrc/qvm_pyrows.c, built by build.py): fills the per-trial lists in C."""
+    if _pyrows[0] is None:
+        import ctypes
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_pyrows.so")
+        try:
+            lib = ctypes.PyDLL(path)
+            lib.qvm_rows_from_indices.restype = ctypes.py_object
+            lib.qvm_rows_from_indices.argtypes = [ctypes.c_void_p, ctypes.c_ssize_t, ctypes.c_void_p, ctypes.c_ssize_t]
+            lib.qvm_rows_from_int64.restype = ctypes.py_object
+            lib.qvm_rows_from_int64.argtypes = [ctypes.c_void_p] + [ctypes.c_ssize_t] * 4
+            _pyrows[0] = lib
+        except (OSError, AttributeError):
+            _pyrows[0] = False           # host-side formatting only: numpy's tolist() does the same, slower
+    return _pyrows[0]
+
+
+def _rows_to_lists(matrix=None, indices=None, sel=None):
+    """One Python list per trial (the reference's return type) from an integer matrix, or directly from sampled
+    basis-state ``indices`` and the bit position ``sel[c]`` each output column reads (outside 0..63: always 0) --
+    without paying the cyclic garbage collector for it.  A million row lists are a million tracked containers:
+    built with the collector running, the generational collections they trigger cost a third of the conversion;
+    built with it paused, the first allocation after it is switched back on starts a full collection that walks
+    all of them (0.15 s per million rows on the GPU box, charged to whoever allocates next).  Rows cannot be part
+    of a cycle, so for large results the collector is told to leave them alone: ``gc.freeze()`` moves everything
+    allocated so far to the permanent generation -- until the next call into the QVM, which thaws
+    (``gc.unfreeze()``) whatever is still alive.  ``QVM_B200_GC_FREEZE=0`` turns this off."""
     _thaw_rows()
     was_enabled = gc.isenabled()
     gc.disable()
     try:
-        out = matrix.tolist()
+        lib = _pyrows_lib()
+        if indices is not None:
+            idx = np.ascontiguousarray(indices, dtype=np.uint64)
+            if lib:
+                cols = np.ascontiguousarray(sel, dtype=np.int32)
+                out = lib.qvm_rows_from_indices(idx.ctypes.data, idx.shape[0], cols.ctypes.data, cols.shape[0])
+            else:
+                picked = np.take(_index_bits(idx, 63), [c if 0 <= c < 64 else 0 for c in sel], axis=1)
+                picked[:, [i for i, c in enumerate(sel) if not 0 <= c < 64]] = 0
+                out = picked.tolist()
+        else:
+            m = np.asarray(matrix, dtype=np.int64)
+            if lib and m.ndim == 2:
+                out = lib.qvm_rows_from_int64(m.ctypes.data, m.shape[0], m.shape[1], m.strides[0], m.strides[1])
+            else:
+                out = m.tolist()
         if _GC_FREEZE and was_enabled and len(out) >= 100000:
             gc.freeze()
             _frozen_rows[0] = True
@@ -677,11 +713,9 @@ class QVM_Wavefunction(QAM):
             t2b = time.perf_counter()
             indices, _ = self._engine.sample(uniforms, physical=True)
             t3 = time.perf_counter()
-            bits = _index_bits(indices, self.num_qubits)
-            # column num_qubits is never set: it stands in for qubits beyond the register
-            sel = [self._engine.position(self._virt[q]) if 0 <= q < self.num_qubits else self.num_qubits
-                   for q in qubits]
-            out = _rows_to_lists(np.take(bits, sel, axis=1))
+            # physical bit position each requested qubit reads; -1 (always 0) for qubits beyond the register
+            sel = [self._engine.position(self._virt[q]) if 0 <= q < self.num_qubits else -1 for q in qubits]
+            out = _rows_to_lists(indices=indices, sel=sel)
             #: where the last call's wall time went (bench.py reports it as e2e.breakdown)
             self.last_timing = {"program_walk_s": t1 - t0, "plan_launch_sync_s": t2 - t1, "host_uniforms_s": t2b - t2,
                                 "cdf_and_draws_s": t3 - t2b,

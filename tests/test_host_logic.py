@@ -242,3 +242,23 @@ def test_batchable_decision():
     wide = Program(H(QVM_Wavefunction.BATCH_MAX_QUBITS), MEASURE(0, 0), H(0))
     assert not qvm._batchable(wide)                  # one block per trial: segments above 2^20 amplitudes keep the loop
     assert not qvm._batchable(Program())
+
+
+def test_result_rows_helper_matches_numpy(monkeypatch):
+    """csrc/qvm_pyrows.c (per-trial result lists built in C) against the numpy path it replaces."""
+    from referenceqvm import qvm_wavefunction as qw
+    assert qw._pyrows_lib(), "referenceqvm/_pyrows.so is built by build.py"
+    rng = np.random.default_rng(5)
+    idx = rng.integers(0, 2 ** 63, size=1000, dtype=np.uint64)
+    idx[:4] = [0, 1, 2 ** 63, 2 ** 64 - 1]
+    sel = [0, 5, 63, -1, 33, 64, 5]
+    fast = qw._rows_to_lists(indices=idx, sel=sel)
+    mat = rng.integers(-2 ** 62, 2 ** 62, size=(50, 12), dtype=np.int64)
+    mat[:, ::2] = rng.integers(0, 2, size=(50, 6))
+    fast_m = qw._rows_to_lists(mat[::2, ::-1])
+    monkeypatch.setattr(qw, "_pyrows", [False])
+    slow = qw._rows_to_lists(indices=idx, sel=sel)
+    assert fast == slow and all(type(v) is int for v in fast[3])
+    assert fast[3] == [1, 1, 1, 0, 1, 0, 1] and fast[0] == [0] * 7
+    assert fast_m == mat[::2, ::-1].tolist() == qw._rows_to_lists(mat[::2, ::-1])
+    assert qw._rows_to_lists(np.zeros((0, 3), dtype=np.int64)) == []

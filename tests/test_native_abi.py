@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(nat.Op) == 4 + 4 + 4 * 6 + 8 + 4 + 4
-    assert ctypes.sizeof(nat.Stats) == 13 * 8
+    assert ctypes.sizeof(nat.Stats) == 14 * 8
 
 
 def test_no_cpu_fallback_without_device():
