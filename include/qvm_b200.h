@@ -126,6 +126,11 @@ int qvm_jit_cache_dir(char* out, uint64_t cap);
  * of a run that starts right away go through the interpreter before any compilation could finish, so the kernels
  * of the later passes should come first. */
 int qvm_jit_defer(int n);
+/* Several processes of one node (one per GPU) walking the same program share the disk cache: of the calling thread's
+ * following qvm_spec_precompile submissions, number i is compiled here only when i % stride == offset; the others are
+ * expected from the process with that offset (launches wait for their cubins like for locally queued ones, and a
+ * cubin that has not appeared after 20 s is compiled locally after all).  (1, 0) = everything here (the default). */
+int qvm_jit_share(int stride, int offset);
 /* Debug: how many ops of each register-tile opcode were encoded so far (32 counters). */
 int qvm_debug_opcode_hist(qvm_t* q, uint64_t* out32);
 int qvm_n_local(const qvm_t* q);
@@ -219,6 +224,10 @@ int qvm_measure(qvm_t* q, int qubit, double r, int* outcome, double* p0);
  * `lane`.  The caller replays the reference's sequential decisions on it -- p0 of each measured qubit given
  * the outcomes so far, one uniform each, outcome 0 iff r < p0, scale 1/sqrt(p0) or 1/sqrt(1 - p0) -- and
  * passes the combined projection to the next call (n_high = 0, hist = NULL for a final collapse only).
+ * do_collapse = 2 ("filter"): nothing is written; the histogram is taken over the amplitudes with
+ * (index & keep_mask) == keep_value only, times scale^2 -- only those amplitudes are read, so after the first
+ * chunk of a run has fixed ten or so bits the following chunks cost next to nothing and the run ends with ONE
+ * collapse call (which, when every local position was measured, is a write-only clear + one amplitude).
  * Summation order is fixed: results are deterministic to the last bit.  On a shard the positions are
  * local and the histogram covers the shard; the caller gathers the shards' histograms (a measured global
  * position is the same bit for a whole shard) and hands every shard its own projection. */

@@ -894,6 +894,15 @@ int qvm_spec_compile_check(int n_local, int n_global, uint64_t shard_index, int 
     return QVM_OK;
 }
 
+namespace {
+// qvm_jit_share: which of this thread's ahead-of-time submissions are compiled here
+struct ShareState {
+    int stride = 1, offset = 0;
+    uint64_t index = 0;
+};
+thread_local ShareState t_share;
+}  // namespace
+
 int qvm_spec_precompile(int n_local, int n_global, uint64_t shard_index, int n_tile, const int32_t* tile_bits, int n_ops,
                         const qvm_op_t* ops, const double* mats, uint64_t mats_entries, int n_low, int n_bring,
                         const int32_t* bring_low, int32_t* new_pos) {
@@ -909,7 +918,8 @@ int qvm_spec_precompile(int n_local, int n_global, uint64_t shard_index, int n_t
     for (int j = 0; j < n_tile; ++j) new_pos[j] = tile_bits[erc == ENC_OK ? g.sigma[j] : j];
     if (erc != ENC_OK || (g.cold.empty() && !g.relabelled) || g.need_full || !generate_spec(g, ss)) return 1;
     std::string err;      // compiled on the background threads: qvm_jit_wait() returns when all cubins are on disk
-    if (!SpecCache::instance().precompile_async(ss.src, &err))
+    const bool foreign = t_share.stride > 1 && (t_share.index++ % t_share.stride) != t_share.offset;
+    if (!SpecCache::instance().precompile_async(ss.src, &err, false, foreign))
         return fail(QVM_ERR_UNSUPPORTED, "ahead-of-time compile failed: %.300s", err.c_str());
     return QVM_OK;
 }
@@ -917,6 +927,14 @@ int qvm_spec_precompile(int n_local, int n_global, uint64_t shard_index, int n_t
 int qvm_jit_counters(uint64_t* out4) {
     if (!out4) return fail(QVM_ERR_INVALID, "null pointer");
     SpecCache::instance().counters(out4);
+    return QVM_OK;
+}
+
+int qvm_jit_share(int stride, int offset) {
+    if (stride < 1 || offset < 0 || offset >= stride) return fail(QVM_ERR_INVALID, "bad share %d/%d", offset, stride);
+    t_share.stride = stride;
+    t_share.offset = offset;
+    t_share.index = 0;
     return QVM_OK;
 }
 
@@ -1361,16 +1379,61 @@ int qvm_measure_hist(qvm_t* q, int n_high, const int32_t* high_pos, int do_colla
         hb.pos[i] = (uint8_t)high_pos[i];
     }
     if (keep_value & ~keep_mask) return fail(QVM_ERR_INVALID, "collapse value outside its mask");
+    if (do_collapse < 0 || do_collapse > 2) return fail(QVM_ERR_INVALID, "do_collapse is 0, 1 or 2");
+    const uint64_t all_local = q->n_elems - 1;
+    if (keep_mask & ~all_local) return fail(QVM_ERR_INVALID, "collapse mask outside the shard");
+    if (do_collapse == 2 && !hist) return fail(QVM_ERR_INVALID, "filter mode returns a histogram");
     const int n_entries = 32 << n_high;
-    const uint64_t n_chunks = q->n_elems >> 5;
-    int grid = (int)std::min<uint64_t>((n_chunks + (kHistThreads / 32) - 1) / (kHistThreads / 32), (uint64_t)q->sm_count * 8);
+    // final collapse of a run that measured every local position: one survivor, write-only
+    if (do_collapse == 1 && !hist && keep_mask == all_local && q->n_elems > 1) {
+        double2* keep = reinterpret_cast<double2*>(q->result_dev);
+        if (scale != 0.0) survivor_fetch_kernel<<<1, 1, 0, q->stream>>>(q->amps, keep_value, scale, keep);
+        QVM_CUDA(q, cudaGetLastError());
+        QVM_CUDA(q, cudaMemsetAsync(q->amps, 0, q->n_elems * sizeof(double2), q->stream));
+        if (scale != 0.0) survivor_store_kernel<<<1, 1, 0, q->stream>>>(q->amps, keep_value, keep);
+        QVM_CUDA(q, cudaGetLastError());
+        q->sample_mode = -1;
+        q->stats.kernel_launches += scale != 0.0 ? 2 : 0;
+        q->stats.hbm_bytes += 16ull * q->n_elems;
+        return QVM_OK;
+    }
+    if (do_collapse == 2 && scale == 0.0) {          // (a shard whose global bits lost: nothing consistent here)
+        memset(hist, 0, n_entries * sizeof(double));
+        return QVM_OK;
+    }
+    const bool filter = do_collapse == 2 && keep_mask != 0;
+    FilterBits fb{};
+    int n_free = q->n_local;
+    if (filter) {
+        n_free = 0;
+        for (int b = 0; b < q->n_local;) {
+            if ((keep_mask >> b) & 1ull) {
+                ++b;
+                continue;
+            }
+            int e = b;
+            while (e < q->n_local && !((keep_mask >> e) & 1ull)) ++e;
+            if (fb.n_runs == 20) return fail(QVM_ERR_UNSUPPORTED, "collapse mask too fragmented for the filtered histogram");
+            fb.start[fb.n_runs] = (uint8_t)b;
+            fb.len[fb.n_runs] = (uint8_t)(e - b);
+            ++fb.n_runs;
+            n_free += e - b;
+            b = e;
+        }
+    }
+    const uint64_t n_items = filter ? (((1ull << n_free) + kHistThreads - 1) / kHistThreads)
+                                    : (((q->n_elems >> 5) + (kHistThreads / 32) - 1) / (kHistThreads / 32));
+    int grid = (int)std::min<uint64_t>(n_items, (uint64_t)q->sm_count * 8);
     if (grid < 1) grid = 1;
     double* dev = nullptr;
     QVM_CUDA(q, cudaMallocAsync(&dev, ((size_t)grid + 1) * n_entries * sizeof(double), q->stream));
     double* d_hist = dev + (size_t)grid * n_entries;
     int rc = QVM_OK;
-    measure_hist_kernel<<<grid, kHistThreads, 0, q->stream>>>(q->amps, q->n_elems, hb, do_collapse ? 1 : 0, keep_mask,
-                                                              keep_value, scale, dev);
+    if (filter)
+        measure_hist_filter_kernel<<<grid, kHistThreads, 0, q->stream>>>(q->amps, n_free, hb, fb, keep_value, dev);
+    else
+        measure_hist_kernel<<<grid, kHistThreads, 0, q->stream>>>(q->amps, q->n_elems, hb, do_collapse == 1 ? 1 : 0, keep_mask,
+                                                                  keep_value, scale, dev);
     if (cudaGetLastError() != cudaSuccess) rc = fail(QVM_ERR_CUDA, "measure_hist_kernel launch failed");
     if (rc == QVM_OK && hist) {
         measure_hist_final_kernel<<<(n_entries + 255) / 256, 256, 0, q->stream>>>(dev, grid, n_entries, d_hist);
@@ -1379,15 +1442,19 @@ int qvm_measure_hist(qvm_t* q, int n_high, const int32_t* high_pos, int do_colla
             cudaMemcpyAsync(host.data(), d_hist, n_entries * sizeof(double), cudaMemcpyDeviceToHost, q->stream) != cudaSuccess ||
             cudaStreamSynchronize(q->stream) != cudaSuccess)
             rc = fail(QVM_ERR_CUDA, "histogram readback failed");
-        else memcpy(hist, host.data(), n_entries * sizeof(double));
+        else {
+            memcpy(hist, host.data(), n_entries * sizeof(double));
+            if (do_collapse == 2)                    // the projection is not applied yet: scale the probabilities instead
+                for (int j = 0; j < n_entries; ++j) hist[j] *= scale * scale;
+        }
         q->stats.kernel_launches += 1;
         q->stats.d2h_bytes += n_entries * sizeof(double);
     }
     cudaFreeAsync(dev, q->stream);
     if (rc != QVM_OK) return rc;
-    q->sample_mode = -1;
+    if (do_collapse == 1) q->sample_mode = -1;
     q->stats.kernel_launches += 1;
-    q->stats.hbm_bytes += (do_collapse ? 32ull : 16ull) * q->n_elems;
+    q->stats.hbm_bytes += filter ? (16ull << n_free) : (do_collapse == 1 ? 32ull : 16ull) * q->n_elems;
     return QVM_OK;
 }
 

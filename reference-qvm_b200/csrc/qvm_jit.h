@@ -15,6 +15,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -434,6 +435,13 @@ public:
         }
         // an ahead-of-time job for this very source is on its way (precompile_async): its cubin will be on disk soon
         if (!path.empty() && policy < 2 && aot_queued_.count(path)) return nullptr;
+        if (!path.empty() && policy < 2) {
+            auto f = foreign_.find(path);
+            if (f != foreign_.end()) {
+                if (now_s() < f->second) return nullptr;
+                foreign_.erase(f);
+            }
+        }
         if (seen_.size() > (1u << 20)) seen_.clear();
         if (policy < 2 && ++seen_[std::hash<std::string>()(src)] < (eager ? 1 : 2)) return nullptr;
         Entry* e = new Entry();
@@ -462,7 +470,13 @@ public:
         auto it = cache_.find(src);
         if (it != cache_.end()) return it->second->state == PENDING;
         const std::string path = disk_path(src);
-        return !path.empty() && aot_queued_.count(path) && access(path.c_str(), R_OK) != 0;
+        if (path.empty() || access(path.c_str(), R_OK) == 0) return false;
+        if (aot_queued_.count(path)) return true;
+        auto f = foreign_.find(path);
+        if (f == foreign_.end()) return false;
+        if (now_s() < f->second) return true;
+        foreign_.erase(f);                 // the other process did not deliver
+        return false;
     }
     bool busy() {
         std::lock_guard<std::mutex> lock(mu_);
@@ -518,8 +532,11 @@ public:
     }
     // the same on the background threads (qvm_jit_wait() drains them): ahead-of-time builds of whole programs
     // `late`: behind every job queued the normal way (the first passes of a run that is about to start: they will have
-    // gone through the interpreter before any compilation can finish, so the later passes' kernels come first)
-    bool precompile_async(const std::string& src, std::string* err, bool late = false) {
+    // gone through the interpreter before any compilation can finish, so the later passes' kernels come first).
+    // `foreign`: another process sharing the disk cache compiles this one (ranks of one node split a program's
+    // structures between them); here the cubin is only expected -- for kForeignPatienceS seconds, after which the
+    // structure is compiled locally like any other.
+    bool precompile_async(const std::string& src, std::string* err, bool late = false, bool foreign = false) {
         const std::string path = disk_path(src);
         if (path.empty()) {
             if (err) *err = "the disk cache is disabled or not writable";
@@ -528,6 +545,11 @@ public:
         if (access(path.c_str(), R_OK) == 0) return true;
         std::unique_lock<std::mutex> lock(mu_);
         if (stopping_) return false;
+        if (foreign) {
+            if (!aot_queued_.count(path)) foreign_[path] = now_s() + kForeignPatienceS;
+            return true;
+        }
+        foreign_.erase(path);
         if (!aot_queued_.insert(path).second) return true;          // already on its way
         if (defer_next_ > 0) {
             --defer_next_;
@@ -809,6 +831,11 @@ private:
     std::unordered_map<size_t, int> seen_;
     std::deque<Job> jobs_, late_jobs_;
     int defer_next_ = 0;
+    static constexpr double kForeignPatienceS = 20.0;
+    std::unordered_map<std::string, double> foreign_;       // cubin path -> until when another process is trusted with it
+    static double now_s() {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    }
     std::unordered_set<std::string> aot_queued_;      // disk paths of ahead-of-time jobs already queued
     int outstanding_ = 0, compiles_ = 0;
     bool workers_started_ = false, stopping_ = false;

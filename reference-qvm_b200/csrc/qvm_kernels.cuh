@@ -465,6 +465,60 @@ measure_hist_kernel(double2* __restrict__ state, uint64_t n_elems, const HistBit
         partials[(size_t)blockIdx.x * (n_bins * 32) + j] = t;
     }
 }
+// The same histogram over the amplitudes CONSISTENT with earlier outcomes only -- (x & keep_mask) == keep_value -- and
+// without writing anything: after the first chunk of a MEASURE run has fixed ten or so bits, the following chunks read
+// a thousandth of the state instead of rewriting all of it, and the run ends with ONE collapse pass.  Thread g walks
+// the compact indices c = g, g + T, ... of the free positions (T a multiple of 32, so the bits of c that land on free
+// positions among the 5 lowest stay the same for a thread: every thread still owns one lane value, several threads
+// of a warp may share it) and deposits c into the free runs.  Fixed summation order, no atomics.
+struct FilterBits {
+    int n_runs;
+    uint8_t start[20], len[20];        // runs of free positions, ascending
+};
+__global__ void __launch_bounds__(kHistThreads)
+measure_hist_filter_kernel(const double2* __restrict__ state, int n_free, const HistBits hb, const FilterBits fb,
+                           uint64_t keep_value, double* __restrict__ partials) {
+    __shared__ double acc[kHistThreads / 32][32][32];
+    __shared__ int lane_of[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_bins = 1 << hb.n_high;
+    for (int b = 0; b < n_bins; ++b) acc[warp][b][lane] = 0.0;
+    auto deposit = [&](uint64_t c) {
+        uint64_t x = keep_value;
+        for (int r = 0; r < fb.n_runs; ++r) {
+            x |= (c & ((1ull << fb.len[r]) - 1ull)) << fb.start[r];
+            c >>= fb.len[r];
+        }
+        return x;
+    };
+    if (threadIdx.x < 32) lane_of[threadIdx.x] = (int)(deposit((uint64_t)threadIdx.x) & 31ull);
+    const uint64_t n = 1ull << n_free;
+    const uint64_t threads_total = (uint64_t)gridDim.x * kHistThreads;
+    for (uint64_t c = (uint64_t)blockIdx.x * kHistThreads + threadIdx.x; c < n; c += threads_total) {
+        const uint64_t x = deposit(c);
+        const double2 a = state[x];
+        int bin = 0;
+        for (int i = 0; i < hb.n_high; ++i) bin |= (int)((x >> hb.pos[i]) & 1ull) << i;
+        acc[warp][bin][lane] += a.x * a.x + a.y * a.y;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n_bins * 32; j += kHistThreads) {
+        double t = 0.0;
+        for (int w = 0; w < kHistThreads / 32; ++w)
+            for (int l = 0; l < 32; ++l)
+                if (lane_of[l] == (j & 31)) t += acc[w][j >> 5][l];
+        partials[(size_t)blockIdx.x * (n_bins * 32) + j] = t;
+    }
+}
+// The run measured EVERY local position: one amplitude survives.  keep[0] = state[x0] * scale, then the shard is
+// cleared (memset) and the survivor written back -- a write-only pass instead of read + write.
+__global__ void survivor_fetch_kernel(const double2* __restrict__ state, uint64_t x0, double scale, double2* __restrict__ keep) {
+    const double2 a = state[x0];
+    keep[0] = make_double2(a.x * scale, a.y * scale);
+}
+__global__ void survivor_store_kernel(double2* __restrict__ state, uint64_t x0, const double2* __restrict__ keep) {
+    state[x0] = keep[0];
+}
 // hist[j] = sum over blocks of partials[block][j], blocks in ascending order
 __global__ void measure_hist_final_kernel(const double* __restrict__ partials, int n_blocks, int n_entries,
                                           double* __restrict__ hist) {

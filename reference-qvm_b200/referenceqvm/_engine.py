@@ -430,7 +430,10 @@ class Engine(object):
         positions = [self.pos_of[q] for q in qubits]
         lanes = np.arange(32)[None, :]
         results = []
+        # the projection so far: applied ONCE, after the last chunk; the chunks in between read only the amplitudes
+        # that are still consistent with it (qvm_measure_hist, filter mode)
         pending = None
+        cum_norm = 1.0
         i = 0
         while i < len(positions):
             chunk, high = [], []
@@ -441,7 +444,7 @@ class Engine(object):
                         break
                     high.append(p)
                 chunk.append(p)
-            hist = self.state.measure_hist(high, pending)
+            hist = self.state.measure_hist(high, pending, apply=False)
             bins = np.arange(1 << len(high))[:, None]
             consistent = np.ones(hist.shape, dtype=bool)
             norm_factor, mask, value = 1.0, 0, 0
@@ -455,7 +458,10 @@ class Engine(object):
                 mask |= 1 << p
                 value |= outcome << p
                 results.append((outcome, p0))
-            pending = (mask, value, float(np.sqrt(norm_factor)))
+            cum_norm *= norm_factor
+            if pending is not None:
+                mask, value = mask | pending[0], value | pending[1]
+            pending = (mask, value, float(np.sqrt(cum_norm)))
             i += len(chunk)
         self.state.measure_hist([], pending, want_hist=False)
         return results

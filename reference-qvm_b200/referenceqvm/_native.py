@@ -64,6 +64,7 @@ _SIGNATURES = {
     "qvm_jit_counters": (C.c_int, [_P]),
     "qvm_jit_cache_dir": (C.c_int, [C.c_char_p, C.c_uint64]),
     "qvm_jit_defer": (C.c_int, [C.c_int]),
+    "qvm_jit_share": (C.c_int, [C.c_int, C.c_int]),
     "qvm_debug_opcode_hist": (C.c_int, [_P, _P]),
     "qvm_n_local": (C.c_int, [_P]),
     "qvm_device_ptr": (_P, [_P]),
@@ -253,6 +254,12 @@ def jit_counters():
 def jit_defer(n):
     """The next ``n`` ahead-of-time submissions are compiled after everything queued the normal way."""
     check(lib().qvm_jit_defer(int(n)))
+
+
+def jit_share(stride, offset):
+    """Of this thread's following ahead-of-time submissions only every ``stride``-th (from ``offset``) is compiled
+    here; the others are expected in the shared disk cache from the sibling processes."""
+    check(lib().qvm_jit_share(int(stride), int(offset)))
 
 
 def jit_cache_dir():
@@ -503,14 +510,16 @@ class DeviceState(object):
         check(code)
         return outcome.value, p0.value
 
-    def measure_hist(self, high_positions, collapse=None, want_hist=True):
+    def measure_hist(self, high_positions, collapse=None, want_hist=True, apply=True):
         """One pass of a MEASURE run (``qvm_measure_hist``): optionally apply ``collapse`` = (keep_mask,
         keep_value, scale), then return hist[bin, lane] over ``high_positions`` (each >= 5, at most 5)
-        and the 5 lowest index bits."""
+        and the 5 lowest index bits.  ``apply=False``: the state is left alone and the histogram is taken over
+        the amplitudes consistent with ``collapse`` only (probabilities times scale^2) -- only those are read."""
         hp = np.ascontiguousarray(high_positions, dtype=np.int32)
         hist = np.empty((1 << hp.size, 32), dtype=np.float64) if want_hist else None
         mask, value, scale = collapse if collapse is not None else (0, 0, 1.0)
-        code = lib().qvm_measure_hist(self.handle, hp.size, hp.ctypes.data, 0 if collapse is None else 1, mask, value,
+        mode = 0 if collapse is None else (1 if apply else 2)
+        code = lib().qvm_measure_hist(self.handle, hp.size, hp.ctypes.data, mode, mask, value,
                                       float(scale), hist.ctypes.data if want_hist else None)
         if code == QVM_ERR_INVALID:
             raise ValueError(last_error())

@@ -282,8 +282,8 @@ class CudaShard(object):
     def prob_zero(self, position):
         return self.state.prob_zero(position)
 
-    def measure_hist(self, high_positions, collapse=None, want_hist=True):
-        return self.state.measure_hist(high_positions, collapse, want_hist)
+    def measure_hist(self, high_positions, collapse=None, want_hist=True, apply=True):
+        return self.state.measure_hist(high_positions, collapse, want_hist, apply)
 
     def density_diag(self, n_rho, pos_of):
         return self.state.density_diag(n_rho, pos_of)
@@ -544,6 +544,7 @@ class ShardedEngine(object):
         if not self.pending:
             return
         ops, self.pending = self.pending, []
+        self._compile_ahead(ops)
         deps = _planner.dependencies(ops)
         n = len(ops)
         done = [False] * n
@@ -598,6 +599,48 @@ class ShardedEngine(object):
                     self._push_finish(fused["pairs"], fused_pass=True)
                 else:
                     self._bring_local(wanted, ops, done)
+
+    def _compile_ahead(self, ops):
+        """First sight of a long gate stream on large shards (as ``Engine._compile_ahead``): walk the schedule
+        without a device so NVRTC builds every group's kernel on the host cores while the first passes run on the
+        interpreter; launches then wait for kernels that are on their way only while the GPU has passes queued."""
+        from referenceqvm import _engine
+        if (self.n_local < 26 or len(ops) < _engine.Engine.AHEAD_MIN_OPS or not self.relabel
+                or getattr(self.shard, "dry", False) or not hasattr(self.shard, "state")
+                or self.pos_of != list(range(self.n)) or self.exchange == "staged"
+                or os.environ.get("QVM_B200_JIT", "1") != "1"):
+            return
+        signature = hash((self.n, self.ctx.world, self.tile_bits, self.low_bits, self.exchange,
+                          tuple((o.kind, o.targets, o.ctrl_mask) for o in ops)))
+        if signature in _engine._walked_ahead:
+            return
+        if len(_engine._walked_ahead) > 4096:
+            _engine._walked_ahead.clear()
+        _engine._walked_ahead.add(signature)
+        try:
+            from referenceqvm import precompile
+            if not nat.jit_cache_dir():
+                return
+            # the processes of one node (torchrun: LOCAL_WORLD_SIZE of them) share the disk cache and walk the same
+            # schedule: each compiles every LOCAL_WORLD_SIZE-th structure and picks the others' cubins up from disk
+            stride, offset = 1, 0
+            if not getattr(self.comm, "same_process", False):
+                try:
+                    stride, offset = int(os.environ["LOCAL_WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+                except (KeyError, ValueError):
+                    stride, offset = 1, 0
+            if not 0 <= offset < stride:
+                stride, offset = 1, 0
+            nat.jit_share(stride, offset)
+            nat.jit_defer(int(_engine.Engine.AHEAD_COMPILE_S / (2.0 ** self.n_local * 32.0 / 2.7e12)) // stride)
+            try:
+                precompile.walk_sharded(ops, self.n, self.ctx.world, self.tile_bits, self.low_bits, self.exchange,
+                                        wait=False)
+            finally:
+                nat.jit_defer(0)
+                nat.jit_share(1, 0)
+        except Exception:            # an optimisation only: the run itself reports real errors
+            pass
 
     def _choose_victims(self, wanted, ops, done, avoid=()):
         """Local logical qubits to trade for the global ones in ``wanted``: those whose next dense use
@@ -897,6 +940,7 @@ class ShardedEngine(object):
         ranks = np.arange(world)[:, None, None]
         results = []
         pending = None
+        cum_norm, alive = 1.0, True
         i = 0
         while i < len(positions):
             chunk, high = [], []
@@ -907,11 +951,11 @@ class ShardedEngine(object):
                         break
                     high.append(p)
                 chunk.append(p)
-            local = self.shard.measure_hist(high, pending)
+            local = self.shard.measure_hist(high, pending, apply=False)
             hist = self.comm.allgather(local.reshape(-1)).reshape((world,) + local.shape)
             bins = np.arange(local.shape[0])[None, :, None]
             consistent = np.ones(hist.shape, dtype=bool)
-            norm_factor, mask, value, alive = 1.0, 0, 0, True
+            norm_factor, mask, value = 1.0, 0, 0
             for j, p in enumerate(chunk):
                 if p >= nl:
                     bit = (ranks >> (p - nl)) & 1
@@ -930,7 +974,12 @@ class ShardedEngine(object):
                     mask |= 1 << p
                     value |= outcome << p
                 results.append((outcome, p0))
-            pending = (mask, value, float(np.sqrt(norm_factor)) if alive else 0.0)
+            # the projection so far is applied once, after the last chunk; until then the histograms are taken over
+            # the amplitudes still consistent with it (qvm_measure_hist, filter mode: only those are read)
+            cum_norm *= norm_factor
+            if pending is not None:
+                mask, value = mask | pending[0], value | pending[1]
+            pending = (mask, value, float(np.sqrt(cum_norm)) if alive else 0.0)
             i += len(chunk)
         self.shard.measure_hist([], pending, want_hist=False)
         return results

@@ -51,6 +51,7 @@ class _DryComm(object):
 
 class _DryShard(object):
     """Plans like ``_sharded.CudaShard`` launches, compiles instead of running."""
+    dry = True
 
     def __init__(self, n_local, ctx):
         self.n_local, self.ctx = n_local, ctx
@@ -131,6 +132,20 @@ def walk_pending(pending, n_qubits, tile_bits, low_bits, wait=True):
     if wait:
         nat.jit_wait()
     return shard
+
+
+def walk_sharded(pending, n_qubits, gpus, tile_bits, low_bits, exchange, wait=True):
+    """The sharded scheduler's walk (exchange epochs, victims, fused pushes) over an already merged op list, from
+    the identity layout: what ``ShardedEngine.flush`` is about to run on every rank.  Group structures do not depend
+    on the rank (the shard index is a launch parameter), so each rank can walk for itself."""
+    ctx = _sharded.ShardContext(_DryComm(gpus), 0)
+    eng = _sharded.ShardedEngine(n_qubits, ctx, tile_bits=tile_bits, low_bits=low_bits, backend_factory=_DryShard,
+                                 exchange=exchange)
+    eng.pending = list(pending)
+    eng.flush()
+    if wait:
+        nat.jit_wait()
+    return eng.shard
 
 
 def precompile_ops(ops, n_qubits, gpus=1, tile_bits=None, low_bits=None, exchange=None):

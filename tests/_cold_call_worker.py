@@ -16,6 +16,7 @@ import numpy as np  # noqa: E402
 
 def main():
     n, depth = int(sys.argv[1]), int(sys.argv[2])
+    import referenceqvm  # noqa: F401  (puts the pyquil stand-in on sys.path when pyquil is absent)
     from pyquil.quil import Program
     from pyquil.quilbase import Gate
     from referenceqvm import _native as nat

@@ -176,12 +176,16 @@ class NumpyShard(object):
             self.psi = self.psi[idx]
         return new_pos
 
-    def measure_hist(self, high_positions, collapse=None, want_hist=True):
-        """Model of qvm_measure_hist on this shard: optional collapse, then |amp|^2 per (high-bin, lane)."""
+    def measure_hist(self, high_positions, collapse=None, want_hist=True, apply=True):
+        """Model of qvm_measure_hist on this shard: optional collapse (applied, or with ``apply=False`` only used
+        as a filter: the state is left alone), then |amp|^2 per (high-bin, lane)."""
         idx = np.arange(self.psi.size, dtype=np.int64)
+        psi = self.psi
         if collapse is not None:
             mask, value, scale = collapse
-            self.psi = np.where((idx & mask) == value, self.psi * scale, 0.0)
+            psi = np.where((idx & mask) == value, self.psi * scale, 0.0)
+            if apply:
+                self.psi = psi
         self.launches += 1
         if not want_hist:
             return None
@@ -190,7 +194,7 @@ class NumpyShard(object):
             assert 5 <= p < self.n_local
             bins |= ((idx >> p) & 1) << i
         hist = np.zeros((1 << len(high_positions), 32))
-        np.add.at(hist, (bins, idx & 31), np.abs(self.psi) ** 2)
+        np.add.at(hist, (bins, idx & 31), np.abs(psi) ** 2)
         return hist
 
     def density_diag(self, n_rho, pos_of):

@@ -589,6 +589,47 @@ def test_measure_hist_kernel_against_numpy():
     st.close()
 
 
+def test_measure_hist_filter_mode_and_single_survivor():
+    """do_collapse = 2: the histogram of the amplitudes consistent with (mask, value), times scale^2, state left
+    alone -- for masks that fix none, some or all of the five lowest bits; then the write-only collapse of a run
+    that measured every position."""
+    n = 13
+    psi = random_state(n, 77)
+    st = nat.DeviceState(n)
+    st.set_state(psi)
+    idx = np.arange(1 << n, dtype=np.int64)
+
+    def model(vec, high):
+        bins = np.zeros_like(idx)
+        for i, p in enumerate(high):
+            bins |= ((idx >> p) & 1) << i
+        hist = np.zeros((1 << len(high), 32))
+        np.add.at(hist, (bins, idx & 31), np.abs(vec) ** 2)
+        return hist
+
+    rs = np.random.RandomState(5)
+    cases = [(0, 0), ((1 << 0) | (1 << 3), 1 << 3), (31, 21), ((1 << 9) | (1 << 12), 1 << 12), (0b1010101010101, 0b1000100000001),
+             ((1 << 10) - 1, 0b1100110011), ((1 << n) - 1 - (1 << 6) - (1 << 11), 0b1001100110101 & ~((1 << 6) | (1 << 11)))]
+    for mask, value in cases:
+        free = [p for p in range(5, n) if not (mask >> p) & 1]
+        high = [int(p) for p in rs.permutation(free)[:min(5, len(free))]]
+        scale = float(rs.uniform(0.5, 3.0))
+        got = st.measure_hist(high, (mask, value, scale), apply=False)
+        want = model(np.where((idx & mask) == value, psi * scale, 0.0), high)
+        assert np.max(np.abs(got - want)) < 1e-13, (mask, value, high)
+        assert np.array_equal(got, st.measure_hist(high, (mask, value, scale), apply=False))     # fixed summation order
+        assert np.array_equal(st.get_state(), psi)                                                # nothing written
+    assert np.count_nonzero(st.measure_hist([7], (3, 1, 0.0), apply=False)) == 0
+    x0 = 0b1011001110101
+    st.measure_hist([], ((1 << n) - 1, x0, 2.5), want_hist=False)
+    want = np.zeros(1 << n, dtype=np.complex128)
+    want[x0] = psi[x0] * 2.5
+    assert np.array_equal(st.get_state(), want)
+    with pytest.raises(ValueError):
+        st.measure_hist([7], (1 << n, 0, 1.0), apply=False)           # mask outside the shard
+    st.close()
+
+
 @pytest.mark.parametrize("n,seed", [(12, 3), (16, 4), (21, 5)])
 def test_measure_many_on_device_matches_sequential_measure(n, seed):
     """Engine.measure_many == the same MEASUREs one by one (same uniforms): outcomes, p0 and the collapsed

@@ -154,12 +154,15 @@ class _HistState(object):
         self.psi = np.array(psi, dtype=np.complex128)
         self.n_local, self.device, self.passes = n, 0, 0
 
-    def measure_hist(self, high_positions, collapse=None, want_hist=True):
+    def measure_hist(self, high_positions, collapse=None, want_hist=True, apply=True):
         self.passes += 1
         idx = np.arange(self.psi.size, dtype=np.int64)
+        psi = self.psi
         if collapse is not None:
             mask, value, scale = collapse
-            self.psi = np.where((idx & mask) == value, self.psi * scale, 0.0)
+            psi = np.where((idx & mask) == value, self.psi * scale, 0.0)
+            if apply:
+                self.psi = psi
         if not want_hist:
             return None
         bins = np.zeros_like(idx)
@@ -167,7 +170,7 @@ class _HistState(object):
             assert p >= 5
             bins |= ((idx >> p) & 1) << i
         hist = np.zeros((1 << len(high_positions), 32))
-        np.add.at(hist, (bins, idx & 31), np.abs(self.psi) ** 2)
+        np.add.at(hist, (bins, idx & 31), np.abs(psi) ** 2)
         return hist
 
     def close(self):
