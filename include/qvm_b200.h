@@ -87,6 +87,12 @@ int qvm_create(int n_local, int device, qvm_t** out);
 /* Same, but adopt caller-owned device memory (e.g. a torch CUDA tensor) of 16 * 2^n_local bytes. */
 int qvm_create_external(int n_local, int device, void* device_ptr, qvm_t** out);
 int qvm_destroy(qvm_t* q);
+/* qvm_destroy parks the resources of a healthy, unshared handle whose state is at most 8 GiB (at most two sets, 8 GiB
+ * in total) and qvm_create of the same shape on the same device takes them over: a dozen allocations, 8 MiB of them
+ * pinned, are milliseconds next to a small program's device time (every density() call returns a cloned handle).  A
+ * failed device allocation inside the library empties the lot and retries; qvm_trim does it on request.
+ * QVM_B200_PARK=0 disables parking. */
+int qvm_trim(void);
 /* Multi-GPU: this handle is shard `shard_index` of 2^n_global (positions >= n_local). */
 int qvm_set_shard(qvm_t* q, int n_global, uint64_t shard_index);
 /* Run on a caller-owned cudaStream_t (0 restores the handle's own stream). */

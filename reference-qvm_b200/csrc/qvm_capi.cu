@@ -116,6 +116,7 @@ struct qvm_state {
     cudaEvent_t pace_ev[2] = {nullptr, nullptr};
     uint64_t pace_n = 0;
     bool capturing = false;
+    bool exported = false;            // the buffer's IPC handle was given out: never recycled through the parking lot
 };
 
 namespace {
@@ -748,7 +749,57 @@ int qvm_device_count(int* count) {
     return QVM_OK;
 }
 
-static int create_impl(int n_local, int device, void* external, qvm_t** out) {
+// Handles of small and mid-sized states come and go at a high rate -- every density() call returns an independent
+// snapshot (a cloned handle), every QVMConnection call on a new register a fresh one -- and a handle is a dozen
+// allocations, 8 MiB of them pinned host memory: milliseconds, next to ~10 ms of device work for a whole 14-qubit
+// noisy density program.  qvm_destroy therefore parks the complete resource set of a healthy, unshared handle (state
+// buffers of at most 8 GiB, at most two sets per process) and qvm_create of the same shape on the same device takes
+// it over.  A failed allocation anywhere in qvm_create empties the lot and retries.  QVM_B200_PARK=0 turns it off.
+namespace {
+struct Parked {
+    int device, n_local, sm_count, measure_grid;
+    double2* amps;
+    unsigned char *ring_host, *ring_dev;
+    double *partials, *result_dev, *result_host, *pow_dev, *total_dev;
+    cudaStream_t stream;
+};
+std::mutex g_park_mu;
+std::vector<Parked> g_parked;
+constexpr uint64_t kParkMaxBytes = 8ull << 30;
+constexpr size_t kParkMaxSets = 2;
+
+bool park_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("QVM_B200_PARK");
+        return !e || atoi(e) != 0;
+    }();
+    return on;
+}
+void parked_free(const Parked& p) {
+    cudaSetDevice(p.device);
+    cudaFree(p.amps);
+    cudaFreeHost(p.ring_host);
+    cudaFree(p.ring_dev);
+    cudaFree(p.partials);
+    cudaFree(p.result_dev);
+    cudaFreeHost(p.result_host);
+    cudaFree(p.pow_dev);
+    cudaFree(p.total_dev);
+    cudaStreamDestroy(p.stream);
+}
+void parked_release_all() {
+    std::vector<Parked> all;
+    {
+        std::lock_guard<std::mutex> lock(g_park_mu);
+        all.swap(g_parked);
+    }
+    for (const Parked& p : all) parked_free(p);
+}
+}  // namespace
+
+static int create_impl(int n_local, int device, void* external, qvm_t** out, bool retried = false);
+
+static int create_impl(int n_local, int device, void* external, qvm_t** out, bool retried) {
     if (!out) return fail(QVM_ERR_INVALID, "null output pointer");
     *out = nullptr;
     if (n_local < 0 || n_local > 40) return fail(QVM_ERR_INVALID, "n_local=%d outside [0, 40]", n_local);
@@ -772,11 +823,45 @@ static int create_impl(int n_local, int device, void* external, qvm_t** out) {
             int code = (_e == cudaErrorMemoryAllocation) ? QVM_ERR_NOMEM : QVM_ERR_CUDA;               \
             fail(code, "%s failed: %s", #expr, cudaGetErrorString(_e));                                \
             cudaGetLastError();                                                                        \
+            q->sticky = code; /* (never parked) */                                                     \
             qvm_destroy(q);                                                                            \
+            if (code == QVM_ERR_NOMEM && !retried) {                                                   \
+                parked_release_all();                                                                  \
+                return create_impl(n_local, device, external, out, true);                              \
+            }                                                                                          \
             return code;                                                                               \
         }                                                                                              \
     } while (0)
     QVM_CREATE_CUDA(cudaSetDevice(device));
+    if (!external && park_enabled()) {
+        Parked p{};
+        bool found = false;
+        {
+            std::lock_guard<std::mutex> lock(g_park_mu);
+            for (size_t i = 0; i < g_parked.size(); ++i)
+                if (g_parked[i].device == device && g_parked[i].n_local == n_local) {
+                    p = g_parked[i];
+                    g_parked.erase(g_parked.begin() + i);
+                    found = true;
+                    break;
+                }
+        }
+        if (found) {
+            q->sm_count = p.sm_count;
+            q->measure_grid = p.measure_grid;
+            q->amps = p.amps;
+            q->ring_host = p.ring_host;
+            q->ring_dev = p.ring_dev;
+            q->partials = p.partials;
+            q->result_dev = p.result_dev;
+            q->result_host = p.result_host;
+            q->pow_dev = p.pow_dev;
+            q->total_dev = p.total_dev;
+            q->own_stream = q->stream = p.stream;
+            *out = q;
+            return QVM_OK;
+        }
+    }
     cudaDeviceProp prop;
     QVM_CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
     q->sm_count = prop.multiProcessorCount;
@@ -816,6 +901,11 @@ static int create_impl(int n_local, int device, void* external, qvm_t** out) {
     return QVM_OK;
 }
 
+int qvm_trim(void) {
+    parked_release_all();
+    return QVM_OK;
+}
+
 int qvm_create(int n_local, int device, qvm_t** out) { return create_impl(n_local, device, nullptr, out); }
 
 int qvm_create_external(int n_local, int device, void* device_ptr, qvm_t** out) {
@@ -827,6 +917,25 @@ int qvm_destroy(qvm_t* q) {
     if (!q) return QVM_OK;
     cudaSetDevice(q->device);
     if (q->stream) cudaStreamSynchronize(q->stream);
+    if (park_enabled() && !q->sticky && q->owns_amps && q->amps && !q->alt && !q->exported && !q->n_global && !q->recording &&
+        q->own_stream && q->stream == q->own_stream && q->ring_host && q->ring_dev && q->partials && q->result_dev &&
+        q->result_host && q->pow_dev && q->total_dev && q->measure_grid && q->n_elems * sizeof(double2) <= kParkMaxBytes &&
+        cudaGetLastError() == cudaSuccess) {
+        std::unique_lock<std::mutex> lock(g_park_mu);
+        uint64_t held = q->n_elems * sizeof(double2);
+        for (const Parked& p : g_parked) held += (sizeof(double2) << p.n_local);
+        if (g_parked.size() < kParkMaxSets && held <= kParkMaxBytes) {
+            g_parked.push_back(Parked{q->device, q->n_local, q->sm_count, q->measure_grid, q->amps, q->ring_host, q->ring_dev,
+                                      q->partials, q->result_dev, q->result_host, q->pow_dev, q->total_dev, q->own_stream});
+            lock.unlock();
+            for (cudaEvent_t ev : q->pace_ev)
+                if (ev) cudaEventDestroy(ev);
+            if (q->cdf) cudaFree(q->cdf);
+            if (q->stage) cudaFreeHost(q->stage);
+            delete q;
+            return QVM_OK;
+        }
+    }
     if (q->amps && q->owns_amps) cudaFree(q->amps);
     if (q->alt) cudaFree(q->alt);
     for (cudaEvent_t ev : q->pace_ev)
@@ -1718,7 +1827,12 @@ int qvm_probs_prepare(qvm_t* q, int mode, int n_rho, double* total) {
         if (q->cdf) cudaFree(q->cdf);
         q->cdf = nullptr;
         q->cdf_cap = 0;
-        QVM_CUDA(q, cudaMalloc(&q->cdf, n_blocks * sizeof(double)));
+        if (cudaMalloc(&q->cdf, n_blocks * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();
+            parked_release_all();
+            cudaSetDevice(q->device);
+            QVM_CUDA(q, cudaMalloc(&q->cdf, n_blocks * sizeof(double)));
+        }
         q->cdf_cap = n_blocks;
     }
     const int threads = 256;
@@ -1834,6 +1948,7 @@ int qvm_ipc_export(qvm_t* q, void* handle64) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t h;
     QVM_CUDA(q, cudaIpcGetMemHandle(&h, q->amps));
+    q->exported = true;
     memcpy(handle64, &h, sizeof(h));
     return QVM_OK;
 }
@@ -1891,6 +2006,12 @@ int qvm_alt_alloc(qvm_t* q) {
     if (q->alt) return QVM_OK;
     if (!q->owns_amps) return fail(QVM_ERR_UNSUPPORTED, "handles on caller-owned memory have no alternate buffer");
     cudaError_t e = cudaMalloc(&q->alt, q->n_elems * sizeof(double2));
+    if (e == cudaErrorMemoryAllocation) {            // whatever the parking lot holds is worth less than this buffer
+        cudaGetLastError();
+        parked_release_all();
+        cudaSetDevice(q->device);
+        e = cudaMalloc(&q->alt, q->n_elems * sizeof(double2));
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
         q->alt = nullptr;

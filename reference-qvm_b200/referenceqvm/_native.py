@@ -64,6 +64,7 @@ _SIGNATURES = {
     "qvm_jit_counters": (C.c_int, [_P]),
     "qvm_jit_cache_dir": (C.c_int, [C.c_char_p, C.c_uint64]),
     "qvm_jit_defer": (C.c_int, [C.c_int]),
+    "qvm_trim": (C.c_int, []),
     "qvm_jit_share": (C.c_int, [C.c_int, C.c_int]),
     "qvm_debug_opcode_hist": (C.c_int, [_P, _P]),
     "qvm_n_local": (C.c_int, [_P]),
@@ -254,6 +255,11 @@ def jit_counters():
 def jit_defer(n):
     """The next ``n`` ahead-of-time submissions are compiled after everything queued the normal way."""
     check(lib().qvm_jit_defer(int(n)))
+
+
+def trim():
+    """Give the parked resources of destroyed handles (``qvm_destroy``) back to the driver."""
+    check(lib().qvm_trim())
 
 
 def jit_share(stride, offset):
