@@ -324,7 +324,10 @@ class Engine(object):
     #: host (~0.1 s for 1300 gates); skipped when the identity layout is not where the flush starts.
     AHEAD_MIN_QUBITS = int(os.environ.get("QVM_B200_AHEAD_MIN_QUBITS", "29"))
     AHEAD_MIN_OPS = 300
-    AHEAD_COMPILE_S = float(os.environ.get("QVM_B200_AHEAD_COMPILE_S", "0.6"))
+    #: > 0: the structures of the passes that start within this many seconds of the run are compiled last
+    #: (``qvm_jit_defer``).  Measured on the 33-qubit cold call: no gain (2151 ms against 2034 ms without; the late
+    #: compilations then compete with the sampling tail for the host cores), so it is off by default.
+    AHEAD_COMPILE_S = float(os.environ.get("QVM_B200_AHEAD_COMPILE_S", "0"))
 
     def _compile_ahead(self, ops):
         if (self.n < self.AHEAD_MIN_QUBITS or len(ops) < self.AHEAD_MIN_OPS or not self.relabel
@@ -341,10 +344,9 @@ class Engine(object):
             from referenceqvm import precompile
             if os.environ.get("QVM_B200_JIT", "1") != "1" or not nat.jit_cache_dir():
                 return
-            # the run starts right behind this walk: its first passes will have gone through the interpreter (about
-            # 2^n * 32 B at ~2.7 TB/s each) before the first compilation (~0.6 s) can land, so their kernels are
-            # compiled last and the later passes' first -- launches wait for a kernel that is on its way for as long
-            # as the GPU has earlier passes queued (qvm_capi.cu, launch_rec)
+            # the run starts right behind this walk; launches wait for a kernel that is on its way for as long as the
+            # GPU has earlier passes queued (qvm_capi.cu, launch_rec).  Optionally (AHEAD_COMPILE_S) the kernels of the
+            # first passes -- which go through the interpreter whatever happens -- are compiled last.
             nat.jit_defer(int(self.AHEAD_COMPILE_S / (2.0 ** self.n * 32.0 / 2.7e12)))
             try:
                 precompile.walk_pending(ops, self.n, self.tile_bits, self.low_bits, wait=False)
