@@ -501,13 +501,29 @@ bool pace_backlog(qvm_state* q) {
     return false;
 }
 
-// A pushing pass walks its tiles with the victim bits as the FASTEST-varying bits of the tile index (the runs of
-// non-tile positions the block index is deposited into are launch parameters): consecutive CTAs then store to
-// different destinations in turn, so the NVLink stores are spread over the whole kernel instead of all local
-// tiles running first and all remote ones after them.  More than 8 runs: the order is left as it is.
-void runs_for_push(const PushSpec& push, int& n_runs, uint64_t& run_start, uint64_t& run_len) {
+// The order in which a pushing pass walks its tiles (the runs of non-tile positions the block index is deposited
+// into are launch parameters) decides when it stores where.  QVM_B200_PUSH_ORDER:
+//   0 (default): the victim bits are the FASTEST-varying bits of the tile index -- consecutive CTAs store to
+//      different destinations in turn, so the NVLink stores are spread over the whole kernel instead of all local
+//      tiles running first and all remote ones after them;
+//   1: the victim bits are the SLOWEST bits, XOR-rotated by the rank's own global bits (PushSpec::rot): the pass
+//      goes through its destinations one after the other and at any time every rank stores to a different peer;
+//   2: the lowest victim bit fastest, the others slowest and rotated: two destinations at a time.
+// More than 8 runs: the order is left as it is.
+int push_order() {
+    static const int mode = [] {
+        const char* e = getenv("QVM_B200_PUSH_ORDER");
+        const int v = e ? atoi(e) : 0;
+        return v < 0 || v > 2 ? 0 : v;
+    }();
+    return mode;
+}
+
+void runs_for_push(PushSpec& push, int& n_runs, uint64_t& run_start, uint64_t& run_len) {
     struct Run { int start, len; };
-    std::vector<Run> runs, head;
+    std::vector<Run> runs, head, tail;
+    const int mode = push.m >= 2 ? push_order() : 0;
+    uint64_t rot_mask = 0;
     for (int r = 0; r < n_runs; ++r)
         runs.push_back(Run{(int)((run_start >> (8 * r)) & 0xFF), (int)((run_len >> (8 * r)) & 0xFF)});
     for (int i = 0; i < push.m; ++i) {
@@ -520,18 +536,25 @@ void runs_for_push(const PushSpec& push, int& n_runs, uint64_t& run_start, uint6
             if (p + 1 < cur.start + cur.len) parts.push_back(Run{p + 1, cur.start + cur.len - p - 1});
             runs.erase(runs.begin() + r);
             runs.insert(runs.begin() + r, parts.begin(), parts.end());
-            head.push_back(Run{p, 1});
+            if (mode == 1 || (mode == 2 && i > 0)) {
+                tail.push_back(Run{p, 1});
+                rot_mask |= 1ull << p;
+            } else {
+                head.push_back(Run{p, 1});
+            }
             break;
         }
     }
-    if (head.empty() || head.size() + runs.size() > 8) return;
+    if ((head.empty() && tail.empty()) || head.size() + runs.size() + tail.size() > 8) return;
     head.insert(head.end(), runs.begin(), runs.end());
+    head.insert(head.end(), tail.begin(), tail.end());
     n_runs = (int)head.size();
     run_start = run_len = 0;
     for (size_t r = 0; r < head.size(); ++r) {
         run_start |= (uint64_t)head[r].start << (8 * r);
         run_len |= (uint64_t)head[r].len << (8 * r);
     }
+    push.rot = push.mine_bits & rot_mask;
 }
 
 // With `push` (a fused exchange, see PushSpec) the register-tiled kernels store the pass straight into the
@@ -605,7 +628,7 @@ int launch_rec(qvm_state* q, LaunchRec& rec, const PushSpec* push = nullptr, boo
             sp.from_zero = from_zero;
             if (push && push->m) {
                 sp.push = *push;
-                runs_for_push(*push, sp.n_runs, sp.run_start, sp.run_len);
+                runs_for_push(sp.push, sp.n_runs, sp.run_start, sp.run_len);
                 if (pushed) *pushed = true;
             }
             void* args[3] = {&amps, &sp, const_cast<double*>(ss.factors.data())};
@@ -648,7 +671,7 @@ int launch_rec(qvm_state* q, LaunchRec& rec, const PushSpec* push = nullptr, boo
     P.from_zero = from_zero;
     if (push && push->m) {
         P.push = *push;
-        runs_for_push(*push, P.n_runs, P.run_start, P.run_len);
+        runs_for_push(P.push, P.n_runs, P.run_start, P.run_len);
         if (pushed) *pushed = true;
     }
     P.rounds = reinterpret_cast<const RoundDesc*>(dp);

@@ -314,7 +314,7 @@ inline bool generate_spec(const EncodedGroup& g, SpecSource& out) {
         "__device__ __forceinline__ uint64_t spec_tile_base(const SpecParams& SP, uint64_t t) {\n  uint64_t base = 0;\n"
         "  for (int r = 0; r < SP.n_runs; ++r) {\n    const uint32_t len = (uint32_t)(SP.run_len >> (8 * r)) & 0xFFu;\n"
         "    base |= (t & ((1ull << len) - 1ull)) << ((uint32_t)(SP.run_start >> (8 * r)) & 0xFFu);\n    t >>= len;\n  }\n"
-        "  return base;\n}\n";
+        "  return base ^ SP.push.rot;\n}\n";
     o << tile_base_fn;
     const unsigned ctas = (pipe || tma)
                               ? std::max(1u, std::min(spec_min_blocks(g.threads), (unsigned)((220u * 1024u) / ((size_t)32 << P.k))))

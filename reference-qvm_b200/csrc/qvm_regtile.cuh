@@ -163,6 +163,9 @@ struct PushSpec {
     uint8_t pos[4];
     uint64_t mask;
     uint64_t mine_bits;
+    uint64_t rot;             // XORed into every tile's outer bits: rotates the order in which a rank visits its
+                              // destinations (victim bits slowest in the tile index, rot = mine_bits: at any time
+                              // every rank stores to a different peer), 0 = tiles in plain index order
     double2* dst[1 << kMaxPushBits];
 };
 
@@ -814,7 +817,7 @@ QVM_HD uint64_t rt_tile_base(const RegTileParams& P, uint64_t tile_index) {
         base |= (t & ((1ull << len) - 1ull)) << ((uint32_t)(P.run_start >> (8 * r)) & 0xFFu);
         t >>= len;
     }
-    return base;
+    return base ^ P.push.rot;
 }
 
 // store base of the tile whose outer bits are `base` (see PushSpec)
