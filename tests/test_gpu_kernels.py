@@ -685,3 +685,31 @@ def test_relabel_and_layout_argument_checks():
     assert sorted(pos_of) == list(range(n)) and sum(1 for p in (5, 6, 7, 8, 9, 10) if pos_of[p] < 4) == 4
     assert np.array_equal(st.get_layout(0, 1, 1 << n, pos_of), psi)
     st.close()
+
+
+# ---- handle parking (qvm_destroy / qvm_create / qvm_trim) ------------------------------------------------------
+def test_parked_handle_resources_are_reused_cleanly():
+    """A destroyed handle's resources are taken over by the next handle of the same shape: the new handle starts
+    with zeroed counters, no sticky state, and computes the same as a fresh one; qvm_trim empties the lot."""
+    n = 13
+    spec = orc.random_circuit_spec(n, 6, 3)
+    want, fresh_stats = _run_circuit_state(n, spec, jit=0)
+    nat.trim()
+    first = nat.DeviceState(n)
+    first.set_state(random_state(n, 9))
+    first.measure(3, 0.4)                      # leaves sampling / scratch state behind
+    ptr = first.device_ptr()
+    first.close()
+    again = nat.DeviceState(n)                 # same shape, same device: the parked set
+    assert again.device_ptr() == ptr
+    st = again.stats()
+    assert st["kernel_launches"] == 0 and st["hbm_passes"] == 0 and st["h2d_bytes"] == 0
+    again.close()
+    got, stats = _run_circuit_state(n, spec, jit=0)
+    assert np.array_equal(got, want) and stats["gate_ops"] == fresh_stats["gate_ops"]
+    other = nat.DeviceState(n + 1)             # another shape never takes it
+    assert other.device_ptr() != ptr
+    other.close()
+    nat.trim()
+    got, _ = _run_circuit_state(n, spec, jit=0)
+    assert np.array_equal(got, want)
