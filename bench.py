@@ -593,7 +593,7 @@ def main():
     n, depth = args.qubits, args.depth
 
     # ---- first calls, BEFORE anything has warmed this process up -------------------------------------------------
-    # e2e_cold: a program nobody has seen (its own seed): no cubin of it anywhere, every structure is new.
+    # e2e_cold: a program nobody has seen (a seed drawn per run): no cubin of it anywhere, every structure is new.
     # e2e_first_call: the benchmark program's own first call in this process; its specialised kernels were compiled
     # ahead of time by build() (referenceqvm/precompile.py) into the library's disk cache, the deployment a known
     # program gets -- "fresh process, warm disk cache".
