@@ -26,6 +26,9 @@ PyObject* qvm_rows_from_indices(const uint64_t* idx, Py_ssize_t rows, const int3
             Py_INCREF(o);
             PyList_SET_ITEM(row, c, o);
         }
+        /* a list of ints cannot be part of a reference cycle: taken off the collector's books, a million of them cost
+         * the cyclic garbage collector nothing (the list itself stays an ordinary list) */
+        PyObject_GC_UnTrack(row);
         PyList_SET_ITEM(out, r, row);
     }
     Py_XDECREF(bit[0]);
@@ -64,6 +67,7 @@ PyObject* qvm_rows_from_int64(const char* m, Py_ssize_t rows, Py_ssize_t cols, P
             }
             PyList_SET_ITEM(row, c, o);
         }
+        if (out) PyObject_GC_UnTrack(row);
     }
     Py_XDECREF(bit[0]);
     Py_XDECREF(bit[1]);

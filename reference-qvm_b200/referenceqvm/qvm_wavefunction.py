@@ -83,7 +83,9 @@ def _pyrows_lib():
 def _rows_to_lists(matrix=None, indices=None, sel=None):
     """One Python list per trial (the reference's return type) from an integer matrix, or directly from sampled
     basis-state ``indices`` and the bit position ``sel[c]`` each output column reads (outside 0..63: always 0) --
-    without paying the cyclic garbage collector for it.  A million row lists are a million tracked containers:
+    without paying the cyclic garbage collector for it.  The C helper takes its rows off the collector's books as it
+    builds them; the rest of this paragraph is about numpy's ``tolist()``, the fallback when ``_pyrows.so`` is
+    missing.  A million row lists are a million tracked containers:
     built with the collector running, the generational collections they trigger cost a third of the conversion;
     built with it paused, the first allocation after it is switched back on starts a full collection that walks
     all of them (0.15 s per million rows on the GPU box, charged to whoever allocates next).  Rows cannot be part
@@ -110,7 +112,9 @@ def _rows_to_lists(matrix=None, indices=None, sel=None):
                 out = lib.qvm_rows_from_int64(m.ctypes.data, m.shape[0], m.shape[1], m.strides[0], m.strides[1])
             else:
                 out = m.tolist()
-        if _GC_FREEZE and was_enabled and len(out) >= 100000:
+        # rows built by the C helper are untracked (PyObject_GC_UnTrack: a list of ints cannot be in a cycle), so
+        # the collector never sees them; only tolist()'s rows need the freeze
+        if not lib and _GC_FREEZE and was_enabled and len(out) >= 100000:
             gc.freeze()
             _frozen_rows[0] = True
         return out

@@ -256,6 +256,8 @@ def test_result_rows_helper_matches_numpy(monkeypatch):
     idx[:4] = [0, 1, 2 ** 63, 2 ** 64 - 1]
     sel = [0, 5, 63, -1, 33, 64, 5]
     fast = qw._rows_to_lists(indices=idx, sel=sel)
+    import gc
+    assert type(fast[0]) is list and not gc.is_tracked(fast[0])      # invisible to the cyclic collector
     mat = rng.integers(-2 ** 62, 2 ** 62, size=(50, 12), dtype=np.int64)
     mat[:, ::2] = rng.integers(0, 2, size=(50, 6))
     fast_m = qw._rows_to_lists(mat[::2, ::-1])
