@@ -93,6 +93,21 @@ int qvm_destroy(qvm_t* q);
  * failed device allocation inside the library empties the lot and retries; qvm_trim does it on request.
  * QVM_B200_PARK=0 disables parking. */
 int qvm_trim(void);
+
+/* ---- host-side planning (no device) ----------------------------------------------------------- */
+/* Which of the pending ops of a flush go into the next fused group (the inner loop of referenceqvm/_planner.py; the
+ * reference has no counterpart: it applies one full-space operator per gate, qvm_wavefunction.py:158-162).  The op
+ * stream is given in CSR form: dense[i] = op i has dense targets tgt[tgt_off[i] .. tgt_off[i+1]) (logical qubits
+ * < 64), dep[dep_off[i] .. dep_off[i+1]) = earlier ops it does not commute with, done[i] = already run.  Scanning
+ * from `first` over at most `lookahead` ops in program order, an op joins when its dependencies have run or joined and
+ * its dense targets fit a tile of k qubits grown from seed_mask with at most max_new qubits outside old_mask (the
+ * qubits that may be kept on the coalescing positions).  depth 0 = first fit; depth d > 0 also tries, d levels deep,
+ * banning one more of the qubits a candidate admitted, and returns the candidate holding the most ops.
+ * chosen[0 .. *n_chosen) (capacity max_group_ops) = op indices in program order, *tile_mask = the group's qubits. */
+int qvm_plan_choose_group(int n_ops, const uint8_t* dense, const int32_t* tgt_off, const int32_t* tgt, const int32_t* dep_off,
+                          const int32_t* dep, const uint8_t* done, int first, int lookahead, int k, int max_new,
+                          uint64_t old_mask, uint64_t seed_mask, int max_group_ops, int depth, int32_t* chosen,
+                          int32_t* n_chosen, uint64_t* tile_mask);
 /* Multi-GPU: this handle is shard `shard_index` of 2^n_global (positions >= n_local). */
 int qvm_set_shard(qvm_t* q, int n_global, uint64_t shard_index);
 /* Run on a caller-owned cudaStream_t (0 restores the handle's own stream). */

@@ -6,6 +6,7 @@
 #include "qvm_regtile.cuh"
 #include "qvm_encode.h"
 #include "qvm_jit.h"
+#include "qvm_planner.h"
 #include "qvm_regtile_src.inc"
 
 #include <algorithm>
@@ -921,6 +922,20 @@ static int create_impl(int n_local, int device, void* external, qvm_t** out, boo
     q->measure_grid = std::min(per_sm * q->sm_count, kPartialsCap);
 #undef QVM_CREATE_CUDA
     *out = q;
+    return QVM_OK;
+}
+
+int qvm_plan_choose_group(int n_ops, const uint8_t* dense, const int32_t* tgt_off, const int32_t* tgt, const int32_t* dep_off,
+                          const int32_t* dep, const uint8_t* done, int first, int lookahead, int k, int max_new,
+                          uint64_t old_mask, uint64_t seed_mask, int max_group_ops, int depth, int32_t* chosen,
+                          int32_t* n_chosen, uint64_t* tile_mask) {
+    if (!dense || !tgt_off || !dep_off || !done || !chosen || !n_chosen || !tile_mask || (tgt_off[n_ops] && !tgt) ||
+        (dep_off[n_ops] && !dep))
+        return fail(QVM_ERR_INVALID, "null pointer");
+    if (n_ops < 0 || first < 0 || first > n_ops || lookahead < 1 || k < 1 || k > 64 || max_group_ops < 1 || depth < 0 || depth > 4)
+        return fail(QVM_ERR_INVALID, "bad planning request");
+    PlanStream s{n_ops, dense, tgt_off, tgt, dep_off, dep, done};
+    *n_chosen = plan_choose(s, first, lookahead, k, max_new, old_mask, seed_mask, max_group_ops, depth, chosen, tile_mask);
     return QVM_OK;
 }
 

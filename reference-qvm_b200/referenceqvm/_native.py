@@ -65,6 +65,8 @@ _SIGNATURES = {
     "qvm_jit_cache_dir": (C.c_int, [C.c_char_p, C.c_uint64]),
     "qvm_jit_defer": (C.c_int, [C.c_int]),
     "qvm_trim": (C.c_int, []),
+    "qvm_plan_choose_group": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64,
+                                        C.c_uint64, C.c_int, C.c_int, _P, _P, _P]),
     "qvm_jit_share": (C.c_int, [C.c_int, C.c_int]),
     "qvm_debug_opcode_hist": (C.c_int, [_P, _P]),
     "qvm_n_local": (C.c_int, [_P]),

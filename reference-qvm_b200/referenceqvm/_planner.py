@@ -10,10 +10,20 @@ Scheduling is commutation aware.  An op touches a qubit either *densely* (it is 
 share is touched diagonally by both, so e.g. RZ / CPHASE / controls never pin a tile bit and can be
 hoisted into any group once the dense ops before them on the same qubits have run.
 """
+import ctypes
+import os
+
+import numpy as np
+
+from referenceqvm import _native as nat
 from referenceqvm._native import OP_DENSE, OP_DIAG, OP_NOP
 
 MAX_GROUP_OPS = 1024        # descriptor budget of one launch (shared-memory copy of the op list)
 LOOKAHEAD = 8192            # ops scanned past the first unscheduled one when filling a group
+#: how hard ``run_relabelled`` looks for a fuller group (``qvm_plan_choose_group``): 0 = first fit; d = also try, d
+#: levels deep, banning one more of the qubits a candidate admitted.  Depth 2 takes 10-15 % of the passes off the
+#: benchmark circuits (33 qubits: 28 -> 25, 30 qubits: 26 -> 23) for ~1 ms of host time per group.
+SEARCH_DEPTH = max(0, min(4, int(os.environ.get("QVM_B200_PLAN_SEARCH", "2"))))
 
 
 class Group(object):
@@ -153,9 +163,50 @@ def summarize(groups):
 # launch is asked to bring the qubits both groups share to the low positions, and the next group's tile
 # follows from the layout the library reports back.
 
+class _Stream(object):
+    """The op stream of one ``run_relabelled`` call in the CSR form ``qvm_plan_choose_group`` reads."""
+
+    def __init__(self, ops, deps):
+        n = len(ops)
+        self.n = n
+        self.dense = np.array([1 if o.kind == OP_DENSE else 0 for o in ops], dtype=np.uint8)
+        tgt, tgt_off, dep, dep_off = [], [0], [], [0]
+        for o, d in zip(ops, deps):
+            if o.kind == OP_DENSE:
+                tgt.extend(o.targets)
+            tgt_off.append(len(tgt))
+            dep.extend(sorted(d))
+            dep_off.append(len(dep))
+        self.tgt = np.array(tgt, dtype=np.int32)
+        self.tgt_off = np.array(tgt_off, dtype=np.int32)
+        self.dep = np.array(dep, dtype=np.int32)
+        self.dep_off = np.array(dep_off, dtype=np.int32)
+        self.done = np.zeros(n, dtype=np.uint8)
+        self.chosen = np.empty(MAX_GROUP_OPS, dtype=np.int32)
+        if self.tgt.size and int(self.tgt.max()) >= 64:
+            raise ValueError("the planner handles at most 64 qubits")
+
+    def choose(self, first, k, max_new, old_qubits, seed_tile, max_group_ops, depth):
+        """(tile qubits, chosen op indices): see ``qvm_plan_choose_group`` (include/qvm_b200.h)."""
+        old_mask = 0
+        for q in old_qubits:
+            old_mask |= 1 << q
+        seed_mask = 0
+        for q in seed_tile:
+            seed_mask |= 1 << q
+        cap = min(int(max_group_ops), self.chosen.size)
+        n_chosen, tile_mask = ctypes.c_int32(0), ctypes.c_uint64(0)
+        nat.check(nat.lib().qvm_plan_choose_group(
+            self.n, self.dense.ctypes.data, self.tgt_off.ctypes.data, self.tgt.ctypes.data, self.dep_off.ctypes.data,
+            self.dep.ctypes.data, self.done.ctypes.data, int(first), LOOKAHEAD, int(k), int(max_new), old_mask, seed_mask,
+            cap, int(depth), self.chosen.ctypes.data, ctypes.byref(n_chosen), ctypes.byref(tile_mask)))
+        return set(_positions(tile_mask.value)), self.chosen[:n_chosen.value].tolist()
+
+
 def _choose_group(ops, deps, done, first, k, max_new, is_old, seed_tile, max_group_ops):
     """Greedy group in LOGICAL qubits: ops whose dependencies are met and whose dense targets fit a tile
-    of k qubits with at most ``max_new`` qubits q for which ``is_old(q)`` is false."""
+    of k qubits with at most ``max_new`` qubits q for which ``is_old(q)`` is false.  (The first-fit scan in
+    Python: what ``qvm_plan_choose_group`` does at depth 0; kept as the reference the tests compare it with.)"""
     tile = set(seed_tile)
     new_count = sum(1 for q in tile if not is_old(q))
     chosen, in_group = [], set()
@@ -181,7 +232,7 @@ def _choose_group(ops, deps, done, first, k, max_new, is_old, seed_tile, max_gro
 
 
 def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_group_ops=MAX_GROUP_OPS,
-                   defer_tail_below=0, leftover=None, on_last=None, last_tile_bits=0):
+                   defer_tail_below=0, leftover=None, on_last=None, last_tile_bits=0, search_depth=None):
     """Run ``ops`` (ClassifiedOps on LOGICAL qubits; every dense target currently on a local position)
     as fused groups with in-tile relabelling.  ``pos_of`` (logical -> physical, mutated in place) is the
     layout; ``launch(tile_positions, physical_ops, bring_low_positions)`` runs one pass and returns the
@@ -218,7 +269,9 @@ def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_g
         return (n + max_group_ops - 1) // max_group_ops
 
     deps = dependencies(ops)
-    done = [False] * n
+    stream = _Stream(ops, deps)
+    done = stream.done
+    depth = SEARCH_DEPTH if search_depth is None else search_depth
     qubit_at = {p: q for q, p in enumerate(pos_of)}
     first = 0
     passes = 0
@@ -230,7 +283,7 @@ def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_g
     def fixed_choice():
         """The layout as it is: the qubits on the low positions are in, k - low more may join."""
         lq = set(low_qubits())
-        return _choose_group(ops, deps, done, first, k, k - low, lambda q: q in lq, lq, max_group_ops)
+        return stream.choose(first, k, k - low, lq, lq, max_group_ops, depth)
 
     k_normal = k
     big = min(int(last_tile_bits or 0), n_local - 1) if on_last is not None else 0
@@ -241,7 +294,7 @@ def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_g
         k = k_normal
         if big > k_normal:
             lq = set(low_qubits())
-            big_tile, big_ops = _choose_group(ops, deps, done, first, big, big - low, lambda q: q in lq, lq, max_group_ops)
+            big_tile, big_ops = stream.choose(first, big, big - low, lq, lq, max_group_ops, 0)
             if len(big_ops) == n - n_done and len(big_ops) > len(cur_ops):
                 cur_tile, cur_ops, k = big_tile, big_ops, big       # the rest of the batch in one (larger) tile
         # physical tile: the low positions, the group's qubits, then the lowest unused positions
@@ -259,7 +312,7 @@ def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_g
         tile_positions = sorted(positions)
         tile_qubits = set(qubit_at[p] for p in tile_positions)
         for i in cur_ops:
-            done[i] = True
+            done[i] = 1
         while first < n and done[first]:
             first += 1
         if first >= n and leftover is not None and len(cur_ops) < defer_tail_below:
@@ -271,8 +324,7 @@ def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_g
         contiguous = all(tile_positions[j] == j for j in range(low))
         n_done += len(cur_ops)
         if first < n and contiguous:
-            nxt_tile, nxt_ops = _choose_group(ops, deps, done, first, k, k - low, lambda q: q in tile_qubits, (),
-                                              max_group_ops)
+            nxt_tile, nxt_ops = stream.choose(first, k, k - low, tile_qubits, (), max_group_ops, depth)
             if (on_last is not None and leftover is not None and len(nxt_ops) == n - n_done
                     and len(nxt_ops) < defer_tail_below):
                 # everything that is left is a thin tail: it will be deferred, so THIS launch is the last one
