@@ -141,6 +141,12 @@ int qvm_spec_precompile(int n_local, int n_global, uint64_t shard_index, int n_t
                         int n_ops, const qvm_op_t* ops, const double* mats, uint64_t mats_entries, int n_low,
                         int n_bring, const int32_t* bring_low, int32_t* new_pos);
 /* out4 = {structures submitted to NVRTC, cubins loaded from the disk cache, cubins written to it, kernels ready} */
+/* Planning aid (no device, nothing compiled): what the encoder makes of one group -- info4 = {register-tile rounds
+ * (-1: the group goes to the shared-memory kernel), ops encoded, rounds that apply a thread scalar, 1 if the group can
+ * be specialised} -- and where the relabelling leaves every tile position (new_pos, as qvm_spec_precompile). */
+int qvm_group_probe(int n_local, int n_global, uint64_t shard_index, int n_tile, const int32_t* tile_bits, int n_ops,
+                    const qvm_op_t* ops, const double* mats, uint64_t mats_entries, int n_low, int n_bring,
+                    const int32_t* bring_low, int32_t* new_pos, int32_t* info4);
 int qvm_jit_counters(uint64_t* out4);
 int qvm_jit_cache_dir(char* out, uint64_t cap);
 /* The next n qvm_spec_precompile submissions are compiled after everything queued the normal way: the first passes

@@ -1071,6 +1071,27 @@ int qvm_spec_precompile(int n_local, int n_global, uint64_t shard_index, int n_t
     return QVM_OK;
 }
 
+// Planning aid (no device, nothing compiled): the rounds the encoder plans for one group and where the relabelling
+// leaves every tile position -- what a planner needs to compare candidate groups by cost.
+int qvm_group_probe(int n_local, int n_global, uint64_t shard_index, int n_tile, const int32_t* tile_bits, int n_ops,
+                    const qvm_op_t* ops, const double* mats, uint64_t mats_entries, int n_low, int n_bring,
+                    const int32_t* bring_low, int32_t* new_pos, int32_t* info4) {
+    if ((n_tile && !tile_bits) || (n_ops && !ops) || (n_bring && !bring_low) || !new_pos || !info4) return fail(QVM_ERR_INVALID, "null pointer");
+    uint32_t low_in = 0;
+    for (int i = 0; i < n_bring; ++i)
+        for (int j = 0; j < n_tile; ++j)
+            if (tile_bits[j] == bring_low[i]) low_in |= 1u << j;
+    EncodedGroup g;
+    const int erc = encode_group(n_local, n_global, shard_index, n_tile, tile_bits, n_ops, ops, mats, mats_entries, g, 4,
+                                 low_in, n_low);
+    for (int j = 0; j < n_tile; ++j) new_pos[j] = tile_bits[erc == ENC_OK ? g.sigma[j] : j];
+    info4[0] = erc == ENC_OK ? (int)g.rounds.size() : -1;
+    info4[1] = erc == ENC_OK ? g.n_gate_ops : 0;
+    info4[2] = erc == ENC_OK ? g.n_dirty_rounds : 0;
+    info4[3] = erc == ENC_OK && !g.need_full ? 1 : 0;
+    return QVM_OK;
+}
+
 int qvm_jit_counters(uint64_t* out4) {
     if (!out4) return fail(QVM_ERR_INVALID, "null pointer");
     SpecCache::instance().counters(out4);

@@ -100,6 +100,15 @@ inline bool place_dense(PlannedRound& rd, const LocalOp& op, uint32_t allowed, i
     return false;
 }
 
+// QVM_B200_ROUND_SEARCH=0: plain first-fit round planning (A/B runs)
+inline bool round_search_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("QVM_B200_ROUND_SEARCH");
+        return !e || atoi(e) != 0;
+    }();
+    return on;
+}
+
 inline bool is_x_matrix(const double* m) {      // compared as numbers: conj(X) carries -0.0 imaginary parts
     return m[0] == 0.0 && m[1] == 0.0 && m[2] == 1.0 && m[3] == 0.0 && m[4] == 1.0 && m[5] == 0.0 && m[6] == 0.0 &&
            m[7] == 0.0;
@@ -219,13 +228,13 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
     std::vector<int> round_of(n, -1);          // earliest legal round of every op (all-ops greedy)
     std::vector<PlannedRound> rounds;
     {
-        std::vector<char> done(n, 0);
-        int remaining = n;
-        while (remaining > 0) {
-            PlannedRound rd;
-            const uint32_t allowed = rounds.empty() ? high_bits : all_bits;
+        // One round, first fit: ops in program order; a dense op joins when its targets get register slots (bits in
+        // `banned` may not become register bits), anything that cannot join blocks what depends on it.
+        auto build_round = [&](const std::vector<char>& done, bool first_round, uint32_t banned, PlannedRound& rd,
+                               std::vector<int>& placed) {
+            const uint32_t allowed = (first_round ? high_bits : all_bits) & ~banned;
             uint32_t blocked_dense = 0, blocked_diag = 0;
-            int placed = 0;
+            placed.clear();
             for (int i = 0; i < n; ++i) {
                 if (done[i]) continue;
                 const LocalOp& op = lops[i];
@@ -241,12 +250,76 @@ inline int encode_group(int n_local, int n_global, uint64_t shard_index, int n_t
                     blocked_diag |= op.diag_mask;
                     continue;
                 }
+                placed.push_back(i);
+            }
+        };
+        // rounds the rest of the group takes with plain first fit from `done` on (store round included); -1: stuck
+        auto rounds_to_finish = [&](std::vector<char> done, int remaining, int rounds_so_far, uint32_t last_mask) {
+            std::vector<int> placed;
+            int total = rounds_so_far;
+            while (remaining > 0) {
+                PlannedRound rd;
+                build_round(done, total == 0, 0, rd, placed);
+                if (placed.empty() && total > 0) return -1;
+                for (int i : placed) done[i] = 1;
+                remaining -= (int)placed.size();
+                last_mask = rd.regmask();
+                ++total;
+            }
+            if (total == 0) total = 1;
+            if ((total > 1 && (last_mask & low5_last)) || (relabel && total == 1)) ++total;
+            return total;
+        };
+        std::vector<char> done(n, 0);
+        std::vector<int> placed, best_placed;
+        int remaining = n;
+        while (remaining > 0) {
+            const bool first_round = rounds.empty();
+            PlannedRound rd;
+            build_round(done, first_round, 0, rd, placed);
+            if (round_search_enabled() && remaining > (int)placed.size()) {
+                // Which tile bits become register bits decides how many rounds the group needs.  First fit hands the
+                // slots to whichever dense op comes first; try keeping one or two of those bits out of this round
+                // and keep the variant with which the group finishes in the fewest rounds (then: most ops now).
+                std::vector<char> trial_done = done;
+                for (int i : placed) trial_done[i] = 1;
+                int best_total = rounds_to_finish(trial_done, remaining - (int)placed.size(), (int)rounds.size() + 1, rd.regmask());
+                if (best_total < 0) best_total = 1 << 20;
+                size_t best_now = placed.size();
+                PlannedRound best_rd = rd;
+                best_placed = placed;
+                const uint32_t base_mask = rd.regmask();
+                std::vector<uint32_t> bans;
+                for (int a = 0; a < n_tile; ++a)
+                    if ((base_mask >> a) & 1u) {
+                        bans.push_back(1u << a);
+                        for (int b = a + 1; b < n_tile; ++b)
+                            if ((base_mask >> b) & 1u) bans.push_back((1u << a) | (1u << b));
+                    }
+                for (uint32_t ban : bans) {
+                    PlannedRound cand;
+                    build_round(done, first_round, ban, cand, placed);
+                    if (placed.empty() && !first_round) continue;
+                    trial_done = done;
+                    for (int i : placed) trial_done[i] = 1;
+                    const int total = rounds_to_finish(trial_done, remaining - (int)placed.size(), (int)rounds.size() + 1, cand.regmask());
+                    if (total < 0) continue;
+                    if (total < best_total || (total == best_total && placed.size() > best_now)) {
+                        best_total = total;
+                        best_now = placed.size();
+                        best_rd = cand;
+                        best_placed = placed;
+                    }
+                }
+                rd = best_rd;
+                placed = best_placed;
+            }
+            for (int i : placed) {
                 round_of[i] = (int)rounds.size();
                 done[i] = 1;
-                ++placed;
             }
-            remaining -= placed;
-            if (placed == 0 && !rounds.empty()) return ENC_ERROR;
+            remaining -= (int)placed.size();
+            if (placed.empty() && !rounds.empty()) return ENC_ERROR;
             rounds.push_back(rd);
         }
     }

@@ -62,6 +62,8 @@ _SIGNATURES = {
     "qvm_spec_precompile": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_int, _P, C.c_int, _P, _P, C.c_uint64, C.c_int, C.c_int,
                                       _P, _P]),
     "qvm_jit_counters": (C.c_int, [_P]),
+    "qvm_group_probe": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_int, _P, C.c_int, _P, _P, C.c_uint64, C.c_int, C.c_int,
+                                  _P, _P, _P]),
     "qvm_jit_cache_dir": (C.c_int, [C.c_char_p, C.c_uint64]),
     "qvm_jit_defer": (C.c_int, [C.c_int]),
     "qvm_trim": (C.c_int, []),
