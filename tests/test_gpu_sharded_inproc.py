@@ -66,7 +66,7 @@ def test_sharded_engine_on_one_gpu(world, exchange):
                 for q, r in ((n - 1, 0.3), (0, 0.8), (n // 2, 0.5)):
                     outcome, p0 = eng.measure(q, r if rank == 0 else -1.0)
                     o_want, p_want, psi = orc.fast_measure(psi, q, n, r)
-                    assert outcome == o_want and abs(p0 - p_want) < 1e-12
+                    assert outcome == o_want and abs(p0 - p_want) < 1e-12, (case, rank, q, r, outcome, o_want, p0, p_want)
                 err = float(np.max(np.abs(eng.amplitudes() - psi)))
                 assert err < 1e-12, ("after measure", err)
                 eng.close()
