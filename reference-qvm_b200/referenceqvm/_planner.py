@@ -22,8 +22,18 @@ MAX_GROUP_OPS = 1024        # descriptor budget of one launch (shared-memory cop
 LOOKAHEAD = 8192            # ops scanned past the first unscheduled one when filling a group
 #: how hard ``run_relabelled`` looks for a fuller group (``qvm_plan_choose_group``): 0 = first fit; d = also try, d
 #: levels deep, banning one more of the qubits a candidate admitted.  Depth 2 takes 10-15 % of the passes off the
-#: benchmark circuits (33 qubits: 28 -> 25, 30 qubits: 26 -> 23) for ~1 ms of host time per group.
-SEARCH_DEPTH = max(0, min(4, int(os.environ.get("QVM_B200_PLAN_SEARCH", "2"))))
+#: benchmark circuits (33 qubits: 28 -> 25, 30 qubits: 26 -> 23) for ~0.3 ms of host time per group; depth 4 another
+#: 3-5 % (33 qubits: 24) for ~3 ms per group -- worth it only when a pass costs tens of milliseconds.  None (the
+#: default, ``QVM_B200_PLAN_SEARCH`` unset) = by shard size: 4 from 2^32 amplitudes (~50 ms per pass), else 2.
+SEARCH_DEPTH = None if os.environ.get("QVM_B200_PLAN_SEARCH") is None else \
+    max(0, min(4, int(os.environ["QVM_B200_PLAN_SEARCH"])))
+DEEP_SEARCH_FROM = 32
+
+
+def search_depth_for(n_local):
+    if SEARCH_DEPTH is not None:
+        return SEARCH_DEPTH
+    return 4 if n_local >= DEEP_SEARCH_FROM else 2
 
 
 class Group(object):
@@ -271,7 +281,7 @@ def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_g
     deps = dependencies(ops)
     stream = _Stream(ops, deps)
     done = stream.done
-    depth = SEARCH_DEPTH if search_depth is None else search_depth
+    depth = search_depth_for(n_local) if search_depth is None else search_depth
     qubit_at = {p: q for q, p in enumerate(pos_of)}
     first = 0
     passes = 0
