@@ -63,7 +63,9 @@ def test_sharded_engine_on_one_gpu(world, exchange):
                 if rank == 0:
                     facts[case] = (eng.swaps, eng.fused_swaps, st["fused_push_launches"], st["push_launches"], jit_all)
                 psi = want
-                for q, r in ((n - 1, 0.3), (0, 0.8), (n // 2, 0.5)):
+                # (uniforms off the round values: a qubit left in an exact |+> has p0 = 0.5 +- 1 ulp, and r = 0.5 would
+                # make the outcome a matter of summation order)
+                for q, r in ((n - 1, 0.3), (0, 0.8), (n // 2, 0.4375)):
                     outcome, p0 = eng.measure(q, r if rank == 0 else -1.0)
                     o_want, p_want, psi = orc.fast_measure(psi, q, n, r)
                     assert outcome == o_want and abs(p0 - p_want) < 1e-12, (case, rank, q, r, outcome, o_want, p0, p_want)
