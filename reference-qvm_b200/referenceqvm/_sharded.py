@@ -781,7 +781,11 @@ class ShardedEngine(object):
         self.groups_launched += _planner.run_relabelled(
             batch, self.n_local, self.pos_of, launch, self.tile_bits, self.low_bits,
             defer_tail_below=self.DEFER_TAIL_BELOW if defer else 0, leftover=leftover, on_last=on_last,
-            last_tile_bits=min(self.PUSH_TILE_BITS, self.n_local - self.g - 2))      # (room for the victims outside the tile)
+            last_tile_bits=min(self.PUSH_TILE_BITS, self.n_local - self.g - 2),      # (room for the victims outside the tile)
+            # a batch whose last pass carries the exchange is planned with the shallow group search: the deep one
+            # (for shards of 2^32 amplitudes) leaves one- and two-round last passes, and those push at 520 GB/s
+            # instead of 710 (33 qubits on 2 GPUs: 1494 gate-apps/s against 1636, profiles/r3a_*)
+            search_depth=min(2, _planner.search_depth_for(self.n_local)) if on_last is not None else None)
         if e0 is not None:
             self.timing["batch"].append((e0, self.shard.record_event()))
         return leftover
