@@ -330,40 +330,43 @@ class Engine(object):
     AHEAD_COMPILE_S = float(os.environ.get("QVM_B200_AHEAD_COMPILE_S", "0"))
 
     def _compile_ahead(self, ops):
+        """Returns the planner's recorded group choices (``_planner.Choices``, ready to replay) when it walked."""
         if (self.n < self.AHEAD_MIN_QUBITS or len(ops) < self.AHEAD_MIN_OPS or not self.relabel
                 or not self.layout_is_identity() or getattr(self.state, "n_global", 0)):
-            return
+            return None
         signature = hash((self.n, self.tile_bits, self.low_bits,
                           tuple((o.kind, o.targets, o.ctrl_mask) for o in ops)))
         if signature in _walked_ahead:
-            return                   # this gate stream has been through here before: its kernels exist or are on their way
+            return None              # this gate stream has been through here before: its kernels exist or are on their way
         if len(_walked_ahead) > 4096:
             _walked_ahead.clear()
         _walked_ahead.add(signature)
+        choices = _planner.Choices()
         try:
             from referenceqvm import precompile
             if os.environ.get("QVM_B200_JIT", "1") != "1" or not nat.jit_cache_dir():
-                return
+                return None
             # the run starts right behind this walk; launches wait for a kernel that is on its way for as long as the
             # GPU has earlier passes queued (qvm_capi.cu, launch_rec).  Optionally (AHEAD_COMPILE_S) the kernels of the
             # first passes -- which go through the interpreter whatever happens -- are compiled last.
             nat.jit_defer(int(self.AHEAD_COMPILE_S / (2.0 ** self.n * 32.0 / 2.7e12)))
             try:
-                precompile.walk_pending(ops, self.n, self.tile_bits, self.low_bits, wait=False)
+                precompile.walk_pending(ops, self.n, self.tile_bits, self.low_bits, wait=False, choices=choices)
             finally:
                 nat.jit_defer(0)
         except Exception:            # an optimisation only: the run itself reports real errors
-            pass
+            return None
+        return choices.replay()
 
     def flush(self):
         self._merger.reset()
         if not self.pending:
             return
         ops, self.pending = self.pending, []
-        self._compile_ahead(ops)
+        choices = self._compile_ahead(ops)      # (the walk's group choices: the run need not search again)
         if self.relabel and self.n > self.tile_bits:
             self.groups_launched += _planner.run_relabelled(ops, self.n, self.pos_of, self._launch_relabelled,
-                                                            self.tile_bits, self.low_bits)
+                                                            self.tile_bits, self.low_bits, choices=choices)
             return
         if not self.layout_is_identity():
             ops = [o.remapped(self.pos_of) for o in ops]

@@ -173,6 +173,34 @@ def summarize(groups):
 # launch is asked to bring the qubits both groups share to the low positions, and the next group's tile
 # follows from the layout the library reports back.
 
+class Choices(object):
+    """The group choices of one ``run_relabelled`` call, in the order they were made.  A walk of the planner without
+    a device (``precompile.walk_pending``, run by ``Engine.flush`` ahead of a long first flush so that NVRTC can start)
+    records them; the real run right behind it replays them instead of searching again -- the choices depend only on
+    the ops and on the layouts the launches report back, and those are the same in both walks."""
+    __slots__ = ("items", "pos", "recording")
+
+    def __init__(self):
+        self.items, self.pos, self.recording = [], 0, True
+
+    def replay(self):
+        self.pos, self.recording = 0, False
+        return self
+
+    def pick(self, compute, valid):
+        if self.recording:
+            out = compute()
+            self.items.append(out)
+            return out
+        if self.pos < len(self.items):
+            tile, chosen = self.items[self.pos]
+            self.pos += 1
+            if valid(tile, chosen):
+                return set(tile), list(chosen)
+            self.pos = len(self.items)   # the two walks diverged (they should not): forget the recording
+        return compute()                 # (or the recording walk stopped early: carry on searching)
+
+
 class _Stream(object):
     """The op stream of one ``run_relabelled`` call in the CSR form ``qvm_plan_choose_group`` reads."""
 
@@ -242,7 +270,7 @@ def _choose_group(ops, deps, done, first, k, max_new, is_old, seed_tile, max_gro
 
 
 def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_group_ops=MAX_GROUP_OPS,
-                   defer_tail_below=0, leftover=None, on_last=None, last_tile_bits=0, search_depth=None):
+                   defer_tail_below=0, leftover=None, on_last=None, last_tile_bits=0, search_depth=None, choices=None):
     """Run ``ops`` (ClassifiedOps on LOGICAL qubits; every dense target currently on a local position)
     as fused groups with in-tile relabelling.  ``pos_of`` (logical -> physical, mutated in place) is the
     layout; ``launch(tile_positions, physical_ops, bring_low_positions)`` runs one pass and returns the
@@ -256,6 +284,9 @@ def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_g
     ``on_last(leftover_indices, tile_positions)``: called right before the LAST launch of the call (the
     thin tail, if any, already set aside); what it returns is handed to that launch as a fourth argument
     -- the sharded engine's fused exchange: the last pass stores straight into the peers' shards.
+
+    ``choices``: a ``Choices`` object -- recording: every group choice is appended to it; replaying
+    (``Choices.replay()``): the recorded choices are used instead of searching.
 
     ``last_tile_bits`` (with ``on_last``): a pass that carries an exchange is bound by NVLink, not by HBM or the
     FP64 pipe, so it may as well do more gate work: as soon as everything that is left fits ONE tile of
@@ -282,6 +313,24 @@ def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_g
     stream = _Stream(ops, deps)
     done = stream.done
     depth = search_depth_for(n_local) if search_depth is None else search_depth
+
+    def legal(tile, chosen, k_, max_new, old, seed):
+        """A replayed choice must be something the search could have returned here."""
+        if not set(seed) <= tile or len(tile) > k_ or sum(1 for q in tile if q not in old) > max_new:
+            return False
+        inside = set()
+        for i in chosen:
+            if done[i] or any(not (done[d] or d in inside) for d in deps[i]):
+                return False
+            if ops[i].kind == OP_DENSE and not set(ops[i].targets) <= tile:
+                return False
+            inside.add(i)
+        return True
+
+    def pick(compute, k_, max_new, old, seed):
+        if choices is None:
+            return compute()
+        return choices.pick(compute, lambda tile, chosen: legal(tile, chosen, k_, max_new, old, seed))
     qubit_at = {p: q for q, p in enumerate(pos_of)}
     first = 0
     passes = 0
@@ -293,7 +342,7 @@ def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_g
     def fixed_choice():
         """The layout as it is: the qubits on the low positions are in, k - low more may join."""
         lq = set(low_qubits())
-        return stream.choose(first, k, k - low, lq, lq, max_group_ops, depth)
+        return pick(lambda: stream.choose(first, k, k - low, lq, lq, max_group_ops, depth), k, k - low, lq, lq)
 
     k_normal = k
     big = min(int(last_tile_bits or 0), n_local - 1) if on_last is not None else 0
@@ -304,7 +353,7 @@ def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_g
         k = k_normal
         if big > k_normal:
             lq = set(low_qubits())
-            big_tile, big_ops = stream.choose(first, big, big - low, lq, lq, max_group_ops, 0)
+            big_tile, big_ops = pick(lambda: stream.choose(first, big, big - low, lq, lq, max_group_ops, 0), big, big - low, lq, lq)
             if len(big_ops) == n - n_done and len(big_ops) > len(cur_ops):
                 cur_tile, cur_ops, k = big_tile, big_ops, big       # the rest of the batch in one (larger) tile
         # physical tile: the low positions, the group's qubits, then the lowest unused positions
@@ -334,7 +383,8 @@ def run_relabelled(ops, n_local, pos_of, launch, tile_bits=11, low_bits=4, max_g
         contiguous = all(tile_positions[j] == j for j in range(low))
         n_done += len(cur_ops)
         if first < n and contiguous:
-            nxt_tile, nxt_ops = stream.choose(first, k, k - low, tile_qubits, (), max_group_ops, depth)
+            nxt_tile, nxt_ops = pick(lambda: stream.choose(first, k, k - low, tile_qubits, (), max_group_ops, depth),
+                                     k, k - low, tile_qubits, ())
             if (on_last is not None and leftover is not None and len(nxt_ops) == n - n_done
                     and len(nxt_ops) < defer_tail_below):
                 # everything that is left is a thin tail: it will be deferred, so THIS launch is the last one

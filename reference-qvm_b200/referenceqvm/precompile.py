@@ -117,16 +117,17 @@ class _DryShard(object):
         return {}
 
 
-def walk_pending(pending, n_qubits, tile_bits, low_bits, wait=True):
+def walk_pending(pending, n_qubits, tile_bits, low_bits, wait=True, choices=None):
     """Single-GPU planner walk over an already merged op list (what ``Engine.flush`` is about to run): every group
     goes to ``qvm_spec_precompile``; with ``wait=False`` the compilations are left running on the library's
-    background threads (``Engine.flush`` calls this ahead of a long run on a large state, see there)."""
+    background threads (``Engine.flush`` calls this ahead of a long run on a large state, see there).  ``choices``
+    (a recording ``_planner.Choices``) receives the planner's group choices for the run to replay."""
     shard = _DryShard(n_qubits, _sharded.ShardContext(_DryComm(1), 0))
     pos_of = list(range(n_qubits))
     if _engine._RELABEL and n_qubits > tile_bits:
         _planner.run_relabelled(pending, n_qubits, pos_of,
                                 lambda tile, gops, bring: shard.apply_group(tile, gops, bring if bring else [], low_bits),
-                                tile_bits, low_bits)
+                                tile_bits, low_bits, choices=choices)
     else:
         shard.apply_groups(pending, tile_bits, low_bits)
     if wait:

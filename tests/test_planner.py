@@ -127,7 +127,7 @@ def test_diagonal_merger_is_exact_up_to_rounding():
 
 
 # ---- the relabelling planner against launchers that do less (or nothing) of what it asks -------------------
-def _run_relabelled_on_model(ops, n, tile_bits, low_bits, honour):
+def _run_relabelled_on_model(ops, n, tile_bits, low_bits, honour, choices=None, log=None):
     """Drive _planner.run_relabelled with a numpy launcher; ``honour(bring)`` picks which requests are granted."""
     import numpy as np
     from _model import apply_op, random_state
@@ -143,6 +143,8 @@ def _run_relabelled_on_model(ops, n, tile_bits, low_bits, honour):
             assert op.kind != 1 or all(t in tile for t in op.targets), "dense target outside the tile"
             box["psi"] = apply_op(box["psi"], op, n)
         box["launches"] += 1
+        if log is not None:
+            log.append((tuple(tile), len(phys_ops), tuple(bring or ())))
         new_pos = list(tile)
         granted = honour(list(bring or []))
         incoming = [p for p in granted if p >= low_bits]
@@ -155,7 +157,7 @@ def _run_relabelled_on_model(ops, n, tile_bits, low_bits, honour):
         box["psi"] = box["psi"][idx]
         return new_pos
 
-    passes = _planner.run_relabelled(ops, n, pos_of, launch, tile_bits, low_bits)
+    passes = _planner.run_relabelled(ops, n, pos_of, launch, tile_bits, low_bits, choices=choices)
     logical = np.arange(1 << n, dtype=np.int64)
     phys = np.zeros_like(logical)
     for q, p in enumerate(pos_of):
@@ -259,3 +261,36 @@ def test_group_search_takes_passes_off_the_benchmark_circuit():
         counts[depth] = _planner.run_relabelled(ops, 33, pos_of, launch, 11, 4, search_depth=depth)
         assert sorted(pos_of) == list(range(33))
     assert counts[2] <= counts[0] - 2, counts
+
+
+def test_recorded_group_choices_replay_without_searching_and_survive_tampering(monkeypatch):
+    """_planner.Choices: the walk ahead of a run records the planner's choices; the run replays them (no search, the
+    same launches); a recording that does not fit the run is dropped instead of trusted."""
+    n = 14
+    ops = _stream_of(n, 14, 8)
+    grant_all = lambda b: b
+    rec = _planner.Choices()
+    first_log, replay_log, tampered_log = [], [], []
+    err, passes, pos_a = _run_relabelled_on_model(ops, n, 9, 4, grant_all, choices=rec, log=first_log)
+    assert err < 1e-12 and len(rec.items) >= passes
+    calls = {"n": 0}
+    orig = _planner._Stream.choose
+
+    def counting(self, *args):
+        calls["n"] += 1
+        return orig(self, *args)
+
+    monkeypatch.setattr(_planner._Stream, "choose", counting)
+    err, passes_b, pos_b = _run_relabelled_on_model(ops, n, 9, 4, grant_all, choices=rec.replay(), log=replay_log)
+    assert err < 1e-12 and calls["n"] == 0 and replay_log == first_log and pos_b == pos_a and passes_b == passes
+    # a recording of ANOTHER stream: its choices are illegal here, the run searches for itself and stays right
+    other = _planner.Choices()
+    _run_relabelled_on_model(_stream_of(n, 14, 9), n, 9, 4, grant_all, choices=other)
+    calls["n"] = 0
+    err, _, _ = _run_relabelled_on_model(ops, n, 9, 4, grant_all, choices=other.replay(), log=tampered_log)
+    assert err < 1e-12 and calls["n"] > 0
+    # a library that grants less than the walk assumed (layouts differ from the recording): still right
+    rec2 = _planner.Choices()
+    _run_relabelled_on_model(ops, n, 9, 4, grant_all, choices=rec2)
+    err, _, _ = _run_relabelled_on_model(ops, n, 9, 4, lambda b: b[:1], choices=rec2.replay())
+    assert err < 1e-12
