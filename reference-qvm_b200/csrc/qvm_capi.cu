@@ -1065,7 +1065,7 @@ int qvm_spec_precompile(int n_local, int n_global, uint64_t shard_index, int n_t
     for (int j = 0; j < n_tile; ++j) new_pos[j] = tile_bits[erc == ENC_OK ? g.sigma[j] : j];
     if (erc != ENC_OK || (g.cold.empty() && !g.relabelled) || g.need_full || !generate_spec(g, ss)) return 1;
     std::string err;      // compiled on the background threads: qvm_jit_wait() returns when all cubins are on disk
-    const bool foreign = t_share.stride > 1 && (t_share.index++ % t_share.stride) != t_share.offset;
+    const bool foreign = t_share.stride > 1 && (int)(t_share.index++ % (uint64_t)t_share.stride) != t_share.offset;
     if (!SpecCache::instance().precompile_async(ss.src, &err, false, foreign))
         return fail(QVM_ERR_UNSUPPORTED, "ahead-of-time compile failed: %.300s", err.c_str());
     return QVM_OK;
