@@ -277,6 +277,25 @@ def test_relabelled_random_circuit(n, depth, seed, tile, low):
     assert passes <= fixed and moved > 0, (passes, fixed, moved)
 
 
+@pytest.mark.parametrize("n,depth,seed,tile,low", [(14, 30, 11, 11, 4), (13, 50, 15, 11, 4), (15, 24, 17, 11, 5)])
+def test_deep_circuits_with_full_groups(n, depth, seed, tile, low):
+    """Deep circuits on few qubits: every group is full (60-90 ops), so the planner's group search and the encoder's
+    round search (bits kept out of a round so that the group finishes in fewer rounds) both have choices to make."""
+    spec = orc.random_circuit_spec(n, depth, seed)
+    ops = []
+    for op in compile_spec(spec):
+        ops += list(_engine.expand_op(op))
+    psi0 = random_state(n, seed)
+    want = psi0
+    for name, params, qubits in spec:
+        m = G.gate_matrix[name]
+        want = orc.fast_apply_gate(want, np.asarray(m(*params) if params else m, dtype=complex), qubits, n)
+    got, pos_of, passes, _ = run_emulated_relabelled(psi0, ops, n, tile, low)
+    assert sorted(pos_of) == list(range(n))
+    assert np.max(np.abs(logical_view(got, pos_of) - want)) < TOL
+    assert passes <= len(_planner.plan(ops, n, tile, low))
+
+
 def test_relabel_only_pass_and_partial_requests():
     """A pass without ops still relabels; requests for qubits already low, or more requests than low
     positions, are honoured as far as possible and reported truthfully."""
