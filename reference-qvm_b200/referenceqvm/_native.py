@@ -293,6 +293,21 @@ def spec_precompile(n_local, tile_bits, ops, n_global=0, shard_index=0, bring_lo
     return code, new_pos.tolist()
 
 
+def group_probe(n_local, tile_bits, ops, n_global=0, shard_index=0, bring_low=(), n_low=0):
+    """``qvm_group_probe`` (no device): (new_pos, {"rounds", "ops", "dirty_rounds", "specialisable"}) for one group."""
+    ops = [o for o in ops if o.kind != OP_NOP]
+    arr, pool, total = marshal_ops(ops)
+    tb = np.ascontiguousarray(sorted(tile_bits), dtype=np.int32)
+    bl = np.ascontiguousarray(list(bring_low), dtype=np.int32)
+    new_pos = np.empty(tb.size, dtype=np.int32)
+    info = np.zeros(4, dtype=np.int32)
+    check(lib().qvm_group_probe(n_local, n_global, shard_index, tb.size, tb.ctypes.data, len(ops), C.cast(arr, _P),
+                                pool.ctypes.data, total, n_low, bl.size, bl.ctypes.data, new_pos.ctypes.data,
+                                info.ctypes.data))
+    return new_pos.tolist(), {"rounds": int(info[0]), "ops": int(info[1]), "dirty_rounds": int(info[2]),
+                              "specialisable": bool(info[3])}
+
+
 def spec_compile_check(n_local, tile_bits, ops, n_global=0, shard_index=0, bring_low=(), n_low=0):
     """``qvm_spec_compile_check``: 0 compiled, 1 left to the interpreter; raises with the NVRTC log."""
     ops = [o for o in ops if o.kind != OP_NOP]

@@ -294,3 +294,52 @@ def test_recorded_group_choices_replay_without_searching_and_survive_tampering(m
     _run_relabelled_on_model(ops, n, 9, 4, grant_all, choices=rec2)
     err, _, _ = _run_relabelled_on_model(ops, n, 9, 4, lambda b: b[:1], choices=rec2.replay())
     assert err < 1e-12
+
+
+PROBE_SCRIPT = r"""
+import json, os, sys
+sys.path[:0] = [%(repo)r, os.path.join(%(repo)r, "reference-qvm_b200")]
+import numpy as np
+import referenceqvm
+from referenceqvm import _engine, _native as nat, _planner
+from referenceqvm.gates import gate_matrix
+from workloads import random_circuit_spec
+n = 33
+pending, merger = [], _engine.DiagonalMerger()
+for name, params, qubits in random_circuit_spec(n, 40, 1234):
+    m = gate_matrix[name]
+    op = _engine.compile_gate(np.asarray(m(*params) if params else m), list(qubits))
+    if op.kind != nat.OP_NOP:
+        for piece in _engine.expand_op(op):
+            if not merger.absorb(pending, piece):
+                pending.append(piece)
+rounds = []
+def launch(tile, gops, bring, push=None):
+    new_pos, info = nat.group_probe(n, tile, gops, bring_low=bring or (), n_low=4)
+    rounds.append(info["rounds"])
+    assert info["specialisable"]
+    return new_pos
+passes = _planner.run_relabelled(pending, n, list(range(n)), launch, 11, 4)
+print(json.dumps({"passes": passes, "rounds": sum(rounds), "max_rounds": max(rounds)}))
+"""
+
+
+def test_searches_on_the_benchmark_circuit_passes_and_rounds():
+    """The numbers DESIGN.md 4.3 quotes for the 33-qubit depth-40 circuit, through the real planner and encoder
+    (qvm_group_probe, no device): first fit 28 passes / 104 rounds; group search + round search (depth by shard
+    size: 4) no more than 24 passes and 90 rounds."""
+    import json
+    import os
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for name, env in (("first_fit", {"QVM_B200_PLAN_SEARCH": "0", "QVM_B200_ROUND_SEARCH": "0"}), ("search", {})):
+        e = {k: v for k, v in os.environ.items() if k not in ("QVM_B200_PLAN_SEARCH", "QVM_B200_ROUND_SEARCH")}
+        e.update(env)
+        proc = subprocess.run([sys.executable, "-c", PROBE_SCRIPT % {"repo": repo}], env=e, stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True, timeout=600)
+        assert proc.returncode == 0, proc.stderr[-2000:]
+        out[name] = json.loads([ln for ln in proc.stdout.splitlines() if ln.startswith("{")][-1])
+    assert out["first_fit"]["passes"] == 28 and out["first_fit"]["rounds"] == 104, out
+    assert out["search"]["passes"] <= 24 and out["search"]["rounds"] <= 90, out
